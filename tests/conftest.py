@@ -1,0 +1,28 @@
+"""pytest configuration: registers the ``gpu`` marker and makes the repo root importable.
+
+``-m "not gpu"``: oracle vs golden fixtures, host logic, C-ABI symbol checks (no GPU needed).
+``-m gpu``      : parity of the sm_100a kernels (through the C-ABI) against the oracle / fixtures.
+"""
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200, sm_100a)")
+
+
+def pytest_collection_modifyitems(config, items):
+    import torch
+
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device in this process")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
