@@ -1,0 +1,237 @@
+// C ABI of libhv_swin.so (declared in include/hv_swin.h): argument validation, dispatch, error text.
+#include <stdarg.h>
+#include <string.h>
+
+#include "hv_common.cuh"
+
+namespace hv {
+
+// ---- kernels implemented in the other translation units ---------------------------------
+int wattn_generic_fwd(const Geom& g, int dtype, const void* qkv, const float* bias_table, const float* tau,
+                      const float* mask, int mask_windows, void* out, float* lse, cudaStream_t st);
+int wattn_generic_bwd(const Geom& g, int dtype, const void* qkv, const void* out, const void* dout, const float* lse,
+                      const float* bias_table, const float* tau, const float* mask, int mask_windows, void* dqkv,
+                      float* dbias_table, float* dtau, cudaStream_t st);
+bool wattn_mma64_supported(const Geom& g, int dtype);
+size_t wattn_mma64_bwd_workspace_bytes(const Geom& g);
+int wattn_mma64_fwd(const Geom& g, const void* qkv, const float* bias_table, const float* tau, const float* mask,
+                    int mask_windows, void* out, float* lse, cudaStream_t st);
+int wattn_mma64_bwd(const Geom& g, const void* qkv, const void* out, const void* dout, const float* lse,
+                    const float* bias_table, const float* tau, const float* mask, int mask_windows, void* dqkv,
+                    float* dbias_table, float* dtau, void* workspace, size_t workspace_bytes, cudaStream_t st);
+size_t ln_residual_bwd_workspace_bytes(int64_t rows, int C);
+int ln_residual_fwd(const void* y, const void* shortcut, const float* gamma, const float* beta, const float* keep_scale,
+                    void* out, float* mean, float* rstd, int64_t rows, int C, int64_t rows_per_sample, float eps,
+                    int y_dtype, int res_dtype, cudaStream_t st);
+int ln_residual_bwd(const void* dout, const void* y, const float* gamma, const float* mean, const float* rstd,
+                    const float* keep_scale, void* dy, float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
+                    int64_t rows, int C, int64_t rows_per_sample, int y_dtype, int res_dtype, cudaStream_t st);
+int patch_merge_gather_fwd(const void* x, void* out, int B, int H, int W, int C, int dtype, cudaStream_t st);
+int patch_merge_gather_bwd(const void* dout, void* dx, int B, int H, int W, int C, int dtype, cudaStream_t st);
+
+// ---- error text / device info --------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static int g_arch_state[64];  // 0 unknown, 1 ok, 2 bad
+static int g_sm_count[64];
+
+static int query_device(int& dev) {
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+    set_error("no current CUDA device (libhv_swin has no CPU fallback)");
+    return HV_ERR_CUDA;
+  }
+  if (g_arch_state[dev] == 0) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) {
+      set_error("cudaGetDeviceProperties failed");
+      return HV_ERR_CUDA;
+    }
+    g_sm_count[dev] = p.multiProcessorCount;
+    g_arch_state[dev] = (p.major == 10 && p.minor == 0) ? 1 : 2;
+  }
+  return HV_OK;
+}
+
+int check_device_arch() {
+  int dev;
+  int rc = query_device(dev);
+  if (rc) return rc;
+  if (g_arch_state[dev] != 1) {
+    set_error("libhv_swin is built for sm_100a (B200) only; current device is not compute capability 10.0");
+    return HV_ERR_ARCH;
+  }
+  return HV_OK;
+}
+
+int num_sms() {
+  int dev;
+  if (query_device(dev)) return 148;
+  return g_sm_count[dev] > 0 ? g_sm_count[dev] : 148;
+}
+
+static int make_checked_geom(int B, int H, int W, int C, int heads, int ws, int shift, Geom& g) {
+  if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || heads <= 0 || ws <= 0)
+    HV_FAIL(HV_ERR_SHAPE, "window_attn: non-positive size (B=%d H=%d W=%d C=%d heads=%d ws=%d)", B, H, W, C, heads, ws);
+  if (C % heads != 0) HV_FAIL(HV_ERR_SHAPE, "window_attn: C=%d not divisible by heads=%d", C, heads);
+  if (H % ws != 0 || W % ws != 0) HV_FAIL(HV_ERR_SHAPE, "window_attn: resolution %dx%d not divisible by window %d", H, W, ws);
+  if (shift < 0 || shift >= ws) HV_FAIL(HV_ERR_SHAPE, "shift_size must in 0-window_size (shift=%d ws=%d)", shift, ws);
+  g = make_geom(B, H, W, C, heads, ws, shift);
+  return HV_OK;
+}
+
+}  // namespace hv
+
+using namespace hv;
+
+extern "C" {
+
+int hv_abi_version(void) { return HV_ABI_VERSION; }
+const char* hv_last_error(void) { return g_err; }
+int hv_compiled_arch(void) { return 100; }
+
+int hv_window_attn_kernel_kind(int C, int heads, int ws, int dtype) {
+  if (heads <= 0 || C % heads) return 0;
+  Geom g = make_geom(1, ws, ws, C, heads, ws, 0);
+  return wattn_mma64_supported(g, dtype) ? 1 : 0;
+}
+
+int hv_relative_position_index(int ws, int64_t* out) {
+  if (!out) HV_FAIL(HV_ERR_NULL, "hv_relative_position_index: out is NULL");
+  if (ws <= 0) HV_FAIL(HV_ERR_SHAPE, "ws=%d", ws);
+  const int N = ws * ws;
+  for (int i = 0; i < N; ++i)
+    for (int j = 0; j < N; ++j) out[(size_t)i * N + j] = rel_pos_index(ws, i, j);
+  return HV_OK;
+}
+
+int hv_shift_window_mask(int H, int W, int ws, int shift, float* out) {
+  if (!out) HV_FAIL(HV_ERR_NULL, "hv_shift_window_mask: out is NULL");
+  Geom g;
+  int rc = make_checked_geom(1, H, W, ws, 1, ws, shift, g);
+  if (rc) return rc;
+  if (shift == 0) HV_FAIL(HV_ERR_SHAPE, "hv_shift_window_mask: shift must be > 0 (the reference has attn_mask=None otherwise)");
+  const int N = g.N;
+  for (int win = 0; win < g.nW; ++win)
+    for (int i = 0; i < N; ++i) {
+      const int ri = window_slot_region(g, win, i);
+      for (int j = 0; j < N; ++j)
+        out[((size_t)win * N + i) * N + j] = (window_slot_region(g, win, j) != ri) ? -100.0f : 0.0f;
+    }
+  return HV_OK;
+}
+
+int hv_window_token_index(int B, int H, int W, int ws, int shift, int64_t* out) {
+  if (!out) HV_FAIL(HV_ERR_NULL, "hv_window_token_index: out is NULL");
+  Geom g;
+  int rc = make_checked_geom(B, H, W, ws, 1, ws, shift, g);
+  if (rc) return rc;
+  for (int b = 0; b < B; ++b)
+    for (int win = 0; win < g.nW; ++win)
+      for (int s = 0; s < g.N; ++s) out[((size_t)b * g.nW + win) * g.N + s] = window_slot_to_token(g, b, win, s);
+  return HV_OK;
+}
+
+int hv_merge_token_index(int B, int H, int W, int64_t* out) {
+  if (!out) HV_FAIL(HV_ERR_NULL, "hv_merge_token_index: out is NULL");
+  if (B <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1)) HV_FAIL(HV_ERR_SHAPE, "x size (%d*%d) are not even.", H, W);
+  size_t o = 0;
+  for (int b = 0; b < B; ++b)
+    for (int i = 0; i < H / 2; ++i)
+      for (int j = 0; j < W / 2; ++j)
+        for (int m = 0; m < 4; ++m) out[o++] = merge_src_token(H, W, b, i, j, m);
+  return HV_OK;
+}
+
+static int attn_common_checks(const char* what, int dtype, const float* mask, int mask_windows, const Geom& g) {
+  if (dtype != HV_F32 && dtype != HV_BF16) HV_FAIL(HV_ERR_DTYPE, "%s: dtype %d", what, dtype);
+  if (mask != nullptr) {
+    if (mask_windows <= 0 || (g.B * g.nW) % mask_windows != 0)
+      HV_FAIL(HV_ERR_SHAPE, "%s: %d windows not divisible by mask_windows=%d", what, g.B * g.nW, mask_windows);
+  }
+  return check_device_arch();
+}
+
+int hv_window_attn_fwd(const void* qkv, const float* bias_table, const float* tau, const float* mask, int mask_windows,
+                       void* out, float* lse, int B, int H, int W, int C, int heads, int ws, int shift, int dtype,
+                       void* stream) {
+  if (!qkv || !bias_table || !tau || !out || !lse) HV_FAIL(HV_ERR_NULL, "hv_window_attn_fwd: NULL argument");
+  Geom g;
+  int rc = make_checked_geom(B, H, W, C, heads, ws, shift, g);
+  if (rc) return rc;
+  rc = attn_common_checks("hv_window_attn_fwd", dtype, mask, mask_windows, g);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (wattn_mma64_supported(g, dtype)) return wattn_mma64_fwd(g, qkv, bias_table, tau, mask, mask_windows, out, lse, st);
+  return wattn_generic_fwd(g, dtype, qkv, bias_table, tau, mask, mask_windows, out, lse, st);
+}
+
+size_t hv_window_attn_bwd_workspace_bytes(int B, int H, int W, int C, int heads, int ws, int dtype) {
+  if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || heads <= 0 || ws <= 0 || C % heads || H % ws || W % ws) return 0;
+  Geom g = make_geom(B, H, W, C, heads, ws, 0);
+  if (wattn_mma64_supported(g, dtype)) return wattn_mma64_bwd_workspace_bytes(g);
+  return 16;  // the generic kernel reduces with atomics
+}
+
+int hv_window_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const float* bias_table,
+                       const float* tau, const float* mask, int mask_windows, void* dqkv, float* dbias_table, float* dtau,
+                       void* workspace, size_t workspace_bytes, int B, int H, int W, int C, int heads, int ws, int shift,
+                       int dtype, void* stream) {
+  if (!qkv || !out || !dout || !lse || !bias_table || !tau || !dqkv || !dbias_table || !dtau)
+    HV_FAIL(HV_ERR_NULL, "hv_window_attn_bwd: NULL argument");
+  Geom g;
+  int rc = make_checked_geom(B, H, W, C, heads, ws, shift, g);
+  if (rc) return rc;
+  rc = attn_common_checks("hv_window_attn_bwd", dtype, mask, mask_windows, g);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (wattn_mma64_supported(g, dtype))
+    return wattn_mma64_bwd(g, qkv, out, dout, lse, bias_table, tau, mask, mask_windows, dqkv, dbias_table, dtau, workspace,
+                           workspace_bytes, st);
+  return wattn_generic_bwd(g, dtype, qkv, out, dout, lse, bias_table, tau, mask, mask_windows, dqkv, dbias_table, dtau, st);
+}
+
+int hv_ln_residual_fwd(const void* y, const void* shortcut, const float* gamma, const float* beta, const float* keep_scale,
+                       void* out, float* mean, float* rstd, int64_t rows, int C, int64_t rows_per_sample, float eps,
+                       int y_dtype, int res_dtype, void* stream) {
+  if (!y || !gamma || !beta || !out || !mean || !rstd) HV_FAIL(HV_ERR_NULL, "hv_ln_residual_fwd: NULL argument");
+  int rc = check_device_arch();
+  if (rc) return rc;
+  return ln_residual_fwd(y, shortcut, gamma, beta, keep_scale, out, mean, rstd, rows, C, rows_per_sample, eps, y_dtype,
+                         res_dtype, static_cast<cudaStream_t>(stream));
+}
+
+size_t hv_ln_residual_bwd_workspace_bytes(int64_t rows, int C) { return ln_residual_bwd_workspace_bytes(rows, C); }
+
+int hv_ln_residual_bwd(const void* dout, const void* y, const float* gamma, const float* mean, const float* rstd,
+                       const float* keep_scale, void* dy, float* dgamma, float* dbeta, void* workspace,
+                       size_t workspace_bytes, int64_t rows, int C, int64_t rows_per_sample, int y_dtype, int res_dtype,
+                       void* stream) {
+  if (!dout || !y || !gamma || !mean || !rstd || !dy || !dgamma || !dbeta) HV_FAIL(HV_ERR_NULL, "hv_ln_residual_bwd: NULL argument");
+  int rc = check_device_arch();
+  if (rc) return rc;
+  return ln_residual_bwd(dout, y, gamma, mean, rstd, keep_scale, dy, dgamma, dbeta, workspace, workspace_bytes, rows, C,
+                         rows_per_sample, y_dtype, res_dtype, static_cast<cudaStream_t>(stream));
+}
+
+int hv_patch_merge_gather_fwd(const void* x, void* out, int B, int H, int W, int C, int dtype, void* stream) {
+  if (!x || !out) HV_FAIL(HV_ERR_NULL, "hv_patch_merge_gather_fwd: NULL argument");
+  int rc = check_device_arch();
+  if (rc) return rc;
+  return patch_merge_gather_fwd(x, out, B, H, W, C, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int hv_patch_merge_gather_bwd(const void* dout, void* dx, int B, int H, int W, int C, int dtype, void* stream) {
+  if (!dout || !dx) HV_FAIL(HV_ERR_NULL, "hv_patch_merge_gather_bwd: NULL argument");
+  int rc = check_device_arch();
+  if (rc) return rc;
+  return patch_merge_gather_bwd(dout, dx, B, H, W, C, dtype, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

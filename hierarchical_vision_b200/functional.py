@@ -1,0 +1,216 @@
+"""torch.autograd.Function wrappers over the C ABI (include/hv_swin.h).
+
+PyTorch is plumbing here: it owns device memory, streams and the autograd graph; all the
+arithmetic of these ops happens in libhv_swin.so.  Tensors are passed as raw device pointers
+plus sizes; nothing in the signatures of the library is a torch type.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import HV_BF16, HV_F32, check
+
+_P = _lib.c_void_p
+
+
+def _code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return HV_F32
+    if t.dtype == torch.bfloat16:
+        return HV_BF16
+    raise RuntimeError(f"hierarchical_vision_b200 kernels take float32 or bfloat16 activations, got {t.dtype}")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return _P(t.data_ptr()) if t is not None else _P(0)
+
+
+def _need_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{what}: tensor is on {t.device}; this package only runs on CUDA (sm_100a), "
+                           "there is no CPU path")
+
+
+def _stream(device) -> _P:
+    return _P(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.float32).contiguous()
+
+
+# Optional per-launch instrumentation used by bench.py: when set to a list, every attention
+# kernel launch appends (tag, start_event, end_event, windows).
+PROFILE_EVENTS = None
+LAUNCH_COUNT = 0
+
+
+def _timed(tag, windows, stream_device, fn):
+    global LAUNCH_COUNT
+    LAUNCH_COUNT += 1
+    if PROFILE_EVENTS is None:
+        return fn()
+    s = torch.cuda.current_stream(stream_device)
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(s)
+    r = fn()
+    e1.record(s)
+    PROFILE_EVENTS.append((tag, e0, e1, windows))
+    return r
+
+
+class _WindowAttention(torch.autograd.Function):
+    """out = fused shifted-window scaled-cosine attention(qkv); see hv_window_attn_fwd."""
+
+    @staticmethod
+    def forward(ctx, qkv, bias_table, tau, mask, B, H, W, C, heads, ws, shift):
+        _need_cuda(qkv, "window_attention")
+        lib = _lib.load()
+        qkv = qkv.contiguous()
+        bias_table = _f32c(bias_table)
+        tau = _f32c(tau)
+        mask_windows = 0
+        if mask is not None:
+            mask = _f32c(mask)
+            mask_windows = mask.shape[0]
+        N = ws * ws
+        nW = (H // ws) * (W // ws)
+        out = torch.empty((B, H * W, C), dtype=qkv.dtype, device=qkv.device)
+        lse = torch.empty((B * nW, heads, N), dtype=torch.float32, device=qkv.device)
+        with torch.cuda.device(qkv.device):
+            rc = _timed("attn_fwd", B * nW, qkv.device, lambda: lib.hv_window_attn_fwd(
+                _ptr(qkv), _ptr(bias_table), _ptr(tau), _ptr(mask), mask_windows, _ptr(out), _ptr(lse),
+                B, H, W, C, heads, ws, shift, _code(qkv), _stream(qkv.device)))
+        check(rc, "hv_window_attn_fwd")
+        ctx.save_for_backward(qkv, out, lse, bias_table, tau, mask)
+        ctx.geom = (B, H, W, C, heads, ws, shift, mask_windows)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, out, lse, bias_table, tau, mask = ctx.saved_tensors
+        B, H, W, C, heads, ws, shift, mask_windows = ctx.geom
+        lib = _lib.load()
+        dout = dout.contiguous()
+        if dout.dtype != qkv.dtype:
+            dout = dout.to(qkv.dtype)
+        dqkv = torch.empty_like(qkv)
+        dbias = torch.empty_like(bias_table)
+        dtau = torch.empty_like(tau)
+        code = _code(qkv)
+        with torch.cuda.device(qkv.device):
+            nbytes = lib.hv_window_attn_bwd_workspace_bytes(B, H, W, C, heads, ws, code)
+            workspace = torch.empty((max(int(nbytes), 16),), dtype=torch.uint8, device=qkv.device)
+            rc = _timed("attn_bwd", B * (H // ws) * (W // ws), qkv.device, lambda: lib.hv_window_attn_bwd(
+                _ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(bias_table), _ptr(tau), _ptr(mask), mask_windows,
+                _ptr(dqkv), _ptr(dbias), _ptr(dtau), _ptr(workspace), workspace.numel(),
+                B, H, W, C, heads, ws, shift, code, _stream(qkv.device)))
+        check(rc, "hv_window_attn_bwd")
+        return dqkv, dbias, dtau, None, None, None, None, None, None, None, None
+
+
+def window_attention(qkv: torch.Tensor, bias_table: torch.Tensor, tau: torch.Tensor, *, B: int, H: int, W: int,
+                     C: int, heads: int, ws: int, shift: int, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """qkv (B, H*W, 3C) in image token order -> (B, H*W, C).  ``bias_table`` is
+    16*sigmoid(cpb_mlp(coords)) of shape ((2ws-1)^2, heads); ``tau`` = exp(clamped logit_scale), (heads,).
+    ``mask`` None: shifted-window mask generated in-kernel from the geometry; else (nW, N, N) added as given."""
+    return _WindowAttention.apply(qkv, bias_table, tau.reshape(-1), mask, B, H, W, C, heads, ws, shift)
+
+
+class _LnResidual(torch.autograd.Function):
+    """out = shortcut + keep_scale[sample] * LayerNorm(y) (shortcut / keep_scale optional)."""
+
+    @staticmethod
+    def forward(ctx, y, shortcut, gamma, beta, keep_scale, rows_per_sample, eps):
+        _need_cuda(y, "ln_residual")
+        lib = _lib.load()
+        y = y.contiguous()
+        C = y.shape[-1]
+        rows = y.numel() // C
+        gamma32, beta32 = _f32c(gamma), _f32c(beta)
+        if shortcut is not None:
+            shortcut = shortcut.contiguous()
+            res_dtype = shortcut.dtype
+        else:
+            res_dtype = y.dtype
+        if keep_scale is not None:
+            keep_scale = _f32c(keep_scale)
+        out = torch.empty(y.shape, dtype=res_dtype, device=y.device)
+        mean = torch.empty((rows,), dtype=torch.float32, device=y.device)
+        rstd = torch.empty((rows,), dtype=torch.float32, device=y.device)
+        with torch.cuda.device(y.device):
+            rc = lib.hv_ln_residual_fwd(_ptr(y), _ptr(shortcut), _ptr(gamma32), _ptr(beta32), _ptr(keep_scale), _ptr(out),
+                                        _ptr(mean), _ptr(rstd), rows, C, rows_per_sample, float(eps), _code(y), _code(out),
+                                        _stream(y.device))
+        check(rc, "hv_ln_residual_fwd")
+        global LAUNCH_COUNT
+        LAUNCH_COUNT += 1
+        ctx.save_for_backward(y, gamma32, mean, rstd, keep_scale)
+        ctx.meta = (rows, C, rows_per_sample, shortcut is not None, gamma.dtype, beta.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        y, gamma32, mean, rstd, keep_scale = ctx.saved_tensors
+        rows, C, rows_per_sample, has_shortcut, gdt, bdt = ctx.meta
+        lib = _lib.load()
+        dout = dout.contiguous()
+        dy = torch.empty_like(y)
+        dgamma = torch.empty_like(gamma32)
+        dbeta = torch.empty_like(gamma32)
+        with torch.cuda.device(y.device):
+            nbytes = lib.hv_ln_residual_bwd_workspace_bytes(rows, C)
+            workspace = torch.empty((int(nbytes),), dtype=torch.uint8, device=y.device)
+            rc = lib.hv_ln_residual_bwd(_ptr(dout), _ptr(y), _ptr(gamma32), _ptr(mean), _ptr(rstd), _ptr(keep_scale),
+                                        _ptr(dy), _ptr(dgamma), _ptr(dbeta), _ptr(workspace), workspace.numel(), rows, C,
+                                        rows_per_sample, _code(y), _code(dout), _stream(y.device))
+        check(rc, "hv_ln_residual_bwd")
+        global LAUNCH_COUNT
+        LAUNCH_COUNT += 2
+        return dy, (dout if has_shortcut else None), dgamma.to(gdt), dbeta.to(bdt), None, None, None
+
+
+def ln_residual(y: torch.Tensor, shortcut: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor,
+                keep_scale: Optional[torch.Tensor] = None, eps: float = 1e-5) -> torch.Tensor:
+    """shortcut + keep_scale[b] * LayerNorm(y) over the last dim; y is (B, L, C) (or (rows, C))."""
+    rows_per_sample = (y.numel() // y.shape[-1]) // y.shape[0] if y.dim() >= 2 else 1
+    return _LnResidual.apply(y, shortcut, gamma, beta, keep_scale, rows_per_sample, eps)
+
+
+class _PatchMergeGather(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, H, W):
+        _need_cuda(x, "patch_merge_gather")
+        lib = _lib.load()
+        x = x.contiguous()
+        B, L, C = x.shape
+        out = torch.empty((B, L // 4, 4 * C), dtype=x.dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = lib.hv_patch_merge_gather_fwd(_ptr(x), _ptr(out), B, H, W, C, _code(x), _stream(x.device))
+        check(rc, "hv_patch_merge_gather_fwd")
+        global LAUNCH_COUNT
+        LAUNCH_COUNT += 1
+        ctx.meta = (B, H, W, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, H, W, C = ctx.meta
+        lib = _lib.load()
+        dout = dout.contiguous()
+        dx = torch.empty((B, H * W, C), dtype=dout.dtype, device=dout.device)
+        with torch.cuda.device(dout.device):
+            rc = lib.hv_patch_merge_gather_bwd(_ptr(dout), _ptr(dx), B, H, W, C, _code(dout), _stream(dout.device))
+        check(rc, "hv_patch_merge_gather_bwd")
+        global LAUNCH_COUNT
+        LAUNCH_COUNT += 1
+        return dx, None, None
+
+
+def patch_merge_gather(x: torch.Tensor, H: int, W: int) -> torch.Tensor:
+    """(B, H*W, C) -> (B, H/2*W/2, 4C), channel blocks ordered (0,0),(1,0),(0,1),(1,1)."""
+    return _PatchMergeGather.apply(x, H, W)

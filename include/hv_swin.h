@@ -1,0 +1,139 @@
+/* hv_swin.h -- C ABI of libhv_swin.so: the sm_100a (B200) implementation of the SwinV2
+ * windowed-attention hot path of samuelstevens/hierarchical-vision.
+ *
+ * The reference implements this path as PyTorch nn.Modules in `swinv2.py`; the drop-in
+ * boundary is those classes (hierarchical_vision_b200/swinv2.py keeps their names, ctor
+ * arguments, forward signatures and state_dict keys).  This header is what sits underneath:
+ * plain pointers and sizes, no torch types.  Each entry point names the reference lines
+ * (file:line in /root/reference) whose work it replaces.
+ *
+ * Conventions
+ *   - every pointer marked "device" is CUDA device memory owned by the caller; the library
+ *     never allocates, frees or keeps a pointer after the call returns;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); calls only enqueue;
+ *   - return value 0 = success, otherwise an HV_ERR_* code; hv_last_error() gives the message
+ *     of the last failing call on the calling thread.  No exceptions cross the boundary;
+ *   - there is no CPU fallback and no other GPU backend: on anything but sm_100 the device
+ *     entry points return HV_ERR_ARCH;
+ *   - dtype codes describe the activation tensors; small parameter tensors (bias table, tau,
+ *     LayerNorm gamma/beta, statistics, gradients of those) are always float32.
+ */
+#ifndef HV_SWIN_H_
+#define HV_SWIN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HV_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define HV_API __attribute__((visibility("default")))
+#else
+#define HV_API
+#endif
+
+enum { HV_F32 = 0, HV_BF16 = 1 };
+
+enum {
+  HV_OK = 0,
+  HV_ERR_SHAPE = 1,     /* unsupported / inconsistent sizes                         */
+  HV_ERR_ALIGN = 2,     /* pointer or row pitch not 16-byte aligned                 */
+  HV_ERR_DTYPE = 3,     /* unknown dtype code or unsupported combination            */
+  HV_ERR_WORKSPACE = 4, /* workspace missing or smaller than hv_*_workspace_bytes() */
+  HV_ERR_ARCH = 5,      /* device is not sm_100 (B200)                              */
+  HV_ERR_CUDA = 6,      /* a CUDA runtime call or launch failed                     */
+  HV_ERR_NULL = 7       /* required pointer is NULL                                 */
+};
+
+/* ---- library info -------------------------------------------------------------------- */
+HV_API int hv_abi_version(void);
+HV_API const char* hv_last_error(void);
+/* 100 when built for sm_100a */
+HV_API int hv_compiled_arch(void);
+/* Which attention kernel a geometry dispatches to: 0 = generic CUDA-core kernel,
+ * 1 = tensor-core kernel (N=64, head dim 32, bf16).  Host-only query. */
+HV_API int hv_window_attn_kernel_kind(int C, int heads, int ws, int dtype);
+
+/* ---- host-side integer maps (CPU; same arithmetic the kernels use on the device) ------ */
+/* relative_position_index (N,N) int64 -- reference swinv2.py:175-190 */
+HV_API int hv_relative_position_index(int ws, int64_t* out);
+/* attn_mask (nW,N,N) float32 in {0,-100} -- reference swinv2.py:357-388 (requires shift > 0) */
+HV_API int hv_shift_window_mask(int H, int W, int ws, int shift, float* out);
+/* token index feeding window row r, slot i: roll(-shift) + window_partition, (B*nW, N) int64
+ * -- reference swinv2.py:69-83, 399-412; also the scatter map of window_reverse + roll(+shift)
+ * (swinv2.py:86-102, 420-429) */
+HV_API int hv_window_token_index(int B, int H, int W, int ws, int shift, int64_t* out);
+/* PatchMerging concat sources (B*H/2*W/2, 4) int64 -- reference swinv2.py:486-490 */
+HV_API int hv_merge_token_index(int B, int H, int W, int64_t* out);
+
+/* ---- fused shifted-window scaled-cosine attention --------------------------------------
+ * Replaces, in SwinTransformerBlock.forward / WindowAttention.forward:
+ *   torch.roll + window_partition            swinv2.py:399-412
+ *   head split, F.normalize(q) @ F.normalize(k)^T, * exp(clamped logit_scale)   :221-231
+ *   + 16*sigmoid(cpb table)[relative_position_index]                            :236-247
+ *   + shifted-window mask, softmax                                              :249-257
+ *   attn @ v, head merge                                                        :261
+ *   window_reverse + torch.roll back                                            :420-429
+ * and the autograd of all of it.  The per-token linears (qkv, proj) stay outside.
+ *
+ *   qkv   device, (B, H*W, 3C) `dtype`, image token order, channel = t*C + head*d + j (t=q,k,v)
+ *   bias_table device float32 ((2ws-1)^2, heads) = 16*sigmoid(cpb_mlp(relative_coords_table))
+ *   tau   device float32 (heads) = exp(min(logit_scale, log 100))
+ *   mask  NULL -> the shift mask is generated in-kernel from (H, W, ws, shift);
+ *         else device float32 (mask_windows, N, N) added to window (row % mask_windows) and the
+ *         in-kernel shift mask is NOT applied (WindowAttention.forward(x, mask) semantics)
+ *   out   device, (B, H*W, C) `dtype`, image token order
+ *   lse   device float32 (B*nW, heads, N): row log-sum-exp (natural log), saved for backward
+ */
+HV_API int hv_window_attn_fwd(const void* qkv, const float* bias_table, const float* tau, const float* mask,
+                       int mask_windows, void* out, float* lse, int B, int H, int W, int C, int heads,
+                       int ws, int shift, int dtype, void* stream);
+
+/* Workspace (bytes) hv_window_attn_bwd needs for its partial reductions. */
+HV_API size_t hv_window_attn_bwd_workspace_bytes(int B, int H, int W, int C, int heads, int ws, int dtype);
+
+/*   dout  device (B, H*W, C) `dtype`: gradient of `out`
+ *   dqkv  device (B, H*W, 3C) `dtype`: fully overwritten
+ *   dbias_table device float32 ((2ws-1)^2, heads): overwritten with d loss / d bias_table
+ *   dtau  device float32 (heads): overwritten with d loss / d tau
+ */
+HV_API int hv_window_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
+                       const float* bias_table, const float* tau, const float* mask, int mask_windows,
+                       void* dqkv, float* dbias_table, float* dtau, void* workspace, size_t workspace_bytes,
+                       int B, int H, int W, int C, int heads, int ws, int shift, int dtype, void* stream);
+
+/* ---- res-post-norm: out = shortcut + keep_scale[sample] * LayerNorm(y) -------------------
+ * Replaces `shortcut + drop_path(norm1(x))` / `x + drop_path(norm2(mlp(x)))`, swinv2.py:431, 434,
+ * and (shortcut == NULL) the plain LayerNorm of PatchMerging, swinv2.py:494.
+ *   y        device (rows, C) y_dtype          shortcut  device (rows, C) res_dtype or NULL
+ *   gamma, beta  device float32 (C)            keep_scale device float32 (rows / rows_per_sample) or NULL
+ *   out      device (rows, C) res_dtype        mean, rstd device float32 (rows), saved for backward
+ */
+HV_API int hv_ln_residual_fwd(const void* y, const void* shortcut, const float* gamma, const float* beta,
+                       const float* keep_scale, void* out, float* mean, float* rstd, int64_t rows, int C,
+                       int64_t rows_per_sample, float eps, int y_dtype, int res_dtype, void* stream);
+
+HV_API size_t hv_ln_residual_bwd_workspace_bytes(int64_t rows, int C);
+
+/*   dout device (rows, C) res_dtype (this is also d shortcut)   dy device (rows, C) y_dtype
+ *   dgamma, dbeta device float32 (C), overwritten */
+HV_API int hv_ln_residual_bwd(const void* dout, const void* y, const float* gamma, const float* mean,
+                       const float* rstd, const float* keep_scale, void* dy, float* dgamma, float* dbeta,
+                       void* workspace, size_t workspace_bytes, int64_t rows, int C, int64_t rows_per_sample,
+                       int y_dtype, int res_dtype, void* stream);
+
+/* ---- PatchMerging 2x2 gather ------------------------------------------------------------
+ * Replaces the four strided slices + torch.cat of swinv2.py:484-491 (forward) and their
+ * autograd (backward = the inverse permutation; every input token is read exactly once).
+ *   x  device (B, H*W, C)      out device (B, H/2*W/2, 4C)       same dtype */
+HV_API int hv_patch_merge_gather_fwd(const void* x, void* out, int B, int H, int W, int C, int dtype, void* stream);
+HV_API int hv_patch_merge_gather_bwd(const void* dout, void* dx, int B, int H, int W, int C, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HV_SWIN_H_ */

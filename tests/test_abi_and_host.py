@@ -1,0 +1,178 @@
+"""CPU: the C-ABI library loads and exports every symbol include/hv_swin.h declares; its host-side
+integer maps (the same inline functions the kernels use) are bit-exact against the oracle and the
+reference-generated digests; the module surface matches the reference's state_dict contract; and
+the product refuses to run without CUDA (no CPU fallback)."""
+import ctypes
+import hashlib
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import hierarchical_vision_b200 as hv
+from hierarchical_vision_b200 import _lib
+from oracle import swin_oracle as O
+from tests._util import digests, load_case, manifest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(_lib.LIB_PATH):
+        from hierarchical_vision_b200 import build
+        build.build()
+    return _lib.load()
+
+
+def test_every_declared_symbol_is_exported(lib):
+    header = open(os.path.join(ROOT, "include", "hv_swin.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(hv_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.hv_abi_version() == 1
+    assert lib.hv_compiled_arch() == 100
+
+
+def test_shared_object_contains_sm100a_code():
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in out.stdout
+
+
+@pytest.mark.parametrize("ws", [2, 4, 7, 8, 12, 16])
+def test_host_relative_position_index_bit_exact(lib, ws):
+    N = ws * ws
+    out = np.empty((N, N), dtype=np.int64)
+    assert lib.hv_relative_position_index(ws, out.ctypes.data_as(ctypes.c_void_p)) == 0
+    assert np.array_equal(out, O.relative_position_index(ws))
+    assert _sha(out) == digests()["relative_position_index"][str(ws)]["sha256"]
+
+
+def test_host_shift_mask_bit_exact(lib):
+    for key, rec in digests()["attn_mask"].items():
+        H, W, ws, s = map(int, key.split(","))
+        out = np.empty(rec["shape"], dtype=np.float32)
+        assert lib.hv_shift_window_mask(H, W, ws, s, out.ctypes.data_as(ctypes.c_void_p)) == 0
+        assert _sha(out) == rec["sha256"], key
+    out = np.empty((1,), dtype=np.float32)
+    assert lib.hv_shift_window_mask(16, 16, 8, 0, out.ctypes.data_as(ctypes.c_void_p)) != 0
+    assert b"shift" in lib.hv_last_error()
+
+
+def test_host_window_token_index_bit_exact(lib):
+    for key, rec in digests()["window_token_index"].items():
+        B, H, W, ws, s = map(int, key.split(","))
+        out = np.empty(rec["shape"], dtype=np.int64)
+        assert lib.hv_window_token_index(B, H, W, ws, s, out.ctypes.data_as(ctypes.c_void_p)) == 0
+        assert _sha(out) == rec["sha256"], key
+
+
+def test_host_merge_token_index(lib):
+    out = np.empty((2 * 3 * 4, 4), dtype=np.int64)
+    assert lib.hv_merge_token_index(2, 6, 8, out.ctypes.data_as(ctypes.c_void_p)) == 0
+    assert np.array_equal(out, O.merge_token_index(2, 6, 8))
+    assert lib.hv_merge_token_index(1, 5, 8, out.ctypes.data_as(ctypes.c_void_p)) != 0
+    assert b"not even" in lib.hv_last_error()
+
+
+def test_bad_arguments_return_codes_not_crashes(lib):
+    assert lib.hv_window_attn_fwd(None, None, None, None, 0, None, None, 1, 8, 8, 32, 1, 8, 0, 0, None) == 7  # HV_ERR_NULL
+    assert lib.hv_relative_position_index(0, None) != 0
+    assert lib.hv_window_attn_bwd_workspace_bytes(1, 8, 8, 30, 4, 8, 1) == 0  # C % heads != 0
+
+
+def test_kernel_kind_dispatch(lib):
+    # bf16, N=64, head dim 32 -> tensor-core kernel; everything else -> generic kernel
+    assert lib.hv_window_attn_kernel_kind(96, 3, 7, _lib.HV_BF16) == 0
+    assert lib.hv_window_attn_kernel_kind(96, 3, 8, _lib.HV_F32) == 0
+
+
+# ------------------------------------------------------------------ module surface
+BLOCKS = [k for k, v in manifest()["cases"].items() if v["kind"] == "block"]
+
+
+@pytest.mark.parametrize("name", BLOCKS)
+def test_block_state_dict_contract(name):
+    meta, state, _ = load_case(name)
+    blk = hv.SwinTransformerBlock(meta["C"], (meta["H"], meta["W"]), meta["heads"], window_size=meta["ws"],
+                                  shift_size=meta["shift"], mlp_ratio=meta["mlp_ratio"])
+    assert blk.window_size == meta["eff_ws"] and blk.shift_size == meta["eff_shift"]
+    mine = blk.state_dict()
+    assert list(mine.keys()) == list(state.keys())  # same names, same order
+    for k in state:
+        assert mine[k].shape == state[k].shape and mine[k].dtype == state[k].dtype, k
+    # constant buffers are bit-identical to the reference's
+    for k in ("attn.relative_position_index", "attn.relative_coords_table", "attn.logit_clamp_max"):
+        assert torch.equal(mine[k], state[k]), k
+    if "attn_mask" in state:
+        assert torch.equal(mine["attn_mask"], state["attn_mask"])
+    blk.load_state_dict(state, strict=True)
+
+
+def test_model_state_dict_contract_and_flops():
+    meta, state, _ = load_case("model_tiny")
+    model = hv.SwinTransformerV2(img_size=meta["img_size"], patch_size=meta["patch_size"], in_chans=meta["in_chans"],
+                                 num_classes=meta["num_classes"], embed_dim=meta["embed_dim"], depths=meta["depths"],
+                                 num_heads=meta["num_heads"], window_size=meta["window_size"], drop_path_rate=0.0)
+    assert list(model.state_dict().keys()) == list(state.keys())
+    model.load_state_dict(state, strict=True)
+    # reference init: res-post-norm gammas are zero (swinv2.py:603-608)
+    fresh = hv.SwinTransformerV2(img_size=64, embed_dim=32, depths=[2, 2], num_heads=[1, 2], window_size=8, num_classes=5)
+    assert float(fresh.layers[0].blocks[0].norm1.weight.abs().sum()) == 0.0
+    assert float(fresh.layers[0].blocks[0].attn.logit_scale[0]) == pytest.approx(float(np.log(10.0)), rel=1e-6)
+    # reference flops() of SwinV2-T 256/w8, 10k classes = 5.93 G MACs
+    t = hv.swinv2_tiny()
+    assert abs(t.flops() / 1e9 - 5.93) < 0.01
+    assert sum(p.numel() for p in t.parameters()) == pytest.approx(35.27e6, rel=2e-3)
+    heads = hv.swinv2_tiny(num_classes=(3, 5)).head
+    assert isinstance(heads, hv.MultitaskHead) and len(heads.heads) == 2
+
+
+def test_checkpoint_filter_and_parse():
+    ck = hv.Checkpoint.parse("swin://some/dir/model.pth")
+    assert ck.source == "swin" and ck.path == "some/dir/model.pth"
+    with pytest.raises(ValueError):
+        hv.Checkpoint.parse("http://x")
+    d = {"layers.0.blocks.0.attn.relative_position_index": 1, "layers.0.blocks.0.attn.qkv.weight": 2,
+         "a.relative_coords_table": 3, "a.logit_clamp_max": 4}
+    assert list(hv.Checkpoint.filter(d)) == ["layers.0.blocks.0.attn.qkv.weight"]
+
+
+def test_window_partition_reverse_roundtrip():
+    x = torch.arange(2 * 8 * 12 * 3).view(2, 8, 12, 3)
+    w = hv.window_partition(x, 4)
+    assert w.shape == (2 * 2 * 3, 4, 4, 3)
+    assert torch.equal(hv.window_reverse(w, 4, 8, 12), x)
+    idx = O.window_token_index(2, 8, 12, 4, 0)
+    assert np.array_equal(w[..., 0].reshape(-1, 16).numpy() // 3, idx)
+
+
+def test_no_cpu_fallback():
+    blk = hv.SwinTransformerBlock(32, (8, 8), 1, window_size=8)
+    with pytest.raises(RuntimeError, match="no CPU path|CUDA"):
+        blk(torch.randn(1, 64, 32))
+    pm = hv.PatchMerging((8, 8), 32)
+    with pytest.raises(RuntimeError, match="no CPU path|CUDA"):
+        pm(torch.randn(1, 64, 32))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "hierarchical_vision_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "oracle/" not in src.replace(
+                    "routes through ``oracle/``", ""), fn

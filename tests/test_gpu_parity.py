@@ -1,0 +1,378 @@
+"""GPU (-m gpu): parity of the sm_100a kernels, called through the C ABI / module surface, against
+(a) the oracle on identical seeded inputs, (b) the committed reference fixtures, and (c) at
+BASELINE.json's full sizes, the oracle plus size-independent properties.
+
+Tolerances (BASELINE.json north_star): integer maps bit-exact; fp32 outputs and gradients
+rel-L2 <= 1e-3; bf16 <= 2e-2 (tiny reduction gradients <= 4e-2, see SURVEY.md 8c bf16 caveat).
+"""
+import numpy as np
+import pytest
+import torch
+
+import hierarchical_vision_b200 as hv
+from hierarchical_vision_b200 import functional as hvf
+from oracle import swin_oracle as O
+from tests._util import assert_close, load_case, manifest, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+TOL = {torch.float32: 1e-3, torch.bfloat16: 2e-2}
+
+
+def _oracle_core(qkv, bias_table, tau, g, do, mask=None):
+    """fp64 oracle of the fused-kernel boundary from the (already dtype-rounded) device inputs."""
+    q64 = qkv.detach().double().cpu()
+    bt = bias_table.detach().double().cpu()
+    t64 = tau.detach().double().cpu()
+    m64 = mask.detach().double().cpu() if mask is not None else None
+    bias = O.expand_bias(bt, g.ws)
+    o, lse = O.attention_core_forward(q64, bias, t64, g, mask=m64, use_shift_mask=mask is None)
+    dqkv, dbias, dtau = O.attention_core_backward(q64, bias, t64, g, do.detach().double().cpu(), mask=m64,
+                                                  use_shift_mask=mask is None)
+    # fold d bias (h,N,N) back onto the ((2ws-1)^2, h) table, as the kernel reports it
+    rpi = torch.from_numpy(O.relative_position_index(g.ws)).reshape(-1)
+    dtab = torch.zeros_like(bt)
+    dtab.index_add_(0, rpi, dbias.permute(1, 2, 0).reshape(-1, g.heads))
+    return o, lse, dqkv, dtab, dtau
+
+
+CORE_CASES = [
+    # B, H, W, C, heads, ws, shift
+    (2, 16, 16, 64, 2, 8, 4),
+    (1, 16, 24, 96, 3, 8, 3),
+    (2, 8, 8, 128, 4, 8, 0),
+    (1, 24, 16, 32, 1, 8, 7),
+    (1, 14, 21, 48, 3, 7, 3),     # reference default window 7, head dim 16
+    (2, 8, 8, 32, 1, 4, 2),
+    (1, 32, 32, 64, 2, 16, 8),    # SwinV2-B window
+    (1, 16, 16, 128, 2, 8, 4),    # head dim 64
+    (3, 16, 16, 192, 6, 8, 4),    # stage-1 shape of SwinV2-T
+]
+
+
+@pytest.mark.parametrize("case", CORE_CASES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_window_attention_core(case, dtype):
+    B, H, W, C, h, ws, s = case
+    g = O.Geometry(B, H, W, C, h, ws, s)
+    gen = torch.Generator().manual_seed(hash(case) % 1000)
+    qkv = torch.randn(B, H * W, 3 * C, generator=gen).to(DEV, dtype).requires_grad_(True)
+    tab = (16 * torch.rand((2 * ws - 1) ** 2, h, generator=gen)).to(DEV).requires_grad_(True)
+    tau = (5 + 40 * torch.rand(h, generator=gen)).to(DEV).requires_grad_(True)
+    do = torch.randn(B, H * W, C, generator=gen).to(DEV, dtype)
+    out = hvf.window_attention(qkv, tab, tau, B=B, H=H, W=W, C=C, heads=h, ws=ws, shift=s)
+    assert out.dtype == dtype and out.shape == (B, H * W, C)
+    out.backward(do)
+    torch.cuda.synchronize()
+    o, lse, dqkv, dtab, dtau = _oracle_core(qkv, tab, tau, g, do)
+    tol = TOL[dtype]
+    assert_close("out", out, o, tol)
+    assert_close("dqkv", qkv.grad, dqkv, tol)
+    assert_close("dbias_table", tab.grad, dtab, tol)
+    assert_close("dtau", tau.grad, dtau, 2 * tol)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_window_attention_explicit_mask_fixture(dtype):
+    """WindowAttention.forward(x, mask) with an arbitrary (nW,N,N) mask vs the reference fixture."""
+    meta, state, a = load_case("window_attention_mask")
+    wa = hv.WindowAttention(meta["C"], (meta["ws"], meta["ws"]), meta["heads"]).to(DEV)
+    wa.load_state_dict(state, strict=True)
+    x = a["x"].to(DEV).requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.bfloat16):
+        y = wa(x, mask=a["mask"].to(DEV))
+    y.float().backward(a["gy"].to(DEV))
+    tol = TOL[dtype]
+    assert_close("y", y, a["ref.y"], tol)
+    assert_close("dx", x.grad, a["ref.dx"], tol)
+    for k, v in a.items():
+        if k.startswith("ref.grad."):
+            assert_close(k, dict(wa.named_parameters())[k[len("ref.grad."):]].grad, v, 2 * tol)
+
+
+BLOCKS = [k for k, v in manifest()["cases"].items() if v["kind"] == "block"]
+
+
+def _build_block(meta, state, dtype=torch.float32):
+    blk = hv.SwinTransformerBlock(meta["C"], (meta["H"], meta["W"]), meta["heads"], window_size=meta["ws"],
+                                  shift_size=meta["shift"], mlp_ratio=meta["mlp_ratio"])
+    blk.load_state_dict(state, strict=True)
+    return blk.to(DEV)
+
+
+@pytest.mark.parametrize("name", BLOCKS)
+def test_block_fp32_vs_reference_fixture(name):
+    meta, state, a = load_case(name)
+    blk = _build_block(meta, state)
+    x = a["x"].to(DEV).requires_grad_(True)
+    y = blk(x)
+    y.backward(a["gy"].to(DEV))
+    assert_close("y", y, a["ref.y"], 1e-3)
+    assert_close("dx", x.grad, a["ref.dx"], 1e-3)
+    params = dict(blk.named_parameters())
+    for k, v in a.items():
+        if k.startswith("ref.grad."):
+            assert_close(k, params[k[len("ref.grad."):]].grad, v, 1e-3)
+
+
+@pytest.mark.parametrize("name", BLOCKS)
+@pytest.mark.parametrize("mode", ["autocast", "pure_bf16"])
+def test_block_bf16_vs_reference_fixture(name, mode):
+    meta, state, a = load_case(name)
+    blk = _build_block(meta, state)
+    x = a["x"].to(DEV)
+    if mode == "pure_bf16":
+        blk = blk.bfloat16()
+        x = x.bfloat16()
+    x.requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=mode == "autocast"):
+        y = blk(x)
+    y.backward(a["gy"].to(DEV, y.dtype))
+    assert_close("y", y, a["ref.y"], 2e-2)
+    assert_close("dx", x.grad, a["ref.dx"], 2e-2)
+    params = dict(blk.named_parameters())
+    for k, v in a.items():
+        if k.startswith("ref.grad."):
+            small = v.numel() <= 2048  # biases / LN affine / logit_scale: reduction gradients
+            assert_close(k, params[k[len("ref.grad."):]].grad, v, 4e-2 if small else 2e-2)
+
+
+@pytest.mark.parametrize("name", ["patch_merging", "patch_merging_rect"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_patch_merging_vs_reference_fixture(name, dtype):
+    meta, state, a = load_case(name)
+    pm = hv.PatchMerging((meta["H"], meta["W"]), meta["C"])
+    pm.load_state_dict(state, strict=True)
+    pm = pm.to(DEV, dtype)
+    x = a["x"].to(DEV, dtype).requires_grad_(True)
+    y = pm(x)
+    y.backward(a["gy"].to(DEV, dtype))
+    tol = TOL[dtype]
+    assert_close("y", y, a["ref.y"], tol)
+    assert_close("dx", x.grad, a["ref.dx"], tol)
+    for k, v in a.items():
+        if k.startswith("ref.grad."):
+            assert_close(k, dict(pm.named_parameters())[k[len("ref.grad."):]].grad, v, 2 * tol)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 6, 8, 16), (1, 64, 64, 96), (3, 16, 16, 768)])
+def test_patch_merge_gather_is_the_exact_permutation(shape, dtype):
+    B, H, W, C = shape
+    x = torch.randn(B, H * W, C, device=DEV).to(dtype).requires_grad_(True)
+    out = hvf.patch_merge_gather(x, H, W)
+    idx = torch.from_numpy(O.merge_token_index(B, H, W)).to(DEV).reshape(-1)
+    want = x.detach().reshape(B * H * W, C)[idx].reshape(B, (H // 2) * (W // 2), 4 * C)
+    assert torch.equal(out, want)  # bit exact: pure data movement
+    g = torch.randn_like(out)
+    out.backward(g)
+    dx = torch.empty_like(x).reshape(B * H * W, C)
+    dx[idx] = g.reshape(-1, C)
+    assert torch.equal(x.grad.reshape(B * H * W, C), dx)
+
+
+LN_CASES = [(2, 64, 96), (2, 40, 192), (3, 17, 384), (2, 9, 768), (1, 33, 128), (2, 8, 1024), (4, 5, 32), (2, 7, 1536)]
+
+
+@pytest.mark.parametrize("shape", LN_CASES)
+@pytest.mark.parametrize("dtypes", [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16),
+                                    (torch.bfloat16, torch.float32)])
+@pytest.mark.parametrize("variant", ["residual+drop", "residual", "plain"])
+def test_ln_residual(shape, dtypes, variant):
+    B, L, C = shape
+    ydt, rdt = dtypes
+    if variant == "plain" and ydt != rdt:
+        pytest.skip("plain LayerNorm keeps the input dtype")
+    if ydt == torch.float32 and C > 1024:
+        pytest.skip("fp32 rows wider than 1024 are outside SwinV2-T/B")
+    gen = torch.Generator().manual_seed(B * 1000 + L * 10 + C)
+    y = (torch.randn(B, L, C, generator=gen) * 2 + 0.5).to(DEV, ydt).requires_grad_(True)
+    sc = torch.randn(B, L, C, generator=gen).to(DEV, rdt).requires_grad_(True) if variant != "plain" else None
+    gam = (1 + 0.1 * torch.randn(C, generator=gen)).to(DEV).requires_grad_(True)
+    bet = (0.1 * torch.randn(C, generator=gen)).to(DEV).requires_grad_(True)
+    keep = None
+    if variant == "residual+drop":
+        keep = (torch.rand(B, generator=gen) < 0.7).float().div(0.7).to(DEV)
+    out = hvf.ln_residual(y, sc, gam, bet, keep)
+    assert out.dtype == (rdt if sc is not None else ydt)
+    go = torch.randn(B, L, C, generator=gen).to(DEV, out.dtype)
+    out.backward(go)
+    y64, g64, b64 = y.detach().double().cpu(), gam.detach().double().cpu(), bet.detach().double().cpu()
+    sc64 = sc.detach().double().cpu() if sc is not None else torch.zeros_like(y64)
+    k64 = keep.double().cpu() if keep is not None else None
+    want = O.layer_norm_residual(y64, sc64, g64, b64, k64)
+    dy, dg, db = O.layer_norm_residual_backward(y64, g64, go.double().cpu(), k64)
+    tol = 1e-3 if out.dtype == torch.float32 and ydt == torch.float32 else 2e-2
+    assert_close("out", out, want, tol if ydt == torch.float32 else 8e-3)
+    assert_close("dy", y.grad, dy, tol)
+    assert_close("dgamma", gam.grad, dg, tol)
+    assert_close("dbeta", bet.grad, db, tol)
+    if sc is not None:
+        assert torch.equal(sc.grad, go)
+
+
+def test_model_tiny_vs_reference_fixture():
+    meta, state, a = load_case("model_tiny")
+    model = hv.SwinTransformerV2(img_size=meta["img_size"], patch_size=meta["patch_size"], in_chans=meta["in_chans"],
+                                 num_classes=meta["num_classes"], embed_dim=meta["embed_dim"], depths=meta["depths"],
+                                 num_heads=meta["num_heads"], window_size=meta["window_size"], drop_path_rate=0.0)
+    model.load_state_dict(state, strict=True)
+    model = model.to(DEV)
+    x = a["x"].to(DEV).requires_grad_(True)
+    y = model(x)
+    y.backward(a["gy"].to(DEV))
+    assert_close("logits", y, a["ref.y"], 1e-3)
+    assert_close("dx", x.grad, a["ref.dx"], 1e-3)
+    params = dict(model.named_parameters())
+    for k, v in a.items():
+        if k.startswith("ref.grad."):
+            assert_close(k, params[k[len("ref.grad."):]].grad, v, 1e-3)
+
+
+# ------------------------------------------------------------------ BASELINE.json full sizes
+def _random_block_state(C, res, heads, ws, shift, seed):
+    torch.manual_seed(seed)
+    blk = hv.SwinTransformerBlock(C, res, heads, window_size=ws, shift_size=shift)
+    with torch.no_grad():
+        for n in (blk.norm1, blk.norm2):
+            n.weight.normal_(1, 0.1)
+            n.bias.normal_(0, 0.1)
+        blk.attn.logit_scale.uniform_(1.6, 3.9)
+        blk.attn.q_bias.normal_(0, 0.05)
+        blk.attn.v_bias.normal_(0, 0.05)
+    return blk
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_cfg1_block_full_size_vs_oracle(dtype):
+    """BASELINE.json configs[0]: batch 8, 64x64 tokens, window 8, 3 heads, dim 96, shifted."""
+    blk = _random_block_state(96, (64, 64), 3, 8, 4, seed=0)
+    state = {k: v.detach().clone() for k, v in blk.state_dict().items()}
+    gen = torch.Generator().manual_seed(1)
+    x = torch.randn(8, 4096, 96, generator=gen)
+    gy = torch.randn(8, 4096, 96, generator=gen)
+    blk = blk.to(DEV)
+    xd = x.to(DEV).requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.bfloat16):
+        y = blk(xd)
+    y.backward(gy.to(DEV, y.dtype))
+    p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in state.items()}
+    xo = x.clone().requires_grad_(True)
+    yo = O.swin_block(xo, p, "", (64, 64), 3, 8, 4)
+    yo.backward(gy)
+    tol = TOL[dtype]
+    assert_close("y", y, yo, tol)
+    assert_close("dx", xd.grad, xo.grad, tol)
+    for k, prm in blk.named_parameters():
+        small = prm.numel() <= 2048
+        assert_close(k, prm.grad, p[k].grad, (2 * tol if small else tol))
+
+
+def test_full_size_properties_shift_equivariance_and_window_locality():
+    """Size-independent properties at the stage-0 shape (B 32, 64x64, C 96, ws 8):
+    (1) with shift 0, translating the token grid by one whole window translates the output;
+    (2) perturbing one window's tokens changes only that window's outputs;
+    (3) the forward is deterministic bit-for-bit."""
+    B, H, W, C, h, ws = 32, 64, 64, 96, 3, 8
+    gen = torch.Generator().manual_seed(3)
+    qkv = torch.randn(B, H * W, 3 * C, generator=gen).to(DEV, torch.bfloat16)
+    tab = (16 * torch.rand((2 * ws - 1) ** 2, h, generator=gen)).to(DEV)
+    tau = (5 + 40 * torch.rand(h, generator=gen)).to(DEV)
+    kw = dict(B=B, H=H, W=W, C=C, heads=h, ws=ws)
+    o0 = hvf.window_attention(qkv, tab, tau, shift=0, **kw)
+    o0b = hvf.window_attention(qkv, tab, tau, shift=0, **kw)
+    assert torch.equal(o0, o0b)
+    rolled = torch.roll(qkv.view(B, H, W, 3 * C), (ws, ws), (1, 2)).reshape(B, H * W, 3 * C)
+    o1 = hvf.window_attention(rolled, tab, tau, shift=0, **kw)
+    assert torch.equal(torch.roll(o0.view(B, H, W, C), (ws, ws), (1, 2)).reshape(B, H * W, C), o1)
+    # locality under the shifted partition
+    s = 4
+    o2 = hvf.window_attention(qkv, tab, tau, shift=s, **kw)
+    idx = torch.from_numpy(O.window_token_index(B, H, W, ws, s)).to(DEV)
+    victim = 5 * 64 + 37  # some window row
+    q2 = qkv.clone().view(B * H * W, 3 * C)
+    q2[idx[victim]] += 1.0
+    o3 = hvf.window_attention(q2.view(B, H * W, 3 * C), tab, tau, shift=s, **kw)
+    changed = (o2.view(B * H * W, C) != o3.view(B * H * W, C)).any(dim=1)
+    inside = torch.zeros(B * H * W, dtype=torch.bool, device=DEV)
+    inside[idx[victim]] = True
+    assert not bool((changed & ~inside).any())
+    assert bool(changed[inside].all())
+
+
+def test_swinv2_tiny_full_model_vs_oracle():
+    """BASELINE.json configs[1] architecture (SwinV2-T, 256x256, window 8, 10k classes), batch 2, fp32."""
+    spec = O.SWINV2_T
+    p = O.init_state(spec, seed=0)
+    model = hv.swinv2_tiny(drop_path_rate=0.0)
+    missing = model.load_state_dict(p, strict=False)
+    assert not missing.unexpected_keys
+    assert all(("relative" in k or "logit_clamp_max" in k or "attn_mask" in k) for k in missing.missing_keys)
+    model = model.to(DEV)
+    gen = torch.Generator().manual_seed(5)
+    img = torch.randn(2, 3, 256, 256, generator=gen)
+    labels = torch.tensor([17, 4242])
+    loss = torch.nn.functional.cross_entropy(model(img.to(DEV)), labels.to(DEV))
+    loss.backward()
+    po = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    loss_o = torch.nn.functional.cross_entropy(O.swin_model(img, po, spec), labels)
+    loss_o.backward()
+    assert abs(loss.item() - loss_o.item()) <= 1e-3 * abs(loss_o.item())
+    params = dict(model.named_parameters())
+    for k in ("layers.0.blocks.1.attn.qkv.weight", "layers.0.blocks.1.attn.cpb_mlp.2.weight",
+              "layers.0.blocks.1.attn.logit_scale", "layers.1.blocks.0.norm1.weight",
+              "layers.2.blocks.5.attn.q_bias", "layers.0.downsample.reduction.weight", "layers.3.blocks.1.mlp.fc1.weight",
+              "patch_embed.proj.weight", "head.weight"):
+        assert_close(k, params[k].grad, po[k].grad, 2e-3)
+
+
+# ------------------------------------------------------------------ module behaviours
+def test_drop_path_training_matches_oracle_given_same_draws():
+    meta, state, a = load_case("block_ws8_shift4")
+    blk = hv.SwinTransformerBlock(meta["C"], (meta["H"], meta["W"]), meta["heads"], window_size=meta["ws"],
+                                  shift_size=meta["shift"], mlp_ratio=meta["mlp_ratio"], drop_path=0.4)
+    blk.load_state_dict(state, strict=True)
+    blk = blk.to(DEV).train()
+    x = a["x"].to(DEV)
+    B = x.shape[0]
+    torch.manual_seed(123)
+    k1 = torch.empty(B, device=DEV).bernoulli_(0.6).div_(0.6)
+    k2 = torch.empty(B, device=DEV).bernoulli_(0.6).div_(0.6)
+    torch.manual_seed(123)
+    y = blk(x)
+    p = {k: v.double() if v.is_floating_point() else v for k, v in state.items()}
+    want = O.swin_block(a["x"].double(), p, "", (meta["H"], meta["W"]), meta["heads"], meta["ws"], meta["shift"],
+                        keep_scale1=k1.double().cpu(), keep_scale2=k2.double().cpu())
+    assert_close("y", y, want, 1e-3)
+    blk.eval()
+    assert_close("y_eval", blk(x), a["ref.y"], 1e-3)
+
+
+def test_activation_checkpointing_and_basic_layer():
+    torch.manual_seed(0)
+    layer = hv.BasicLayer(64, (16, 16), 2, 2, 8, downsample=hv.PatchMerging, use_checkpoint=True).to(DEV)
+    with torch.no_grad():
+        for blk in layer.blocks:
+            blk.norm1.weight.fill_(1.0)
+            blk.norm2.weight.fill_(1.0)
+    x = torch.randn(2, 256, 64, device=DEV, requires_grad=True)
+    y = layer(x)
+    assert y.shape == (2, 64, 128)
+    y.sum().backward()
+    g_ckpt = x.grad.clone()
+    layer.use_checkpoint = False
+    x.grad = None
+    layer(x).sum().backward()
+    assert_close("dx", g_ckpt, x.grad, 1e-6)
+    assert layer.blocks[0].shift_size == 0 and layer.blocks[1].shift_size == 4
+
+
+def test_library_reports_errors_instead_of_crashing():
+    lib = hv._lib.load()
+    x = torch.randn(1, 64, 30, device=DEV)  # C*4 bytes not a multiple of 16
+    with pytest.raises(RuntimeError, match="multiple"):
+        hvf.ln_residual(x, None, torch.ones(30, device=DEV), torch.zeros(30, device=DEV))
+    with pytest.raises(RuntimeError, match="float32 or bfloat16"):
+        hvf.patch_merge_gather(torch.randn(1, 16, 8, device=DEV).half(), 4, 4)
+    assert lib.hv_compiled_arch() == 100
