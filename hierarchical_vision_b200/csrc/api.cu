@@ -168,7 +168,7 @@ int hv_window_attn_fwd(const void* qkv, const float* bias_table, const float* ta
   rc = attn_common_checks("hv_window_attn_fwd", dtype, mask, mask_windows, g);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (wattn_mma64_supported(g, dtype)) return wattn_mma64_fwd(g, qkv, bias_table, tau, mask, mask_windows, out, lse, st);
+  if (mask == nullptr && wattn_mma64_supported(g, dtype)) return wattn_mma64_fwd(g, qkv, bias_table, tau, mask, mask_windows, out, lse, st);
   return wattn_generic_fwd(g, dtype, qkv, bias_table, tau, mask, mask_windows, out, lse, st);
 }
 
@@ -191,7 +191,7 @@ int hv_window_attn_bwd(const void* qkv, const void* out, const void* dout, const
   rc = attn_common_checks("hv_window_attn_bwd", dtype, mask, mask_windows, g);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (wattn_mma64_supported(g, dtype))
+  if (mask == nullptr && wattn_mma64_supported(g, dtype))
     return wattn_mma64_bwd(g, qkv, out, dout, lse, bias_table, tau, mask, mask_windows, dqkv, dbias_table, dtau, workspace,
                            workspace_bytes, st);
   return wattn_generic_bwd(g, dtype, qkv, out, dout, lse, bias_table, tau, mask, mask_windows, dqkv, dbias_table, dtau, st);

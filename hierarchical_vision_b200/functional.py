@@ -63,53 +63,69 @@ def _timed(tag, windows, stream_device, fn):
     return r
 
 
+def window_attention_fwd_raw(qkv, bias_table, tau, mask, out, lse, B, H, W, C, heads, ws, shift):
+    """Enqueue hv_window_attn_fwd on the current stream; every tensor is caller-allocated."""
+    lib = _lib.load()
+    with torch.cuda.device(qkv.device):
+        rc = lib.hv_window_attn_fwd(_ptr(qkv), _ptr(bias_table), _ptr(tau), _ptr(mask),
+                                    mask.shape[0] if mask is not None else 0, _ptr(out), _ptr(lse),
+                                    B, H, W, C, heads, ws, shift, _code(qkv), _stream(qkv.device))
+    check(rc, "hv_window_attn_fwd")
+
+
+def window_attention_bwd_workspace(qkv, B, H, W, C, heads, ws):
+    lib = _lib.load()
+    with torch.cuda.device(qkv.device):
+        nbytes = lib.hv_window_attn_bwd_workspace_bytes(B, H, W, C, heads, ws, _code(qkv))
+    return torch.empty((max(int(nbytes), 16),), dtype=torch.uint8, device=qkv.device)
+
+
+def window_attention_bwd_raw(qkv, out, dout, lse, bias_table, tau, mask, dqkv, dbias, dtau, workspace,
+                             B, H, W, C, heads, ws, shift):
+    """Enqueue hv_window_attn_bwd on the current stream; every tensor is caller-allocated."""
+    lib = _lib.load()
+    with torch.cuda.device(qkv.device):
+        rc = lib.hv_window_attn_bwd(_ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(bias_table), _ptr(tau), _ptr(mask),
+                                    mask.shape[0] if mask is not None else 0, _ptr(dqkv), _ptr(dbias), _ptr(dtau),
+                                    _ptr(workspace), workspace.numel(), B, H, W, C, heads, ws, shift, _code(qkv),
+                                    _stream(qkv.device))
+    check(rc, "hv_window_attn_bwd")
+
+
 class _WindowAttention(torch.autograd.Function):
     """out = fused shifted-window scaled-cosine attention(qkv); see hv_window_attn_fwd."""
 
     @staticmethod
     def forward(ctx, qkv, bias_table, tau, mask, B, H, W, C, heads, ws, shift):
         _need_cuda(qkv, "window_attention")
-        lib = _lib.load()
         qkv = qkv.contiguous()
         bias_table = _f32c(bias_table)
         tau = _f32c(tau)
-        mask_windows = 0
         if mask is not None:
             mask = _f32c(mask)
-            mask_windows = mask.shape[0]
         N = ws * ws
         nW = (H // ws) * (W // ws)
         out = torch.empty((B, H * W, C), dtype=qkv.dtype, device=qkv.device)
         lse = torch.empty((B * nW, heads, N), dtype=torch.float32, device=qkv.device)
-        with torch.cuda.device(qkv.device):
-            rc = _timed("attn_fwd", B * nW, qkv.device, lambda: lib.hv_window_attn_fwd(
-                _ptr(qkv), _ptr(bias_table), _ptr(tau), _ptr(mask), mask_windows, _ptr(out), _ptr(lse),
-                B, H, W, C, heads, ws, shift, _code(qkv), _stream(qkv.device)))
-        check(rc, "hv_window_attn_fwd")
+        _timed(f"attn_fwd/C{C}", B * nW, qkv.device, lambda: window_attention_fwd_raw(
+            qkv, bias_table, tau, mask, out, lse, B, H, W, C, heads, ws, shift))
         ctx.save_for_backward(qkv, out, lse, bias_table, tau, mask)
-        ctx.geom = (B, H, W, C, heads, ws, shift, mask_windows)
+        ctx.geom = (B, H, W, C, heads, ws, shift)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         qkv, out, lse, bias_table, tau, mask = ctx.saved_tensors
-        B, H, W, C, heads, ws, shift, mask_windows = ctx.geom
-        lib = _lib.load()
+        B, H, W, C, heads, ws, shift = ctx.geom
         dout = dout.contiguous()
         if dout.dtype != qkv.dtype:
             dout = dout.to(qkv.dtype)
         dqkv = torch.empty_like(qkv)
         dbias = torch.empty_like(bias_table)
         dtau = torch.empty_like(tau)
-        code = _code(qkv)
-        with torch.cuda.device(qkv.device):
-            nbytes = lib.hv_window_attn_bwd_workspace_bytes(B, H, W, C, heads, ws, code)
-            workspace = torch.empty((max(int(nbytes), 16),), dtype=torch.uint8, device=qkv.device)
-            rc = _timed("attn_bwd", B * (H // ws) * (W // ws), qkv.device, lambda: lib.hv_window_attn_bwd(
-                _ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(bias_table), _ptr(tau), _ptr(mask), mask_windows,
-                _ptr(dqkv), _ptr(dbias), _ptr(dtau), _ptr(workspace), workspace.numel(),
-                B, H, W, C, heads, ws, shift, code, _stream(qkv.device)))
-        check(rc, "hv_window_attn_bwd")
+        workspace = window_attention_bwd_workspace(qkv, B, H, W, C, heads, ws)
+        _timed(f"attn_bwd/C{C}", B * (H // ws) * (W // ws), qkv.device, lambda: window_attention_bwd_raw(
+            qkv, out, dout, lse, bias_table, tau, mask, dqkv, dbias, dtau, workspace, B, H, W, C, heads, ws, shift))
         return dqkv, dbias, dtau, None, None, None, None, None, None, None, None
 
 

@@ -192,8 +192,11 @@ class WindowAttention(nn.Module):
     def _bias_table(self):
         """((2Wh-1)(2Ww-1), heads): 16*sigmoid(cpb_mlp(coords)); sigmoid commutes with the gather
         of swinv2.py:236-246, which the kernel performs from the closed-form index."""
-        table = self.cpb_mlp(self.relative_coords_table).view(-1, self.num_heads)
-        return 16 * torch.sigmoid(table.float())
+        # 225..961 rows x (2 -> 512 -> heads): microscopic, so it is kept out of autocast (fp32 weights
+        # stay fp32); the reference lets autocast run it in bf16, which costs it ~5% on these gradients.
+        with torch.autocast(device_type=self.relative_coords_table.device.type, enabled=False):
+            table = self.cpb_mlp(self.relative_coords_table.to(self.cpb_mlp[0].weight.dtype))
+        return 16 * torch.sigmoid(table.view(-1, self.num_heads).float())
 
     def _tau(self):
         return torch.clamp(self.logit_scale.float(), max=self.logit_clamp_max.float()).exp().reshape(-1)

@@ -54,6 +54,30 @@ def _run(module, x, gy, dtype):
     return y.detach(), xin.grad.detach(), grads
 
 
+def _rel(a, b):
+    a, b = a.double().reshape(-1), b.double().reshape(-1)
+    n = b.norm().item()
+    return ((a - b).norm().item() / n) if n > 0 else (a - b).norm().item()
+
+
+def _bf16_autocast_errors(module, x, gy, res64):
+    """How far the *reference itself* lands from its fp64 result when run the way the reference's
+    training loop runs it (autocast, main.py:32 precision="amp"), here with bfloat16 on the CPU.
+    Stored in the manifest to calibrate the bf16 tolerance of hard cases (large logit_scale
+    amplifies the bf16 rounding of q/k by up to 100x before the softmax)."""
+    m = module.to(torch.float32)
+    m.zero_grad(set_to_none=True)
+    xin = x.clone().requires_grad_(True)
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        y = m(xin)
+    y.float().backward(gy)
+    y64, dx64, g64 = res64
+    out = {"y": _rel(y, y64), "dx": _rel(xin.grad, dx64)}
+    for k, p_ in m.named_parameters():
+        out["grad." + k] = _rel(p_.grad, g64[k])
+    return out
+
+
 def _pack(prefix, state, x, gy, res32, res64):
     out = {f"{prefix}x": x.numpy(), f"{prefix}gy": gy.numpy()}
     for k, v in state.items():
@@ -69,11 +93,14 @@ def _pack(prefix, state, x, gy, res32, res64):
     return out
 
 
-def block_case(ref, name, B, H, W, C, heads, ws, shift, seed, clamp_head=False, mlp_ratio=1.0):
+def block_case(ref, name, B, H, W, C, heads, ws, shift, seed, clamp_head=False, mlp_ratio=1.0, init_scale=False):
     gen = torch.Generator().manual_seed(seed)
     torch.manual_seed(seed)
     blk = ref.SwinTransformerBlock(C, (H, W), heads, window_size=ws, shift_size=shift, mlp_ratio=mlp_ratio)
     _randomise(blk, gen)
+    if init_scale:  # keep logit_scale at the reference's init value log(10) (swinv2.py:135-137)
+        with torch.no_grad():
+            blk.attn.logit_scale.fill_(float(torch.log(torch.tensor(10.0))))
     if clamp_head:  # one head above log(100): clamp active, zero logit_scale gradient (swinv2.py:230)
         with torch.no_grad():
             blk.attn.logit_scale[0] = 5.0
@@ -82,7 +109,8 @@ def block_case(ref, name, B, H, W, C, heads, ws, shift, seed, clamp_head=False, 
     gy = torch.randn(B, H * W, C, generator=gen)
     r32 = _run(blk, x, gy, torch.float32)
     r64 = _run(blk, x, gy, torch.float64)
-    meta = dict(kind="block", B=B, H=H, W=W, C=C, heads=heads, ws=ws, shift=shift, mlp_ratio=mlp_ratio,
+    bf16_err = _bf16_autocast_errors(blk, x, gy, r64)
+    meta = dict(kind="block", ref_bf16_autocast_rel_l2=bf16_err, init_scale=init_scale, B=B, H=H, W=W, C=C, heads=heads, ws=ws, shift=shift, mlp_ratio=mlp_ratio,
                 eff_ws=blk.window_size, eff_shift=blk.shift_size)
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **_pack("", state, x, gy, r32, r64))
     return meta
@@ -212,6 +240,8 @@ def main():
     c["block_ws8_rect_shift3"] = block_case(ref, "block_ws8_rect_shift3", 1, 16, 24, 96, 3, 8, 3, seed=3)
     c["block_res_le_ws"] = block_case(ref, "block_res_le_ws", 1, 8, 8, 128, 4, 8, 4, seed=4)
     c["block_ws16_shift8"] = block_case(ref, "block_ws16_shift8", 1, 32, 32, 64, 2, 16, 8, seed=5)
+    c["block_ws8_shift4_initscale"] = block_case(ref, "block_ws8_shift4_initscale", 1, 16, 16, 96, 3, 8, 4, seed=11,
+                                                 init_scale=True)
     c["block_ws4_shift2"] = block_case(ref, "block_ws4_shift2", 2, 8, 8, 32, 1, 4, 2, seed=6)
     c["window_attention_mask"] = window_attention_case(ref, "window_attention_mask", 4, 8, 64, 2, 2, seed=7)
     c["patch_merging"] = patch_merging_case(ref, "patch_merging", 2, 16, 16, 48, seed=8)
