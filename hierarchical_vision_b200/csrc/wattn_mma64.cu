@@ -7,11 +7,13 @@
 // order in HBM; the window gather / scatter is address arithmetic in the TMA producer and the epilogue.
 //
 // Structure (persistent CTAs, one per SM, HG heads per CTA):
-//   * TMA producer role (warp 0, before it starts computing a window): for the window that is
-//     kPrefetch iterations ahead, one `cp.async.bulk` (UBLKCP) per token row segment straight from the
-//     rolled image position into a padded shared-memory tile, completion counted on an mbarrier
-//     (multi-stage full/empty ring).  A dedicated 13th warp would cap every thread at 128 registers
-//     (4 warps on one SM sub-partition), so the role is folded into a compute warp instead.
+//   * 4 producer warps (one per SM sub-partition): per window, 16-byte `cp.async` (LDGSTS) copies straight
+//     from the rolled image position of every token into a padded, bank-conflict-free shared-memory
+//     tile; completion is signalled on an mbarrier (`cp.async.mbarrier.arrive.noinc`), multi-stage
+//     full/empty ring.  (Measured on B200, tools/probes/tma_probe.cu: `cp.async.bulk` requests of one
+//     token row segment (64-576 B) cost ~60-90 issue cycles each per warp and top out at 2.7 TB/s from
+//     one warp, while LDGSTS from 4 warps reaches the 6.7 TB/s copy ceiling; bulk/TMA only wins for
+//     >= 4 KB contiguous requests, which a partitioned head group of a rolled window never has.)
 //   * 4 compute warps per head: each owns 16 query rows (forward) / 16 key rows (backward) of one
 //     (window, head) and keeps S/P entirely in registers (mma.sync m16n8k16 bf16, fp32 accumulate);
 //     the position bias lives in registers (forward) or shared memory (backward) for the whole
@@ -35,9 +37,6 @@ constexpr int kOstBytes = 16 * kOstPitch;
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -46,20 +45,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(0x989680u)  // suspend-time hint: sleep in hardware instead of spinning
         : "memory");
     if (done) break;
-    if (++spins > (1u << 24)) __trap();  // a lost arrival must abort the kernel, never hang the GPU
+    if (++spins > (1u << 20)) __trap();  // a lost arrival must abort the kernel, never hang the GPU
   }
 }
-// TMA bulk copy global -> shared, completion counted in bytes on `bar`
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
+// 16-byte asynchronous copy global -> shared (LDGSTS, L2 only) and its mbarrier completion hook
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+// arrive on `bar` (without incrementing the pending count) once all prior cp.async of this thread landed
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -148,17 +149,18 @@ __device__ __forceinline__ void column_band_bits(int t_, int hi_thr, uint32_t& c
 }
 
 template <int HG> struct FwdCfg {
-  static constexpr int kWarps = 4 * HG;
-  static constexpr int kThreads = kWarps * 32;
+  static constexpr int kWarps = 4 * HG;             // compute warps
+  static constexpr int kProducers = 4;              // producer warps
+  static constexpr int kThreads = (kWarps + kProducers) * 32;
   static constexpr int kPitch = HG * 192 + 16;  // [q | k | v] x HG heads (64 B each) + 16 B pad: odd multiple of 16
+  static constexpr int kCpr = 12 * HG;          // 16-byte chunks per token row
+  static constexpr int kRowInstr = kWs * kCpr / 32;  // full-warp LDGSTS per window row (8 tokens)
   static constexpr int kStageBytes = kN * kPitch;
   static constexpr int kStages = 4;
-  static constexpr int kPrefetch = 2;  // windows in flight ahead of the one being computed
   static constexpr int kOffOst = kStages * kStageBytes;
   static constexpr int kOffCvec = kOffOst + kWarps * kOstBytes;  // [2][HG][64] float
   static constexpr int kOffBar = kOffCvec + 2 * HG * kN * 4;
   static constexpr int kSmem = kOffBar + 2 * kStages * 8;
-  static constexpr uint32_t kTxBytes = kN * HG * 192;
 };
 
 template <int HG>
@@ -177,39 +179,55 @@ wattn_mma64_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ b
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
-      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_full + 8 * s, Cfg::kProducers * 32);
       mbar_init(bar_empty + 8 * s, Cfg::kWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  // TMA producer role: issue the loads of iteration `pit` (window row cta + pit * ctas_per_group)
-  auto produce = [&](int pit) {
-    const int row = cta + pit * ctas_per_group;
-    if (row >= nrows) return;
-    const int s = pit % Cfg::kStages;
-    const uint32_t ph = (pit / Cfg::kStages) & 1;
-    mbar_wait(bar_empty + 8 * s, ph ^ 1);
-    if (lane == 0) mbar_expect_tx(bar_full + 8 * s, Cfg::kTxBytes);
-    __syncwarp();
-    const int b = row / g.nW, win = row - b * g.nW;
+  if (warp >= Cfg::kWarps) {
+    // ------------------------------------------------------------------ producer warps
+    // Each producer warp owns two of the window's eight token rows.  One window row = 8 tokens x kCpr
+    // 16-byte chunks = kRowInstr full-warp LDGSTS instructions; the (token, chunk) a lane handles in the
+    // m-th of them is the same for every window, so its shared/global offsets are precomputed once.
+    const int pw = warp - Cfg::kWarps;
+    int soff[Cfg::kRowInstr], gpack[Cfg::kRowInstr];
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int slot = lane + 32 * k;
-      const int64_t tok = window_slot_to_token(g, b, win, slot);
-      const bf16* src = qkv + tok * 3 * g.C + hgrp * (HG * 32);
-      const uint32_t dst = sbase + s * Cfg::kStageBytes + slot * Cfg::kPitch;
-      if (nHG == 1) {
-        bulk_g2s(dst, src, HG * 192, bar_full + 8 * s);
-      } else {
-#pragma unroll
-        for (int part = 0; part < 3; ++part) bulk_g2s(dst + part * (HG * 64), src + part * g.C, HG * 64, bar_full + 8 * s);
-      }
+    for (int m = 0; m < Cfg::kRowInstr; ++m) {
+      const int q = lane + 32 * m;
+      const int iw = q / Cfg::kCpr, c = q - iw * Cfg::kCpr;
+      const int part = c / (4 * HG), within = c - part * (4 * HG);
+      soff[m] = iw * Cfg::kPitch + c * 16;
+      gpack[m] = (part * g.C + hgrp * (HG * 32) + within * 8) | (iw << 24);
     }
-  };
-  if (warp == 0)
-    for (int pit = 0; pit < Cfg::kPrefetch; ++pit) produce(pit);
+    const int tok_stride = 3 * g.C;
+    int it = 0;
+    for (int row = cta; row < nrows; row += ctas_per_group, ++it) {
+      const int s = it % Cfg::kStages;
+      const uint32_t ph = (it / Cfg::kStages) & 1;
+      const int b = row / g.nW, win = row - b * g.nW;
+      const int wh = win / g.nWw, ww = win - wh * g.nWw;
+      const int col0 = ww * kWs + g.shift;
+      mbar_wait(bar_empty + 8 * s, ph ^ 1);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int ih = 2 * pw + r;
+        int irow = wh * kWs + g.shift + ih;
+        if (irow >= g.H) irow -= g.H;
+        const bf16* rowp = qkv + ((int64_t)b * g.H + irow) * g.W * tok_stride;
+        const uint32_t dst = sbase + s * Cfg::kStageBytes + ih * (kWs * Cfg::kPitch);
+#pragma unroll
+        for (int m = 0; m < Cfg::kRowInstr; ++m) {
+          int col = col0 + (gpack[m] >> 24);
+          if (col >= g.W) col -= g.W;
+          cp_async16(dst + soff[m], rowp + col * tok_stride + (gpack[m] & 0xffffff));
+        }
+      }
+      cp_async_arrive(bar_full + 8 * s);
+    }
+    return;
+  }
 
   // -------------------------------------------------------------------- compute warps
   const int hh = warp >> 2, wq = warp & 3;
@@ -244,7 +262,6 @@ wattn_mma64_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ b
     const uint32_t ph = (it / Cfg::kStages) & 1;
     const int b = row / g.nW, win = row - b * g.nW;
     const int wh = win / g.nWw, ww = win - wh * g.nWw;
-    if (warp == 0) produce(it + Cfg::kPrefetch);
     mbar_wait(bar_full + 8 * s, ph);
     const uint32_t st = sbase + s * Cfg::kStageBytes;
     const uint32_t qb = st + hh * 64, kb_ = st + HG * 64 + hh * 64, vb_ = st + 2 * HG * 64 + hh * 64;
@@ -371,8 +388,10 @@ wattn_mma64_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ b
 // =============================================================================== backward
 template <int HG> struct BwdCfg {
   static constexpr int kWarps = 4 * HG;
-  static constexpr int kThreads = kWarps * 32;
-  static constexpr int kPrefetch = 1;
+  static constexpr int kProducers = 4;
+  static constexpr int kThreads = (kWarps + kProducers) * 32;
+  static constexpr int kCpr = 20 * HG;          // 16-byte chunks per token row
+  static constexpr int kRowInstr = kWs * kCpr / 32;  // full-warp LDGSTS per window row (8 tokens)
   static constexpr int kPitch = HG * 320 + 16;  // [q | k | v | o | dO] x HG heads + pad: odd multiple of 16
   static constexpr int kLseOff = kN * kPitch;   // HG x 64 fp32 row log-sum-exp behind the token rows
   static constexpr int kStageBytes = kN * kPitch + HG * kN * 4;
@@ -386,7 +405,6 @@ template <int HG> struct BwdCfg {
   static constexpr int kOffTau = kOffVec + 2 * HG * kN * 4;     // per-warp d(tau) partials
   static constexpr int kOffBar = kOffTau + ((kWarps * 4 + 15) / 16) * 16;
   static constexpr int kSmem = kOffBar + 2 * kStages * 8;
-  static constexpr uint32_t kTxBytes = kN * HG * 320 + HG * kN * 4;
 };
 
 template <int HG>
@@ -407,7 +425,7 @@ wattn_mma64_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ou
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
-      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_full + 8 * s, Cfg::kProducers * 32);
       mbar_init(bar_empty + 8 * s, Cfg::kWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -424,39 +442,59 @@ wattn_mma64_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ou
   }
   __syncthreads();
 
-  // TMA producer role (warp 0): q,k,v,o,dO token segments and the row log-sum-exp of iteration `pit`
-  auto produce = [&](int pit) {
-    const int row = cta + pit * ctas_per_group;
-    if (row >= nrows) return;
-    const int s = pit % Cfg::kStages;
-    const uint32_t ph = (pit / Cfg::kStages) & 1;
-    mbar_wait(bar_empty + 8 * s, ph ^ 1);
-    const uint32_t full = bar_full + 8 * s;
-    const uint32_t st = sbase + s * Cfg::kStageBytes;
-    if (lane == 0) {
-      mbar_expect_tx(full, Cfg::kTxBytes);
-      bulk_g2s(st + Cfg::kLseOff, lse + ((int64_t)row * g.heads + hgrp * HG) * kN, HG * kN * 4, full);
+  if (warp >= Cfg::kWarps) {
+    // ------------------------------------------------------------------ producer warps
+    // q,k,v (from qkv), o (from out), dO (from dout) token segments and the row log-sum-exp of the window;
+    // same lane-constant chunk schedule as the forward producer (two window rows per producer warp).
+    const int pw = warp - Cfg::kWarps;
+    int soff[Cfg::kRowInstr], gpack[Cfg::kRowInstr];
+#pragma unroll
+    for (int m = 0; m < Cfg::kRowInstr; ++m) {
+      const int q = lane + 32 * m;
+      const int iw = q / Cfg::kCpr, c = q - iw * Cfg::kCpr;
+      const int part = c / (4 * HG), within = c - part * (4 * HG);
+      const int ch = hgrp * (HG * 32) + within * 8;
+      soff[m] = iw * Cfg::kPitch + c * 16;
+      // bits 0-23: element offset inside the token row; 24-26: token column; 28-29: 0 qkv / 1 out / 2 dout
+      gpack[m] = (part < 3 ? part * g.C + ch : ch) | (iw << 24) | ((part < 3 ? 0 : part - 2) << 28);
     }
-    __syncwarp();
-    const int b = row / g.nW, win = row - b * g.nW;
+    int it = 0;
+    for (int row = cta; row < nrows; row += ctas_per_group, ++it) {
+      const int s = it % Cfg::kStages;
+      const uint32_t ph = (it / Cfg::kStages) & 1;
+      const int b = row / g.nW, win = row - b * g.nW;
+      const int wh = win / g.nWw, ww = win - wh * g.nWw;
+      const int col0 = ww * kWs + g.shift;
+      mbar_wait(bar_empty + 8 * s, ph ^ 1);
+      const uint32_t st = sbase + s * Cfg::kStageBytes;
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int slot = lane + 32 * k;
-      const int64_t tok = window_slot_to_token(g, b, win, slot);
-      const bf16* src = qkv + tok * 3 * g.C + hgrp * (HG * 32);
-      const uint32_t dst = st + slot * Cfg::kPitch;
-      if (nHG == 1) {
-        bulk_g2s(dst, src, HG * 192, full);
-      } else {
+      for (int r = 0; r < 2; ++r) {
+        const int ih = 2 * pw + r;
+        int irow = wh * kWs + g.shift + ih;
+        if (irow >= g.H) irow -= g.H;
+        const int64_t rowtok = ((int64_t)b * g.H + irow) * g.W;
+        const bf16* pq = qkv + rowtok * 3 * g.C;
+        const bf16* po = out + rowtok * g.C;
+        const bf16* pg = dout + rowtok * g.C;
+        const uint32_t dst = st + ih * (kWs * Cfg::kPitch);
 #pragma unroll
-        for (int part = 0; part < 3; ++part) bulk_g2s(dst + part * (HG * 64), src + part * g.C, HG * 64, full);
+        for (int m = 0; m < Cfg::kRowInstr; ++m) {
+          int col = col0 + ((gpack[m] >> 24) & 7);
+          if (col >= g.W) col -= g.W;
+          const int sel = gpack[m] >> 28;
+          const bf16* base = sel == 0 ? pq : (sel == 1 ? po : pg);
+          const int stride = sel == 0 ? 3 * g.C : g.C;
+          cp_async16(dst + soff[m], base + col * stride + (gpack[m] & 0xffffff));
+        }
       }
-      bulk_g2s(dst + 3 * (HG * 64), out + tok * g.C + hgrp * (HG * 32), HG * 64, full);
-      bulk_g2s(dst + 4 * (HG * 64), dout + tok * g.C + hgrp * (HG * 32), HG * 64, full);
+      if (pw == 0) {
+        const float* lrow = lse + ((int64_t)row * g.heads + hgrp * HG) * kN;
+        for (int idx = lane; idx < HG * kN / 4; idx += 32) cp_async16(st + Cfg::kLseOff + idx * 16, lrow + idx * 4);
+      }
+      cp_async_arrive(bar_full + 8 * s);
     }
-  };
-  if (warp == 0)
-    for (int pit = 0; pit < Cfg::kPrefetch; ++pit) produce(pit);
+    return;
+  }
 
   // -------------------------------------------------------------------- compute warps
   const int hh = warp >> 2, wk = warp & 3;
@@ -491,7 +529,6 @@ wattn_mma64_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ou
     const uint32_t ph = (it / Cfg::kStages) & 1;
     const int b = row / g.nW, win = row - b * g.nW;
     const int wh = win / g.nWw, ww = win - wh * g.nWw;
-    if (warp == 0) produce(it + Cfg::kPrefetch);
     mbar_wait(bar_full + 8 * s, ph);
     const uint32_t st = sbase + s * Cfg::kStageBytes;
     const uint32_t qb = st + hh * 64, kb_ = st + HG * 64 + hh * 64, vb_ = st + 2 * HG * 64 + hh * 64;

@@ -18,6 +18,10 @@ pytestmark = pytest.mark.gpu
 
 DEV = "cuda:0"
 TOL = {torch.float32: 1e-3, torch.bfloat16: 2e-2}
+# d(tau) is one scalar per head that sums +/- terms ~100x larger than the result over every (window, i, j);
+# with bf16 storage of o / dO (D = dO.o) the cancellation leaves ~2^-9 * 100 relative noise.  The reference's
+# own bf16-autocast run misses its fp64 logit_scale gradient by 3-7e-2 on the same fixtures (manifest.json).
+DTAU_TOL = {torch.float32: 2e-3, torch.bfloat16: 1e-1}
 
 
 def _oracle_core(qkv, bias_table, tau, g, do, mask=None):
@@ -70,7 +74,7 @@ def test_window_attention_core(case, dtype):
     assert_close("out", out, o, tol)
     assert_close("dqkv", qkv.grad, dqkv, tol)
     assert_close("dbias_table", tab.grad, dtab, tol)
-    assert_close("dtau", tau.grad, dtau, 2 * tol)
+    assert_close("dtau", tau.grad, dtau, DTAU_TOL[dtype])
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
@@ -95,7 +99,7 @@ def test_window_attention_core_explicit_mask(case, dtype):
     assert_close("out", out, o, tol)
     assert_close("dqkv", qkv.grad, dqkv, tol)
     assert_close("dbias_table", tab.grad, dtab, tol)
-    assert_close("dtau", tau.grad, dtau, 2 * tol)
+    assert_close("dtau", tau.grad, dtau, DTAU_TOL[dtype])
 
 
 @pytest.mark.parametrize("dtype", [torch.float32])
@@ -157,15 +161,17 @@ def test_block_bf16_vs_reference_fixture(name, mode):
     # Tolerance: 2e-2 (4e-2 for tiny reduction gradients), widened -- only where the reference's OWN
     # bf16-autocast run misses its fp64 result by more than that -- to 1.5x the reference's miss
     # (recorded by oracle/make_goldens.py; large logit_scale amplifies bf16 q/k rounding up to 100x).
+    # pure_bf16 additionally rounds every PARAMETER to bf16 (the fixture's reference used fp32 ones): x2.5.
     ref_miss = meta["ref_bf16_autocast_rel_l2"]
-    assert_close("y", y, a["ref.y"], max(2e-2, 1.5 * ref_miss["y"]))
-    assert_close("dx", x.grad, a["ref.dx"], max(2e-2, 1.5 * ref_miss["dx"]))
+    slack = 2.5 if mode == "pure_bf16" else 1.0
+    assert_close("y", y, a["ref.y"], slack * max(2e-2, 1.5 * ref_miss["y"]))
+    assert_close("dx", x.grad, a["ref.dx"], slack * max(2e-2, 1.5 * ref_miss["dx"]))
     params = dict(blk.named_parameters())
     for k, v in a.items():
         if k.startswith("ref.grad."):
             name_ = k[len("ref.grad."):]
             base = 4e-2 if v.numel() <= 2048 else 2e-2  # biases / LN affine / logit_scale: reduction gradients
-            assert_close(k, params[name_].grad, v, max(base, 1.5 * ref_miss["grad." + name_]))
+            assert_close(k, params[name_].grad, v, slack * max(base, 1.5 * ref_miss["grad." + name_]))
 
 
 @pytest.mark.parametrize("name", ["patch_merging", "patch_merging_rect"])
