@@ -148,6 +148,33 @@ __device__ __forceinline__ void column_band_bits(int t_, int hi_thr, uint32_t& c
     }
 }
 
+// Window cursor of a persistent CTA: (image b, window win) advance by a fixed stride per iteration, so the
+// per-iteration update is two adds and a compare instead of integer divisions.
+struct Cursor {
+  int b, win, step_b, step_w;
+  __device__ __forceinline__ void init(const Geom& g, int first_row, int stride) {
+    b = first_row / g.nW; win = first_row - b * g.nW;
+    step_b = stride / g.nW; step_w = stride - step_b * g.nW;
+  }
+  __device__ __forceinline__ void next(const Geom& g) {
+    b += step_b; win += step_w;
+    if (win >= g.nW) { win -= g.nW; ++b; }
+  }
+};
+// Window (wh, ww) from win: exact for win < 2^16 (float reciprocal + 0.5 guard).
+__device__ __forceinline__ void window_rc(const Geom& g, float inv_nWw, int win, int& wh, int& ww) {
+  wh = __float2int_rz((win + 0.5f) * inv_nWw);
+  ww = win - wh * g.nWw;
+}
+// Token index of slot (ih, iw) of the window whose first shifted row/col are row0/col0.
+__device__ __forceinline__ int64_t tile_token(const Geom& g, int b, int row0, int col0, int ih, int iw) {
+  int r = row0 + ih; if (r >= g.H) r -= g.H;
+  int c = col0 + iw; if (c >= g.W) c -= g.W;
+  return ((int64_t)b * g.H + r) * g.W + c;
+}
+// 1 / max(sqrt(ss), 1e-12): F.normalize's denominator (reference swinv2.py:229)
+__device__ __forceinline__ float inv_norm(float ss) { return rsqrtf(fmaxf(ss, 1e-24f)); }
+
 template <int HG> struct FwdCfg {
   static constexpr int kWarps = 4 * HG;             // compute warps
   static constexpr int kProducers = 4;              // producer warps
@@ -202,20 +229,24 @@ wattn_mma64_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ b
       gpack[m] = (part * g.C + hgrp * (HG * 32) + within * 8) | (iw << 24);
     }
     const int tok_stride = 3 * g.C;
+    const float inv_nWw = 1.0f / (float)g.nWw;
+    Cursor cur;
+    cur.init(g, cta, ctas_per_group);
     int it = 0;
-    for (int row = cta; row < nrows; row += ctas_per_group, ++it) {
+    for (int row = cta; row < nrows; row += ctas_per_group, ++it, cur.next(g)) {
       const int s = it % Cfg::kStages;
       const uint32_t ph = (it / Cfg::kStages) & 1;
-      const int b = row / g.nW, win = row - b * g.nW;
-      const int wh = win / g.nWw, ww = win - wh * g.nWw;
+      int wh, ww;
+      window_rc(g, inv_nWw, cur.win, wh, ww);
       const int col0 = ww * kWs + g.shift;
-      mbar_wait(bar_empty + 8 * s, ph ^ 1);
+      if (pw == 0) mbar_wait(bar_empty + 8 * s, ph ^ 1);  // one waiter; the other producers sleep in the barrier
+      named_bar_sync(10, Cfg::kProducers * 32);
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         const int ih = 2 * pw + r;
         int irow = wh * kWs + g.shift + ih;
         if (irow >= g.H) irow -= g.H;
-        const bf16* rowp = qkv + ((int64_t)b * g.H + irow) * g.W * tok_stride;
+        const bf16* rowp = qkv + ((int64_t)cur.b * g.H + irow) * g.W * tok_stride;
         const uint32_t dst = sbase + s * Cfg::kStageBytes + ih * (kWs * Cfg::kPitch);
 #pragma unroll
         for (int m = 0; m < Cfg::kRowInstr; ++m) {
@@ -256,13 +287,19 @@ wattn_mma64_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ b
   const int arow = lane_row16(lane), acolb = (lane >> 4) * 16;
   const int brow = lane & 7, bcolb = (lane >> 3) * 16;
 
+  const float inv_nWw = 1.0f / (float)g.nWw;
+  const uint32_t ones_b = (g_ == 0) ? 0x3F803F80u : 0u;  // B fragment of a ones column: row sums of P by MMA
+  Cursor cur;
+  cur.init(g, cta, ctas_per_group);
   int it = 0;
-  for (int row = cta; row < nrows; row += ctas_per_group, ++it) {
+  for (int row = cta; row < nrows; row += ctas_per_group, ++it, cur.next(g)) {
     const int s = it % Cfg::kStages;
     const uint32_t ph = (it / Cfg::kStages) & 1;
-    const int b = row / g.nW, win = row - b * g.nW;
-    const int wh = win / g.nWw, ww = win - wh * g.nWw;
-    mbar_wait(bar_full + 8 * s, ph);
+    int wh, ww;
+    window_rc(g, inv_nWw, cur.win, wh, ww);
+    const int row0 = wh * kWs + g.shift, col0 = ww * kWs + g.shift;
+    if (wq == 0) mbar_wait(bar_full + 8 * s, ph);  // one waiter per head; the rest sleep in the barrier
+    named_bar_sync(1 + hh, 128);
     const uint32_t st = sbase + s * Cfg::kStageBytes;
     const uint32_t qb = st + hh * 64, kb_ = st + HG * 64 + hh * 64, vb_ = st + 2 * HG * 64 + hh * 64;
 
@@ -277,8 +314,8 @@ wattn_mma64_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ b
       s0 = quad_sum(s0);
       s1 = quad_sum(s1);
       if (t_ == 0) {
-        cvec[i0] = tau2 / fmaxf(sqrtf(s0), kNormEps);
-        cvec[i1] = tau2 / fmaxf(sqrtf(s1), kNormEps);
+        cvec[i0] = tau2 * inv_norm(s0);
+        cvec[i1] = tau2 * inv_norm(s1);
       }
     }
     named_bar_sync(1 + hh, 128);
@@ -289,8 +326,8 @@ wattn_mma64_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ b
     ldsm_x4(qb + (16 * wq + arow) * Cfg::kPitch + acolb + 32, qa[1]);
     float r0 = quad_sum(sq2(qa[0][0]) + sq2(qa[0][2]) + sq2(qa[1][0]) + sq2(qa[1][2]));
     float r1 = quad_sum(sq2(qa[0][1]) + sq2(qa[0][3]) + sq2(qa[1][1]) + sq2(qa[1][3]));
-    r0 = 1.0f / fmaxf(sqrtf(r0), kNormEps);
-    r1 = 1.0f / fmaxf(sqrtf(r1), kNormEps);
+    r0 = inv_norm(r0);
+    r1 = inv_norm(r1);
 
     // --- S = Q K^T (raw dot products)
     float acc[8][4];
@@ -334,18 +371,16 @@ wattn_mma64_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ b
     }
     mx0 = quad_max(mx0);
     mx1 = quad_max(mx1);
-    float l0 = 0.f, l1 = 0.f;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       acc[nt][0] = ex2(acc[nt][0] - mx0);
       acc[nt][1] = ex2(acc[nt][1] - mx0);
       acc[nt][2] = ex2(acc[nt][2] - mx1);
       acc[nt][3] = ex2(acc[nt][3] - mx1);
-      l0 += acc[nt][0] + acc[nt][1];
-      l1 += acc[nt][2] + acc[nt][3];
     }
-    // --- O = P V
-    float o[4][4];
+    // --- O = P V ; the row sums l = P 1 ride along as a fifth n-tile whose B operand is a ones column
+    float o[4][4], lacc[4];
+    lacc[0] = lacc[1] = lacc[2] = lacc[3] = 0.f;
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
 #pragma unroll
@@ -362,13 +397,15 @@ wattn_mma64_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ b
         mma_bf16(o[2 * half], pa, vf[0], vf[1]);
         mma_bf16(o[2 * half + 1], pa, vf[2], vf[3]);
       }
+      mma_bf16(lacc, pa, ones_b, ones_b);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_empty + 8 * s);  // the stage is free for the producer
 
-    l0 = quad_sum(l0);
-    l1 = quad_sum(l1);
-    const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+    // column 0 of the ones tile sits in the t == 0 lane of every quad
+    const float l0 = __shfl_sync(0xffffffffu, lacc[0], lane & ~3);
+    const float l1 = __shfl_sync(0xffffffffu, lacc[2], lane & ~3);
+    const float inv0 = __fdividef(1.0f, l0), inv1 = __fdividef(1.0f, l1);
     if (t_ == 0) {
       float* lp = lse + ((int64_t)row * g.heads + head) * kN;
       lp[i0] = (mx0 + __log2f(l0)) * kLn2;
@@ -379,8 +416,9 @@ wattn_mma64_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ b
       o[nt][0] *= inv0; o[nt][1] *= inv0;
       o[nt][2] *= inv1; o[nt][3] *= inv1;
     }
-    bf16* orow0 = out + window_slot_to_token(g, b, win, i0) * g.C + head * 32;
-    bf16* orow1 = out + window_slot_to_token(g, b, win, i1) * g.C + head * 32;
+    // own rows: slot i0 = (ih 2*wq, iw g_), i1 = (ih 2*wq+1, iw g_)
+    bf16* orow0 = out + tile_token(g, cur.b, row0, col0, 2 * wq, g_) * g.C + head * 32;
+    bf16* orow1 = out + tile_token(g, cur.b, row0, col0, 2 * wq + 1, g_) * g.C + head * 32;
     store_tile_bf16(o, ost, g_, t_, orow0, orow1);
   }
 }
@@ -447,44 +485,50 @@ wattn_mma64_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ou
     // q,k,v (from qkv), o (from out), dO (from dout) token segments and the row log-sum-exp of the window;
     // same lane-constant chunk schedule as the forward producer (two window rows per producer warp).
     const int pw = warp - Cfg::kWarps;
-    int soff[Cfg::kRowInstr], gpack[Cfg::kRowInstr];
+    // per lane-chunk: shared offset | token column, the tensor it reads (base pointer incl. channel offset)
+    // and that tensor's token stride, so that one chunk costs a wrap test, one wide multiply-add and the copy
+    int spack[Cfg::kRowInstr], stride_b[Cfg::kRowInstr];
+    const char* gbase[Cfg::kRowInstr];
 #pragma unroll
     for (int m = 0; m < Cfg::kRowInstr; ++m) {
       const int q = lane + 32 * m;
       const int iw = q / Cfg::kCpr, c = q - iw * Cfg::kCpr;
       const int part = c / (4 * HG), within = c - part * (4 * HG);
       const int ch = hgrp * (HG * 32) + within * 8;
-      soff[m] = iw * Cfg::kPitch + c * 16;
-      // bits 0-23: element offset inside the token row; 24-26: token column; 28-29: 0 qkv / 1 out / 2 dout
-      gpack[m] = (part < 3 ? part * g.C + ch : ch) | (iw << 24) | ((part < 3 ? 0 : part - 2) << 28);
+      spack[m] = (iw * Cfg::kPitch + c * 16) | (iw << 24);
+      if (part < 3) {
+        gbase[m] = reinterpret_cast<const char*>(qkv + part * g.C + ch);
+        stride_b[m] = 6 * g.C;
+      } else {
+        gbase[m] = reinterpret_cast<const char*>((part == 3 ? out : dout) + ch);
+        stride_b[m] = 2 * g.C;
+      }
     }
+    const float inv_nWw = 1.0f / (float)g.nWw;
+    Cursor cur;
+    cur.init(g, cta, ctas_per_group);
     int it = 0;
-    for (int row = cta; row < nrows; row += ctas_per_group, ++it) {
+    for (int row = cta; row < nrows; row += ctas_per_group, ++it, cur.next(g)) {
       const int s = it % Cfg::kStages;
       const uint32_t ph = (it / Cfg::kStages) & 1;
-      const int b = row / g.nW, win = row - b * g.nW;
-      const int wh = win / g.nWw, ww = win - wh * g.nWw;
+      int wh, ww;
+      window_rc(g, inv_nWw, cur.win, wh, ww);
       const int col0 = ww * kWs + g.shift;
-      mbar_wait(bar_empty + 8 * s, ph ^ 1);
+      if (pw == 0) mbar_wait(bar_empty + 8 * s, ph ^ 1);  // one waiter; the other producers sleep in the barrier
+      named_bar_sync(10, Cfg::kProducers * 32);
       const uint32_t st = sbase + s * Cfg::kStageBytes;
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         const int ih = 2 * pw + r;
         int irow = wh * kWs + g.shift + ih;
         if (irow >= g.H) irow -= g.H;
-        const int64_t rowtok = ((int64_t)b * g.H + irow) * g.W;
-        const bf16* pq = qkv + rowtok * 3 * g.C;
-        const bf16* po = out + rowtok * g.C;
-        const bf16* pg = dout + rowtok * g.C;
+        const int rowtok = (cur.b * g.H + irow) * g.W;  // token index < 2^31 (checked on the host)
         const uint32_t dst = st + ih * (kWs * Cfg::kPitch);
 #pragma unroll
         for (int m = 0; m < Cfg::kRowInstr; ++m) {
-          int col = col0 + ((gpack[m] >> 24) & 7);
+          int col = col0 + (spack[m] >> 24);
           if (col >= g.W) col -= g.W;
-          const int sel = gpack[m] >> 28;
-          const bf16* base = sel == 0 ? pq : (sel == 1 ? po : pg);
-          const int stride = sel == 0 ? 3 * g.C : g.C;
-          cp_async16(dst + soff[m], base + col * stride + (gpack[m] & 0xffffff));
+          cp_async16(dst + (spack[m] & 0xffffff), gbase[m] + (int64_t)(rowtok + col) * stride_b[m]);
         }
       }
       if (pw == 0) {
@@ -523,13 +567,21 @@ wattn_mma64_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ou
   for (int nt = 0; nt < 8; ++nt) dbias[nt][0] = dbias[nt][1] = dbias[nt][2] = dbias[nt][3] = 0.f;
   float dtau_acc = 0.f;
 
+  const float inv_nWw = 1.0f / (float)g.nWw;
+  Cursor cur;
+  cur.init(g, cta, ctas_per_group);
   int it = 0;
-  for (int row = cta; row < nrows; row += ctas_per_group, ++it) {
+  for (int row = cta; row < nrows; row += ctas_per_group, ++it, cur.next(g)) {
     const int s = it % Cfg::kStages;
     const uint32_t ph = (it / Cfg::kStages) & 1;
-    const int b = row / g.nW, win = row - b * g.nW;
-    const int wh = win / g.nWw, ww = win - wh * g.nWw;
-    mbar_wait(bar_full + 8 * s, ph);
+    int wh, ww;
+    window_rc(g, inv_nWw, cur.win, wh, ww);
+    const int row0 = wh * kWs + g.shift, col0 = ww * kWs + g.shift;
+    // own token rows: slot j0 = (ih 2*wk, iw g_), j1 = (ih 2*wk+1, iw g_)
+    const int64_t tok0 = tile_token(g, cur.b, row0, col0, 2 * wk, g_);
+    const int64_t tok1 = tile_token(g, cur.b, row0, col0, 2 * wk + 1, g_);
+    if (wk == 0) mbar_wait(bar_full + 8 * s, ph);  // one waiter per head; the rest sleep in the barrier
+    named_bar_sync(1 + hh, 128);
     const uint32_t st = sbase + s * Cfg::kStageBytes;
     const uint32_t qb = st + hh * 64, kb_ = st + HG * 64 + hh * 64, vb_ = st + 2 * HG * 64 + hh * 64;
     const uint32_t ob = st + 3 * HG * 64 + hh * 64, gb = st + 4 * HG * 64 + hh * 64;
@@ -544,15 +596,15 @@ wattn_mma64_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ou
       ldsm_x4(kb_ + own + 32, ka[1]);
       c0 = quad_sum(sq2(ka[0][0]) + sq2(ka[0][2]) + sq2(ka[1][0]) + sq2(ka[1][2]));
       c1 = quad_sum(sq2(ka[0][1]) + sq2(ka[0][3]) + sq2(ka[1][1]) + sq2(ka[1][3]));
-      c0 = 1.0f / fmaxf(sqrtf(c0), kNormEps);
-      c1 = 1.0f / fmaxf(sqrtf(c1), kNormEps);
+      c0 = inv_norm(c0);
+      c1 = inv_norm(c1);
       uint32_t qa[2][4];
       ldsm_x4(qb + own, qa[0]);
       ldsm_x4(qb + own + 32, qa[1]);
       r0 = quad_sum(sq2(qa[0][0]) + sq2(qa[0][2]) + sq2(qa[1][0]) + sq2(qa[1][2]));
       r1 = quad_sum(sq2(qa[0][1]) + sq2(qa[0][3]) + sq2(qa[1][1]) + sq2(qa[1][3]));
-      r0 = 1.0f / fmaxf(sqrtf(r0), kNormEps);
-      r1 = 1.0f / fmaxf(sqrtf(r1), kNormEps);
+      r0 = inv_norm(r0);
+      r1 = inv_norm(r1);
       uint32_t oa[4], ga[4];
       float d0 = 0.f, d1 = 0.f;
 #pragma unroll
@@ -633,9 +685,7 @@ wattn_mma64_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ou
           mma_bf16(dv[2 * half], pa[ks], gf[0], gf[1]);
           mma_bf16(dv[2 * half + 1], pa[ks], gf[2], gf[3]);
         }
-      bf16* row0 = dqkv + window_slot_to_token(g, b, win, j0) * 3 * g.C + 2 * g.C + head * 32;
-      bf16* row1 = dqkv + window_slot_to_token(g, b, win, j1) * 3 * g.C + 2 * g.C + head * 32;
-      store_tile_bf16(dv, ost, g_, t_, row0, row1);
+      store_tile_bf16(dv, ost, g_, t_, dqkv + tok0 * 3 * g.C + 2 * g.C + head * 32, dqkv + tok1 * 3 * g.C + 2 * g.C + head * 32);
     }
     // --- dP^T = V dO^T, dS^T = P^T o (dP^T - D)
 #pragma unroll
@@ -695,9 +745,7 @@ wattn_mma64_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ou
         dk[2 * ks][2] -= e1 * bf16lo_to_f32(ka[ks][1]);     dk[2 * ks][3] -= e1 * bf16hi_to_f32(ka[ks][1]);
         dk[2 * ks + 1][2] -= e1 * bf16lo_to_f32(ka[ks][3]); dk[2 * ks + 1][3] -= e1 * bf16hi_to_f32(ka[ks][3]);
       }
-      bf16* row0 = dqkv + window_slot_to_token(g, b, win, j0) * 3 * g.C + g.C + head * 32;
-      bf16* row1 = dqkv + window_slot_to_token(g, b, win, j1) * 3 * g.C + g.C + head * 32;
-      store_tile_bf16(dk, ost, g_, t_, row0, row1);
+      store_tile_bf16(dk, ost, g_, t_, dqkv + tok0 * 3 * g.C + g.C + head * 32, dqkv + tok1 * 3 * g.C + g.C + head * 32);
     }
     named_bar_sync(1 + hh, 128);  // dS~ of all 64 keys is in shared memory
 
@@ -742,9 +790,7 @@ wattn_mma64_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ou
         dq[2 * ks][2] -= e1 * bf16lo_to_f32(qa[ks][1]);     dq[2 * ks][3] -= e1 * bf16hi_to_f32(qa[ks][1]);
         dq[2 * ks + 1][2] -= e1 * bf16lo_to_f32(qa[ks][3]); dq[2 * ks + 1][3] -= e1 * bf16hi_to_f32(qa[ks][3]);
       }
-      bf16* row0 = dqkv + window_slot_to_token(g, b, win, j0) * 3 * g.C + head * 32;
-      bf16* row1 = dqkv + window_slot_to_token(g, b, win, j1) * 3 * g.C + head * 32;
-      store_tile_bf16(dq, ost, g_, t_, row0, row1);
+      store_tile_bf16(dq, ost, g_, t_, dqkv + tok0 * 3 * g.C + head * 32, dqkv + tok1 * 3 * g.C + head * 32);
     }
   }
 
@@ -843,7 +889,9 @@ int launch_bwd(const Geom& g, const void* qkv, const void* out, const void* dout
 }  // namespace
 
 bool wattn_mma64_supported(const Geom& g, int dtype) {
-  return dtype == HV_BF16 && g.ws == kWs && g.d == 32 && g.C % 32 == 0;
+  // token index must fit 31 bits and the per-image window count 16 bits (Cursor / window_rc arithmetic)
+  return dtype == HV_BF16 && g.ws == kWs && g.d == 32 && g.C % 32 == 0 && g.nW < 65536 &&
+         (int64_t)g.B * g.H * g.W < (int64_t(1) << 31);
 }
 
 size_t wattn_mma64_bwd_workspace_bytes(const Geom& g) {
