@@ -48,9 +48,9 @@ PROFILE_EVENTS = None
 LAUNCH_COUNT = 0
 
 
-def _timed(tag, windows, stream_device, fn):
+def _timed(tag, windows, stream_device, fn, kernels=1):
     global LAUNCH_COUNT
-    LAUNCH_COUNT += 1
+    LAUNCH_COUNT += kernels
     if PROFILE_EVENTS is None:
         return fn()
     s = torch.cuda.current_stream(stream_device)
@@ -125,7 +125,8 @@ class _WindowAttention(torch.autograd.Function):
         dtau = torch.empty_like(tau)
         workspace = window_attention_bwd_workspace(qkv, B, H, W, C, heads, ws)
         _timed(f"attn_bwd/C{C}", B * (H // ws) * (W // ws), qkv.device, lambda: window_attention_bwd_raw(
-            qkv, out, dout, lse, bias_table, tau, mask, dqkv, dbias, dtau, workspace, B, H, W, C, heads, ws, shift))
+            qkv, out, dout, lse, bias_table, tau, mask, dqkv, dbias, dtau, workspace, B, H, W, C, heads, ws, shift),
+            kernels=2)  # backward kernel + partial-sum reduction kernel
         return dqkv, dbias, dtau, None, None, None, None, None, None, None, None
 
 
