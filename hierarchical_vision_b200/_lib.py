@@ -30,9 +30,9 @@ SIGNATURES = {
     "hv_window_attn_bwd_workspace_bytes": (_S, [_I, _I, _I, _I, _I, _I, _I]),
     "hv_window_attn_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _S,
                                 _I, _I, _I, _I, _I, _I, _I, _I, _P]),
-    "hv_ln_residual_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _L, _F, _I, _I, _P]),
+    "hv_ln_residual_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _L, _F, _I, _I, _P]),
     "hv_ln_residual_bwd_workspace_bytes": (_S, [_L, _I]),
-    "hv_ln_residual_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _S, _L, _I, _L, _I, _I, _P]),
+    "hv_ln_residual_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _S, _L, _I, _L, _I, _I, _P]),
     "hv_patch_merge_gather_fwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "hv_patch_merge_gather_bwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
 }

@@ -20,12 +20,13 @@ int wattn_mma64_bwd(const Geom& g, const void* qkv, const void* out, const void*
                     const float* bias_table, const float* tau, const float* mask, int mask_windows, void* dqkv,
                     float* dbias_table, float* dtau, void* workspace, size_t workspace_bytes, cudaStream_t st);
 size_t ln_residual_bwd_workspace_bytes(int64_t rows, int C);
-int ln_residual_fwd(const void* y, const void* shortcut, const float* gamma, const float* beta, const float* keep_scale,
-                    void* out, float* mean, float* rstd, int64_t rows, int C, int64_t rows_per_sample, float eps,
-                    int y_dtype, int res_dtype, cudaStream_t st);
-int ln_residual_bwd(const void* dout, const void* y, const float* gamma, const float* mean, const float* rstd,
-                    const float* keep_scale, void* dy, float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
-                    int64_t rows, int C, int64_t rows_per_sample, int y_dtype, int res_dtype, cudaStream_t st);
+int ln_residual_fwd(const void* y, const void* shortcut, const float* gamma, const float* beta, const float* bias,
+                    const float* keep_scale, void* out, float* mean, float* rstd, int64_t rows, int C,
+                    int64_t rows_per_sample, float eps, int y_dtype, int res_dtype, cudaStream_t st);
+int ln_residual_bwd(const void* dout, const void* y, const float* gamma, const float* bias, const float* mean,
+                    const float* rstd, const float* keep_scale, void* dy, float* dgamma, float* dbeta, float* dbias,
+                    void* workspace, size_t workspace_bytes, int64_t rows, int C, int64_t rows_per_sample, int y_dtype,
+                    int res_dtype, cudaStream_t st);
 int patch_merge_gather_fwd(const void* x, void* out, int B, int H, int W, int C, int dtype, cudaStream_t st);
 int patch_merge_gather_bwd(const void* dout, void* dx, int B, int H, int W, int C, int dtype, cudaStream_t st);
 
@@ -197,27 +198,27 @@ int hv_window_attn_bwd(const void* qkv, const void* out, const void* dout, const
   return wattn_generic_bwd(g, dtype, qkv, out, dout, lse, bias_table, tau, mask, mask_windows, dqkv, dbias_table, dtau, st);
 }
 
-int hv_ln_residual_fwd(const void* y, const void* shortcut, const float* gamma, const float* beta, const float* keep_scale,
-                       void* out, float* mean, float* rstd, int64_t rows, int C, int64_t rows_per_sample, float eps,
-                       int y_dtype, int res_dtype, void* stream) {
+int hv_ln_residual_fwd(const void* y, const void* shortcut, const float* gamma, const float* beta, const float* bias,
+                       const float* keep_scale, void* out, float* mean, float* rstd, int64_t rows, int C,
+                       int64_t rows_per_sample, float eps, int y_dtype, int res_dtype, void* stream) {
   if (!y || !gamma || !beta || !out || !mean || !rstd) HV_FAIL(HV_ERR_NULL, "hv_ln_residual_fwd: NULL argument");
   int rc = check_device_arch();
   if (rc) return rc;
-  return ln_residual_fwd(y, shortcut, gamma, beta, keep_scale, out, mean, rstd, rows, C, rows_per_sample, eps, y_dtype,
-                         res_dtype, static_cast<cudaStream_t>(stream));
+  return ln_residual_fwd(y, shortcut, gamma, beta, bias, keep_scale, out, mean, rstd, rows, C, rows_per_sample, eps,
+                         y_dtype, res_dtype, static_cast<cudaStream_t>(stream));
 }
 
 size_t hv_ln_residual_bwd_workspace_bytes(int64_t rows, int C) { return ln_residual_bwd_workspace_bytes(rows, C); }
 
-int hv_ln_residual_bwd(const void* dout, const void* y, const float* gamma, const float* mean, const float* rstd,
-                       const float* keep_scale, void* dy, float* dgamma, float* dbeta, void* workspace,
-                       size_t workspace_bytes, int64_t rows, int C, int64_t rows_per_sample, int y_dtype, int res_dtype,
-                       void* stream) {
+int hv_ln_residual_bwd(const void* dout, const void* y, const float* gamma, const float* bias, const float* mean,
+                       const float* rstd, const float* keep_scale, void* dy, float* dgamma, float* dbeta, float* dbias,
+                       void* workspace, size_t workspace_bytes, int64_t rows, int C, int64_t rows_per_sample, int y_dtype,
+                       int res_dtype, void* stream) {
   if (!dout || !y || !gamma || !mean || !rstd || !dy || !dgamma || !dbeta) HV_FAIL(HV_ERR_NULL, "hv_ln_residual_bwd: NULL argument");
   int rc = check_device_arch();
   if (rc) return rc;
-  return ln_residual_bwd(dout, y, gamma, mean, rstd, keep_scale, dy, dgamma, dbeta, workspace, workspace_bytes, rows, C,
-                         rows_per_sample, y_dtype, res_dtype, static_cast<cudaStream_t>(stream));
+  return ln_residual_bwd(dout, y, gamma, bias, mean, rstd, keep_scale, dy, dgamma, dbeta, dbias, workspace, workspace_bytes,
+                         rows, C, rows_per_sample, y_dtype, res_dtype, static_cast<cudaStream_t>(stream));
 }
 
 int hv_patch_merge_gather_fwd(const void* x, void* out, int B, int H, int W, int C, int dtype, void* stream) {

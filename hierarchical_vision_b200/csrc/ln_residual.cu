@@ -1,52 +1,85 @@
-// Res-post-norm: out = shortcut + keep_scale[sample] * LayerNorm(y)   (reference swinv2.py:431, 434)
-// and, with shortcut == nullptr, the plain LayerNorm of PatchMerging (swinv2.py:494).
+// Res-post-norm: out = shortcut + keep_scale[sample] * LayerNorm(y + bias)   (reference swinv2.py:431, 434;
+// `bias` is the bias of the Linear that produced y -- attn.proj.bias / mlp.fc2.bias, swinv2.py:262, 64 -- folded
+// in here so that its gradient falls out of this kernel's backward instead of a separate column reduction)
+// and, with shortcut == nullptr, the plain LayerNorm of PatchMerging / PatchEmbed (swinv2.py:494, 656).
 //
-// HBM-bound streaming kernels: a row (token) is owned by a group of GS lanes, every lane moves
-// K 16-byte vectors of y per row, statistics are reduced with warp shuffles, gamma/beta live in
-// registers for the lifetime of the thread.  Backward keeps its d-gamma / d-beta partial sums in
-// registers across all the rows a thread visits and reduces them once per CTA (deterministic
-// two-stage reduction through a workspace; no atomics).
+// HBM-bound streaming kernels.  A row (token) is owned by a group of GS lanes; every lane moves K 16-byte
+// vectors of y per row and R rows per loop iteration (all loads issued before the first use, so each lane
+// keeps R*K*(2..3) independent 16-byte requests in flight); statistics are reduced with warp shuffles;
+// gamma/beta/bias live in registers for the lifetime of the thread.  Backward keeps its d-gamma / d-beta /
+// d-bias partial sums in registers across all the rows a thread visits, folds them once per CTA and a second
+// tiny kernel sums the per-CTA rows (deterministic two-stage reduction; no global atomics).
 #include "hv_common.cuh"
 
 namespace hv {
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kFinalizeRows = 8;  // row-groups per finalize block
 
-template <typename T, int VE> struct RowVec {  // VE consecutive elements of T <-> fp32 registers
-  static constexpr int kVecs = VE * sizeof(T) / 16;
-  __device__ __forceinline__ static void load(const T* p, float (&f)[VE]) {
-#pragma unroll
-    for (int v = 0; v < kVecs; ++v) {
-      float t[Vec16<T>::n];
-      Vec16<T>::load(p + v * Vec16<T>::n, t);
-#pragma unroll
-      for (int e = 0; e < Vec16<T>::n; ++e) f[v * Vec16<T>::n + e] = t[e];
-    }
+// One 16-byte global vector kept PACKED in registers (4 regs) until it is needed as fp32: keeps the
+// register footprint of the R*K vectors a lane has in flight small enough for 3-4 CTAs per SM.
+template <typename T> struct Pk;
+template <> struct Pk<float> {
+  static constexpr int n = 4;
+  float4 v;
+  __device__ __forceinline__ void load(const float* p) { v = *reinterpret_cast<const float4*>(p); }
+  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = v; }
+  __device__ __forceinline__ void zero() { v = make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ void get(float* f) const { f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w; }
+  __device__ __forceinline__ void set(const float* f) { v = make_float4(f[0], f[1], f[2], f[3]); }
+};
+template <> struct Pk<bf16> {
+  static constexpr int n = 8;
+  uint4 v;
+  __device__ __forceinline__ void load(const bf16* p) { v = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void store(bf16* p) const { *reinterpret_cast<uint4*>(p) = v; }
+  __device__ __forceinline__ void zero() { v = make_uint4(0u, 0u, 0u, 0u); }
+  __device__ __forceinline__ void get(float* f) const {
+    f[0] = bf16lo_to_f32(v.x); f[1] = bf16hi_to_f32(v.x); f[2] = bf16lo_to_f32(v.y); f[3] = bf16hi_to_f32(v.y);
+    f[4] = bf16lo_to_f32(v.z); f[5] = bf16hi_to_f32(v.z); f[6] = bf16lo_to_f32(v.w); f[7] = bf16hi_to_f32(v.w);
   }
-  __device__ __forceinline__ static void store(T* p, const float (&f)[VE]) {
+  __device__ __forceinline__ void set(const float* f) {
+    v = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+  }
+};
+// VE consecutive elements of T (VE = elements of the *y* vector; T may be wider than y's type)
+template <typename T, int VE> struct PkRow {
+  static constexpr int kVecs = VE / Pk<T>::n;
+  Pk<T> p[kVecs];
+  __device__ __forceinline__ void load(const T* q) {
 #pragma unroll
-    for (int v = 0; v < kVecs; ++v) {
-      float t[Vec16<T>::n];
+    for (int i = 0; i < kVecs; ++i) p[i].load(q + i * Pk<T>::n);
+  }
+  __device__ __forceinline__ void store(T* q) const {
 #pragma unroll
-      for (int e = 0; e < Vec16<T>::n; ++e) t[e] = f[v * Vec16<T>::n + e];
-      Vec16<T>::store(p + v * Vec16<T>::n, t);
-    }
+    for (int i = 0; i < kVecs; ++i) p[i].store(q + i * Pk<T>::n);
+  }
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int i = 0; i < kVecs; ++i) p[i].zero();
+  }
+  __device__ __forceinline__ void get(float (&f)[VE]) const {
+#pragma unroll
+    for (int i = 0; i < kVecs; ++i) p[i].get(f + i * Pk<T>::n);
+  }
+  __device__ __forceinline__ void set(const float (&f)[VE]) {
+#pragma unroll
+    for (int i = 0; i < kVecs; ++i) p[i].set(f + i * Pk<T>::n);
   }
 };
 
-template <typename TY, typename TR, int GS, int K>
-__global__ void __launch_bounds__(kThreads) ln_residual_fwd_kernel(const TY* __restrict__ y, const TR* __restrict__ shortcut,
-                                                                   const float* __restrict__ gamma,
-                                                                   const float* __restrict__ beta,
-                                                                   const float* __restrict__ keep_scale, TR* __restrict__ out,
-                                                                   float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                                                                   int64_t rows, int C, int64_t rows_per_sample, float eps) {
+template <typename TY, typename TR, int GS, int K, int R, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
+ln_residual_fwd_kernel(const TY* __restrict__ y, const TR* __restrict__ shortcut, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, const float* __restrict__ bias, const float* __restrict__ keep_scale,
+                       TR* __restrict__ out, float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t rows, int C,
+                       int64_t rows_per_sample, float eps) {
   constexpr int VE = 16 / sizeof(TY);
-  constexpr int RPW = 32 / GS;  // rows per warp per iteration
+  constexpr int RPW = 32 / GS;  // rows per warp per sub-iteration
   const int lane = threadIdx.x & 31, gl = lane % GS, gi = lane / GS;
   const int vpr = C / VE;  // vectors per row
-  float gam[K][VE], bet[K][VE];
+  float gam[K][VE], bet[K][VE], bia[K][VE];
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     const int v = gl + k * GS;
@@ -54,177 +87,238 @@ __global__ void __launch_bounds__(kThreads) ln_residual_fwd_kernel(const TY* __r
     for (int e = 0; e < VE; ++e) {
       gam[k][e] = (v < vpr) ? gamma[v * VE + e] : 0.f;
       bet[k][e] = (v < vpr) ? beta[v * VE + e] : 0.f;
+      bia[k][e] = (v < vpr && bias != nullptr) ? bias[v * VE + e] : 0.f;
     }
   }
   const int64_t warp_global = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   const int64_t warp_stride = (int64_t)gridDim.x * (kThreads / 32);
   const float inv_c = 1.0f / (float)C;
-  for (int64_t r0 = warp_global * RPW; r0 < rows; r0 += warp_stride * RPW) {
-    const int64_t r = r0 + gi;
-    const bool row_ok = r < rows;
-    float x[K][VE];
-    float sum = 0.f;
+  for (int64_t r0 = warp_global * (RPW * R); r0 < rows; r0 += warp_stride * (RPW * R)) {
+    PkRow<TY, VE> xv[R][K];
+    PkRow<TR, VE> rv[R][K];
+    // phase 1: every y vector of the R rows in flight at once
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const int v = gl + k * GS;
-      if (row_ok && v < vpr) {
-        RowVec<TY, VE>::load(y + r * C + v * VE, x[k]);
-      } else {
+    for (int rr = 0; rr < R; ++rr) {
+      const int64_t r = r0 + rr * RPW + gi;
 #pragma unroll
-        for (int e = 0; e < VE; ++e) x[k][e] = 0.f;
+      for (int k = 0; k < K; ++k) {
+        const int v = gl + k * GS;
+        if (r < rows && v < vpr) xv[rr][k].load(y + r * C + v * VE);
+        else xv[rr][k].zero();
       }
-#pragma unroll
-      for (int e = 0; e < VE; ++e) sum += x[k][e];
     }
-    const float mean = group_sum<GS>(sum) * inv_c;
-    float sq = 0.f;
+    // phase 2: the shortcut vectors follow immediately (independent of phase 1's data)
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const int v = gl + k * GS;
-      if (v < vpr) {
+    for (int rr = 0; rr < R; ++rr) {
+      const int64_t r = r0 + rr * RPW + gi;
 #pragma unroll
-        for (int e = 0; e < VE; ++e) {
-          const float dlt = x[k][e] - mean;
-          sq = fmaf(dlt, dlt, sq);
+      for (int k = 0; k < K; ++k) {
+        const int v = gl + k * GS;
+        if (shortcut != nullptr && r < rows && v < vpr) rv[rr][k].load(shortcut + r * C + v * VE);
+        else rv[rr][k].zero();
+      }
+    }
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) {
+      const int64_t r = r0 + rr * RPW + gi;
+      const bool row_ok = r < rows;
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        float x[VE];
+        xv[rr][k].get(x);
+#pragma unroll
+        for (int e = 0; e < VE; ++e) sum += x[e] + bia[k][e];
+      }
+      const float mean = group_sum<GS>(sum) * inv_c;
+      float sq = 0.f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        if (gl + k * GS < vpr) {
+          float x[VE];
+          xv[rr][k].get(x);
+#pragma unroll
+          for (int e = 0; e < VE; ++e) {
+            const float dlt = x[e] + bia[k][e] - mean;
+            sq = fmaf(dlt, dlt, sq);
+          }
         }
       }
-    }
-    const float rstd = rsqrtf(group_sum<GS>(sq) * inv_c + eps);
-    const float ks = (keep_scale != nullptr && row_ok) ? keep_scale[r / rows_per_sample] : 1.0f;
+      const float rstd = rsqrtf(group_sum<GS>(sq) * inv_c + eps);
+      const float ks = (keep_scale != nullptr && row_ok) ? keep_scale[r / rows_per_sample] : 1.0f;
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const int v = gl + k * GS;
-      if (row_ok && v < vpr) {
-        float res[VE];
-        if (shortcut != nullptr) {
-          RowVec<TR, VE>::load(shortcut + r * C + v * VE, res);
-        } else {
+      for (int k = 0; k < K; ++k) {
+        const int v = gl + k * GS;
+        if (row_ok && v < vpr) {
+          float x[VE], res[VE];
+          xv[rr][k].get(x);
+          rv[rr][k].get(res);
 #pragma unroll
-          for (int e = 0; e < VE; ++e) res[e] = 0.f;
+          for (int e = 0; e < VE; ++e) res[e] += ks * fmaf((x[e] + bia[k][e] - mean) * rstd, gam[k][e], bet[k][e]);
+          PkRow<TR, VE> o;
+          o.set(res);
+          o.store(out + r * C + v * VE);
         }
-#pragma unroll
-        for (int e = 0; e < VE; ++e) res[e] += ks * fmaf((x[k][e] - mean) * rstd, gam[k][e], bet[k][e]);
-        RowVec<TR, VE>::store(out + r * C + v * VE, res);
       }
-    }
-    if (row_ok && gl == 0) {
-      mean_out[r] = mean;
-      rstd_out[r] = rstd;
+      if (row_ok && gl == 0) {
+        mean_out[r] = mean;
+        rstd_out[r] = rstd;
+      }
     }
   }
 }
 
-// workspace layout: [gridDim.x][2][C] float partials (dgamma, dbeta)
-template <typename TY, typename TR, int GS, int K>
-__global__ void __launch_bounds__(kThreads) ln_residual_bwd_kernel(const TR* __restrict__ dout, const TY* __restrict__ y,
-                                                                   const float* __restrict__ gamma,
-                                                                   const float* __restrict__ mean_in,
-                                                                   const float* __restrict__ rstd_in,
-                                                                   const float* __restrict__ keep_scale, TY* __restrict__ dy,
-                                                                   float* __restrict__ partials, int64_t rows, int C,
-                                                                   int64_t rows_per_sample) {
+// workspace layout: [gridDim.x][3][C] float partials (dgamma, dbeta, dbias)
+template <typename TY, typename TR, int GS, int K, int R, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
+ln_residual_bwd_kernel(const TR* __restrict__ dout, const TY* __restrict__ y, const float* __restrict__ gamma,
+                       const float* __restrict__ bias, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                       const float* __restrict__ keep_scale, TY* __restrict__ dy, float* __restrict__ partials, int64_t rows,
+                       int C, int64_t rows_per_sample) {
   constexpr int VE = 16 / sizeof(TY);
   constexpr int RPW = 32 / GS;
-  extern __shared__ float red[];  // [2][C] per CTA
+  extern __shared__ float red[];  // [3][C] per CTA
   const int lane = threadIdx.x & 31, gl = lane % GS, gi = lane / GS;
   const int vpr = C / VE;
-  float gam[K][VE], dg[K][VE], db[K][VE];
+  float gam[K][VE], bia[K][VE], dg[K][VE], db[K][VE], dbi[K][VE];
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     const int v = gl + k * GS;
 #pragma unroll
     for (int e = 0; e < VE; ++e) {
       gam[k][e] = (v < vpr) ? gamma[v * VE + e] : 0.f;
+      bia[k][e] = (v < vpr && bias != nullptr) ? bias[v * VE + e] : 0.f;
       dg[k][e] = 0.f;
       db[k][e] = 0.f;
+      dbi[k][e] = 0.f;
     }
   }
-  for (int c = threadIdx.x; c < 2 * C; c += kThreads) red[c] = 0.f;
+  for (int c = threadIdx.x; c < 3 * C; c += kThreads) red[c] = 0.f;
   __syncthreads();
   const int64_t warp_global = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   const int64_t warp_stride = (int64_t)gridDim.x * (kThreads / 32);
   const float inv_c = 1.0f / (float)C;
-  for (int64_t r0 = warp_global * RPW; r0 < rows; r0 += warp_stride * RPW) {
-    const int64_t r = r0 + gi;
-    const bool row_ok = r < rows;
-    const float mean = row_ok ? mean_in[r] : 0.f;
-    const float rstd = row_ok ? rstd_in[r] : 0.f;
-    const float ks = (keep_scale != nullptr && row_ok) ? keep_scale[r / rows_per_sample] : 1.0f;
-    float xh[K][VE], gx[K][VE];
-    float s1 = 0.f, s2 = 0.f;
+  for (int64_t r0 = warp_global * (RPW * R); r0 < rows; r0 += warp_stride * (RPW * R)) {
+    PkRow<TY, VE> yv[R][K];
+    PkRow<TR, VE> gv[R][K];
+    float mean[R], rstd[R], ks[R];
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const int v = gl + k * GS;
-      if (row_ok && v < vpr) {
-        float gv[VE];
-        RowVec<TY, VE>::load(y + r * C + v * VE, xh[k]);
-        RowVec<TR, VE>::load(dout + r * C + v * VE, gv);
+    for (int rr = 0; rr < R; ++rr) {
+      const int64_t r = r0 + rr * RPW + gi;
+      const bool row_ok = r < rows;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const int v = gl + k * GS;
+        if (row_ok && v < vpr) {
+          yv[rr][k].load(y + r * C + v * VE);
+          gv[rr][k].load(dout + r * C + v * VE);
+        } else {
+          yv[rr][k].zero();
+          gv[rr][k].zero();
+        }
+      }
+      mean[rr] = row_ok ? mean_in[r] : 0.f;
+      rstd[rr] = row_ok ? rstd_in[r] : 0.f;
+      ks[rr] = (keep_scale != nullptr && row_ok) ? keep_scale[r / rows_per_sample] : 1.0f;
+    }
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) {
+      const int64_t r = r0 + rr * RPW + gi;
+      const bool row_ok = r < rows;
+      float xh[K][VE], gx[K][VE];
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const bool ok = row_ok && (gl + k * GS < vpr);
+        float yy[VE], gg[VE];
+        yv[rr][k].get(yy);
+        gv[rr][k].get(gg);
 #pragma unroll
         for (int e = 0; e < VE; ++e) {
-          const float g = gv[e] * ks;
-          xh[k][e] = (xh[k][e] - mean) * rstd;
-          dg[k][e] = fmaf(g, xh[k][e], dg[k][e]);
+          const float g = gg[e] * ks[rr];
+          const float xhat = ok ? (yy[e] + bia[k][e] - mean[rr]) * rstd[rr] : 0.f;
+          xh[k][e] = xhat;
+          dg[k][e] = fmaf(g, xhat, dg[k][e]);
           db[k][e] += g;
-          gx[k][e] = g * gam[k][e];
-          s1 = fmaf(gx[k][e], xh[k][e], s1);
-          s2 += gx[k][e];
+          const float gxv = g * gam[k][e];
+          gx[k][e] = gxv;
+          s1 = fmaf(gxv, xhat, s1);
+          s2 += gxv;
         }
-      } else {
-#pragma unroll
-        for (int e = 0; e < VE; ++e) { xh[k][e] = 0.f; gx[k][e] = 0.f; }
       }
-    }
-    const float c1 = group_sum<GS>(s1) * inv_c;
-    const float c2 = group_sum<GS>(s2) * inv_c;
+      const float c1 = group_sum<GS>(s1) * inv_c;
+      const float c2 = group_sum<GS>(s2) * inv_c;
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const int v = gl + k * GS;
-      if (row_ok && v < vpr) {
-        float o[VE];
+      for (int k = 0; k < K; ++k) {
+        const int v = gl + k * GS;
+        if (row_ok && v < vpr) {
+          float o[VE];
 #pragma unroll
-        for (int e = 0; e < VE; ++e) o[e] = rstd * (gx[k][e] - c2 - xh[k][e] * c1);
-        RowVec<TY, VE>::store(dy + r * C + v * VE, o);
+          for (int e = 0; e < VE; ++e) {
+            o[e] = rstd[rr] * (gx[k][e] - c2 - xh[k][e] * c1);
+            dbi[k][e] += o[e];
+          }
+          PkRow<TY, VE> ov;
+          ov.set(o);
+          ov.store(dy + r * C + v * VE);
+        }
       }
     }
   }
-  // fold the 32/GS row groups of a warp, then the warps of the CTA (shared-memory atomics: 8 warps,
-  // distinct columns within a warp instruction), then one plain store per column per CTA.
+  // fold the 32/GS row groups of a warp (shuffles), then the warps of the CTA (shared-memory atomics on
+  // distinct columns), then one plain store per column per CTA.
 #pragma unroll
   for (int k = 0; k < K; ++k) {
 #pragma unroll
     for (int e = 0; e < VE; ++e) {
-      float a = dg[k][e], b = db[k][e];
+      float a = dg[k][e], b = db[k][e], c = dbi[k][e];
 #pragma unroll
       for (int o = GS; o < 32; o <<= 1) {
         a += __shfl_xor_sync(0xffffffffu, a, o);
         b += __shfl_xor_sync(0xffffffffu, b, o);
+        c += __shfl_xor_sync(0xffffffffu, c, o);
       }
       const int v = gl + k * GS;
       if (gi == 0 && v < vpr) {
         atomicAdd(&red[v * VE + e], a);
         atomicAdd(&red[C + v * VE + e], b);
+        atomicAdd(&red[2 * C + v * VE + e], c);
       }
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < 2 * C; c += kThreads) partials[(int64_t)blockIdx.x * 2 * C + c] = red[c];
+  for (int c = threadIdx.x; c < 3 * C; c += kThreads) partials[(int64_t)blockIdx.x * 3 * C + c] = red[c];
 }
 
-__global__ void ln_param_grad_finalize_kernel(const float* __restrict__ partials, int nblocks, int C,
-                                              float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= 2 * C) return;
+// Sum the per-CTA partial rows: block = 32 columns x kFinalizeRows row-groups, coalesced 128-byte reads.
+__global__ void __launch_bounds__(32 * kFinalizeRows) ln_param_grad_finalize_kernel(const float* __restrict__ partials, int nblocks,
+                                                                                   int C, float* __restrict__ dgamma,
+                                                                                   float* __restrict__ dbeta,
+                                                                                   float* __restrict__ dbias) {
+  __shared__ float sm[kFinalizeRows][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
   float s = 0.f;
-  for (int b = 0; b < nblocks; ++b) s += partials[(int64_t)b * 2 * C + c];
-  if (c < C) dgamma[c] = s; else dbeta[c - C] = s;
+  if (c < 3 * C)
+    for (int b = ty; b < nblocks; b += kFinalizeRows) s += partials[(int64_t)b * 3 * C + c];
+  sm[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < 3 * C) {
+#pragma unroll
+    for (int k = 1; k < kFinalizeRows; ++k) s += sm[k][tx];
+    if (c < C) dgamma[c] = s;
+    else if (c < 2 * C) dbeta[c - C] = s;
+    else if (dbias != nullptr) dbias[c - 2 * C] = s;
+  }
 }
 
-int grid_for_rows(int64_t rows, int rows_per_warp) {
-  const int64_t warps = (rows + rows_per_warp - 1) / rows_per_warp;
+int grid_for_rows(int64_t rows, int rows_per_warp_iter, int ctas_per_sm) {
+  const int64_t warps = (rows + rows_per_warp_iter - 1) / rows_per_warp_iter;
   const int64_t blocks = (warps + (kThreads / 32) - 1) / (kThreads / 32);
-  const int64_t cap = (int64_t)num_sms() * 8;  // 8 CTAs of 256 threads = 2048 threads per SM
+  const int64_t cap = (int64_t)num_sms() * ctas_per_sm;
   return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
 }
+constexpr int kBwdCtasPerSm = 2;  // also bounds the number of partial rows the finalize kernel sums
 
 struct Shape { int gs, k; };
 bool pick_shape(int vpr, Shape& s) {
@@ -235,23 +329,28 @@ bool pick_shape(int vpr, Shape& s) {
 }
 
 template <typename TY, typename TR, int GS, int K>
-int run_fwd(const void* y, const void* sc, const float* gamma, const float* beta, const float* ks, void* out, float* mean,
-            float* rstd, int64_t rows, int C, int64_t rps, float eps, cudaStream_t st) {
-  const int grid = grid_for_rows(rows, 32 / GS);
-  ln_residual_fwd_kernel<TY, TR, GS, K><<<grid, kThreads, 0, st>>>((const TY*)y, (const TR*)sc, gamma, beta, ks, (TR*)out,
-                                                                   mean, rstd, rows, C, rps, eps);
+int run_fwd(const void* y, const void* sc, const float* gamma, const float* beta, const float* bias, const float* ks,
+            void* out, float* mean, float* rstd, int64_t rows, int C, int64_t rps, float eps, cudaStream_t st) {
+  constexpr int R = K == 1 ? 4 : (K == 2 ? 2 : 1);
+  constexpr int MINB = K <= 2 ? 2 : 1;
+  const int grid = grid_for_rows(rows, (32 / GS) * R, 2 * MINB);
+  ln_residual_fwd_kernel<TY, TR, GS, K, R, MINB><<<grid, kThreads, 0, st>>>((const TY*)y, (const TR*)sc, gamma, beta, bias, ks,
+                                                                      (TR*)out, mean, rstd, rows, C, rps, eps);
   HV_LAUNCH_OK("ln_residual_fwd_kernel");
   return HV_OK;
 }
 
 template <typename TY, typename TR, int GS, int K>
-int run_bwd(const void* dout, const void* y, const float* gamma, const float* mean, const float* rstd, const float* ks,
-            void* dy, float* dgamma, float* dbeta, float* partials, int64_t rows, int C, int64_t rps, cudaStream_t st) {
-  const int grid = grid_for_rows(rows, 32 / GS);
-  ln_residual_bwd_kernel<TY, TR, GS, K><<<grid, kThreads, 2 * C * sizeof(float), st>>>(
-      (const TR*)dout, (const TY*)y, gamma, mean, rstd, ks, (TY*)dy, partials, rows, C, rps);
+int run_bwd(const void* dout, const void* y, const float* gamma, const float* bias, const float* mean, const float* rstd,
+            const float* ks, void* dy, float* dgamma, float* dbeta, float* dbias, float* partials, int64_t rows, int C,
+            int64_t rps, cudaStream_t st) {
+  constexpr int R = K == 1 ? 2 : 1;
+  constexpr int MINB = K <= 2 ? 2 : 1;
+  const int grid = grid_for_rows(rows, (32 / GS) * R, kBwdCtasPerSm);
+  ln_residual_bwd_kernel<TY, TR, GS, K, R, MINB><<<grid, kThreads, 3 * C * sizeof(float), st>>>(
+      (const TR*)dout, (const TY*)y, gamma, bias, mean, rstd, ks, (TY*)dy, partials, rows, C, rps);
   HV_LAUNCH_OK("ln_residual_bwd_kernel");
-  ln_param_grad_finalize_kernel<<<(2 * C + 127) / 128, 128, 0, st>>>(partials, grid, C, dgamma, dbeta);
+  ln_param_grad_finalize_kernel<<<(3 * C + 31) / 32, 32 * kFinalizeRows, 0, st>>>(partials, grid, C, dgamma, dbeta, dbias);
   HV_LAUNCH_OK("ln_param_grad_finalize_kernel");
   return HV_OK;
 }
@@ -282,29 +381,30 @@ int check_common(int64_t rows, int C, int y_dtype, int res_dtype, Shape& shape) 
 
 size_t ln_residual_bwd_workspace_bytes(int64_t rows, int C) {
   (void)rows;
-  return (size_t)num_sms() * 8 * 2 * (size_t)C * sizeof(float);
+  return (size_t)num_sms() * kBwdCtasPerSm * 3 * (size_t)C * sizeof(float);
 }
 
-int ln_residual_fwd(const void* y, const void* shortcut, const float* gamma, const float* beta, const float* keep_scale,
-                    void* out, float* mean, float* rstd, int64_t rows, int C, int64_t rows_per_sample, float eps,
-                    int y_dtype, int res_dtype, cudaStream_t st) {
+int ln_residual_fwd(const void* y, const void* shortcut, const float* gamma, const float* beta, const float* bias,
+                    const float* keep_scale, void* out, float* mean, float* rstd, int64_t rows, int C,
+                    int64_t rows_per_sample, float eps, int y_dtype, int res_dtype, cudaStream_t st) {
   Shape shape;
   int rc = check_common(rows, C, y_dtype, res_dtype, shape);
   if (rc) return rc;
   if (!aligned16(y) || !aligned16(out) || (shortcut && !aligned16(shortcut))) HV_FAIL(HV_ERR_ALIGN, "ln_residual_fwd: pointers must be 16-byte aligned");
   if (rows_per_sample <= 0) rows_per_sample = rows;
   if (y_dtype == HV_F32) {
-    HV_LN_DISPATCH_SHAPE(run_fwd, float, float, y, shortcut, gamma, beta, keep_scale, out, mean, rstd, rows, C, rows_per_sample, eps, st)
+    HV_LN_DISPATCH_SHAPE(run_fwd, float, float, y, shortcut, gamma, beta, bias, keep_scale, out, mean, rstd, rows, C, rows_per_sample, eps, st)
   } else if (res_dtype == HV_BF16) {
-    HV_LN_DISPATCH_SHAPE(run_fwd, bf16, bf16, y, shortcut, gamma, beta, keep_scale, out, mean, rstd, rows, C, rows_per_sample, eps, st)
+    HV_LN_DISPATCH_SHAPE(run_fwd, bf16, bf16, y, shortcut, gamma, beta, bias, keep_scale, out, mean, rstd, rows, C, rows_per_sample, eps, st)
   } else {
-    HV_LN_DISPATCH_SHAPE(run_fwd, bf16, float, y, shortcut, gamma, beta, keep_scale, out, mean, rstd, rows, C, rows_per_sample, eps, st)
+    HV_LN_DISPATCH_SHAPE(run_fwd, bf16, float, y, shortcut, gamma, beta, bias, keep_scale, out, mean, rstd, rows, C, rows_per_sample, eps, st)
   }
 }
 
-int ln_residual_bwd(const void* dout, const void* y, const float* gamma, const float* mean, const float* rstd,
-                    const float* keep_scale, void* dy, float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
-                    int64_t rows, int C, int64_t rows_per_sample, int y_dtype, int res_dtype, cudaStream_t st) {
+int ln_residual_bwd(const void* dout, const void* y, const float* gamma, const float* bias, const float* mean,
+                    const float* rstd, const float* keep_scale, void* dy, float* dgamma, float* dbeta, float* dbias,
+                    void* workspace, size_t workspace_bytes, int64_t rows, int C, int64_t rows_per_sample, int y_dtype,
+                    int res_dtype, cudaStream_t st) {
   Shape shape;
   int rc = check_common(rows, C, y_dtype, res_dtype, shape);
   if (rc) return rc;
@@ -314,11 +414,11 @@ int ln_residual_bwd(const void* dout, const void* y, const float* gamma, const f
   if (rows_per_sample <= 0) rows_per_sample = rows;
   float* partials = static_cast<float*>(workspace);
   if (y_dtype == HV_F32) {
-    HV_LN_DISPATCH_SHAPE(run_bwd, float, float, dout, y, gamma, mean, rstd, keep_scale, dy, dgamma, dbeta, partials, rows, C, rows_per_sample, st)
+    HV_LN_DISPATCH_SHAPE(run_bwd, float, float, dout, y, gamma, bias, mean, rstd, keep_scale, dy, dgamma, dbeta, dbias, partials, rows, C, rows_per_sample, st)
   } else if (res_dtype == HV_BF16) {
-    HV_LN_DISPATCH_SHAPE(run_bwd, bf16, bf16, dout, y, gamma, mean, rstd, keep_scale, dy, dgamma, dbeta, partials, rows, C, rows_per_sample, st)
+    HV_LN_DISPATCH_SHAPE(run_bwd, bf16, bf16, dout, y, gamma, bias, mean, rstd, keep_scale, dy, dgamma, dbeta, dbias, partials, rows, C, rows_per_sample, st)
   } else {
-    HV_LN_DISPATCH_SHAPE(run_bwd, bf16, float, dout, y, gamma, mean, rstd, keep_scale, dy, dgamma, dbeta, partials, rows, C, rows_per_sample, st)
+    HV_LN_DISPATCH_SHAPE(run_bwd, bf16, float, dout, y, gamma, bias, mean, rstd, keep_scale, dy, dgamma, dbeta, dbias, partials, rows, C, rows_per_sample, st)
   }
 }
 

@@ -139,16 +139,17 @@ def window_attention(qkv: torch.Tensor, bias_table: torch.Tensor, tau: torch.Ten
 
 
 class _LnResidual(torch.autograd.Function):
-    """out = shortcut + keep_scale[sample] * LayerNorm(y) (shortcut / keep_scale optional)."""
+    """out = shortcut + keep_scale[sample] * LayerNorm(y + bias) (shortcut / bias / keep_scale optional)."""
 
     @staticmethod
-    def forward(ctx, y, shortcut, gamma, beta, keep_scale, rows_per_sample, eps):
+    def forward(ctx, y, shortcut, gamma, beta, bias, keep_scale, rows_per_sample, eps):
         _need_cuda(y, "ln_residual")
         lib = _lib.load()
         y = y.contiguous()
         C = y.shape[-1]
         rows = y.numel() // C
         gamma32, beta32 = _f32c(gamma), _f32c(beta)
+        bias32 = _f32c(bias) if bias is not None else None
         if shortcut is not None:
             shortcut = shortcut.contiguous()
             res_dtype = shortcut.dtype
@@ -160,42 +161,47 @@ class _LnResidual(torch.autograd.Function):
         mean = torch.empty((rows,), dtype=torch.float32, device=y.device)
         rstd = torch.empty((rows,), dtype=torch.float32, device=y.device)
         with torch.cuda.device(y.device):
-            rc = lib.hv_ln_residual_fwd(_ptr(y), _ptr(shortcut), _ptr(gamma32), _ptr(beta32), _ptr(keep_scale), _ptr(out),
-                                        _ptr(mean), _ptr(rstd), rows, C, rows_per_sample, float(eps), _code(y), _code(out),
-                                        _stream(y.device))
+            rc = lib.hv_ln_residual_fwd(_ptr(y), _ptr(shortcut), _ptr(gamma32), _ptr(beta32), _ptr(bias32), _ptr(keep_scale),
+                                        _ptr(out), _ptr(mean), _ptr(rstd), rows, C, rows_per_sample, float(eps), _code(y),
+                                        _code(out), _stream(y.device))
         check(rc, "hv_ln_residual_fwd")
         global LAUNCH_COUNT
         LAUNCH_COUNT += 1
-        ctx.save_for_backward(y, gamma32, mean, rstd, keep_scale)
-        ctx.meta = (rows, C, rows_per_sample, shortcut is not None, gamma.dtype, beta.dtype)
+        ctx.save_for_backward(y, gamma32, bias32, mean, rstd, keep_scale)
+        ctx.meta = (rows, C, rows_per_sample, shortcut is not None, gamma.dtype, beta.dtype,
+                    bias.dtype if bias is not None else None)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        y, gamma32, mean, rstd, keep_scale = ctx.saved_tensors
-        rows, C, rows_per_sample, has_shortcut, gdt, bdt = ctx.meta
+        y, gamma32, bias32, mean, rstd, keep_scale = ctx.saved_tensors
+        rows, C, rows_per_sample, has_shortcut, gdt, bdt, biasdt = ctx.meta
         lib = _lib.load()
         dout = dout.contiguous()
         dy = torch.empty_like(y)
         dgamma = torch.empty_like(gamma32)
         dbeta = torch.empty_like(gamma32)
+        dbias = torch.empty_like(gamma32) if bias32 is not None else None
         with torch.cuda.device(y.device):
             nbytes = lib.hv_ln_residual_bwd_workspace_bytes(rows, C)
             workspace = torch.empty((int(nbytes),), dtype=torch.uint8, device=y.device)
-            rc = lib.hv_ln_residual_bwd(_ptr(dout), _ptr(y), _ptr(gamma32), _ptr(mean), _ptr(rstd), _ptr(keep_scale),
-                                        _ptr(dy), _ptr(dgamma), _ptr(dbeta), _ptr(workspace), workspace.numel(), rows, C,
-                                        rows_per_sample, _code(y), _code(dout), _stream(y.device))
+            rc = lib.hv_ln_residual_bwd(_ptr(dout), _ptr(y), _ptr(gamma32), _ptr(bias32), _ptr(mean), _ptr(rstd),
+                                        _ptr(keep_scale), _ptr(dy), _ptr(dgamma), _ptr(dbeta), _ptr(dbias), _ptr(workspace),
+                                        workspace.numel(), rows, C, rows_per_sample, _code(y), _code(dout), _stream(y.device))
         check(rc, "hv_ln_residual_bwd")
         global LAUNCH_COUNT
         LAUNCH_COUNT += 2
-        return dy, (dout if has_shortcut else None), dgamma.to(gdt), dbeta.to(bdt), None, None, None
+        return (dy, (dout if has_shortcut else None), dgamma.to(gdt), dbeta.to(bdt),
+                (dbias.to(biasdt) if dbias is not None else None), None, None, None)
 
 
 def ln_residual(y: torch.Tensor, shortcut: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor,
-                keep_scale: Optional[torch.Tensor] = None, eps: float = 1e-5) -> torch.Tensor:
-    """shortcut + keep_scale[b] * LayerNorm(y) over the last dim; y is (B, L, C) (or (rows, C))."""
+                keep_scale: Optional[torch.Tensor] = None, eps: float = 1e-5,
+                bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """shortcut + keep_scale[b] * LayerNorm(y + bias) over the last dim; y is (B, L, C) (or (rows, C)).
+    ``bias``: the bias of the Linear that produced ``y`` when that Linear was run without it."""
     rows_per_sample = (y.numel() // y.shape[-1]) // y.shape[0] if y.dim() >= 2 else 1
-    return _LnResidual.apply(y, shortcut, gamma, beta, keep_scale, rows_per_sample, eps)
+    return _LnResidual.apply(y, shortcut, gamma, beta, bias, keep_scale, rows_per_sample, eps)
 
 
 class _PatchMergeGather(torch.autograd.Function):

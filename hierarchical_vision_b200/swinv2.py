@@ -201,7 +201,7 @@ class WindowAttention(nn.Module):
     def _tau(self):
         return torch.clamp(self.logit_scale.float(), max=self.logit_clamp_max.float()).exp().reshape(-1)
 
-    def _fused(self, x_tokens, B, H, W, shift, mask):
+    def _fused(self, x_tokens, B, H, W, shift, mask, with_proj_bias=True):
         if self.window_size[0] != self.window_size[1]:
             raise NotImplementedError("fused window attention needs square windows (the reference's "
                                       "SwinTransformerBlock only ever builds square ones, swinv2.py:339)")
@@ -209,7 +209,9 @@ class WindowAttention(nn.Module):
             raise NotImplementedError("attention dropout is not fused; every reference config uses attn_drop=0")
         o = hvf.window_attention(self._qkv(x_tokens), self._bias_table(), self._tau(), B=B, H=H, W=W, C=self.dim,
                                  heads=self.num_heads, ws=self.window_size[0], shift=shift, mask=mask)
-        return self.proj_drop(self.proj(o))
+        if with_proj_bias:
+            return self.proj_drop(self.proj(o))
+        return F.linear(o, self.proj.weight)  # the caller folds proj.bias into its LayerNorm kernel
 
     def forward(self, x, mask=None):
         """x: (num_windows*B, N, C); mask: (num_windows, N, N) of 0/-100 or None (swinv2.py:204-264)."""
@@ -258,21 +260,35 @@ class SwinTransformerBlock(nn.Module):
         # regenerates the same pattern from (H, W, ws, shift) and never reads this tensor.
         self.register_buffer("attn_mask", _shift_mask(H, W, self.window_size, self.shift_size))
 
-    def _post_norm(self, norm, branch, shortcut):
+    @staticmethod
+    def _fusable(norm):
+        return type(norm) is nn.LayerNorm and norm.elementwise_affine and norm.bias is not None
+
+    def _post_norm(self, norm, branch, shortcut, bias=None):
         p = self.drop_path.drop_prob if isinstance(self.drop_path, DropPath) else 0.0
-        if type(norm) is nn.LayerNorm and norm.elementwise_affine and norm.bias is not None:
+        if self._fusable(norm):
             return hvf.ln_residual(branch, shortcut, norm.weight, norm.bias, _keep_scale(branch, p, self.training),
-                                   norm.eps)
+                                   norm.eps, bias=bias)
+        if bias is not None:
+            branch = branch + bias
         return shortcut + self.drop_path(norm(branch))  # non-LayerNorm norm_layer: library ops
 
     def forward(self, x):
         H, W = self.input_resolution
         B, L, C = x.shape
         assert L == H * W, "input feature has wrong size"
+        # The biases of the two Linears that feed a LayerNorm (attn.proj, mlp.fc2) are added inside the
+        # LayerNorm kernel (dropout p = 0 in between, as in every reference config), so their gradients
+        # come out of its backward instead of two extra full-tensor column reductions.
+        fold1 = self._fusable(self.norm1) and self.attn.proj_drop.p == 0.0
+        fold2 = self._fusable(self.norm2) and self.mlp.drop.p == 0.0 and isinstance(self.mlp, Mlp)
         # roll + partition + attention + reverse + roll back: one kernel, no rolled / partitioned copy
-        y = self.attn._fused(x, B, H, W, self.shift_size, None)
-        x = self._post_norm(self.norm1, y, x)                  # swinv2.py:431
-        return self._post_norm(self.norm2, self.mlp(x), x)     # swinv2.py:434
+        y = self.attn._fused(x, B, H, W, self.shift_size, None, with_proj_bias=not fold1)
+        x = self._post_norm(self.norm1, y, x, self.attn.proj.bias if fold1 else None)          # swinv2.py:431
+        if fold2:
+            m = F.linear(self.mlp.act(self.mlp.fc1(x)), self.mlp.fc2.weight)
+            return self._post_norm(self.norm2, m, x, self.mlp.fc2.bias)                         # swinv2.py:434
+        return self._post_norm(self.norm2, self.mlp(x), x)
 
     def extra_repr(self) -> str:
         return (f"dim={self.dim}, input_resolution={self.input_resolution}, num_heads={self.num_heads}, "

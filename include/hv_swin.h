@@ -106,25 +106,30 @@ HV_API int hv_window_attn_bwd(const void* qkv, const void* out, const void* dout
                        void* dqkv, float* dbias_table, float* dtau, void* workspace, size_t workspace_bytes,
                        int B, int H, int W, int C, int heads, int ws, int shift, int dtype, void* stream);
 
-/* ---- res-post-norm: out = shortcut + keep_scale[sample] * LayerNorm(y) -------------------
+/* ---- res-post-norm: out = shortcut + keep_scale[sample] * LayerNorm(y + bias) ------------
  * Replaces `shortcut + drop_path(norm1(x))` / `x + drop_path(norm2(mlp(x)))`, swinv2.py:431, 434,
- * and (shortcut == NULL) the plain LayerNorm of PatchMerging, swinv2.py:494.
+ * and (shortcut == NULL) the plain LayerNorm of PatchMerging / PatchEmbed, swinv2.py:494, 656.
+ * `bias` (optional) is the bias of the Linear that produced y (attn.proj.bias swinv2.py:262,
+ * mlp.fc2.bias swinv2.py:64): the caller runs that Linear without bias and hands the bias here, so
+ * that its gradient is produced by hv_ln_residual_bwd instead of a separate column reduction.
  *   y        device (rows, C) y_dtype          shortcut  device (rows, C) res_dtype or NULL
- *   gamma, beta  device float32 (C)            keep_scale device float32 (rows / rows_per_sample) or NULL
+ *   gamma, beta  device float32 (C)            bias      device float32 (C) or NULL
+ *   keep_scale   device float32 (rows / rows_per_sample) or NULL (DropPath factor per sample)
  *   out      device (rows, C) res_dtype        mean, rstd device float32 (rows), saved for backward
  */
 HV_API int hv_ln_residual_fwd(const void* y, const void* shortcut, const float* gamma, const float* beta,
-                       const float* keep_scale, void* out, float* mean, float* rstd, int64_t rows, int C,
-                       int64_t rows_per_sample, float eps, int y_dtype, int res_dtype, void* stream);
+                       const float* bias, const float* keep_scale, void* out, float* mean, float* rstd,
+                       int64_t rows, int C, int64_t rows_per_sample, float eps, int y_dtype, int res_dtype,
+                       void* stream);
 
 HV_API size_t hv_ln_residual_bwd_workspace_bytes(int64_t rows, int C);
 
 /*   dout device (rows, C) res_dtype (this is also d shortcut)   dy device (rows, C) y_dtype
- *   dgamma, dbeta device float32 (C), overwritten */
-HV_API int hv_ln_residual_bwd(const void* dout, const void* y, const float* gamma, const float* mean,
-                       const float* rstd, const float* keep_scale, void* dy, float* dgamma, float* dbeta,
-                       void* workspace, size_t workspace_bytes, int64_t rows, int C, int64_t rows_per_sample,
-                       int y_dtype, int res_dtype, void* stream);
+ *   dgamma, dbeta device float32 (C), overwritten; dbias device float32 (C) or NULL (= column sums of dy) */
+HV_API int hv_ln_residual_bwd(const void* dout, const void* y, const float* gamma, const float* bias,
+                       const float* mean, const float* rstd, const float* keep_scale, void* dy, float* dgamma,
+                       float* dbeta, float* dbias, void* workspace, size_t workspace_bytes, int64_t rows, int C,
+                       int64_t rows_per_sample, int y_dtype, int res_dtype, void* stream);
 
 /* ---- PatchMerging 2x2 gather ------------------------------------------------------------
  * Replaces the four strided slices + torch.cat of swinv2.py:484-491 (forward) and their

@@ -96,15 +96,15 @@ def bench_ln(B, L, C, ydt, rdt, iters):
     st = hvf._stream(torch.device("cuda", torch.cuda.current_device()))
     wbytes = lib.hv_ln_residual_bwd_workspace_bytes(rows, C)
     wsp = torch.empty(wbytes, dtype=torch.uint8, device=dev)
-    dg, db = torch.empty(C, device=dev), torch.empty(C, device=dev)
+    dg, db, dbi = torch.empty(C, device=dev), torch.empty(C, device=dev), torch.empty(C, device=dev)
     cy, cr = hvf._code(sets[0][0]), hvf._code(sets[0][1])
 
     def f(s):
-        rc = lib.hv_ln_residual_fwd(P(s[0]), P(s[1]), P(gam), P(bet), P(None), P(s[2]), P(s[3]), P(s[4]), rows, C, L, 1e-5, cy, cr, st)
+        rc = lib.hv_ln_residual_fwd(P(s[0]), P(s[1]), P(gam), P(bet), P(gam), P(None), P(s[2]), P(s[3]), P(s[4]), rows, C, L, 1e-5, cy, cr, st)
         assert rc == 0, lib.hv_last_error()
 
     def b(s):
-        rc = lib.hv_ln_residual_bwd(P(s[2]), P(s[0]), P(gam), P(s[3]), P(s[4]), P(None), P(s[5]), P(dg), P(db), P(wsp), wbytes,
+        rc = lib.hv_ln_residual_bwd(P(s[2]), P(s[0]), P(gam), P(gam), P(s[3]), P(s[4]), P(None), P(s[5]), P(dg), P(db), P(dbi), P(wsp), wbytes,
                                     rows, C, L, cy, cr, st)
         assert rc == 0, lib.hv_last_error()
 
