@@ -305,7 +305,7 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * n,
-                       "precision": "torch.autocast(bfloat16), fp32 master weights, fp32 residual stream",
+                       "precision": "torch.autocast(bfloat16), fp32 master weights, bf16 activations",
                        "optimizer": "SGD momentum 0.875 wd 5e-4, grad-clip 2.0, drop_path 0.1", "parallelism": f"dp{n}",
                        "l2": "no flush needed: each step streams > 10 GB of activations, far beyond the 126 MB L2"},
             "clocks": clocks,

@@ -27,6 +27,10 @@ int ln_residual_bwd(const void* dout, const void* y, const float* gamma, const f
                     const float* rstd, const float* keep_scale, void* dy, float* dgamma, float* dbeta, float* dbias,
                     void* workspace, size_t workspace_bytes, int64_t rows, int C, int64_t rows_per_sample, int y_dtype,
                     int res_dtype, cudaStream_t st);
+size_t bias_gelu_bwd_workspace_bytes(int64_t rows, int cols);
+int bias_gelu_fwd(const void* h, const float* bias, void* out, int64_t rows, int cols, int dtype, cudaStream_t st);
+int bias_gelu_bwd(const void* dout, const void* h, const float* bias, void* dh, float* dbias, void* workspace,
+                  size_t workspace_bytes, int64_t rows, int cols, int dtype, cudaStream_t st);
 int patch_merge_gather_fwd(const void* x, void* out, int B, int H, int W, int C, int dtype, cudaStream_t st);
 int patch_merge_gather_bwd(const void* dout, void* dx, int B, int H, int W, int C, int dtype, cudaStream_t st);
 
@@ -219,6 +223,24 @@ int hv_ln_residual_bwd(const void* dout, const void* y, const float* gamma, cons
   if (rc) return rc;
   return ln_residual_bwd(dout, y, gamma, bias, mean, rstd, keep_scale, dy, dgamma, dbeta, dbias, workspace, workspace_bytes,
                          rows, C, rows_per_sample, y_dtype, res_dtype, static_cast<cudaStream_t>(stream));
+}
+
+int hv_bias_gelu_fwd(const void* h, const float* bias, void* out, int64_t rows, int cols, int dtype, void* stream) {
+  if (!h || !bias || !out) HV_FAIL(HV_ERR_NULL, "hv_bias_gelu_fwd: NULL argument");
+  int rc = check_device_arch();
+  if (rc) return rc;
+  return bias_gelu_fwd(h, bias, out, rows, cols, dtype, static_cast<cudaStream_t>(stream));
+}
+
+size_t hv_bias_gelu_bwd_workspace_bytes(int64_t rows, int cols) { return bias_gelu_bwd_workspace_bytes(rows, cols); }
+
+int hv_bias_gelu_bwd(const void* dout, const void* h, const float* bias, void* dh, float* dbias, void* workspace,
+                     size_t workspace_bytes, int64_t rows, int cols, int dtype, void* stream) {
+  if (!dout || !h || !bias || !dh || !dbias) HV_FAIL(HV_ERR_NULL, "hv_bias_gelu_bwd: NULL argument");
+  int rc = check_device_arch();
+  if (rc) return rc;
+  return bias_gelu_bwd(dout, h, bias, dh, dbias, workspace, workspace_bytes, rows, cols, dtype,
+                       static_cast<cudaStream_t>(stream));
 }
 
 int hv_patch_merge_gather_fwd(const void* x, void* out, int B, int H, int W, int C, int dtype, void* stream) {

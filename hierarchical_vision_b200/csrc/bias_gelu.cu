@@ -1,0 +1,200 @@
+// Mlp activation of the SwinV2 block (reference swinv2.py:60-63): a = GELU_erf(h + b1), where h = x W1^T is the
+// fc1 GEMM output computed WITHOUT its bias.  Folding the bias add into the activation kernel makes the
+// gradient of fc1.bias a by-product of the activation backward (column sums of d h accumulated in registers)
+// instead of a separate full-tensor reduction over the largest activation of the block.
+//
+// Pure streaming kernels (HBM-bound): a half-warp owns a strip of 16 consecutive 16-byte vectors of one row,
+// so a warp instruction covers two rows x 256 contiguous bytes; every lane always sees the same columns, which
+// is what lets the bias (forward) and the d-bias partial sums (backward) live in registers.
+#include "hv_common.cuh"
+
+namespace hv {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kRowsPerIter = 4;  // per half-warp: vectors in flight per lane
+
+// erf via Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7): one reciprocal and one exp2; the same exp(-x^2/2)
+// is the Gaussian density the derivative needs.
+struct GeluParts { float cdf, pdf_x; };  // Phi(x), x * phi(x)
+__device__ __forceinline__ GeluParts gelu_parts(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float e = exp2f(-z * z * 1.4426950408889634f);  // exp(-x^2/2)
+  const float erf_abs = fmaf(-poly, e, 1.0f);
+  GeluParts p;
+  p.cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
+  p.pdf_x = x * e * 0.3989422804014327f;
+  return p;
+}
+
+template <typename T> struct V16;  // one packed 16-byte vector
+template <> struct V16<float> {
+  static constexpr int n = 4;
+  float4 v;
+  __device__ __forceinline__ void load(const float* p) { v = *reinterpret_cast<const float4*>(p); }
+  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = v; }
+  __device__ __forceinline__ void get(float* f) const { f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w; }
+  __device__ __forceinline__ void set(const float* f) { v = make_float4(f[0], f[1], f[2], f[3]); }
+};
+template <> struct V16<bf16> {
+  static constexpr int n = 8;
+  uint4 v;
+  __device__ __forceinline__ void load(const bf16* p) { v = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void store(bf16* p) const { *reinterpret_cast<uint4*>(p) = v; }
+  __device__ __forceinline__ void get(float* f) const {
+    f[0] = bf16lo_to_f32(v.x); f[1] = bf16hi_to_f32(v.x); f[2] = bf16lo_to_f32(v.y); f[3] = bf16hi_to_f32(v.y);
+    f[4] = bf16lo_to_f32(v.z); f[5] = bf16hi_to_f32(v.z); f[6] = bf16lo_to_f32(v.w); f[7] = bf16hi_to_f32(v.w);
+  }
+  __device__ __forceinline__ void set(const float* f) {
+    v = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+  }
+};
+
+// strips = vectors_per_row / 16; warp w handles strip (w % strips) of rows rgroup*2R + ..., rgroup = w / strips
+template <typename T, bool BACKWARD>
+__global__ void __launch_bounds__(kThreads, 4)
+bias_gelu_kernel(const T* __restrict__ h, const T* __restrict__ dout, const float* __restrict__ bias, T* __restrict__ out,
+                 float* __restrict__ partials, int64_t rows, int cols, int strips, int rgroups) {
+  constexpr int VE = V16<T>::n;
+  constexpr int R = kRowsPerIter;
+  const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
+  const int64_t warp = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  const int strip = (int)(warp % strips);
+  const int64_t rgroup = warp / strips;
+  if (rgroup >= rgroups) return;
+  const int col = (strip * 16 + hl) * VE;
+  float b[VE], acc[VE];
+#pragma unroll
+  for (int e = 0; e < VE; ++e) {
+    b[e] = bias[col + e];
+    acc[e] = 0.f;
+  }
+  for (int64_t r0 = rgroup * (2 * R); r0 < rows; r0 += (int64_t)rgroups * (2 * R)) {
+    V16<T> hv_[R], gv_[R];
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) {
+      const int64_t r = r0 + 2 * rr + half;
+      if (r < rows) {
+        hv_[rr].load(h + r * cols + col);
+        if (BACKWARD) gv_[rr].load(dout + r * cols + col);
+      }
+    }
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) {
+      const int64_t r = r0 + 2 * rr + half;
+      if (r < rows) {
+        float x[VE], g[VE], o[VE];
+        hv_[rr].get(x);
+        if (BACKWARD) gv_[rr].get(g);
+#pragma unroll
+        for (int e = 0; e < VE; ++e) {
+          const float xe = x[e] + b[e];
+          const GeluParts p = gelu_parts(xe);
+          if (BACKWARD) {
+            o[e] = g[e] * (p.cdf + p.pdf_x);
+            acc[e] += o[e];
+          } else {
+            o[e] = xe * p.cdf;
+          }
+        }
+        V16<T> ov;
+        ov.set(o);
+        ov.store(out + r * cols + col);
+      }
+    }
+  }
+  if (BACKWARD) {
+#pragma unroll
+    for (int e = 0; e < VE; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+    if (half == 0) {
+      float* dst = partials + rgroup * cols + col;
+#pragma unroll
+      for (int e = 0; e < VE; ++e) dst[e] = acc[e];
+    }
+  }
+}
+
+// out[c] = sum over `nrows` partial rows: block = 32 columns x 8 row-groups
+__global__ void __launch_bounds__(256) colsum_rows_kernel(const float* __restrict__ partials, int nrows, int ncols,
+                                                          float* __restrict__ out) {
+  __shared__ float sm[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  float s = 0.f;
+  if (c < ncols)
+    for (int r = ty; r < nrows; r += 8) s += partials[(int64_t)r * ncols + c];
+  sm[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < ncols) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) s += sm[k][tx];
+    out[c] = s;
+  }
+}
+
+struct Plan { int strips, rgroups, blocks; };
+bool make_plan(int64_t rows, int cols, int ve, Plan& p) {
+  if (cols % (16 * ve) != 0) return false;
+  p.strips = cols / (16 * ve);
+  const int64_t max_warps = (int64_t)num_sms() * 4 * (kThreads / 32);  // 4 CTAs per SM resident
+  int64_t rg = max_warps / p.strips;
+  const int64_t need = (rows + 2 * kRowsPerIter - 1) / (2 * kRowsPerIter);
+  if (rg > need) rg = need;
+  if (rg < 1) rg = 1;
+  p.rgroups = (int)rg;
+  const int64_t warps = rg * p.strips;
+  p.blocks = (int)((warps + (kThreads / 32) - 1) / (kThreads / 32));
+  return true;
+}
+
+}  // namespace
+
+size_t bias_gelu_bwd_workspace_bytes(int64_t rows, int cols) {
+  (void)rows;
+  // rgroups <= resident warps / strips, so rgroups * cols <= resident warps * 16 * VE floats (VE <= 8)
+  return (size_t)num_sms() * 4 * (kThreads / 32) * 16 * 8 * sizeof(float);
+}
+
+int bias_gelu_fwd(const void* h, const float* bias, void* out, int64_t rows, int cols, int dtype, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) HV_FAIL(HV_ERR_SHAPE, "bias_gelu: rows=%lld cols=%d", (long long)rows, cols);
+  if (dtype != HV_F32 && dtype != HV_BF16) HV_FAIL(HV_ERR_DTYPE, "bias_gelu: dtype %d", dtype);
+  if (!aligned16(h) || !aligned16(out)) HV_FAIL(HV_ERR_ALIGN, "bias_gelu: pointers must be 16-byte aligned");
+  Plan p;
+  if (!make_plan(rows, cols, dtype == HV_F32 ? 4 : 8, p))
+    HV_FAIL(HV_ERR_SHAPE, "bias_gelu: cols=%d must be a multiple of %d", cols, dtype == HV_F32 ? 64 : 128);
+  if (dtype == HV_F32)
+    bias_gelu_kernel<float, false><<<p.blocks, kThreads, 0, st>>>((const float*)h, nullptr, bias, (float*)out, nullptr, rows, cols, p.strips, p.rgroups);
+  else
+    bias_gelu_kernel<bf16, false><<<p.blocks, kThreads, 0, st>>>((const bf16*)h, nullptr, bias, (bf16*)out, nullptr, rows, cols, p.strips, p.rgroups);
+  HV_LAUNCH_OK("bias_gelu_kernel<fwd>");
+  return HV_OK;
+}
+
+int bias_gelu_bwd(const void* dout, const void* h, const float* bias, void* dh, float* dbias, void* workspace,
+                  size_t workspace_bytes, int64_t rows, int cols, int dtype, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) HV_FAIL(HV_ERR_SHAPE, "bias_gelu_bwd: rows=%lld cols=%d", (long long)rows, cols);
+  if (dtype != HV_F32 && dtype != HV_BF16) HV_FAIL(HV_ERR_DTYPE, "bias_gelu_bwd: dtype %d", dtype);
+  if (!aligned16(h) || !aligned16(dout) || !aligned16(dh)) HV_FAIL(HV_ERR_ALIGN, "bias_gelu_bwd: pointers must be 16-byte aligned");
+  Plan p;
+  if (!make_plan(rows, cols, dtype == HV_F32 ? 4 : 8, p))
+    HV_FAIL(HV_ERR_SHAPE, "bias_gelu_bwd: cols=%d must be a multiple of %d", cols, dtype == HV_F32 ? 64 : 128);
+  if (workspace == nullptr || workspace_bytes < (size_t)p.rgroups * cols * sizeof(float))
+    HV_FAIL(HV_ERR_WORKSPACE, "bias_gelu_bwd: workspace of %zu bytes required", bias_gelu_bwd_workspace_bytes(rows, cols));
+  float* partials = static_cast<float*>(workspace);
+  if (dtype == HV_F32)
+    bias_gelu_kernel<float, true><<<p.blocks, kThreads, 0, st>>>((const float*)h, (const float*)dout, bias, (float*)dh, partials, rows, cols, p.strips, p.rgroups);
+  else
+    bias_gelu_kernel<bf16, true><<<p.blocks, kThreads, 0, st>>>((const bf16*)h, (const bf16*)dout, bias, (bf16*)dh, partials, rows, cols, p.strips, p.rgroups);
+  HV_LAUNCH_OK("bias_gelu_kernel<bwd>");
+  colsum_rows_kernel<<<(cols + 31) / 32, 256, 0, st>>>(partials, p.rgroups, cols, dbias);
+  HV_LAUNCH_OK("colsum_rows_kernel");
+  return HV_OK;
+}
+
+}  // namespace hv

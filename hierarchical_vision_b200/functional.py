@@ -204,6 +204,58 @@ def ln_residual(y: torch.Tensor, shortcut: Optional[torch.Tensor], gamma: torch.
     return _LnResidual.apply(y, shortcut, gamma, beta, bias, keep_scale, rows_per_sample, eps)
 
 
+class _BiasGelu(torch.autograd.Function):
+    """out = GELU_erf(h + bias); backward returns (dh, dbias) with dbias = column sums of dh."""
+
+    @staticmethod
+    def forward(ctx, h, bias):
+        _need_cuda(h, "bias_gelu")
+        lib = _lib.load()
+        h = h.contiguous()
+        cols = h.shape[-1]
+        rows = h.numel() // cols
+        bias32 = _f32c(bias)
+        out = torch.empty_like(h)
+        with torch.cuda.device(h.device):
+            rc = lib.hv_bias_gelu_fwd(_ptr(h), _ptr(bias32), _ptr(out), rows, cols, _code(h), _stream(h.device))
+        check(rc, "hv_bias_gelu_fwd")
+        global LAUNCH_COUNT
+        LAUNCH_COUNT += 1
+        ctx.save_for_backward(h, bias32)
+        ctx.meta = (rows, cols, bias.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        h, bias32 = ctx.saved_tensors
+        rows, cols, bdt = ctx.meta
+        lib = _lib.load()
+        dout = dout.contiguous()
+        if dout.dtype != h.dtype:
+            dout = dout.to(h.dtype)
+        dh = torch.empty_like(h)
+        dbias = torch.empty_like(bias32)
+        with torch.cuda.device(h.device):
+            nbytes = lib.hv_bias_gelu_bwd_workspace_bytes(rows, cols)
+            workspace = torch.empty((int(nbytes),), dtype=torch.uint8, device=h.device)
+            rc = lib.hv_bias_gelu_bwd(_ptr(dout), _ptr(h), _ptr(bias32), _ptr(dh), _ptr(dbias), _ptr(workspace),
+                                      workspace.numel(), rows, cols, _code(h), _stream(h.device))
+        check(rc, "hv_bias_gelu_bwd")
+        global LAUNCH_COUNT
+        LAUNCH_COUNT += 2
+        return dh, dbias.to(bdt)
+
+
+def bias_gelu_supported(h: torch.Tensor) -> bool:
+    cols = h.shape[-1]
+    return h.is_cuda and ((h.dtype == torch.bfloat16 and cols % 128 == 0) or (h.dtype == torch.float32 and cols % 64 == 0))
+
+
+def bias_gelu(h: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """GELU (exact erf form) of ``h + bias`` where ``h`` is the bias-free fc1 output (..., cols)."""
+    return _BiasGelu.apply(h, bias)
+
+
 class _PatchMergeGather(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, H, W):

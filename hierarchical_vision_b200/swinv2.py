@@ -89,8 +89,18 @@ class Mlp(nn.Module):
         self.fc2 = nn.Linear(hidden_features or in_features, out_features or in_features)
         self.drop = nn.Dropout(drop)
 
+    def _hidden(self, x):
+        """act(fc1(x)): for the reference's default nn.GELU (exact erf form) the fc1 bias add and the
+        activation run as one kernel whose backward also yields d fc1.bias."""
+        if type(self.act) is nn.GELU and getattr(self.act, "approximate", "none") == "none" and self.fc1.bias is not None:
+            h = F.linear(x, self.fc1.weight)
+            if hvf.bias_gelu_supported(h):
+                return hvf.bias_gelu(h, self.fc1.bias)
+            return self.act(h + self.fc1.bias)
+        return self.act(self.fc1(x))
+
     def forward(self, x):
-        return self.drop(self.fc2(self.drop(self.act(self.fc1(x)))))
+        return self.drop(self.fc2(self.drop(self._hidden(x))))
 
 
 def window_partition(x, window_size):
@@ -286,7 +296,7 @@ class SwinTransformerBlock(nn.Module):
         y = self.attn._fused(x, B, H, W, self.shift_size, None, with_proj_bias=not fold1)
         x = self._post_norm(self.norm1, y, x, self.attn.proj.bias if fold1 else None)          # swinv2.py:431
         if fold2:
-            m = F.linear(self.mlp.act(self.mlp.fc1(x)), self.mlp.fc2.weight)
+            m = F.linear(self.mlp._hidden(x), self.mlp.fc2.weight)
             return self._post_norm(self.norm2, m, x, self.mlp.fc2.bias)                         # swinv2.py:434
         return self._post_norm(self.norm2, self.mlp(x), x)
 

@@ -131,6 +131,16 @@ HV_API int hv_ln_residual_bwd(const void* dout, const void* y, const float* gamm
                        float* dbeta, float* dbias, void* workspace, size_t workspace_bytes, int64_t rows, int C,
                        int64_t rows_per_sample, int y_dtype, int res_dtype, void* stream);
 
+/* ---- Mlp activation with the fc1 bias folded in: out = GELU_erf(h + bias) ------------------
+ * Replaces the bias add of `fc1` plus `self.act(x)` (nn.GELU, exact erf form), swinv2.py:61-62, and their
+ * autograd; the caller runs fc1 as a bias-free GEMM.  Backward also yields d fc1.bias (column sums of dh).
+ *   h, out, dout, dh  device (rows, cols) `dtype`; cols a multiple of 64 (fp32) / 128 (bf16)
+ *   bias, dbias       device float32 (cols) */
+HV_API int hv_bias_gelu_fwd(const void* h, const float* bias, void* out, int64_t rows, int cols, int dtype, void* stream);
+HV_API size_t hv_bias_gelu_bwd_workspace_bytes(int64_t rows, int cols);
+HV_API int hv_bias_gelu_bwd(const void* dout, const void* h, const float* bias, void* dh, float* dbias, void* workspace,
+                     size_t workspace_bytes, int64_t rows, int cols, int dtype, void* stream);
+
 /* ---- PatchMerging 2x2 gather ------------------------------------------------------------
  * Replaces the four strided slices + torch.cat of swinv2.py:484-491 (forward) and their
  * autograd (backward = the inverse permutation; every input token is read exactly once).

@@ -424,3 +424,24 @@ def test_library_reports_errors_instead_of_crashing():
     with pytest.raises(RuntimeError, match="float32 or bfloat16"):
         hvf.patch_merge_gather(torch.randn(1, 16, 8, device=DEV).half(), 4, 4)
     assert lib.hv_compiled_arch() == 100
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 100, 384), (3, 17, 768), (1, 9, 3072), (5, 3, 128)])
+def test_bias_gelu(shape, dtype):
+    """fc1 bias + exact GELU (swinv2.py:61-62) and its backward incl. d fc1.bias, vs torch in fp64."""
+    B, L, C4 = shape
+    gen = torch.Generator().manual_seed(C4 + L)
+    h = (2 * torch.randn(B, L, C4, generator=gen)).to(DEV, dtype).requires_grad_(True)
+    b = (0.5 * torch.randn(C4, generator=gen)).to(DEV).requires_grad_(True)
+    out = hvf.bias_gelu(h, b)
+    go = torch.randn(B, L, C4, generator=gen).to(DEV, dtype)
+    out.backward(go)
+    h64 = h.detach().double().cpu().requires_grad_(True)
+    b64 = b.detach().double().cpu().requires_grad_(True)
+    want = torch.nn.functional.gelu(h64 + b64)
+    want.backward(go.double().cpu())
+    tol = 1e-5 if dtype == torch.float32 else 8e-3
+    assert_close("out", out, want, tol)
+    assert_close("dh", h.grad, h64.grad, tol)
+    assert_close("dbias", b.grad, b64.grad, 1e-4 if dtype == torch.float32 else 2e-2)

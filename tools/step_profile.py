@@ -37,8 +37,8 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
 agg = defaultdict(lambda: [0, 0.0])
 for ev in prof.events():
     if ev.device_type == torch.autograd.DeviceType.CUDA:
-        n = re.sub(r"\(.*", "", ev.name.replace("void ", ""))
-        n = n.replace("at::native::", "")[:100]
+        n = ev.name.replace("void ", "").replace("(anonymous namespace)::", "").replace("at::native::", "")
+        n = re.sub(r"\(.*", "", n)[:100]
         agg[n][0] += 1
         agg[n][1] += ev.device_time
 tot = sum(v[1] for v in agg.values())
