@@ -120,16 +120,17 @@ __device__ __forceinline__ int lane_row16(int l) { return (l & 7) + 8 * ((l >> 3
 
 // Store a 16 x 32 fp32 accumulator tile (rows g, g+8 of the warp's block; 4 n-tiles) as bf16 to two
 // global rows: fragments -> per-warp shared staging -> one 16-byte store per row per lane.
+template <int PITCH = kOstPitch>
 __device__ __forceinline__ void store_tile_bf16(const float (&acc)[4][4], uint32_t ost, int g_, int t_, bf16* row0,
                                                 bf16* row1) {
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) {
-    sts32(ost + g_ * kOstPitch + nt * 16 + t_ * 4, pack_bf16x2(acc[nt][0], acc[nt][1]));
-    sts32(ost + (g_ + 8) * kOstPitch + nt * 16 + t_ * 4, pack_bf16x2(acc[nt][2], acc[nt][3]));
+    sts32(ost + g_ * PITCH + nt * 16 + t_ * 4, pack_bf16x2(acc[nt][0], acc[nt][1]));
+    sts32(ost + (g_ + 8) * PITCH + nt * 16 + t_ * 4, pack_bf16x2(acc[nt][2], acc[nt][3]));
   }
   __syncwarp();
-  const uint4 v0 = lds128(ost + g_ * kOstPitch + t_ * 16);
-  const uint4 v1 = lds128(ost + (g_ + 8) * kOstPitch + t_ * 16);
+  const uint4 v0 = lds128(ost + g_ * PITCH + t_ * 16);
+  const uint4 v1 = lds128(ost + (g_ + 8) * PITCH + t_ * 16);
   *reinterpret_cast<uint4*>(row0 + t_ * 8) = v0;
   *reinterpret_cast<uint4*>(row1 + t_ * 8) = v1;
   __syncwarp();
@@ -433,13 +434,10 @@ template <int HG> struct BwdCfg {
   static constexpr int kPitch = HG * 320 + 16;  // [q | k | v | o | dO] x HG heads + pad: odd multiple of 16
   static constexpr int kLseOff = kN * kPitch;   // HG x 64 fp32 row log-sum-exp behind the token rows
   static constexpr int kStageBytes = kN * kPitch + HG * kN * 4;
-  static constexpr int kStages = 2;
-  static constexpr int kBiasPitch = 72;                     // floats; 72 % 32 == 8 -> conflict-free float2 rows
+  static constexpr int kStages = 3;
   static constexpr int kDsPitch = 144;                      // bytes per dS~ row (64 bf16 + 16 B pad)
-  static constexpr int kOffBias = kStages * kStageBytes;    // [HG][64][72] float: bias^T * log2e, later d(bias)
-  static constexpr int kOffDs = kOffBias + HG * kN * kBiasPitch * 4;  // [HG][64 j][64 i] bf16
-  static constexpr int kOffOst = kOffDs + HG * kN * kDsPitch;
-  static constexpr int kOffVec = kOffOst + kWarps * kOstBytes;  // r[HG][64], D[HG][64] float
+  static constexpr int kOffDs = kStages * kStageBytes;      // [HG][64 j][64 i] bf16; at the end: d(bias) partials
+  static constexpr int kOffVec = kOffDs + HG * kN * kDsPitch;   // r[HG][64], D[HG][64] float
   static constexpr int kOffTau = kOffVec + 2 * HG * kN * 4;     // per-warp d(tau) partials
   static constexpr int kOffBar = kOffTau + ((kWarps * 4 + 15) / 16) * 16;
   static constexpr int kSmem = kOffBar + 2 * kStages * 8;
@@ -467,16 +465,6 @@ wattn_mma64_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ou
       mbar_init(bar_empty + 8 * s, Cfg::kWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  // bias^T in the log2 domain: biasT[hh][j][i] = log2e * table[rel(i, j)][head]
-  {
-    float* biasT = reinterpret_cast<float*>(smem + Cfg::kOffBias);
-    for (int e = threadIdx.x; e < HG * kN * kN; e += Cfg::kThreads) {
-      const int hh = e / (kN * kN), rem = e - hh * kN * kN;
-      const int j = rem / kN, i = rem - j * kN;
-      biasT[(hh * kN + j) * Cfg::kBiasPitch + i] =
-          kLog2e * __ldg(&bias_table[rel_pos_index(kWs, i, j) * g.heads + hgrp * HG + hh]);
-    }
   }
   __syncthreads();
 
@@ -554,17 +542,24 @@ wattn_mma64_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ou
   const int nWh = g.H / kWs;
   const float kNeg = kMaskValue * kLog2e;
 
-  const uint32_t ost = sbase + Cfg::kOffOst + warp * kOstBytes;
-  const float* biasT = reinterpret_cast<const float*>(smem + Cfg::kOffBias) + hh * kN * Cfg::kBiasPitch;
   const uint32_t dsT = sbase + Cfg::kOffDs + hh * kN * Cfg::kDsPitch;
+  // The bias is block-Toeplitz in (ih - jh, iw - jw).  For this thread's rows (key jh = 2*wk + rh, jw = g) and
+  // columns (query ih = nt, iw = 2t + e) only d = nt - rh + 1 in [0, 8] and e in {0, 1} vary, so 18 registers hold
+  // every bias value it will ever need, and 18 more accumulate d(bias) directly in table-bin space.
+  float bias2[9][2], dbias[9][2];
+#pragma unroll
+  for (int d = 0; d < 9; ++d)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int r = (d - 1 - 2 * wk + 7) * 15 + (2 * t_ + e - g_ + 7);
+      bias2[d][e] = kLog2e * __ldg(&bias_table[r * g.heads + head]);
+      dbias[d][e] = 0.f;
+    }
   float* rvec = reinterpret_cast<float*>(smem + Cfg::kOffVec) + hh * kN;
   float* dvec = rvec + HG * kN;
   const int arow = lane_row16(lane), acolb = (lane >> 4) * 16;
   const int brow = lane & 7, bcolb = (lane >> 3) * 16;
 
-  float dbias[8][4];
-#pragma unroll
-  for (int nt = 0; nt < 8; ++nt) dbias[nt][0] = dbias[nt][1] = dbias[nt][2] = dbias[nt][3] = 0.f;
   float dtau_acc = 0.f;
 
   const float inv_nWw = 1.0f / (float)g.nWw;
@@ -587,6 +582,8 @@ wattn_mma64_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ou
     const uint32_t ob = st + 3 * HG * 64 + hh * 64, gb = st + 4 * HG * 64 + hh * 64;
     const float* lse_s = reinterpret_cast<const float*>(smem + s * Cfg::kStageBytes + Cfg::kLseOff) + hh * kN;
     const uint32_t own = (16 * wk + arow) * Cfg::kPitch + acolb;
+    // output staging: the O segment of this warp's own 16 token rows is dead after the pre-pass below
+    const uint32_t ost = ob + (16 * wk) * Cfg::kPitch;
 
     // --- pre-pass over this warp's 16 token rows: 1/|k|, 1/|q|, D = dO . O
     uint32_t ka[2][4], va[2][4];
@@ -640,12 +637,10 @@ wattn_mma64_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ou
     for (int nt = 0; nt < 8; ++nt) {
       const int i = 8 * nt + 2 * t_;
       const float2 ri = *reinterpret_cast<const float2*>(&rvec[i]);
-      const float2 b0 = *reinterpret_cast<const float2*>(&biasT[j0 * Cfg::kBiasPitch + i]);
-      const float2 b1 = *reinterpret_cast<const float2*>(&biasT[j1 * Cfg::kBiasPitch + i]);
-      acc[nt][0] = fmaf(acc[nt][0] * cs0, ri.x, b0.x);
-      acc[nt][1] = fmaf(acc[nt][1] * cs0, ri.y, b0.y);
-      acc[nt][2] = fmaf(acc[nt][2] * cs1, ri.x, b1.x);
-      acc[nt][3] = fmaf(acc[nt][3] * cs1, ri.y, b1.y);
+      acc[nt][0] = fmaf(acc[nt][0] * cs0, ri.x, bias2[nt + 1][0]);
+      acc[nt][1] = fmaf(acc[nt][1] * cs0, ri.y, bias2[nt + 1][1]);
+      acc[nt][2] = fmaf(acc[nt][2] * cs1, ri.x, bias2[nt][0]);
+      acc[nt][3] = fmaf(acc[nt][3] * cs1, ri.y, bias2[nt][1]);
     }
     if (g.shift > 0) {
       const bool bottom = wh == nWh - 1, right = ww == g.nWw - 1;
@@ -685,7 +680,7 @@ wattn_mma64_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ou
           mma_bf16(dv[2 * half], pa[ks], gf[0], gf[1]);
           mma_bf16(dv[2 * half + 1], pa[ks], gf[2], gf[3]);
         }
-      store_tile_bf16(dv, ost, g_, t_, dqkv + tok0 * 3 * g.C + 2 * g.C + head * 32, dqkv + tok1 * 3 * g.C + 2 * g.C + head * 32);
+      store_tile_bf16<Cfg::kPitch>(dv, ost, g_, t_, dqkv + tok0 * 3 * g.C + 2 * g.C + head * 32, dqkv + tok1 * 3 * g.C + 2 * g.C + head * 32);
     }
     // --- dP^T = V dO^T, dS^T = P^T o (dP^T - D)
 #pragma unroll
@@ -708,7 +703,7 @@ wattn_mma64_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ou
       const float ds1 = bf16hi_to_f32(pw0) * (acc[nt][1] - di.y);
       const float ds2 = bf16lo_to_f32(pw1) * (acc[nt][2] - di.x);
       const float ds3 = bf16hi_to_f32(pw1) * (acc[nt][3] - di.y);
-      dbias[nt][0] += ds0; dbias[nt][1] += ds1; dbias[nt][2] += ds2; dbias[nt][3] += ds3;
+      dbias[nt + 1][0] += ds0; dbias[nt + 1][1] += ds1; dbias[nt][0] += ds2; dbias[nt][1] += ds3;
       const uint32_t w0 = pack_bf16x2(ds0 * ct0 * ri.x, ds1 * ct0 * ri.y);
       const uint32_t w1 = pack_bf16x2(ds2 * ct1 * ri.x, ds3 * ct1 * ri.y);
       dsa[nt >> 1][2 * (nt & 1)] = w0;
@@ -745,7 +740,7 @@ wattn_mma64_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ou
         dk[2 * ks][2] -= e1 * bf16lo_to_f32(ka[ks][1]);     dk[2 * ks][3] -= e1 * bf16hi_to_f32(ka[ks][1]);
         dk[2 * ks + 1][2] -= e1 * bf16lo_to_f32(ka[ks][3]); dk[2 * ks + 1][3] -= e1 * bf16hi_to_f32(ka[ks][3]);
       }
-      store_tile_bf16(dk, ost, g_, t_, dqkv + tok0 * 3 * g.C + g.C + head * 32, dqkv + tok1 * 3 * g.C + g.C + head * 32);
+      store_tile_bf16<Cfg::kPitch>(dk, ost, g_, t_, dqkv + tok0 * 3 * g.C + g.C + head * 32, dqkv + tok1 * 3 * g.C + g.C + head * 32);
     }
     named_bar_sync(1 + hh, 128);  // dS~ of all 64 keys is in shared memory
 
@@ -770,8 +765,6 @@ wattn_mma64_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ou
       uint32_t qa[2][4];
       ldsm_x4(qb + own, qa[0]);
       ldsm_x4(qb + own + 32, qa[1]);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_empty + 8 * s);  // last read of this stage
       float e0 = 0.f, e1 = 0.f;
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
@@ -790,18 +783,21 @@ wattn_mma64_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ou
         dq[2 * ks][2] -= e1 * bf16lo_to_f32(qa[ks][1]);     dq[2 * ks][3] -= e1 * bf16hi_to_f32(qa[ks][1]);
         dq[2 * ks + 1][2] -= e1 * bf16lo_to_f32(qa[ks][3]); dq[2 * ks + 1][3] -= e1 * bf16hi_to_f32(qa[ks][3]);
       }
-      store_tile_bf16(dq, ost, g_, t_, dqkv + tok0 * 3 * g.C + head * 32, dqkv + tok1 * 3 * g.C + head * 32);
+      store_tile_bf16<Cfg::kPitch>(dq, ost, g_, t_, dqkv + tok0 * 3 * g.C + head * 32, dqkv + tok1 * 3 * g.C + head * 32);
+      if (lane == 0) mbar_arrive(bar_empty + 8 * s);  // staging lives in the stage: release it only now
     }
   }
 
-  // ---- fold this CTA's d(bias) (64x64 per head, in registers) onto the 225-row table; d(tau)
-  named_bar_sync(9, Cfg::kWarps * 32);  // every compute warp is done reading bias^T
-  float* full = reinterpret_cast<float*>(smem + Cfg::kOffBias) + hh * kN * Cfg::kBiasPitch;  // [j][i]
+  // ---- fold this CTA's d(bias) bins onto the 225-row table (fixed summation order); d(tau)
+  named_bar_sync(9, Cfg::kWarps * 32);  // every compute warp is done with the dS~ buffer
+  float* bins = reinterpret_cast<float*>(smem + Cfg::kOffDs);  // [HG][4 wk][32 lanes][9][2]
+  {
+    float* mine = bins + ((hh * 4 + wk) * 32 + lane) * 18;
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
-    const int i = 8 * nt + 2 * t_;
-    *reinterpret_cast<float2*>(&full[j0 * Cfg::kBiasPitch + i]) = make_float2(dbias[nt][0], dbias[nt][1]);
-    *reinterpret_cast<float2*>(&full[j1 * Cfg::kBiasPitch + i]) = make_float2(dbias[nt][2], dbias[nt][3]);
+    for (int d = 0; d < 9; ++d) {
+      mine[2 * d] = dbias[d][0];
+      mine[2 * d + 1] = dbias[d][1];
+    }
   }
   dtau_acc = warp_sum(dtau_acc);
   float* dtau_s = reinterpret_cast<float*>(smem + Cfg::kOffTau);
@@ -811,13 +807,13 @@ wattn_mma64_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ou
   for (int r = tid_h; r < kTab; r += 128) {
     const int dh = r / 15 - 7, dw = r % 15 - 7;  // (ih - jh, iw - jw)
     float sum = 0.f;
-    for (int jh = 0; jh < kWs; ++jh) {
-      const int ih = jh + dh;
-      if (ih < 0 || ih >= kWs) continue;
-      for (int jw = 0; jw < kWs; ++jw) {
-        const int iw = jw + dw;
-        if (iw < 0 || iw >= kWs) continue;
-        sum += full[(jh * kWs + jw) * Cfg::kBiasPitch + ih * kWs + iw];
+    for (int w2 = 0; w2 < 4; ++w2) {
+      const int d = dh + 2 * w2 + 1;
+      if (d < 0 || d > 8) continue;
+      for (int g2 = 0; g2 < 8; ++g2) {
+        const int c = dw + g2;  // = 2t + e
+        if (c < 0 || c >= kWs) continue;
+        sum += bins[((hh * 4 + w2) * 32 + g2 * 4 + (c >> 1)) * 18 + 2 * d + (c & 1)];
       }
     }
     ws_dbias[((int64_t)cta * g.heads + head) * kTab + r] = sum;
