@@ -22,6 +22,8 @@
 //     once (bf16) to be re-read transposed for dQ; d(bias) is accumulated in registers over all
 //     windows of the CTA and folded to the ((2ws-1)^2, heads) table deterministically.
 // The kernel is HBM-bound (37 FLOP/B): the design goal is bytes in flight, not MMA rate.
+#include <stdlib.h>
+
 #include "hv_common.cuh"
 
 namespace hv {
@@ -586,7 +588,7 @@ wattn_mma64_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ou
     const uint32_t ost = ob + (16 * wk) * Cfg::kPitch;
 
     // --- pre-pass over this warp's 16 token rows: 1/|k|, 1/|q|, D = dO . O
-    uint32_t ka[2][4], va[2][4];
+    uint32_t ka[2][4];
     float c0, c1, r0, r1;
     {
       ldsm_x4(kb_ + own, ka[0]);
@@ -617,8 +619,6 @@ wattn_mma64_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ou
         rvec[j0] = r0; rvec[j1] = r1;
         dvec[j0] = d0; dvec[j1] = d1;
       }
-      ldsm_x4(vb_ + own, va[0]);
-      ldsm_x4(vb_ + own + 32, va[1]);
     }
     named_bar_sync(1 + hh, 128);  // r, D of all 64 rows visible; previous tile's dS~ fully consumed
 
@@ -682,7 +682,11 @@ wattn_mma64_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ou
         }
       store_tile_bf16<Cfg::kPitch>(dv, ost, g_, t_, dqkv + tok0 * 3 * g.C + 2 * g.C + head * 32, dqkv + tok1 * 3 * g.C + 2 * g.C + head * 32);
     }
-    // --- dP^T = V dO^T, dS^T = P^T o (dP^T - D)
+    // --- dP^T = V dO^T, dS^T = P^T o (dP^T - D)   (V / K fragments are (re)loaded where they are used:
+    // 16 registers less live across the softmax keeps the kernel out of local memory at 128 registers)
+    uint32_t va[2][4];
+    ldsm_x4(vb_ + own, va[0]);
+    ldsm_x4(vb_ + own + 32, va[1]);
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
@@ -725,6 +729,8 @@ wattn_mma64_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ou
           mma_bf16(dk[2 * half], dsa[ks], qf[0], qf[1]);
           mma_bf16(dk[2 * half + 1], dsa[ks], qf[2], qf[3]);
         }
+      ldsm_x4(kb_ + own, ka[0]);
+      ldsm_x4(kb_ + own + 32, ka[1]);
       float e0 = 0.f, e1 = 0.f;
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
@@ -840,7 +846,11 @@ __global__ void wattn_mma64_reduce_kernel(const float* __restrict__ ws_dbias, co
   }
 }
 
-int pick_hg(int heads) { return heads % 3 == 0 ? 3 : (heads % 2 == 0 ? 2 : 1); }
+int pick_hg(int heads) {
+  static const int forced = []() { const char* e = getenv("HV_ATTN_HEADS_PER_CTA"); return e ? atoi(e) : 0; }();
+  if (forced >= 1 && forced <= 3 && heads % forced == 0) return forced;  // tuning knob for experiments
+  return heads % 3 == 0 ? 3 : (heads % 2 == 0 ? 2 : 1);
+}
 
 int ctas_per_group(const Geom& g, int hg) {
   const int nHG = g.heads / hg;
