@@ -28,7 +28,7 @@ SIGNATURES = {
     "hv_merge_token_index": (_I, [_I, _I, _I, _P]),
     "hv_window_attn_fwd": (_I, [_P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "hv_window_attn_bwd_workspace_bytes": (_S, [_I, _I, _I, _I, _I, _I, _I]),
-    "hv_window_attn_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _S,
+    "hv_window_attn_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _S,
                                 _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "hv_ln_residual_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _L, _F, _I, _I, _P]),
     "hv_ln_residual_bwd_workspace_bytes": (_S, [_L, _I]),
@@ -58,8 +58,8 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.hv_abi_version() != 1:
-        raise RuntimeError(f"libhv_swin.so ABI version {lib.hv_abi_version()} != 1")
+    if lib.hv_abi_version() != 2:
+        raise RuntimeError(f"libhv_swin.so ABI version {lib.hv_abi_version()} != 2")
     _lib = lib
     return lib
 

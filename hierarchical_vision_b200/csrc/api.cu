@@ -18,7 +18,8 @@ int wattn_mma64_fwd(const Geom& g, const void* qkv, const float* bias_table, con
                     int mask_windows, void* out, float* lse, cudaStream_t st);
 int wattn_mma64_bwd(const Geom& g, const void* qkv, const void* out, const void* dout, const float* lse,
                     const float* bias_table, const float* tau, const float* mask, int mask_windows, void* dqkv,
-                    float* dbias_table, float* dtau, void* workspace, size_t workspace_bytes, cudaStream_t st);
+                    float* dbias_table, float* dtau, float* dq_colsum, void* workspace, size_t workspace_bytes,
+                    cudaStream_t st);
 size_t ln_residual_bwd_workspace_bytes(int64_t rows, int C);
 int ln_residual_fwd(const void* y, const void* shortcut, const float* gamma, const float* beta, const float* bias,
                     const float* keep_scale, void* out, float* mean, float* rstd, int64_t rows, int C,
@@ -186,8 +187,8 @@ size_t hv_window_attn_bwd_workspace_bytes(int B, int H, int W, int C, int heads,
 
 int hv_window_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const float* bias_table,
                        const float* tau, const float* mask, int mask_windows, void* dqkv, float* dbias_table, float* dtau,
-                       void* workspace, size_t workspace_bytes, int B, int H, int W, int C, int heads, int ws, int shift,
-                       int dtype, void* stream) {
+                       float* dq_colsum, void* workspace, size_t workspace_bytes, int B, int H, int W, int C, int heads,
+                       int ws, int shift, int dtype, void* stream) {
   if (!qkv || !out || !dout || !lse || !bias_table || !tau || !dqkv || !dbias_table || !dtau)
     HV_FAIL(HV_ERR_NULL, "hv_window_attn_bwd: NULL argument");
   Geom g;
@@ -197,8 +198,11 @@ int hv_window_attn_bwd(const void* qkv, const void* out, const void* dout, const
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (mask == nullptr && wattn_mma64_supported(g, dtype))
-    return wattn_mma64_bwd(g, qkv, out, dout, lse, bias_table, tau, mask, mask_windows, dqkv, dbias_table, dtau, workspace,
-                           workspace_bytes, st);
+    return wattn_mma64_bwd(g, qkv, out, dout, lse, bias_table, tau, mask, mask_windows, dqkv, dbias_table, dtau, dq_colsum,
+                           workspace, workspace_bytes, st);
+  if (dq_colsum != nullptr)
+    HV_FAIL(HV_ERR_SHAPE, "hv_window_attn_bwd: dq_colsum is only produced by the tensor-core kernel "
+                          "(hv_window_attn_kernel_kind() == 1 and mask == NULL)");
   return wattn_generic_bwd(g, dtype, qkv, out, dout, lse, bias_table, tau, mask, mask_windows, dqkv, dbias_table, dtau, st);
 }
 

@@ -4,24 +4,32 @@
 // Replaces reference swinv2.py:399-412 (roll + window_partition), 221-261 (head split, cosine logits,
 // logit scale, position bias, shift mask, softmax, attn @ v, head merge), 420-429 (window_reverse +
 // roll back) and their autograd.  Data layout: qkv (B, H*W, 3C) and out (B, H*W, C) stay in IMAGE token
-// order in HBM; the window gather / scatter is address arithmetic in the TMA producer and the epilogue.
+// order in HBM; the window gather / scatter is address arithmetic in the producer and the epilogue.
 //
 // Structure (persistent CTAs, one per SM, HG heads per CTA):
-//   * 4 producer warps (one per SM sub-partition): per window, 16-byte `cp.async` (LDGSTS) copies straight
-//     from the rolled image position of every token into a padded, bank-conflict-free shared-memory
-//     tile; completion is signalled on an mbarrier (`cp.async.mbarrier.arrive.noinc`), multi-stage
-//     full/empty ring.  (Measured on B200, tools/probes/tma_probe.cu: `cp.async.bulk` requests of one
-//     token row segment (64-576 B) cost ~60-90 issue cycles each per warp and top out at 2.7 TB/s from
-//     one warp, while LDGSTS from 4 warps reaches the 6.7 TB/s copy ceiling; bulk/TMA only wins for
-//     >= 4 KB contiguous requests, which a partitioned head group of a rolled window never has.)
-//   * 4 compute warps per head: each owns 16 query rows (forward) / 16 key rows (backward) of one
-//     (window, head) and keeps S/P entirely in registers (mma.sync m16n8k16 bf16, fp32 accumulate);
-//     the position bias lives in registers (forward) or shared memory (backward) for the whole
-//     kernel, the shift mask is two 16-bit patterns per thread, softmax uses ex2.
-//   * backward recomputes S from q,k and the saved row log-sum-exp; dS~ goes through shared memory
-//     once (bf16) to be re-read transposed for dQ; d(bias) is accumulated in registers over all
-//     windows of the CTA and folded to the ((2ws-1)^2, heads) table deterministically.
-// The kernel is HBM-bound (37 FLOP/B): the design goal is bytes in flight, not MMA rate.
+//   * 4 producer warps (one per SM sub-partition, 40 registers each after `setmaxnreg.dec`): per window,
+//     16-byte `cp.async` (LDGSTS) copies straight from the rolled image position of every token into a
+//     padded, bank-conflict-free shared-memory tile; completion is signalled on an mbarrier
+//     (`cp.async.mbarrier.arrive.noinc`), multi-stage full/empty ring.  (Measured on B200,
+//     tools/probes/tma_probe.cu: `cp.async.bulk` requests of one token row segment (64-576 B) cost
+//     ~60-90 issue cycles each per warp and top out at 2.7 TB/s from one warp, while LDGSTS from 4 warps
+//     reaches the 6.7 TB/s copy ceiling; bulk/TMA only wins for >= 4 KB contiguous requests, which a
+//     partitioned head group of a rolled window never has.)
+//   * 4 compute warps per head (152 registers each after `setmaxnreg.inc`): each owns 16 query rows
+//     (forward) / 16 key rows (backward) of one (window, head) and keeps S/P entirely in registers
+//     (mma.sync m16n8k16 bf16, fp32 accumulate).  The kernel is issue-bound on the CUDA cores, so every
+//     reduction that can ride on the (otherwise ~80 % idle) tensor pipe does: squared row norms and
+//     D = dO.o are diagonals of 16x16 self products, the softmax row sums are a ones-column MMA, the
+//     subtraction of D from dP is an extra k-step against a (hi, lo) bf16 split of -D, and d(bias) is
+//     accumulated over all windows of the CTA by MMAs against an identity selector.
+//   * the position bias is block-Toeplitz in (ih - jh, iw - jw): 18 registers per thread hold every value
+//     it ever needs; the shift mask is two 16-bit patterns per thread; softmax uses ex2 and skips the
+//     running maximum for heads whose logit range provably fits fp32 (|logit| <= tau + bias range).
+//   * backward recomputes S from q,k and the saved row log-sum-exp; dS goes through shared memory once
+//     (bf16, stmatrix) to be re-read transposed for dQ; d(bias), d(tau) and the column sums of dq
+//     (= gradient of q_bias) are reduced deterministically (per-CTA partials + a reduce kernel).
+// The kernel is HBM-bound by bytes (37 FLOP/B): the design goal is bytes in flight and as few
+// issue slots per logit as possible, not MMA rate.
 #include <stdlib.h>
 
 #include "hv_common.cuh"
@@ -34,6 +42,7 @@ constexpr int kWs = 8;       // window side
 constexpr int kTab = 225;    // (2*8-1)^2 bias-table rows
 constexpr int kOstPitch = 80;                 // bytes per row of the per-warp 16x32 bf16 staging tile
 constexpr int kOstBytes = 16 * kOstPitch;
+constexpr float kNoMaxRange = 64.0f;  // log2 units: skip the running max when 2*tau2 + bias range <= this
 
 // ---------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -74,6 +83,11 @@ __device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                : "r"(addr));
 }
+__device__ __forceinline__ void stsm_x4(uint32_t addr, const uint32_t (&r)[4]) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3])
+               : "memory");
+}
 __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -84,6 +98,11 @@ __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+__device__ __forceinline__ uint32_t hmul2_bf16(uint32_t a, uint32_t b) {  // packed bf16x2 product
+  uint32_t d;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -96,6 +115,12 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
   return v;
 }
+template <int N> __device__ __forceinline__ void reg_alloc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N> __device__ __forceinline__ void reg_dealloc() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
 __device__ __forceinline__ float quad_sum(float v) {
   v += __shfl_xor_sync(0xffffffffu, v, 1);
   v += __shfl_xor_sync(0xffffffffu, v, 2);
@@ -106,12 +131,28 @@ __device__ __forceinline__ float quad_max(float v) {
   v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
   return v;
 }
-__device__ __forceinline__ float sq2(uint32_t w) {  // sum of squares of a packed bf16 pair
-  const float a = bf16lo_to_f32(w), b = bf16hi_to_f32(w);
-  return fmaf(a, a, b * b);
-}
 __device__ __forceinline__ float dot2(uint32_t w, float x, float y) {  // packed pair . (x, y)
   return fmaf(bf16lo_to_f32(w), x, bf16hi_to_f32(w) * y);
+}
+
+// Row-wise dot products x_i . y_i of two 16 x 32 bf16 tiles held as m16n8k16 A fragments (two k-steps each),
+// exact in fp32, on the tensor pipe: rows 0-7 (8-15) of Y reinterpreted as a B operand are registers (0, 2)
+// ((1, 3)) of the same fragment, so X Y^T costs four MMAs and the wanted values are its diagonal.  Row g
+// (= lane / 4) lands in the quad's lane t = g / 2, element g % 2; a shuffle broadcasts it to the quad.
+// Returns s0 = x_g . y_g and s1 = x_{g+8} . y_{g+8} in every lane.
+__device__ __forceinline__ void rowdot_mma(const uint32_t (&x)[2][4], const uint32_t (&y)[2][4], int lane, float& s0,
+                                           float& s1) {
+  float n0[4] = {0.f, 0.f, 0.f, 0.f}, n1[4] = {0.f, 0.f, 0.f, 0.f};
+  mma_bf16(n0, x[0], y[0][0], y[0][2]);
+  mma_bf16(n1, x[0], y[0][1], y[0][3]);
+  mma_bf16(n0, x[1], y[1][0], y[1][2]);
+  mma_bf16(n1, x[1], y[1][1], y[1][3]);
+  const bool odd = (lane >> 2) & 1;
+  const float v0 = odd ? n0[1] : n0[0];
+  const float v1 = odd ? n1[3] : n1[2];
+  const int src = (lane & ~3) | (lane >> 3);
+  s0 = __shfl_sync(0xffffffffu, v0, src);
+  s1 = __shfl_sync(0xffffffffu, v1, src);
 }
 
 // Lane address pieces for ldmatrix.x4 (byte offsets relative to a [row][pitch] bf16 tile)
@@ -164,6 +205,14 @@ struct Cursor {
     if (win >= g.nW) { win -= g.nW; ++b; }
   }
 };
+// Stage cursor of the full/empty ring
+template <int STAGES> struct Ring {
+  int s = 0;
+  uint32_t ph = 0;
+  __device__ __forceinline__ void next() {
+    if (++s == STAGES) { s = 0; ph ^= 1u; }
+  }
+};
 // Window (wh, ww) from win: exact for win < 2^16 (float reciprocal + 0.5 guard).
 __device__ __forceinline__ void window_rc(const Geom& g, float inv_nWw, int win, int& wh, int& ww) {
   wh = __float2int_rz((win + 0.5f) * inv_nWw);
@@ -178,13 +227,42 @@ __device__ __forceinline__ int64_t tile_token(const Geom& g, int b, int row0, in
 // 1 / max(sqrt(ss), 1e-12): F.normalize's denominator (reference swinv2.py:229)
 __device__ __forceinline__ float inv_norm(float ss) { return rsqrtf(fmaxf(ss, 1e-24f)); }
 
+// Register split between the roles (only when the CTA fills the register file: 16 warps x 128)
+template <int HG> struct Regs {
+  static constexpr bool kSplit = (HG == 3);
+  static constexpr int kCompute = 152, kProducer = 40;
+};
+
+// Shift-mask patterns of one thread (rows g, g+8 of a 16-row block wq; columns 8nt+2t+e)
+struct MaskBits {
+  uint32_t colH, colW;
+  bool r0H, r1H, rW;
+  __device__ __forceinline__ void init(int wq, int g_, int t_, int hi_thr) {
+    column_band_bits(t_, hi_thr, colH, colW);
+    r0H = (2 * wq) >= hi_thr; r1H = (2 * wq + 1) >= hi_thr; rW = g_ >= hi_thr;
+  }
+  __device__ __forceinline__ void apply(float (&acc)[8][4], bool bottom, bool right, float neg) const {
+    // Only edge windows come here (warp-uniform).  The convergence point keeps ptxas from if-converting the 64
+    // predicated adds into the straight-line path that every interior window executes.
+    __syncwarp();
+    const uint32_t m0 = (bottom ? (r0H ? ~colH : colH) : 0u) | (right ? (rW ? ~colW : colW) : 0u);
+    const uint32_t m1 = (bottom ? (r1H ? ~colH : colH) : 0u) | (right ? (rW ? ~colW : colW) : 0u);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        if (m0 & (1u << (2 * nt + e))) acc[nt][e] += neg;
+        if (m1 & (1u << (2 * nt + e))) acc[nt][2 + e] += neg;
+      }
+  }
+};
+
+// =============================================================================== forward
 template <int HG> struct FwdCfg {
   static constexpr int kWarps = 4 * HG;             // compute warps
   static constexpr int kProducers = 4;              // producer warps
   static constexpr int kThreads = (kWarps + kProducers) * 32;
   static constexpr int kPitch = HG * 192 + 16;  // [q | k | v] x HG heads (64 B each) + 16 B pad: odd multiple of 16
-  static constexpr int kCpr = 12 * HG;          // 16-byte chunks per token row
-  static constexpr int kRowInstr = kWs * kCpr / 32;  // full-warp LDGSTS per window row (8 tokens)
   static constexpr int kStageBytes = kN * kPitch;
   static constexpr int kStages = 4;
   static constexpr int kOffOst = kStages * kStageBytes;
@@ -218,31 +296,31 @@ wattn_mma64_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ b
 
   if (warp >= Cfg::kWarps) {
     // ------------------------------------------------------------------ producer warps
-    // Each producer warp owns two of the window's eight token rows.  One window row = 8 tokens x kCpr
-    // 16-byte chunks = kRowInstr full-warp LDGSTS instructions; the (token, chunk) a lane handles in the
-    // m-th of them is the same for every window, so its shared/global offsets are precomputed once.
+    // Each producer warp owns two of the window's eight token rows; the (token, chunk) a lane handles in a given
+    // instruction is the same for every window, so its shared/global offsets are precomputed once.
+    if constexpr (Regs<HG>::kSplit) reg_dealloc<Regs<HG>::kProducer>();
     const int pw = warp - Cfg::kWarps;
-    int soff[Cfg::kRowInstr], gpack[Cfg::kRowInstr];
+    // One window row of one part (q, k or v) = 8 tokens x 4*HG chunks = HG full-warp instructions, so instruction
+    // (part, p) copies the same (token, chunk) pattern p for every part: HG lane constants instead of kRowInstr.
+    int p_iw[HG], p_soff[HG], p_goff[HG];
 #pragma unroll
-    for (int m = 0; m < Cfg::kRowInstr; ++m) {
-      const int q = lane + 32 * m;
-      const int iw = q / Cfg::kCpr, c = q - iw * Cfg::kCpr;
-      const int part = c / (4 * HG), within = c - part * (4 * HG);
-      soff[m] = iw * Cfg::kPitch + c * 16;
-      gpack[m] = (part * g.C + hgrp * (HG * 32) + within * 8) | (iw << 24);
+    for (int p = 0; p < HG; ++p) {
+      const int q = lane + 32 * p;
+      p_iw[p] = q / (4 * HG);
+      const int within = q - p_iw[p] * (4 * HG);
+      p_soff[p] = p_iw[p] * Cfg::kPitch + within * 16;
+      p_goff[p] = hgrp * (HG * 32) + within * 8;
     }
     const int tok_stride = 3 * g.C;
     const float inv_nWw = 1.0f / (float)g.nWw;
     Cursor cur;
     cur.init(g, cta, ctas_per_group);
-    int it = 0;
-    for (int row = cta; row < nrows; row += ctas_per_group, ++it, cur.next(g)) {
-      const int s = it % Cfg::kStages;
-      const uint32_t ph = (it / Cfg::kStages) & 1;
+    Ring<Cfg::kStages> ring;
+    for (int row = cta; row < nrows; row += ctas_per_group, cur.next(g), ring.next()) {
       int wh, ww;
       window_rc(g, inv_nWw, cur.win, wh, ww);
       const int col0 = ww * kWs + g.shift;
-      if (pw == 0) mbar_wait(bar_empty + 8 * s, ph ^ 1);  // one waiter; the other producers sleep in the barrier
+      if (pw == 0) mbar_wait(bar_empty + 8 * ring.s, ring.ph ^ 1);  // one waiter; the other producers sleep in the barrier
       named_bar_sync(10, Cfg::kProducers * 32);
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
@@ -250,38 +328,55 @@ wattn_mma64_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ b
         int irow = wh * kWs + g.shift + ih;
         if (irow >= g.H) irow -= g.H;
         const bf16* rowp = qkv + ((int64_t)cur.b * g.H + irow) * g.W * tok_stride;
-        const uint32_t dst = sbase + s * Cfg::kStageBytes + ih * (kWs * Cfg::kPitch);
+        const uint32_t dst = sbase + ring.s * Cfg::kStageBytes + ih * (kWs * Cfg::kPitch);
 #pragma unroll
-        for (int m = 0; m < Cfg::kRowInstr; ++m) {
-          int col = col0 + (gpack[m] >> 24);
+        for (int p = 0; p < HG; ++p) {
+          int col = col0 + p_iw[p];
           if (col >= g.W) col -= g.W;
-          cp_async16(dst + soff[m], rowp + col * tok_stride + (gpack[m] & 0xffffff));
+          const bf16* src = rowp + col * tok_stride + p_goff[p];
+#pragma unroll
+          for (int part = 0; part < 3; ++part) cp_async16(dst + p_soff[p] + part * (HG * 64), src + part * g.C);
         }
       }
-      cp_async_arrive(bar_full + 8 * s);
+      cp_async_arrive(bar_full + 8 * ring.s);
     }
     return;
   }
 
   // -------------------------------------------------------------------- compute warps
+  if constexpr (Regs<HG>::kSplit) reg_alloc<Regs<HG>::kCompute>();
   const int hh = warp >> 2, wq = warp & 3;
   const int head = hgrp * HG + hh;
   const int g_ = lane >> 2, t_ = lane & 3;
-  const int i0 = 16 * wq + g_, i1 = i0 + 8;  // own query slots
-  float bias2[8][4];
+  const int i0 = 16 * wq + g_, i1 = i0 + 8;  // own query slots: (ih 2wq, iw g), (ih 2wq+1, iw g)
+  const float tau2 = __ldg(&tau[head]) * kLog2e;
+  // Logits are tau2*cos + bias2 with |cos| <= 1: if 2*tau2 + (bias range) stays far inside the fp32 exponent range,
+  // exp2(logit - (tau2 + max bias)) can neither overflow nor lose the row, and the running maximum is skipped.
+  float bmx = -3.0e38f, bmn = 3.0e38f;
+  for (int r = lane; r < kTab; r += 32) {
+    const float b = kLog2e * __ldg(&bias_table[r * g.heads + head]);
+    bmx = fmaxf(bmx, b); bmn = fminf(bmn, b);
+  }
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt)
+  for (int o = 16; o > 0; o >>= 1) {
+    bmx = fmaxf(bmx, __shfl_xor_sync(0xffffffffu, bmx, o));
+    bmn = fminf(bmn, __shfl_xor_sync(0xffffffffu, bmn, o));
+  }
+  const bool use_max = !(2.0f * tau2 + (bmx - bmn) <= kNoMaxRange);
+  const float off = use_max ? 0.f : tau2 + bmx;
+  // The bias is block-Toeplitz: rows (ih = 2wq + rh, iw = g), columns (jh = nt, jw = 2t + e) only involve
+  // d = nt - rh + 1 in [0, 8] and e, so 18 registers hold every value this thread needs (pre-shifted by -off).
+  float bias2[9][2];
+#pragma unroll
+  for (int d = 0; d < 9; ++d)
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      const int j = 8 * nt + 2 * t_ + e;
-      bias2[nt][e] = kLog2e * __ldg(&bias_table[rel_pos_index(kWs, i0, j) * g.heads + head]);
-      bias2[nt][2 + e] = kLog2e * __ldg(&bias_table[rel_pos_index(kWs, i1, j) * g.heads + head]);
+      const int r = (2 * wq + 1 - d + 7) * 15 + (g_ - 2 * t_ - e + 7);
+      bias2[d][e] = kLog2e * __ldg(&bias_table[r * g.heads + head]) - off;
     }
-  const float tau2 = __ldg(&tau[head]) * kLog2e;
   const int hi_thr = kWs - g.shift;
-  uint32_t colH, colW;
-  column_band_bits(t_, hi_thr, colH, colW);
-  const bool r0H = (2 * wq) >= hi_thr, r1H = (2 * wq + 1) >= hi_thr, rW = g_ >= hi_thr;
+  MaskBits mb;
+  mb.init(wq, g_, t_, hi_thr);
   const int nWh = g.H / kWs;
   const float kNeg = kMaskValue * kLog2e;
 
@@ -289,97 +384,92 @@ wattn_mma64_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ b
   float* cvec_base = reinterpret_cast<float*>(smem + Cfg::kOffCvec);
   const int arow = lane_row16(lane), acolb = (lane >> 4) * 16;
   const int brow = lane & 7, bcolb = (lane >> 3) * 16;
+  const uint32_t own = (16 * wq + arow) * Cfg::kPitch + acolb;
 
   const float inv_nWw = 1.0f / (float)g.nWw;
   const uint32_t ones_b = (g_ == 0) ? 0x3F803F80u : 0u;  // B fragment of a ones column: row sums of P by MMA
   Cursor cur;
   cur.init(g, cta, ctas_per_group);
+  Ring<Cfg::kStages> ring;
   int it = 0;
-  for (int row = cta; row < nrows; row += ctas_per_group, ++it, cur.next(g)) {
-    const int s = it % Cfg::kStages;
-    const uint32_t ph = (it / Cfg::kStages) & 1;
+  for (int row = cta; row < nrows; row += ctas_per_group, ++it, cur.next(g), ring.next()) {
     int wh, ww;
     window_rc(g, inv_nWw, cur.win, wh, ww);
     const int row0 = wh * kWs + g.shift, col0 = ww * kWs + g.shift;
-    if (wq == 0) mbar_wait(bar_full + 8 * s, ph);  // one waiter per head; the rest sleep in the barrier
+    if (wq == 0) mbar_wait(bar_full + 8 * ring.s, ring.ph);  // one waiter per head; the rest sleep in the barrier
     named_bar_sync(1 + hh, 128);
-    const uint32_t st = sbase + s * Cfg::kStageBytes;
+    const uint32_t st = sbase + ring.s * Cfg::kStageBytes;
     const uint32_t qb = st + hh * 64, kb_ = st + HG * 64 + hh * 64, vb_ = st + 2 * HG * 64 + hh * 64;
 
-    // --- inverse norms of this warp's 16 key rows -> shared vector (scaled by tau*log2e)
+    // --- own 16 key rows and 16 query rows: inverse norms (key norms, scaled by tau*log2e, go to a shared vector)
+    uint32_t ka[2][4], qa[2][4], kf[2][4];
+    ldsm_x4(kb_ + own, ka[0]);
+    ldsm_x4(kb_ + own + 32, ka[1]);
+    ldsm_x4(qb + own, qa[0]);
+    ldsm_x4(qb + own + 32, qa[1]);
+    ldsm_x4(kb_ + brow * Cfg::kPitch + bcolb, kf[0]);
     float* cvec = cvec_base + ((it & 1) * HG + hh) * kN;
+    float r0, r1;
     {
-      uint32_t ka[2][4];
-      ldsm_x4(kb_ + (16 * wq + arow) * Cfg::kPitch + acolb, ka[0]);
-      ldsm_x4(kb_ + (16 * wq + arow) * Cfg::kPitch + acolb + 32, ka[1]);
-      float s0 = sq2(ka[0][0]) + sq2(ka[0][2]) + sq2(ka[1][0]) + sq2(ka[1][2]);
-      float s1 = sq2(ka[0][1]) + sq2(ka[0][3]) + sq2(ka[1][1]) + sq2(ka[1][3]);
-      s0 = quad_sum(s0);
-      s1 = quad_sum(s1);
+      float s0, s1;
+      rowdot_mma(ka, ka, lane, s0, s1);
       if (t_ == 0) {
         cvec[i0] = tau2 * inv_norm(s0);
         cvec[i1] = tau2 * inv_norm(s1);
       }
+      rowdot_mma(qa, qa, lane, s0, s1);
+      r0 = inv_norm(s0);
+      r1 = inv_norm(s1);
     }
     named_bar_sync(1 + hh, 128);
 
-    // --- Q fragments + own-row inverse norms
-    uint32_t qa[2][4];
-    ldsm_x4(qb + (16 * wq + arow) * Cfg::kPitch + acolb, qa[0]);
-    ldsm_x4(qb + (16 * wq + arow) * Cfg::kPitch + acolb + 32, qa[1]);
-    float r0 = quad_sum(sq2(qa[0][0]) + sq2(qa[0][2]) + sq2(qa[1][0]) + sq2(qa[1][2]));
-    float r1 = quad_sum(sq2(qa[0][1]) + sq2(qa[0][3]) + sq2(qa[1][1]) + sq2(qa[1][3]));
-    r0 = inv_norm(r0);
-    r1 = inv_norm(r1);
-
-    // --- S = Q K^T (raw dot products)
+    // --- S = Q K^T (raw dot products), K fragments double-buffered ahead of the MMAs
     float acc[8][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
+      if (nt + 1 < 8) ldsm_x4(kb_ + (8 * (nt + 1) + brow) * Cfg::kPitch + bcolb, kf[(nt + 1) & 1]);
       acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
-      uint32_t kf[4];
-      ldsm_x4(kb_ + (8 * nt + brow) * Cfg::kPitch + bcolb, kf);
-      mma_bf16(acc[nt], qa[0], kf[0], kf[1]);
-      mma_bf16(acc[nt], qa[1], kf[2], kf[3]);
+      mma_bf16(acc[nt], qa[0], kf[nt & 1][0], kf[nt & 1][1]);
+      mma_bf16(acc[nt], qa[1], kf[nt & 1][2], kf[nt & 1][3]);
     }
+    uint32_t vf[2][4];
+    ldsm_x4_t(vb_ + arow * Cfg::kPitch + acolb, vf[0]);
     // --- logits in the log2 domain: tau*cos + bias (+ mask)
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       const float2 c = *reinterpret_cast<const float2*>(&cvec[8 * nt + 2 * t_]);
-      acc[nt][0] = fmaf(acc[nt][0] * r0, c.x, bias2[nt][0]);
-      acc[nt][1] = fmaf(acc[nt][1] * r0, c.y, bias2[nt][1]);
-      acc[nt][2] = fmaf(acc[nt][2] * r1, c.x, bias2[nt][2]);
-      acc[nt][3] = fmaf(acc[nt][3] * r1, c.y, bias2[nt][3]);
+      acc[nt][0] = fmaf(acc[nt][0] * r0, c.x, bias2[nt + 1][0]);
+      acc[nt][1] = fmaf(acc[nt][1] * r0, c.y, bias2[nt + 1][1]);
+      acc[nt][2] = fmaf(acc[nt][2] * r1, c.x, bias2[nt][0]);
+      acc[nt][3] = fmaf(acc[nt][3] * r1, c.y, bias2[nt][1]);
     }
     if (g.shift > 0) {
       const bool bottom = wh == nWh - 1, right = ww == g.nWw - 1;
-      if (bottom || right) {
-        const uint32_t m0 = (bottom ? (r0H ? ~colH : colH) : 0u) | (right ? (rW ? ~colW : colW) : 0u);
-        const uint32_t m1 = (bottom ? (r1H ? ~colH : colH) : 0u) | (right ? (rW ? ~colW : colW) : 0u);
+      if (bottom || right) mb.apply(acc, bottom, right, kNeg);
+    }
+    // --- softmax numerators (rows g, g+8)
+    float mx0 = 0.f, mx1 = 0.f;
+    if (use_max) {
+      mx0 = acc[0][0]; mx1 = acc[0][2];
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt)
+      for (int nt = 0; nt < 8; ++nt) {
+        mx0 = fmaxf(mx0, fmaxf(acc[nt][0], acc[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(acc[nt][2], acc[nt][3]));
+      }
+      mx0 = quad_max(mx0);
+      mx1 = quad_max(mx1);
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            if (m0 & (1u << (2 * nt + e))) acc[nt][e] += kNeg;
-            if (m1 & (1u << (2 * nt + e))) acc[nt][2 + e] += kNeg;
-          }
+      for (int nt = 0; nt < 8; ++nt) {
+        acc[nt][0] -= mx0; acc[nt][1] -= mx0;
+        acc[nt][2] -= mx1; acc[nt][3] -= mx1;
       }
     }
-    // --- softmax (rows g, g+8)
-    float mx0 = acc[0][0], mx1 = acc[0][2];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      mx0 = fmaxf(mx0, fmaxf(acc[nt][0], acc[nt][1]));
-      mx1 = fmaxf(mx1, fmaxf(acc[nt][2], acc[nt][3]));
-    }
-    mx0 = quad_max(mx0);
-    mx1 = quad_max(mx1);
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      acc[nt][0] = ex2(acc[nt][0] - mx0);
-      acc[nt][1] = ex2(acc[nt][1] - mx0);
-      acc[nt][2] = ex2(acc[nt][2] - mx1);
-      acc[nt][3] = ex2(acc[nt][3] - mx1);
+      acc[nt][0] = ex2(acc[nt][0]);
+      acc[nt][1] = ex2(acc[nt][1]);
+      acc[nt][2] = ex2(acc[nt][2]);
+      acc[nt][3] = ex2(acc[nt][3]);
     }
     // --- O = P V ; the row sums l = P 1 ride along as a fifth n-tile whose B operand is a ones column
     float o[4][4], lacc[4];
@@ -395,31 +485,31 @@ wattn_mma64_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ b
       pa[3] = pack_bf16x2(acc[2 * ks + 1][2], acc[2 * ks + 1][3]);
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        uint32_t vf[4];
-        ldsm_x4_t(vb_ + (16 * ks + arow) * Cfg::kPitch + half * 32 + acolb, vf);
-        mma_bf16(o[2 * half], pa, vf[0], vf[1]);
-        mma_bf16(o[2 * half + 1], pa, vf[2], vf[3]);
+        const int idx = 2 * ks + half;
+        if (idx + 1 < 8)
+          ldsm_x4_t(vb_ + (16 * ((idx + 1) >> 1) + arow) * Cfg::kPitch + ((idx + 1) & 1) * 32 + acolb, vf[(idx + 1) & 1]);
+        mma_bf16(o[2 * half], pa, vf[idx & 1][0], vf[idx & 1][1]);
+        mma_bf16(o[2 * half + 1], pa, vf[idx & 1][2], vf[idx & 1][3]);
       }
       mma_bf16(lacc, pa, ones_b, ones_b);
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(bar_empty + 8 * s);  // the stage is free for the producer
+    if (lane == 0) mbar_arrive(bar_empty + 8 * ring.s);  // the stage is free for the producer
 
     // column 0 of the ones tile sits in the t == 0 lane of every quad
     const float l0 = __shfl_sync(0xffffffffu, lacc[0], lane & ~3);
     const float l1 = __shfl_sync(0xffffffffu, lacc[2], lane & ~3);
     const float inv0 = __fdividef(1.0f, l0), inv1 = __fdividef(1.0f, l1);
-    if (t_ == 0) {
+    if (t_ == 0) {  // row log-sum-exp in log2 units (what the backward kernel consumes)
       float* lp = lse + ((int64_t)row * g.heads + head) * kN;
-      lp[i0] = (mx0 + __log2f(l0)) * kLn2;
-      lp[i1] = (mx1 + __log2f(l1)) * kLn2;
+      lp[i0] = off + mx0 + __log2f(l0);
+      lp[i1] = off + mx1 + __log2f(l1);
     }
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
       o[nt][0] *= inv0; o[nt][1] *= inv0;
       o[nt][2] *= inv1; o[nt][3] *= inv1;
     }
-    // own rows: slot i0 = (ih 2*wq, iw g_), i1 = (ih 2*wq+1, iw g_)
     bf16* orow0 = out + tile_token(g, cur.b, row0, col0, 2 * wq, g_) * g.C + head * 32;
     bf16* orow1 = out + tile_token(g, cur.b, row0, col0, 2 * wq + 1, g_) * g.C + head * 32;
     store_tile_bf16(o, ost, g_, t_, orow0, orow1);
@@ -431,26 +521,29 @@ template <int HG> struct BwdCfg {
   static constexpr int kWarps = 4 * HG;
   static constexpr int kProducers = 4;
   static constexpr int kThreads = (kWarps + kProducers) * 32;
-  static constexpr int kCpr = 20 * HG;          // 16-byte chunks per token row
-  static constexpr int kRowInstr = kWs * kCpr / 32;  // full-warp LDGSTS per window row (8 tokens)
   static constexpr int kPitch = HG * 320 + 16;  // [q | k | v | o | dO] x HG heads + pad: odd multiple of 16
   static constexpr int kLseOff = kN * kPitch;   // HG x 64 fp32 row log-sum-exp behind the token rows
   static constexpr int kStageBytes = kN * kPitch + HG * kN * 4;
   static constexpr int kStages = 3;
-  static constexpr int kDsPitch = 144;                      // bytes per dS~ row (64 bf16 + 16 B pad)
-  static constexpr int kOffDs = kStages * kStageBytes;      // [HG][64 j][64 i] bf16; at the end: d(bias) partials
-  static constexpr int kOffVec = kOffDs + HG * kN * kDsPitch;   // r[HG][64], D[HG][64] float
-  static constexpr int kOffTau = kOffVec + 2 * HG * kN * 4;     // per-warp d(tau) partials
-  static constexpr int kOffBar = kOffTau + ((kWarps * 4 + 15) / 16) * 16;
+  static constexpr int kDsPitch = 144;                      // bytes per dS row (64 bf16 + 16 B pad)
+  static constexpr int kOffDs = kStages * kStageBytes;      // [HG][64 j][64 i] bf16
+  // per-head vectors over the window's 64 rows: (r, lse) float2 | -D as (hi, lo) bf16 pair | r as bf16
+  static constexpr int kVecBytes = kN * 8 + kN * 4 + kN * 2;
+  static constexpr int kOffVec = kOffDs + HG * kN * kDsPitch;
+  static constexpr int kOffRed = kOffVec + HG * kVecBytes;      // per-warp d(tau) partials, [HG][4][32] column sums
+  static constexpr int kRedBytes = kWarps * 4 + kWarps * 32 * 4;
+  static constexpr int kOffBar = kOffRed + ((kRedBytes + 15) / 16) * 16;
   static constexpr int kSmem = kOffBar + 2 * kStages * 8;
+  static constexpr int kBinBytes = kWarps * 32 * 32 * 4;        // end-of-kernel d(bias) bins, reuse the stage ring
+  static_assert(kBinBytes <= kStages * kStageBytes, "d(bias) bins must fit in the stage ring");
 };
 
 template <int HG>
 __global__ void __launch_bounds__(BwdCfg<HG>::kThreads, 1)
 wattn_mma64_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out, const bf16* __restrict__ dout,
                        const float* __restrict__ lse, const float* __restrict__ bias_table, const float* __restrict__ tau,
-                       bf16* __restrict__ dqkv, float* __restrict__ ws_dbias, float* __restrict__ ws_dtau, Geom g,
-                       int ctas_per_group) {
+                       bf16* __restrict__ dqkv, float* __restrict__ ws_dbias, float* __restrict__ ws_dtau,
+                       float* __restrict__ ws_colsum, Geom g, int ctas_per_group) {
   using Cfg = BwdCfg<HG>;
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -474,39 +567,30 @@ wattn_mma64_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ou
     // ------------------------------------------------------------------ producer warps
     // q,k,v (from qkv), o (from out), dO (from dout) token segments and the row log-sum-exp of the window;
     // same lane-constant chunk schedule as the forward producer (two window rows per producer warp).
+    if constexpr (Regs<HG>::kSplit) reg_dealloc<Regs<HG>::kProducer>();
     const int pw = warp - Cfg::kWarps;
-    // per lane-chunk: shared offset | token column, the tensor it reads (base pointer incl. channel offset)
-    // and that tensor's token stride, so that one chunk costs a wrap test, one wide multiply-add and the copy
-    int spack[Cfg::kRowInstr], stride_b[Cfg::kRowInstr];
-    const char* gbase[Cfg::kRowInstr];
+    // One window row of one part (q, k, v, o or dO) = 8 tokens x 4*HG chunks = HG full-warp instructions, so
+    // instruction (part, p) copies the same (token, chunk) pattern p for every part: HG lane constants.
+    int p_iw[HG], p_soff[HG], p_goff[HG];
 #pragma unroll
-    for (int m = 0; m < Cfg::kRowInstr; ++m) {
-      const int q = lane + 32 * m;
-      const int iw = q / Cfg::kCpr, c = q - iw * Cfg::kCpr;
-      const int part = c / (4 * HG), within = c - part * (4 * HG);
-      const int ch = hgrp * (HG * 32) + within * 8;
-      spack[m] = (iw * Cfg::kPitch + c * 16) | (iw << 24);
-      if (part < 3) {
-        gbase[m] = reinterpret_cast<const char*>(qkv + part * g.C + ch);
-        stride_b[m] = 6 * g.C;
-      } else {
-        gbase[m] = reinterpret_cast<const char*>((part == 3 ? out : dout) + ch);
-        stride_b[m] = 2 * g.C;
-      }
+    for (int p = 0; p < HG; ++p) {
+      const int q = lane + 32 * p;
+      p_iw[p] = q / (4 * HG);
+      const int within = q - p_iw[p] * (4 * HG);
+      p_soff[p] = p_iw[p] * Cfg::kPitch + within * 16;
+      p_goff[p] = hgrp * (HG * 32) + within * 8;
     }
     const float inv_nWw = 1.0f / (float)g.nWw;
     Cursor cur;
     cur.init(g, cta, ctas_per_group);
-    int it = 0;
-    for (int row = cta; row < nrows; row += ctas_per_group, ++it, cur.next(g)) {
-      const int s = it % Cfg::kStages;
-      const uint32_t ph = (it / Cfg::kStages) & 1;
+    Ring<Cfg::kStages> ring;
+    for (int row = cta; row < nrows; row += ctas_per_group, cur.next(g), ring.next()) {
       int wh, ww;
       window_rc(g, inv_nWw, cur.win, wh, ww);
       const int col0 = ww * kWs + g.shift;
-      if (pw == 0) mbar_wait(bar_empty + 8 * s, ph ^ 1);  // one waiter; the other producers sleep in the barrier
+      if (pw == 0) mbar_wait(bar_empty + 8 * ring.s, ring.ph ^ 1);  // one waiter; the other producers sleep in the barrier
       named_bar_sync(10, Cfg::kProducers * 32);
-      const uint32_t st = sbase + s * Cfg::kStageBytes;
+      const uint32_t st = sbase + ring.s * Cfg::kStageBytes;
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         const int ih = 2 * pw + r;
@@ -515,22 +599,31 @@ wattn_mma64_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ou
         const int rowtok = (cur.b * g.H + irow) * g.W;  // token index < 2^31 (checked on the host)
         const uint32_t dst = st + ih * (kWs * Cfg::kPitch);
 #pragma unroll
-        for (int m = 0; m < Cfg::kRowInstr; ++m) {
-          int col = col0 + (spack[m] >> 24);
+        for (int p = 0; p < HG; ++p) {
+          int col = col0 + p_iw[p];
           if (col >= g.W) col -= g.W;
-          cp_async16(dst + (spack[m] & 0xffffff), gbase[m] + (int64_t)(rowtok + col) * stride_b[m]);
+          const int64_t tok = rowtok + col;
+          const bf16* s3 = qkv + tok * (3 * g.C) + p_goff[p];
+          const int64_t o1 = tok * g.C + p_goff[p];
+          const uint32_t d = dst + p_soff[p];
+          cp_async16(d, s3);
+          cp_async16(d + HG * 64, s3 + g.C);
+          cp_async16(d + 2 * HG * 64, s3 + 2 * g.C);
+          cp_async16(d + 3 * HG * 64, out + o1);
+          cp_async16(d + 4 * HG * 64, dout + o1);
         }
       }
       if (pw == 0) {
         const float* lrow = lse + ((int64_t)row * g.heads + hgrp * HG) * kN;
         for (int idx = lane; idx < HG * kN / 4; idx += 32) cp_async16(st + Cfg::kLseOff + idx * 16, lrow + idx * 4);
       }
-      cp_async_arrive(bar_full + 8 * s);
+      cp_async_arrive(bar_full + 8 * ring.s);
     }
     return;
   }
 
   // -------------------------------------------------------------------- compute warps
+  if constexpr (Regs<HG>::kSplit) reg_alloc<Regs<HG>::kCompute>();
   const int hh = warp >> 2, wk = warp & 3;
   const int head = hgrp * HG + hh;
   const int g_ = lane >> 2, t_ = lane & 3;
@@ -538,133 +631,128 @@ wattn_mma64_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ou
   const float tau_h = __ldg(&tau[head]);
   const float tau2 = tau_h * kLog2e;
   const int hi_thr = kWs - g.shift;
-  uint32_t colH, colW;
-  column_band_bits(t_, hi_thr, colH, colW);
-  const bool r0H = (2 * wk) >= hi_thr, r1H = (2 * wk + 1) >= hi_thr, rW = g_ >= hi_thr;
+  MaskBits mb;
+  mb.init(wk, g_, t_, hi_thr);
   const int nWh = g.H / kWs;
   const float kNeg = kMaskValue * kLog2e;
 
   const uint32_t dsT = sbase + Cfg::kOffDs + hh * kN * Cfg::kDsPitch;
-  // The bias is block-Toeplitz in (ih - jh, iw - jw).  For this thread's rows (key jh = 2*wk + rh, jw = g) and
-  // columns (query ih = nt, iw = 2t + e) only d = nt - rh + 1 in [0, 8] and e in {0, 1} vary, so 18 registers hold
-  // every bias value it will ever need, and 18 more accumulate d(bias) directly in table-bin space.
-  float bias2[9][2], dbias[9][2];
+  // Bias, S^T orientation: rows = keys (jh = 2wk + rh, jw = g), columns = queries (ih = nt, iw = 2t + e);
+  // d = nt - rh + 1 in [0, 8]
+  float bias2[9][2];
 #pragma unroll
   for (int d = 0; d < 9; ++d)
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       const int r = (d - 1 - 2 * wk + 7) * 15 + (2 * t_ + e - g_ + 7);
       bias2[d][e] = kLog2e * __ldg(&bias_table[r * g.heads + head]);
-      dbias[d][e] = 0.f;
     }
-  float* rvec = reinterpret_cast<float*>(smem + Cfg::kOffVec) + hh * kN;
-  float* dvec = rvec + HG * kN;
+  // d(bias) of this warp's 16 x 64 block of (key, query) pairs, accumulated over all windows by the tensor pipe
+  float dbacc[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) dbacc[nt][0] = dbacc[nt][1] = dbacc[nt][2] = dbacc[nt][3] = 0.f;
+  float qsum[8];  // column sums (over this thread's rows, all windows) of dq
+#pragma unroll
+  for (int i = 0; i < 8; ++i) qsum[i] = 0.f;
+  float dtau_acc = 0.f;
+
+  unsigned char* vecs = smem + Cfg::kOffVec + hh * Cfg::kVecBytes;
+  float2* rl = reinterpret_cast<float2*>(vecs);                 // (1/|q_i|, lse2_i)
+  uint32_t* dhl = reinterpret_cast<uint32_t*>(vecs + kN * 8);   // -D_i as bf16 (hi, lo)
+  bf16* rb16 = reinterpret_cast<bf16*>(vecs + kN * 12);         // 1/|q_i| as bf16
+  const uint32_t rl_u = smem_u32(rl), dhl_u = smem_u32(dhl), rb_u = smem_u32(rb16);
+
   const int arow = lane_row16(lane), acolb = (lane >> 4) * 16;
   const int brow = lane & 7, bcolb = (lane >> 3) * 16;
-
-  float dtau_acc = 0.f;
+  const uint32_t own = (16 * wk + arow) * Cfg::kPitch + acolb;
+  // constant fragments: A = ones in k = 0, 1 (picks the (hi, lo) row of the -D operand); B = identity selector
+  uint32_t ones_a[4];
+  ones_a[0] = ones_a[1] = (t_ == 0) ? 0x3F803F80u : 0u;
+  ones_a[2] = ones_a[3] = 0u;
+  const uint32_t sel = ((2 * t_ == g_) ? 0x00003F80u : 0u) | ((2 * t_ + 1 == g_) ? 0x3F800000u : 0u);
 
   const float inv_nWw = 1.0f / (float)g.nWw;
   Cursor cur;
   cur.init(g, cta, ctas_per_group);
-  int it = 0;
-  for (int row = cta; row < nrows; row += ctas_per_group, ++it, cur.next(g)) {
-    const int s = it % Cfg::kStages;
-    const uint32_t ph = (it / Cfg::kStages) & 1;
+  Ring<Cfg::kStages> ring;
+  for (int row = cta; row < nrows; row += ctas_per_group, cur.next(g), ring.next()) {
     int wh, ww;
     window_rc(g, inv_nWw, cur.win, wh, ww);
     const int row0 = wh * kWs + g.shift, col0 = ww * kWs + g.shift;
     // own token rows: slot j0 = (ih 2*wk, iw g_), j1 = (ih 2*wk+1, iw g_)
-    const int64_t tok0 = tile_token(g, cur.b, row0, col0, 2 * wk, g_);
-    const int64_t tok1 = tile_token(g, cur.b, row0, col0, 2 * wk + 1, g_);
-    if (wk == 0) mbar_wait(bar_full + 8 * s, ph);  // one waiter per head; the rest sleep in the barrier
+    const int tok0 = (int)tile_token(g, cur.b, row0, col0, 2 * wk, g_);  // < 2^31 (checked on the host)
+    const int tok1 = (int)tile_token(g, cur.b, row0, col0, 2 * wk + 1, g_);
+    if (wk == 0) mbar_wait(bar_full + 8 * ring.s, ring.ph);  // one waiter per head; the rest sleep in the barrier
     named_bar_sync(1 + hh, 128);
-    const uint32_t st = sbase + s * Cfg::kStageBytes;
+    const uint32_t st = sbase + ring.s * Cfg::kStageBytes;
     const uint32_t qb = st + hh * 64, kb_ = st + HG * 64 + hh * 64, vb_ = st + 2 * HG * 64 + hh * 64;
     const uint32_t ob = st + 3 * HG * 64 + hh * 64, gb = st + 4 * HG * 64 + hh * 64;
-    const float* lse_s = reinterpret_cast<const float*>(smem + s * Cfg::kStageBytes + Cfg::kLseOff) + hh * kN;
-    const uint32_t own = (16 * wk + arow) * Cfg::kPitch + acolb;
+    const float* lse_s = reinterpret_cast<const float*>(smem + ring.s * Cfg::kStageBytes + Cfg::kLseOff) + hh * kN;
     // output staging: the O segment of this warp's own 16 token rows is dead after the pre-pass below
     const uint32_t ost = ob + (16 * wk) * Cfg::kPitch;
 
-    // --- pre-pass over this warp's 16 token rows: 1/|k|, 1/|q|, D = dO . O
-    uint32_t ka[2][4];
+    // --- pre-pass over this warp's 16 token rows: 1/|k|, 1/|q|, D = dO . O (tensor pipe, exact)
+    uint32_t ka[2][4], qf[2][4];
     float c0, c1, r0, r1;
     {
+      uint32_t qa[2][4], oa[2][4], ga[2][4];
       ldsm_x4(kb_ + own, ka[0]);
       ldsm_x4(kb_ + own + 32, ka[1]);
-      c0 = quad_sum(sq2(ka[0][0]) + sq2(ka[0][2]) + sq2(ka[1][0]) + sq2(ka[1][2]));
-      c1 = quad_sum(sq2(ka[0][1]) + sq2(ka[0][3]) + sq2(ka[1][1]) + sq2(ka[1][3]));
-      c0 = inv_norm(c0);
-      c1 = inv_norm(c1);
-      uint32_t qa[2][4];
       ldsm_x4(qb + own, qa[0]);
       ldsm_x4(qb + own + 32, qa[1]);
-      r0 = quad_sum(sq2(qa[0][0]) + sq2(qa[0][2]) + sq2(qa[1][0]) + sq2(qa[1][2]));
-      r1 = quad_sum(sq2(qa[0][1]) + sq2(qa[0][3]) + sq2(qa[1][1]) + sq2(qa[1][3]));
-      r0 = inv_norm(r0);
-      r1 = inv_norm(r1);
-      uint32_t oa[4], ga[4];
-      float d0 = 0.f, d1 = 0.f;
-#pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {
-        ldsm_x4(ob + own + 32 * ks, oa);
-        ldsm_x4(gb + own + 32 * ks, ga);
-        d0 += dot2(oa[0], bf16lo_to_f32(ga[0]), bf16hi_to_f32(ga[0])) + dot2(oa[2], bf16lo_to_f32(ga[2]), bf16hi_to_f32(ga[2]));
-        d1 += dot2(oa[1], bf16lo_to_f32(ga[1]), bf16hi_to_f32(ga[1])) + dot2(oa[3], bf16lo_to_f32(ga[3]), bf16hi_to_f32(ga[3]));
-      }
-      d0 = quad_sum(d0);
-      d1 = quad_sum(d1);
+      ldsm_x4(ob + own, oa[0]);
+      ldsm_x4(ob + own + 32, oa[1]);
+      ldsm_x4(gb + own, ga[0]);
+      ldsm_x4(gb + own + 32, ga[1]);
+      float d0, d1;
+      rowdot_mma(ka, ka, lane, c0, c1);
+      rowdot_mma(qa, qa, lane, r0, r1);
+      rowdot_mma(ga, oa, lane, d0, d1);
+      c0 = inv_norm(c0); c1 = inv_norm(c1);
+      r0 = inv_norm(r0); r1 = inv_norm(r1);
       if (t_ == 0) {
-        rvec[j0] = r0; rvec[j1] = r1;
-        dvec[j0] = d0; dvec[j1] = d1;
+        rl[j0] = make_float2(r0, lse_s[j0]);
+        rl[j1] = make_float2(r1, lse_s[j1]);
+        rb16[j0] = __float2bfloat16_rn(r0);
+        rb16[j1] = __float2bfloat16_rn(r1);
+        const bf16 h0 = __float2bfloat16_rn(-d0), h1 = __float2bfloat16_rn(-d1);
+        dhl[j0] = pack_bf16x2(__bfloat162float(h0), -d0 - __bfloat162float(h0));
+        dhl[j1] = pack_bf16x2(__bfloat162float(h1), -d1 - __bfloat162float(h1));
       }
     }
-    named_bar_sync(1 + hh, 128);  // r, D of all 64 rows visible; previous tile's dS~ fully consumed
+    ldsm_x4(qb + brow * Cfg::kPitch + bcolb, qf[0]);
+    named_bar_sync(1 + hh, 128);  // vectors of all 64 rows visible; previous tile's dS fully consumed
 
     // --- S^T = K Q^T for own 16 keys (rows) x 64 queries (columns), then P^T
     float acc[8][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
+      if (nt + 1 < 8) ldsm_x4(qb + (8 * (nt + 1) + brow) * Cfg::kPitch + bcolb, qf[(nt + 1) & 1]);
       acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
-      uint32_t qf[4];
-      ldsm_x4(qb + (8 * nt + brow) * Cfg::kPitch + bcolb, qf);
-      mma_bf16(acc[nt], ka[0], qf[0], qf[1]);
-      mma_bf16(acc[nt], ka[1], qf[2], qf[3]);
+      mma_bf16(acc[nt], ka[0], qf[nt & 1][0], qf[nt & 1][1]);
+      mma_bf16(acc[nt], ka[1], qf[nt & 1][2], qf[nt & 1][3]);
     }
+    uint32_t gf[2][4];
+    ldsm_x4_t(gb + arow * Cfg::kPitch + acolb, gf[0]);
     const float cs0 = c0 * tau2, cs1 = c1 * tau2;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      const int i = 8 * nt + 2 * t_;
-      const float2 ri = *reinterpret_cast<const float2*>(&rvec[i]);
-      acc[nt][0] = fmaf(acc[nt][0] * cs0, ri.x, bias2[nt + 1][0]);
-      acc[nt][1] = fmaf(acc[nt][1] * cs0, ri.y, bias2[nt + 1][1]);
-      acc[nt][2] = fmaf(acc[nt][2] * cs1, ri.x, bias2[nt][0]);
-      acc[nt][3] = fmaf(acc[nt][3] * cs1, ri.y, bias2[nt][1]);
+      const uint4 w = lds128(rl_u + (8 * nt + 2 * t_) * 8);  // (r_i, lse_i, r_i+1, lse_i+1)
+      const float rx = __uint_as_float(w.x), lx = __uint_as_float(w.y), ry = __uint_as_float(w.z), ly = __uint_as_float(w.w);
+      acc[nt][0] = fmaf(acc[nt][0] * cs0, rx, bias2[nt + 1][0]) - lx;
+      acc[nt][1] = fmaf(acc[nt][1] * cs0, ry, bias2[nt + 1][1]) - ly;
+      acc[nt][2] = fmaf(acc[nt][2] * cs1, rx, bias2[nt][0]) - lx;
+      acc[nt][3] = fmaf(acc[nt][3] * cs1, ry, bias2[nt][1]) - ly;
     }
     if (g.shift > 0) {
       const bool bottom = wh == nWh - 1, right = ww == g.nWw - 1;
-      if (bottom || right) {
-        const uint32_t m0 = (bottom ? (r0H ? ~colH : colH) : 0u) | (right ? (rW ? ~colW : colW) : 0u);
-        const uint32_t m1 = (bottom ? (r1H ? ~colH : colH) : 0u) | (right ? (rW ? ~colW : colW) : 0u);
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            if (m0 & (1u << (2 * nt + e))) acc[nt][e] += kNeg;
-            if (m1 & (1u << (2 * nt + e))) acc[nt][2 + e] += kNeg;
-          }
-      }
+      if (bottom || right) mb.apply(acc, bottom, right, kNeg);
     }
     uint32_t pa[4][4];  // P^T as A fragments (rows = keys, k = queries)
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      const float2 ls = *reinterpret_cast<const float2*>(&lse_s[8 * nt + 2 * t_]);
-      const float lx = ls.x * kLog2e, ly = ls.y * kLog2e;
-      const float p0 = ex2(acc[nt][0] - lx), p1 = ex2(acc[nt][1] - ly);
-      const float p2 = ex2(acc[nt][2] - lx), p3 = ex2(acc[nt][3] - ly);
-      pa[nt >> 1][2 * (nt & 1)] = pack_bf16x2(p0, p1);
-      pa[nt >> 1][2 * (nt & 1) + 1] = pack_bf16x2(p2, p3);
+      pa[nt >> 1][2 * (nt & 1)] = pack_bf16x2(ex2(acc[nt][0]), ex2(acc[nt][1]));
+      pa[nt >> 1][2 * (nt & 1) + 1] = pack_bf16x2(ex2(acc[nt][2]), ex2(acc[nt][3]));
     }
     // --- dV = P^T dO  (own 16 keys x 32)
     {
@@ -675,59 +763,75 @@ wattn_mma64_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ou
       for (int ks = 0; ks < 4; ++ks)
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-          uint32_t gf[4];
-          ldsm_x4_t(gb + (16 * ks + arow) * Cfg::kPitch + half * 32 + acolb, gf);
-          mma_bf16(dv[2 * half], pa[ks], gf[0], gf[1]);
-          mma_bf16(dv[2 * half + 1], pa[ks], gf[2], gf[3]);
+          const int idx = 2 * ks + half;
+          if (idx + 1 < 8)
+            ldsm_x4_t(gb + (16 * ((idx + 1) >> 1) + arow) * Cfg::kPitch + ((idx + 1) & 1) * 32 + acolb, gf[(idx + 1) & 1]);
+          mma_bf16(dv[2 * half], pa[ks], gf[idx & 1][0], gf[idx & 1][1]);
+          mma_bf16(dv[2 * half + 1], pa[ks], gf[idx & 1][2], gf[idx & 1][3]);
         }
-      store_tile_bf16<Cfg::kPitch>(dv, ost, g_, t_, dqkv + tok0 * 3 * g.C + 2 * g.C + head * 32, dqkv + tok1 * 3 * g.C + 2 * g.C + head * 32);
+      store_tile_bf16<Cfg::kPitch>(dv, ost, g_, t_, dqkv + (int64_t)tok0 * (3 * g.C) + 2 * g.C + head * 32, dqkv + (int64_t)tok1 * (3 * g.C) + 2 * g.C + head * 32);
     }
-    // --- dP^T = V dO^T, dS^T = P^T o (dP^T - D)   (V / K fragments are (re)loaded where they are used:
-    // 16 registers less live across the softmax keeps the kernel out of local memory at 128 registers)
-    uint32_t va[2][4];
-    ldsm_x4(vb_ + own, va[0]);
-    ldsm_x4(vb_ + own + 32, va[1]);
+    // --- dP^T - D = V dO^T + 1 (-D)^T : the last term is one more k-step against the (hi, lo) split of -D
+    {
+      uint32_t va[2][4];
+      ldsm_x4(vb_ + own, va[0]);
+      ldsm_x4(vb_ + own + 32, va[1]);
+      ldsm_x4(gb + brow * Cfg::kPitch + bcolb, gf[0]);
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
-      uint32_t gf[4];
-      ldsm_x4(gb + (8 * nt + brow) * Cfg::kPitch + bcolb, gf);
-      mma_bf16(acc[nt], va[0], gf[0], gf[1]);
-      mma_bf16(acc[nt], va[1], gf[2], gf[3]);
+      for (int nt = 0; nt < 8; ++nt) {
+        if (nt + 1 < 8) ldsm_x4(gb + (8 * (nt + 1) + brow) * Cfg::kPitch + bcolb, gf[(nt + 1) & 1]);
+        uint32_t dneg;
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(dneg) : "r"(dhl_u + (8 * nt + g_) * 4) : "memory");
+        acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+        mma_bf16(acc[nt], va[0], gf[nt & 1][0], gf[nt & 1][1]);
+        mma_bf16(acc[nt], va[1], gf[nt & 1][2], gf[nt & 1][3]);
+        mma_bf16(acc[nt], ones_a, dneg, dneg);
+      }
     }
-    const float ct0 = c0 * tau_h, ct1 = c1 * tau_h;
-    uint32_t dsa[4][4];  // dS~^T = dS^T * tau * r_i * c_j as A fragments
+    // --- dS^T = P^T o (dP^T - D) in packed bf16; d(bias) += dS^T via identity-selector MMAs;
+    //     then the two scaled copies: dS * c_j (to shared memory, A operand of dQ) and dS * r_i (registers, A of dK)
+    {
+      const uint32_t cp0 = pack_bf16x2(c0, c0), cp1 = pack_bf16x2(c1, c1);
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const int i = 8 * nt + 2 * t_;
-      const float2 di = *reinterpret_cast<const float2*>(&dvec[i]);
-      const float2 ri = *reinterpret_cast<const float2*>(&rvec[i]);
-      const uint32_t pw0 = pa[nt >> 1][2 * (nt & 1)], pw1 = pa[nt >> 1][2 * (nt & 1) + 1];
-      const float ds0 = bf16lo_to_f32(pw0) * (acc[nt][0] - di.x);
-      const float ds1 = bf16hi_to_f32(pw0) * (acc[nt][1] - di.y);
-      const float ds2 = bf16lo_to_f32(pw1) * (acc[nt][2] - di.x);
-      const float ds3 = bf16hi_to_f32(pw1) * (acc[nt][3] - di.y);
-      dbias[nt + 1][0] += ds0; dbias[nt + 1][1] += ds1; dbias[nt][0] += ds2; dbias[nt][1] += ds3;
-      const uint32_t w0 = pack_bf16x2(ds0 * ct0 * ri.x, ds1 * ct0 * ri.y);
-      const uint32_t w1 = pack_bf16x2(ds2 * ct1 * ri.x, ds3 * ct1 * ri.y);
-      dsa[nt >> 1][2 * (nt & 1)] = w0;
-      dsa[nt >> 1][2 * (nt & 1) + 1] = w1;
-      sts32(dsT + j0 * Cfg::kDsPitch + i * 2, w0);
-      sts32(dsT + j1 * Cfg::kDsPitch + i * 2, w1);
+      for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int nt = 2 * ks + hf;
+          pa[ks][2 * hf] = hmul2_bf16(pa[ks][2 * hf], pack_bf16x2(acc[nt][0], acc[nt][1]));
+          pa[ks][2 * hf + 1] = hmul2_bf16(pa[ks][2 * hf + 1], pack_bf16x2(acc[nt][2], acc[nt][3]));
+        }
+        mma_bf16(dbacc[2 * ks], pa[ks], sel, 0u);
+        mma_bf16(dbacc[2 * ks + 1], pa[ks], 0u, sel);
+        uint32_t dsc[4];
+        dsc[0] = hmul2_bf16(pa[ks][0], cp0);
+        dsc[1] = hmul2_bf16(pa[ks][1], cp1);
+        dsc[2] = hmul2_bf16(pa[ks][2], cp0);
+        dsc[3] = hmul2_bf16(pa[ks][3], cp1);
+        stsm_x4(dsT + (16 * wk + arow) * Cfg::kDsPitch + ks * 32 + acolb, dsc);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t rp;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(rp) : "r"(rb_u + (8 * (2 * ks + hf) + 2 * t_) * 2) : "memory");
+          pa[ks][2 * hf] = hmul2_bf16(pa[ks][2 * hf], rp);
+          pa[ks][2 * hf + 1] = hmul2_bf16(pa[ks][2 * hf + 1], rp);
+        }
+      }
     }
-    // --- dK = dS~^T Q, then the L2-normalisation backward: dk = M - c^2 (k.M) k
+    // --- dK: M = (dS r)^T Q, then dk = tau c (M - c^2 (k.M) k)   (scale and L2-normalisation backward)
     {
       float dk[4][4];
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) dk[nt][0] = dk[nt][1] = dk[nt][2] = dk[nt][3] = 0.f;
+      ldsm_x4_t(qb + arow * Cfg::kPitch + acolb, qf[0]);
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks)
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-          uint32_t qf[4];
-          ldsm_x4_t(qb + (16 * ks + arow) * Cfg::kPitch + half * 32 + acolb, qf);
-          mma_bf16(dk[2 * half], dsa[ks], qf[0], qf[1]);
-          mma_bf16(dk[2 * half + 1], dsa[ks], qf[2], qf[3]);
+          const int idx = 2 * ks + half;
+          if (idx + 1 < 8)
+            ldsm_x4_t(qb + (16 * ((idx + 1) >> 1) + arow) * Cfg::kPitch + ((idx + 1) & 1) * 32 + acolb, qf[(idx + 1) & 1]);
+          mma_bf16(dk[2 * half], pa[ks], qf[idx & 1][0], qf[idx & 1][1]);
+          mma_bf16(dk[2 * half + 1], pa[ks], qf[idx & 1][2], qf[idx & 1][3]);
         }
       ldsm_x4(kb_ + own, ka[0]);
       ldsm_x4(kb_ + own + 32, ka[1]);
@@ -737,35 +841,44 @@ wattn_mma64_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ou
         e0 += dot2(ka[ks][0], dk[2 * ks][0], dk[2 * ks][1]) + dot2(ka[ks][2], dk[2 * ks + 1][0], dk[2 * ks + 1][1]);
         e1 += dot2(ka[ks][1], dk[2 * ks][2], dk[2 * ks][3]) + dot2(ka[ks][3], dk[2 * ks + 1][2], dk[2 * ks + 1][3]);
       }
-      e0 = quad_sum(e0) * c0 * c0;
-      e1 = quad_sum(e1) * c1 * c1;
+      const float tc0 = tau_h * c0, tc1 = tau_h * c1;
+      e0 = -quad_sum(e0) * c0 * c0 * tc0;
+      e1 = -quad_sum(e1) * c1 * c1 * tc1;
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
-        dk[2 * ks][0] -= e0 * bf16lo_to_f32(ka[ks][0]);     dk[2 * ks][1] -= e0 * bf16hi_to_f32(ka[ks][0]);
-        dk[2 * ks + 1][0] -= e0 * bf16lo_to_f32(ka[ks][2]); dk[2 * ks + 1][1] -= e0 * bf16hi_to_f32(ka[ks][2]);
-        dk[2 * ks][2] -= e1 * bf16lo_to_f32(ka[ks][1]);     dk[2 * ks][3] -= e1 * bf16hi_to_f32(ka[ks][1]);
-        dk[2 * ks + 1][2] -= e1 * bf16lo_to_f32(ka[ks][3]); dk[2 * ks + 1][3] -= e1 * bf16hi_to_f32(ka[ks][3]);
+        dk[2 * ks][0] = fmaf(dk[2 * ks][0], tc0, e0 * bf16lo_to_f32(ka[ks][0]));
+        dk[2 * ks][1] = fmaf(dk[2 * ks][1], tc0, e0 * bf16hi_to_f32(ka[ks][0]));
+        dk[2 * ks + 1][0] = fmaf(dk[2 * ks + 1][0], tc0, e0 * bf16lo_to_f32(ka[ks][2]));
+        dk[2 * ks + 1][1] = fmaf(dk[2 * ks + 1][1], tc0, e0 * bf16hi_to_f32(ka[ks][2]));
+        dk[2 * ks][2] = fmaf(dk[2 * ks][2], tc1, e1 * bf16lo_to_f32(ka[ks][1]));
+        dk[2 * ks][3] = fmaf(dk[2 * ks][3], tc1, e1 * bf16hi_to_f32(ka[ks][1]));
+        dk[2 * ks + 1][2] = fmaf(dk[2 * ks + 1][2], tc1, e1 * bf16lo_to_f32(ka[ks][3]));
+        dk[2 * ks + 1][3] = fmaf(dk[2 * ks + 1][3], tc1, e1 * bf16hi_to_f32(ka[ks][3]));
       }
-      store_tile_bf16<Cfg::kPitch>(dk, ost, g_, t_, dqkv + tok0 * 3 * g.C + g.C + head * 32, dqkv + tok1 * 3 * g.C + g.C + head * 32);
+      store_tile_bf16<Cfg::kPitch>(dk, ost, g_, t_, dqkv + (int64_t)tok0 * (3 * g.C) + g.C + head * 32, dqkv + (int64_t)tok1 * (3 * g.C) + g.C + head * 32);
     }
-    named_bar_sync(1 + hh, 128);  // dS~ of all 64 keys is in shared memory
+    named_bar_sync(1 + hh, 128);  // dS c of all 64 keys is in shared memory
 
-    // --- dQ = dS~ K for own 16 queries, dq = M - r^2 (q.M) q ; d(tau) += q.M
+    // --- dQ: M = (dS c) K for own 16 queries, dq = tau r (M - r^2 (q.M) q) ; d(tau) += r (q.M)
     {
       float dq[4][4];
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) dq[nt][0] = dq[nt][1] = dq[nt][2] = dq[nt][3] = 0.f;
+      uint32_t da[2][4];
+      // A = dS[i][j] read transposed from dsT[j][i]: matrix m -> j half (m>>1), i half (m&1)
+      const uint32_t da_addr = dsT + ((lane & 7) + 8 * (lane >> 4)) * Cfg::kDsPitch + (16 * wk + 8 * ((lane >> 3) & 1)) * 2;
+      ldsm_x4_t(da_addr, da[0]);
+      ldsm_x4_t(kb_ + arow * Cfg::kPitch + acolb, qf[0]);
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
-        uint32_t da[4];
-        // A = dS~[i][j] read transposed from dsT[j][i]: matrix m -> j half (m>>1), i half (m&1)
-        ldsm_x4_t(dsT + (16 * ks + (lane & 7) + 8 * (lane >> 4)) * Cfg::kDsPitch + (16 * wk + 8 * ((lane >> 3) & 1)) * 2, da);
+        if (ks + 1 < 4) ldsm_x4_t(da_addr + 16 * (ks + 1) * Cfg::kDsPitch, da[(ks + 1) & 1]);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-          uint32_t kf[4];
-          ldsm_x4_t(kb_ + (16 * ks + arow) * Cfg::kPitch + half * 32 + acolb, kf);
-          mma_bf16(dq[2 * half], da, kf[0], kf[1]);
-          mma_bf16(dq[2 * half + 1], da, kf[2], kf[3]);
+          const int idx = 2 * ks + half;
+          if (idx + 1 < 8)
+            ldsm_x4_t(kb_ + (16 * ((idx + 1) >> 1) + arow) * Cfg::kPitch + ((idx + 1) & 1) * 32 + acolb, qf[(idx + 1) & 1]);
+          mma_bf16(dq[2 * half], da[ks & 1], qf[idx & 1][0], qf[idx & 1][1]);
+          mma_bf16(dq[2 * half + 1], da[ks & 1], qf[idx & 1][2], qf[idx & 1][3]);
         }
       }
       uint32_t qa[2][4];
@@ -779,70 +892,103 @@ wattn_mma64_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ou
       }
       e0 = quad_sum(e0);
       e1 = quad_sum(e1);
-      if (t_ == 0) dtau_acc += e0 + e1;
-      e0 *= r0 * r0;
-      e1 *= r1 * r1;
+      if (t_ == 0) dtau_acc += fmaf(e0, r0, e1 * r1);
+      const float tr0 = tau_h * r0, tr1 = tau_h * r1;
+      e0 *= -r0 * r0 * tr0;
+      e1 *= -r1 * r1 * tr1;
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
-        dq[2 * ks][0] -= e0 * bf16lo_to_f32(qa[ks][0]);     dq[2 * ks][1] -= e0 * bf16hi_to_f32(qa[ks][0]);
-        dq[2 * ks + 1][0] -= e0 * bf16lo_to_f32(qa[ks][2]); dq[2 * ks + 1][1] -= e0 * bf16hi_to_f32(qa[ks][2]);
-        dq[2 * ks][2] -= e1 * bf16lo_to_f32(qa[ks][1]);     dq[2 * ks][3] -= e1 * bf16hi_to_f32(qa[ks][1]);
-        dq[2 * ks + 1][2] -= e1 * bf16lo_to_f32(qa[ks][3]); dq[2 * ks + 1][3] -= e1 * bf16hi_to_f32(qa[ks][3]);
+        dq[2 * ks][0] = fmaf(dq[2 * ks][0], tr0, e0 * bf16lo_to_f32(qa[ks][0]));
+        dq[2 * ks][1] = fmaf(dq[2 * ks][1], tr0, e0 * bf16hi_to_f32(qa[ks][0]));
+        dq[2 * ks + 1][0] = fmaf(dq[2 * ks + 1][0], tr0, e0 * bf16lo_to_f32(qa[ks][2]));
+        dq[2 * ks + 1][1] = fmaf(dq[2 * ks + 1][1], tr0, e0 * bf16hi_to_f32(qa[ks][2]));
+        dq[2 * ks][2] = fmaf(dq[2 * ks][2], tr1, e1 * bf16lo_to_f32(qa[ks][1]));
+        dq[2 * ks][3] = fmaf(dq[2 * ks][3], tr1, e1 * bf16hi_to_f32(qa[ks][1]));
+        dq[2 * ks + 1][2] = fmaf(dq[2 * ks + 1][2], tr1, e1 * bf16lo_to_f32(qa[ks][3]));
+        dq[2 * ks + 1][3] = fmaf(dq[2 * ks + 1][3], tr1, e1 * bf16hi_to_f32(qa[ks][3]));
       }
-      store_tile_bf16<Cfg::kPitch>(dq, ost, g_, t_, dqkv + tok0 * 3 * g.C + head * 32, dqkv + tok1 * 3 * g.C + head * 32);
-      if (lane == 0) mbar_arrive(bar_empty + 8 * s);  // staging lives in the stage: release it only now
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        qsum[2 * nt] += dq[nt][0] + dq[nt][2];
+        qsum[2 * nt + 1] += dq[nt][1] + dq[nt][3];
+      }
+      store_tile_bf16<Cfg::kPitch>(dq, ost, g_, t_, dqkv + (int64_t)tok0 * (3 * g.C) + head * 32, dqkv + (int64_t)tok1 * (3 * g.C) + head * 32);
+      if (lane == 0) mbar_arrive(bar_empty + 8 * ring.s);  // staging lives in the stage: release it only now
     }
   }
 
-  // ---- fold this CTA's d(bias) bins onto the 225-row table (fixed summation order); d(tau)
-  named_bar_sync(9, Cfg::kWarps * 32);  // every compute warp is done with the dS~ buffer
-  float* bins = reinterpret_cast<float*>(smem + Cfg::kOffDs);  // [HG][4 wk][32 lanes][9][2]
-  {
-    float* mine = bins + ((hh * 4 + wk) * 32 + lane) * 18;
+  // ---- end of kernel: fold this CTA's d(bias) accumulators onto the 225-row table (fixed summation order),
+  //      d(tau) and the dq / dv column sums.  The stage ring is idle by now (every load was consumed).
+  named_bar_sync(9, Cfg::kWarps * 32);
+  float* bins = reinterpret_cast<float*>(smem);  // [HG][4 wk][32 slots (nt*4 + c)][32 lanes]
 #pragma unroll
-    for (int d = 0; d < 9; ++d) {
-      mine[2 * d] = dbias[d][0];
-      mine[2 * d + 1] = dbias[d][1];
-    }
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) bins[((hh * 4 + wk) * 32 + nt * 4 + c) * 32 + lane] = dbacc[nt][c];
+  // column sums: reduce over g (lanes with equal t), lanes 0-3 then hold columns 8nt + 2t + e
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) qsum[i] += __shfl_xor_sync(0xffffffffu, qsum[i], o);
   }
   dtau_acc = warp_sum(dtau_acc);
-  float* dtau_s = reinterpret_cast<float*>(smem + Cfg::kOffTau);
+  float* dtau_s = reinterpret_cast<float*>(smem + Cfg::kOffRed);
+  float* csum_s = dtau_s + Cfg::kWarps;  // [HG][4 wk][32]
   if (lane == 0) dtau_s[warp] = dtau_acc;
+  if (lane < 4) {
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) csum_s[(hh * 4 + wk) * 32 + 8 * nt + 2 * lane + e] = qsum[2 * nt + e];
+  }
   named_bar_sync(9, Cfg::kWarps * 32);
   const int tid_h = wk * 32 + lane;
   for (int r = tid_h; r < kTab; r += 128) {
     const int dh = r / 15 - 7, dw = r % 15 - 7;  // (ih - jh, iw - jw)
     float sum = 0.f;
-    for (int w2 = 0; w2 < 4; ++w2) {
-      const int d = dh + 2 * w2 + 1;
-      if (d < 0 || d > 8) continue;
-      for (int g2 = 0; g2 < 8; ++g2) {
-        const int c = dw + g2;  // = 2t + e
-        if (c < 0 || c >= kWs) continue;
-        sum += bins[((hh * 4 + w2) * 32 + g2 * 4 + (c >> 1)) * 18 + 2 * d + (c & 1)];
+    for (int jh = 0; jh < kWs; ++jh) {
+      const int ih = jh + dh;
+      if (ih < 0 || ih >= kWs) continue;
+      for (int jw = 0; jw < kWs; ++jw) {
+        const int iw = jw + dw;
+        if (iw < 0 || iw >= kWs) continue;
+        sum += bins[((hh * 4 + (jh >> 1)) * 32 + ih * 4 + (jh & 1) * 2 + (iw & 1)) * 32 + jw * 4 + (iw >> 1)];
       }
     }
     ws_dbias[((int64_t)cta * g.heads + head) * kTab + r] = sum;
   }
-  if (tid_h == 0)
-    ws_dtau[cta * g.heads + head] =
-        (dtau_s[4 * hh] + dtau_s[4 * hh + 1] + dtau_s[4 * hh + 2] + dtau_s[4 * hh + 3]) / tau_h;
+  if (tid_h == 0) ws_dtau[cta * g.heads + head] = dtau_s[4 * hh] + dtau_s[4 * hh + 1] + dtau_s[4 * hh + 2] + dtau_s[4 * hh + 3];
+  if (tid_h < 32) {
+    float s = 0.f;
+#pragma unroll
+    for (int w2 = 0; w2 < 4; ++w2) s += csum_s[(hh * 4 + w2) * 32 + tid_h];
+    ws_colsum[(int64_t)cta * g.C + head * 32 + tid_h] = s;
+  }
 }
 
-// Sum the per-CTA partial tables: one thread per (head, table row) and one per (head) for d(tau).
-__global__ void wattn_mma64_reduce_kernel(const float* __restrict__ ws_dbias, const float* __restrict__ ws_dtau, int nparts,
-                                          int heads, float* __restrict__ dbias_table, float* __restrict__ dtau) {
+// Sum the per-CTA partials: one thread per (head, table row), per (head) for d(tau), per channel for the dq column sums.
+__global__ void wattn_mma64_reduce_kernel(const float* __restrict__ ws_dbias, const float* __restrict__ ws_dtau,
+                                          const float* __restrict__ ws_colsum, int nparts, int heads, int C,
+                                          float* __restrict__ dbias_table, float* __restrict__ dtau,
+                                          float* __restrict__ dq_colsum) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int per_head = kTab + 1;
-  if (idx >= heads * per_head) return;
-  const int head = idx / per_head, r = idx - head * per_head;
-  float s = 0.f;
-  if (r < kTab) {
-    for (int c = 0; c < nparts; ++c) s += ws_dbias[((int64_t)c * heads + head) * kTab + r];
-    dbias_table[r * heads + head] = s;
-  } else {
-    for (int c = 0; c < nparts; ++c) s += ws_dtau[c * heads + head];
-    dtau[head] = s;
+  const int n_tab = heads * per_head;
+  if (idx < n_tab) {
+    const int head = idx / per_head, r = idx - head * per_head;
+    float s = 0.f;
+    if (r < kTab) {
+      for (int c = 0; c < nparts; ++c) s += ws_dbias[((int64_t)c * heads + head) * kTab + r];
+      dbias_table[r * heads + head] = s;
+    } else {
+      for (int c = 0; c < nparts; ++c) s += ws_dtau[c * heads + head];
+      dtau[head] = s;
+    }
+  } else if (idx < n_tab + C && dq_colsum != nullptr) {
+    const int k = idx - n_tab;
+    float s = 0.f;
+    for (int c = 0; c < nparts; ++c) s += ws_colsum[(int64_t)c * C + k];
+    dq_colsum[k] = s;
   }
 }
 
@@ -875,19 +1021,21 @@ int launch_fwd(const Geom& g, const void* qkv, const float* bias_table, const fl
 
 template <int HG>
 int launch_bwd(const Geom& g, const void* qkv, const void* out, const void* dout, const float* lse, const float* bias_table,
-               const float* tau, void* dqkv, float* dbias_table, float* dtau, float* ws, cudaStream_t st) {
+               const float* tau, void* dqkv, float* dbias_table, float* dtau, float* dq_colsum, float* ws, cudaStream_t st) {
   using Cfg = BwdCfg<HG>;
   auto kern = wattn_mma64_bwd_kernel<HG>;
   HV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
   const int per = ctas_per_group(g, HG);
   const int grid = per * (g.heads / HG);
   float* ws_dbias = ws;
-  float* ws_dtau = ws + (size_t)per * g.heads * kTab;
+  float* ws_dtau = ws_dbias + (size_t)per * g.heads * kTab;
+  float* ws_colsum = ws_dtau + (size_t)per * g.heads;
   kern<<<grid, Cfg::kThreads, Cfg::kSmem, st>>>((const bf16*)qkv, (const bf16*)out, (const bf16*)dout, lse, bias_table, tau,
-                                                (bf16*)dqkv, ws_dbias, ws_dtau, g, per);
+                                                (bf16*)dqkv, ws_dbias, ws_dtau, ws_colsum, g, per);
   HV_LAUNCH_OK("wattn_mma64_bwd_kernel");
-  const int n = g.heads * (kTab + 1);
-  wattn_mma64_reduce_kernel<<<(n + 127) / 128, 128, 0, st>>>(ws_dbias, ws_dtau, per, g.heads, dbias_table, dtau);
+  const int n = g.heads * (kTab + 1) + g.C;
+  wattn_mma64_reduce_kernel<<<(n + 127) / 128, 128, 0, st>>>(ws_dbias, ws_dtau, ws_colsum, per, g.heads, g.C, dbias_table,
+                                                            dtau, dq_colsum);
   HV_LAUNCH_OK("wattn_mma64_reduce_kernel");
   return HV_OK;
 }
@@ -901,8 +1049,8 @@ bool wattn_mma64_supported(const Geom& g, int dtype) {
 }
 
 size_t wattn_mma64_bwd_workspace_bytes(const Geom& g) {
-  // per-CTA partial tables; sized for the largest grid (one CTA per SM)
-  return (size_t)num_sms() * g.heads * (kTab + 1) * sizeof(float) + 256;
+  // per-CTA partials (bias table, tau, dq/dv column sums); sized for the largest grid (one CTA per SM)
+  return (size_t)num_sms() * (g.heads * (kTab + 1) + g.C) * sizeof(float) + 256;
 }
 
 int wattn_mma64_fwd(const Geom& g, const void* qkv, const float* bias_table, const float* tau, const float* mask,
@@ -918,7 +1066,8 @@ int wattn_mma64_fwd(const Geom& g, const void* qkv, const float* bias_table, con
 
 int wattn_mma64_bwd(const Geom& g, const void* qkv, const void* out, const void* dout, const float* lse,
                     const float* bias_table, const float* tau, const float* mask, int mask_windows, void* dqkv,
-                    float* dbias_table, float* dtau, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                    float* dbias_table, float* dtau, float* dq_colsum, void* workspace, size_t workspace_bytes,
+                    cudaStream_t st) {
   (void)mask; (void)mask_windows;
   if (!aligned16(qkv) || !aligned16(out) || !aligned16(dout) || !aligned16(dqkv) || !aligned16(lse))
     HV_FAIL(HV_ERR_ALIGN, "window_attn_bwd: tensors must be 16-byte aligned");
@@ -926,9 +1075,9 @@ int wattn_mma64_bwd(const Geom& g, const void* qkv, const void* out, const void*
     HV_FAIL(HV_ERR_WORKSPACE, "window_attn_bwd: workspace of %zu bytes required", wattn_mma64_bwd_workspace_bytes(g));
   float* ws = static_cast<float*>(workspace);
   switch (pick_hg(g.heads)) {
-    case 3: return launch_bwd<3>(g, qkv, out, dout, lse, bias_table, tau, dqkv, dbias_table, dtau, ws, st);
-    case 2: return launch_bwd<2>(g, qkv, out, dout, lse, bias_table, tau, dqkv, dbias_table, dtau, ws, st);
-    default: return launch_bwd<1>(g, qkv, out, dout, lse, bias_table, tau, dqkv, dbias_table, dtau, ws, st);
+    case 3: return launch_bwd<3>(g, qkv, out, dout, lse, bias_table, tau, dqkv, dbias_table, dtau, dq_colsum, ws, st);
+    case 2: return launch_bwd<2>(g, qkv, out, dout, lse, bias_table, tau, dqkv, dbias_table, dtau, dq_colsum, ws, st);
+    default: return launch_bwd<1>(g, qkv, out, dout, lse, bias_table, tau, dqkv, dbias_table, dtau, dq_colsum, ws, st);
   }
 }
 

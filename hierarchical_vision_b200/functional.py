@@ -81,14 +81,14 @@ def window_attention_bwd_workspace(qkv, B, H, W, C, heads, ws):
 
 
 def window_attention_bwd_raw(qkv, out, dout, lse, bias_table, tau, mask, dqkv, dbias, dtau, workspace,
-                             B, H, W, C, heads, ws, shift):
+                             B, H, W, C, heads, ws, shift, dq_colsum=None):
     """Enqueue hv_window_attn_bwd on the current stream; every tensor is caller-allocated."""
     lib = _lib.load()
     with torch.cuda.device(qkv.device):
         rc = lib.hv_window_attn_bwd(_ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(bias_table), _ptr(tau), _ptr(mask),
                                     mask.shape[0] if mask is not None else 0, _ptr(dqkv), _ptr(dbias), _ptr(dtau),
-                                    _ptr(workspace), workspace.numel(), B, H, W, C, heads, ws, shift, _code(qkv),
-                                    _stream(qkv.device))
+                                    _ptr(dq_colsum), _ptr(workspace), workspace.numel(), B, H, W, C, heads, ws, shift,
+                                    _code(qkv), _stream(qkv.device))
     check(rc, "hv_window_attn_bwd")
 
 

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define HV_ABI_VERSION 1
+#define HV_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define HV_API __attribute__((visibility("default")))
@@ -87,7 +87,9 @@ HV_API int hv_merge_token_index(int B, int H, int W, int64_t* out);
  *         else device float32 (mask_windows, N, N) added to window (row % mask_windows) and the
  *         in-kernel shift mask is NOT applied (WindowAttention.forward(x, mask) semantics)
  *   out   device, (B, H*W, C) `dtype`, image token order
- *   lse   device float32 (B*nW, heads, N): row log-sum-exp (natural log), saved for backward
+ *   lse   device float32 (B*nW, heads, N): softmax row statistics saved for hv_window_attn_bwd.  Opaque to the
+ *         caller: row log-sum-exp in natural-log units (generic kernel) or log2 units (tensor-core kernel); the
+ *         pair fwd/bwd of one geometry always dispatches to the same kernel kind.
  */
 HV_API int hv_window_attn_fwd(const void* qkv, const float* bias_table, const float* tau, const float* mask,
                        int mask_windows, void* out, float* lse, int B, int H, int W, int C, int heads,
@@ -100,11 +102,17 @@ HV_API size_t hv_window_attn_bwd_workspace_bytes(int B, int H, int W, int C, int
  *   dqkv  device (B, H*W, 3C) `dtype`: fully overwritten
  *   dbias_table device float32 ((2ws-1)^2, heads): overwritten with d loss / d bias_table
  *   dtau  device float32 (heads): overwritten with d loss / d tau
+ *   dq_colsum  NULL, or device float32 (C): overwritten with the sum over all tokens of the q third of dqkv,
+ *         i.e. the gradient of WindowAttention.q_bias (swinv2.py:193-195, 211-220), so that no separate column
+ *         reduction over dqkv is needed (v_bias needs none: softmax rows sum to one, so v_bias passes through the
+ *         attention as a plain additive term of `out`; k has no bias).  Only the tensor-core kernel
+ *         (hv_window_attn_kernel_kind() == 1, mask == NULL) produces it; otherwise it must be NULL.
  */
 HV_API int hv_window_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
                        const float* bias_table, const float* tau, const float* mask, int mask_windows,
-                       void* dqkv, float* dbias_table, float* dtau, void* workspace, size_t workspace_bytes,
-                       int B, int H, int W, int C, int heads, int ws, int shift, int dtype, void* stream);
+                       void* dqkv, float* dbias_table, float* dtau, float* dq_colsum, void* workspace,
+                       size_t workspace_bytes, int B, int H, int W, int C, int heads, int ws, int shift, int dtype,
+                       void* stream);
 
 /* ---- res-post-norm: out = shortcut + keep_scale[sample] * LayerNorm(y + bias) ------------
  * Replaces `shortcut + drop_path(norm1(x))` / `x + drop_path(norm2(mlp(x)))`, swinv2.py:431, 434,

@@ -77,6 +77,63 @@ def test_window_attention_core(case, dtype):
     assert_close("dtau", tau.grad, dtau, DTAU_TOL[dtype])
 
 
+@pytest.mark.parametrize("taus", [(0.05, 10.0, 100.0), (100.0, 100.0, 100.0), (1.0, 13.0, 15.0), (30.0, 2.0, 60.0)])
+@pytest.mark.parametrize("shift", [0, 4])
+def test_window_attention_core_tau_range(taus, shift):
+    """Tensor-core kernel across the whole logit-scale range: exp(logit_scale) from ~0 to the clamp at 100
+    (swinv2.py:230).  Heads with a small scale take the softmax path without a running maximum, heads near the
+    clamp the path with it; both must agree with the fp64 oracle on the same bf16 inputs."""
+    B, H, W, C, h, ws = 2, 16, 24, 96, 3, 8
+    g = O.Geometry(B, H, W, C, h, ws, shift)
+    gen = torch.Generator().manual_seed(int(sum(taus) * 10) + shift)
+    qkv = torch.randn(B, H * W, 3 * C, generator=gen).to(DEV, torch.bfloat16).requires_grad_(True)
+    tab = (16 * torch.sigmoid(2 * torch.randn((2 * ws - 1) ** 2, h, generator=gen))).to(DEV).requires_grad_(True)
+    tau = torch.tensor(taus).to(DEV).requires_grad_(True)
+    do = torch.randn(B, H * W, C, generator=gen).to(DEV, torch.bfloat16)
+    out = hvf.window_attention(qkv, tab, tau, B=B, H=H, W=W, C=C, heads=h, ws=ws, shift=shift)
+    out.backward(do)
+    torch.cuda.synchronize()
+    o, lse, dqkv, dtab, dtau = _oracle_core(qkv, tab, tau, g, do)
+    assert torch.isfinite(out).all() and torch.isfinite(qkv.grad).all()
+    assert_close("out", out, o, 2e-2)
+    assert_close("dqkv", qkv.grad, dqkv, 2e-2)
+    assert_close("dbias_table", tab.grad, dtab, 2e-2)
+    # d(tau) = sum_ij dS_ij cos_ij with sum_j dS_ij = 0: the bf16 rounding of dS (2^-9 per entry) leaves a residue
+    # ~2^-9 * |cos| against a result of size ~|delta cos| ~ 1/tau, i.e. ~tau * 2e-3 relative.  Near the clamp this
+    # gradient is multiplied by d clamp / d logit_scale = 0 (swinv2.py:230), so only its order of magnitude matters.
+    assert_close("dtau", tau.grad, dtau, DTAU_TOL[torch.bfloat16] if max(taus) < 50 else 0.35)
+
+
+@pytest.mark.parametrize("case", [(2, 16, 16, 96, 3, 4), (1, 32, 16, 192, 6, 0), (3, 8, 8, 64, 2, 0), (1, 16, 16, 32, 1, 5)])
+def test_window_attention_dq_colsum(case):
+    """hv_window_attn_bwd's optional dq_colsum output (gradient of q_bias, swinv2.py:211-220) equals the column
+    sums of the q third of dqkv that the same call wrote; the generic kernel rejects the request."""
+    B, H, W, C, h, s = case
+    ws = 8
+    gen = torch.Generator().manual_seed(B * 7 + C)
+    qkv = torch.randn(B, H * W, 3 * C, generator=gen).to(DEV, torch.bfloat16)
+    tab = (16 * torch.rand((2 * ws - 1) ** 2, h, generator=gen)).to(DEV)
+    tau = (5 + 40 * torch.rand(h, generator=gen)).to(DEV)
+    do = torch.randn(B, H * W, C, generator=gen).to(DEV, torch.bfloat16)
+    nW = (H // ws) * (W // ws)
+    out = torch.empty(B, H * W, C, device=DEV, dtype=torch.bfloat16)
+    lse = torch.empty(B * nW, h, ws * ws, device=DEV)
+    hvf.window_attention_fwd_raw(qkv, tab, tau, None, out, lse, B, H, W, C, h, ws, s)
+    dqkv = torch.empty_like(qkv)
+    dbias, dtau, colsum = torch.empty_like(tab), torch.empty_like(tau), torch.full((C,), float("nan"), device=DEV)
+    wsp = hvf.window_attention_bwd_workspace(qkv, B, H, W, C, h, ws)
+    hvf.window_attention_bwd_raw(qkv, out, do, lse, tab, tau, None, dqkv, dbias, dtau, wsp, B, H, W, C, h, ws, s,
+                                 dq_colsum=colsum)
+    torch.cuda.synchronize()
+    want = dqkv[..., :C].double().sum(dim=(0, 1))
+    # the kernel sums the fp32 values before they are rounded to bf16 for dqkv
+    assert_close("dq_colsum", colsum, want, 1e-2)
+    qkv32 = qkv.float()
+    with pytest.raises(RuntimeError, match="dq_colsum"):
+        hvf.window_attention_bwd_raw(qkv32, out.float(), do.float(), lse, tab, tau, None, torch.empty_like(qkv32), dbias,
+                                     dtau, wsp, B, H, W, C, h, ws, s, dq_colsum=colsum)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("case", [(4, 8, 96, 3, 2), (6, 8, 64, 2, 3), (4, 7, 32, 2, 4)])
 def test_window_attention_core_explicit_mask(case, dtype):

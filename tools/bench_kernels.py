@@ -33,7 +33,7 @@ def timeit(fns, iters, warmup=5):
     return e0.elapsed_time(e1) / iters
 
 
-def bench_attn(B, res, C, heads, ws, shift, dtype, iters):
+def bench_attn(B, res, C, heads, ws, shift, dtype, iters, tau_mode="init"):
     dev = "cuda"
     L = res * res
     nW = (res // ws) ** 2
@@ -43,7 +43,10 @@ def bench_attn(B, res, C, heads, ws, shift, dtype, iters):
     nsets = min(nsets, 6)
     M = (2 * ws - 1) ** 2
     tab = (16 * torch.rand(M, heads, device=dev)).float()
-    tau = (5 + 20 * torch.rand(heads, device=dev)).float()
+    # init: exp(logit_scale) of a freshly constructed model (log 10, swinv2.py:135-137); clamp: every head at the
+    # clamp of 100 (swinv2.py:230), the other softmax path of the tensor-core kernel
+    tau = {"init": torch.full((heads,), 10.0, device=dev), "clamp": torch.full((heads,), 100.0, device=dev),
+           "mixed": (5 + 20 * torch.rand(heads, device=dev)).float()}[tau_mode]
     sets = []
     for _ in range(nsets):
         qkv = torch.randn(B, L, 3 * C, device=dev).to(dtype)
@@ -66,7 +69,7 @@ def bench_attn(B, res, C, heads, ws, shift, dtype, iters):
     windows = B * nW
     bytes_f = windows * 4 * ws * ws * C * esz
     bytes_b = windows * 8 * ws * ws * C * esz
-    return dict(kernel="window_attn", B=B, res=res, C=C, heads=heads, ws=ws, shift=shift, dtype=str(dtype).split(".")[-1],
+    return dict(kernel="window_attn", B=B, res=res, C=C, heads=heads, ws=ws, shift=shift, dtype=str(dtype).split(".")[-1], tau=tau_mode,
                 windows=windows, fwd_ms=t_f, bwd_ms=t_b, fwd_gbs=bytes_f / t_f / 1e6, bwd_gbs=bytes_b / t_b / 1e6,
                 fwdbwd_gbs=(bytes_f + bytes_b) / (t_f + t_b) / 1e6, windows_per_s=windows / (t_f + t_b) * 1e3,
                 frac_fwd=bytes_f / t_f / 1e6 / PEAK, frac_bwd=bytes_b / t_b / 1e6 / PEAK,
@@ -143,6 +146,7 @@ def main():
     ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--json", default="")
     ap.add_argument("--only", default="")
+    ap.add_argument("--tau", default="init", choices=["init", "clamp", "mixed"])
     a = ap.parse_args()
     rows = []
     B = a.batch
@@ -150,7 +154,7 @@ def main():
     if a.only in ("", "attn"):
         for res, C, h in stages:
             for shift in ((0, 4) if res > 8 else (0,)):
-                rows.append(bench_attn(B, res, C, h, 8, shift, torch.bfloat16, a.iters))
+                rows.append(bench_attn(B, res, C, h, 8, shift, torch.bfloat16, a.iters, a.tau))
                 print(json.dumps(rows[-1]), flush=True)
         rows.append(bench_attn(max(B // 8, 8), 64, 96, 3, 8, 4, torch.float32, max(a.iters // 6, 3)))
         print(json.dumps(rows[-1]), flush=True)

@@ -17,6 +17,7 @@ ap.add_argument("--ws", type=int, default=8)
 ap.add_argument("--shift", type=int, default=4)
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--dtype", default="bf16")
+ap.add_argument("--tau", type=float, default=10.0)
 a = ap.parse_args()
 dev = "cuda"
 dt = torch.bfloat16 if a.dtype == "bf16" else torch.float32
@@ -28,7 +29,7 @@ lse = torch.empty(B * nW, h, ws * ws, device=dev)
 dout = torch.randn(B, L, C, device=dev).to(dt)
 dqkv = torch.empty_like(qkv)
 tab = 16 * torch.rand((2 * ws - 1) ** 2, h, device=dev)
-tau = 5 + 20 * torch.rand(h, device=dev)
+tau = torch.full((h,), a.tau, device=dev)
 dbias, dtau = torch.empty_like(tab), torch.empty_like(tau)
 wsp = hvf.window_attention_bwd_workspace(qkv, B, a.res, a.res, C, h, ws)
 geom = (B, a.res, a.res, C, h, ws, a.shift)
