@@ -193,8 +193,6 @@ def run_ours(args):
 
     B = args.batch
     model = build_model(device)
-    ddp = T.wrap_ddp(model, env, device)
-    opt = T.build_optimizer(ddp, lr=0.05)
     norm = T.NormalizeOnDevice().to(device)
 
     gen = torch.Generator().manual_seed(1234 + env.rank)
@@ -203,20 +201,50 @@ def run_ours(args):
     host_lab = [torch.randint(0, 10000, (B,), generator=gen).pin_memory() for _ in range(n_host)]
     dev_img = [t.to(device) for t in host_img]
     dev_lab = [t.to(device) for t in host_lab]
-    stage_img = torch.empty_like(dev_img[0])
-    stage_lab = torch.empty_like(dev_lab[0])
 
-    def step(img_u8, lab):
-        return T.train_step(ddp, opt, (norm(img_u8), lab), autocast_dtype=torch.bfloat16, clip_norm=2.0)
+    use_graph = not args.no_graph
+    if use_graph:
+        # one CUDA graph per step; gradients in one flat buffer, one captured NCCL all-reduce when N > 1
+        opt = T.build_optimizer(model, lr=0.05)
+        gs = T.GraphedTrainStep(model, opt, env, (dev_img[0], dev_lab[0]), transform=norm,
+                                autocast_dtype=torch.bfloat16, clip_norm=2.0)
+        eager = gs.eager
+    else:
+        ddp = T.wrap_ddp(model, env, device)
+        opt = T.build_optimizer(ddp, lr=0.05)
+
+        def eager(img_u8, lab):
+            return T.train_step(ddp, opt, (norm(img_u8), lab), autocast_dtype=torch.bfloat16, clip_norm=2.0)
 
     for i in range(args.warmup):
-        step(dev_img[i % n_host], dev_lab[i % n_host])
+        eager(dev_img[i % n_host], dev_lab[i % n_host])
+    torch.cuda.synchronize()
+    # ---- per-kernel accounting: CUDA events around every fused-attention launch of a few eager steps of the same
+    #      training step (graph replays launch the identical kernels; events cannot be queried inside a graph)
+    launches0 = hvf.LAUNCH_COUNT
+    n_instr = 1 if use_graph else 0
+    if use_graph:
+        hvf.PROFILE_EVENTS = []
+        n_instr = min(args.steps, 4)
+        for i in range(n_instr):
+            eager(dev_img[i % n_host], dev_lab[i % n_host])
+        torch.cuda.synchronize()
+        events = hvf.PROFILE_EVENTS
+        hvf.PROFILE_EVENTS = None
+        launches_per_step = (hvf.LAUNCH_COUNT - launches0) // n_instr
+        gs.capture()
+        step = gs
+        for i in range(2):
+            step(dev_img[i % n_host], dev_lab[i % n_host])
+    else:
+        step = eager
     torch.cuda.synchronize()
 
     sampler = ClockSampler(device.index) if env.is_main else None
     # ---------------------------------------------------------------- device-resident throughput
-    hvf.PROFILE_EVENTS = []
-    launches0 = hvf.LAUNCH_COUNT
+    if not use_graph:
+        hvf.PROFILE_EVENTS = []
+        launches0 = hvf.LAUNCH_COUNT
     T.barrier(env)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -227,24 +255,33 @@ def run_ours(args):
     torch.cuda.synchronize()
     T.barrier(env)
     ms_total = T.max_over_ranks(e0.elapsed_time(e1), env, device)
-    launches = hvf.LAUNCH_COUNT - launches0
-    events = hvf.PROFILE_EVENTS
-    hvf.PROFILE_EVENTS = None
+    if use_graph:
+        launches = launches_per_step * args.steps
+    else:
+        launches = hvf.LAUNCH_COUNT - launches0
+        events = hvf.PROFILE_EVENTS
+        hvf.PROFILE_EVENTS = None
     final_loss = float(loss)
 
     # ---------------------------------------------------------------- end to end from pinned host memory
-    for i in range(2):
+    stage_img = torch.empty_like(dev_img[0])
+    stage_lab = torch.empty_like(dev_lab[0])
+
+    def e2e_step(i):
+        if use_graph:  # the graph's static input buffers are the H2D destination
+            return step(host_img[i % n_host], host_lab[i % n_host]).item()
         stage_img.copy_(host_img[i % n_host], non_blocking=True)
         stage_lab.copy_(host_lab[i % n_host], non_blocking=True)
-        step(stage_img, stage_lab).item()
+        return step(stage_img, stage_lab).item()  # D2H read of the step's loss
+
+    for i in range(2):
+        e2e_step(i)
     T.barrier(env)
     torch.cuda.synchronize()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     for i in range(args.steps):
-        stage_img.copy_(host_img[i % n_host], non_blocking=True)
-        stage_lab.copy_(host_lab[i % n_host], non_blocking=True)
-        loss_host = step(stage_img, stage_lab).item()  # D2H read of the step's loss
+        loss_host = e2e_step(i)
     e3.record()
     torch.cuda.synchronize()
     T.barrier(env)
@@ -296,7 +333,11 @@ def run_ours(args):
     window_attn = {"windows_per_s_fwd_bwd": attn_windows / (tot_ms / 1e3) if tot_ms else None,
                    "hbm_gbs": tot_bytes / tot_ms / 1e6 if tot_ms else None,
                    "frac_of_hbm_roofline": tot_bytes / tot_ms / 1e6 / peak if tot_ms else None,
-                   "share_of_step": tot_ms / ms_total if ms_total else None, "kernels": kernels}
+                   "share_of_step": (tot_ms / (n_instr if use_graph else args.steps)) / (ms_total / args.steps) if ms_total else None,
+                   "kernels": kernels,
+                   "timing": ("CUDA events around each launch in %d eager steps of the same training step, same process "
+                              "(the timed region replays a CUDA graph of it)" % n_instr) if use_graph
+                   else "CUDA events around each launch inside the timed region"}
 
     cb = cpu_baseline() if (env.world_size == 1 and not args.no_cpu_baseline) else None
     n = env.world_size
@@ -307,6 +348,8 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * n,
                        "precision": "torch.autocast(bfloat16), fp32 master weights, bf16 activations",
                        "optimizer": "SGD momentum 0.875 wd 5e-4, grad-clip 2.0, drop_path 0.1", "parallelism": f"dp{n}",
+                       "launch": ("one CUDA graph per step (flat fp32 gradient buffer, one NCCL all-reduce(avg) captured "
+                                  "in the graph when N > 1)") if use_graph else "eager, DistributedDataParallel",
                        "l2": "no flush needed: each step streams > 10 GB of activations, far beyond the 126 MB L2"},
             "clocks": clocks,
             "e2e": {"value": imgs / (ms_e2e / 1e3), "unit": "img/s", "ms_per_step": ms_e2e / args.steps,
@@ -326,6 +369,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (the eager step is host-launch-bound below ~200)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager step + DistributedDataParallel instead of the CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: at least three warm-up steps

@@ -99,6 +99,21 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float lg2_fast(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rsqrt_fast(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t hmul2_bf16(uint32_t a, uint32_t b) {  // packed bf16x2 product
   uint32_t d;
   asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
@@ -225,7 +240,7 @@ __device__ __forceinline__ int64_t tile_token(const Geom& g, int b, int row0, in
   return ((int64_t)b * g.H + r) * g.W + c;
 }
 // 1 / max(sqrt(ss), 1e-12): F.normalize's denominator (reference swinv2.py:229)
-__device__ __forceinline__ float inv_norm(float ss) { return rsqrtf(fmaxf(ss, 1e-24f)); }
+__device__ __forceinline__ float inv_norm(float ss) { return rsqrt_fast(fmaxf(ss, 1e-24f)); }
 
 // Register split between the roles (only when the CTA fills the register file: 16 warps x 128)
 template <int HG> struct Regs {
@@ -353,9 +368,12 @@ wattn_mma64_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ b
   // Logits are tau2*cos + bias2 with |cos| <= 1: if 2*tau2 + (bias range) stays far inside the fp32 exponent range,
   // exp2(logit - (tau2 + max bias)) can neither overflow nor lose the row, and the running maximum is skipped.
   float bmx = -3.0e38f, bmn = 3.0e38f;
-  for (int r = lane; r < kTab; r += 32) {
-    const float b = kLog2e * __ldg(&bias_table[r * g.heads + head]);
-    bmx = fmaxf(bmx, b); bmn = fminf(bmn, b);
+  {
+    float bv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) bv[k] = __ldg(&bias_table[min(lane + 32 * k, kTab - 1) * g.heads + head]);  // 8 loads in flight
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { bmx = fmaxf(bmx, kLog2e * bv[k]); bmn = fminf(bmn, kLog2e * bv[k]); }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -499,11 +517,11 @@ wattn_mma64_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ b
     // column 0 of the ones tile sits in the t == 0 lane of every quad
     const float l0 = __shfl_sync(0xffffffffu, lacc[0], lane & ~3);
     const float l1 = __shfl_sync(0xffffffffu, lacc[2], lane & ~3);
-    const float inv0 = __fdividef(1.0f, l0), inv1 = __fdividef(1.0f, l1);
+    const float inv0 = rcp_fast(l0), inv1 = rcp_fast(l1);
     if (t_ == 0) {  // row log-sum-exp in log2 units (what the backward kernel consumes)
       float* lp = lse + ((int64_t)row * g.heads + head) * kN;
-      lp[i0] = off + mx0 + __log2f(l0);
-      lp[i1] = off + mx1 + __log2f(l1);
+      lp[i0] = off + mx0 + lg2_fast(l0);
+      lp[i1] = off + mx1 + lg2_fast(l1);
     }
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
@@ -1011,7 +1029,13 @@ int launch_fwd(const Geom& g, const void* qkv, const float* bias_table, const fl
                cudaStream_t st) {
   using Cfg = FwdCfg<HG>;
   auto kern = wattn_mma64_fwd_kernel<HG>;
-  HV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+  static thread_local int attr_dev = -1;  // once per device and thread: keeps the call out of CUDA-graph captures
+  int dev = 0;
+  HV_CUDA_OK(cudaGetDevice(&dev));
+  if (attr_dev != dev) {
+    HV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+    attr_dev = dev;
+  }
   const int per = ctas_per_group(g, HG);
   const int grid = per * (g.heads / HG);
   kern<<<grid, Cfg::kThreads, Cfg::kSmem, st>>>((const bf16*)qkv, bias_table, tau, (bf16*)out, lse, g, per);
@@ -1024,7 +1048,13 @@ int launch_bwd(const Geom& g, const void* qkv, const void* out, const void* dout
                const float* tau, void* dqkv, float* dbias_table, float* dtau, float* dq_colsum, float* ws, cudaStream_t st) {
   using Cfg = BwdCfg<HG>;
   auto kern = wattn_mma64_bwd_kernel<HG>;
-  HV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+  static thread_local int attr_dev = -1;
+  int dev = 0;
+  HV_CUDA_OK(cudaGetDevice(&dev));
+  if (attr_dev != dev) {
+    HV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+    attr_dev = dev;
+  }
   const int per = ctas_per_group(g, HG);
   const int grid = per * (g.heads / HG);
   float* ws_dbias = ws;

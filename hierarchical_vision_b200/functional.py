@@ -138,6 +138,70 @@ def window_attention(qkv: torch.Tensor, bias_table: torch.Tensor, tau: torch.Ten
     return _WindowAttention.apply(qkv, bias_table, tau.reshape(-1), mask, B, H, W, C, heads, ws, shift)
 
 
+def window_attention_kind(C: int, heads: int, ws: int, dtype: torch.dtype) -> int:
+    """1 when (C, heads, ws, dtype) runs on the tensor-core kernel (N = 64, head dim 32, bf16), else 0."""
+    if dtype not in (torch.float32, torch.bfloat16):
+        return 0
+    return int(_lib.load().hv_window_attn_kernel_kind(C, heads, ws, HV_BF16 if dtype == torch.bfloat16 else HV_F32))
+
+
+class _QkvWindowAttention(torch.autograd.Function):
+    """out = window_attention(x @ W^T + [q_bias, 0, 0]) for the tensor-core kernel.  One autograd node for the
+    qkv Linear (cuBLAS) and the fused attention, so that the gradient of q_bias is the kernel's dq column sum
+    (hv_window_attn_bwd's dq_colsum) instead of a separate reduction over the (tokens, 3C) gradient.  v_bias is
+    not an input: softmax rows sum to one, so it is added to the output by the caller (swinv2.py:211-220, 261)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, q_bias, bias_table, tau, B, H, W, C, heads, ws, shift):
+        _need_cuda(x, "qkv_window_attention")
+        x = x.contiguous()
+        bias = None
+        if q_bias is not None:
+            bias = torch.zeros((3 * C,), dtype=x.dtype, device=x.device)
+            bias[:C] = q_bias
+        qkv = torch.nn.functional.linear(x, weight, bias)
+        bias_table = _f32c(bias_table)
+        tau = _f32c(tau)
+        nW = (H // ws) * (W // ws)
+        out = torch.empty((B, H * W, C), dtype=qkv.dtype, device=qkv.device)
+        lse = torch.empty((B * nW, heads, ws * ws), dtype=torch.float32, device=qkv.device)
+        _timed(f"attn_fwd/C{C}", B * nW, qkv.device, lambda: window_attention_fwd_raw(
+            qkv, bias_table, tau, None, out, lse, B, H, W, C, heads, ws, shift))
+        ctx.save_for_backward(x, weight, qkv, out, lse, bias_table, tau)
+        ctx.geom = (B, H, W, C, heads, ws, shift)
+        ctx.q_bias_dtype = q_bias.dtype if q_bias is not None else None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, weight, qkv, out, lse, bias_table, tau = ctx.saved_tensors
+        B, H, W, C, heads, ws, shift = ctx.geom
+        dout = dout.contiguous()
+        if dout.dtype != qkv.dtype:
+            dout = dout.to(qkv.dtype)
+        dqkv = torch.empty_like(qkv)
+        dbias = torch.empty_like(bias_table)
+        dtau = torch.empty_like(tau)
+        dq_colsum = torch.empty((C,), dtype=torch.float32, device=qkv.device) if ctx.q_bias_dtype is not None else None
+        workspace = window_attention_bwd_workspace(qkv, B, H, W, C, heads, ws)
+        _timed(f"attn_bwd/C{C}", B * (H // ws) * (W // ws), qkv.device, lambda: window_attention_bwd_raw(
+            qkv, out, dout, lse, bias_table, tau, None, dqkv, dbias, dtau, workspace, B, H, W, C, heads, ws, shift,
+            dq_colsum=dq_colsum), kernels=2)
+        d2 = dqkv.view(-1, 3 * C)
+        dx = torch.matmul(d2, weight).view(x.shape) if ctx.needs_input_grad[0] else None
+        dw = torch.matmul(d2.t(), x.view(-1, C)) if ctx.needs_input_grad[1] else None
+        dqb = dq_colsum.to(ctx.q_bias_dtype) if dq_colsum is not None and ctx.needs_input_grad[2] else None
+        return dx, dw, dqb, dbias, dtau, None, None, None, None, None, None, None
+
+
+def qkv_window_attention(x: torch.Tensor, weight: torch.Tensor, q_bias: Optional[torch.Tensor],
+                         bias_table: torch.Tensor, tau: torch.Tensor, *, B: int, H: int, W: int, C: int, heads: int,
+                         ws: int, shift: int) -> torch.Tensor:
+    """x (B, H*W, C) bf16, weight (3C, C) bf16 -> attention output (B, H*W, C) WITHOUT the v_bias term (add it to the
+    result, or fold W_proj v_bias into the proj bias).  Tensor-core kernel geometries only."""
+    return _QkvWindowAttention.apply(x, weight, q_bias, bias_table, tau.reshape(-1), B, H, W, C, heads, ws, shift)
+
+
 class _LnResidual(torch.autograd.Function):
     """out = shortcut + keep_scale[sample] * LayerNorm(y + bias) (shortcut / bias / keep_scale optional)."""
 

@@ -217,11 +217,29 @@ class WindowAttention(nn.Module):
                                       "SwinTransformerBlock only ever builds square ones, swinv2.py:339)")
         if self.attn_drop.p > 0.0 and self.training:
             raise NotImplementedError("attention dropout is not fused; every reference config uses attn_drop=0")
-        o = hvf.window_attention(self._qkv(x_tokens), self._bias_table(), self._tau(), B=B, H=H, W=W, C=self.dim,
-                                 heads=self.num_heads, ws=self.window_size[0], shift=shift, mask=mask)
+        ws = self.window_size[0]
+        table, tau = self._bias_table(), self._tau()
+        dt = torch.get_autocast_dtype("cuda") if (x_tokens.is_cuda and torch.is_autocast_enabled("cuda")) else x_tokens.dtype
+        v_bias = None
+        if mask is None and x_tokens.is_cuda and hvf.window_attention_kind(self.dim, self.num_heads, ws, dt) == 1:
+            # tensor-core kernel: qkv Linear + attention are one autograd node (q_bias gradient from the kernel);
+            # v_bias leaves the attention as a plain additive term because softmax rows sum to one
+            o = hvf.qkv_window_attention(x_tokens.to(dt), self.qkv.weight.to(dt), self.q_bias, table, tau, B=B, H=H, W=W,
+                                         C=self.dim, heads=self.num_heads, ws=ws, shift=shift)
+            v_bias = self.v_bias
+        else:
+            o = hvf.window_attention(self._qkv(x_tokens), table, tau, B=B, H=H, W=W, C=self.dim,
+                                     heads=self.num_heads, ws=ws, shift=shift, mask=mask)
         if with_proj_bias:
+            if v_bias is not None:
+                o = o + v_bias.to(o.dtype)
             return self.proj_drop(self.proj(o))
-        return F.linear(o, self.proj.weight)  # the caller folds proj.bias into its LayerNorm kernel
+        # the caller folds the bias into its LayerNorm kernel: proj(o + v_bias) = o W^T + (W v_bias + proj.bias)
+        bias = self.proj.bias
+        if v_bias is not None:
+            with torch.autocast(device_type="cuda", enabled=False):
+                bias = bias + F.linear(v_bias.float(), self.proj.weight.float())
+        return F.linear(o, self.proj.weight), bias
 
     def forward(self, x, mask=None):
         """x: (num_windows*B, N, C); mask: (num_windows, N, N) of 0/-100 or None (swinv2.py:204-264)."""
@@ -293,8 +311,11 @@ class SwinTransformerBlock(nn.Module):
         fold1 = self._fusable(self.norm1) and self.attn.proj_drop.p == 0.0
         fold2 = self._fusable(self.norm2) and self.mlp.drop.p == 0.0 and isinstance(self.mlp, Mlp)
         # roll + partition + attention + reverse + roll back: one kernel, no rolled / partitioned copy
-        y = self.attn._fused(x, B, H, W, self.shift_size, None, with_proj_bias=not fold1)
-        x = self._post_norm(self.norm1, y, x, self.attn.proj.bias if fold1 else None)          # swinv2.py:431
+        if fold1:
+            y, proj_bias = self.attn._fused(x, B, H, W, self.shift_size, None, with_proj_bias=False)
+        else:
+            y, proj_bias = self.attn._fused(x, B, H, W, self.shift_size, None), None
+        x = self._post_norm(self.norm1, y, x, proj_bias)                                       # swinv2.py:431
         if fold2:
             m = F.linear(self.mlp._hidden(x), self.mlp.fc2.weight)
             return self._post_norm(self.norm2, m, x, self.mlp.fc2.bias)                         # swinv2.py:434

@@ -156,6 +156,95 @@ def train_step(model: nn.Module, optimizer: torch.optim.Optimizer, batch, *, aut
     return loss.detach()
 
 
+class GraphedTrainStep:
+    """The whole training step as ONE CUDA graph: uint8 normalisation, forward, loss, backward, gradient
+    all-reduce, clipping and the SGD update are captured once and replayed, so a step costs one launch on the
+    host instead of ~1000 (the eager step is launch-bound below ~200 images per GPU, and DistributedDataParallel's
+    per-bucket hooks add host work on top).
+
+    Gradients live in one flat fp32 buffer (every ``p.grad`` is a view into it, like DDP's
+    ``gradient_as_bucket_view``); with world_size > 1 the only collective is one NCCL all-reduce(avg) of that
+    buffer, captured inside the graph (parameter-gradient sync only, nothing to overlap it with is
+    lost: 141 MB over NVLink is < 2 % of the step).  Inputs are copied into static buffers before each replay.
+    """
+
+    def __init__(self, model: "Model", optimizer: torch.optim.Optimizer, env: DistEnv, example_batch, *,
+                 transform: Optional[nn.Module] = None, autocast_dtype=torch.bfloat16,
+                 clip_norm: Optional[float] = 2.0, warmup: int = 3):
+        img, lab = example_batch
+        if not img.is_cuda:
+            raise RuntimeError("GraphedTrainStep needs CUDA tensors")
+        self.model, self.optimizer, self.env = model, optimizer, env
+        self.transform, self.autocast_dtype, self.clip_norm = transform, autocast_dtype, clip_norm
+        self.static_img = torch.empty_like(img)
+        self.static_lab = torch.empty_like(lab)
+        params = [p for p in model.parameters() if p.requires_grad]
+        self.flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=img.device)
+        off = 0
+        for p in params:
+            if p.dtype != torch.float32:
+                raise RuntimeError("GraphedTrainStep keeps fp32 master weights")
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.params = params
+        self.launches_per_step = 0
+        self.graph = None
+        self.static_loss = None
+        self.static_img.copy_(img)
+        self.static_lab.copy_(lab)
+        self._warmup = warmup
+
+    def eager(self, img: torch.Tensor, lab: torch.Tensor) -> torch.Tensor:
+        """The same step without the graph (warm-up, per-kernel instrumentation, debugging)."""
+        self.static_img.copy_(img, non_blocking=True)
+        self.static_lab.copy_(lab, non_blocking=True)
+        return self._body()
+
+    def capture(self) -> "GraphedTrainStep":
+        dev = self.static_img.device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(self._warmup):
+                self._body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        from . import functional as hvf
+
+        n0 = hvf.LAUNCH_COUNT
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_loss = self._body()
+        self.launches_per_step = hvf.LAUNCH_COUNT - n0
+        return self
+
+    def _body(self) -> torch.Tensor:
+        self.flat.zero_()
+        x = self.transform(self.static_img) if self.transform is not None else self.static_img
+        batch = (x, self.static_lab)
+        with torch.autocast("cuda", dtype=self.autocast_dtype, enabled=self.autocast_dtype is not None):
+            outputs = self.model(batch)
+            loss = self.model.loss(outputs, batch)
+        loss.backward()
+        if self.env.world_size > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)
+        if self.clip_norm is not None:
+            # torch.nn.utils.clip_grad_norm_ on the flat view: one norm, one scale
+            total = torch.linalg.vector_norm(self.flat)
+            self.flat.mul_(torch.clamp(self.clip_norm / (total + 1e-6), max=1.0))
+        self.optimizer.step()
+        return loss.detach()
+
+    def __call__(self, img: torch.Tensor, lab: torch.Tensor) -> torch.Tensor:
+        """Copy the batch (device or pinned host memory) into the static buffers, replay, return the loss tensor."""
+        if self.graph is None:
+            self.capture()
+        self.static_img.copy_(img, non_blocking=True)
+        self.static_lab.copy_(lab, non_blocking=True)
+        self.graph.replay()
+        return self.static_loss
+
+
 def max_over_ranks(value: float, env: DistEnv, device: torch.device) -> float:
     """Timing rule: a multi-GPU duration is the max over ranks."""
     if env.world_size == 1:

@@ -98,9 +98,9 @@ def test_window_attention_core_tau_range(taus, shift):
     assert_close("out", out, o, 2e-2)
     assert_close("dqkv", qkv.grad, dqkv, 2e-2)
     assert_close("dbias_table", tab.grad, dtab, 2e-2)
-    # d(tau) = sum_ij dS_ij cos_ij with sum_j dS_ij = 0: the bf16 rounding of dS (2^-9 per entry) leaves a residue
-    # ~2^-9 * |cos| against a result of size ~|delta cos| ~ 1/tau, i.e. ~tau * 2e-3 relative.  Near the clamp this
-    # gradient is multiplied by d clamp / d logit_scale = 0 (swinv2.py:230), so only its order of magnitude matters.
+    # d(tau) = sum_ij dS_ij cos_ij with sum_j dS_ij = 0: every bf16 rounding on the way to dS (2^-9 per entry) leaves a
+    # residue ~2^-9 * |cos| against a result of size ~|delta cos| ~ 1/tau, i.e. ~tau * 2e-3 relative.  Near the clamp
+    # this gradient is multiplied by d clamp / d logit_scale = 0 (swinv2.py:230), so only its order of magnitude matters.
     assert_close("dtau", tau.grad, dtau, DTAU_TOL[torch.bfloat16] if max(taus) < 50 else 0.35)
 
 
@@ -228,9 +228,13 @@ def test_block_bf16_vs_reference_fixture(name, mode):
         if k.startswith("ref.grad."):
             name_ = k[len("ref.grad."):]
             base = 4e-2 if v.numel() <= 2048 else 2e-2  # biases / LN affine: reduction gradients
+            mult = 1.5
             if name_.endswith("logit_scale"):
-                base = DTAU_TOL[torch.bfloat16]  # scalar-per-head sum with heavy cancellation, see DTAU_TOL
-            assert_close(k, params[name_].grad, v, slack * max(base, 1.5 * ref_miss["grad." + name_]))
+                # scalar-per-head sum with heavy cancellation (see DTAU_TOL): sum_ij dS_ij cos_ij with rows of dS summing
+                # to zero, so EVERY bf16 rounding between P and dS (the kernel has three, in packed bf16x2 arithmetic)
+                # leaves a residue; the band is 2x the reference's own bf16 miss on the same fixture
+                base, mult = DTAU_TOL[torch.bfloat16], 2.0
+            assert_close(k, params[name_].grad, v, slack * max(base, mult * ref_miss["grad." + name_]))
 
 
 @pytest.mark.parametrize("name", ["patch_merging", "patch_merging_rect"])
@@ -502,3 +506,50 @@ def test_bias_gelu(shape, dtype):
     assert_close("out", out, want, tol)
     assert_close("dh", h.grad, h64.grad, tol)
     assert_close("dbias", b.grad, b64.grad, 1e-4 if dtype == torch.float32 else 2e-2)
+
+
+def test_graphed_train_step_matches_eager():
+    """GraphedTrainStep (one CUDA graph per step, flat gradient buffer) takes the same optimisation steps as the
+    eager train_step on identical weights and batches (drop_path 0, so no RNG is involved)."""
+    from hierarchical_vision_b200 import train as T
+
+    def make():
+        torch.manual_seed(3)
+        net = hv.SwinTransformerV2(img_size=64, patch_size=4, embed_dim=32, depths=[2, 2], num_heads=[1, 2], window_size=8,
+                                   num_classes=16, drop_path_rate=0.0)
+        with torch.no_grad():
+            for layer in net.layers:
+                for blk in layer.blocks:
+                    for n in (blk.norm1, blk.norm2):
+                        n.weight.normal_(1.0, 0.1)
+                        n.bias.normal_(0.0, 0.1)
+        return T.Model(net).to(DEV)
+
+    gen = torch.Generator().manual_seed(5)
+    imgs = [torch.randint(0, 256, (4, 3, 64, 64), dtype=torch.uint8, generator=gen).to(DEV) for _ in range(3)]
+    labs = [torch.randint(0, 16, (4,), generator=gen).to(DEV) for _ in range(3)]
+    norm = T.NormalizeOnDevice().to(DEV)
+    env = T.DistEnv()
+
+    m_e = make()
+    opt_e = T.build_optimizer(m_e, lr=0.05)
+    losses_e = [float(T.train_step(m_e, opt_e, (norm(i), l), autocast_dtype=torch.bfloat16, clip_norm=2.0))
+                for i, l in zip(imgs, labs)]
+
+    m_g = make()
+    opt_g = T.build_optimizer(m_g, lr=0.05)
+    gs = T.GraphedTrainStep(m_g, opt_g, env, (imgs[0], labs[0]), transform=norm, autocast_dtype=torch.bfloat16,
+                            clip_norm=2.0, warmup=1)
+    state0 = {k: v.clone() for k, v in m_g.state_dict().items()}
+    gs.capture()  # one eager warm-up step (creates the momentum buffers), then the capture (does not execute)
+    m_g.load_state_dict(state0)
+    for st in opt_g.state.values():
+        st["momentum_buffer"].zero_()  # first eager step sets buf = grad, which is what 0 * m + grad gives
+    losses_g = [float(gs(i, l)) for i, l in zip(imgs, labs)]
+    torch.cuda.synchronize()
+    assert gs.launches_per_step > 0
+    for a, b in zip(losses_e, losses_g):
+        assert abs(a - b) <= 2e-2 * max(1.0, abs(a)), (losses_e, losses_g)
+    pe, pg = dict(m_e.named_parameters()), dict(m_g.named_parameters())
+    worst = max(rel_l2(pg[k], pe[k]) for k in pe)
+    assert worst < 2e-2, worst
