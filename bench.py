@@ -112,6 +112,9 @@ def build_model(device, drop_path_rate=0.1):
                 for n in (blk.norm1, blk.norm2):
                     n.weight.normal_(1.0, 0.1)
                     n.bias.normal_(0.0, 0.1)
+    # uint8 batches go straight into the model: (x - mean) / std (reference data.py:130-136) is folded into the
+    # patch-embedding gather instead of materialising a float image
+    backbone.set_input_normalization([m * 255.0 for m in T.IMAGENET_MEAN], [v * 255.0 for v in T.IMAGENET_STD])
     return T.Model(backbone).to(device)
 
 
@@ -193,8 +196,6 @@ def run_ours(args):
 
     B = args.batch
     model = build_model(device)
-    norm = T.NormalizeOnDevice().to(device)
-
     gen = torch.Generator().manual_seed(1234 + env.rank)
     n_host = 2
     host_img = [torch.randint(0, 256, (B, 3, 256, 256), dtype=torch.uint8, generator=gen).pin_memory() for _ in range(n_host)]
@@ -206,7 +207,7 @@ def run_ours(args):
     if use_graph:
         # one CUDA graph per step; gradients in one flat buffer, one captured NCCL all-reduce when N > 1
         opt = T.build_optimizer(model, lr=0.05)
-        gs = T.GraphedTrainStep(model, opt, env, (dev_img[0], dev_lab[0]), transform=norm,
+        gs = T.GraphedTrainStep(model, opt, env, (dev_img[0], dev_lab[0]), transform=None,
                                 autocast_dtype=torch.bfloat16, clip_norm=2.0)
         eager = gs.eager
     else:
@@ -214,7 +215,7 @@ def run_ours(args):
         opt = T.build_optimizer(ddp, lr=0.05)
 
         def eager(img_u8, lab):
-            return T.train_step(ddp, opt, (norm(img_u8), lab), autocast_dtype=torch.bfloat16, clip_norm=2.0)
+            return T.train_step(ddp, opt, (img_u8, lab), autocast_dtype=torch.bfloat16, clip_norm=2.0)
 
     for i in range(args.warmup):
         eager(dev_img[i % n_host], dev_lab[i % n_host])

@@ -13,7 +13,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_size_t, c_void_
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libhv_swin.so")
 
-HV_F32, HV_BF16 = 0, 1
+HV_F32, HV_BF16, HV_U8 = 0, 1, 2
 
 # name -> (restype, argtypes); mirrors include/hv_swin.h one to one
 _I, _P, _F, _L, _S = c_int, c_void_p, c_float, c_int64, c_size_t
@@ -38,6 +38,7 @@ SIGNATURES = {
     "hv_bias_gelu_bwd": (_I, [_P, _P, _P, _P, _P, _P, _S, _L, _I, _I, _P]),
     "hv_patch_merge_gather_fwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "hv_patch_merge_gather_bwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "hv_patch_rows": (_I, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
 }
 
 _lib = None

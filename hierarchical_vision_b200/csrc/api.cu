@@ -34,6 +34,8 @@ int bias_gelu_bwd(const void* dout, const void* h, const float* bias, void* dh, 
                   size_t workspace_bytes, int64_t rows, int cols, int dtype, cudaStream_t st);
 int patch_merge_gather_fwd(const void* x, void* out, int B, int H, int W, int C, int dtype, cudaStream_t st);
 int patch_merge_gather_bwd(const void* dout, void* dx, int B, int H, int W, int C, int dtype, cudaStream_t st);
+int patch_rows(const void* img, int img_dtype, const float* scale, const float* shift, void* out, int out_dtype, int B,
+               int Cin, int H, int W, int P, cudaStream_t st);
 
 // ---- error text / device info --------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -259,6 +261,15 @@ int hv_patch_merge_gather_bwd(const void* dout, void* dx, int B, int H, int W, i
   int rc = check_device_arch();
   if (rc) return rc;
   return patch_merge_gather_bwd(dout, dx, B, H, W, C, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int hv_patch_rows(const void* img, int img_dtype, const float* scale, const float* shift, void* out, int out_dtype,
+                  int B, int Cin, int H, int W, int P, void* stream) {
+  if (!img || !out) HV_FAIL(HV_ERR_NULL, "hv_patch_rows: NULL argument");
+  if ((scale == nullptr) != (shift == nullptr)) HV_FAIL(HV_ERR_NULL, "hv_patch_rows: scale and shift go together");
+  int rc = check_device_arch();
+  if (rc) return rc;
+  return patch_rows(img, img_dtype, scale, shift, out, out_dtype, B, Cin, H, W, P, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -11,7 +11,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import HV_BF16, HV_F32, check
+from ._lib import HV_BF16, HV_F32, HV_U8, check
 
 _P = _lib.c_void_p
 
@@ -353,3 +353,26 @@ class _PatchMergeGather(torch.autograd.Function):
 def patch_merge_gather(x: torch.Tensor, H: int, W: int) -> torch.Tensor:
     """(B, H*W, C) -> (B, H/2*W/2, 4C), channel blocks ordered (0,0),(1,0),(0,1),(1,1)."""
     return _PatchMergeGather.apply(x, H, W)
+
+
+def patch_rows(img: torch.Tensor, scale: Optional[torch.Tensor], shift: Optional[torch.Tensor],
+               out_dtype: torch.dtype, patch: int = 4) -> torch.Tensor:
+    """(B, 3, H, W) uint8 / float32 / bfloat16 image -> (B * H/4 * W/4, 48) rows in the conv weight's (c, dy, dx)
+    order, each pixel mapped to ``x * scale[c] + shift[c]`` (both None: identity).  No gradient flows to the image."""
+    _need_cuda(img, "patch_rows")
+    if img.requires_grad:
+        raise RuntimeError("patch_rows does not differentiate with respect to the image")
+    lib = _lib.load()
+    img = img.contiguous()
+    B, C, H, W = img.shape
+    code = HV_U8 if img.dtype == torch.uint8 else _code(img)
+    out = torch.empty((B * (H // patch) * (W // patch), C * patch * patch), dtype=out_dtype, device=img.device)
+    if scale is not None:
+        scale, shift = _f32c(scale), _f32c(shift)
+    with torch.cuda.device(img.device):
+        rc = lib.hv_patch_rows(_ptr(img), code, _ptr(scale), _ptr(shift), _ptr(out), _code(out), B, C, H, W, patch,
+                               _stream(img.device))
+    check(rc, "hv_patch_rows")
+    global LAUNCH_COUNT
+    LAUNCH_COUNT += 1
+    return out

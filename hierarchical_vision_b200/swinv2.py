@@ -416,14 +416,43 @@ class PatchEmbed(nn.Module):
         self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=self.patch_size, stride=self.patch_size)
         self.norm = norm_layer(embed_dim) if norm_layer is not None else None
 
-    def forward(self, x):
+    def forward(self, x, input_norm=None):
+        """x: (B, C, H, W) float image (reference swinv2.py:648-657).  Extension: a uint8 image together with
+        ``input_norm = (mean, std)`` per channel in pixel units, in which case the reference's on-device
+        normalisation (data.py:130-136) is folded into the patch gather."""
         B, C, H, W = x.shape
         assert H == self.img_size[0] and W == self.img_size[1], \
             f"Input image size ({H}*{W}) doesn't match model ({self.img_size[0]}*{self.img_size[1]})."
-        x = self.proj(x).flatten(2).transpose(1, 2)
+        fast = (x.is_cuda and C == 3 and tuple(self.patch_size) == (4, 4) and not x.requires_grad
+                and x.dtype in (torch.uint8, torch.float32, torch.bfloat16))
+        if not fast:
+            if x.dtype == torch.uint8:
+                mean, std = input_norm
+                x = (x.float() - mean.view(1, -1, 1, 1)) / std.view(1, -1, 1, 1)
+            x = self.proj(x).flatten(2).transpose(1, 2)
+            bias = None
+        else:
+            # Conv2d(k = s = 4) == per-patch GEMM: gather kernel (normalisation folded in) + library GEMM; replaces
+            # cuDNN's NCHW<->NHWC transposes around the convolution
+            scale = shift = None
+            if input_norm is not None:
+                mean, std = input_norm
+                scale, shift = 1.0 / std.float(), -mean.float() / std.float()
+            if torch.is_autocast_enabled("cuda"):
+                dt = torch.get_autocast_dtype("cuda")
+            else:
+                dt = x.dtype if x.is_floating_point() else self.proj.weight.dtype
+            if dt not in (torch.float32, torch.bfloat16):
+                dt = torch.float32
+            rows = hvf.patch_rows(x, scale, shift, dt)
+            fold = type(self.norm) is nn.LayerNorm and self.norm.elementwise_affine and self.norm.bias is not None
+            w = self.proj.weight.view(self.embed_dim, -1)
+            x = F.linear(rows, w.to(dt), None if (fold or self.proj.bias is None) else self.proj.bias.to(dt))
+            x = x.view(B, -1, self.embed_dim)
+            bias = self.proj.bias if fold else None
         if self.norm is not None:
             if type(self.norm) is nn.LayerNorm and x.is_cuda and x.dtype in (torch.float32, torch.bfloat16):
-                x = hvf.ln_residual(x, None, self.norm.weight, self.norm.bias, None, self.norm.eps)
+                x = hvf.ln_residual(x, None, self.norm.weight, self.norm.bias, None, self.norm.eps, bias=bias)
             else:
                 x = self.norm(x)
         return x
@@ -502,8 +531,20 @@ class SwinTransformerV2(nn.Module):
     def no_weight_decay_keywords(self):
         return {"cpb_mlp", "logit_scale", "relative_position_bias_table"}
 
+    def set_input_normalization(self, mean, std):
+        """Extension for uint8 batches: per-channel mean / std in pixel units (data.py:130-136 applies
+        ``(x - mean) / std`` on the device before the model); folded into the patch-embedding gather."""
+        self.register_buffer("input_mean", torch.as_tensor(mean, dtype=torch.float32).reshape(-1), persistent=False)
+        self.register_buffer("input_std", torch.as_tensor(std, dtype=torch.float32).reshape(-1), persistent=False)
+        return self
+
     def forward_features(self, x, output_activations=False):
-        x = self.patch_embed(x)
+        if x.dtype == torch.uint8:
+            if getattr(self, "input_mean", None) is None:
+                raise RuntimeError("uint8 input needs set_input_normalization(mean, std) first")
+            x = self.patch_embed(x, input_norm=(self.input_mean, self.input_std))
+        else:
+            x = self.patch_embed(x)
         if self.ape:
             x = x + self.absolute_pos_embed
         x = self.pos_drop(x)

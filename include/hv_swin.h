@@ -36,7 +36,7 @@ extern "C" {
 #define HV_API
 #endif
 
-enum { HV_F32 = 0, HV_BF16 = 1 };
+enum { HV_F32 = 0, HV_BF16 = 1, HV_U8 = 2 /* images only */ };
 
 enum {
   HV_OK = 0,
@@ -155,6 +155,16 @@ HV_API int hv_bias_gelu_bwd(const void* dout, const void* h, const float* bias, 
  *   x  device (B, H*W, C)      out device (B, H/2*W/2, 4C)       same dtype */
 HV_API int hv_patch_merge_gather_fwd(const void* x, void* out, int B, int H, int W, int C, int dtype, void* stream);
 HV_API int hv_patch_merge_gather_bwd(const void* dout, void* dx, int B, int H, int W, int C, int dtype, void* stream);
+
+/* ---- PatchEmbed input gather -------------------------------------------------------------
+ * Left operand of PatchEmbed's Conv2d(in_chans, embed_dim, kernel = stride = patch) seen as a per-patch GEMM
+ * (swinv2.py:648-657): out[(b, ph, pw), (c, dy, dx)] = img[b, c, ph*P + dy, pw*P + dx] * scale[c] + shift[c].
+ * `scale`/`shift` (device float32 (Cin), or both NULL) fold the reference's on-device normalisation
+ * (data.py:130-136: (x - mean) / std) into the gather, so a uint8 batch is read exactly once.
+ *   img  device (B, Cin, H, W), img_dtype in {HV_U8, HV_F32, HV_BF16}; only Cin = 3, P = 4
+ *   out  device (B * H/P * W/P, Cin*P*P) out_dtype in {HV_F32, HV_BF16}; multiply by proj.weight.view(E, -1)^T */
+HV_API int hv_patch_rows(const void* img, int img_dtype, const float* scale, const float* shift, void* out,
+                  int out_dtype, int B, int Cin, int H, int W, int P, void* stream);
 
 #ifdef __cplusplus
 }

@@ -553,3 +553,60 @@ def test_graphed_train_step_matches_eager():
     pe, pg = dict(m_e.named_parameters()), dict(m_g.named_parameters())
     worst = max(rel_l2(pg[k], pe[k]) for k in pe)
     assert worst < 2e-2, worst
+
+
+@pytest.mark.parametrize("in_dtype", [torch.uint8, torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+def test_patch_rows_is_the_exact_gather(in_dtype, out_dtype):
+    """hv_patch_rows == unfold(kernel = stride = 4) in the conv weight's (c, dy, dx) order (swinv2.py:648-657), with the
+    per-channel normalisation of data.py:130-136 applied on the fly; bit exact where no rounding is involved."""
+    B, H, W = 3, 24, 40
+    gen = torch.Generator().manual_seed(11)
+    if in_dtype == torch.uint8:
+        img = torch.randint(0, 256, (B, 3, H, W), dtype=torch.uint8, generator=gen).to(DEV)
+    else:
+        img = torch.randn(B, 3, H, W, generator=gen).to(DEV, in_dtype)
+    mean = torch.tensor([123.7, 116.3, 103.5], device=DEV)
+    std = torch.tensor([58.4, 57.1, 57.4], device=DEV)
+    unf = torch.nn.functional.unfold(img.float(), kernel_size=4, stride=4)            # (B, 48, L), (c, dy, dx) major
+    want_raw = unf.transpose(1, 2).reshape(-1, 48)
+    got_raw = hvf.patch_rows(img, None, None, out_dtype)
+    assert got_raw.shape == want_raw.shape
+    assert torch.equal(got_raw, want_raw.to(out_dtype))
+    ch = torch.arange(48, device=DEV) // 16
+    want = (want_raw - mean[ch]) / std[ch]
+    got = hvf.patch_rows(img, 1.0 / std, -mean / std, out_dtype)
+    assert_close("normalised", got, want, 1e-6 if out_dtype == torch.float32 else 4e-3)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_patch_embed_matches_conv_path(mode):
+    """PatchEmbed through the gather + GEMM + fused LayerNorm path vs Conv2d + LayerNorm (swinv2.py:648-657), outputs
+    and parameter gradients; and the uint8 entry with folded normalisation vs normalising first."""
+    torch.manual_seed(2)
+    pe = hv.PatchEmbed(img_size=32, patch_size=4, in_chans=3, embed_dim=96, norm_layer=torch.nn.LayerNorm).to(DEV)
+    with torch.no_grad():
+        pe.norm.weight.normal_(1, 0.1)
+        pe.norm.bias.normal_(0, 0.1)
+        pe.proj.bias.normal_(0, 0.1)
+    img_u8 = torch.randint(0, 256, (4, 3, 32, 32), dtype=torch.uint8, device=DEV)
+    mean = torch.tensor([123.7, 116.3, 103.5], device=DEV)
+    std = torch.tensor([58.4, 57.1, 57.4], device=DEV)
+    x = (img_u8.float() - mean.view(1, 3, 1, 1)) / std.view(1, 3, 1, 1)
+    gy = torch.randn(4, 64, 96, device=DEV)
+    ac = dict(device_type="cuda", dtype=torch.bfloat16, enabled=mode == "bf16")
+    # reference arithmetic: conv + LayerNorm in fp64
+    ref = torch.nn.Sequential()
+    w64 = {k: v.detach().double().requires_grad_(True) for k, v in pe.named_parameters()}
+    y64 = torch.nn.functional.conv2d(x.double(), w64["proj.weight"], w64["proj.bias"], stride=4).flatten(2).transpose(1, 2)
+    y64 = torch.nn.functional.layer_norm(y64, (96,), w64["norm.weight"], w64["norm.bias"], pe.norm.eps)
+    y64.backward(gy.double())
+    tol = 1e-3 if mode == "fp32" else 2e-2
+    for inp, kw in ((x, {}), (img_u8, {"input_norm": (mean, std)})):
+        pe.zero_grad(set_to_none=True)
+        with torch.autocast(**ac):
+            y = pe(inp, **kw)
+        y.backward(gy.to(y.dtype))
+        assert_close("y", y, y64, tol)
+        for k, p in pe.named_parameters():
+            assert_close(k, p.grad, w64[k].grad, 2 * tol)
