@@ -170,10 +170,12 @@ class _QkvWindowAttention(torch.autograd.Function):
         ctx.save_for_backward(x, weight, qkv, out, lse, bias_table, tau)
         ctx.geom = (B, H, W, C, heads, ws, shift)
         ctx.q_bias_dtype = q_bias.dtype if q_bias is not None else None
-        return out
+        # second output: x itself, for the residual shortcut.  Its gradient comes back into this node, where it is
+        # the accumulator (beta = 1) of the dx GEMM instead of a separate elementwise add kernel.
+        return out, x.view_as(x)
 
     @staticmethod
-    def backward(ctx, dout):
+    def backward(ctx, dout, dx_shortcut):
         x, weight, qkv, out, lse, bias_table, tau = ctx.saved_tensors
         B, H, W, C, heads, ws, shift = ctx.geom
         dout = dout.contiguous()
@@ -188,7 +190,14 @@ class _QkvWindowAttention(torch.autograd.Function):
             qkv, out, dout, lse, bias_table, tau, None, dqkv, dbias, dtau, workspace, B, H, W, C, heads, ws, shift,
             dq_colsum=dq_colsum), kernels=2)
         d2 = dqkv.view(-1, 3 * C)
-        dx = torch.matmul(d2, weight).view(x.shape) if ctx.needs_input_grad[0] else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            if dx_shortcut is not None:
+                dx = torch.addmm(dx_shortcut.reshape(-1, C).to(d2.dtype), d2, weight).view(x.shape)
+            else:
+                dx = torch.matmul(d2, weight).view(x.shape)
+        elif dx_shortcut is not None:
+            dx = dx_shortcut
         dw = torch.matmul(d2.t(), x.view(-1, C)) if ctx.needs_input_grad[1] else None
         dqb = dq_colsum.to(ctx.q_bias_dtype) if dq_colsum is not None and ctx.needs_input_grad[2] else None
         return dx, dw, dqb, dbias, dtau, None, None, None, None, None, None, None
@@ -197,9 +206,41 @@ class _QkvWindowAttention(torch.autograd.Function):
 def qkv_window_attention(x: torch.Tensor, weight: torch.Tensor, q_bias: Optional[torch.Tensor],
                          bias_table: torch.Tensor, tau: torch.Tensor, *, B: int, H: int, W: int, C: int, heads: int,
                          ws: int, shift: int) -> torch.Tensor:
-    """x (B, H*W, C) bf16, weight (3C, C) bf16 -> attention output (B, H*W, C) WITHOUT the v_bias term (add it to the
-    result, or fold W_proj v_bias into the proj bias).  Tensor-core kernel geometries only."""
+    """x (B, H*W, C) bf16, weight (3C, C) bf16 -> (attention output (B, H*W, C) WITHOUT the v_bias term (add it to the
+    result, or fold W_proj v_bias into the proj bias), x again for the residual shortcut).  Use the returned x for the
+    shortcut: its gradient is then accumulated by the dx GEMM.  Tensor-core kernel geometries only."""
     return _QkvWindowAttention.apply(x, weight, q_bias, bias_table, tau.reshape(-1), B, H, W, C, heads, ws, shift)
+
+
+class _LinearShortcut(torch.autograd.Function):
+    """(x W^T, x): a bias-free Linear whose input also feeds a residual shortcut.  The shortcut's gradient is the
+    accumulator (beta = 1) of the dx GEMM, which removes the elementwise add autograd would otherwise launch at
+    the fork (swinv2.py:434: x = x + drop_path(norm2(mlp(x))))."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        ctx.save_for_backward(x, weight)
+        return torch.nn.functional.linear(x, weight), x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy, dx_shortcut):
+        x, weight = ctx.saved_tensors
+        d2 = dy.reshape(-1, dy.shape[-1])
+        dx = None
+        if ctx.needs_input_grad[0]:
+            if dx_shortcut is not None:
+                dx = torch.addmm(dx_shortcut.reshape(-1, x.shape[-1]).to(d2.dtype), d2, weight).view(x.shape)
+            else:
+                dx = torch.matmul(d2, weight).view(x.shape)
+        elif dx_shortcut is not None:
+            dx = dx_shortcut
+        dw = torch.matmul(d2.t(), x.reshape(-1, x.shape[-1])) if ctx.needs_input_grad[1] else None
+        return dx, dw
+
+
+def linear_shortcut(x: torch.Tensor, weight: torch.Tensor):
+    """Returns (F.linear(x, weight), x); use the returned x for the residual shortcut."""
+    return _LinearShortcut.apply(x, weight)
 
 
 class _LnResidual(torch.autograd.Function):

@@ -89,15 +89,25 @@ class Mlp(nn.Module):
         self.fc2 = nn.Linear(hidden_features or in_features, out_features or in_features)
         self.drop = nn.Dropout(drop)
 
-    def _hidden(self, x):
+    def _hidden(self, x, with_shortcut=False):
         """act(fc1(x)): for the reference's default nn.GELU (exact erf form) the fc1 bias add and the
-        activation run as one kernel whose backward also yields d fc1.bias."""
+        activation run as one kernel whose backward also yields d fc1.bias.  ``with_shortcut``: also return x for
+        the caller's residual connection (its gradient is then accumulated inside the fc1 dx GEMM)."""
+        sc = x
         if type(self.act) is nn.GELU and getattr(self.act, "approximate", "none") == "none" and self.fc1.bias is not None:
-            h = F.linear(x, self.fc1.weight)
+            if with_shortcut and x.is_cuda and torch.is_autocast_enabled("cuda") and x.dtype == torch.get_autocast_dtype("cuda"):
+                h, sc = hvf.linear_shortcut(x, self.fc1.weight.to(x.dtype))
+            elif with_shortcut and x.is_cuda and not torch.is_autocast_enabled("cuda") and x.dtype == self.fc1.weight.dtype:
+                h, sc = hvf.linear_shortcut(x, self.fc1.weight)
+            else:
+                h = F.linear(x, self.fc1.weight)
             if hvf.bias_gelu_supported(h):
-                return hvf.bias_gelu(h, self.fc1.bias)
-            return self.act(h + self.fc1.bias)
-        return self.act(self.fc1(x))
+                a = hvf.bias_gelu(h, self.fc1.bias)
+            else:
+                a = self.act(h + self.fc1.bias)
+        else:
+            a = self.act(self.fc1(x))
+        return (a, sc) if with_shortcut else a
 
     def forward(self, x):
         return self.drop(self.fc2(self.drop(self._hidden(x))))
@@ -218,14 +228,17 @@ class WindowAttention(nn.Module):
         if self.attn_drop.p > 0.0 and self.training:
             raise NotImplementedError("attention dropout is not fused; every reference config uses attn_drop=0")
         ws = self.window_size[0]
+        self._shortcut = None
         table, tau = self._bias_table(), self._tau()
         dt = torch.get_autocast_dtype("cuda") if (x_tokens.is_cuda and torch.is_autocast_enabled("cuda")) else x_tokens.dtype
         v_bias = None
         if mask is None and x_tokens.is_cuda and hvf.window_attention_kind(self.dim, self.num_heads, ws, dt) == 1:
             # tensor-core kernel: qkv Linear + attention are one autograd node (q_bias gradient from the kernel);
             # v_bias leaves the attention as a plain additive term because softmax rows sum to one
-            o = hvf.qkv_window_attention(x_tokens.to(dt), self.qkv.weight.to(dt), self.q_bias, table, tau, B=B, H=H, W=W,
-                                         C=self.dim, heads=self.num_heads, ws=ws, shift=shift)
+            o, sc = hvf.qkv_window_attention(x_tokens.to(dt), self.qkv.weight.to(dt), self.q_bias, table, tau, B=B, H=H,
+                                             W=W, C=self.dim, heads=self.num_heads, ws=ws, shift=shift)
+            if sc.dtype == x_tokens.dtype:
+                self._shortcut = sc  # same tensor as x_tokens; picked up by SwinTransformerBlock for the residual
             v_bias = self.v_bias
         else:
             o = hvf.window_attention(self._qkv(x_tokens), table, tau, B=B, H=H, W=W, C=self.dim,
@@ -247,7 +260,9 @@ class WindowAttention(nn.Module):
         ws = self.window_size[0]
         assert N == self.window_size[0] * self.window_size[1], "input feature has wrong size"
         # a pre-partitioned window is a ws x ws image with no shift
-        return self._fused(x, B_, ws, ws, 0, mask)
+        out = self._fused(x, B_, ws, ws, 0, mask)
+        self._shortcut = None
+        return out
 
     def extra_repr(self) -> str:
         return (f"dim={self.dim}, window_size={self.window_size}, "
@@ -315,9 +330,12 @@ class SwinTransformerBlock(nn.Module):
             y, proj_bias = self.attn._fused(x, B, H, W, self.shift_size, None, with_proj_bias=False)
         else:
             y, proj_bias = self.attn._fused(x, B, H, W, self.shift_size, None), None
+        if self.attn._shortcut is not None:  # x itself, routed through the attention node (gradient add fused into its GEMM)
+            x, self.attn._shortcut = self.attn._shortcut, None
         x = self._post_norm(self.norm1, y, x, proj_bias)                                       # swinv2.py:431
         if fold2:
-            m = F.linear(self.mlp._hidden(x), self.mlp.fc2.weight)
+            a, x = self.mlp._hidden(x, with_shortcut=True)
+            m = F.linear(a, self.mlp.fc2.weight)
             return self._post_norm(self.norm2, m, x, self.mlp.fc2.bias)                         # swinv2.py:434
         return self._post_norm(self.norm2, self.mlp(x), x)
 
