@@ -13,6 +13,9 @@ int wattn_generic_bwd(const Geom& g, int dtype, const void* qkv, const void* out
                       const float* bias_table, const float* tau, const float* mask, int mask_windows, void* dqkv,
                       float* dbias_table, float* dtau, cudaStream_t st);
 bool wattn_mma64_supported(const Geom& g, int dtype);
+bool wattn_tc64_supported(const Geom& g, int dtype);
+int wattn_tc64_fwd(const Geom& g, const void* qkv, const float* bias_table, const float* tau, void* out, float* lse,
+                   cudaStream_t st);
 size_t wattn_mma64_bwd_workspace_bytes(const Geom& g);
 int wattn_mma64_fwd(const Geom& g, const void* qkv, const float* bias_table, const float* tau, const float* mask,
                     int mask_windows, void* out, float* lse, cudaStream_t st);
@@ -176,7 +179,12 @@ int hv_window_attn_fwd(const void* qkv, const float* bias_table, const float* ta
   rc = attn_common_checks("hv_window_attn_fwd", dtype, mask, mask_windows, g);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (mask == nullptr && wattn_mma64_supported(g, dtype)) return wattn_mma64_fwd(g, qkv, bias_table, tau, mask, mask_windows, out, lse, st);
+  // tensor-core kernels (bf16, 8x8 window, head dim 32, in-kernel shift mask): tcgen05/TMEM/TMA forward when the
+  // shift is even, otherwise the mma.sync one; both write lse in log2 units for wattn_mma64_bwd
+  if (mask == nullptr && wattn_mma64_supported(g, dtype)) {
+    if (wattn_tc64_supported(g, dtype)) return wattn_tc64_fwd(g, qkv, bias_table, tau, out, lse, st);
+    return wattn_mma64_fwd(g, qkv, bias_table, tau, mask, mask_windows, out, lse, st);
+  }
   return wattn_generic_fwd(g, dtype, qkv, bias_table, tau, mask, mask_windows, out, lse, st);
 }
 

@@ -1,0 +1,615 @@
+// tcgen05 / TMEM / TMA forward kernel of the fused shifted-window scaled-cosine attention, window 8x8 (N = 64), head
+// dim 32, bf16 (every stage of SwinV2-T).  Same contract as wattn_mma64_fwd (qkv (B, H*W, 3C) and out (B, H*W, C) in
+// IMAGE token order, lse in log2 units), different machine mapping:
+//
+//   * the cyclic shift + window partition (swinv2.py:399-412) is the coordinate of a 4-D TMA tile load: one
+//     `cp.async.bulk.tensor.4d` with box (32 channels, 8, 8, 1) and SWIZZLE_64B brings the q, k or v tile of one
+//     (window, head) -- 64 rows x 64 B -- straight into the K-major layout tcgen05.mma reads.  Windows that wrap
+//     around the image edge are split into 2 boxes (rows) or 16 row boxes (columns), never copied twice;
+//   * two (window, head) units are stacked into one M = 128 tile: S = [Q_a; Q_b][K_a; K_b]^T is one
+//     tcgen05.mma (N = 128, K = 32) whose diagonal 64 x 64 blocks are the two logit matrices, accumulated in TMEM;
+//   * 128 softmax threads own one query row each (TMEM lane = row): tcgen05.ld, scale by 1/|q_i| * tau/|k_j|, add the
+//     continuous position bias (expanded once per CTA into shared memory), shift mask, exp2, and write P back to TMEM
+//     as bf16 (tcgen05.st) -- no shuffles, no fragments; O = P V and the row sums l = P 1 are tcgen05.mma with A
+//     from TMEM and V (MN-major, the same TMA tile) / a ones tile from shared memory;
+//   * warp roles: 0 TMA producer, 1 MMA issuer (one thread), 2-3 L2 norms of the q / k rows (tensor-pipe self
+//     products via mma.sync on the swizzled tiles), 4-11 two softmax groups working on alternate unit pairs so that
+//     the MMAs, the loads and the exponentials of neighbouring pairs overlap; everything hands over through mbarriers.
+#include <cuda.h>
+
+#include "hv_common.cuh"
+
+namespace hv {
+namespace {
+
+constexpr int kN = 64;
+constexpr int kWs = 8;
+constexpr int kTab = 225;
+constexpr int kTile = kN * 64;        // one (window, head) q / k / v tile: 64 rows x 64 B
+constexpr int kStage = 6 * kTile;     // q_a q_b k_a k_b v_a v_b
+constexpr int kStages = 4;
+constexpr int kBiasPitch = 68;        // floats per expanded-bias row (64 + pad: conflict-free 16-byte row reads)
+constexpr int kThreads = 384;
+constexpr float kNoMaxRange = 64.0f;
+
+// ---- shared memory map (dynamic, 1024-byte aligned base)
+constexpr int kOffStage = 0;
+constexpr int kOffOnes = kOffStage + kStages * kStage;                 // 64 x 64 B of bf16 ones
+constexpr int kOffBias = kOffOnes + kTile;                             // [2 units][64][kBiasPitch] float
+constexpr int kOffVec = kOffBias + 2 * kN * kBiasPitch * 4;            // [kStages][2 units][2 (r, c)][64] float
+constexpr int kOffBar = kOffVec + kStages * 2 * 2 * kN * 4;
+constexpr int kNumBars = 3 * kStages + 4 * 2;
+constexpr int kOffTmem = kOffBar + kNumBars * 8;
+constexpr int kSmem = kOffTmem + 16;
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity), "r"(20000u)  // suspend-time hint (ns)
+        : "memory");
+    if (done) break;
+    if (++spins > (1u << 17)) __trap();  // a lost arrival must abort the kernel (~seconds), never hang the GPU
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+#define HV_TMEM_LD32(taddr, r)                                                                                      \
+  asm volatile(                                                                                                     \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,"   \
+      "%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"                                                \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),  \
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),      \
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),     \
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                   \
+      : "r"(taddr))
+#define HV_TMEM_ST32(taddr, r)                                                                                      \
+  asm volatile(                                                                                                     \
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,"    \
+      "%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"                                               \
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),          \
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]),   \
+        "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), \
+        "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])                                      \
+      : "memory")
+
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+  uint32_t v;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr));
+  return v;
+}
+
+// K-major / MN-major SWIZZLE_64B shared-memory operand descriptor: 64-byte rows, 8-row groups 512 B apart
+// (cute::UMMA::SmemDescriptor: start >> 4 | LBO << 16 | SBO << 32 | version 1 << 46 | layout type << 61)
+__device__ __forceinline__ uint64_t sw64_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)4 << 61);
+}
+// instruction descriptor, kind::f16: bf16 x bf16 -> f32 (cute::UMMA::InstrDescriptor)
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_fast(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float inv_norm(float ss) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(fmaxf(ss, 1e-24f)));
+  return y;
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// squared norms of 16 rows x 32 bf16 held as two A fragments: diagonal of X X^T (see wattn_mma64.cu::rowdot_mma)
+__device__ __forceinline__ void rownorm2_mma(const uint32_t (&x)[2][4], int lane, float& s0, float& s1) {
+  float n0[4] = {0.f, 0.f, 0.f, 0.f}, n1[4] = {0.f, 0.f, 0.f, 0.f};
+  mma_bf16(n0, x[0], x[0][0], x[0][2]);
+  mma_bf16(n1, x[0], x[0][1], x[0][3]);
+  mma_bf16(n0, x[1], x[1][0], x[1][2]);
+  mma_bf16(n1, x[1], x[1][1], x[1][3]);
+  const bool odd = (lane >> 2) & 1;
+  const float v0 = odd ? n0[1] : n0[0];
+  const float v1 = odd ? n1[3] : n1[2];
+  const int src = (lane & ~3) | (lane >> 3);
+  s0 = __shfl_sync(0xffffffffu, v0, src);
+  s1 = __shfl_sync(0xffffffffu, v1, src);
+}
+
+struct TcParams {
+  Geom g;
+  int n_same;        // head groups whose two units are heads (2g, 2g+1) of the same window
+  int has_cross;     // 1: a last group pairs the odd head of two consecutive windows
+  int ctas_same;     // CTAs per same-window group
+  int ctas_cross;    // CTAs of the cross-window group
+};
+
+// The work of one CTA: group, position inside the group, and the unit pairs it walks through
+struct CtaWork {
+  int head_a, head_b, cross, first, stride, npairs;
+  __device__ __forceinline__ void init(const TcParams& p, int cta) {
+    const int nrows = p.g.B * p.g.nW;
+    const int same_total = p.n_same * p.ctas_same;
+    if (cta < same_total) {
+      const int grp = cta / p.ctas_same;
+      cross = 0; head_a = 2 * grp; head_b = 2 * grp + 1;
+      first = cta - grp * p.ctas_same; stride = p.ctas_same;
+      npairs = first < nrows ? (nrows - first + stride - 1) / stride : 0;
+    } else {
+      cross = 1; head_a = head_b = p.g.heads - 1;
+      first = cta - same_total; stride = p.ctas_cross;
+      const int nrp = (nrows + 1) / 2;
+      npairs = first < nrp ? (nrp - first + stride - 1) / stride : 0;
+    }
+  }
+  // window row of unit `which` of pair k; valid = false for the padding unit of an odd tail
+  __device__ __forceinline__ int row(int k, int which, int nrows, bool& valid) const {
+    const int idx = first + k * stride;
+    valid = true;
+    if (!cross) return idx;
+    const int r = 2 * idx + which;
+    if (r >= nrows) { valid = false; return nrows - 1; }
+    return r;
+  }
+};
+
+struct WinPos {
+  int b, row0, col0;
+  bool bottom, right;  // window touches the wrapped band along h / w
+};
+__device__ __forceinline__ WinPos win_pos(const Geom& g, int r) {
+  WinPos w;
+  w.b = r / g.nW;
+  const int win = r - w.b * g.nW;
+  const int wh = win / g.nWw, ww = win - wh * g.nWw;
+  w.row0 = wh * kWs + g.shift;
+  w.col0 = ww * kWs + g.shift;
+  w.bottom = g.shift > 0 && wh == g.H / kWs - 1;
+  w.right = g.shift > 0 && ww == g.nWw - 1;
+  return w;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+wattn_tc64_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_constant__ CUtensorMap map_ha,
+                      const __grid_constant__ CUtensorMap map_hb, const __grid_constant__ CUtensorMap map_ra,
+                      const __grid_constant__ CUtensorMap map_rb, const float* __restrict__ bias_table,
+                      const float* __restrict__ tau, bf16* __restrict__ out, float* __restrict__ lse, TcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const Geom& g = p.g;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t sb = smem_u32(smem);
+  const uint32_t bar0 = sb + kOffBar;
+  auto bar_full = [&](int s) { return bar0 + 8 * s; };
+  auto bar_empty = [&](int s) { return bar0 + 8 * (kStages + s); };
+  auto bar_norm = [&](int s) { return bar0 + 8 * (2 * kStages + s); };
+  auto bar_s = [&](int t) { return bar0 + 8 * (3 * kStages + t); };
+  auto bar_p = [&](int t) { return bar0 + 8 * (3 * kStages + 2 + t); };
+  auto bar_o = [&](int t) { return bar0 + 8 * (3 * kStages + 4 + t); };
+  auto bar_free = [&](int t) { return bar0 + 8 * (3 * kStages + 6 + t); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmem);
+  const int nrows = g.B * g.nW;
+
+  CtaWork work;
+  work.init(p, blockIdx.x);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 3);  // two norm warps + the MMA warp's commit
+      mbar_init(bar_norm(s), 2);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(bar_s(t), 1);
+      mbar_init(bar_p(t), 128);
+      mbar_init(bar_o(t), 1);
+      mbar_init(bar_free(t), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  // ones tile (B operand of the row-sum MMA) and the expanded bias of the CTA's two heads, in log2 units.
+  // Logits are tau2*cos + bias2 with |cos| <= 1: if 2*tau2 + (bias range) stays far inside the fp32 exponent range the
+  // running maximum is skipped and exp2(logit - (tau2 + max bias)) is used directly (see wattn_mma64.cu).
+  for (int i = threadIdx.x; i < kTile / 4; i += kThreads) reinterpret_cast<uint32_t*>(smem + kOffOnes)[i] = 0x3F803F80u;
+  __shared__ float s_off[2];
+  __shared__ int s_usemax[2];
+  if (warp < 2) {
+    const int head = warp == 0 ? work.head_a : work.head_b;
+    float bmx = -3.0e38f, bmn = 3.0e38f;
+    for (int r = lane; r < kTab; r += 32) {
+      const float b = kLog2e * __ldg(&bias_table[r * g.heads + head]);
+      bmx = fmaxf(bmx, b); bmn = fminf(bmn, b);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      bmx = fmaxf(bmx, __shfl_xor_sync(0xffffffffu, bmx, o));
+      bmn = fminf(bmn, __shfl_xor_sync(0xffffffffu, bmn, o));
+    }
+    const float tau2 = __ldg(&tau[head]) * kLog2e;
+    const bool use_max = !(2.0f * tau2 + (bmx - bmn) <= kNoMaxRange);
+    if (lane == 0) {
+      s_usemax[warp] = use_max ? 1 : 0;
+      s_off[warp] = use_max ? 0.f : tau2 + bmx;
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // ones tile is read by the tensor core (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  {
+    float* bias_s = reinterpret_cast<float*>(smem + kOffBias);
+    for (int idx = threadIdx.x; idx < 2 * kN * kN; idx += kThreads) {
+      const int u = idx >> 12, i = (idx >> 6) & 63, j = idx & 63;
+      const int head = u == 0 ? work.head_a : work.head_b;
+      bias_s[(u * kN + i) * kBiasPitch + j] = kLog2e * __ldg(&bias_table[rel_pos_index(kWs, i, j) * g.heads + head]) - s_off[u];
+    }
+  }
+  __syncthreads();
+  const uint32_t tmem = *tmem_slot;
+  const int npairs = work.npairs;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    for (int k = 0; k < npairs; ++k) {
+      const int s = k % kStages;
+      const uint32_t ph = (k / kStages) & 1;
+      mbar_wait(bar_empty(s), ph ^ 1);
+      if (lane == 0) mbar_expect_tx(bar_full(s), kStage);
+      __syncwarp();
+      const uint32_t st = sb + kOffStage + s * kStage;
+#pragma unroll 1
+      for (int t = 0; t < 6; ++t) {
+        const int which = t & 1, part = t >> 1;
+        bool valid;
+        const int r = work.row(k, which, nrows, valid);
+        const WinPos w = win_pos(g, r);
+        const int head = which == 0 ? work.head_a : work.head_b;
+        const int c0 = part * g.C + head * 32;
+        const uint32_t dst = st + t * kTile;
+        const bool hwrap = w.row0 + kWs > g.H, wwrap = w.col0 + kWs > g.W;
+        if (!wwrap) {
+          if (lane == 0) {
+            if (!hwrap) {
+              tma_load_4d(dst, &map_full, bar_full(s), c0, w.col0, w.row0, w.b);
+            } else {
+              tma_load_4d(dst, &map_ha, bar_full(s), c0, w.col0, w.row0, w.b);
+              tma_load_4d(dst + (kWs - g.shift) * kWs * 64, &map_hb, bar_full(s), c0, w.col0, 0, w.b);
+            }
+          }
+        } else if (lane < 16) {
+          const int ih = lane >> 1, second = lane & 1;
+          int irow = w.row0 + ih;
+          if (irow >= g.H) irow -= g.H;
+          if (!second) tma_load_4d(dst + ih * 512, &map_ra, bar_full(s), c0, w.col0, irow, w.b);
+          else tma_load_4d(dst + ih * 512 + (kWs - g.shift) * 64, &map_rb, bar_full(s), c0, 0, irow, w.b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t id_s = idesc_bf16(128, 128, 0, 0), id_o = idesc_bf16(128, 32, 0, 1);
+    const uint64_t ones_desc = sw64_desc(sb + kOffOnes);
+    auto issue_s = [&](int k) {
+      const int s = k % kStages, t = k & 1;
+      mbar_wait(bar_full(s), (k / kStages) & 1);
+      mbar_wait(bar_free(t), ((k >> 1) & 1) ^ 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t st = sb + kOffStage + s * kStage;
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk)
+          umma_ss(tmem + 256 * t, sw64_desc(st + 32 * kk), sw64_desc(st + 2 * kTile + 32 * kk), id_s, kk > 0);
+        umma_commit(bar_s(t));
+      }
+      __syncwarp();
+    };
+    if (npairs > 0) issue_s(0);
+    for (int k = 0; k < npairs; ++k) {
+      const int s = k % kStages, t = k & 1;
+      if (k + 1 < npairs) issue_s(k + 1);
+      mbar_wait(bar_p(t), (k >> 1) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t st = sb + kOffStage + s * kStage;
+        const uint32_t tb = tmem + 256 * t;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_ts(tb + 128 + 32 * half, tb + 8 * ks, sw64_desc(st + (4 + half) * kTile + 1024 * ks), id_o, ks > 0);
+        }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) umma_ts(tb + 192, tb + 8 * ks, ones_desc + (uint64_t)(64 * ks), id_o, ks > 0);
+        umma_commit(bar_o(t));
+        umma_commit(bar_empty(s));
+      }
+      __syncwarp();
+    }
+  } else if (warp < 4) {
+    // ------------------------------------------------------------------ norm warps: unit (warp - 2) of every pair
+    const int u = warp - 2;
+    const int head = u == 0 ? work.head_a : work.head_b;
+    const float tau2 = __ldg(&tau[head]) * kLog2e;
+    const int g_ = lane >> 2, t_ = lane & 3;
+    const int arow = (lane & 7) + 8 * ((lane >> 3) & 1), achunk = lane >> 4;
+    for (int k = 0; k < npairs; ++k) {
+      const int s = k % kStages;
+      mbar_wait(bar_full(s), (k / kStages) & 1);
+      const uint32_t st = sb + kOffStage + s * kStage;
+      float* vec = reinterpret_cast<float*>(smem + kOffVec) + (s * 2 + u) * 2 * kN;  // [r | c][64]
+#pragma unroll
+      for (int part = 0; part < 2; ++part) {
+        const uint32_t tile = st + (2 * part + u) * kTile;
+#pragma unroll
+        for (int blk = 0; blk < 4; ++blk) {
+          const int row = 16 * blk + arow;
+          uint32_t x[2][4];
+          ldsm_x4(tile + row * 64 + (((achunk) ^ ((row >> 1) & 3)) << 4), x[0]);
+          ldsm_x4(tile + row * 64 + (((2 + achunk) ^ ((row >> 1) & 3)) << 4), x[1]);
+          float s0, s1;
+          rownorm2_mma(x, lane, s0, s1);
+          if (t_ == 0) {
+            const float m = part == 0 ? 1.0f : tau2;
+            vec[part * kN + 16 * blk + g_] = m * inv_norm(s0);
+            vec[part * kN + 16 * blk + g_ + 8] = m * inv_norm(s1);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar_norm(s));
+        mbar_arrive(bar_empty(s));
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax groups (warps 4-7: even pairs, 8-11: odd)
+    const int grp = (warp - 4) >> 2;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;      // accumulator row = TMEM lane
+    const int u = row >> 6, i = row & 63;  // unit of the pair, query slot inside the window
+    const int head = u == 0 ? work.head_a : work.head_b;
+    const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16) + 256 * grp;
+    const bool use_max = s_usemax[u] != 0;
+    const float off = s_off[u];
+    const float kNeg = kMaskValue * kLog2e;
+    const int ih = i >> 3, iw = i & 7;
+    const int thr = kWs - g.shift;
+    // 64-bit column patterns of the wrapped band (bit j <-> key slot j)
+    unsigned long long colH = 0ull, colW = 0ull;
+    for (int j = 0; j < 64; ++j) {
+      if ((j >> 3) >= thr) colH |= 1ull << j;
+      if ((j & 7) >= thr) colW |= 1ull << j;
+    }
+    const unsigned long long mH = ih >= thr ? ~colH : colH, mW = iw >= thr ? ~colW : colW;
+    const float* bias_row = reinterpret_cast<const float*>(smem + kOffBias) + (u * kN + i) * kBiasPitch;
+
+    for (int k = grp; k < npairs; k += 2) {
+      const int s = k % kStages;
+      const uint32_t tph = (k >> 1) & 1;
+      bool valid;
+      const int r = work.row(k, u, nrows, valid);
+      const WinPos w = win_pos(g, r);
+      mbar_wait(bar_norm(s), (k / kStages) & 1);
+      const float* vec = reinterpret_cast<const float*>(smem + kOffVec) + (s * 2 + u) * 2 * kN;
+      const float ri = vec[i];
+      mbar_wait(bar_s(grp), tph);
+      tc_fence_after();
+      uint32_t acc[64];
+      HV_TMEM_LD32(tl + 64 * u, acc);
+      {
+        uint32_t(&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&acc[32]);
+        HV_TMEM_LD32(tl + 64 * u + 32, hi);
+      }
+      tmem_wait_ld();
+      float sv[64];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const float4 c = *reinterpret_cast<const float4*>(&vec[kN + 4 * q]);
+        const float4 b = *reinterpret_cast<const float4*>(&bias_row[4 * q]);
+        sv[4 * q + 0] = fmaf(__uint_as_float(acc[4 * q + 0]) * ri, c.x, b.x);
+        sv[4 * q + 1] = fmaf(__uint_as_float(acc[4 * q + 1]) * ri, c.y, b.y);
+        sv[4 * q + 2] = fmaf(__uint_as_float(acc[4 * q + 2]) * ri, c.z, b.z);
+        sv[4 * q + 3] = fmaf(__uint_as_float(acc[4 * q + 3]) * ri, c.w, b.w);
+      }
+      if (w.bottom || w.right) {  // warp-uniform: a warp's 32 rows belong to one unit
+        __syncwarp();             // convergence point: keeps the 64 predicated adds out of the interior-window path
+        const unsigned long long m = (w.bottom ? mH : 0ull) | (w.right ? mW : 0ull);
+#pragma unroll
+        for (int j = 0; j < 64; ++j)
+          if ((m >> j) & 1ull) sv[j] += kNeg;
+      }
+      float mx = 0.f;
+      if (use_max) {
+        mx = sv[0];
+#pragma unroll
+        for (int j = 1; j < 64; ++j) mx = fmaxf(mx, sv[j]);
+#pragma unroll
+        for (int j = 0; j < 64; ++j) sv[j] -= mx;
+      }
+      uint32_t pk[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) pk[j] = pack_bf16x2(ex2(sv[2 * j]), ex2(sv[2 * j + 1]));
+      HV_TMEM_ST32(tl, pk);  // P aliases the first 32 columns of the S block
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(bar_p(grp));
+
+      // ---- epilogue: O and l from TMEM, normalise, store the token's 64 B; row log-sum-exp in log2 units
+      mbar_wait(bar_o(grp), tph);
+      tc_fence_after();
+      uint32_t o[32];
+      HV_TMEM_LD32(tl + 128 + 32 * u, o);
+      const float l = __uint_as_float(tmem_ld1(tl + 192));
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(bar_free(grp));
+      if (valid) {
+        const float inv = rcp_fast(l);
+        int prow = w.row0 + ih; if (prow >= g.H) prow -= g.H;
+        int pcol = w.col0 + iw; if (pcol >= g.W) pcol -= g.W;
+        const int64_t tok = ((int64_t)w.b * g.H + prow) * g.W + pcol;
+        uint4* dst = reinterpret_cast<uint4*>(out + tok * g.C + head * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(o[8 * q + 0]) * inv, __uint_as_float(o[8 * q + 1]) * inv);
+          v.y = pack_bf16x2(__uint_as_float(o[8 * q + 2]) * inv, __uint_as_float(o[8 * q + 3]) * inv);
+          v.z = pack_bf16x2(__uint_as_float(o[8 * q + 4]) * inv, __uint_as_float(o[8 * q + 5]) * inv);
+          v.w = pack_bf16x2(__uint_as_float(o[8 * q + 6]) * inv, __uint_as_float(o[8 * q + 7]) * inv);
+          dst[q] = v;
+        }
+        lse[((int64_t)r * g.heads + head) * kN + i] = off + mx + lg2_fast(l);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+// (B, H, W, 3C) bf16 viewed as a 4-D tensor (channels, w, h, b); box = (32 channels, bw, bh, 1), 64-byte swizzle
+int make_map(CUtensorMap* m, const void* base, const Geom& g, int row_elems, int bw, int bh) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) HV_FAIL(HV_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[4] = {(cuuint64_t)row_elems, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.B};
+  cuuint64_t strides[3] = {(cuuint64_t)row_elems * 2, (cuuint64_t)g.W * row_elems * 2, (cuuint64_t)g.H * g.W * row_elems * 2};
+  cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) HV_FAIL(HV_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for box (32, %d, %d)", (int)r, bw, bh);
+  return HV_OK;
+}
+
+}  // namespace
+
+bool wattn_tc64_supported(const Geom& g, int dtype) {
+  static const bool enabled = []() { const char* e = getenv("HV_ATTN_TCGEN05"); return e != nullptr && atoi(e) != 0; }();
+  // an odd shift would put the second half of a column-wrapped row at a 64-byte (not 128-byte) shared-memory offset
+  return enabled && dtype == HV_BF16 && g.ws == kWs && g.d == 32 && g.C % 32 == 0 && (g.shift & 1) == 0 &&
+         (int64_t)g.B * g.H * g.W < (int64_t(1) << 31) && g.W * 3 * g.C * 2 % 16 == 0;
+}
+
+int wattn_tc64_fwd(const Geom& g, const void* qkv, const float* bias_table, const float* tau, void* out, float* lse,
+                   cudaStream_t st) {
+  if (!aligned16(qkv) || !aligned16(out)) HV_FAIL(HV_ERR_ALIGN, "window_attn: qkv/out must be 16-byte aligned");
+  CUtensorMap m_full, m_ha, m_hb, m_ra, m_rb;
+  const int s = g.shift;
+  int rc;
+  if ((rc = make_map(&m_full, qkv, g, 3 * g.C, kWs, kWs))) return rc;
+  if ((rc = make_map(&m_ha, qkv, g, 3 * g.C, kWs, s ? kWs - s : kWs))) return rc;
+  if ((rc = make_map(&m_hb, qkv, g, 3 * g.C, kWs, s ? s : kWs))) return rc;
+  if ((rc = make_map(&m_ra, qkv, g, 3 * g.C, s ? kWs - s : kWs, 1))) return rc;
+  if ((rc = make_map(&m_rb, qkv, g, 3 * g.C, s ? s : kWs, 1))) return rc;
+  TcParams p;
+  p.g = g;
+  p.n_same = g.heads / 2;
+  p.has_cross = g.heads & 1;
+  const int nsm = num_sms();
+  const int nrows = g.B * g.nW;
+  if (p.n_same == 0) {
+    p.ctas_same = 0;
+    p.ctas_cross = nsm;
+  } else if (!p.has_cross) {
+    p.ctas_same = nsm / p.n_same;
+    p.ctas_cross = 0;
+  } else {
+    p.ctas_cross = nsm / (2 * p.n_same + 1);
+    if (p.ctas_cross < 1) p.ctas_cross = 1;
+    p.ctas_same = (nsm - p.ctas_cross) / p.n_same;
+  }
+  if (p.ctas_same < 1 && p.n_same) p.ctas_same = 1;
+  if (p.ctas_same > nrows) p.ctas_same = nrows;
+  if (p.ctas_cross > (nrows + 1) / 2) p.ctas_cross = (nrows + 1) / 2;
+  const int grid = p.n_same * p.ctas_same + p.ctas_cross;
+  static thread_local int attr_dev = -1;
+  int dev = 0;
+  HV_CUDA_OK(cudaGetDevice(&dev));
+  if (attr_dev != dev) {
+    HV_CUDA_OK(cudaFuncSetAttribute(wattn_tc64_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    attr_dev = dev;
+  }
+  wattn_tc64_fwd_kernel<<<grid, kThreads, kSmem, st>>>(m_full, m_ha, m_hb, m_ra, m_rb, bias_table, tau, (bf16*)out, lse, p);
+  HV_LAUNCH_OK("wattn_tc64_fwd_kernel");
+  return HV_OK;
+}
+
+}  // namespace hv
