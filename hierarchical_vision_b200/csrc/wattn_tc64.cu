@@ -29,15 +29,20 @@ constexpr int kTile = kN * 64;        // one (window, head) q / k / v tile: 64 r
 constexpr int kStage = 6 * kTile;     // q_a q_b k_a k_b v_a v_b
 constexpr int kStages = 4;
 constexpr int kBiasPitch = 68;        // floats per expanded-bias row (64 + pad: conflict-free 16-byte row reads)
-constexpr int kThreads = 384;
+constexpr int kThreads = 896;  // 28 warps: 0 TMA, 1 MMA, (2-3 idle), 4-7 norms, 8-23 softmax, 24-27 epilogue
 constexpr float kNoMaxRange = 64.0f;
 
 // ---- shared memory map (dynamic, 1024-byte aligned base)
 constexpr int kOffStage = 0;
 constexpr int kOffOnes = kOffStage + kStages * kStage;                 // 64 x 64 B of bf16 ones
-constexpr int kOffBias = kOffOnes + kTile;                             // [2 units][64][kBiasPitch] float
-constexpr int kOffVec = kOffBias + 2 * kN * kBiasPitch * 4;            // [kStages][2 units][2 (r, c)][64] float
-constexpr int kOffBar = kOffVec + kStages * 2 * 2 * kN * 4;
+constexpr int kOffBias = kOffOnes + kTile;                             // [2 orders][2 units][64][kBiasPitch] float
+constexpr int kOffVec = kOffBias + 4 * kN * kBiasPitch * 4;            // [kStages][2 units][2 (r, c)][64] float
+constexpr int kOffMx = kOffVec + kStages * 2 * 2 * kN * 4;             // [2 slots][2 phases][128] float
+constexpr int kOffHmx = kOffMx + 4 * 128 * 4;                          // [2 slots][2 phases][2 halves][128] float
+constexpr int kOffTab = kOffHmx + 8 * 128 * 4;                         // [2 units][256] float
+constexpr int kOffGeo = kOffTab + 2 * 256 * 4;                         // [8][2] UnitGeo
+constexpr int kOffSlotMap = kOffGeo + 8 * 2 * 16;                      // [2 orders][64] bytes
+constexpr int kOffBar = kOffSlotMap + 128;
 constexpr int kNumBars = 3 * kStages + 4 * 2;
 constexpr int kOffTmem = kOffBar + kNumBars * 8;
 constexpr int kSmem = kOffTmem + 16;
@@ -183,6 +188,8 @@ struct TcParams {
   int ctas_same;     // CTAs per same-window group
   int ctas_cross;    // CTAs of the cross-window group
 };
+// box shapes (w, h): 0 full (8,8) | 1 (8,8-s) 2 (8,s) row wrap | 3 (8-s,8) 4 (s,8) column wrap | 5..8 corner
+struct TcMaps { CUtensorMap m[9]; };
 
 // The work of one CTA: group, position inside the group, and the unit pairs it walks through
 struct CtaWork {
@@ -228,11 +235,34 @@ __device__ __forceinline__ WinPos win_pos(const Geom& g, int r) {
   w.right = g.shift > 0 && ww == g.nWw - 1;
   return w;
 }
+// Window slot (ih, iw) held by tile row t.  Interior / row-wrapped windows are loaded in slot order; a column-wrapped
+// window arrives as two dense boxes (columns [0, 8-s) then [8-s, 8)), i.e. in a permuted row order.  Attention does
+// not care about the order of the tokens as long as bias, mask and the output address follow it.
+__device__ __forceinline__ void tile_row_slot(int t, int shift, bool perm, int& ih, int& iw) {
+  if (!perm) { ih = t >> 3; iw = t & 7; return; }
+  const int wa = kWs - shift;
+  if (t < kWs * wa) { ih = t / wa; iw = t - ih * wa; }
+  else { const int t2 = t - kWs * wa; ih = t2 / shift; iw = wa + t2 - ih * shift; }
+}
+
+template <int N> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// TMEM columns of one pair slot (two slots = all 512 columns)
+constexpr int kColS = 0, kColP = 128, kColO = 160, kColL = 224, kSlotCols = 256;
+
+// geometry of one unit of a pair, written by the producer, read by the softmax and epilogue threads
+struct UnitGeo { int b, row0, col0, rflags; };  // rflags = window row << 3 | right << 2 | bottom << 1 | valid
+
+#define HV_TMEM_ST16(taddr, r)                                                                                      \
+  asm volatile(                                                                                                     \
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"       \
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),          \
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])                \
+      : "memory")
 
 __global__ void __launch_bounds__(kThreads, 1)
-wattn_tc64_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_constant__ CUtensorMap map_ha,
-                      const __grid_constant__ CUtensorMap map_hb, const __grid_constant__ CUtensorMap map_ra,
-                      const __grid_constant__ CUtensorMap map_rb, const float* __restrict__ bias_table,
+wattn_tc64_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ bias_table,
                       const float* __restrict__ tau, bf16* __restrict__ out, float* __restrict__ lse, TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const Geom& g = p.g;
@@ -245,24 +275,27 @@ wattn_tc64_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid
   auto bar_s = [&](int t) { return bar0 + 8 * (3 * kStages + t); };
   auto bar_p = [&](int t) { return bar0 + 8 * (3 * kStages + 2 + t); };
   auto bar_o = [&](int t) { return bar0 + 8 * (3 * kStages + 4 + t); };
-  auto bar_free = [&](int t) { return bar0 + 8 * (3 * kStages + 6 + t); };
+  auto bar_ofree = [&](int t) { return bar0 + 8 * (3 * kStages + 6 + t); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmem);
   const int nrows = g.B * g.nW;
 
-  CtaWork work;
-  work.init(p, blockIdx.x);
-
+  // the CTA's work description lives in shared memory and every role copies it into its own registers after the role
+  // split (a value computed before the split would be live across all roles and spill in the small-register ones)
+  __shared__ CtaWork s_work;
   if (threadIdx.x == 0) {
+    CtaWork w0;
+    w0.init(p, blockIdx.x);
+    s_work = w0;
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_full(s), 1);
-      mbar_init(bar_empty(s), 3);  // two norm warps + the MMA warp's commit
-      mbar_init(bar_norm(s), 2);
+      mbar_init(bar_empty(s), 5);  // four norm warps + the MMA warp's commit
+      mbar_init(bar_norm(s), 4);
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(bar_s(t), 1);
-      mbar_init(bar_p(t), 128);
+      mbar_init(bar_p(t), 256);
       mbar_init(bar_o(t), 1);
-      mbar_init(bar_free(t), 128);
+      mbar_init(bar_ofree(t), 128);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -270,19 +303,30 @@ wattn_tc64_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  // ones tile (B operand of the row-sum MMA) and the expanded bias of the CTA's two heads, in log2 units.
+  // ---- one-time tables: ones tile (B operand of the row-sum MMA), window slot of every tile row in both load orders,
+  //      the bias table of the CTA's two heads in log2 units, and from those the expanded 64 x 64 bias matrices.
   // Logits are tau2*cos + bias2 with |cos| <= 1: if 2*tau2 + (bias range) stays far inside the fp32 exponent range the
   // running maximum is skipped and exp2(logit - (tau2 + max bias)) is used directly (see wattn_mma64.cu).
   for (int i = threadIdx.x; i < kTile / 4; i += kThreads) reinterpret_cast<uint32_t*>(smem + kOffOnes)[i] = 0x3F803F80u;
+  unsigned char* slotmap = smem + kOffSlotMap;  // [2 orders][64]: ih << 3 | iw
+  float* tab_s = reinterpret_cast<float*>(smem + kOffTab);  // [2 units][256]
   __shared__ float s_off[2];
   __shared__ int s_usemax[2];
+  if (threadIdx.x < 128) {
+    int ih, iw;
+    tile_row_slot(threadIdx.x & 63, g.shift > 0 ? g.shift : 4, threadIdx.x >= 64 && g.shift > 0, ih, iw);
+    slotmap[threadIdx.x] = (unsigned char)(ih << 3 | iw);
+  }
   if (warp < 2) {
-    const int head = warp == 0 ? work.head_a : work.head_b;
-    float bmx = -3.0e38f, bmn = 3.0e38f;
-    for (int r = lane; r < kTab; r += 32) {
-      const float b = kLog2e * __ldg(&bias_table[r * g.heads + head]);
-      bmx = fmaxf(bmx, b); bmn = fminf(bmn, b);
-    }
+    CtaWork w0;
+    w0.init(p, blockIdx.x);
+    const int head = warp == 0 ? w0.head_a : w0.head_b;
+    float bv[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) bv[q] = kLog2e * __ldg(&bias_table[min(lane + 32 * q, kTab - 1) * g.heads + head]);
+    float bmx = bv[0], bmn = bv[0];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) { bmx = fmaxf(bmx, bv[q]); bmn = fminf(bmn, bv[q]); }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       bmx = fmaxf(bmx, __shfl_xor_sync(0xffffffffu, bmx, o));
@@ -290,9 +334,13 @@ wattn_tc64_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid
     }
     const float tau2 = __ldg(&tau[head]) * kLog2e;
     const bool use_max = !(2.0f * tau2 + (bmx - bmn) <= kNoMaxRange);
+    const float off = use_max ? 0.f : tau2 + bmx;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (lane + 32 * q < kTab) tab_s[warp * 256 + lane + 32 * q] = bv[q] - off;
     if (lane == 0) {
       s_usemax[warp] = use_max ? 1 : 0;
-      s_off[warp] = use_max ? 0.f : tau2 + bmx;
+      s_off[warp] = off;
     }
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // ones tile is read by the tensor core (async proxy)
@@ -300,122 +348,138 @@ wattn_tc64_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid
   __syncthreads();
   tc_fence_after();
   {
+    // expanded bias: [order (slot / permuted)][unit][row][kBiasPitch]; the permuted copy only exists when shift > 0
     float* bias_s = reinterpret_cast<float*>(smem + kOffBias);
-    for (int idx = threadIdx.x; idx < 2 * kN * kN; idx += kThreads) {
-      const int u = idx >> 12, i = (idx >> 6) & 63, j = idx & 63;
-      const int head = u == 0 ? work.head_a : work.head_b;
-      bias_s[(u * kN + i) * kBiasPitch + j] = kLog2e * __ldg(&bias_table[rel_pos_index(kWs, i, j) * g.heads + head]) - s_off[u];
+    const int norders = g.shift > 0 ? 2 : 1;
+    for (int idx = threadIdx.x; idx < norders * 2 * kN * kN; idx += kThreads) {
+      const int ord = idx >> 13, u = (idx >> 12) & 1, ti = (idx >> 6) & 63, tj = idx & 63;
+      const int si = slotmap[ord * 64 + ti], sj = slotmap[ord * 64 + tj];
+      const int rel = ((si >> 3) - (sj >> 3) + kWs - 1) * (2 * kWs - 1) + ((si & 7) - (sj & 7) + kWs - 1);
+      bias_s[((ord * 2 + u) * kN + ti) * kBiasPitch + tj] = tab_s[u * 256 + rel];
     }
   }
   __syncthreads();
   const uint32_t tmem = *tmem_slot;
+  const CtaWork work = s_work;
   const int npairs = work.npairs;
+  float* mxv = reinterpret_cast<float*>(smem + kOffMx);    // [2 slots][2 phases][128]: off + row max, softmax -> epilogue
+  float* hmx = reinterpret_cast<float*>(smem + kOffHmx);   // [2 slots][2 phases][2 halves][128]: half-row maxima
+  UnitGeo* geo = reinterpret_cast<UnitGeo*>(smem + kOffGeo);  // [8][2]
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    for (int k = 0; k < npairs; ++k) {
-      const int s = k % kStages;
-      const uint32_t ph = (k / kStages) & 1;
-      mbar_wait(bar_empty(s), ph ^ 1);
-      if (lane == 0) mbar_expect_tx(bar_full(s), kStage);
-      __syncwarp();
-      const uint32_t st = sb + kOffStage + s * kStage;
-#pragma unroll 1
-      for (int t = 0; t < 6; ++t) {
-        const int which = t & 1, part = t >> 1;
+  if (warp < 4) {
+    reg_dealloc<40>();
+    if (warp == 0) {
+      // ---------------------------------------------------------------- TMA producer: lane t loads tile t of the stage
+      for (int k = 0; k < npairs; ++k) {
+        const int s = k % kStages;
+        const uint32_t ph = (k / kStages) & 1;
+        mbar_wait(bar_empty(s), ph ^ 1);
+        const int which = lane & 1, part = lane >> 1;
         bool valid;
         const int r = work.row(k, which, nrows, valid);
         const WinPos w = win_pos(g, r);
-        const int head = which == 0 ? work.head_a : work.head_b;
-        const int c0 = part * g.C + head * 32;
-        const uint32_t dst = st + t * kTile;
-        const bool hwrap = w.row0 + kWs > g.H, wwrap = w.col0 + kWs > g.W;
-        if (!wwrap) {
-          if (lane == 0) {
-            if (!hwrap) {
-              tma_load_4d(dst, &map_full, bar_full(s), c0, w.col0, w.row0, w.b);
-            } else {
-              tma_load_4d(dst, &map_ha, bar_full(s), c0, w.col0, w.row0, w.b);
-              tma_load_4d(dst + (kWs - g.shift) * kWs * 64, &map_hb, bar_full(s), c0, w.col0, 0, w.b);
-            }
+        if (lane < 2) {
+          UnitGeo ug;
+          ug.b = w.b; ug.row0 = w.row0; ug.col0 = w.col0;
+          ug.rflags = (r << 3) | (w.right ? 4 : 0) | (w.bottom ? 2 : 0) | (valid ? 1 : 0);
+          geo[(k & 7) * 2 + which] = ug;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_expect_tx(bar_full(s), kStage);
+        __syncwarp();
+        if (lane < 6) {
+          const int head = which == 0 ? work.head_a : work.head_b;
+          const int c0 = part * g.C + head * 32;
+          const uint32_t dst = sb + kOffStage + s * kStage + lane * kTile;
+          const uint32_t bar = bar_full(s);
+          const bool hwrap = w.row0 + kWs > g.H, wwrap = w.col0 + kWs > g.W;
+          const int sh = g.shift, wa = kWs - g.shift;
+          if (!wwrap && !hwrap) {
+            tma_load_4d(dst, &maps.m[0], bar, c0, w.col0, w.row0, w.b);
+          } else if (!wwrap) {
+            tma_load_4d(dst, &maps.m[1], bar, c0, w.col0, w.row0, w.b);
+            tma_load_4d(dst + wa * kWs * 64, &maps.m[2], bar, c0, w.col0, 0, w.b);
+          } else if (!hwrap) {
+            tma_load_4d(dst, &maps.m[3], bar, c0, w.col0, w.row0, w.b);
+            tma_load_4d(dst + kWs * wa * 64, &maps.m[4], bar, c0, 0, w.row0, w.b);
+          } else {
+            tma_load_4d(dst, &maps.m[5], bar, c0, w.col0, w.row0, w.b);                                  // (wa, wa)
+            tma_load_4d(dst + wa * wa * 64, &maps.m[6], bar, c0, w.col0, 0, w.b);                        // (wa, s)
+            tma_load_4d(dst + kWs * wa * 64, &maps.m[7], bar, c0, 0, w.row0, w.b);                       // (s, wa)
+            tma_load_4d(dst + kWs * wa * 64 + sh * wa * 64, &maps.m[8], bar, c0, 0, 0, w.b);             // (s, s)
           }
-        } else if (lane < 16) {
-          const int ih = lane >> 1, second = lane & 1;
-          int irow = w.row0 + ih;
-          if (irow >= g.H) irow -= g.H;
-          if (!second) tma_load_4d(dst + ih * 512, &map_ra, bar_full(s), c0, w.col0, irow, w.b);
-          else tma_load_4d(dst + ih * 512 + (kWs - g.shift) * 64, &map_rb, bar_full(s), c0, 0, irow, w.b);
         }
       }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    const uint32_t id_s = idesc_bf16(128, 128, 0, 0), id_o = idesc_bf16(128, 32, 0, 1);
-    const uint64_t ones_desc = sw64_desc(sb + kOffOnes);
-    auto issue_s = [&](int k) {
-      const int s = k % kStages, t = k & 1;
-      mbar_wait(bar_full(s), (k / kStages) & 1);
-      mbar_wait(bar_free(t), ((k >> 1) & 1) ^ 1);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t st = sb + kOffStage + s * kStage;
+    } else if (warp == 1) {
+      // ---------------------------------------------------------------- MMA issuer
+      const uint32_t id_s = idesc_bf16(128, 128, 0, 0), id_o = idesc_bf16(128, 32, 0, 1);
+      const uint64_t ones_desc = sw64_desc(sb + kOffOnes);
+      auto issue_s = [&](int k) {
+        const int s = k % kStages, t = k & 1;
+        mbar_wait(bar_full(s), (k / kStages) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t st = sb + kOffStage + s * kStage;
 #pragma unroll
-        for (int kk = 0; kk < 2; ++kk)
-          umma_ss(tmem + 256 * t, sw64_desc(st + 32 * kk), sw64_desc(st + 2 * kTile + 32 * kk), id_s, kk > 0);
-        umma_commit(bar_s(t));
-      }
-      __syncwarp();
-    };
-    if (npairs > 0) issue_s(0);
-    for (int k = 0; k < npairs; ++k) {
-      const int s = k % kStages, t = k & 1;
-      if (k + 1 < npairs) issue_s(k + 1);
-      mbar_wait(bar_p(t), (k >> 1) & 1);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t st = sb + kOffStage + s * kStage;
-        const uint32_t tb = tmem + 256 * t;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_ts(tb + 128 + 32 * half, tb + 8 * ks, sw64_desc(st + (4 + half) * kTile + 1024 * ks), id_o, ks > 0);
+          for (int kk = 0; kk < 2; ++kk)
+            umma_ss(tmem + kSlotCols * t + kColS, sw64_desc(st + 32 * kk), sw64_desc(st + 2 * kTile + 32 * kk), id_s, kk > 0);
+          umma_commit(bar_s(t));
         }
+        __syncwarp();
+      };
+      if (npairs > 0) issue_s(0);
+      if (npairs > 1) issue_s(1);
+      for (int k = 0; k < npairs; ++k) {
+        const int s = k % kStages, t = k & 1;
+        mbar_wait(bar_p(t), (k >> 1) & 1);
+        mbar_wait(bar_ofree(t), ((k >> 1) & 1) ^ 1);  // epilogue of pair k-2 has drained O / l of this slot
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t st = sb + kOffStage + s * kStage;
+          const uint32_t tb = tmem + kSlotCols * t;
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) umma_ts(tb + 192, tb + 8 * ks, ones_desc + (uint64_t)(64 * ks), id_o, ks > 0);
-        umma_commit(bar_o(t));
-        umma_commit(bar_empty(s));
+          for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_ts(tb + kColO + 32 * half, tb + kColP + 8 * ks, sw64_desc(st + (4 + half) * kTile + 1024 * ks), id_o, ks > 0);
+          }
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) umma_ts(tb + kColL, tb + kColP + 8 * ks, ones_desc + (uint64_t)(64 * ks), id_o, ks > 0);
+          umma_commit(bar_o(t));
+          umma_commit(bar_empty(s));
+        }
+        __syncwarp();
+        // S of the pair after next goes right behind (the tensor pipe runs in issue order; its S columns were consumed
+        // by the softmax group before it signalled P of pair k)
+        if (k + 2 < npairs) issue_s(k + 2);
       }
-      __syncwarp();
     }
-  } else if (warp < 4) {
-    // ------------------------------------------------------------------ norm warps: unit (warp - 2) of every pair
-    const int u = warp - 2;
+  } else if (warp < 8) {
+    // ------------------------------------------------------------------ norm warps: one (unit, q | k) tile of every pair each
+    const int u = warp & 1, part = (warp >> 1) & 1;
     const int head = u == 0 ? work.head_a : work.head_b;
-    const float tau2 = __ldg(&tau[head]) * kLog2e;
+    const float mult = part == 0 ? 1.0f : __ldg(&tau[head]) * kLog2e;
     const int g_ = lane >> 2, t_ = lane & 3;
     const int arow = (lane & 7) + 8 * ((lane >> 3) & 1), achunk = lane >> 4;
     for (int k = 0; k < npairs; ++k) {
       const int s = k % kStages;
       mbar_wait(bar_full(s), (k / kStages) & 1);
-      const uint32_t st = sb + kOffStage + s * kStage;
-      float* vec = reinterpret_cast<float*>(smem + kOffVec) + (s * 2 + u) * 2 * kN;  // [r | c][64]
+      const uint32_t tile = sb + kOffStage + s * kStage + (2 * part + u) * kTile;
+      float* vec = reinterpret_cast<float*>(smem + kOffVec) + ((s * 2 + u) * 2 + part) * kN;  // r (q tile) or c (k tile)
+      uint32_t x[4][2][4];
 #pragma unroll
-      for (int part = 0; part < 2; ++part) {
-        const uint32_t tile = st + (2 * part + u) * kTile;
+      for (int blk = 0; blk < 4; ++blk) {
+        const int row = 16 * blk + arow;
+        ldsm_x4(tile + row * 64 + (((achunk) ^ ((row >> 1) & 3)) << 4), x[blk][0]);
+        ldsm_x4(tile + row * 64 + (((2 + achunk) ^ ((row >> 1) & 3)) << 4), x[blk][1]);
+      }
 #pragma unroll
-        for (int blk = 0; blk < 4; ++blk) {
-          const int row = 16 * blk + arow;
-          uint32_t x[2][4];
-          ldsm_x4(tile + row * 64 + (((achunk) ^ ((row >> 1) & 3)) << 4), x[0]);
-          ldsm_x4(tile + row * 64 + (((2 + achunk) ^ ((row >> 1) & 3)) << 4), x[1]);
-          float s0, s1;
-          rownorm2_mma(x, lane, s0, s1);
-          if (t_ == 0) {
-            const float m = part == 0 ? 1.0f : tau2;
-            vec[part * kN + 16 * blk + g_] = m * inv_norm(s0);
-            vec[part * kN + 16 * blk + g_ + 8] = m * inv_norm(s1);
-          }
+      for (int blk = 0; blk < 4; ++blk) {
+        float s0, s1;
+        rownorm2_mma(x[blk], lane, s0, s1);
+        if (t_ == 0) {
+          vec[16 * blk + g_] = mult * inv_norm(s0);
+          vec[16 * blk + g_ + 8] = mult * inv_norm(s1);
         }
       }
       __syncwarp();
@@ -424,93 +488,119 @@ wattn_tc64_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid
         mbar_arrive(bar_empty(s));
       }
     }
-  } else {
-    // ------------------------------------------------------------------ softmax groups (warps 4-7: even pairs, 8-11: odd)
-    const int grp = (warp - 4) >> 2;
+  } else if (warp < 24) {
+    // ------------------------------------------------------------------ softmax: 2 groups (alternate pairs) x 2 column
+    // halves x 4 lane quadrants; a thread owns half a logit row (32 keys) of one query
+    reg_alloc<80>();
+    const int grp = (warp - 8) >> 3;
+    const int half = ((warp - 8) >> 2) & 1;
     const int quad = warp & 3;
     const int row = quad * 32 + lane;      // accumulator row = TMEM lane
-    const int u = row >> 6, i = row & 63;  // unit of the pair, query slot inside the window
-    const int head = u == 0 ? work.head_a : work.head_b;
-    const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16) + 256 * grp;
+    const int u = row >> 6, i = row & 63;  // unit of the pair, tile row inside the unit
+    const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16) + kSlotCols * grp;
     const bool use_max = s_usemax[u] != 0;
     const float off = s_off[u];
     const float kNeg = kMaskValue * kLog2e;
-    const int ih = i >> 3, iw = i & 7;
     const int thr = kWs - g.shift;
-    // 64-bit column patterns of the wrapped band (bit j <-> key slot j)
-    unsigned long long colH = 0ull, colW = 0ull;
-    for (int j = 0; j < 64; ++j) {
-      if ((j >> 3) >= thr) colH |= 1ull << j;
-      if ((j & 7) >= thr) colW |= 1ull << j;
+    // 32-bit patterns of the wrapped band over this thread's 32 keys, xor-ed with the own row's membership:
+    // slot order / permuted order
+    uint32_t mHn = 0u, mWn = 0u, mHp = 0u, mWp = 0u;
+    if (g.shift > 0) {
+      for (int j = 0; j < 32; ++j) {
+        const int sn = slotmap[32 * half + j], sp = slotmap[64 + 32 * half + j];
+        if ((sn >> 3) >= thr) mHn |= 1u << j;
+        if ((sn & 7) >= thr) mWn |= 1u << j;
+        if ((sp >> 3) >= thr) mHp |= 1u << j;
+        if ((sp & 7) >= thr) mWp |= 1u << j;
+      }
+      const int sn = slotmap[i], sp = slotmap[64 + i];
+      if ((sn >> 3) >= thr) mHn = ~mHn;
+      if ((sn & 7) >= thr) mWn = ~mWn;
+      if ((sp >> 3) >= thr) mHp = ~mHp;
+      if ((sp & 7) >= thr) mWp = ~mWp;
     }
-    const unsigned long long mH = ih >= thr ? ~colH : colH, mW = iw >= thr ? ~colW : colW;
-    const float* bias_row = reinterpret_cast<const float*>(smem + kOffBias) + (u * kN + i) * kBiasPitch;
+    const float* bias_n = reinterpret_cast<const float*>(smem + kOffBias) + (u * kN + i) * kBiasPitch + 32 * half;
+    const float* bias_p = bias_n + 2 * kN * kBiasPitch;
 
     for (int k = grp; k < npairs; k += 2) {
       const int s = k % kStages;
       const uint32_t tph = (k >> 1) & 1;
-      bool valid;
-      const int r = work.row(k, u, nrows, valid);
-      const WinPos w = win_pos(g, r);
       mbar_wait(bar_norm(s), (k / kStages) & 1);
+      const int rflags = geo[(k & 7) * 2 + u].rflags;
+      const float* bias_row = (rflags & 4) ? bias_p : bias_n;
       const float* vec = reinterpret_cast<const float*>(smem + kOffVec) + (s * 2 + u) * 2 * kN;
       const float ri = vec[i];
       mbar_wait(bar_s(grp), tph);
       tc_fence_after();
-      uint32_t acc[64];
-      HV_TMEM_LD32(tl + 64 * u, acc);
-      {
-        uint32_t(&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&acc[32]);
-        HV_TMEM_LD32(tl + 64 * u + 32, hi);
-      }
+      uint32_t acc[32];
+      HV_TMEM_LD32(tl + kColS + 64 * u + 32 * half, acc);
       tmem_wait_ld();
-      float sv[64];
+      float sv[32];
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const float4 c = *reinterpret_cast<const float4*>(&vec[kN + 4 * q]);
+      for (int q = 0; q < 8; ++q) {
+        const float4 c = *reinterpret_cast<const float4*>(&vec[kN + 32 * half + 4 * q]);
         const float4 b = *reinterpret_cast<const float4*>(&bias_row[4 * q]);
         sv[4 * q + 0] = fmaf(__uint_as_float(acc[4 * q + 0]) * ri, c.x, b.x);
         sv[4 * q + 1] = fmaf(__uint_as_float(acc[4 * q + 1]) * ri, c.y, b.y);
         sv[4 * q + 2] = fmaf(__uint_as_float(acc[4 * q + 2]) * ri, c.z, b.z);
         sv[4 * q + 3] = fmaf(__uint_as_float(acc[4 * q + 3]) * ri, c.w, b.w);
       }
-      if (w.bottom || w.right) {  // warp-uniform: a warp's 32 rows belong to one unit
-        __syncwarp();             // convergence point: keeps the 64 predicated adds out of the interior-window path
-        const unsigned long long m = (w.bottom ? mH : 0ull) | (w.right ? mW : 0ull);
+      if (rflags & 6) {  // warp-uniform: a warp's 32 rows belong to one unit
+        __syncwarp();    // convergence point: keeps the predicated adds out of the interior-window path
+        const bool right = rflags & 4, bottom = rflags & 2;
+        const uint32_t m = (bottom ? (right ? mHp : mHn) : 0u) | (right ? mWp : 0u);
 #pragma unroll
-        for (int j = 0; j < 64; ++j)
-          if ((m >> j) & 1ull) sv[j] += kNeg;
+        for (int j = 0; j < 32; ++j)
+          if ((m >> j) & 1u) sv[j] += kNeg;
       }
       float mx = 0.f;
       if (use_max) {
         mx = sv[0];
 #pragma unroll
-        for (int j = 1; j < 64; ++j) mx = fmaxf(mx, sv[j]);
+        for (int j = 1; j < 32; ++j) mx = fmaxf(mx, sv[j]);
+        float* hm = hmx + ((grp * 2 + tph) * 2) * 128;
+        hm[half * 128 + row] = mx;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + grp * 4 + quad) : "memory");
+        mx = fmaxf(mx, hm[(half ^ 1) * 128 + row]);
 #pragma unroll
-        for (int j = 0; j < 64; ++j) sv[j] -= mx;
+        for (int j = 0; j < 32; ++j) sv[j] -= mx;
       }
-      uint32_t pk[32];
+      uint32_t pk[16];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) pk[j] = pack_bf16x2(ex2(sv[2 * j]), ex2(sv[2 * j + 1]));
-      HV_TMEM_ST32(tl, pk);  // P aliases the first 32 columns of the S block
+      for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(ex2(sv[2 * j]), ex2(sv[2 * j + 1]));
+      HV_TMEM_ST16(tl + kColP + 16 * half, pk);
+      if (half == 0) mxv[(grp * 2 + tph) * 128 + row] = off + mx;
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(bar_p(grp));
-
-      // ---- epilogue: O and l from TMEM, normalise, store the token's 64 B; row log-sum-exp in log2 units
-      mbar_wait(bar_o(grp), tph);
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps: O and l from TMEM, normalise, store
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int u = row >> 6, i = row & 63;
+    const int head = u == 0 ? work.head_a : work.head_b;
+    const int sn = slotmap[i], sp = slotmap[64 + i];
+    for (int k = 0; k < npairs; ++k) {
+      const int t = k & 1;
+      const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16) + kSlotCols * t;
+      mbar_wait(bar_o(t), (k >> 1) & 1);
       tc_fence_after();
       uint32_t o[32];
-      HV_TMEM_LD32(tl + 128 + 32 * u, o);
-      const float l = __uint_as_float(tmem_ld1(tl + 192));
+      HV_TMEM_LD32(tl + kColO + 32 * u, o);
+      const float l = __uint_as_float(tmem_ld1(tl + kColL));
       tmem_wait_ld();
+      const float lse_off = mxv[(t * 2 + ((k >> 1) & 1)) * 128 + row];
+      const UnitGeo ug = geo[(k & 7) * 2 + u];
       tc_fence_before();
-      mbar_arrive(bar_free(grp));
-      if (valid) {
+      mbar_arrive(bar_ofree(t));
+      if (ug.rflags & 1) {
         const float inv = rcp_fast(l);
-        int prow = w.row0 + ih; if (prow >= g.H) prow -= g.H;
-        int pcol = w.col0 + iw; if (pcol >= g.W) pcol -= g.W;
-        const int64_t tok = ((int64_t)w.b * g.H + prow) * g.W + pcol;
+        const int sl = (ug.rflags & 4) ? sp : sn;
+        const int ih = sl >> 3, iw = sl & 7;
+        int prow = ug.row0 + ih; if (prow >= g.H) prow -= g.H;
+        int pcol = ug.col0 + iw; if (pcol >= g.W) pcol -= g.W;
+        const int64_t tok = ((int64_t)ug.b * g.H + prow) * g.W + pcol;
         uint4* dst = reinterpret_cast<uint4*>(out + tok * g.C + head * 32);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -521,7 +611,7 @@ wattn_tc64_fwd_kernel(const __grid_constant__ CUtensorMap map_full, const __grid
           v.w = pack_bf16x2(__uint_as_float(o[8 * q + 6]) * inv, __uint_as_float(o[8 * q + 7]) * inv);
           dst[q] = v;
         }
-        lse[((int64_t)r * g.heads + head) * kN + i] = off + mx + lg2_fast(l);
+        lse[((int64_t)(ug.rflags >> 3) * g.heads + head) * kN + sl] = lse_off + lg2_fast(l);
       }
     }
   }
@@ -562,7 +652,7 @@ int make_map(CUtensorMap* m, const void* base, const Geom& g, int row_elems, int
 }  // namespace
 
 bool wattn_tc64_supported(const Geom& g, int dtype) {
-  static const bool enabled = []() { const char* e = getenv("HV_ATTN_TCGEN05"); return e != nullptr && atoi(e) != 0; }();
+  static const bool enabled = []() { const char* e = getenv("HV_ATTN_TCGEN05"); return e == nullptr || atoi(e) != 0; }();
   // an odd shift would put the second half of a column-wrapped row at a 64-byte (not 128-byte) shared-memory offset
   return enabled && dtype == HV_BF16 && g.ws == kWs && g.d == 32 && g.C % 32 == 0 && (g.shift & 1) == 0 &&
          (int64_t)g.B * g.H * g.W < (int64_t(1) << 31) && g.W * 3 * g.C * 2 % 16 == 0;
@@ -571,14 +661,15 @@ bool wattn_tc64_supported(const Geom& g, int dtype) {
 int wattn_tc64_fwd(const Geom& g, const void* qkv, const float* bias_table, const float* tau, void* out, float* lse,
                    cudaStream_t st) {
   if (!aligned16(qkv) || !aligned16(out)) HV_FAIL(HV_ERR_ALIGN, "window_attn: qkv/out must be 16-byte aligned");
-  CUtensorMap m_full, m_ha, m_hb, m_ra, m_rb;
-  const int s = g.shift;
-  int rc;
-  if ((rc = make_map(&m_full, qkv, g, 3 * g.C, kWs, kWs))) return rc;
-  if ((rc = make_map(&m_ha, qkv, g, 3 * g.C, kWs, s ? kWs - s : kWs))) return rc;
-  if ((rc = make_map(&m_hb, qkv, g, 3 * g.C, kWs, s ? s : kWs))) return rc;
-  if ((rc = make_map(&m_ra, qkv, g, 3 * g.C, s ? kWs - s : kWs, 1))) return rc;
-  if ((rc = make_map(&m_rb, qkv, g, 3 * g.C, s ? s : kWs, 1))) return rc;
+  TcMaps maps;
+  const int s = g.shift, wa = kWs - g.shift;
+  // (w, h) of every box; with shift 0 only the first is used (the others just need to be valid descriptors)
+  const int bw[9] = {kWs, kWs, kWs, s ? wa : kWs, s ? s : kWs, s ? wa : kWs, s ? wa : kWs, s ? s : kWs, s ? s : kWs};
+  const int bh[9] = {kWs, s ? wa : kWs, s ? s : kWs, kWs, kWs, s ? wa : kWs, s ? s : kWs, s ? wa : kWs, s ? s : kWs};
+  for (int i = 0; i < 9; ++i) {
+    const int rc = make_map(&maps.m[i], qkv, g, 3 * g.C, bw[i], bh[i]);
+    if (rc) return rc;
+  }
   TcParams p;
   p.g = g;
   p.n_same = g.heads / 2;
@@ -607,7 +698,7 @@ int wattn_tc64_fwd(const Geom& g, const void* qkv, const float* bias_table, cons
     HV_CUDA_OK(cudaFuncSetAttribute(wattn_tc64_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     attr_dev = dev;
   }
-  wattn_tc64_fwd_kernel<<<grid, kThreads, kSmem, st>>>(m_full, m_ha, m_hb, m_ra, m_rb, bias_table, tau, (bf16*)out, lse, p);
+  wattn_tc64_fwd_kernel<<<grid, kThreads, kSmem, st>>>(maps, bias_table, tau, (bf16*)out, lse, p);
   HV_LAUNCH_OK("wattn_tc64_fwd_kernel");
   return HV_OK;
 }
