@@ -14,6 +14,7 @@ int wattn_generic_bwd(const Geom& g, int dtype, const void* qkv, const void* out
                       float* dbias_table, float* dtau, cudaStream_t st);
 bool wattn_mma64_supported(const Geom& g, int dtype);
 bool wattn_tc64_supported(const Geom& g, int dtype);
+int wattn_fwd_variant_set(int v);
 int wattn_tc64_fwd(const Geom& g, const void* qkv, const float* bias_table, const float* tau, void* out, float* lse,
                    cudaStream_t st);
 size_t wattn_mma64_bwd_workspace_bytes(const Geom& g);
@@ -106,6 +107,12 @@ extern "C" {
 int hv_abi_version(void) { return HV_ABI_VERSION; }
 const char* hv_last_error(void) { return g_err; }
 int hv_compiled_arch(void) { return 100; }
+
+int hv_window_attn_fwd_variant(int variant) {
+  if (variant < -1 || variant > 1) HV_FAIL(HV_ERR_SHAPE, "hv_window_attn_fwd_variant: variant %d", variant);
+  wattn_fwd_variant_set(variant);
+  return HV_OK;
+}
 
 int hv_window_attn_kernel_kind(int C, int heads, int ws, int dtype) {
   if (heads <= 0 || C % heads) return 0;

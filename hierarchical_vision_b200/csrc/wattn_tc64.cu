@@ -70,6 +70,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (++spins > (1u << 17)) __trap();  // a lost arrival must abort the kernel (~seconds), never hang the GPU
   }
 }
+// latency-critical variant: plain try_wait loop (the hardware's default suspend window), no extra sleep
+__device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > (1u << 24)) __trap();
+  }
+}
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -416,7 +431,7 @@ wattn_tc64_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restri
       const uint64_t ones_desc = sw64_desc(sb + kOffOnes);
       auto issue_s = [&](int k) {
         const int s = k % kStages, t = k & 1;
-        mbar_wait(bar_full(s), (k / kStages) & 1);
+        mbar_wait_fast(bar_full(s), (k / kStages) & 1);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t st = sb + kOffStage + s * kStage;
@@ -431,8 +446,8 @@ wattn_tc64_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restri
       if (npairs > 1) issue_s(1);
       for (int k = 0; k < npairs; ++k) {
         const int s = k % kStages, t = k & 1;
-        mbar_wait(bar_p(t), (k >> 1) & 1);
-        mbar_wait(bar_ofree(t), ((k >> 1) & 1) ^ 1);  // epilogue of pair k-2 has drained O / l of this slot
+        mbar_wait_fast(bar_p(t), (k >> 1) & 1);
+        mbar_wait_fast(bar_ofree(t), ((k >> 1) & 1) ^ 1);  // epilogue of pair k-2 has drained O / l of this slot
         tc_fence_after();
         if (lane == 0) {
           const uint32_t st = sb + kOffStage + s * kStage;
@@ -525,12 +540,12 @@ wattn_tc64_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restri
     for (int k = grp; k < npairs; k += 2) {
       const int s = k % kStages;
       const uint32_t tph = (k >> 1) & 1;
-      mbar_wait(bar_norm(s), (k / kStages) & 1);
+      mbar_wait_fast(bar_norm(s), (k / kStages) & 1);
       const int rflags = geo[(k & 7) * 2 + u].rflags;
       const float* bias_row = (rflags & 4) ? bias_p : bias_n;
       const float* vec = reinterpret_cast<const float*>(smem + kOffVec) + (s * 2 + u) * 2 * kN;
       const float ri = vec[i];
-      mbar_wait(bar_s(grp), tph);
+      mbar_wait_fast(bar_s(grp), tph);
       tc_fence_after();
       uint32_t acc[32];
       HV_TMEM_LD32(tl + kColS + 64 * u + 32 * half, acc);
@@ -584,7 +599,7 @@ wattn_tc64_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restri
     for (int k = 0; k < npairs; ++k) {
       const int t = k & 1;
       const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16) + kSlotCols * t;
-      mbar_wait(bar_o(t), (k >> 1) & 1);
+      mbar_wait_fast(bar_o(t), (k >> 1) & 1);
       tc_fence_after();
       uint32_t o[32];
       HV_TMEM_LD32(tl + kColO + 32 * u, o);
@@ -651,8 +666,17 @@ int make_map(CUtensorMap* m, const void* base, const Geom& g, int row_elems, int
 
 }  // namespace
 
+static int g_fwd_variant = -1;  // -1: HV_ATTN_TCGEN05 environment variable (default off), 0: mma.sync, 1: tcgen05
+
+int wattn_fwd_variant_set(int v) {
+  const int old = g_fwd_variant;
+  g_fwd_variant = v;
+  return old;
+}
+
 bool wattn_tc64_supported(const Geom& g, int dtype) {
-  static const bool enabled = []() { const char* e = getenv("HV_ATTN_TCGEN05"); return e == nullptr || atoi(e) != 0; }();
+  static const bool env_on = []() { const char* e = getenv("HV_ATTN_TCGEN05"); return e != nullptr && atoi(e) != 0; }();
+  const bool enabled = g_fwd_variant < 0 ? env_on : g_fwd_variant == 1;
   // an odd shift would put the second half of a column-wrapped row at a 64-byte (not 128-byte) shared-memory offset
   return enabled && dtype == HV_BF16 && g.ws == kWs && g.d == 32 && g.C % 32 == 0 && (g.shift & 1) == 0 &&
          (int64_t)g.B * g.H * g.W < (int64_t(1) << 31) && g.W * 3 * g.C * 2 % 16 == 0;

@@ -63,6 +63,11 @@ def _timed(tag, windows, stream_device, fn, kernels=1):
     return r
 
 
+def set_attention_forward_variant(variant: int) -> None:
+    """0: mma.sync forward kernel, 1: tcgen05/TMEM/TMA forward kernel, -1: HV_ATTN_TCGEN05 environment (default 0)."""
+    check(_lib.load().hv_window_attn_fwd_variant(int(variant)), "hv_window_attn_fwd_variant")
+
+
 def window_attention_fwd_raw(qkv, bias_table, tau, mask, out, lse, B, H, W, C, heads, ws, shift):
     """Enqueue hv_window_attn_fwd on the current stream; every tensor is caller-allocated."""
     lib = _lib.load()

@@ -58,6 +58,11 @@ HV_API int hv_compiled_arch(void);
  * 1 = tensor-core kernel (N=64, head dim 32, bf16).  Host-only query. */
 HV_API int hv_window_attn_kernel_kind(int C, int heads, int ws, int dtype);
 
+/* Forward kernel of the tensor-core path (kind 1): 0 = mma.sync + cp.async kernel, 1 = tcgen05 / TMEM / TMA kernel
+ * (even shift sizes; falls back to 0 otherwise), -1 = decided by the HV_ATTN_TCGEN05 environment variable
+ * (default 0).  Both write the same outputs; process-wide setting, not thread-safe against concurrent launches. */
+HV_API int hv_window_attn_fwd_variant(int variant);
+
 /* ---- host-side integer maps (CPU; same arithmetic the kernels use on the device) ------ */
 /* relative_position_index (N,N) int64 -- reference swinv2.py:175-190 */
 HV_API int hv_relative_position_index(int ws, int64_t* out);

@@ -55,9 +55,17 @@ CORE_CASES = [
 ]
 
 
+@pytest.fixture(params=[0, 1], ids=["fwd_mma_sync", "fwd_tcgen05"])
+def fwd_variant(request):
+    """Both forward kernels of the tensor-core path: mma.sync + cp.async, and tcgen05 / TMEM / TMA."""
+    hvf.set_attention_forward_variant(request.param)
+    yield request.param
+    hvf.set_attention_forward_variant(-1)
+
+
 @pytest.mark.parametrize("case", CORE_CASES)
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_window_attention_core(case, dtype):
+def test_window_attention_core(case, dtype, fwd_variant):
     B, H, W, C, h, ws, s = case
     g = O.Geometry(B, H, W, C, h, ws, s)
     gen = torch.Generator().manual_seed(hash(case) % 1000)
@@ -78,8 +86,8 @@ def test_window_attention_core(case, dtype):
 
 
 @pytest.mark.parametrize("taus", [(0.05, 10.0, 100.0), (100.0, 100.0, 100.0), (1.0, 13.0, 15.0), (30.0, 2.0, 60.0)])
-@pytest.mark.parametrize("shift", [0, 4])
-def test_window_attention_core_tau_range(taus, shift):
+@pytest.mark.parametrize("shift", [0, 4, 2, 6])
+def test_window_attention_core_tau_range(taus, shift, fwd_variant):
     """Tensor-core kernel across the whole logit-scale range: exp(logit_scale) from ~0 to the clamp at 100
     (swinv2.py:230).  Heads with a small scale take the softmax path without a running maximum, heads near the
     clamp the path with it; both must agree with the fp64 oracle on the same bf16 inputs."""
