@@ -269,12 +269,16 @@ def run_ours(args):
     stage_lab = torch.empty_like(dev_lab[0])
 
     def e2e_step(i):
-        if use_graph:  # the graph's static input buffers are the H2D destination
-            return step(host_img[i % n_host], host_lab[i % n_host]).item()
+        if use_graph:  # batch i was prefetched during step i-1; start the copy of batch i+1, then run step i
+            loss_t = step.step_prefetched()
+            step.prefetch(host_img[(i + 1) % n_host], host_lab[(i + 1) % n_host])
+            return loss_t.item()  # D2H read of the step's loss
         stage_img.copy_(host_img[i % n_host], non_blocking=True)
         stage_lab.copy_(host_lab[i % n_host], non_blocking=True)
         return step(stage_img, stage_lab).item()  # D2H read of the step's loss
 
+    if use_graph:
+        step.prefetch(host_img[0], host_lab[0])
     for i in range(2):
         e2e_step(i)
     T.barrier(env)
@@ -282,7 +286,7 @@ def run_ours(args):
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     for i in range(args.steps):
-        loss_host = e2e_step(i)
+        loss_host = e2e_step(2 + i)
     e3.record()
     torch.cuda.synchronize()
     T.barrier(env)
@@ -349,6 +353,8 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * n,
                        "precision": "torch.autocast(bfloat16), fp32 master weights, bf16 activations",
                        "optimizer": "SGD momentum 0.875 wd 5e-4, grad-clip 2.0, drop_path 0.1", "parallelism": f"dp{n}",
+                       "e2e_input": ("every step copies its uint8 batch + labels from pinned host memory (side stream, overlapped "
+                                     "with the previous step) and reads the loss back") if use_graph else "copy, step, read back",
                        "launch": ("one CUDA graph per step (flat fp32 gradient buffer, one NCCL all-reduce(avg) captured "
                                   "in the graph when N > 1)") if use_graph else "eager, DistributedDataParallel",
                        "l2": "no flush needed: each step streams > 10 GB of activations, far beyond the 126 MB L2"},

@@ -193,6 +193,12 @@ class GraphedTrainStep:
         self.static_img.copy_(img)
         self.static_lab.copy_(lab)
         self._warmup = warmup
+        # input pipeline: host batches are copied on a side stream into one of two device staging buffers while the
+        # previous step is still running; the step then starts with a device-to-device copy into the static buffers
+        self._copy_stream = torch.cuda.Stream(device=img.device)
+        self._stage = [(torch.empty_like(img), torch.empty_like(lab), torch.cuda.Event()) for _ in range(2)]
+        self._consumed = [torch.cuda.Event() for _ in range(2)]  # staging slot copied into the static buffers
+        self._staged = 0
 
     def eager(self, img: torch.Tensor, lab: torch.Tensor) -> torch.Tensor:
         """The same step without the graph (warm-up, per-kernel instrumentation, debugging)."""
@@ -234,6 +240,31 @@ class GraphedTrainStep:
             self.flat.mul_(torch.clamp(self.clip_norm / (total + 1e-6), max=1.0))
         self.optimizer.step()
         return loss.detach()
+
+    def prefetch(self, img: torch.Tensor, lab: torch.Tensor) -> None:
+        """Start the host->device copy of the NEXT batch (pinned host tensors) on the copy stream; it overlaps with
+        whatever the compute stream is doing.  Consume it with :meth:`step_prefetched`."""
+        slot = self._staged ^ 1
+        dimg, dlab, ev = self._stage[slot]
+        self._copy_stream.wait_event(self._consumed[slot])  # the slot's previous content has been copied out
+        with torch.cuda.stream(self._copy_stream):
+            dimg.copy_(img, non_blocking=True)
+            dlab.copy_(lab, non_blocking=True)
+            ev.record(self._copy_stream)
+        self._staged = slot
+
+    def step_prefetched(self) -> torch.Tensor:
+        """Run one step on the batch handed to the last :meth:`prefetch`."""
+        if self.graph is None:
+            self.capture()
+        dimg, dlab, ev = self._stage[self._staged]
+        cur = torch.cuda.current_stream(dimg.device)
+        cur.wait_event(ev)
+        self.static_img.copy_(dimg, non_blocking=True)
+        self.static_lab.copy_(dlab, non_blocking=True)
+        self._consumed[self._staged].record(cur)
+        self.graph.replay()
+        return self.static_loss
 
     def __call__(self, img: torch.Tensor, lab: torch.Tensor) -> torch.Tensor:
         """Copy the batch (device or pinned host memory) into the static buffers, replay, return the loss tensor."""
