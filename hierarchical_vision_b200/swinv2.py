@@ -613,11 +613,13 @@ class Checkpoint:
 
 def swinv2_tiny(num_classes=10000, img_size=256, window_size=8, **kw):
     """SwinV2-T hyper-parameters (not in the reference tree; upstream Swin-V2 values)."""
-    return SwinTransformerV2(img_size=img_size, num_classes=num_classes, embed_dim=96, depths=[2, 2, 6, 2],
-                             num_heads=[3, 6, 12, 24], window_size=window_size, **kw)
+    cfg = dict(embed_dim=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24])
+    cfg.update(kw)
+    return SwinTransformerV2(img_size=img_size, num_classes=num_classes, window_size=window_size, **cfg)
 
 
 def swinv2_base(num_classes=(3, 13, 51, 273, 1103, 4884, 10000), img_size=256, window_size=16, **kw):
     """SwinV2-B with the iNat21 taxonomy tiers as multitask heads (BASELINE.json configs[3])."""
-    return SwinTransformerV2(img_size=img_size, num_classes=num_classes, embed_dim=128, depths=[2, 2, 18, 2],
-                             num_heads=[4, 8, 16, 32], window_size=window_size, **kw)
+    cfg = dict(embed_dim=128, depths=[2, 2, 18, 2], num_heads=[4, 8, 16, 32])
+    cfg.update(kw)
+    return SwinTransformerV2(img_size=img_size, num_classes=num_classes, window_size=window_size, **cfg)

@@ -444,6 +444,60 @@ def test_swinv2_tiny_full_model_vs_oracle():
         assert_close(k, params[k].grad, po[k].grad, 2e-3)
 
 
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_swinv2_base_multitask_vs_oracle(mode):
+    """BASELINE.json configs[3]: SwinV2-B geometry (embed 128, heads 4/8/16/32, window 16 -> 256-token windows with
+    shift 8 in stages 0-1, an unshifted full-resolution window in stage 2, the window clamped to 8 in stage 3) with
+    the seven taxonomy heads and the multitask cross entropy (hierarchy.py:65-94); depths cut to (2, 2, 2, 2) so that
+    the CPU oracle finishes in seconds."""
+    import dataclasses
+    from hierarchical_vision_b200 import train as T
+    spec = dataclasses.replace(O.SWINV2_B, depths=(2, 2, 2, 2))
+    p = O.init_state(spec, seed=1)
+    gen = torch.Generator().manual_seed(9)
+    for k in p:  # the reference zero-inits every block's LayerNorm affine (swinv2.py:603-608): make the blocks do work
+        if ".blocks." in k and ".norm" in k:
+            p[k] = (torch.randn(p[k].shape, generator=gen) * 0.1 + (1.0 if k.endswith("weight") else 0.0))
+    model = hv.swinv2_base(depths=list(spec.depths), drop_path_rate=0.0)
+    missing = model.load_state_dict(p, strict=False)
+    assert not missing.unexpected_keys
+    model = model.to(DEV)
+    img = torch.randn(2, 3, 256, 256, generator=gen)
+    tiers = spec.num_classes
+    labels = torch.stack([torch.randint(0, n, (2,), generator=gen) for n in tiers], dim=1)
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=mode == "bf16"):
+        logits = model(img.to(DEV))
+    assert isinstance(logits, (list, tuple)) and [lg.shape[1] for lg in logits] == list(tiers)
+    loss = T.multitask_cross_entropy(list(logits), labels.to(DEV))
+    loss.backward()
+    po = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    logits_o = O.swin_model(img, po, spec)
+    loss_o = O.multitask_cross_entropy(logits_o, labels)
+    loss_o.backward()
+    params = dict(model.named_parameters())
+    keys = ("layers.0.blocks.1.attn.qkv.weight", "layers.0.blocks.1.attn.cpb_mlp.2.weight", "layers.1.blocks.1.attn.q_bias",
+            "layers.2.blocks.0.attn.proj.weight", "layers.3.blocks.1.attn.qkv.weight", "layers.1.downsample.reduction.weight",
+            "patch_embed.proj.weight", "head.heads.0.weight", "head.heads.6.weight")
+    if mode == "fp32":
+        assert abs(loss.item() - loss_o.item()) <= 2e-3 * abs(loss_o.item())
+        for lg, lo in zip(logits, logits_o):
+            assert_close("logits", lg, lo, 2e-3)
+        for k in keys:
+            assert_close(k, params[k].grad, po[k].grad, 4e-3)
+        return
+    # bf16: this random-init network with two images is badly conditioned -- the reference arithmetic itself, run under
+    # bf16 autocast (the oracle on the CPU), misses its own fp32 logits by ~9 % and its stem gradients by ~80 %.  The
+    # band per tensor is that miss (floor 6e-2): the kernels must not be less accurate than the reference's own bf16.
+    pb = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        logits_b = O.swin_model(img, pb, spec)
+    O.multitask_cross_entropy([lg.float() for lg in logits_b], labels).backward()
+    for lg, lo, lb in zip(logits, logits_o, logits_b):
+        assert_close("logits", lg, lo, max(6e-2, rel_l2(lb.float(), lo)))
+    for k in keys:
+        assert_close(k, params[k].grad, po[k].grad, max(6e-2, rel_l2(pb[k].grad, po[k].grad)))
+
+
 # ------------------------------------------------------------------ module behaviours
 def test_drop_path_training_matches_oracle_given_same_draws():
     meta, state, a = load_case("block_ws8_shift4")
