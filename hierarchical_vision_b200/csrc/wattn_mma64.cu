@@ -245,7 +245,8 @@ __device__ __forceinline__ float inv_norm(float ss) { return rsqrt_fast(fmaxf(ss
 // Register split between the roles (only when the CTA fills the register file: 16 warps x 128)
 template <int HG> struct Regs {
   static constexpr bool kSplit = (HG == 3);
-  static constexpr int kCompute = 152, kProducer = 40;
+  static constexpr int kCompute = 152, kProducer = 40;        // forward
+  static constexpr int kComputeBwd = 152, kProducerBwd = 56;  // backward: the producers also run the pre-pass
 };
 
 // Shift-mask patterns of one thread (rows g, g+8 of a 16-row block wq; columns 8nt+2t+e)
@@ -541,17 +542,18 @@ template <int HG> struct BwdCfg {
   static constexpr int kThreads = (kWarps + kProducers) * 32;
   static constexpr int kPitch = HG * 320 + 16;  // [q | k | v | o | dO] x HG heads + pad: odd multiple of 16
   static constexpr int kLseOff = kN * kPitch;   // HG x 64 fp32 row log-sum-exp behind the token rows
-  static constexpr int kStageBytes = kN * kPitch + HG * kN * 4;
+  // per-head vectors over the window's 64 rows, written by the producer warps' pre-pass:
+  // (r, lse) float2 | -D as (hi, lo) bf16 pair | r as bf16 | c float
+  static constexpr int kVecBytes = kN * 8 + kN * 4 + kN * 2 + kN * 4 + kN * 2 /* pad to 16 B multiple */;
+  static constexpr int kVecOff = kLseOff + HG * kN * 4;
+  static constexpr int kStageBytes = kVecOff + HG * kVecBytes;
   static constexpr int kStages = 3;
   static constexpr int kDsPitch = 144;                      // bytes per dS row (64 bf16 + 16 B pad)
   static constexpr int kOffDs = kStages * kStageBytes;      // [HG][64 j][64 i] bf16
-  // per-head vectors over the window's 64 rows: (r, lse) float2 | -D as (hi, lo) bf16 pair | r as bf16
-  static constexpr int kVecBytes = kN * 8 + kN * 4 + kN * 2;
-  static constexpr int kOffVec = kOffDs + HG * kN * kDsPitch;
-  static constexpr int kOffRed = kOffVec + HG * kVecBytes;      // per-warp d(tau) partials, [HG][4][32] column sums
+  static constexpr int kOffRed = kOffDs + HG * kN * kDsPitch;   // per-warp d(tau) partials, [HG][4][32] column sums
   static constexpr int kRedBytes = kWarps * 4 + kWarps * 32 * 4;
   static constexpr int kOffBar = kOffRed + ((kRedBytes + 15) / 16) * 16;
-  static constexpr int kSmem = kOffBar + 2 * kStages * 8;
+  static constexpr int kSmem = kOffBar + 3 * kStages * 8;       // full | empty | pre
   static constexpr int kBinBytes = kWarps * 32 * 32 * 4;        // end-of-kernel d(bias) bins, reuse the stage ring
   static_assert(kBinBytes <= kStages * kStageBytes, "d(bias) bins must fit in the stage ring");
 };
@@ -571,11 +573,13 @@ wattn_mma64_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ou
   const int nrows = g.B * g.nW;
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar_full = sbase + Cfg::kOffBar, bar_empty = bar_full + 8 * Cfg::kStages;
+  const uint32_t bar_pre = bar_empty + 8 * Cfg::kStages;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(bar_full + 8 * s, Cfg::kProducers * 32);
       mbar_init(bar_empty + 8 * s, Cfg::kWarps);
+      mbar_init(bar_pre + 8 * s, Cfg::kProducers);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -585,7 +589,7 @@ wattn_mma64_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ou
     // ------------------------------------------------------------------ producer warps
     // q,k,v (from qkv), o (from out), dO (from dout) token segments and the row log-sum-exp of the window;
     // same lane-constant chunk schedule as the forward producer (two window rows per producer warp).
-    if constexpr (Regs<HG>::kSplit) reg_dealloc<Regs<HG>::kProducer>();
+    if constexpr (Regs<HG>::kSplit) reg_dealloc<Regs<HG>::kProducerBwd>();
     const int pw = warp - Cfg::kWarps;
     // One window row of one part (q, k, v, o or dO) = 8 tokens x 4*HG chunks = HG full-warp instructions, so
     // instruction (part, p) copies the same (token, chunk) pattern p for every part: HG lane constants.
@@ -599,9 +603,59 @@ wattn_mma64_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ou
       p_goff[p] = hgrp * (HG * 32) + within * 8;
     }
     const float inv_nWw = 1.0f / (float)g.nWw;
+    const int g_ = lane >> 2, t_ = lane & 3;
+    const int arow = lane_row16(lane), acolb = (lane >> 4) * 16;
+    const uint32_t own = (16 * pw + arow) * Cfg::kPitch + acolb;
+    // Pre-pass over the 16 token rows this warp loaded itself (all HG heads): 1/|k|, 1/|q|, D = dO . O on the tensor
+    // pipe, published as per-stage vectors.  It runs one stage behind the copies, so the compute warps find the
+    // vectors ready and never wait for each other before the first MMA of a window.
+    auto prepass = [&](int s) {
+      const uint32_t st = sbase + s * Cfg::kStageBytes;
+      unsigned char* stg = smem + s * Cfg::kStageBytes;
+#pragma unroll 1
+      for (int hh = 0; hh < HG; ++hh) {
+        const uint32_t qb = st + hh * 64, kb_ = st + HG * 64 + hh * 64;
+        const uint32_t ob = st + 3 * HG * 64 + hh * 64, gb = st + 4 * HG * 64 + hh * 64;
+        uint32_t ka[2][4], qa[2][4], oa[2][4], ga[2][4];
+        ldsm_x4(kb_ + own, ka[0]);
+        ldsm_x4(kb_ + own + 32, ka[1]);
+        ldsm_x4(qb + own, qa[0]);
+        ldsm_x4(qb + own + 32, qa[1]);
+        ldsm_x4(ob + own, oa[0]);
+        ldsm_x4(ob + own + 32, oa[1]);
+        ldsm_x4(gb + own, ga[0]);
+        ldsm_x4(gb + own + 32, ga[1]);
+        float c0, c1, r0, r1, d0, d1;
+        rowdot_mma(ka, ka, lane, c0, c1);
+        rowdot_mma(qa, qa, lane, r0, r1);
+        rowdot_mma(ga, oa, lane, d0, d1);
+        if (t_ == 0) {
+          const float* lse_s = reinterpret_cast<const float*>(stg + Cfg::kLseOff) + hh * kN;
+          unsigned char* vecs = stg + Cfg::kVecOff + hh * Cfg::kVecBytes;
+          float2* rl = reinterpret_cast<float2*>(vecs);
+          uint32_t* dhl = reinterpret_cast<uint32_t*>(vecs + kN * 8);
+          bf16* rb16 = reinterpret_cast<bf16*>(vecs + kN * 12);
+          float* cv = reinterpret_cast<float*>(vecs + kN * 14);
+          const int j0 = 16 * pw + g_, j1 = j0 + 8;
+          r0 = inv_norm(r0); r1 = inv_norm(r1);
+          rl[j0] = make_float2(r0, lse_s[j0]);
+          rl[j1] = make_float2(r1, lse_s[j1]);
+          rb16[j0] = __float2bfloat16_rn(r0);
+          rb16[j1] = __float2bfloat16_rn(r1);
+          cv[j0] = inv_norm(c0);
+          cv[j1] = inv_norm(c1);
+          const bf16 h0 = __float2bfloat16_rn(-d0), h1 = __float2bfloat16_rn(-d1);
+          dhl[j0] = pack_bf16x2(__bfloat162float(h0), -d0 - __bfloat162float(h0));
+          dhl[j1] = pack_bf16x2(__bfloat162float(h1), -d1 - __bfloat162float(h1));
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_pre + 8 * s);
+    };
     Cursor cur;
     cur.init(g, cta, ctas_per_group);
     Ring<Cfg::kStages> ring;
+    int prev_s = -1;
     for (int row = cta; row < nrows; row += ctas_per_group, cur.next(g), ring.next()) {
       int wh, ww;
       window_rc(g, inv_nWw, cur.win, wh, ww);
@@ -631,17 +685,30 @@ wattn_mma64_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ou
           cp_async16(d + 4 * HG * 64, dout + o1);
         }
       }
-      if (pw == 0) {
-        const float* lrow = lse + ((int64_t)row * g.heads + hgrp * HG) * kN;
-        for (int idx = lane; idx < HG * kN / 4; idx += 32) cp_async16(st + Cfg::kLseOff + idx * 16, lrow + idx * 4);
+      if (lane < 4 * HG) {  // the row log-sum-exp of this warp's own 16 rows: 64 B per head
+        const int hh = lane >> 2, ch = lane & 3;
+        const float* lrow = lse + ((int64_t)row * g.heads + hgrp * HG + hh) * kN + 16 * pw + 4 * ch;
+        cp_async16(st + Cfg::kLseOff + (hh * kN + 16 * pw + 4 * ch) * 4, lrow);
       }
       cp_async_arrive(bar_full + 8 * ring.s);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (prev_s >= 0) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");  // the previous stage's copies of this warp have landed
+        __syncwarp();
+        prepass(prev_s);
+      }
+      prev_s = ring.s;
+    }
+    if (prev_s >= 0) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+      prepass(prev_s);
     }
     return;
   }
 
   // -------------------------------------------------------------------- compute warps
-  if constexpr (Regs<HG>::kSplit) reg_alloc<Regs<HG>::kCompute>();
+  if constexpr (Regs<HG>::kSplit) reg_alloc<Regs<HG>::kComputeBwd>();
   const int hh = warp >> 2, wk = warp & 3;
   const int head = hgrp * HG + hh;
   const int g_ = lane >> 2, t_ = lane & 3;
@@ -674,12 +741,6 @@ wattn_mma64_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ou
   for (int i = 0; i < 8; ++i) qsum[i] = 0.f;
   float dtau_acc = 0.f;
 
-  unsigned char* vecs = smem + Cfg::kOffVec + hh * Cfg::kVecBytes;
-  float2* rl = reinterpret_cast<float2*>(vecs);                 // (1/|q_i|, lse2_i)
-  uint32_t* dhl = reinterpret_cast<uint32_t*>(vecs + kN * 8);   // -D_i as bf16 (hi, lo)
-  bf16* rb16 = reinterpret_cast<bf16*>(vecs + kN * 12);         // 1/|q_i| as bf16
-  const uint32_t rl_u = smem_u32(rl), dhl_u = smem_u32(dhl), rb_u = smem_u32(rb16);
-
   const int arow = lane_row16(lane), acolb = (lane >> 4) * 16;
   const int brow = lane & 7, bcolb = (lane >> 3) * 16;
   const uint32_t own = (16 * wk + arow) * Cfg::kPitch + acolb;
@@ -700,46 +761,26 @@ wattn_mma64_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ ou
     // own token rows: slot j0 = (ih 2*wk, iw g_), j1 = (ih 2*wk+1, iw g_)
     const int tok0 = (int)tile_token(g, cur.b, row0, col0, 2 * wk, g_);  // < 2^31 (checked on the host)
     const int tok1 = (int)tile_token(g, cur.b, row0, col0, 2 * wk + 1, g_);
-    if (wk == 0) mbar_wait(bar_full + 8 * ring.s, ring.ph);  // one waiter per head; the rest sleep in the barrier
+    // the producers' pre-pass barrier implies the stage is full (each producer arrives after its own copies landed);
+    // one waiter per head, the rest sleep in the named barrier, which also fences the previous tile's dS buffer
+    if (wk == 0) mbar_wait(bar_pre + 8 * ring.s, ring.ph);
     named_bar_sync(1 + hh, 128);
     const uint32_t st = sbase + ring.s * Cfg::kStageBytes;
     const uint32_t qb = st + hh * 64, kb_ = st + HG * 64 + hh * 64, vb_ = st + 2 * HG * 64 + hh * 64;
     const uint32_t ob = st + 3 * HG * 64 + hh * 64, gb = st + 4 * HG * 64 + hh * 64;
-    const float* lse_s = reinterpret_cast<const float*>(smem + ring.s * Cfg::kStageBytes + Cfg::kLseOff) + hh * kN;
-    // output staging: the O segment of this warp's own 16 token rows is dead after the pre-pass below
+    // per-stage vectors published by the producers: (1/|q_i|, lse2_i) | -D_i as bf16 (hi, lo) | 1/|q_i| bf16 | 1/|k_j|
+    const uint32_t vec_u = st + Cfg::kVecOff + hh * Cfg::kVecBytes;
+    const uint32_t rl_u = vec_u, dhl_u = vec_u + kN * 8, rb_u = vec_u + kN * 12;
+    const float* vecf = reinterpret_cast<const float*>(smem + ring.s * Cfg::kStageBytes + Cfg::kVecOff + hh * Cfg::kVecBytes);
+    // output staging: the O segment of this warp's own 16 token rows is dead once the producers' pre-pass is done
     const uint32_t ost = ob + (16 * wk) * Cfg::kPitch;
 
-    // --- pre-pass over this warp's 16 token rows: 1/|k|, 1/|q|, D = dO . O (tensor pipe, exact)
     uint32_t ka[2][4], qf[2][4];
-    float c0, c1, r0, r1;
-    {
-      uint32_t qa[2][4], oa[2][4], ga[2][4];
-      ldsm_x4(kb_ + own, ka[0]);
-      ldsm_x4(kb_ + own + 32, ka[1]);
-      ldsm_x4(qb + own, qa[0]);
-      ldsm_x4(qb + own + 32, qa[1]);
-      ldsm_x4(ob + own, oa[0]);
-      ldsm_x4(ob + own + 32, oa[1]);
-      ldsm_x4(gb + own, ga[0]);
-      ldsm_x4(gb + own + 32, ga[1]);
-      float d0, d1;
-      rowdot_mma(ka, ka, lane, c0, c1);
-      rowdot_mma(qa, qa, lane, r0, r1);
-      rowdot_mma(ga, oa, lane, d0, d1);
-      c0 = inv_norm(c0); c1 = inv_norm(c1);
-      r0 = inv_norm(r0); r1 = inv_norm(r1);
-      if (t_ == 0) {
-        rl[j0] = make_float2(r0, lse_s[j0]);
-        rl[j1] = make_float2(r1, lse_s[j1]);
-        rb16[j0] = __float2bfloat16_rn(r0);
-        rb16[j1] = __float2bfloat16_rn(r1);
-        const bf16 h0 = __float2bfloat16_rn(-d0), h1 = __float2bfloat16_rn(-d1);
-        dhl[j0] = pack_bf16x2(__bfloat162float(h0), -d0 - __bfloat162float(h0));
-        dhl[j1] = pack_bf16x2(__bfloat162float(h1), -d1 - __bfloat162float(h1));
-      }
-    }
+    ldsm_x4(kb_ + own, ka[0]);
+    ldsm_x4(kb_ + own + 32, ka[1]);
     ldsm_x4(qb + brow * Cfg::kPitch + bcolb, qf[0]);
-    named_bar_sync(1 + hh, 128);  // vectors of all 64 rows visible; previous tile's dS fully consumed
+    const float c0 = vecf[kN * 14 / 4 + j0], c1 = vecf[kN * 14 / 4 + j1];
+    const float r0 = vecf[2 * j0], r1 = vecf[2 * j1];
 
     // --- S^T = K Q^T for own 16 keys (rows) x 64 queries (columns), then P^T
     float acc[8][4];
