@@ -42,6 +42,23 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
     return t.to(torch.float32).contiguous()
 
 
+# The residual shortcut's gradient arrives in the node that also produces the branch's dx (see _QkvWindowAttention /
+# _LinearShortcut): the dx GEMM then accumulates straight into that incoming buffer (beta = 1, in place) instead of
+# copying it first.  The buffer is the LayerNorm backward's pass-through of its own incoming gradient, which nothing
+# reads again.  Set to False to accumulate out of place.
+INPLACE_SHORTCUT_GRAD = True
+
+
+def _dx_with_shortcut(dx_shortcut, d2, weight, shape):
+    C = shape[-1]
+    if dx_shortcut is None:
+        return torch.matmul(d2, weight).view(shape)
+    if (INPLACE_SHORTCUT_GRAD and dx_shortcut.dtype == d2.dtype and dx_shortcut.is_contiguous()
+            and not torch.is_grad_enabled() and not dx_shortcut.requires_grad):
+        return dx_shortcut.view(-1, C).addmm_(d2, weight).view(shape)
+    return torch.addmm(dx_shortcut.reshape(-1, C).to(d2.dtype), d2, weight).view(shape)
+
+
 # Optional per-launch instrumentation used by bench.py: when set to a list, every attention
 # kernel launch appends (tag, start_event, end_event, windows).
 PROFILE_EVENTS = None
@@ -197,10 +214,7 @@ class _QkvWindowAttention(torch.autograd.Function):
         d2 = dqkv.view(-1, 3 * C)
         dx = None
         if ctx.needs_input_grad[0]:
-            if dx_shortcut is not None:
-                dx = torch.addmm(dx_shortcut.reshape(-1, C).to(d2.dtype), d2, weight).view(x.shape)
-            else:
-                dx = torch.matmul(d2, weight).view(x.shape)
+            dx = _dx_with_shortcut(dx_shortcut, d2, weight, x.shape)
         elif dx_shortcut is not None:
             dx = dx_shortcut
         dw = torch.matmul(d2.t(), x.view(-1, C)) if ctx.needs_input_grad[1] else None
@@ -233,10 +247,7 @@ class _LinearShortcut(torch.autograd.Function):
         d2 = dy.reshape(-1, dy.shape[-1])
         dx = None
         if ctx.needs_input_grad[0]:
-            if dx_shortcut is not None:
-                dx = torch.addmm(dx_shortcut.reshape(-1, x.shape[-1]).to(d2.dtype), d2, weight).view(x.shape)
-            else:
-                dx = torch.matmul(d2, weight).view(x.shape)
+            dx = _dx_with_shortcut(dx_shortcut, d2, weight, x.shape)
         elif dx_shortcut is not None:
             dx = dx_shortcut
         dw = torch.matmul(d2.t(), x.reshape(-1, x.shape[-1])) if ctx.needs_input_grad[1] else None
