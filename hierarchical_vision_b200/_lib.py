@@ -39,6 +39,8 @@ SIGNATURES = {
     "hv_bias_gelu_bwd": (_I, [_P, _P, _P, _P, _P, _P, _S, _L, _I, _I, _P]),
     "hv_patch_merge_gather_fwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "hv_patch_merge_gather_bwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "hv_cpb_bias_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "hv_cpb_bias_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "hv_patch_rows": (_I, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
 }
 

@@ -38,6 +38,10 @@ int bias_gelu_bwd(const void* dout, const void* h, const float* bias, void* dh, 
                   size_t workspace_bytes, int64_t rows, int cols, int dtype, cudaStream_t st);
 int patch_merge_gather_fwd(const void* x, void* out, int B, int H, int W, int C, int dtype, cudaStream_t st);
 int patch_merge_gather_bwd(const void* dout, void* dx, int B, int H, int W, int C, int dtype, cudaStream_t st);
+int cpb_bias_fwd(const float* coords, const float* w1, const float* b1, const float* w2, float* table, int M, int hid,
+                 int heads, cudaStream_t st);
+int cpb_bias_bwd(const float* coords, const float* w1, const float* b1, const float* w2, const float* dtable, float* dw1,
+                 float* db1, float* dw2, float* workspace, int M, int hid, int heads, cudaStream_t st);
 int patch_rows(const void* img, int img_dtype, const float* scale, const float* shift, void* out, int out_dtype, int B,
                int Cin, int H, int W, int P, cudaStream_t st);
 
@@ -285,6 +289,23 @@ int hv_patch_rows(const void* img, int img_dtype, const float* scale, const floa
   int rc = check_device_arch();
   if (rc) return rc;
   return patch_rows(img, img_dtype, scale, shift, out, out_dtype, B, Cin, H, W, P, static_cast<cudaStream_t>(stream));
+}
+
+int hv_cpb_bias_fwd(const float* coords, const float* w1, const float* b1, const float* w2, float* table, int M, int hidden,
+                    int heads, void* stream) {
+  if (!coords || !w1 || !b1 || !w2 || !table) HV_FAIL(HV_ERR_NULL, "hv_cpb_bias_fwd: NULL argument");
+  int rc = check_device_arch();
+  if (rc) return rc;
+  return cpb_bias_fwd(coords, w1, b1, w2, table, M, hidden, heads, static_cast<cudaStream_t>(stream));
+}
+
+int hv_cpb_bias_bwd(const float* coords, const float* w1, const float* b1, const float* w2, const float* dtable, float* dw1,
+                    float* db1, float* dw2, float* workspace, int M, int hidden, int heads, void* stream) {
+  if (!coords || !w1 || !b1 || !w2 || !dtable || !dw1 || !db1 || !dw2 || !workspace)
+    HV_FAIL(HV_ERR_NULL, "hv_cpb_bias_bwd: NULL argument");
+  int rc = check_device_arch();
+  if (rc) return rc;
+  return cpb_bias_bwd(coords, w1, b1, w2, dtable, dw1, db1, dw2, workspace, M, hidden, heads, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -433,3 +433,48 @@ def patch_rows(img: torch.Tensor, scale: Optional[torch.Tensor], shift: Optional
     global LAUNCH_COUNT
     LAUNCH_COUNT += 1
     return out
+
+
+class _CpbBias(torch.autograd.Function):
+    """table = 16 * sigmoid(Linear(hidden, heads, no bias)(relu(Linear(2, hidden)(coords)))), fp32."""
+
+    @staticmethod
+    def forward(ctx, coords, w1, b1, w2):
+        _need_cuda(coords, "cpb_bias")
+        lib = _lib.load()
+        coords, w1, b1, w2 = _f32c(coords.reshape(-1, 2)), _f32c(w1), _f32c(b1), _f32c(w2)
+        M, hid, heads = coords.shape[0], w1.shape[0], w2.shape[0]
+        table = torch.empty((M, heads), dtype=torch.float32, device=coords.device)
+        with torch.cuda.device(coords.device):
+            rc = lib.hv_cpb_bias_fwd(_ptr(coords), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(table), M, hid, heads,
+                                     _stream(coords.device))
+        check(rc, "hv_cpb_bias_fwd")
+        global LAUNCH_COUNT
+        LAUNCH_COUNT += 1
+        ctx.save_for_backward(coords, w1, b1, w2)
+        return table
+
+    @staticmethod
+    def backward(ctx, dtable):
+        coords, w1, b1, w2 = ctx.saved_tensors
+        lib = _lib.load()
+        M, hid, heads = coords.shape[0], w1.shape[0], w2.shape[0]
+        dtable = _f32c(dtable)
+        dw1, db1, dw2 = torch.empty_like(w1), torch.empty_like(b1), torch.empty_like(w2)
+        workspace = torch.empty((M, heads), dtype=torch.float32, device=coords.device)
+        with torch.cuda.device(coords.device):
+            rc = lib.hv_cpb_bias_bwd(_ptr(coords), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(dtable), _ptr(dw1), _ptr(db1),
+                                     _ptr(dw2), _ptr(workspace), M, hid, heads, _stream(coords.device))
+        check(rc, "hv_cpb_bias_bwd")
+        global LAUNCH_COUNT
+        LAUNCH_COUNT += 2
+        return None, dw1, db1, dw2
+
+
+def cpb_bias_supported(w1: torch.Tensor, w2: torch.Tensor) -> bool:
+    return w1.is_cuda and w1.shape[0] <= 512 and w1.shape[0] % 32 == 0 and w2.shape[0] <= 32
+
+
+def cpb_bias(coords: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor) -> torch.Tensor:
+    """((2ws-1)^2, heads) continuous position bias table, 16 * sigmoid(cpb_mlp(coords)) (swinv2.py:233-246)."""
+    return _CpbBias.apply(coords, w1, b1, w2)

@@ -214,6 +214,10 @@ class WindowAttention(nn.Module):
         of swinv2.py:236-246, which the kernel performs from the closed-form index."""
         # 225..961 rows x (2 -> 512 -> heads): microscopic, so it is kept out of autocast (fp32 weights
         # stay fp32); the reference lets autocast run it in bf16, which costs it ~5% on these gradients.
+        l1, l2 = self.cpb_mlp[0], self.cpb_mlp[2]
+        if (self.relative_coords_table.is_cuda and l1.weight.dtype == torch.float32
+                and hvf.cpb_bias_supported(l1.weight, l2.weight)):
+            return hvf.cpb_bias(self.relative_coords_table, l1.weight, l1.bias, l2.weight)  # one kernel each way
         with torch.autocast(device_type=self.relative_coords_table.device.type, enabled=False):
             table = self.cpb_mlp(self.relative_coords_table.to(self.cpb_mlp[0].weight.dtype))
         return 16 * torch.sigmoid(table.view(-1, self.num_heads).float())

@@ -161,6 +161,17 @@ HV_API int hv_bias_gelu_bwd(const void* dout, const void* h, const float* bias, 
 HV_API int hv_patch_merge_gather_fwd(const void* x, void* out, int B, int H, int W, int C, int dtype, void* stream);
 HV_API int hv_patch_merge_gather_bwd(const void* dout, void* dx, int B, int H, int W, int C, int dtype, void* stream);
 
+/* ---- continuous position bias table -----------------------------------------------------
+ * table[r, h] = 16 * sigmoid(cpb_mlp(relative_coords_table)[r, h]) with cpb_mlp = Linear(2, hidden) + ReLU +
+ * Linear(hidden, heads, no bias) (swinv2.py:141-145, 233-246); the gather through relative_position_index is done by
+ * the attention kernels.  Replaces ~5 (forward) / ~8 (backward) tiny library kernels per block and step.
+ *   coords device float32 (M, 2)   w1 (hidden, 2)   b1 (hidden)   w2 (heads, hidden)   table, dtable (M, heads)
+ *   hidden <= 512 and a multiple of 32, heads <= 32;  workspace: M * heads floats (backward) */
+HV_API int hv_cpb_bias_fwd(const float* coords, const float* w1, const float* b1, const float* w2, float* table, int M,
+                    int hidden, int heads, void* stream);
+HV_API int hv_cpb_bias_bwd(const float* coords, const float* w1, const float* b1, const float* w2, const float* dtable,
+                    float* dw1, float* db1, float* dw2, float* workspace, int M, int hidden, int heads, void* stream);
+
 /* ---- PatchEmbed input gather -------------------------------------------------------------
  * Left operand of PatchEmbed's Conv2d(in_chans, embed_dim, kernel = stride = patch) seen as a per-patch GEMM
  * (swinv2.py:648-657): out[(b, ph, pw), (c, dy, dx)] = img[b, c, ph*P + dy, pw*P + dx] * scale[c] + shift[c].

@@ -672,3 +672,26 @@ def test_patch_embed_matches_conv_path(mode):
         assert_close("y", y, y64, tol)
         for k, p in pe.named_parameters():
             assert_close(k, p.grad, w64[k].grad, 2 * tol)
+
+
+@pytest.mark.parametrize("ws,heads", [(8, 3), (8, 24), (16, 4), (16, 32), (7, 6)])
+def test_cpb_bias_table_and_gradients(ws, heads):
+    """hv_cpb_bias_{fwd,bwd} == 16 * sigmoid(cpb_mlp(relative_coords_table)) (swinv2.py:141-145, 233-246) and its autograd."""
+    torch.manual_seed(ws * 100 + heads)
+    wa = hv.WindowAttention(32 * heads, (ws, ws), heads).to(DEV)
+    with torch.no_grad():
+        wa.cpb_mlp[0].weight.normal_(0, 0.5)
+        wa.cpb_mlp[0].bias.normal_(0, 0.5)
+        wa.cpb_mlp[2].weight.normal_(0, 0.2)
+    table = wa._bias_table()
+    g = torch.randn_like(table)
+    table.backward(g)
+    p64 = {k: v.detach().double().cpu().requires_grad_(True) for k, v in wa.cpb_mlp.named_parameters()}
+    c64 = wa.relative_coords_table.double().cpu().reshape(-1, 2)
+    hdn = torch.relu(c64 @ p64["0.weight"].t() + p64["0.bias"])
+    want = 16 * torch.sigmoid(hdn @ p64["2.weight"].t())
+    want.backward(g.double().cpu())
+    assert table.shape == ((2 * ws - 1) ** 2, heads)
+    assert_close("table", table, want, 1e-5)
+    for k, p in wa.cpb_mlp.named_parameters():
+        assert_close(k, p.grad, p64[k].grad, 1e-4)
