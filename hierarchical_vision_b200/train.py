@@ -126,7 +126,9 @@ def build_optimizer(model: nn.Module, lr: float = 0.1, momentum: float = 0.875, 
         short = name.split("module.")[-1]
         (no_decay if (p.dim() == 1 or name.endswith(".bias") or short in skip) else decay).append(p)
     groups = [{"params": decay}, {"params": no_decay, "weight_decay": 0.0}]
-    return torch.optim.SGD(groups, lr=lr, momentum=momentum, weight_decay=weight_decay)
+    # one fused multi-tensor kernel per group on CUDA instead of a foreach chain of ~25 launches
+    fused = all(p.is_cuda for p in decay + no_decay) and len(decay) + len(no_decay) > 0
+    return torch.optim.SGD(groups, lr=lr, momentum=momentum, weight_decay=weight_decay, fused=fused)
 
 
 def wrap_ddp(model: nn.Module, env: DistEnv, device: torch.device) -> nn.Module:
