@@ -196,6 +196,13 @@ __device__ __forceinline__ void rownorm2_mma(const uint32_t (&x)[2][4], int lane
   s1 = __shfl_sync(0xffffffffu, v1, src);
 }
 
+#ifdef HV_TC_TRACE
+__device__ long long* g_trace = nullptr;  // [pairs][16 events] clock64 stamps of CTA 0
+#define TRACE(k, ev) do { if (blockIdx.x == 0 && lane == 0 && g_trace && (k) < 64) g_trace[(k) * 16 + (ev)] = clock64(); } while (0)
+#else
+#define TRACE(k, ev) do { } while (0)
+#endif
+
 struct TcParams {
   Geom g;
   int n_same;        // head groups whose two units are heads (2g, 2g+1) of the same window
@@ -389,6 +396,7 @@ wattn_tc64_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restri
         const int s = k % kStages;
         const uint32_t ph = (k / kStages) & 1;
         mbar_wait(bar_empty(s), ph ^ 1);
+        if (warp == 0) TRACE(k, 0);  // producer: stage free
         const int which = lane & 1, part = lane >> 1;
         bool valid;
         const int r = work.row(k, which, nrows, valid);
@@ -439,6 +447,7 @@ wattn_tc64_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restri
           for (int kk = 0; kk < 2; ++kk)
             umma_ss(tmem + kSlotCols * t + kColS, sw64_desc(st + 32 * kk), sw64_desc(st + 2 * kTile + 32 * kk), id_s, kk > 0);
           umma_commit(bar_s(t));
+          TRACE(k, 3);  // S issued
         }
         __syncwarp();
       };
@@ -447,6 +456,7 @@ wattn_tc64_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restri
       for (int k = 0; k < npairs; ++k) {
         const int s = k % kStages, t = k & 1;
         mbar_wait_fast(bar_p(t), (k >> 1) & 1);
+        TRACE(k, 7);  // MMA warp saw P
         mbar_wait_fast(bar_ofree(t), ((k >> 1) & 1) ^ 1);  // epilogue of pair k-2 has drained O / l of this slot
         tc_fence_after();
         if (lane == 0) {
@@ -461,6 +471,7 @@ wattn_tc64_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restri
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) umma_ts(tb + kColL, tb + kColP + 8 * ks, ones_desc + (uint64_t)(64 * ks), id_o, ks > 0);
           umma_commit(bar_o(t));
+          TRACE(k, 8);  // PV issued
           umma_commit(bar_empty(s));
         }
         __syncwarp();
@@ -479,6 +490,7 @@ wattn_tc64_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restri
     for (int k = 0; k < npairs; ++k) {
       const int s = k % kStages;
       mbar_wait(bar_full(s), (k / kStages) & 1);
+      if (warp == 4) TRACE(k, 1);  // norm warp saw full
       const uint32_t tile = sb + kOffStage + s * kStage + (2 * part + u) * kTile;
       float* vec = reinterpret_cast<float*>(smem + kOffVec) + ((s * 2 + u) * 2 + part) * kN;  // r (q tile) or c (k tile)
       uint32_t x[4][2][4];
@@ -500,6 +512,7 @@ wattn_tc64_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restri
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(bar_norm(s));
+        if (warp == 4) TRACE(k, 2);  // norm done
         mbar_arrive(bar_empty(s));
       }
     }
@@ -541,11 +554,13 @@ wattn_tc64_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restri
       const int s = k % kStages;
       const uint32_t tph = (k >> 1) & 1;
       mbar_wait_fast(bar_norm(s), (k / kStages) & 1);
+      if (quad == 0 && half == 0) TRACE(k, 4);  // softmax saw norm
       const int rflags = geo[(k & 7) * 2 + u].rflags;
       const float* bias_row = (rflags & 4) ? bias_p : bias_n;
       const float* vec = reinterpret_cast<const float*>(smem + kOffVec) + (s * 2 + u) * 2 * kN;
       const float ri = vec[i];
       mbar_wait_fast(bar_s(grp), tph);
+      if (quad == 0 && half == 0) TRACE(k, 5);  // softmax saw S
       tc_fence_after();
       uint32_t acc[32];
       HV_TMEM_LD32(tl + kColS + 64 * u + 32 * half, acc);
@@ -587,6 +602,7 @@ wattn_tc64_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restri
       if (half == 0) mxv[(grp * 2 + tph) * 128 + row] = off + mx;
       tmem_wait_st();
       tc_fence_before();
+      if (quad == 0 && half == 0) TRACE(k, 6);  // softmax P arrive
       mbar_arrive(bar_p(grp));
     }
   } else {
@@ -600,6 +616,7 @@ wattn_tc64_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restri
       const int t = k & 1;
       const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16) + kSlotCols * t;
       mbar_wait_fast(bar_o(t), (k >> 1) & 1);
+      if (quad == 0) TRACE(k, 9);  // epilogue saw O
       tc_fence_after();
       uint32_t o[32];
       HV_TMEM_LD32(tl + kColO + 32 * u, o);
@@ -609,6 +626,7 @@ wattn_tc64_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restri
       const UnitGeo ug = geo[(k & 7) * 2 + u];
       tc_fence_before();
       mbar_arrive(bar_ofree(t));
+      if (quad == 0) TRACE(k, 10);  // epilogue freed slot
       if (ug.rflags & 1) {
         const float inv = rcp_fast(l);
         const int sl = (ug.rflags & 4) ? sp : sn;
@@ -722,8 +740,28 @@ int wattn_tc64_fwd(const Geom& g, const void* qkv, const float* bias_table, cons
     HV_CUDA_OK(cudaFuncSetAttribute(wattn_tc64_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     attr_dev = dev;
   }
+#ifdef HV_TC_TRACE
+  static long long* dtrace = nullptr;
+  if (!dtrace) {
+    cudaMalloc(&dtrace, 64 * 16 * sizeof(long long));
+    cudaMemcpyToSymbol(g_trace, &dtrace, sizeof(dtrace));
+  }
+  cudaMemsetAsync(dtrace, 0, 64 * 16 * sizeof(long long), st);
+#endif
   wattn_tc64_fwd_kernel<<<grid, kThreads, kSmem, st>>>(maps, bias_table, tau, (bf16*)out, lse, p);
   HV_LAUNCH_OK("wattn_tc64_fwd_kernel");
+#ifdef HV_TC_TRACE
+  if (getenv("HV_TC_TRACE_DUMP")) {
+    static long long h[64 * 16];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, dtrace, sizeof(h), cudaMemcpyDeviceToHost);
+    FILE* f = fopen(getenv("HV_TC_TRACE_DUMP"), "w");
+    if (f) {
+      for (int k = 0; k < 64; ++k) { for (int e = 0; e < 11; ++e) fprintf(f, "%lld ", h[k * 16 + e] ? h[k * 16 + e] - h[0] : -1LL); fprintf(f, "\n"); }
+      fclose(f);
+    }
+  }
+#endif
   return HV_OK;
 }
 
