@@ -48,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if (not force and os.path.exists(obj)
                 and os.path.getmtime(obj) >= max(os.path.getmtime(spath), headers_newest)):
             return obj, ""
-        cmd = [nvcc, *ARCH, *CFLAGS, "-c", spath, "-o", obj]
+        cmd = [nvcc, *ARCH, *CFLAGS, *os.environ.get("HV_NVCC_FLAGS", "").split(), "-c", spath, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")

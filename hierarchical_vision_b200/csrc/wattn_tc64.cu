@@ -27,7 +27,10 @@ constexpr int kWs = 8;
 constexpr int kTab = 225;
 constexpr int kTile = kN * 64;        // one (window, head) q / k / v tile: 64 rows x 64 B
 constexpr int kStage = 6 * kTile;     // q_a q_b k_a k_b v_a v_b
-constexpr int kStages = 4;
+#ifndef HV_TC_STAGES
+#define HV_TC_STAGES 5
+#endif
+constexpr int kStages = HV_TC_STAGES;
 constexpr int kBiasPitch = 68;        // floats per expanded-bias row (64 + pad: conflict-free 16-byte row reads)
 constexpr int kThreads = 896;  // 28 warps: 0 TMA, 1 MMA, (2-3 idle), 4-7 norms, 8-23 softmax, 24-27 epilogue
 constexpr float kNoMaxRange = 64.0f;
@@ -36,14 +39,18 @@ constexpr float kNoMaxRange = 64.0f;
 constexpr int kOffStage = 0;
 constexpr int kOffOnes = kOffStage + kStages * kStage;                 // 64 x 64 B of bf16 ones
 constexpr int kOffBias = kOffOnes + kTile;                             // [2 orders][2 units][64][kBiasPitch] float
-constexpr int kOffVec = kOffBias + 4 * kN * kBiasPitch * 4;            // [kStages][2 units][2 (r, c)][64] float
+#ifdef HV_TC_ONE_ORDER  // experiment: shift 0 only, no permuted bias copy
+constexpr int kOffVec = kOffBias + 2 * kN * kBiasPitch * 4;
+#else
+constexpr int kOffVec = kOffBias + 4 * kN * kBiasPitch * 4;
+#endif            // [kStages][2 units][2 (r, c)][64] float
 constexpr int kOffMx = kOffVec + kStages * 2 * 2 * kN * 4;             // [2 slots][2 phases][128] float
 constexpr int kOffHmx = kOffMx + 4 * 128 * 4;                          // [2 slots][2 phases][2 halves][128] float
 constexpr int kOffTab = kOffHmx + 8 * 128 * 4;                         // [2 units][256] float
 constexpr int kOffGeo = kOffTab + 2 * 256 * 4;                         // [8][2] UnitGeo
 constexpr int kOffSlotMap = kOffGeo + 8 * 2 * 16;                      // [2 orders][64] bytes
 constexpr int kOffBar = kOffSlotMap + 128;
-constexpr int kNumBars = 3 * kStages + 4 * 2;
+constexpr int kNumBars = 3 * kStages + 5 * 2;
 constexpr int kOffTmem = kOffBar + kNumBars * 8;
 constexpr int kSmem = kOffTmem + 16;
 
@@ -176,7 +183,7 @@ __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
                : "r"(addr));
 }
 __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
+  asm(
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
@@ -199,8 +206,10 @@ __device__ __forceinline__ void rownorm2_mma(const uint32_t (&x)[2][4], int lane
 #ifdef HV_TC_TRACE
 __device__ long long* g_trace = nullptr;  // [pairs][16 events] clock64 stamps of CTA 0
 #define TRACE(k, ev) do { if (blockIdx.x == 0 && lane == 0 && g_trace && (k) < 64) g_trace[(k) * 16 + (ev)] = clock64(); } while (0)
+#define KO(bit) (p.ko & (bit))
 #else
 #define TRACE(k, ev) do { } while (0)
+#define KO(bit) false
 #endif
 
 struct TcParams {
@@ -209,6 +218,7 @@ struct TcParams {
   int has_cross;     // 1: a last group pairs the odd head of two consecutive windows
   int ctas_same;     // CTAs per same-window group
   int ctas_cross;    // CTAs of the cross-window group
+  int ko;            // HV_TC_TRACE builds only: knock-out bits for bottleneck experiments (results are wrong)
 };
 // box shapes (w, h): 0 full (8,8) | 1 (8,8-s) 2 (8,s) row wrap | 3 (8-s,8) 4 (s,8) column wrap | 5..8 corner
 struct TcMaps { CUtensorMap m[9]; };
@@ -267,6 +277,15 @@ __device__ __forceinline__ void tile_row_slot(int t, int shift, bool perm, int& 
   else { const int t2 = t - kWs * wa; ih = t2 / shift; iw = wa + t2 - ih * shift; }
 }
 
+// one converged-warp leader: the compiler emits single-thread tcgen05 / TMA instructions without an election loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 template <int N> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
@@ -298,6 +317,7 @@ wattn_tc64_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restri
   auto bar_p = [&](int t) { return bar0 + 8 * (3 * kStages + 2 + t); };
   auto bar_o = [&](int t) { return bar0 + 8 * (3 * kStages + 4 + t); };
   auto bar_ofree = [&](int t) { return bar0 + 8 * (3 * kStages + 6 + t); };
+  auto bar_sfree = [&](int t) { return bar0 + 8 * (3 * kStages + 8 + t); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmem);
   const int nrows = g.B * g.nW;
 
@@ -318,6 +338,7 @@ wattn_tc64_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restri
       mbar_init(bar_p(t), 256);
       mbar_init(bar_o(t), 1);
       mbar_init(bar_ofree(t), 128);
+      mbar_init(bar_sfree(t), 8);  // one arrival per softmax warp of the group: its S columns are in registers
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -408,9 +429,9 @@ wattn_tc64_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restri
           geo[(k & 7) * 2 + which] = ug;
         }
         __syncwarp();
-        if (lane == 0) mbar_expect_tx(bar_full(s), kStage);
+        if (lane == 0) mbar_expect_tx(bar_full(s), KO(8) ? 0 : kStage);
         __syncwarp();
-        if (lane < 6) {
+        if (lane < 6 && !KO(8)) {
           const int head = which == 0 ? work.head_a : work.head_b;
           const int c0 = part * g.C + head * 32;
           const uint32_t dst = sb + kOffStage + s * kStage + lane * kTile;
@@ -434,39 +455,46 @@ wattn_tc64_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restri
         }
       }
     } else if (warp == 1) {
-      // ---------------------------------------------------------------- MMA issuer
-      const uint32_t id_s = idesc_bf16(128, 128, 0, 0), id_o = idesc_bf16(128, 32, 0, 1);
-      const uint64_t ones_desc = sw64_desc(sb + kOffOnes);
-      auto issue_s = [&](int k) {
+      // ---------------------------------------------------------------- S issuer: S(k) = [Q_a; Q_b] [K_a; K_b]^T
+      // S of pair k goes in as soon as the softmax group has pulled S of pair k-2 out of TMEM (P has its own columns),
+      // so the group finds its next logits waiting when it is done with the exponentials of the previous pair.
+      // A warp of its own: every wait / commit costs the issuing warp ~100 cycles, PV and S issue would add up.
+      const uint32_t id_s = idesc_bf16(128, 128, 0, 0);
+      const uint64_t d_q = sw64_desc(sb + kOffStage), d_k = sw64_desc(sb + kOffStage + 2 * kTile);
+      for (int k = 0; k < npairs; ++k) {
         const int s = k % kStages, t = k & 1;
+        if (k >= 2) mbar_wait_fast(bar_sfree(t), ((k - 2) >> 1) & 1);
         mbar_wait_fast(bar_full(s), (k / kStages) & 1);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t st = sb + kOffStage + s * kStage;
+        if (elect_one()) {
+          const uint64_t so = (uint64_t)((s * kStage) >> 4);
 #pragma unroll
           for (int kk = 0; kk < 2; ++kk)
-            umma_ss(tmem + kSlotCols * t + kColS, sw64_desc(st + 32 * kk), sw64_desc(st + 2 * kTile + 32 * kk), id_s, kk > 0);
+            umma_ss(tmem + kSlotCols * t + kColS, d_q + so + 2 * kk, d_k + so + 2 * kk, id_s, kk > 0);
           umma_commit(bar_s(t));
           TRACE(k, 3);  // S issued
         }
         __syncwarp();
-      };
-      if (npairs > 0) issue_s(0);
-      if (npairs > 1) issue_s(1);
+      }
+    } else if (warp == 2) {
+      // ---------------------------------------------------------------- PV issuer: O = P V, l = P 1 (A from TMEM)
+      const uint32_t id_o = idesc_bf16(128, 32, 0, 1);
+      const uint64_t ones_desc = sw64_desc(sb + kOffOnes);
+      const uint64_t d_v = sw64_desc(sb + kOffStage + 4 * kTile);
       for (int k = 0; k < npairs; ++k) {
         const int s = k % kStages, t = k & 1;
         mbar_wait_fast(bar_p(t), (k >> 1) & 1);
         TRACE(k, 7);  // MMA warp saw P
         mbar_wait_fast(bar_ofree(t), ((k >> 1) & 1) ^ 1);  // epilogue of pair k-2 has drained O / l of this slot
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t st = sb + kOffStage + s * kStage;
+        if (elect_one()) {
+          const uint64_t so = (uint64_t)((s * kStage) >> 4);
           const uint32_t tb = tmem + kSlotCols * t;
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
-              umma_ts(tb + kColO + 32 * half, tb + kColP + 8 * ks, sw64_desc(st + (4 + half) * kTile + 1024 * ks), id_o, ks > 0);
+              umma_ts(tb + kColO + 32 * half, tb + kColP + 8 * ks, d_v + so + (uint64_t)(256 * half + 64 * ks), id_o, ks > 0);
           }
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) umma_ts(tb + kColL, tb + kColP + 8 * ks, ones_desc + (uint64_t)(64 * ks), id_o, ks > 0);
@@ -475,9 +503,6 @@ wattn_tc64_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restri
           umma_commit(bar_empty(s));
         }
         __syncwarp();
-        // S of the pair after next goes right behind (the tensor pipe runs in issue order; its S columns were consumed
-        // by the softmax group before it signalled P of pair k)
-        if (k + 2 < npairs) issue_s(k + 2);
       }
     }
   } else if (warp < 8) {
@@ -489,24 +514,49 @@ wattn_tc64_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restri
     const int arow = (lane & 7) + 8 * ((lane >> 3) & 1), achunk = lane >> 4;
     for (int k = 0; k < npairs; ++k) {
       const int s = k % kStages;
-      mbar_wait(bar_full(s), (k / kStages) & 1);
+      mbar_wait_fast(bar_full(s), (k / kStages) & 1);
       if (warp == 4) TRACE(k, 1);  // norm warp saw full
       const uint32_t tile = sb + kOffStage + s * kStage + (2 * part + u) * kTile;
       float* vec = reinterpret_cast<float*>(smem + kOffVec) + ((s * 2 + u) * 2 + part) * kN;  // r (q tile) or c (k tile)
-      uint32_t x[4][2][4];
+      // two 16-row blocks at a time with every step batched (loads, products, shuffles, rsqrt) so that the four
+      // dependent chains overlap instead of running back to back
 #pragma unroll
-      for (int blk = 0; blk < 4; ++blk) {
-        const int row = 16 * blk + arow;
-        ldsm_x4(tile + row * 64 + (((achunk) ^ ((row >> 1) & 3)) << 4), x[blk][0]);
-        ldsm_x4(tile + row * 64 + (((2 + achunk) ^ ((row >> 1) & 3)) << 4), x[blk][1]);
-      }
+      for (int bp = 0; bp < 2; ++bp) {
+        if (KO(1)) { vec[lane + 32 * bp] = mult; continue; }
+        uint32_t x[2][2][4];
 #pragma unroll
-      for (int blk = 0; blk < 4; ++blk) {
-        float s0, s1;
-        rownorm2_mma(x[blk], lane, s0, s1);
+        for (int b = 0; b < 2; ++b) {
+          const int row = 16 * (2 * bp + b) + arow;
+          ldsm_x4(tile + row * 64 + (((achunk) ^ ((row >> 1) & 3)) << 4), x[b][0]);
+          ldsm_x4(tile + row * 64 + (((2 + achunk) ^ ((row >> 1) & 3)) << 4), x[b][1]);
+        }
+        float n0[2][4], n1[2][4];
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) n0[b][e] = n1[b][e] = 0.f;
+          mma_bf16(n0[b], x[b][0], x[b][0][0], x[b][0][2]);
+          mma_bf16(n1[b], x[b][0], x[b][0][1], x[b][0][3]);
+        }
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          mma_bf16(n0[b], x[b][1], x[b][1][0], x[b][1][2]);
+          mma_bf16(n1[b], x[b][1], x[b][1][1], x[b][1][3]);
+        }
+        const bool odd = (lane >> 2) & 1;
+        const int src = (lane & ~3) | (lane >> 3);
+        float s0[2], s1[2];
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          s0[b] = __shfl_sync(0xffffffffu, odd ? n0[b][1] : n0[b][0], src);
+          s1[b] = __shfl_sync(0xffffffffu, odd ? n1[b][3] : n1[b][2], src);
+        }
         if (t_ == 0) {
-          vec[16 * blk + g_] = mult * inv_norm(s0);
-          vec[16 * blk + g_ + 8] = mult * inv_norm(s1);
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            vec[16 * (2 * bp + b) + g_] = mult * inv_norm(s0[b]);
+            vec[16 * (2 * bp + b) + g_ + 8] = mult * inv_norm(s1[b]);
+          }
         }
       }
       __syncwarp();
@@ -565,7 +615,14 @@ wattn_tc64_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restri
       uint32_t acc[32];
       HV_TMEM_LD32(tl + kColS + 64 * u + 32 * half, acc);
       tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_sfree(grp));
       float sv[32];
+      if (KO(2)) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sv[j] = __uint_as_float(acc[j]);
+      } else
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const float4 c = *reinterpret_cast<const float4*>(&vec[kN + 32 * half + 4 * q]);
@@ -597,7 +654,7 @@ wattn_tc64_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restri
       }
       uint32_t pk[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(ex2(sv[2 * j]), ex2(sv[2 * j + 1]));
+      for (int j = 0; j < 16; ++j) pk[j] = KO(2) ? pack_bf16x2(sv[2 * j], sv[2 * j + 1]) : pack_bf16x2(ex2(sv[2 * j]), ex2(sv[2 * j + 1]));
       HV_TMEM_ST16(tl + kColP + 16 * half, pk);
       if (half == 0) mxv[(grp * 2 + tph) * 128 + row] = off + mx;
       tmem_wait_st();
@@ -627,7 +684,7 @@ wattn_tc64_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restri
       tc_fence_before();
       mbar_arrive(bar_ofree(t));
       if (quad == 0) TRACE(k, 10);  // epilogue freed slot
-      if (ug.rflags & 1) {
+      if ((ug.rflags & 1) && !KO(4)) {
         const float inv = rcp_fast(l);
         const int sl = (ug.rflags & 4) ? sp : sn;
         const int ih = sl >> 3, iw = sl & 7;
@@ -684,7 +741,7 @@ int make_map(CUtensorMap* m, const void* base, const Geom& g, int row_elems, int
 
 }  // namespace
 
-static int g_fwd_variant = -1;  // -1: HV_ATTN_TCGEN05 environment variable (default off), 0: mma.sync, 1: tcgen05
+static int g_fwd_variant = -1;  // -1: HV_ATTN_TCGEN05 environment variable (default automatic), 0: mma.sync, 1: tcgen05
 
 int wattn_fwd_variant_set(int v) {
   const int old = g_fwd_variant;
@@ -693,29 +750,58 @@ int wattn_fwd_variant_set(int v) {
 }
 
 bool wattn_tc64_supported(const Geom& g, int dtype) {
-  static const bool env_on = []() { const char* e = getenv("HV_ATTN_TCGEN05"); return e != nullptr && atoi(e) != 0; }();
-  const bool enabled = g_fwd_variant < 0 ? env_on : g_fwd_variant == 1;
+  // HV_ATTN_TCGEN05: unset = automatic (where it is measured to be the faster forward), 0 = never, 1 = wherever valid
+  static const int env = []() { const char* e = getenv("HV_ATTN_TCGEN05"); return e == nullptr ? -1 : (atoi(e) != 0 ? 1 : 0); }();
+  const int mode = g_fwd_variant < 0 ? env : g_fwd_variant;
+  if (mode == 0) return false;
   // an odd shift would put the second half of a column-wrapped row at a 64-byte (not 128-byte) shared-memory offset
-  return enabled && dtype == HV_BF16 && g.ws == kWs && g.d == 32 && g.C % 32 == 0 && (g.shift & 1) == 0 &&
-         (int64_t)g.B * g.H * g.W < (int64_t(1) << 31) && g.W * 3 * g.C * 2 % 16 == 0;
+  const bool valid = dtype == HV_BF16 && g.ws == kWs && g.d == 32 && g.C % 32 == 0 && (g.shift & 1) == 0 &&
+                     (int64_t)g.B * g.H * g.W < (int64_t(1) << 31) && g.W * 3 * g.C * 2 % 16 == 0;
+  if (!valid || mode == 1) return valid;
+  // automatic: B200 measurements (tools/bench_kernels.py, batch 256): 0.74 vs 0.65 of the HBM roofline at the stage-0
+  // shape (3 heads, 16 k windows); with more head groups per launch the mma.sync kernel's 192-byte reads still win
+  return g.heads <= 4 && (int64_t)g.B * g.nW >= 4096;
 }
 
 int wattn_tc64_fwd(const Geom& g, const void* qkv, const float* bias_table, const float* tau, void* out, float* lse,
                    cudaStream_t st) {
   if (!aligned16(qkv) || !aligned16(out)) HV_FAIL(HV_ERR_ALIGN, "window_attn: qkv/out must be 16-byte aligned");
-  TcMaps maps;
-  const int s = g.shift, wa = kWs - g.shift;
-  // (w, h) of every box; with shift 0 only the first is used (the others just need to be valid descriptors)
-  const int bw[9] = {kWs, kWs, kWs, s ? wa : kWs, s ? s : kWs, s ? wa : kWs, s ? wa : kWs, s ? s : kWs, s ? s : kWs};
-  const int bh[9] = {kWs, s ? wa : kWs, s ? s : kWs, kWs, kWs, s ? wa : kWs, s ? s : kWs, s ? wa : kWs, s ? s : kWs};
-  for (int i = 0; i < 9; ++i) {
-    const int rc = make_map(&maps.m[i], qkv, g, 3 * g.C, bw[i], bh[i]);
-    if (rc) return rc;
+  // the nine descriptors depend on the qkv pointer and the geometry only: a training step replays the same handful of
+  // (pointer, stage) combinations, so encode once and keep the last few (cuTensorMapEncodeTiled costs ~1 us each)
+  struct MapKey { const void* ptr; int B, H, W, C, shift; };
+  struct MapEntry { MapKey key; TcMaps maps; };
+  static thread_local MapEntry cache[32];
+  static thread_local int cache_n = 0, cache_next = 0;
+  const MapKey key = {qkv, g.B, g.H, g.W, g.C, g.shift};
+  const TcMaps* mp = nullptr;
+  for (int i = 0; i < cache_n; ++i) {
+    const MapKey& c = cache[i].key;
+    if (c.ptr == key.ptr && c.B == key.B && c.H == key.H && c.W == key.W && c.C == key.C && c.shift == key.shift) { mp = &cache[i].maps; break; }
   }
+  if (!mp) {
+    MapEntry& e = cache[cache_next];
+    const int s = g.shift, wa = kWs - g.shift;
+    // (w, h) of every box; with shift 0 only the first is used (the others just need to be valid descriptors)
+    const int bw[9] = {kWs, kWs, kWs, s ? wa : kWs, s ? s : kWs, s ? wa : kWs, s ? wa : kWs, s ? s : kWs, s ? s : kWs};
+    const int bh[9] = {kWs, s ? wa : kWs, s ? s : kWs, kWs, kWs, s ? wa : kWs, s ? s : kWs, s ? wa : kWs, s ? s : kWs};
+    for (int i = 0; i < 9; ++i) {
+      const int rc = make_map(&e.maps.m[i], qkv, g, 3 * g.C, bw[i], bh[i]);
+      if (rc) return rc;
+    }
+    e.key = key;
+    mp = &e.maps;
+    cache_next = (cache_next + 1) % 32;
+    if (cache_n < 32) ++cache_n;
+  }
+  const TcMaps& maps = *mp;
   TcParams p;
   p.g = g;
   p.n_same = g.heads / 2;
   p.has_cross = g.heads & 1;
+  p.ko = 0;
+#ifdef HV_TC_TRACE
+  if (getenv("HV_TC_KO")) p.ko = atoi(getenv("HV_TC_KO"));
+#endif
   const int nsm = num_sms();
   const int nrows = g.B * g.nW;
   if (p.n_same == 0) {

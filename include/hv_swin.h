@@ -60,7 +60,8 @@ HV_API int hv_window_attn_kernel_kind(int C, int heads, int ws, int dtype);
 
 /* Forward kernel of the tensor-core path (kind 1): 0 = mma.sync + cp.async kernel, 1 = tcgen05 / TMEM / TMA kernel
  * (even shift sizes; falls back to 0 otherwise), -1 = decided by the HV_ATTN_TCGEN05 environment variable
- * (default 0).  Both write the same outputs; process-wide setting, not thread-safe against concurrent launches. */
+ * (0 / 1 as above; unset = automatic: the tcgen05 kernel where it is the faster one, i.e. <= 4 heads and >= 4096
+ * windows per launch).  Both write the same outputs; process-wide setting, not thread-safe against concurrent launches. */
 HV_API int hv_window_attn_fwd_variant(int variant);
 
 /* ---- host-side integer maps (CPU; same arithmetic the kernels use on the device) ------ */

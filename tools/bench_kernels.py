@@ -151,13 +151,14 @@ def main():
     rows = []
     B = a.batch
     stages = [(64, 96, 3), (32, 192, 6), (16, 384, 12), (8, 768, 24)]
-    if a.only in ("", "attn"):
+    if a.only in ("", "attn", "attn0"):
         for res, C, h in stages:
-            for shift in ((0, 4) if res > 8 else (0,)):
+            for shift in ((0, 4) if res > 8 and a.only != "attn0" else (0,)):
                 rows.append(bench_attn(B, res, C, h, 8, shift, torch.bfloat16, a.iters, a.tau))
                 print(json.dumps(rows[-1]), flush=True)
-        rows.append(bench_attn(max(B // 8, 8), 64, 96, 3, 8, 4, torch.float32, max(a.iters // 6, 3)))
-        print(json.dumps(rows[-1]), flush=True)
+        if a.only != "attn0":
+            rows.append(bench_attn(max(B // 8, 8), 64, 96, 3, 8, 4, torch.float32, max(a.iters // 6, 3)))
+            print(json.dumps(rows[-1]), flush=True)
     if a.only in ("", "ln"):
         for res, C, h in stages:
             for ydt, rdt in ((torch.bfloat16, torch.bfloat16), (torch.bfloat16, torch.float32), (torch.float32, torch.float32)):
