@@ -23,6 +23,7 @@ SIGNATURES = {
     "hv_compiled_arch": (_I, []),
     "hv_window_attn_kernel_kind": (_I, [_I, _I, _I, _I]),
     "hv_window_attn_fwd_variant": (_I, [_I]),
+    "hv_window_attn_bwd_variant": (_I, [_I]),
     "hv_relative_position_index": (_I, [_I, _P]),
     "hv_shift_window_mask": (_I, [_I, _I, _I, _I, _P]),
     "hv_window_token_index": (_I, [_I, _I, _I, _I, _I, _P]),

@@ -18,6 +18,12 @@ int wattn_fwd_variant_set(int v);
 int wattn_tc64_fwd(const Geom& g, const void* qkv, const float* bias_table, const float* tau, void* out, float* lse,
                    cudaStream_t st);
 size_t wattn_mma64_bwd_workspace_bytes(const Geom& g);
+bool wattn_tc64_bwd_supported(const Geom& g, int dtype);
+int wattn_bwd_variant_set(int v);
+size_t wattn_tc64_bwd_workspace_bytes(const Geom& g);
+int wattn_tc64_bwd(const Geom& g, const void* qkv, const void* out, const void* dout, const float* lse,
+                   const float* bias_table, const float* tau, void* dqkv, float* dbias_table, float* dtau,
+                   float* dq_colsum, void* workspace, size_t workspace_bytes, cudaStream_t st);
 int wattn_mma64_fwd(const Geom& g, const void* qkv, const float* bias_table, const float* tau, const float* mask,
                     int mask_windows, void* out, float* lse, cudaStream_t st);
 int wattn_mma64_bwd(const Geom& g, const void* qkv, const void* out, const void* dout, const float* lse,
@@ -118,6 +124,12 @@ int hv_window_attn_fwd_variant(int variant) {
   return HV_OK;
 }
 
+int hv_window_attn_bwd_variant(int variant) {
+  if (variant < -1 || variant > 1) HV_FAIL(HV_ERR_SHAPE, "hv_window_attn_bwd_variant: variant %d", variant);
+  wattn_bwd_variant_set(variant);
+  return HV_OK;
+}
+
 int hv_window_attn_kernel_kind(int C, int heads, int ws, int dtype) {
   if (heads <= 0 || C % heads) return 0;
   Geom g = make_geom(1, ws, ws, C, heads, ws, 0);
@@ -202,7 +214,10 @@ int hv_window_attn_fwd(const void* qkv, const float* bias_table, const float* ta
 size_t hv_window_attn_bwd_workspace_bytes(int B, int H, int W, int C, int heads, int ws, int dtype) {
   if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || heads <= 0 || ws <= 0 || C % heads || H % ws || W % ws) return 0;
   Geom g = make_geom(B, H, W, C, heads, ws, 0);
-  if (wattn_mma64_supported(g, dtype)) return wattn_mma64_bwd_workspace_bytes(g);
+  if (wattn_mma64_supported(g, dtype)) {  // either tensor-core backward may be selected at call time
+    const size_t a = wattn_mma64_bwd_workspace_bytes(g), b = wattn_tc64_bwd_workspace_bytes(g);
+    return a > b ? a : b;
+  }
   return 16;  // the generic kernel reduces with atomics
 }
 
@@ -218,9 +233,13 @@ int hv_window_attn_bwd(const void* qkv, const void* out, const void* dout, const
   rc = attn_common_checks("hv_window_attn_bwd", dtype, mask, mask_windows, g);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (mask == nullptr && wattn_mma64_supported(g, dtype))
+  if (mask == nullptr && wattn_mma64_supported(g, dtype)) {
+    if (wattn_tc64_bwd_supported(g, dtype))
+      return wattn_tc64_bwd(g, qkv, out, dout, lse, bias_table, tau, dqkv, dbias_table, dtau, dq_colsum, workspace,
+                            workspace_bytes, st);
     return wattn_mma64_bwd(g, qkv, out, dout, lse, bias_table, tau, mask, mask_windows, dqkv, dbias_table, dtau, dq_colsum,
                            workspace, workspace_bytes, st);
+  }
   if (dq_colsum != nullptr)
     HV_FAIL(HV_ERR_SHAPE, "hv_window_attn_bwd: dq_colsum is only produced by the tensor-core kernel "
                           "(hv_window_attn_kernel_kind() == 1 and mask == NULL)");

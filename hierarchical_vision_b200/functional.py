@@ -85,6 +85,11 @@ def set_attention_forward_variant(variant: int) -> None:
     check(_lib.load().hv_window_attn_fwd_variant(int(variant)), "hv_window_attn_fwd_variant")
 
 
+def set_attention_backward_variant(variant: int) -> None:
+    """0: mma.sync backward kernel, 1: tcgen05/TMEM/TMA backward kernel, -1: HV_ATTN_TCGEN05_BWD environment (unset: automatic)."""
+    check(_lib.load().hv_window_attn_bwd_variant(int(variant)), "hv_window_attn_bwd_variant")
+
+
 def window_attention_fwd_raw(qkv, bias_table, tau, mask, out, lse, B, H, W, C, heads, ws, shift):
     """Enqueue hv_window_attn_fwd on the current stream; every tensor is caller-allocated."""
     lib = _lib.load()

@@ -63,6 +63,10 @@ HV_API int hv_window_attn_kernel_kind(int C, int heads, int ws, int dtype);
  * (0 / 1 as above; unset = automatic: the tcgen05 kernel where it is the faster one, i.e. <= 4 heads and >= 4096
  * windows per launch).  Both write the same outputs; process-wide setting, not thread-safe against concurrent launches. */
 HV_API int hv_window_attn_fwd_variant(int variant);
+/* Backward kernel of the tensor-core path: 0 = mma.sync + cp.async kernel, 1 = tcgen05 / TMEM / TMA kernel (shift 0 or
+ * ws / 2; falls back to 0 otherwise), -1 = decided by the HV_ATTN_TCGEN05_BWD environment variable (unset = automatic).
+ * Same outputs and workspace; process-wide setting. */
+HV_API int hv_window_attn_bwd_variant(int variant);
 
 /* ---- host-side integer maps (CPU; same arithmetic the kernels use on the device) ------ */
 /* relative_position_index (N,N) int64 -- reference swinv2.py:175-190 */

@@ -63,9 +63,17 @@ def fwd_variant(request):
     hvf.set_attention_forward_variant(-1)
 
 
+@pytest.fixture(params=[0, 1], ids=["bwd_mma_sync", "bwd_tcgen05"])
+def bwd_variant(request):
+    """Both backward kernels of the tensor-core path (the tcgen05 one covers shift 0 and ws / 2, else falls back)."""
+    hvf.set_attention_backward_variant(request.param)
+    yield request.param
+    hvf.set_attention_backward_variant(-1)
+
+
 @pytest.mark.parametrize("case", CORE_CASES)
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_window_attention_core(case, dtype, fwd_variant):
+def test_window_attention_core(case, dtype, fwd_variant, bwd_variant):
     B, H, W, C, h, ws, s = case
     g = O.Geometry(B, H, W, C, h, ws, s)
     gen = torch.Generator().manual_seed(hash(case) % 1000)
@@ -87,7 +95,7 @@ def test_window_attention_core(case, dtype, fwd_variant):
 
 @pytest.mark.parametrize("taus", [(0.05, 10.0, 100.0), (100.0, 100.0, 100.0), (1.0, 13.0, 15.0), (30.0, 2.0, 60.0)])
 @pytest.mark.parametrize("shift", [0, 4, 2, 6])
-def test_window_attention_core_tau_range(taus, shift, fwd_variant):
+def test_window_attention_core_tau_range(taus, shift, fwd_variant, bwd_variant):
     """Tensor-core kernel across the whole logit-scale range: exp(logit_scale) from ~0 to the clamp at 100
     (swinv2.py:230).  Heads with a small scale take the softmax path without a running maximum, heads near the
     clamp the path with it; both must agree with the fp64 oracle on the same bf16 inputs."""
@@ -113,7 +121,7 @@ def test_window_attention_core_tau_range(taus, shift, fwd_variant):
 
 
 @pytest.mark.parametrize("case", [(2, 16, 16, 96, 3, 4), (1, 32, 16, 192, 6, 0), (3, 8, 8, 64, 2, 0), (1, 16, 16, 32, 1, 5)])
-def test_window_attention_dq_colsum(case):
+def test_window_attention_dq_colsum(case, bwd_variant):
     """hv_window_attn_bwd's optional dq_colsum output (gradient of q_bias, swinv2.py:211-220) equals the column
     sums of the q third of dqkv that the same call wrote; the generic kernel rejects the request."""
     B, H, W, C, h, s = case
