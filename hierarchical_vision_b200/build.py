@@ -38,6 +38,12 @@ def _newest_dep() -> float:
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(BUILD, exist_ok=True)
     nvcc = _nvcc()
+    # extra flags (HV_NVCC_FLAGS, e.g. -DHV_TC_TRACE) are part of the build identity: a change rebuilds everything
+    flags, stamp = os.environ.get("HV_NVCC_FLAGS", ""), os.path.join(BUILD, "flags.txt")
+    if not os.path.exists(stamp) or open(stamp).read() != flags:
+        force = True
+        with open(stamp, "w") as f:
+            f.write(flags)
     newest = _newest_dep()
     headers_newest = max(os.path.getmtime(os.path.join(CSRC, f)) for f in os.listdir(CSRC) if not f.endswith(".cu"))
     headers_newest = max(headers_newest, os.path.getmtime(os.path.join(os.path.dirname(PKG), "include", "hv_swin.h")))

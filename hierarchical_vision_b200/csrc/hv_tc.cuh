@@ -42,6 +42,9 @@ __device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (done) break;
+#ifdef HV_SPIN_SLEEP_NS
+    asm volatile("nanosleep.u32 %0;" ::"n"(HV_SPIN_SLEEP_NS));  // back off: a tight poll loop takes issue slots from the working warps
+#endif
     if (++spins > (1u << 24)) __trap();
   }
 }
@@ -91,6 +94,26 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
         "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), \
         "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])                                      \
       : "memory")
+
+#define HV_TMEM_LD16(taddr, r)                                                                                      \
+  asm volatile(                                                                                                     \
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"      \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),  \
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])                    \
+      : "r"(taddr))
+#define HV_REG_FENCE16(r)                                                                                           \
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),  \
+               "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])  \
+               ::"memory")
+
+// Compiler-level fence on 32 registers filled by an asynchronous tcgen05.ld: nothing that reads them may be scheduled
+// above this point (place it right after tcgen05.wait::ld when the load was issued earlier)
+#define HV_REG_FENCE32(r)                                                                                           \
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),  \
+               "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), \
+               "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]),           \
+               "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]),           \
+               "+r"(r[30]), "+r"(r[31])::"memory")
 
 __device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
   uint32_t v;

@@ -32,26 +32,28 @@ constexpr int kN = 64;
 constexpr int kWs = 8;
 constexpr int kTab = 225;
 constexpr int kTile = kN * 64;         // one (window, head) q / k / v / dO / o tile: 64 rows x 64 B (SWIZZLE_64B)
-constexpr int kStage = 10 * kTile;     // q_a q_b k_a k_b v_a v_b g_a g_b o_a o_b   (g = dO)
+constexpr int kStage = 8 * kTile;      // q_a q_b k_a k_b v_a v_b g_a g_b   (g = dO; o is never read, see D below)
 constexpr int kStages = 4;
-constexpr int kThreads = 768;
+constexpr int kThreads = 896;  // 28 warps
 constexpr int kPdTile = kN * 128;      // P or dS of one unit: 64 rows x 128 B (SWIZZLE_128B)
 constexpr int kBiasRow = 20;           // floats per table row (15 + alignment slack)
 constexpr int kBiasCopy = 328;         // floats per alignment copy: >= 15 * 20 and = 8 (mod 32) so 8 lanes hit 8 bank groups
 
 // ---- shared memory map (dynamic, 1024-byte aligned base)
 constexpr int kOffStage = 0;
-constexpr int kOffP = kOffStage + kStages * kStage;       // [2 units][64][128 B]
-constexpr int kOffDS = kOffP + 2 * kPdTile;
-constexpr int kOffEye = kOffDS + 2 * kPdTile;             // 64 x 64 bf16 identity (SWIZZLE_128B)
+constexpr int kOffP = kOffStage + kStages * kStage;       // [2 buffers][2 units][64][128 B]
+constexpr int kOffDS = kOffP + 4 * kPdTile;
+constexpr int kOffEye = kOffDS + 4 * kPdTile;             // 64 x 64 bf16 identity (SWIZZLE_128B)
 constexpr int kOffBias = kOffEye + kPdTile;               // [2 units][4 copies][kBiasCopy] float
-constexpr int kOffVec = kOffBias + 2 * 4 * kBiasCopy * 4; // [kStages][4: r, c, D, lse][128] float
-constexpr int kOffBins = kOffVec + kStages * 4 * 128 * 4; // [2][256] float: d(bias) bins at the end of the kernel
-constexpr int kOffCol = kOffBins + 2 * 256 * 4;           // [2][32] float dq column sums, [2] d(tau)
+constexpr int kOffVec = kOffBias + 2 * 4 * kBiasCopy * 4; // [kStages][3: r, c, lse][128] float
+constexpr int kOffDot = kOffVec + kStages * 3 * 128 * 4;  // [2 pair parity][2 halves][128] float: sum_j dS_ij t_ij per half row
+constexpr int kOffDpart = kOffDot + 2 * 2 * 128 * 4;      // [2 pair parity][2 halves][128] float: sum_j P_ij dP_ij per half row
+constexpr int kOffCol = kOffDpart + 2 * 2 * 128 * 4;      // [2][32] float dq column sums, [2] d(tau)
+constexpr int kOffBins = kOffP;                           // [2][256] float: d(bias) bins, after the main loop (aliases P)
 constexpr int kOffGeo = kOffCol + (2 * 32 + 4) * 4;       // [8][2] UnitGeo
 constexpr int kOffSlotMap = kOffGeo + 8 * 2 * 16;         // [64] bytes
 constexpr int kOffBar = kOffSlotMap + 64;
-constexpr int kNumBars = 5 * kStages + 5;
+constexpr int kNumBars = 5 * kStages + 7;
 constexpr int kOffTmem = kOffBar + kNumBars * 8;
 constexpr int kSmem = kOffTmem + 16;
 static_assert(kOffP % 1024 == 0 && kOffBias % 16 == 0 && kOffBar % 8 == 0, "shared-memory alignment");
@@ -63,9 +65,10 @@ constexpr int kColS = 0, kColDP = 128, kColDV = 256, kColDK = 320, kColDQ = 384,
 struct BwdParams {
   Geom g;
   int n_same, has_cross, ctas_same, ctas_cross;
+  int ko;  // HV_TC_TRACE builds only: knock-out bits for bottleneck experiments (results are wrong)
 };
 // per tensor: [0] full (8, 8) | split order: [1] (wa, 8) [2] (s, 8) [3] (wa, wa) [4] (wa, s) [5] (s, wa) [6] (s, s)
-struct BwdMaps { CUtensorMap m[3][7]; };  // qkv, dout, out
+struct BwdMaps { CUtensorMap m[2][7]; };  // qkv, dout
 
 struct CtaWork {
   int head_a, head_b, cross, first, stride, npairs;
@@ -133,7 +136,17 @@ __device__ __forceinline__ void rowdot_mma(const uint32_t (&x)[2][4], const uint
   mma_bf16(n1, x[1], y[1][1], y[1][3]);
 }
 
+#ifdef HV_TC_TRACE
+__device__ long long* g_btrace = nullptr;  // [pairs][16 events] clock64 stamps of CTA 0
+#define TRACE(k, ev) do { if (blockIdx.x == 0 && lane == 0 && g_btrace && (k) < 64) g_btrace[(k) * 16 + (ev)] = clock64(); } while (0)
+#define KO(bit) (p.ko & (bit))
+#else
+#define TRACE(k, ev) do { } while (0)
+#define KO(bit) false
+#endif
+
 template <bool V> struct BoolTag { static constexpr bool value = V; };
+template <int V> struct IntTag { static constexpr int value = V; };
 
 template <bool kSplit>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -151,10 +164,10 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
   auto bar_hat = [&](int s) { return bar0 + 8 * (3 * kStages + s); };
   auto bar_sdp = [&](int s) { return bar0 + 8 * (4 * kStages + s); };
   const uint32_t bar_sfree = bar0 + 8 * (5 * kStages + 0);
-  const uint32_t bar_staged = bar0 + 8 * (5 * kStages + 1);
-  const uint32_t bar_stfree = bar0 + 8 * (5 * kStages + 2);
-  const uint32_t bar_acc = bar0 + 8 * (5 * kStages + 3);
-  const uint32_t bar_accfree = bar0 + 8 * (5 * kStages + 4);
+  const uint32_t bar_acc = bar0 + 8 * (5 * kStages + 1);
+  const uint32_t bar_accfree = bar0 + 8 * (5 * kStages + 2);
+  auto bar_staged = [&](int b) { return bar0 + 8 * (5 * kStages + 3 + b); };  // P / dS staging buffer b written
+  auto bar_stfree = [&](int b) { return bar0 + 8 * (5 * kStages + 5 + b); };  // ... and read by the MMAs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmem);
   const int nrows = g.B * g.nW;
 
@@ -165,16 +178,18 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
     s_work = w0;
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_full(s), 1);
-      mbar_init(bar_empty(s), 8);  // the eight epilogue warps
+      mbar_init(bar_empty(s), 8);  // the dK and dQ epilogue warps (the dV warps do not touch the stage)
       mbar_init(bar_pre(s), 4);
       mbar_init(bar_hat(s), 4);
       mbar_init(bar_sdp(s), 1);
     }
     mbar_init(bar_sfree, 8);
-    mbar_init(bar_staged, 8);
-    mbar_init(bar_stfree, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_staged(b), 8);
+      mbar_init(bar_stfree(b), 1);
+    }
     mbar_init(bar_acc, 1);
-    mbar_init(bar_accfree, 8);
+    mbar_init(bar_accfree, 12);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -193,7 +208,7 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
     reinterpret_cast<uint32_t*>(smem + kOffEye)[idx] = w;
   }
   if (threadIdx.x < 64) slotmap[threadIdx.x] = (unsigned char)tile_row_slot(threadIdx.x, g.shift);
-  for (int idx = threadIdx.x; idx < 2 * 256 + 2 * 32 + 4; idx += kThreads) reinterpret_cast<float*>(smem + kOffBins)[idx] = 0.f;
+  for (int idx = threadIdx.x; idx < 2 * 32 + 4; idx += kThreads) reinterpret_cast<float*>(smem + kOffCol)[idx] = 0.f;
   {
     CtaWork w0;
     w0.init(p, blockIdx.x);
@@ -221,11 +236,12 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
   if (warp < 4) {
     reg_dealloc<40>();
     if (warp == 0) {
-      // ---------------------------------------------------------------- TMA producer: lane t < 10 loads tile t of the stage
+      // ---------------------------------------------------------------- TMA producer: lane t < 8 loads tile t of the stage
       for (int k = 0; k < npairs; ++k) {
         const int s = k % kStages;
         mbar_wait(bar_empty(s), ((k / kStages) & 1) ^ 1);
-        const int which = lane & 1, kind = lane >> 1;  // kind: 0 q, 1 k, 2 v, 3 dO, 4 o
+        TRACE(k, 0);
+        const int which = lane & 1, kind = lane >> 1;  // kind: 0 q, 1 k, 2 v, 3 dO
         bool valid;
         const int r = work.row(k, which, nrows, valid);
         const int b = r / g.nW, win = r - b * g.nW;
@@ -239,11 +255,11 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
           geo[(k & 7) * 2 + which] = ug;
         }
         __syncwarp();
-        if (lane == 0) mbar_expect_tx(bar_full(s), kStage);
+        if (lane == 0) mbar_expect_tx(bar_full(s), KO(1) ? 0 : kStage);
         __syncwarp();
-        if (lane < 10) {
+        if (lane < 8 && !KO(1)) {
           const int head = which == 0 ? work.head_a : work.head_b;
-          const int tsr = kind < 3 ? 0 : (kind == 3 ? 1 : 2);
+          const int tsr = kind < 3 ? 0 : 1;
           const int c0 = (kind < 3 ? kind * g.C : 0) + head * 32;
           const uint32_t dst = sb + kOffStage + s * kStage + lane * kTile;
           const uint32_t bar = bar_full(s);
@@ -275,6 +291,7 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
       for (int k = 0; k < npairs; ++k) {
         const int s = k % kStages;
         mbar_wait_fast(bar_full(s), (k / kStages) & 1);
+        TRACE(k, 1);
         if (k > 0) mbar_wait_fast(bar_sfree, (k - 1) & 1);  // the softmax threads hold S, dP of pair k-1 in registers
         tc_fence_after();
         if (elect_one()) {
@@ -284,6 +301,7 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
 #pragma unroll
           for (int kk = 0; kk < 2; ++kk) umma_ss(tmem + kColDP, d_g + so + 2 * kk, d_v + so + 2 * kk, id, kk > 0);
           umma_commit(bar_sdp(s));
+          TRACE(k, 2);
         }
         __syncwarp();
       }
@@ -302,35 +320,40 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
       const uint64_t b_g = smem_desc(sb + kOffStage + 6 * kTile, 4096, 512, 4);
       for (int k = 0; k < npairs; ++k) {
         const int s = k % kStages;
-        mbar_wait_fast(bar_staged, k & 1);
+        const int buf = k & 1;
+        mbar_wait_fast(bar_staged(buf), (k >> 1) & 1);
+        TRACE(k, 10);
         mbar_wait_fast(bar_hat(s), (k / kStages) & 1);
         if (k > 0) mbar_wait_fast(bar_accfree, (k - 1) & 1);
         tc_fence_after();
         if (elect_one()) {
-          const uint64_t so = (uint64_t)((s * kStage) >> 4);
+          const uint64_t so = (uint64_t)((s * kStage) >> 4), bo = (uint64_t)(buf * ((2 * kPdTile) >> 4));
+          if (!KO(8)) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)  // 16 queries per step: A += 2 KB, B += 1 KB
-            umma_ss(tmem + kColDV, a_pt + (uint64_t)(128 * ks), b_g + so + (uint64_t)(64 * ks), id_t, ks > 0);
+            umma_ss(tmem + kColDV, a_pt + bo + (uint64_t)(128 * ks), b_g + so + (uint64_t)(64 * ks), id_t, ks > 0);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
-            umma_ss(tmem + kColDK, a_dst + (uint64_t)(128 * ks), b_q + so + (uint64_t)(64 * ks), id_t, ks > 0);
+            umma_ss(tmem + kColDK, a_dst + bo + (uint64_t)(128 * ks), b_q + so + (uint64_t)(64 * ks), id_t, ks > 0);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)  // 16 keys per step: A += 32 B inside the swizzle atom, B += 1 KB
-            umma_ss(tmem + kColDQ, a_ds + (uint64_t)(2 * ks), b_k + so + (uint64_t)(64 * ks), id_q, ks > 0);
+            umma_ss(tmem + kColDQ, a_ds + bo + (uint64_t)(2 * ks), b_k + so + (uint64_t)(64 * ks), id_q, ks > 0);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
-            umma_ss(tmem + kColDB, a_ds + (uint64_t)(2 * ks), b_eye + (uint64_t)(2 * ks), id_b, (k > 0 || ks > 0) ? 1u : 0u);
+            umma_ss(tmem + kColDB, a_ds + bo + (uint64_t)(2 * ks), b_eye + (uint64_t)(2 * ks), id_b, (k > 0 || ks > 0) ? 1u : 0u);
+          }
           umma_commit(bar_acc);
-          umma_commit(bar_stfree);
+          umma_commit(bar_stfree(buf));
+          TRACE(k, 12);
         }
         __syncwarp();
       }
     }
   } else if (warp < 8) {
     // ------------------------------------------------------------------ pre-pass warps
-    reg_dealloc<64>();
+    reg_dealloc<56>();
     const int w4 = warp - 4;
-    const int u = w4 & 1, part = w4 >> 1;  // norms: tile (part: q | k, unit u); D: unit u, rows 32 * part ..
+    const int u = w4 & 1, part = w4 >> 1;  // norms: tile (part: q | k, unit u)
     const int head_u = u == 0 ? work.head_a : work.head_b;
     const float tau_u = __ldg(&tau[head_u]);
     const float mult = part == 0 ? 1.0f : tau_u * kLog2e;
@@ -345,15 +368,14 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
 
     auto pre = [&](int k) {
       const int s = k % kStages;
-      mbar_wait_fast(bar_full(s), (k / kStages) & 1);
+      mbar_wait(bar_full(s), (k / kStages) & 1);  // sleeping wait: polling would take issue slots from the softmax warps
       const uint32_t st = sb + kOffStage + s * kStage;
-      float* vec = vecs + s * 4 * 128;
-      {  // lse of the pair's rows (1e30 for the padding unit of an odd tail: P = dS = 0 there)
-        const int rf = geo[(k & 7) * 2 + lu].rflags;
-        vec[3 * 128 + lrow] = (rf & 1) ? __ldg(&lse[((int64_t)(rf >> 3) * g.heads + lhead) * kN + lslot]) : 1e30f;
-      }
+      float* vec = vecs + s * 3 * 128;
+      // lse of the pair's rows (1e30 for the padding unit of an odd tail: P = dS = 0 there); the load is issued first and
+      // consumed at the end of the pre-pass so that its latency hides behind the tensor-pipe work
+      const int rf = geo[(k & 7) * 2 + lu].rflags;
+      const float lse_v = (rf & 1) ? __ldg(&lse[((int64_t)(rf >> 3) * g.heads + lhead) * kN + lslot]) : 1e30f;
       const uint32_t tile = st + (2 * part + u) * kTile;
-      const uint32_t gt = st + (6 + u) * kTile, ot = st + (8 + u) * kTile;
 #pragma unroll
       for (int bp = 0; bp < 2; ++bp) {
         uint32_t x[2][2][4];
@@ -376,56 +398,43 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
           }
         }
       }
-      {  // D = rowsum(dO o o) for rows 32 * part .. + 32 of unit u
-        uint32_t x[2][2][4], y[2][2][4];
-#pragma unroll
-        for (int b2 = 0; b2 < 2; ++b2) {
-          const int row = 32 * part + 16 * b2 + arow;
-          const uint32_t o0 = row * 64 + (((achunk) ^ ((row >> 1) & 3)) << 4), o1 = row * 64 + (((2 + achunk) ^ ((row >> 1) & 3)) << 4);
-          ldsm_x4(gt + o0, x[b2][0]);
-          ldsm_x4(gt + o1, x[b2][1]);
-          ldsm_x4(ot + o0, y[b2][0]);
-          ldsm_x4(ot + o1, y[b2][1]);
-        }
-        float n0[2][4], n1[2][4];
-#pragma unroll
-        for (int b2 = 0; b2 < 2; ++b2) rowdot_mma(x[b2], y[b2], n0[b2], n1[b2]);
-#pragma unroll
-        for (int b2 = 0; b2 < 2; ++b2) {
-          const float s0 = __shfl_sync(0xffffffffu, odd ? n0[b2][1] : n0[b2][0], src);
-          const float s1 = __shfl_sync(0xffffffffu, odd ? n1[b2][3] : n1[b2][2], src);
-          if (t_ == 0) {
-            vec[2 * 128 + 64 * u + 32 * part + 16 * b2 + g_] = s0;
-            vec[2 * 128 + 64 * u + 32 * part + 16 * b2 + g_ + 8] = s1;
-          }
-        }
-      }
+      vec[2 * 128 + lrow] = lse_v;
       __syncwarp();
+      if (warp == 4) TRACE(k, 3);
       if (lane == 0) mbar_arrive(bar_pre(s));
     };
     // in-place normalisation of tile (part, u) once S has been computed from the raw tile: q^ = q / |q|, k^ = k / |k|
     auto hat = [&](int k) {
       const int s = k % kStages;
-      mbar_wait_fast(bar_sdp(s), (k / kStages) & 1);
+      mbar_wait(bar_sdp(s), (k / kStages) & 1);
       const uint32_t tile = sb + kOffStage + s * kStage + (2 * part + u) * kTile;
-      const float* vec = vecs + s * 4 * 128 + part * 128 + 64 * u;
+      const float* vec = vecs + s * 3 * 128 + part * 128 + 64 * u;
+      if (!KO(16)) {
+      uint4 v[2][4];
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int row = lane + 32 * rr;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) v[rr][ch] = lds128(tile + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
+      }
 #pragma unroll
       for (int rr = 0; rr < 2; ++rr) {
         const int row = lane + 32 * rr;
         const float sc = vec[row] * inv_mult;
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-          const uint32_t a = tile + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4);
-          uint4 v = lds128(a);
-          v.x = pack_bf16x2(bf16lo_to_f32(v.x) * sc, bf16hi_to_f32(v.x) * sc);
-          v.y = pack_bf16x2(bf16lo_to_f32(v.y) * sc, bf16hi_to_f32(v.y) * sc);
-          v.z = pack_bf16x2(bf16lo_to_f32(v.z) * sc, bf16hi_to_f32(v.z) * sc);
-          v.w = pack_bf16x2(bf16lo_to_f32(v.w) * sc, bf16hi_to_f32(v.w) * sc);
-          sts128(a, v);
+          uint4 w = v[rr][ch];
+          w.x = pack_bf16x2(bf16lo_to_f32(w.x) * sc, bf16hi_to_f32(w.x) * sc);
+          w.y = pack_bf16x2(bf16lo_to_f32(w.y) * sc, bf16hi_to_f32(w.y) * sc);
+          w.z = pack_bf16x2(bf16lo_to_f32(w.z) * sc, bf16hi_to_f32(w.z) * sc);
+          w.w = pack_bf16x2(bf16lo_to_f32(w.w) * sc, bf16hi_to_f32(w.w) * sc);
+          sts128(tile + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4), w);
         }
+      }
       }
       fence_async_smem();
       __syncwarp();
+      if (warp == 4) TRACE(k, 4);
       if (lane == 0) mbar_arrive(bar_hat(s));
     };
     if (npairs > 0) pre(0);
@@ -459,65 +468,124 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
     }
     const uint32_t p_row = sb + kOffP + u * kPdTile + i * 128, ds_row = sb + kOffDS + u * kPdTile + i * 128;
     float acc_tau = 0.f;
+    float* dots = reinterpret_cast<float*>(smem + kOffDot);
 
-    for (int k = 0; k < npairs; ++k) {
+    // The thread's 32 keys are two chunks of 16.  TMEM reads (64 KB per pair at 64 B/clk) are the longest serial piece of
+    // this role, so they run one chunk ahead of the arithmetic: chunk B of pair k lands while chunk A is computed, chunk A
+    // of pair k+1 while P / dS of pair k are staged.  S / dP go back to the issuer as soon as chunk B has landed.
+    uint32_t sA[16], pA[16], sB[16], pB[16];
+    const uint32_t tS = tl + kColS + 64 * u + 32 * half, tP = tl + kColDP + 64 * u + 32 * half;
+    auto fetch_a = [&](int k) {
       const int s = k % kStages;
+      mbar_wait_fast(bar_sdp(s), (k / kStages) & 1);
+      if (warp == 8) TRACE(k, 6);
+      tc_fence_after();
+      HV_TMEM_LD16(tS, sA);
+      HV_TMEM_LD16(tP, pA);
+    };
+    auto fetch_b = [&]() {
+      HV_TMEM_LD16(tS + 16, sB);
+      HV_TMEM_LD16(tP + 16, pB);
+    };
+    if (npairs > 0) {
+      fetch_a(0);
+      tmem_wait_ld();
+      HV_REG_FENCE16(sA);
+      HV_REG_FENCE16(pA);
+      fetch_b();
+    }
+    float* dpart = reinterpret_cast<float*>(smem + kOffDpart);
+    for (int k = 0; k < npairs; ++k) {
+      const int s = k % kStages, buf = k & 1;
       const uint32_t ph = (k / kStages) & 1;
       mbar_wait_fast(bar_pre(s), ph);
+      if (warp == 8) TRACE(k, 5);
       const int rflags = geo[(k & 7) * 2 + u].rflags;
-      const float* vec = vecs + s * 4 * 128;
-      const float ri = vec[row], Di = vec[2 * 128 + row], li = vec[3 * 128 + row];
+      const float* vec = vecs + s * 3 * 128;
+      const float ri = vec[row], li = vec[2 * 128 + row];
       const float* cv = vec + 128 + 64 * u + 32 * half;
-      mbar_wait_fast(bar_sdp(s), ph);
-      tc_fence_after();
-      uint32_t sa[32], pa[32];
-      HV_TMEM_LD32(tl + kColS + 64 * u + 32 * half, sa);
-      HV_TMEM_LD32(tl + kColDP + 64 * u + 32 * half, pa);
-      tmem_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_sfree);
-      uint32_t pp[16], dd[16];
+      // pass 1: P_ij = exp2(t_ij + b_ij - lse_i) replaces S, w_ij = P_ij dP_ij replaces dP; three row sums:
+      //   D = sum_j w (= dO_i . o_i, so the o tile is never loaded), U = sum_j w t, V = sum_j P t
       // masked / unmasked instantiations: only windows on the wrap pay for the mask test (a warp's rows share one window)
-      auto compute = [&](auto masked, uint32_t m) {
+      float Dp = 0.f, U = 0.f, V = 0.f;
+      auto pass1 = [&](auto masked, auto chunk, uint32_t m, uint32_t (&sa)[16], uint32_t (&pa)[16]) {
+        constexpr int ck = decltype(chunk)::value;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int qq = 0; qq < 4; ++qq) {
+          const int q = 4 * ck + qq;
           // keys 4q .. 4q + 3 of this half: slot order = window row 4 half + q / 2, columns 4 (q & 1) ..;
           // split order = window row q, columns 4 half ..
           const float4 b = *reinterpret_cast<const float4*>(bias_base + (kSplit ? -q * kBiasRow : -(q >> 1) * kBiasRow + 4 * (q & 1)));
           const float4 c = *reinterpret_cast<const float4*>(cv + 4 * q);
           const float bb[4] = {b.x, b.y, b.z, b.w}, cc[4] = {c.x, c.y, c.z, c.w};
-          float pv[4], dv[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int j = 4 * q + e;
-            const float t = (__uint_as_float(sa[j]) * ri) * cc[e];  // tau log2e cos(q_i, k_j)
+            const float t = (__uint_as_float(sa[4 * qq + e]) * ri) * cc[e];  // tau log2e cos(q_i, k_j)
             float x = (t + bb[e]) - li;
             if (decltype(masked)::value && ((m >> j) & 1u)) x += kNeg;
             const float pe = ex2(x);
-            const float de = pe * (__uint_as_float(pa[j]) - Di);
-            acc_tau = fmaf(de, t, acc_tau);
-            pv[e] = pe;
-            dv[e] = de;
+            const float w = pe * __uint_as_float(pa[4 * qq + e]);
+            Dp += w;
+            U = fmaf(w, t, U);
+            V = fmaf(pe, t, V);
+            sa[4 * qq + e] = __float_as_uint(pe);
+            pa[4 * qq + e] = __float_as_uint(w);
           }
-          pp[2 * q] = pack_bf16x2(pv[0], pv[1]);
-          pp[2 * q + 1] = pack_bf16x2(pv[2], pv[3]);
-          dd[2 * q] = pack_bf16x2(dv[0], dv[1]);
-          dd[2 * q + 1] = pack_bf16x2(dv[2], dv[3]);
         }
       };
-      if (kSplit && (rflags & 6)) compute(BoolTag<true>{}, ((rflags & 2) ? mH : 0u) | ((rflags & 4) ? mW : 0u));
-      else compute(BoolTag<false>{}, 0u);
-      if (k > 0) mbar_wait_fast(bar_stfree, (k - 1) & 1);  // the MMAs of pair k-1 have read the staging tiles
+      const bool wrap = kSplit && (rflags & 6);
+      const uint32_t m = wrap ? (((rflags & 2) ? mH : 0u) | ((rflags & 4) ? mW : 0u)) : 0u;
+      if (KO(4)) { }
+      else if (wrap) pass1(BoolTag<true>{}, IntTag<0>{}, m, sA, pA);
+      else pass1(BoolTag<false>{}, IntTag<0>{}, 0u, sA, pA);
+      tmem_wait_ld();  // chunk B has landed: all of S / dP of this pair is in registers
+      HV_REG_FENCE16(sB);
+      HV_REG_FENCE16(pB);
+      tc_fence_before();
+      __syncwarp();
+      if (warp == 8) TRACE(k, 7);
+      if (lane == 0) mbar_arrive(bar_sfree);
+      if (KO(4)) { }
+      else if (wrap) pass1(BoolTag<true>{}, IntTag<1>{}, m, sB, pB);
+      else pass1(BoolTag<false>{}, IntTag<1>{}, 0u, sB, pB);
+      // the two half-row threads of a query exchange their partial D through shared memory (warps w and w + 4)
+      dpart[(buf * 2 + half) * 128 + row] = Dp;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+      const float Di = Dp + dpart[(buf * 2 + (half ^ 1)) * 128 + row];
+      const float racc = fmaf(-Di, V, U);  // sum_j dS_ij t_ij over this half row: d(tau) and the dQ epilogue's q^.M
+      acc_tau += racc;
+      // pass 2: dS = P (dP - D) = w - D P, packed to bf16 together with P
+      uint32_t pp[16], dd[16];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        pp[e] = pack_bf16x2(__uint_as_float(sA[2 * e]), __uint_as_float(sA[2 * e + 1]));
+        dd[e] = pack_bf16x2(fmaf(-Di, __uint_as_float(sA[2 * e]), __uint_as_float(pA[2 * e])),
+                            fmaf(-Di, __uint_as_float(sA[2 * e + 1]), __uint_as_float(pA[2 * e + 1])));
+        pp[8 + e] = pack_bf16x2(__uint_as_float(sB[2 * e]), __uint_as_float(sB[2 * e + 1]));
+        dd[8 + e] = pack_bf16x2(fmaf(-Di, __uint_as_float(sB[2 * e]), __uint_as_float(pB[2 * e])),
+                                fmaf(-Di, __uint_as_float(sB[2 * e + 1]), __uint_as_float(pB[2 * e + 1])));
+      }
+      if (warp == 8) TRACE(k, 8);
+      if (k + 1 < npairs) fetch_a(k + 1);
+      if (k > 1) mbar_wait_fast(bar_stfree(buf), ((k - 2) >> 1) & 1);  // the MMAs of pair k-2 have read this buffer
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const uint32_t off = (uint32_t)(((4 * half + q) ^ (i & 7)) << 4);
+        const uint32_t off = (uint32_t)(buf * 2 * kPdTile) + (uint32_t)(((4 * half + q) ^ (i & 7)) << 4);
         sts128(p_row + off, make_uint4(pp[4 * q], pp[4 * q + 1], pp[4 * q + 2], pp[4 * q + 3]));
         sts128(ds_row + off, make_uint4(dd[4 * q], dd[4 * q + 1], dd[4 * q + 2], dd[4 * q + 3]));
       }
+      dots[(buf * 2 + half) * 128 + row] = racc;
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_staged);
+      if (warp == 8) TRACE(k, 9);
+      if (lane == 0) mbar_arrive(bar_staged(buf));
+      if (k + 1 < npairs) {
+        tmem_wait_ld();
+        HV_REG_FENCE16(sA);
+        HV_REG_FENCE16(pA);
+        fetch_b();
+      }
     }
     // d(tau) = sum dS cos = sum dS t / (tau log2e); one shared-memory atomic per warp (a warp's 32 rows are one unit)
     const float tot = warp_sum(acc_tau);
@@ -526,10 +594,11 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
       atomicAdd(reinterpret_cast<float*>(smem + kOffCol) + 64 + u, tot / tu);
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps: 16-19 dV and dK, 20-23 dQ
-    auto epilogue = [&](auto qs) {
-    constexpr bool qside = decltype(qs)::value;
-    if (qside) reg_alloc<96>(); else reg_dealloc<64>();
+    // ------------------------------------------------------------------ epilogue warps: 16-19 dV, 20-23 dK, 24-27 dQ
+    // (one accumulator each, so the TMEM columns go back to the issuer after a single 32-column load)
+    auto epilogue = [&](auto role_tag) {
+    constexpr int role = decltype(role_tag)::value;  // 0 dV, 1 dK, 2 dQ
+    if (role == 0) reg_dealloc<48>(); else if (role == 1) reg_dealloc<64>(); else reg_alloc<88>();
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const int u = row >> 6, t = row & 63;
@@ -537,27 +606,37 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
     const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16);
     const int sl = slotmap[t], ih = sl >> 3, iw = sl & 7;
     const float tau_h = __ldg(&tau[head]);
+    const float inv_tl = 1.0f / (tau_h * kLog2e);
     float csum[32];
 #pragma unroll
     for (int e = 0; e < 32; ++e) csum[e] = 0.f;
 
     for (int k = 0; k < npairs; ++k) {
       const int s = k % kStages;
-      mbar_wait_fast(bar_acc, k & 1);
+      mbar_wait(bar_acc, k & 1);  // sleeping wait (twelve warps mostly idle)
+      if (warp == 16) TRACE(k, 13);
       tc_fence_after();
+      uint32_t a[32];
+      HV_TMEM_LD32(tl + (role == 0 ? kColDV : (role == 1 ? kColDK : kColDQ)) + 32 * u, a);
       const UnitGeo ug = geo[(k & 7) * 2 + u];
       int prow = ug.row0 + ih; if (prow >= g.H) prow -= g.H;
       int pcol = ug.col0 + iw; if (pcol >= g.W) pcol -= g.W;
       const int64_t tok = ((int64_t)ug.b * g.H + prow) * g.W + pcol;
-      bf16* drow = dqkv + tok * (3 * g.C) + head * 32;
-      const bool valid = ug.rflags & 1;
-      const float* vec = vecs + s * 4 * 128;
-      uint32_t a[32];
-      if (!qside) {
-        HV_TMEM_LD32(tl + kColDV + 32 * u, a);
-        tmem_wait_ld();
+      bf16* drow = dqkv + tok * (3 * g.C) + head * 32 + (role == 0 ? 2 * g.C : (role == 1 ? g.C : 0));
+      const bool valid = (ug.rflags & 1) && !KO(2);
+      float qdot = 0.f;
+      if (role == 2) {
+        const float* dp = reinterpret_cast<const float*>(smem + kOffDot) + (k & 1) * 256 + row;
+        qdot = (dp[0] + dp[128]) * inv_tl;
+      }
+      tmem_wait_ld();
+      HV_REG_FENCE32(a);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_accfree);
+      if (role == 0) {
         if (valid) {
-          uint4* dst = reinterpret_cast<uint4*>(drow + 2 * g.C);
+          uint4* dst = reinterpret_cast<uint4*>(drow);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             uint4 v;
@@ -568,46 +647,61 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
             dst[q] = v;
           }
         }
-        HV_TMEM_LD32(tl + kColDK + 32 * u, a);
-      } else {
-        HV_TMEM_LD32(tl + kColDQ + 32 * u, a);
+        continue;
       }
-      tmem_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_accfree);
       // projection of the gradient of the normalised row back to the raw row: d x = sc (M - (x^ . M) x^)
-      const uint32_t tile = sb + kOffStage + s * kStage + ((qside ? 0 : 2) + u) * kTile + t * 64;
-      const float sc = qside ? vec[row] * tau_h : vec[128 + row] * kLn2;  // tau / |q_i|  |  tau / |k_j| = c_j ln 2
-      uint32_t xh[16];
+      const float* vec = vecs + s * 3 * 128;
+      const uint32_t tile = sb + kOffStage + s * kStage + ((role == 2 ? 0 : 2) + u) * kTile + t * 64;
+      const float sc = role == 2 ? vec[row] * tau_h : vec[128 + row] * kLn2;  // tau / |q_i|  |  tau / |k_j| = c_j ln 2
+      uint4* dst = reinterpret_cast<uint4*>(drow);
+      if (role == 1) {
+        uint32_t xh[16];
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        const uint4 v = lds128(tile + ((ch ^ ((t >> 1) & 3)) << 4));
-        xh[4 * ch] = v.x; xh[4 * ch + 1] = v.y; xh[4 * ch + 2] = v.z; xh[4 * ch + 3] = v.w;
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_empty(s));  // last read of the stage by this warp
-      float dot = 0.f;
+        for (int ch = 0; ch < 4; ++ch) {
+          const uint4 v = lds128(tile + ((ch ^ ((t >> 1) & 3)) << 4));
+          xh[4 * ch] = v.x; xh[4 * ch + 1] = v.y; xh[4 * ch + 2] = v.z; xh[4 * ch + 3] = v.w;
+        }
+        __syncwarp();
+        if (warp == 20) TRACE(k, 15);
+        if (lane == 0) mbar_arrive(bar_empty(s));  // last read of the stage by this warp
+        float dot = 0.f;
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        dot = fmaf(bf16lo_to_f32(xh[e]), __uint_as_float(a[2 * e]), dot);
-        dot = fmaf(bf16hi_to_f32(xh[e]), __uint_as_float(a[2 * e + 1]), dot);
-      }
-      uint32_t o[16];
+        for (int e = 0; e < 16; ++e) {
+          dot = fmaf(bf16lo_to_f32(xh[e]), __uint_as_float(a[2 * e]), dot);
+          dot = fmaf(bf16hi_to_f32(xh[e]), __uint_as_float(a[2 * e + 1]), dot);
+        }
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const float v0 = sc * fmaf(-dot, bf16lo_to_f32(xh[e]), __uint_as_float(a[2 * e]));
-        const float v1 = sc * fmaf(-dot, bf16hi_to_f32(xh[e]), __uint_as_float(a[2 * e + 1]));
-        if (qside && valid) { csum[2 * e] += v0; csum[2 * e + 1] += v1; }
-        o[e] = pack_bf16x2(v0, v1);
-      }
-      if (valid) {
-        uint4* dst = reinterpret_cast<uint4*>(drow + (qside ? 0 : g.C));
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t o[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+          for (int e = 0; e < 4; ++e) {
+            const float v0 = sc * fmaf(-dot, bf16lo_to_f32(xh[4 * ch + e]), __uint_as_float(a[8 * ch + 2 * e]));
+            const float v1 = sc * fmaf(-dot, bf16hi_to_f32(xh[4 * ch + e]), __uint_as_float(a[8 * ch + 2 * e + 1]));
+            o[e] = pack_bf16x2(v0, v1);
+          }
+          if (valid) dst[ch] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      } else {
+        // q^_i . M_i = sum_j dS_ij cos_ij: the softmax threads already have it (two half-row sums of dS t, t = tau log2e cos)
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const uint4 v = lds128(tile + ((ch ^ ((t >> 1) & 3)) << 4));
+          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+          uint32_t o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float v0 = sc * fmaf(-qdot, bf16lo_to_f32(w[e]), __uint_as_float(a[8 * ch + 2 * e]));
+            const float v1 = sc * fmaf(-qdot, bf16hi_to_f32(w[e]), __uint_as_float(a[8 * ch + 2 * e + 1]));
+            if (valid) { csum[8 * ch + 2 * e] += v0; csum[8 * ch + 2 * e + 1] += v1; }
+            o[e] = pack_bf16x2(v0, v1);
+          }
+          if (valid) dst[ch] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty(s));  // last read of the stage by this warp
       }
     }
-    if (qside && want_colsum) {
+    if (role == 2 && want_colsum) {
       float* col = reinterpret_cast<float*>(smem + kOffCol) + u * 32;
 #pragma unroll
       for (int e = 0; e < 32; ++e) {
@@ -616,13 +710,15 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
       }
     }
     };
-    if (warp >= 20) epilogue(BoolTag<true>{}); else epilogue(BoolTag<false>{});
+    if (warp < 20) epilogue(IntTag<0>{}); else if (warp < 24) epilogue(IntTag<1>{}); else epilogue(IntTag<2>{});
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  for (int idx = threadIdx.x; idx < 2 * 256; idx += kThreads) reinterpret_cast<float*>(smem + kOffBins)[idx] = 0.f;
+  __syncthreads();
   // ---- d(bias): fold the 64 x 64 accumulators of the two units into the 225 table bins
-  if (warp >= 16 && warp < 20 && npairs > 0) {
+  if (warp >= 20 && warp < 24 && npairs > 0) {
     const int quad = warp & 3, row = quad * 32 + lane, u = row >> 6, t = row & 63;
     const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16);
     const int si = slotmap[t];
@@ -740,9 +836,9 @@ int wattn_tc64_bwd(const Geom& g, const void* qkv, const void* out, const void* 
     const int s = g.shift, wa = kWs - g.shift;
     const int bw[7] = {kWs, s ? wa : kWs, s ? s : kWs, s ? wa : kWs, s ? wa : kWs, s ? s : kWs, s ? s : kWs};
     const int bh[7] = {kWs, kWs, kWs, s ? wa : kWs, s ? s : kWs, s ? wa : kWs, s ? s : kWs};
-    const void* base[3] = {qkv, dout, out};
-    const int row_elems[3] = {3 * g.C, g.C, g.C};
-    for (int t = 0; t < 3; ++t)
+    const void* base[2] = {qkv, dout};
+    const int row_elems[2] = {3 * g.C, g.C};
+    for (int t = 0; t < 2; ++t)
       for (int i = 0; i < 7; ++i) {
         const int rc = make_map(&e.maps.m[t][i], base[t], g, row_elems[t], bw[i], bh[i]);
         if (rc) return rc;
@@ -756,6 +852,10 @@ int wattn_tc64_bwd(const Geom& g, const void* qkv, const void* out, const void* 
   p.g = g;
   p.n_same = g.heads / 2;
   p.has_cross = g.heads & 1;
+  p.ko = 0;
+#ifdef HV_TC_TRACE
+  if (getenv("HV_TC_KO")) p.ko = atoi(getenv("HV_TC_KO"));
+#endif
   const int nsm = num_sms();
   const int nrows = g.B * g.nW;
   if (p.n_same == 0) {
@@ -784,6 +884,14 @@ int wattn_tc64_bwd(const Geom& g, const void* qkv, const void* out, const void* 
     HV_CUDA_OK(cudaFuncSetAttribute(wattn_tc64_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     attr_dev = dev;
   }
+#ifdef HV_TC_TRACE
+  static long long* dtrace = nullptr;
+  if (!dtrace) {
+    cudaMalloc(&dtrace, 64 * 16 * sizeof(long long));
+    cudaMemcpyToSymbol(g_btrace, &dtrace, sizeof(dtrace));
+  }
+  cudaMemsetAsync(dtrace, 0, 64 * 16 * sizeof(long long), st);
+#endif
   if (g.shift > 0)
     wattn_tc64_bwd_kernel<true><<<grid, kThreads, kSmem, st>>>(*mp, lse, bias_table, tau, (bf16*)dqkv, ws_dbias, ws_dtau, ws_colsum,
                                                                dq_colsum != nullptr, p);
@@ -791,6 +899,18 @@ int wattn_tc64_bwd(const Geom& g, const void* qkv, const void* out, const void* 
     wattn_tc64_bwd_kernel<false><<<grid, kThreads, kSmem, st>>>(*mp, lse, bias_table, tau, (bf16*)dqkv, ws_dbias, ws_dtau, ws_colsum,
                                                                 dq_colsum != nullptr, p);
   HV_LAUNCH_OK("wattn_tc64_bwd_kernel");
+#ifdef HV_TC_TRACE
+  if (getenv("HV_TC_BTRACE_DUMP")) {
+    static long long h[64 * 16];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, dtrace, sizeof(h), cudaMemcpyDeviceToHost);
+    FILE* f = fopen(getenv("HV_TC_BTRACE_DUMP"), "w");
+    if (f) {
+      for (int k = 0; k < 64; ++k) { for (int e = 0; e < 16; ++e) fprintf(f, "%lld ", h[k * 16 + e] ? h[k * 16 + e] - h[0] : -1LL); fprintf(f, "\n"); }
+      fclose(f);
+    }
+  }
+#endif
   const int n = g.heads * (kTab + 1) + g.C;
   wattn_tc64_bwd_reduce_kernel<<<(n + 127) / 128, 128, 0, st>>>(ws_dbias, ws_dtau, ws_colsum, p, dbias_table, dtau, dq_colsum);
   HV_LAUNCH_OK("wattn_tc64_bwd_reduce_kernel");
