@@ -76,6 +76,38 @@ def bench_attn(B, res, C, heads, ws, shift, dtype, iters, tau_mode="init"):
                 frac_fwdbwd=(bytes_f + bytes_b) / (t_f + t_b) / 1e6 / PEAK)
 
 
+def bench_gelu(rows, cols, dtype, iters):
+    """bias + GELU streaming kernels (Mlp activation): fwd reads h, writes a; bwd reads dout, h, writes dh."""
+    dev = "cuda"
+    esz = 2 if dtype == torch.bfloat16 else 4
+    per_set = rows * cols * esz * 3
+    nsets = min(6, max(2, int(2 * L2_BYTES / per_set) + 1))
+    lib = hvf._lib.load()
+    P = hvf._ptr
+    st = hvf._stream(torch.device("cuda", torch.cuda.current_device()))
+    bias = torch.randn(cols, device=dev)
+    wbytes = lib.hv_bias_gelu_bwd_workspace_bytes(rows, cols)
+    wsp = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+    db = torch.empty(cols, device=dev)
+    sets = [(torch.randn(rows, cols, device=dev).to(dtype), torch.empty(rows, cols, device=dev, dtype=dtype),
+             torch.randn(rows, cols, device=dev).to(dtype)) for _ in range(nsets)]
+    code = hvf._code(sets[0][0])
+
+    def f(s):
+        rc = lib.hv_bias_gelu_fwd(P(s[0]), P(bias), P(s[1]), rows, cols, code, st)
+        assert rc == 0, lib.hv_last_error()
+
+    def b(s):
+        rc = lib.hv_bias_gelu_bwd(P(s[2]), P(s[0]), P(bias), P(s[1]), P(db), P(wsp), wbytes, rows, cols, code, st)
+        assert rc == 0, lib.hv_last_error()
+
+    t_f = timeit([lambda s=s: f(s) for s in sets], iters)
+    t_b = timeit([lambda s=s: b(s) for s in sets], iters)
+    bf, bb = rows * cols * esz * 2, rows * cols * esz * 3
+    return dict(kernel="bias_gelu", rows=rows, cols=cols, dtype=str(dtype).split(".")[-1], fwd_ms=t_f, bwd_ms=t_b,
+                fwd_gbs=bf / t_f / 1e6, bwd_gbs=bb / t_b / 1e6, frac_fwd=bf / t_f / 1e6 / PEAK, frac_bwd=bb / t_b / 1e6 / PEAK)
+
+
 def bench_ln(B, L, C, ydt, rdt, iters):
     dev = "cuda"
     ey = 2 if ydt == torch.bfloat16 else 4
@@ -158,6 +190,10 @@ def main():
                 print(json.dumps(rows[-1]), flush=True)
         if a.only != "attn0":
             rows.append(bench_attn(max(B // 8, 8), 64, 96, 3, 8, 4, torch.float32, max(a.iters // 6, 3)))
+            print(json.dumps(rows[-1]), flush=True)
+    if a.only in ("", "gelu"):
+        for res, C, h in stages:
+            rows.append(bench_gelu(B * res * res, 4 * C, torch.bfloat16, a.iters))
             print(json.dumps(rows[-1]), flush=True)
     if a.only in ("", "ln"):
         for res, C, h in stages:
