@@ -17,6 +17,15 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kFinalizeRows = 8;  // row-groups per finalize block
 
+// Packed fp32 arithmetic of sm_100 (FADD2 / FMUL2 / FFMA2: two elements per instruction).  With bf16 activations these
+// kernels move 6 bytes per element and are bound by issue slots, not by HBM; neighbouring elements of a vector are
+// independent, so all the normalisation arithmetic pairs up.
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 f2s(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
 // One 16-byte global vector kept PACKED in registers (4 regs) until it is needed as fp32: keeps the
 // register footprint of the R*K vectors a lane has in flight small enough for 3-4 CTAs per SM.
 template <typename T> struct Pk;
@@ -122,30 +131,32 @@ ln_residual_fwd_kernel(const TY* __restrict__ y, const TR* __restrict__ shortcut
     for (int rr = 0; rr < R; ++rr) {
       const int64_t r = r0 + rr * RPW + gi;
       const bool row_ok = r < rows;
-      float sum = 0.f;
+      float2 sum2 = f2s(0.f);
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         float x[VE];
         xv[rr][k].get(x);
 #pragma unroll
-        for (int e = 0; e < VE; ++e) sum += x[e] + bia[k][e];
+        for (int e = 0; e < VE; e += 2) sum2 = f2add(sum2, f2add(f2(x[e], x[e + 1]), f2(bia[k][e], bia[k][e + 1])));
       }
-      const float mean = group_sum<GS>(sum) * inv_c;
-      float sq = 0.f;
+      const float mean = group_sum<GS>(sum2.x + sum2.y) * inv_c;
+      const float2 nmean = f2s(-mean);
+      float2 sq2 = f2s(0.f);
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         if (gl + k * GS < vpr) {
           float x[VE];
           xv[rr][k].get(x);
 #pragma unroll
-          for (int e = 0; e < VE; ++e) {
-            const float dlt = x[e] + bia[k][e] - mean;
-            sq = fmaf(dlt, dlt, sq);
+          for (int e = 0; e < VE; e += 2) {
+            const float2 dlt = f2add(f2add(f2(x[e], x[e + 1]), f2(bia[k][e], bia[k][e + 1])), nmean);
+            sq2 = f2fma(dlt, dlt, sq2);
           }
         }
       }
-      const float rstd = rsqrtf(group_sum<GS>(sq) * inv_c + eps);
+      const float rstd = rsqrtf(group_sum<GS>(sq2.x + sq2.y) * inv_c + eps);
       const float ks = (keep_scale != nullptr && row_ok) ? keep_scale[r / rows_per_sample] : 1.0f;
+      const float2 rs2 = f2s(rstd), nmr2 = f2s(-mean * rstd), ks2 = f2s(ks);
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         const int v = gl + k * GS;
@@ -154,7 +165,13 @@ ln_residual_fwd_kernel(const TY* __restrict__ y, const TR* __restrict__ shortcut
           xv[rr][k].get(x);
           rv[rr][k].get(res);
 #pragma unroll
-          for (int e = 0; e < VE; ++e) res[e] += ks * fmaf((x[e] + bia[k][e] - mean) * rstd, gam[k][e], bet[k][e]);
+          for (int e = 0; e < VE; e += 2) {
+            // res + ks * (((x + bias) * rstd - mean * rstd) * gamma + beta)
+            const float2 xh = f2fma(f2add(f2(x[e], x[e + 1]), f2(bia[k][e], bia[k][e + 1])), rs2, nmr2);
+            const float2 o = f2fma(ks2, f2fma(xh, f2(gam[k][e], gam[k][e + 1]), f2(bet[k][e], bet[k][e + 1])), f2(res[e], res[e + 1]));
+            res[e] = o.x;
+            res[e + 1] = o.y;
+          }
           PkRow<TR, VE> o;
           o.set(res);
           o.store(out + r * C + v * VE);
@@ -226,37 +243,45 @@ ln_residual_bwd_kernel(const TR* __restrict__ dout, const TY* __restrict__ y, co
       const int64_t r = r0 + rr * RPW + gi;
       const bool row_ok = r < rows;
       float xh[K][VE], gx[K][VE];
-      float s1 = 0.f, s2 = 0.f;
+      float2 s1 = f2s(0.f), s2 = f2s(0.f);
+      const float2 ks2 = f2s(ks[rr]), rs2 = f2s(rstd[rr]), nmr2 = f2s(-mean[rr] * rstd[rr]);
 #pragma unroll
       for (int k = 0; k < K; ++k) {
-        const bool ok = row_ok && (gl + k * GS < vpr);
+        // rows / vectors outside the tensor were loaded as zeros (and mean = rstd = 0, gamma = bias = 0 there), so every
+        // sum below receives exact zeros from them without a select
         float yy[VE], gg[VE];
         yv[rr][k].get(yy);
         gv[rr][k].get(gg);
 #pragma unroll
-        for (int e = 0; e < VE; ++e) {
-          const float g = gg[e] * ks[rr];
-          const float xhat = ok ? (yy[e] + bia[k][e] - mean[rr]) * rstd[rr] : 0.f;
-          xh[k][e] = xhat;
-          dg[k][e] = fmaf(g, xhat, dg[k][e]);
-          db[k][e] += g;
-          const float gxv = g * gam[k][e];
-          gx[k][e] = gxv;
-          s1 = fmaf(gxv, xhat, s1);
-          s2 += gxv;
+        for (int e = 0; e < VE; e += 2) {
+          const float2 g = f2mul(f2(gg[e], gg[e + 1]), ks2);
+          const float2 xhat = f2fma(f2add(f2(yy[e], yy[e + 1]), f2(bia[k][e], bia[k][e + 1])), rs2, nmr2);
+          xh[k][e] = xhat.x; xh[k][e + 1] = xhat.y;
+          const float2 dg2 = f2fma(g, xhat, f2(dg[k][e], dg[k][e + 1]));
+          dg[k][e] = dg2.x; dg[k][e + 1] = dg2.y;
+          const float2 db2 = f2add(f2(db[k][e], db[k][e + 1]), g);
+          db[k][e] = db2.x; db[k][e + 1] = db2.y;
+          const float2 gxv = f2mul(g, f2(gam[k][e], gam[k][e + 1]));
+          gx[k][e] = gxv.x; gx[k][e + 1] = gxv.y;
+          s1 = f2fma(gxv, xhat, s1);
+          s2 = f2add(s2, gxv);
         }
       }
-      const float c1 = group_sum<GS>(s1) * inv_c;
-      const float c2 = group_sum<GS>(s2) * inv_c;
+      const float c1 = group_sum<GS>(s1.x + s1.y) * inv_c;
+      const float c2 = group_sum<GS>(s2.x + s2.y) * inv_c;
+      const float2 nc1 = f2s(-c1), nc2 = f2s(-c2);
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         const int v = gl + k * GS;
         if (row_ok && v < vpr) {
           float o[VE];
 #pragma unroll
-          for (int e = 0; e < VE; ++e) {
-            o[e] = rstd[rr] * (gx[k][e] - c2 - xh[k][e] * c1);
-            dbi[k][e] += o[e];
+          for (int e = 0; e < VE; e += 2) {
+            // rstd * (gx - c2 - xhat * c1)
+            const float2 t = f2mul(rs2, f2fma(f2(xh[k][e], xh[k][e + 1]), nc1, f2add(f2(gx[k][e], gx[k][e + 1]), nc2)));
+            o[e] = t.x; o[e + 1] = t.y;
+            const float2 d2 = f2add(f2(dbi[k][e], dbi[k][e + 1]), t);
+            dbi[k][e] = d2.x; dbi[k][e + 1] = d2.y;
           }
           PkRow<TY, VE> ov;
           ov.set(o);
@@ -344,7 +369,8 @@ template <typename TY, typename TR, int GS, int K>
 int run_bwd(const void* dout, const void* y, const float* gamma, const float* bias, const float* mean, const float* rstd,
             const float* ks, void* dy, float* dgamma, float* dbeta, float* dbias, float* partials, int64_t rows, int C,
             int64_t rps, cudaStream_t st) {
-  constexpr int R = K == 1 ? 2 : 1;
+  // rows in flight per lane group: enough 16-byte requests outstanding to cover the HBM latency at 2 CTAs per SM
+  constexpr int R = K == 1 ? 4 : (K == 3 ? 2 : 1);
   constexpr int MINB = K <= 2 ? 2 : 1;
   const int grid = grid_for_rows(rows, (32 / GS) * R, kBwdCtasPerSm);
   ln_residual_bwd_kernel<TY, TR, GS, K, R, MINB><<<grid, kThreads, 3 * C * sizeof(float), st>>>(
