@@ -38,5 +38,5 @@ for n, c in tot.most_common(12):
     print(f"  {n:28s} {100*c/max(s,1):6.2f}%")
 print(f"\ntop {top} lines by samples")
 for r in sorted(data, key=lambda r: -f(r, "# Samples"))[:top]:
-    st = sorted(((f(r, n), n) for n in stall_cols), reverse=True)[:2]
+    st = (sorted(((f(r, n), n) for n in stall_cols), reverse=True) + [(0.0, "stall_-"), (0.0, "stall_-")])[:2]
     print(f"  {f(r,'# Samples'):7.0f}  {f(r,'Instructions Executed'):10.0f}  {r[col['Source']][:70]:70s} {st[0][1][6:]}:{st[0][0]:.0f} {st[1][1][6:]}:{st[1][0]:.0f}")
