@@ -346,7 +346,10 @@ int grid_for_rows(int64_t rows, int rows_per_warp_iter, int ctas_per_sm) {
 constexpr int kBwdCtasPerSm = 2;  // also bounds the number of partial rows the finalize kernel sums
 
 struct Shape { int gs, k; };
-bool pick_shape(int vpr, Shape& s) {
+bool pick_shape(int vpr, bool exact_fit, Shape& s) {
+  // rows of 12 / 24 / 48 vectors (C = 96 / 192 / 384 in bf16: stages 0-2 of SwinV2-T) fill a lane group exactly with three
+  // vectors per lane; the power-of-two groups below would leave a quarter of the lanes idle
+  if (exact_fit && (vpr == 12 || vpr == 24 || vpr == 48)) { s.gs = vpr / 3; s.k = 3; return true; }
   static const Shape table[] = {{8, 1}, {16, 1}, {32, 1}, {32, 2}, {32, 3}, {32, 4}, {32, 6}, {32, 8}};
   for (const Shape& t : table)
     if (vpr <= t.gs * t.k) { s = t; return true; }
@@ -356,8 +359,8 @@ bool pick_shape(int vpr, Shape& s) {
 template <typename TY, typename TR, int GS, int K>
 int run_fwd(const void* y, const void* sc, const float* gamma, const float* beta, const float* bias, const float* ks,
             void* out, float* mean, float* rstd, int64_t rows, int C, int64_t rps, float eps, cudaStream_t st) {
-  constexpr int R = K == 1 ? 4 : (K == 2 ? 2 : 1);
-  constexpr int MINB = K <= 2 ? 2 : 1;
+  constexpr int R = K == 1 ? 4 : ((K == 2 || GS < 32) ? 2 : 1);
+  constexpr int MINB = (K <= 2 || GS < 32) ? 2 : 1;
   const int grid = grid_for_rows(rows, (32 / GS) * R, 2 * MINB);
   ln_residual_fwd_kernel<TY, TR, GS, K, R, MINB><<<grid, kThreads, 0, st>>>((const TY*)y, (const TR*)sc, gamma, beta, bias, ks,
                                                                       (TR*)out, mean, rstd, rows, C, rps, eps);
@@ -383,6 +386,9 @@ int run_bwd(const void* dout, const void* y, const float* gamma, const float* bi
 
 #define HV_LN_DISPATCH_SHAPE(FN, TY, TR, ...)                                  \
   switch (shape.gs * 100 + shape.k) {                                          \
+    case 403:  return FN<TY, TR, 4, 3>(__VA_ARGS__);                           \
+    case 803:  return FN<TY, TR, 8, 3>(__VA_ARGS__);                           \
+    case 1603: return FN<TY, TR, 16, 3>(__VA_ARGS__);                          \
     case 801:  return FN<TY, TR, 8, 1>(__VA_ARGS__);                           \
     case 1601: return FN<TY, TR, 16, 1>(__VA_ARGS__);                          \
     case 3201: return FN<TY, TR, 32, 1>(__VA_ARGS__);                          \
@@ -393,13 +399,17 @@ int run_bwd(const void* dout, const void* y, const float* gamma, const float* bi
     default:   return FN<TY, TR, 32, 8>(__VA_ARGS__);                          \
   }
 
-int check_common(int64_t rows, int C, int y_dtype, int res_dtype, Shape& shape) {
+int check_common(int64_t rows, int C, int y_dtype, int res_dtype, bool backward, Shape& shape) {
   if (rows <= 0 || C <= 0) HV_FAIL(HV_ERR_SHAPE, "ln_residual: rows=%lld C=%d", (long long)rows, C);
   if (!((y_dtype == HV_F32 && res_dtype == HV_F32) || (y_dtype == HV_BF16 && (res_dtype == HV_BF16 || res_dtype == HV_F32))))
     HV_FAIL(HV_ERR_DTYPE, "ln_residual: unsupported dtype pair y=%d residual=%d", y_dtype, res_dtype);
   const int ve = y_dtype == HV_F32 ? 4 : 8;
   if (C % ve != 0) HV_FAIL(HV_ERR_SHAPE, "ln_residual: C=%d must be a multiple of %d", C, ve);
-  if (!pick_shape(C / ve, shape)) HV_FAIL(HV_ERR_SHAPE, "ln_residual: C=%d too wide (max %d)", C, 256 * ve);
+  // exact-fit groups: always in the backward; in the forward only where measured faster (same-type residual, 24 vectors
+  // per row or fp32 rows -- the other cases run out of registers with three vectors and two tensors per lane)
+  const int vpr = C / ve;
+  const bool exact_fit = backward || (y_dtype == res_dtype && (vpr == 24 || y_dtype == HV_F32));
+  if (!pick_shape(vpr, exact_fit, shape)) HV_FAIL(HV_ERR_SHAPE, "ln_residual: C=%d too wide (max %d)", C, 256 * ve);
   return HV_OK;
 }
 
@@ -414,7 +424,7 @@ int ln_residual_fwd(const void* y, const void* shortcut, const float* gamma, con
                     const float* keep_scale, void* out, float* mean, float* rstd, int64_t rows, int C,
                     int64_t rows_per_sample, float eps, int y_dtype, int res_dtype, cudaStream_t st) {
   Shape shape;
-  int rc = check_common(rows, C, y_dtype, res_dtype, shape);
+  int rc = check_common(rows, C, y_dtype, res_dtype, false, shape);
   if (rc) return rc;
   if (!aligned16(y) || !aligned16(out) || (shortcut && !aligned16(shortcut))) HV_FAIL(HV_ERR_ALIGN, "ln_residual_fwd: pointers must be 16-byte aligned");
   if (rows_per_sample <= 0) rows_per_sample = rows;
@@ -432,7 +442,7 @@ int ln_residual_bwd(const void* dout, const void* y, const float* gamma, const f
                     void* workspace, size_t workspace_bytes, int64_t rows, int C, int64_t rows_per_sample, int y_dtype,
                     int res_dtype, cudaStream_t st) {
   Shape shape;
-  int rc = check_common(rows, C, y_dtype, res_dtype, shape);
+  int rc = check_common(rows, C, y_dtype, res_dtype, true, shape);
   if (rc) return rc;
   if (!aligned16(y) || !aligned16(dout) || !aligned16(dy)) HV_FAIL(HV_ERR_ALIGN, "ln_residual_bwd: pointers must be 16-byte aligned");
   if (workspace == nullptr || workspace_bytes < ln_residual_bwd_workspace_bytes(rows, C))
