@@ -180,3 +180,15 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dirpath, fn)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "oracle/" not in src.replace(
                     "routes through ``oracle/``", ""), fn
+
+
+@pytest.mark.parametrize("setter", ["hv_window_attn_fwd_variant", "hv_window_attn_bwd_variant"])
+def test_kernel_variant_setters_validate_their_argument(lib, setter):
+    """The forward / backward variant switches are host-only state: -1 (automatic), 0 (mma.sync), 1 (tcgen05) are
+    accepted, anything else is an error code with a message, never a crash."""
+    fn = getattr(lib, setter)
+    for v in (0, 1, -1):
+        assert fn(v) == 0
+    assert fn(2) != 0 and b"variant" in lib.hv_last_error()
+    assert fn(-2) != 0
+    assert fn(-1) == 0
