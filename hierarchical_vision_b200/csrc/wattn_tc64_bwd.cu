@@ -32,9 +32,9 @@ constexpr int kN = 64;
 constexpr int kWs = 8;
 constexpr int kTab = 225;
 constexpr int kTile = kN * 64;         // one (window, head) q / k / v / dO / o tile: 64 rows x 64 B (SWIZZLE_64B)
-constexpr int kStage = 8 * kTile;      // q_a q_b k_a k_b v_a v_b g_a g_b   (g = dO; o is never read, see D below)
-constexpr int kStages = 4;
-constexpr int kThreads = 896;  // 28 warps
+constexpr int kStage = 10 * kTile;     // q_a q_b k_a k_b v_a v_b g_a g_b o_a o_b   (g = dO)
+constexpr int kStages = 3;
+constexpr int kThreads = 1024;  // 32 warps
 constexpr int kPdTile = kN * 128;      // P or dS of one unit: 64 rows x 128 B (SWIZZLE_128B)
 constexpr int kBiasRow = 20;           // floats per table row (15 + alignment slack)
 constexpr int kBiasCopy = 328;         // floats per alignment copy: >= 15 * 20 and = 8 (mod 32) so 8 lanes hit 8 bank groups
@@ -45,22 +45,24 @@ constexpr int kOffP = kOffStage + kStages * kStage;       // [2 buffers][2 units
 constexpr int kOffDS = kOffP + 4 * kPdTile;
 constexpr int kOffEye = kOffDS + 4 * kPdTile;             // 64 x 64 bf16 identity (SWIZZLE_128B)
 constexpr int kOffBias = kOffEye + kPdTile;               // [2 units][4 copies][kBiasCopy] float
-constexpr int kOffVec = kOffBias + 2 * 4 * kBiasCopy * 4; // [kStages][3: r, c, lse][128] float
-constexpr int kOffDot = kOffVec + kStages * 3 * 128 * 4;  // [2 pair parity][2 halves][128] float: sum_j dS_ij t_ij per half row
-constexpr int kOffDpart = kOffDot + 2 * 2 * 128 * 4;      // [2 pair parity][2 halves][128] float: sum_j P_ij dP_ij per half row
-constexpr int kOffCol = kOffDpart + 2 * 2 * 128 * 4;      // [2][32] float dq column sums, [2] d(tau)
+constexpr int kOffVec = kOffBias + 2 * 4 * kBiasCopy * 4; // [kStages][4: r, c, D, lse][128] float
+constexpr int kOffDot = kOffVec + kStages * 4 * 128 * 4;  // [4 pairs in flight][2 halves][128] float: sum_j dS_ij t_ij per half row
+constexpr int kOffCol = kOffDot + 4 * 2 * 128 * 4;        // [2][32] float dq column sums, [2] d(tau)
 constexpr int kOffBins = kOffP;                           // [2][256] float: d(bias) bins, after the main loop (aliases P)
 constexpr int kOffGeo = kOffCol + (2 * 32 + 4) * 4;       // [8][2] UnitGeo
 constexpr int kOffSlotMap = kOffGeo + 8 * 2 * 16;         // [64] bytes
 constexpr int kOffBar = kOffSlotMap + 64;
-constexpr int kNumBars = 5 * kStages + 7;
+constexpr int kNumBars = 5 * kStages + 8;
 constexpr int kOffTmem = kOffBar + kNumBars * 8;
 constexpr int kSmem = kOffTmem + 16;
 static_assert(kOffP % 1024 == 0 && kOffBias % 16 == 0 && kOffBar % 8 == 0, "shared-memory alignment");
 static_assert(kSmem <= 227 * 1024, "shared memory budget");
 
 // TMEM columns
-constexpr int kColS = 0, kColDP = 128, kColDV = 256, kColDK = 320, kColDQ = 384, kColDB = 448;
+// S and dP of a pair take 64 columns each: the two units are separate M = 64 MMAs whose accumulators interleave in the
+// 128 lanes (rows 16q .. 16q + 15 of unit a in lanes 32q .. 32q + 15, of unit b in lanes 32q + 16 .. 32q + 31; measured with
+// tools/probes/umma_m64_probe.cu) -- no wasted off-diagonal blocks, and room for two buffers
+constexpr int kColS = 0, kColDP = 128, kColDV = 256, kColDK = 320, kColDQ = 384, kColDB = 448;  // S, dP: + 64 * buffer
 
 struct BwdParams {
   Geom g;
@@ -68,7 +70,7 @@ struct BwdParams {
   int ko;  // HV_TC_TRACE builds only: knock-out bits for bottleneck experiments (results are wrong)
 };
 // per tensor: [0] full (8, 8) | split order: [1] (wa, 8) [2] (s, 8) [3] (wa, wa) [4] (wa, s) [5] (s, wa) [6] (s, s)
-struct BwdMaps { CUtensorMap m[2][7]; };  // qkv, dout
+struct BwdMaps { CUtensorMap m[3][7]; };  // qkv, dout, out
 
 struct CtaWork {
   int head_a, head_b, cross, first, stride, npairs;
@@ -163,9 +165,9 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
   auto bar_pre = [&](int s) { return bar0 + 8 * (2 * kStages + s); };
   auto bar_hat = [&](int s) { return bar0 + 8 * (3 * kStages + s); };
   auto bar_sdp = [&](int s) { return bar0 + 8 * (4 * kStages + s); };
-  const uint32_t bar_sfree = bar0 + 8 * (5 * kStages + 0);
   const uint32_t bar_acc = bar0 + 8 * (5 * kStages + 1);
   const uint32_t bar_accfree = bar0 + 8 * (5 * kStages + 2);
+  auto bar_sfree = [&](int b) { return bar0 + 8 * (5 * kStages + (b ? 0 : 7)); };  // S / dP buffer b read by its softmax group
   auto bar_staged = [&](int b) { return bar0 + 8 * (5 * kStages + 3 + b); };  // P / dS staging buffer b written
   auto bar_stfree = [&](int b) { return bar0 + 8 * (5 * kStages + 5 + b); };  // ... and read by the MMAs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmem);
@@ -178,18 +180,18 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
     s_work = w0;
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_full(s), 1);
-      mbar_init(bar_empty(s), 8);  // the dK and dQ epilogue warps (the dV warps do not touch the stage)
+      mbar_init(bar_empty(s), 8);  // the eight epilogue warps
       mbar_init(bar_pre(s), 4);
       mbar_init(bar_hat(s), 4);
       mbar_init(bar_sdp(s), 1);
     }
-    mbar_init(bar_sfree, 8);
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_staged(b), 8);
       mbar_init(bar_stfree(b), 1);
+      mbar_init(bar_sfree(b), 8);
     }
     mbar_init(bar_acc, 1);
-    mbar_init(bar_accfree, 12);
+    mbar_init(bar_accfree, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -241,7 +243,7 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
         const int s = k % kStages;
         mbar_wait(bar_empty(s), ((k / kStages) & 1) ^ 1);
         TRACE(k, 0);
-        const int which = lane & 1, kind = lane >> 1;  // kind: 0 q, 1 k, 2 v, 3 dO
+        const int which = lane & 1, kind = lane >> 1;  // kind: 0 q, 1 k, 2 v, 3 dO, 4 o
         bool valid;
         const int r = work.row(k, which, nrows, valid);
         const int b = r / g.nW, win = r - b * g.nW;
@@ -257,9 +259,9 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
         __syncwarp();
         if (lane == 0) mbar_expect_tx(bar_full(s), KO(1) ? 0 : kStage);
         __syncwarp();
-        if (lane < 8 && !KO(1)) {
+        if (lane < 10 && !KO(1)) {
           const int head = which == 0 ? work.head_a : work.head_b;
-          const int tsr = kind < 3 ? 0 : 1;
+          const int tsr = kind < 3 ? 0 : (kind == 3 ? 1 : 2);
           const int c0 = (kind < 3 ? kind * g.C : 0) + head * 32;
           const uint32_t dst = sb + kOffStage + s * kStage + lane * kTile;
           const uint32_t bar = bar_full(s);
@@ -285,21 +287,28 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
       }
     } else if (warp == 1) {
       // ---------------------------------------------------------------- issuer of S = Q K^T and dP = dO V^T
-      const uint32_t id = idesc_bf16(128, 128, 0, 0);
+      const uint32_t id = idesc_bf16(64, 64, 0, 0);
       const uint64_t d_q = smem_desc(sb + kOffStage, 16, 512, 4), d_k = smem_desc(sb + kOffStage + 2 * kTile, 16, 512, 4);
       const uint64_t d_v = smem_desc(sb + kOffStage + 4 * kTile, 16, 512, 4), d_g = smem_desc(sb + kOffStage + 6 * kTile, 16, 512, 4);
       for (int k = 0; k < npairs; ++k) {
-        const int s = k % kStages;
+        const int s = k % kStages, buf = k & 1;
         mbar_wait_fast(bar_full(s), (k / kStages) & 1);
         TRACE(k, 1);
-        if (k > 0) mbar_wait_fast(bar_sfree, (k - 1) & 1);  // the softmax threads hold S, dP of pair k-1 in registers
+        if (k > 1) mbar_wait_fast(bar_sfree(buf), ((k >> 1) - 1) & 1);  // the group of pair k-2 has read this S / dP buffer
         tc_fence_after();
         if (elect_one()) {
           const uint64_t so = (uint64_t)((s * kStage) >> 4);
 #pragma unroll
-          for (int kk = 0; kk < 2; ++kk) umma_ss(tmem + kColS, d_q + so + 2 * kk, d_k + so + 2 * kk, id, kk > 0);
+          for (int u = 0; u < 2; ++u) {  // unit u: tiles q_u, k_u (one tile = 4 KB further), accumulator lanes + 16 u
+            const uint32_t dl = (uint32_t)(16 * u) << 16;
+            const uint64_t uo = (uint64_t)(u * (kTile >> 4));
 #pragma unroll
-          for (int kk = 0; kk < 2; ++kk) umma_ss(tmem + kColDP, d_g + so + 2 * kk, d_v + so + 2 * kk, id, kk > 0);
+            for (int kk = 0; kk < 2; ++kk)
+              umma_ss(tmem + dl + kColS + 64 * buf, d_q + so + uo + 2 * kk, d_k + so + uo + 2 * kk, id, kk > 0);
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk)
+              umma_ss(tmem + dl + kColDP + 64 * buf, d_g + so + uo + 2 * kk, d_v + so + uo + 2 * kk, id, kk > 0);
+          }
           umma_commit(bar_sdp(s));
           TRACE(k, 2);
         }
@@ -351,13 +360,11 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
     }
   } else if (warp < 8) {
     // ------------------------------------------------------------------ pre-pass warps
-    reg_dealloc<56>();
     const int w4 = warp - 4;
-    const int u = w4 & 1, part = w4 >> 1;  // norms: tile (part: q | k, unit u)
+    const int u = w4 & 1, part = w4 >> 1;  // norms: tile (part: q | k, unit u); D: unit u, rows 32 * part ..
     const int head_u = u == 0 ? work.head_a : work.head_b;
     const float tau_u = __ldg(&tau[head_u]);
     const float mult = part == 0 ? 1.0f : tau_u * kLog2e;
-    const float inv_mult = part == 0 ? 1.0f : 1.0f / (tau_u * kLog2e);
     const int g_ = lane >> 2, t_ = lane & 3;
     const int arow = (lane & 7) + 8 * ((lane >> 3) & 1), achunk = lane >> 4;
     const bool odd = (lane >> 2) & 1;
@@ -370,12 +377,13 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
       const int s = k % kStages;
       mbar_wait(bar_full(s), (k / kStages) & 1);  // sleeping wait: polling would take issue slots from the softmax warps
       const uint32_t st = sb + kOffStage + s * kStage;
-      float* vec = vecs + s * 3 * 128;
+      float* vec = vecs + s * 4 * 128;
       // lse of the pair's rows (1e30 for the padding unit of an odd tail: P = dS = 0 there); the load is issued first and
       // consumed at the end of the pre-pass so that its latency hides behind the tensor-pipe work
       const int rf = geo[(k & 7) * 2 + lu].rflags;
       const float lse_v = (rf & 1) ? __ldg(&lse[((int64_t)(rf >> 3) * g.heads + lhead) * kN + lslot]) : 1e30f;
       const uint32_t tile = st + (2 * part + u) * kTile;
+      const uint32_t gt = st + (6 + u) * kTile, ot = st + (8 + u) * kTile;
 #pragma unroll
       for (int bp = 0; bp < 2; ++bp) {
         uint32_t x[2][2][4];
@@ -398,17 +406,176 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
           }
         }
       }
-      vec[2 * 128 + lrow] = lse_v;
+      {  // D = rowsum(dO o o) for rows 32 * part .. + 32 of unit u
+        uint32_t x[2][2][4], y[2][2][4];
+#pragma unroll
+        for (int b2 = 0; b2 < 2; ++b2) {
+          const int row = 32 * part + 16 * b2 + arow;
+          const uint32_t o0 = row * 64 + (((achunk) ^ ((row >> 1) & 3)) << 4), o1 = row * 64 + (((2 + achunk) ^ ((row >> 1) & 3)) << 4);
+          ldsm_x4(gt + o0, x[b2][0]);
+          ldsm_x4(gt + o1, x[b2][1]);
+          ldsm_x4(ot + o0, y[b2][0]);
+          ldsm_x4(ot + o1, y[b2][1]);
+        }
+        float n0[2][4], n1[2][4];
+#pragma unroll
+        for (int b2 = 0; b2 < 2; ++b2) rowdot_mma(x[b2], y[b2], n0[b2], n1[b2]);
+#pragma unroll
+        for (int b2 = 0; b2 < 2; ++b2) {
+          const float s0 = __shfl_sync(0xffffffffu, odd ? n0[b2][1] : n0[b2][0], src);
+          const float s1 = __shfl_sync(0xffffffffu, odd ? n1[b2][3] : n1[b2][2], src);
+          if (t_ == 0) {
+            vec[2 * 128 + 64 * u + 32 * part + 16 * b2 + g_] = s0;
+            vec[2 * 128 + 64 * u + 32 * part + 16 * b2 + g_ + 8] = s1;
+          }
+        }
+      }
+      vec[3 * 128 + lrow] = lse_v;
       __syncwarp();
       if (warp == 4) TRACE(k, 3);
       if (lane == 0) mbar_arrive(bar_pre(s));
     };
-    // in-place normalisation of tile (part, u) once S has been computed from the raw tile: q^ = q / |q|, k^ = k / |k|
+    for (int k = 0; k < npairs; ++k) pre(k);
+
+  } else if (warp < 24) {
+    // ------------------------------------------------------------------ softmax / dS threads: two groups (warps 8-15 even
+    // pairs, 16-23 odd pairs) so that the hand-over latencies of one group hide behind the arithmetic of the other; a thread
+    // owns half a logit row and streams it from TMEM 16 keys at a time (64 registers per thread: S / dP stay in TMEM, which
+    // has room for one buffer per group).  Lanes 0-15 of a warp are rows of unit a, lanes 16-31 of unit b (M = 64 layout).
+    const int grp = (warp - 8) >> 3;
+    const int half = ((warp - 8) >> 2) & 1;
+    const int quad = warp & 3;
+    const int u = lane >> 4, i = 16 * quad + (lane & 15);  // unit of the pair, tile row (query) inside the unit
+    const int row = 64 * u + i;                            // row of the pair in the per-stage vectors
+    const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16);
+    const float kNeg = kMaskValue * kLog2e;
+    const int si = slotmap[i], ih = si >> 3, iw = si & 7;
+    // Toeplitz bias: float index of (dh = ih + 7, x = 7 - iw) in the alignment copy that makes x a multiple of 4
+    const int cpy = (7 - iw) & 3;
+    const float* bias_base = reinterpret_cast<const float*>(smem + kOffBias) + u * 4 * kBiasCopy + cpy * kBiasCopy +
+                             (ih + 7) * kBiasRow + (7 - iw - cpy) + 4 + (kSplit ? 4 * half : -(4 * half) * kBiasRow);
+    // masks of a shifted layer: bit j set = key j of this thread's half sits on the other side of the wrap than the query
+    uint32_t mH = 0u, mW = 0u;
+    if (kSplit) {
+      const int thr = kWs - g.shift;
+      for (int j = 0; j < 32; ++j) {
+        const int sj = slotmap[32 * half + j];
+        if (((sj >> 3) >= thr) != (ih >= thr)) mH |= 1u << j;
+        if (((sj & 7) >= thr) != (iw >= thr)) mW |= 1u << j;
+      }
+    }
+    const uint32_t p_row = sb + kOffP + grp * 2 * kPdTile + u * kPdTile + i * 128;
+    const uint32_t ds_row = sb + kOffDS + grp * 2 * kPdTile + u * kPdTile + i * 128;
+    const uint32_t tS = tl + kColS + 64 * grp + 32 * half, tP = tl + kColDP + 64 * grp + 32 * half;
+    float acc_tau = 0.f;
+    float* dots = reinterpret_cast<float*>(smem + kOffDot);
+
+    for (int k = grp; k < npairs; k += 2) {
+      const int s = k % kStages;
+      const uint32_t ph = (k / kStages) & 1;
+      mbar_wait_fast(bar_pre(s), ph);
+      if (warp == 8) TRACE(k, 5);
+      const int rflags = geo[(k & 7) * 2 + u].rflags;
+      const float* vec = vecs + s * 4 * 128;
+      const float ri = vec[row], Di = vec[2 * 128 + row], li = vec[3 * 128 + row];
+      const float* cv = vec + 128 + 64 * u + 32 * half;
+      uint32_t m = 0u;
+      if (kSplit) m = ((rflags & 2) ? mH : 0u) | ((rflags & 4) ? mW : 0u);
+      const bool any_mask = kSplit && __any_sync(0xffffffffu, m != 0u);
+      if (k > 1) mbar_wait_fast(bar_stfree(grp), ((k >> 1) - 1) & 1);  // the MMAs of pair k-2 have read this group's staging tiles
+      mbar_wait_fast(bar_sdp(s), ph);
+      if (warp == 8) TRACE(k, 6);
+      tc_fence_after();
+      float racc = 0.f;  // sum_j dS_ij t_ij over this half row: d(tau) contribution and the dQ epilogue's q^.M
+      auto chunk = [&](auto masked, auto ck_tag) {
+        constexpr int ck = decltype(ck_tag)::value;  // keys 16 ck .. 16 ck + 15 of this half
+        uint32_t sa[16], pa[16];
+        HV_TMEM_LD16(tS + 16 * ck, sa);
+        HV_TMEM_LD16(tP + 16 * ck, pa);
+        tmem_wait_ld();
+        if (ck == 1) {  // the whole half row has left TMEM: hand the buffer back to the S / dP issuer
+          tc_fence_before();
+          __syncwarp();
+          if (warp == 8) TRACE(k, 7);
+          if (lane == 0) mbar_arrive(bar_sfree(grp));
+        }
+#pragma unroll
+        for (int h8 = 0; h8 < 2; ++h8) {  // eight keys = one 16-byte staging chunk of P and of dS
+          uint32_t pp[4], dd[4];
+#pragma unroll
+          for (int q2 = 0; q2 < 2; ++q2) {
+            const int q = 4 * ck + 2 * h8 + q2;
+            // keys 4q .. 4q + 3 of this half: slot order = window row 4 half + q / 2, columns 4 (q & 1) ..;
+            // split order = window row q, columns 4 half ..
+            const float4 b = *reinterpret_cast<const float4*>(bias_base + (kSplit ? -q * kBiasRow : -(q >> 1) * kBiasRow + 4 * (q & 1)));
+            const float4 c = *reinterpret_cast<const float4*>(cv + 4 * q);
+            const float bb[4] = {b.x, b.y, b.z, b.w}, cc[4] = {c.x, c.y, c.z, c.w};
+            float pv[4], dv[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = 4 * q + e, jj = 8 * h8 + 4 * q2 + e;
+              const float t = (__uint_as_float(sa[jj]) * ri) * cc[e];  // tau log2e cos(q_i, k_j)
+              float x = (t + bb[e]) - li;
+              if (decltype(masked)::value && ((m >> j) & 1u)) x += kNeg;
+              const float pe = ex2(x);
+              const float de = pe * (__uint_as_float(pa[jj]) - Di);
+              racc = fmaf(de, t, racc);
+              pv[e] = pe;
+              dv[e] = de;
+            }
+            pp[2 * q2] = pack_bf16x2(pv[0], pv[1]);
+            pp[2 * q2 + 1] = pack_bf16x2(pv[2], pv[3]);
+            dd[2 * q2] = pack_bf16x2(dv[0], dv[1]);
+            dd[2 * q2 + 1] = pack_bf16x2(dv[2], dv[3]);
+          }
+          const uint32_t off = (uint32_t)(((4 * half + 2 * ck + h8) ^ (i & 7)) << 4);
+          sts128(p_row + off, make_uint4(pp[0], pp[1], pp[2], pp[3]));
+          sts128(ds_row + off, make_uint4(dd[0], dd[1], dd[2], dd[3]));
+        }
+      };
+      if (any_mask) { chunk(BoolTag<true>{}, IntTag<0>{}); chunk(BoolTag<true>{}, IntTag<1>{}); }
+      else { chunk(BoolTag<false>{}, IntTag<0>{}); chunk(BoolTag<false>{}, IntTag<1>{}); }
+      if (warp == 8) TRACE(k, 8);
+      acc_tau += racc;
+      dots[((k & 3) * 2 + half) * 128 + row] = racc;
+      fence_async_smem();
+      __syncwarp();
+      if (warp == 8) TRACE(k, 9);
+      if (lane == 0) mbar_arrive(bar_staged(grp));
+    }
+    // d(tau) = sum dS cos = sum dS t / (tau log2e); lanes 0-15 / 16-31 of a warp belong to unit a / b
+    const float tot = group_sum<16>(acc_tau);
+    if ((lane & 15) == 0) {
+      const float tu = __ldg(&tau[u == 0 ? work.head_a : work.head_b]) * kLog2e;
+      atomicAdd(reinterpret_cast<float*>(smem + kOffCol) + 64 + u, tot / tu);
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps: 24-27 dV and dK, 28-31 dQ
+    auto epilogue = [&](auto role_tag) {
+    constexpr int role = decltype(role_tag)::value;  // 1 dV + dK, 2 dQ
+    if (role == 2) reg_alloc<88>();
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int u = row >> 6, t = row & 63;
+    const int head = u == 0 ? work.head_a : work.head_b;
+    const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16);
+    const int sl = slotmap[t], ih = sl >> 3, iw = sl & 7;
+    const float tau_h = __ldg(&tau[head]);
+    const float inv_tl = 1.0f / (tau_h * kLog2e);
+    float csum[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) csum[e] = 0.f;
+    // In-place normalisation of one q / k tile per dV+dK warp once S has been computed from the raw tile (q^ = q / |q|,
+    // k^ = k / |k|): done here, one pair ahead of this warp's epilogue work, so that it never waits behind the pre-pass
+    // of a later pair and the output MMAs find their B operands ready
+    const int hpart = quad >> 1, hu = quad & 1;
+    const float inv_mult = hpart == 0 ? 1.0f : 1.0f / (__ldg(&tau[hu == 0 ? work.head_a : work.head_b]) * kLog2e);
     auto hat = [&](int k) {
       const int s = k % kStages;
+      mbar_wait(bar_pre(s), (k / kStages) & 1);
       mbar_wait(bar_sdp(s), (k / kStages) & 1);
-      const uint32_t tile = sb + kOffStage + s * kStage + (2 * part + u) * kTile;
-      const float* vec = vecs + s * 3 * 128 + part * 128 + 64 * u;
+      const uint32_t tile = sb + kOffStage + s * kStage + (2 * hpart + hu) * kTile;
+      const float* vec = vecs + s * 4 * 128 + hpart * 128 + 64 * hu;
       if (!KO(16)) {
       uint4 v[2][4];
 #pragma unroll
@@ -434,209 +601,30 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
       }
       fence_async_smem();
       __syncwarp();
-      if (warp == 4) TRACE(k, 4);
+      if (warp == 24) TRACE(k, 4);
       if (lane == 0) mbar_arrive(bar_hat(s));
     };
-    if (npairs > 0) pre(0);
-    for (int k = 0; k < npairs; ++k) {
-      if (k + 1 < npairs) pre(k + 1);
-      hat(k);
-    }
-  } else if (warp < 16) {
-    // ------------------------------------------------------------------ softmax / dS threads: half a logit row each
-    reg_alloc<104>();
-    const int half = (warp - 8) >> 2;
-    const int quad = warp & 3;
-    const int row = quad * 32 + lane;      // TMEM lane
-    const int u = row >> 6, i = row & 63;  // unit of the pair, tile row (query) inside the unit
-    const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16);
-    const float kNeg = kMaskValue * kLog2e;
-    const int si = slotmap[i], ih = si >> 3, iw = si & 7;
-    // Toeplitz bias: float index of (dh = ih + 7, x = 7 - iw) in the alignment copy that makes x a multiple of 4
-    const int cpy = (7 - iw) & 3;
-    const float* bias_base = reinterpret_cast<const float*>(smem + kOffBias) + u * 4 * kBiasCopy + cpy * kBiasCopy +
-                             (ih + 7) * kBiasRow + (7 - iw - cpy) + 4 + (kSplit ? 4 * half : -(4 * half) * kBiasRow);
-    // masks of a shifted layer: bit j set = key j of this thread's half sits on the other side of the wrap than the query
-    uint32_t mH = 0u, mW = 0u;
-    if (kSplit) {
-      const int thr = kWs - g.shift;
-      for (int j = 0; j < 32; ++j) {
-        const int sj = slotmap[32 * half + j];
-        if (((sj >> 3) >= thr) != (ih >= thr)) mH |= 1u << j;
-        if (((sj & 7) >= thr) != (iw >= thr)) mW |= 1u << j;
-      }
-    }
-    const uint32_t p_row = sb + kOffP + u * kPdTile + i * 128, ds_row = sb + kOffDS + u * kPdTile + i * 128;
-    float acc_tau = 0.f;
-    float* dots = reinterpret_cast<float*>(smem + kOffDot);
-
-    // The thread's 32 keys are two chunks of 16.  TMEM reads (64 KB per pair at 64 B/clk) are the longest serial piece of
-    // this role, so they run one chunk ahead of the arithmetic: chunk B of pair k lands while chunk A is computed, chunk A
-    // of pair k+1 while P / dS of pair k are staged.  S / dP go back to the issuer as soon as chunk B has landed.
-    uint32_t sA[16], pA[16], sB[16], pB[16];
-    const uint32_t tS = tl + kColS + 64 * u + 32 * half, tP = tl + kColDP + 64 * u + 32 * half;
-    auto fetch_a = [&](int k) {
-      const int s = k % kStages;
-      mbar_wait_fast(bar_sdp(s), (k / kStages) & 1);
-      if (warp == 8) TRACE(k, 6);
-      tc_fence_after();
-      HV_TMEM_LD16(tS, sA);
-      HV_TMEM_LD16(tP, pA);
-    };
-    auto fetch_b = [&]() {
-      HV_TMEM_LD16(tS + 16, sB);
-      HV_TMEM_LD16(tP + 16, pB);
-    };
-    if (npairs > 0) {
-      fetch_a(0);
-      tmem_wait_ld();
-      HV_REG_FENCE16(sA);
-      HV_REG_FENCE16(pA);
-      fetch_b();
-    }
-    float* dpart = reinterpret_cast<float*>(smem + kOffDpart);
-    for (int k = 0; k < npairs; ++k) {
-      const int s = k % kStages, buf = k & 1;
-      const uint32_t ph = (k / kStages) & 1;
-      mbar_wait_fast(bar_pre(s), ph);
-      if (warp == 8) TRACE(k, 5);
-      const int rflags = geo[(k & 7) * 2 + u].rflags;
-      const float* vec = vecs + s * 3 * 128;
-      const float ri = vec[row], li = vec[2 * 128 + row];
-      const float* cv = vec + 128 + 64 * u + 32 * half;
-      // pass 1: P_ij = exp2(t_ij + b_ij - lse_i) replaces S, w_ij = P_ij dP_ij replaces dP; three row sums:
-      //   D = sum_j w (= dO_i . o_i, so the o tile is never loaded), U = sum_j w t, V = sum_j P t
-      // masked / unmasked instantiations: only windows on the wrap pay for the mask test (a warp's rows share one window)
-      float Dp = 0.f, U = 0.f, V = 0.f;
-      auto pass1 = [&](auto masked, auto chunk, uint32_t m, uint32_t (&sa)[16], uint32_t (&pa)[16]) {
-        constexpr int ck = decltype(chunk)::value;
-#pragma unroll
-        for (int qq = 0; qq < 4; ++qq) {
-          const int q = 4 * ck + qq;
-          // keys 4q .. 4q + 3 of this half: slot order = window row 4 half + q / 2, columns 4 (q & 1) ..;
-          // split order = window row q, columns 4 half ..
-          const float4 b = *reinterpret_cast<const float4*>(bias_base + (kSplit ? -q * kBiasRow : -(q >> 1) * kBiasRow + 4 * (q & 1)));
-          const float4 c = *reinterpret_cast<const float4*>(cv + 4 * q);
-          const float bb[4] = {b.x, b.y, b.z, b.w}, cc[4] = {c.x, c.y, c.z, c.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int j = 4 * q + e;
-            const float t = (__uint_as_float(sa[4 * qq + e]) * ri) * cc[e];  // tau log2e cos(q_i, k_j)
-            float x = (t + bb[e]) - li;
-            if (decltype(masked)::value && ((m >> j) & 1u)) x += kNeg;
-            const float pe = ex2(x);
-            const float w = pe * __uint_as_float(pa[4 * qq + e]);
-            Dp += w;
-            U = fmaf(w, t, U);
-            V = fmaf(pe, t, V);
-            sa[4 * qq + e] = __float_as_uint(pe);
-            pa[4 * qq + e] = __float_as_uint(w);
-          }
-        }
-      };
-      const bool wrap = kSplit && (rflags & 6);
-      const uint32_t m = wrap ? (((rflags & 2) ? mH : 0u) | ((rflags & 4) ? mW : 0u)) : 0u;
-      if (KO(4)) { }
-      else if (wrap) pass1(BoolTag<true>{}, IntTag<0>{}, m, sA, pA);
-      else pass1(BoolTag<false>{}, IntTag<0>{}, 0u, sA, pA);
-      tmem_wait_ld();  // chunk B has landed: all of S / dP of this pair is in registers
-      HV_REG_FENCE16(sB);
-      HV_REG_FENCE16(pB);
-      tc_fence_before();
-      __syncwarp();
-      if (warp == 8) TRACE(k, 7);
-      if (lane == 0) mbar_arrive(bar_sfree);
-      if (KO(4)) { }
-      else if (wrap) pass1(BoolTag<true>{}, IntTag<1>{}, m, sB, pB);
-      else pass1(BoolTag<false>{}, IntTag<1>{}, 0u, sB, pB);
-      // the two half-row threads of a query exchange their partial D through shared memory (warps w and w + 4)
-      dpart[(buf * 2 + half) * 128 + row] = Dp;
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
-      const float Di = Dp + dpart[(buf * 2 + (half ^ 1)) * 128 + row];
-      const float racc = fmaf(-Di, V, U);  // sum_j dS_ij t_ij over this half row: d(tau) and the dQ epilogue's q^.M
-      acc_tau += racc;
-      // pass 2: dS = P (dP - D) = w - D P, packed to bf16 together with P
-      uint32_t pp[16], dd[16];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        pp[e] = pack_bf16x2(__uint_as_float(sA[2 * e]), __uint_as_float(sA[2 * e + 1]));
-        dd[e] = pack_bf16x2(fmaf(-Di, __uint_as_float(sA[2 * e]), __uint_as_float(pA[2 * e])),
-                            fmaf(-Di, __uint_as_float(sA[2 * e + 1]), __uint_as_float(pA[2 * e + 1])));
-        pp[8 + e] = pack_bf16x2(__uint_as_float(sB[2 * e]), __uint_as_float(sB[2 * e + 1]));
-        dd[8 + e] = pack_bf16x2(fmaf(-Di, __uint_as_float(sB[2 * e]), __uint_as_float(pB[2 * e])),
-                                fmaf(-Di, __uint_as_float(sB[2 * e + 1]), __uint_as_float(pB[2 * e + 1])));
-      }
-      if (warp == 8) TRACE(k, 8);
-      if (k + 1 < npairs) fetch_a(k + 1);
-      if (k > 1) mbar_wait_fast(bar_stfree(buf), ((k - 2) >> 1) & 1);  // the MMAs of pair k-2 have read this buffer
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint32_t off = (uint32_t)(buf * 2 * kPdTile) + (uint32_t)(((4 * half + q) ^ (i & 7)) << 4);
-        sts128(p_row + off, make_uint4(pp[4 * q], pp[4 * q + 1], pp[4 * q + 2], pp[4 * q + 3]));
-        sts128(ds_row + off, make_uint4(dd[4 * q], dd[4 * q + 1], dd[4 * q + 2], dd[4 * q + 3]));
-      }
-      dots[(buf * 2 + half) * 128 + row] = racc;
-      fence_async_smem();
-      __syncwarp();
-      if (warp == 8) TRACE(k, 9);
-      if (lane == 0) mbar_arrive(bar_staged(buf));
-      if (k + 1 < npairs) {
-        tmem_wait_ld();
-        HV_REG_FENCE16(sA);
-        HV_REG_FENCE16(pA);
-        fetch_b();
-      }
-    }
-    // d(tau) = sum dS cos = sum dS t / (tau log2e); one shared-memory atomic per warp (a warp's 32 rows are one unit)
-    const float tot = warp_sum(acc_tau);
-    if (lane == 0) {
-      const float tu = __ldg(&tau[u == 0 ? work.head_a : work.head_b]) * kLog2e;
-      atomicAdd(reinterpret_cast<float*>(smem + kOffCol) + 64 + u, tot / tu);
-    }
-  } else {
-    // ------------------------------------------------------------------ epilogue warps: 16-19 dV, 20-23 dK, 24-27 dQ
-    // (one accumulator each, so the TMEM columns go back to the issuer after a single 32-column load)
-    auto epilogue = [&](auto role_tag) {
-    constexpr int role = decltype(role_tag)::value;  // 0 dV, 1 dK, 2 dQ
-    if (role == 0) reg_dealloc<48>(); else if (role == 1) reg_dealloc<64>(); else reg_alloc<88>();
-    const int quad = warp & 3;
-    const int row = quad * 32 + lane;
-    const int u = row >> 6, t = row & 63;
-    const int head = u == 0 ? work.head_a : work.head_b;
-    const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16);
-    const int sl = slotmap[t], ih = sl >> 3, iw = sl & 7;
-    const float tau_h = __ldg(&tau[head]);
-    const float inv_tl = 1.0f / (tau_h * kLog2e);
-    float csum[32];
-#pragma unroll
-    for (int e = 0; e < 32; ++e) csum[e] = 0.f;
+    if (role == 1 && npairs > 0) hat(0);
 
     for (int k = 0; k < npairs; ++k) {
       const int s = k % kStages;
-      mbar_wait(bar_acc, k & 1);  // sleeping wait (twelve warps mostly idle)
-      if (warp == 16) TRACE(k, 13);
+      if (role == 1 && k + 1 < npairs) hat(k + 1);
+      mbar_wait(bar_acc, k & 1);  // sleeping wait (these warps are mostly idle)
+      if (warp == 24) TRACE(k, 13);
       tc_fence_after();
       uint32_t a[32];
-      HV_TMEM_LD32(tl + (role == 0 ? kColDV : (role == 1 ? kColDK : kColDQ)) + 32 * u, a);
       const UnitGeo ug = geo[(k & 7) * 2 + u];
       int prow = ug.row0 + ih; if (prow >= g.H) prow -= g.H;
       int pcol = ug.col0 + iw; if (pcol >= g.W) pcol -= g.W;
       const int64_t tok = ((int64_t)ug.b * g.H + prow) * g.W + pcol;
-      bf16* drow = dqkv + tok * (3 * g.C) + head * 32 + (role == 0 ? 2 * g.C : (role == 1 ? g.C : 0));
+      bf16* drow = dqkv + tok * (3 * g.C) + head * 32 + (role == 1 ? g.C : 0);
       const bool valid = (ug.rflags & 1) && !KO(2);
-      float qdot = 0.f;
-      if (role == 2) {
-        const float* dp = reinterpret_cast<const float*>(smem + kOffDot) + (k & 1) * 256 + row;
-        qdot = (dp[0] + dp[128]) * inv_tl;
-      }
-      tmem_wait_ld();
-      HV_REG_FENCE32(a);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_accfree);
-      if (role == 0) {
+      if (role == 1) {  // dV first: pack and store, then the same registers take dK
+        HV_TMEM_LD32(tl + kColDV + 32 * u, a);
+        tmem_wait_ld();
+        HV_REG_FENCE32(a);
         if (valid) {
-          uint4* dst = reinterpret_cast<uint4*>(drow);
+          uint4* dst = reinterpret_cast<uint4*>(drow + g.C);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             uint4 v;
@@ -647,10 +635,20 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
             dst[q] = v;
           }
         }
-        continue;
       }
+      HV_TMEM_LD32(tl + (role == 1 ? kColDK : kColDQ) + 32 * u, a);
+      float qdot = 0.f;
+      if (role == 2) {
+        const float* dp = reinterpret_cast<const float*>(smem + kOffDot) + (k & 3) * 256 + row;
+        qdot = (dp[0] + dp[128]) * inv_tl;
+      }
+      tmem_wait_ld();
+      HV_REG_FENCE32(a);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_accfree);
       // projection of the gradient of the normalised row back to the raw row: d x = sc (M - (x^ . M) x^)
-      const float* vec = vecs + s * 3 * 128;
+      const float* vec = vecs + s * 4 * 128;
       const uint32_t tile = sb + kOffStage + s * kStage + ((role == 2 ? 0 : 2) + u) * kTile + t * 64;
       const float sc = role == 2 ? vec[row] * tau_h : vec[128 + row] * kLn2;  // tau / |q_i|  |  tau / |k_j| = c_j ln 2
       uint4* dst = reinterpret_cast<uint4*>(drow);
@@ -662,7 +660,7 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
           xh[4 * ch] = v.x; xh[4 * ch + 1] = v.y; xh[4 * ch + 2] = v.z; xh[4 * ch + 3] = v.w;
         }
         __syncwarp();
-        if (warp == 20) TRACE(k, 15);
+        if (warp == 24) TRACE(k, 15);
         if (lane == 0) mbar_arrive(bar_empty(s));  // last read of the stage by this warp
         float dot = 0.f;
 #pragma unroll
@@ -710,7 +708,7 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
       }
     }
     };
-    if (warp < 20) epilogue(IntTag<0>{}); else if (warp < 24) epilogue(IntTag<1>{}); else epilogue(IntTag<2>{});
+    if (warp < 28) epilogue(IntTag<1>{}); else epilogue(IntTag<2>{});
   }
   tc_fence_before();
   __syncthreads();
@@ -718,7 +716,7 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
   for (int idx = threadIdx.x; idx < 2 * 256; idx += kThreads) reinterpret_cast<float*>(smem + kOffBins)[idx] = 0.f;
   __syncthreads();
   // ---- d(bias): fold the 64 x 64 accumulators of the two units into the 225 table bins
-  if (warp >= 20 && warp < 24 && npairs > 0) {
+  if (warp >= 24 && warp < 28 && npairs > 0) {
     const int quad = warp & 3, row = quad * 32 + lane, u = row >> 6, t = row & 63;
     const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16);
     const int si = slotmap[t];
@@ -836,9 +834,9 @@ int wattn_tc64_bwd(const Geom& g, const void* qkv, const void* out, const void* 
     const int s = g.shift, wa = kWs - g.shift;
     const int bw[7] = {kWs, s ? wa : kWs, s ? s : kWs, s ? wa : kWs, s ? wa : kWs, s ? s : kWs, s ? s : kWs};
     const int bh[7] = {kWs, kWs, kWs, s ? wa : kWs, s ? s : kWs, s ? wa : kWs, s ? s : kWs};
-    const void* base[2] = {qkv, dout};
-    const int row_elems[2] = {3 * g.C, g.C};
-    for (int t = 0; t < 2; ++t)
+    const void* base[3] = {qkv, dout, out};
+    const int row_elems[3] = {3 * g.C, g.C, g.C};
+    for (int t = 0; t < 3; ++t)
       for (int i = 0; i < 7; ++i) {
         const int rc = make_map(&e.maps.m[t][i], base[t], g, row_elems[t], bw[i], bh[i]);
         if (rc) return rc;
