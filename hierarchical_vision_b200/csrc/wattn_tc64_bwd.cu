@@ -32,8 +32,12 @@ constexpr int kN = 64;
 constexpr int kWs = 8;
 constexpr int kTab = 225;
 constexpr int kTile = kN * 64;         // one (window, head) q / k / v / dO / o tile: 64 rows x 64 B (SWIZZLE_64B)
-constexpr int kStage = 10 * kTile;     // q_a q_b k_a k_b v_a v_b g_a g_b o_a o_b   (g = dO)
-constexpr int kStages = 3;
+// Two rings: v and o are dead as soon as dP and D exist (early in the life of a pair), q, k and dO live until the epilogue
+// has read the normalised rows.  Splitting them lets the long-lived ring be four deep in the same shared memory.
+constexpr int kStage = 6 * kTile;      // late ring:  q_a q_b k_a k_b g_a g_b   (g = dO)
+constexpr int kStages = 4;
+constexpr int kStageE = 4 * kTile;     // early ring: v_a v_b o_a o_b
+constexpr int kStagesE = 2;
 constexpr int kThreads = 1024;  // 32 warps
 constexpr int kPdTile = kN * 128;      // P or dS of one unit: 64 rows x 128 B (SWIZZLE_128B)
 constexpr int kBiasRow = 20;           // floats per table row (15 + alignment slack)
@@ -41,7 +45,8 @@ constexpr int kBiasCopy = 328;         // floats per alignment copy: >= 15 * 20 
 
 // ---- shared memory map (dynamic, 1024-byte aligned base)
 constexpr int kOffStage = 0;
-constexpr int kOffP = kOffStage + kStages * kStage;       // [2 buffers][2 units][64][128 B]
+constexpr int kOffStageE = kOffStage + kStages * kStage;
+constexpr int kOffP = kOffStageE + kStagesE * kStageE;    // [2 buffers][2 units][64][128 B]
 constexpr int kOffDS = kOffP + 4 * kPdTile;
 constexpr int kOffEye = kOffDS + 4 * kPdTile;             // 64 x 64 bf16 identity (SWIZZLE_128B)
 constexpr int kOffBias = kOffEye + kPdTile;               // [2 units][4 copies][kBiasCopy] float
@@ -52,7 +57,7 @@ constexpr int kOffBins = kOffP;                           // [2][256] float: d(b
 constexpr int kOffGeo = kOffCol + (2 * 32 + 4) * 4;       // [8][2] UnitGeo
 constexpr int kOffSlotMap = kOffGeo + 8 * 2 * 16;         // [64] bytes
 constexpr int kOffBar = kOffSlotMap + 64;
-constexpr int kNumBars = 5 * kStages + 8;
+constexpr int kNumBars = 5 * kStages + 8 + 2 * kStagesE;
 constexpr int kOffTmem = kOffBar + kNumBars * 8;
 constexpr int kSmem = kOffTmem + 16;
 static_assert(kOffP % 1024 == 0 && kOffBias % 16 == 0 && kOffBar % 8 == 0, "shared-memory alignment");
@@ -167,7 +172,9 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
   auto bar_sdp = [&](int s) { return bar0 + 8 * (4 * kStages + s); };
   const uint32_t bar_acc = bar0 + 8 * (5 * kStages + 1);
   const uint32_t bar_accfree = bar0 + 8 * (5 * kStages + 2);
-  auto bar_sfree = [&](int b) { return bar0 + 8 * (5 * kStages + (b ? 0 : 7)); };  // S / dP buffer b read by its softmax group
+  auto bar_sfree = [&](int b) { return bar0 + 8 * (5 * kStages + (b ? 0 : 7)); };
+  auto bar_fullE = [&](int s) { return bar0 + 8 * (5 * kStages + 8 + s); };
+  auto bar_emptyE = [&](int s) { return bar0 + 8 * (5 * kStages + 8 + kStagesE + s); };  // S / dP buffer b read by its softmax group
   auto bar_staged = [&](int b) { return bar0 + 8 * (5 * kStages + 3 + b); };  // P / dS staging buffer b written
   auto bar_stfree = [&](int b) { return bar0 + 8 * (5 * kStages + 5 + b); };  // ... and read by the MMAs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmem);
@@ -182,8 +189,12 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
       mbar_init(bar_full(s), 1);
       mbar_init(bar_empty(s), 8);  // the eight epilogue warps
       mbar_init(bar_pre(s), 4);
-      mbar_init(bar_hat(s), 4);
+      mbar_init(bar_hat(s), 8);
       mbar_init(bar_sdp(s), 1);
+    }
+    for (int s = 0; s < kStagesE; ++s) {
+      mbar_init(bar_fullE(s), 1);
+      mbar_init(bar_emptyE(s), 5);  // the four pre-pass warps (o, for D) and the commit behind the dP MMAs (v)
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_staged(b), 8);
@@ -240,8 +251,9 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
     if (warp == 0) {
       // ---------------------------------------------------------------- TMA producer: lane t < 8 loads tile t of the stage
       for (int k = 0; k < npairs; ++k) {
-        const int s = k % kStages;
+        const int s = k % kStages, se = k % kStagesE;
         mbar_wait(bar_empty(s), ((k / kStages) & 1) ^ 1);
+        mbar_wait(bar_emptyE(se), ((k / kStagesE) & 1) ^ 1);
         TRACE(k, 0);
         const int which = lane & 1, kind = lane >> 1;  // kind: 0 q, 1 k, 2 v, 3 dO, 4 o
         bool valid;
@@ -257,14 +269,19 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
           geo[(k & 7) * 2 + which] = ug;
         }
         __syncwarp();
-        if (lane == 0) mbar_expect_tx(bar_full(s), KO(1) ? 0 : kStage);
+        if (lane == 0) {
+          mbar_expect_tx(bar_full(s), KO(1) ? 0 : kStage);
+          mbar_expect_tx(bar_fullE(se), KO(1) ? 0 : kStageE);
+        }
         __syncwarp();
         if (lane < 10 && !KO(1)) {
           const int head = which == 0 ? work.head_a : work.head_b;
           const int tsr = kind < 3 ? 0 : (kind == 3 ? 1 : 2);
           const int c0 = (kind < 3 ? kind * g.C : 0) + head * 32;
-          const uint32_t dst = sb + kOffStage + s * kStage + lane * kTile;
-          const uint32_t bar = bar_full(s);
+          const bool early = kind == 2 || kind == 4;  // v, o
+          const int tidx = (kind == 0 ? 0 : (kind == 1 ? 2 : (kind == 3 ? 4 : (kind == 2 ? 0 : 2)))) + which;
+          const uint32_t dst = early ? sb + kOffStageE + se * kStageE + tidx * kTile : sb + kOffStage + s * kStage + tidx * kTile;
+          const uint32_t bar = early ? bar_fullE(se) : bar_full(s);
           const CUtensorMap* mm = maps.m[tsr];
           if (!kSplit) {
             tma_load_4d(dst, &mm[0], bar, c0, col0, row0, b);
@@ -289,15 +306,16 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
       // ---------------------------------------------------------------- issuer of S = Q K^T and dP = dO V^T
       const uint32_t id = idesc_bf16(64, 64, 0, 0);
       const uint64_t d_q = smem_desc(sb + kOffStage, 16, 512, 4), d_k = smem_desc(sb + kOffStage + 2 * kTile, 16, 512, 4);
-      const uint64_t d_v = smem_desc(sb + kOffStage + 4 * kTile, 16, 512, 4), d_g = smem_desc(sb + kOffStage + 6 * kTile, 16, 512, 4);
+      const uint64_t d_v = smem_desc(sb + kOffStageE, 16, 512, 4), d_g = smem_desc(sb + kOffStage + 4 * kTile, 16, 512, 4);
       for (int k = 0; k < npairs; ++k) {
-        const int s = k % kStages, buf = k & 1;
+        const int s = k % kStages, se = k % kStagesE, buf = k & 1;
         mbar_wait_fast(bar_full(s), (k / kStages) & 1);
+        mbar_wait_fast(bar_fullE(se), (k / kStagesE) & 1);
         TRACE(k, 1);
         if (k > 1) mbar_wait_fast(bar_sfree(buf), ((k >> 1) - 1) & 1);  // the group of pair k-2 has read this S / dP buffer
         tc_fence_after();
         if (elect_one()) {
-          const uint64_t so = (uint64_t)((s * kStage) >> 4);
+          const uint64_t so = (uint64_t)((s * kStage) >> 4), soe = (uint64_t)((se * kStageE) >> 4);
 #pragma unroll
           for (int u = 0; u < 2; ++u) {  // unit u: tiles q_u, k_u (one tile = 4 KB further), accumulator lanes + 16 u
             const uint32_t dl = (uint32_t)(16 * u) << 16;
@@ -307,9 +325,10 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
               umma_ss(tmem + dl + kColS + 64 * buf, d_q + so + uo + 2 * kk, d_k + so + uo + 2 * kk, id, kk > 0);
 #pragma unroll
             for (int kk = 0; kk < 2; ++kk)
-              umma_ss(tmem + dl + kColDP + 64 * buf, d_g + so + uo + 2 * kk, d_v + so + uo + 2 * kk, id, kk > 0);
+              umma_ss(tmem + dl + kColDP + 64 * buf, d_g + so + uo + 2 * kk, d_v + soe + uo + 2 * kk, id, kk > 0);
           }
           umma_commit(bar_sdp(s));
+          umma_commit(bar_emptyE(se));  // v is dead once dP exists
           TRACE(k, 2);
         }
         __syncwarp();
@@ -326,7 +345,7 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
       const uint64_t b_eye = smem_desc(sb + kOffEye, 16, 1024, 2);
       // B, MN-major view of two adjacent 64 x 64-byte tiles (units a | b): 32 channels = one 64-byte atom, unit b 4 KB further
       const uint64_t b_q = smem_desc(sb + kOffStage, 4096, 512, 4), b_k = smem_desc(sb + kOffStage + 2 * kTile, 4096, 512, 4);
-      const uint64_t b_g = smem_desc(sb + kOffStage + 6 * kTile, 4096, 512, 4);
+      const uint64_t b_g = smem_desc(sb + kOffStage + 4 * kTile, 4096, 512, 4);
       for (int k = 0; k < npairs; ++k) {
         const int s = k % kStages;
         const int buf = k & 1;
@@ -374,8 +393,9 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
     const int lhead = lu == 0 ? work.head_a : work.head_b;
 
     auto pre = [&](int k) {
-      const int s = k % kStages;
+      const int s = k % kStages, se = k % kStagesE;
       mbar_wait(bar_full(s), (k / kStages) & 1);  // sleeping wait: polling would take issue slots from the softmax warps
+      mbar_wait(bar_fullE(se), (k / kStagesE) & 1);
       const uint32_t st = sb + kOffStage + s * kStage;
       float* vec = vecs + s * 4 * 128;
       // lse of the pair's rows (1e30 for the padding unit of an odd tail: P = dS = 0 there); the load is issued first and
@@ -383,7 +403,7 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
       const int rf = geo[(k & 7) * 2 + lu].rflags;
       const float lse_v = (rf & 1) ? __ldg(&lse[((int64_t)(rf >> 3) * g.heads + lhead) * kN + lslot]) : 1e30f;
       const uint32_t tile = st + (2 * part + u) * kTile;
-      const uint32_t gt = st + (6 + u) * kTile, ot = st + (8 + u) * kTile;
+      const uint32_t gt = st + (4 + u) * kTile, ot = sb + kOffStageE + se * kStageE + (2 + u) * kTile;
 #pragma unroll
       for (int bp = 0; bp < 2; ++bp) {
         uint32_t x[2][2][4];
@@ -433,7 +453,10 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
       vec[3 * 128 + lrow] = lse_v;
       __syncwarp();
       if (warp == 4) TRACE(k, 3);
-      if (lane == 0) mbar_arrive(bar_pre(s));
+      if (lane == 0) {
+        mbar_arrive(bar_pre(s));
+        mbar_arrive(bar_emptyE(se));  // o is dead once D exists
+      }
     };
     for (int k = 0; k < npairs; ++k) pre(k);
 
@@ -565,10 +588,10 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
     float csum[32];
 #pragma unroll
     for (int e = 0; e < 32; ++e) csum[e] = 0.f;
-    // In-place normalisation of one q / k tile per dV+dK warp once S has been computed from the raw tile (q^ = q / |q|,
-    // k^ = k / |k|): done here, one pair ahead of this warp's epilogue work, so that it never waits behind the pre-pass
-    // of a later pair and the output MMAs find their B operands ready
-    const int hpart = quad >> 1, hu = quad & 1;
+    // In-place normalisation of the q / k tiles once S has been computed from the raw tiles (q^ = q / |q|, k^ = k / |k|):
+    // half a tile (one row per lane) per epilogue warp, one pair ahead and right after the accumulators of the current
+    // pair have been handed back, so that neither the pre-pass nor the epilogue arithmetic sits in front of it
+    const int hw = warp - 24, htile = hw >> 1, hpart = htile >> 1, hu = htile & 1, hrow = 32 * (hw & 1) + lane;
     const float inv_mult = hpart == 0 ? 1.0f : 1.0f / (__ldg(&tau[hu == 0 ? work.head_a : work.head_b]) * kLog2e);
     auto hat = [&](int k) {
       const int s = k % kStages;
@@ -577,39 +600,30 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
       const uint32_t tile = sb + kOffStage + s * kStage + (2 * hpart + hu) * kTile;
       const float* vec = vecs + s * 4 * 128 + hpart * 128 + 64 * hu;
       if (!KO(16)) {
-      uint4 v[2][4];
+        uint4 v[4];
 #pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        const int row = lane + 32 * rr;
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) v[rr][ch] = lds128(tile + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
-      }
-#pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        const int row = lane + 32 * rr;
-        const float sc = vec[row] * inv_mult;
+        for (int ch = 0; ch < 4; ++ch) v[ch] = lds128(tile + hrow * 64 + ((ch ^ ((hrow >> 1) & 3)) << 4));
+        const float sc = vec[hrow] * inv_mult;
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-          uint4 w = v[rr][ch];
+          uint4 w = v[ch];
           w.x = pack_bf16x2(bf16lo_to_f32(w.x) * sc, bf16hi_to_f32(w.x) * sc);
           w.y = pack_bf16x2(bf16lo_to_f32(w.y) * sc, bf16hi_to_f32(w.y) * sc);
           w.z = pack_bf16x2(bf16lo_to_f32(w.z) * sc, bf16hi_to_f32(w.z) * sc);
           w.w = pack_bf16x2(bf16lo_to_f32(w.w) * sc, bf16hi_to_f32(w.w) * sc);
-          sts128(tile + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4), w);
+          sts128(tile + hrow * 64 + ((ch ^ ((hrow >> 1) & 3)) << 4), w);
         }
-      }
       }
       fence_async_smem();
       __syncwarp();
       if (warp == 24) TRACE(k, 4);
       if (lane == 0) mbar_arrive(bar_hat(s));
     };
-    if (role == 1 && npairs > 0) hat(0);
+    if (npairs > 0) hat(0);
 
     for (int k = 0; k < npairs; ++k) {
       const int s = k % kStages;
-      if (role == 1 && k + 1 < npairs) hat(k + 1);
-      mbar_wait(bar_acc, k & 1);  // sleeping wait (these warps are mostly idle)
+      mbar_wait_fast(bar_acc, k & 1);
       if (warp == 24) TRACE(k, 13);
       tc_fence_after();
       uint32_t a[32];
@@ -647,6 +661,7 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_accfree);
+      if (k + 1 < npairs) hat(k + 1);
       // projection of the gradient of the normalised row back to the raw row: d x = sc (M - (x^ . M) x^)
       const float* vec = vecs + s * 4 * 128;
       const uint32_t tile = sb + kOffStage + s * kStage + ((role == 2 ? 0 : 2) + u) * kTile + t * 64;
@@ -750,12 +765,13 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
 }
 
 // Sum the per-CTA partials.  CTA c of a same-window group holds heads (2 grp, 2 grp + 1) in units 0 / 1; the CTAs of the
-// cross group hold the last (odd) head in both units.
-__global__ void wattn_tc64_bwd_reduce_kernel(const float* __restrict__ ws_dbias, const float* __restrict__ ws_dtau,
-                                             const float* __restrict__ ws_colsum, BwdParams p,
-                                             float* __restrict__ dbias_table, float* __restrict__ dtau,
-                                             float* __restrict__ dq_colsum) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+// cross group hold the last (odd) head in both units.  One warp per output value: the lanes stride over the CTAs (a serial
+// loop over ~100 partial rows would cost more than the attention kernel's own tail).
+__global__ void __launch_bounds__(256) wattn_tc64_bwd_reduce_kernel(const float* __restrict__ ws_dbias, const float* __restrict__ ws_dtau,
+                                                                    const float* __restrict__ ws_colsum, BwdParams p,
+                                                                    float* __restrict__ dbias_table, float* __restrict__ dtau,
+                                                                    float* __restrict__ dq_colsum) {
+  const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int heads = p.g.heads, per_head = kTab + 1, n_tab = heads * per_head;
   int head, what, e = 0;  // what: 0 bias bin, 1 tau, 2 column sum
   if (idx < n_tab) {
@@ -776,9 +792,11 @@ __global__ void wattn_tc64_bwd_reduce_kernel(const float* __restrict__ ws_dbias,
     c0 = p.n_same * p.ctas_same; c1 = c0 + p.ctas_cross; u0 = 0; u1 = 1;
   }
   float s = 0.f;
-  for (int c = c0; c < c1; ++c)
+  for (int c = c0 + lane; c < c1; c += 32)
     for (int u = u0; u <= u1; ++u)
       s += what == 0 ? ws_dbias[((int64_t)c * 2 + u) * kTab + e] : (what == 1 ? ws_dtau[c * 2 + u] : ws_colsum[c * 64 + u * 32 + e]);
+  s = warp_sum(s);
+  if (lane != 0) return;
   if (what == 0) dbias_table[e * heads + head] = s;
   else if (what == 1) dtau[head] = s;
   else dq_colsum[idx - n_tab] = s;
@@ -910,7 +928,7 @@ int wattn_tc64_bwd(const Geom& g, const void* qkv, const void* out, const void* 
   }
 #endif
   const int n = g.heads * (kTab + 1) + g.C;
-  wattn_tc64_bwd_reduce_kernel<<<(n + 127) / 128, 128, 0, st>>>(ws_dbias, ws_dtau, ws_colsum, p, dbias_table, dtau, dq_colsum);
+  wattn_tc64_bwd_reduce_kernel<<<(n + 7) / 8, 256, 0, st>>>(ws_dbias, ws_dtau, ws_colsum, p, dbias_table, dtau, dq_colsum);
   HV_LAUNCH_OK("wattn_tc64_bwd_reduce_kernel");
   return HV_OK;
 }
