@@ -57,7 +57,7 @@ constexpr int kOffBins = kOffP;                           // [2][256] float: d(b
 constexpr int kOffGeo = kOffCol + (2 * 32 + 4) * 4;       // [8][2] UnitGeo
 constexpr int kOffSlotMap = kOffGeo + 8 * 2 * 16;         // [64] bytes
 constexpr int kOffBar = kOffSlotMap + 64;
-constexpr int kNumBars = 5 * kStages + 8 + 2 * kStagesE;
+constexpr int kNumBars = 5 * kStages + 10 + 2 * kStagesE;
 constexpr int kOffTmem = kOffBar + kNumBars * 8;
 constexpr int kSmem = kOffTmem + 16;
 static_assert(kOffP % 1024 == 0 && kOffBias % 16 == 0 && kOffBar % 8 == 0, "shared-memory alignment");
@@ -67,7 +67,9 @@ static_assert(kSmem <= 227 * 1024, "shared memory budget");
 // S and dP of a pair take 64 columns each: the two units are separate M = 64 MMAs whose accumulators interleave in the
 // 128 lanes (rows 16q .. 16q + 15 of unit a in lanes 32q .. 32q + 15, of unit b in lanes 32q + 16 .. 32q + 31; measured with
 // tools/probes/umma_m64_probe.cu) -- no wasted off-diagonal blocks, and room for two buffers
-constexpr int kColS = 0, kColDP = 128, kColDV = 256, kColDK = 320, kColDQ = 384, kColDB = 448;  // S, dP: + 64 * buffer
+constexpr int kColS = 0, kColDP = 128;                                  // + 64 * buffer (one per softmax group)
+constexpr int kColDV = 256, kColDK = 288, kColDQ = 320, kAccCols = 96;  // + 96 * buffer: M = 64 output MMAs, 32 columns each
+constexpr int kColDB = 448;
 
 struct BwdParams {
   Geom g;
@@ -170,11 +172,12 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
   auto bar_pre = [&](int s) { return bar0 + 8 * (2 * kStages + s); };
   auto bar_hat = [&](int s) { return bar0 + 8 * (3 * kStages + s); };
   auto bar_sdp = [&](int s) { return bar0 + 8 * (4 * kStages + s); };
-  const uint32_t bar_acc = bar0 + 8 * (5 * kStages + 1);
-  const uint32_t bar_accfree = bar0 + 8 * (5 * kStages + 2);
-  auto bar_sfree = [&](int b) { return bar0 + 8 * (5 * kStages + (b ? 0 : 7)); };
+  // accumulator buffer a (= pair parity): output MMAs complete / epilogue has pulled the accumulators out of TMEM
+  auto bar_acc = [&](int a) { return bar0 + 8 * (a ? 5 * kStages + 8 + 2 * kStagesE : 5 * kStages + 1); };
+  auto bar_accfree = [&](int a) { return bar0 + 8 * (a ? 5 * kStages + 9 + 2 * kStagesE : 5 * kStages + 2); };
+  auto bar_sfree = [&](int b) { return bar0 + 8 * (5 * kStages + (b ? 0 : 7)); };  // S / dP buffer b read by its softmax group
   auto bar_fullE = [&](int s) { return bar0 + 8 * (5 * kStages + 8 + s); };
-  auto bar_emptyE = [&](int s) { return bar0 + 8 * (5 * kStages + 8 + kStagesE + s); };  // S / dP buffer b read by its softmax group
+  auto bar_emptyE = [&](int s) { return bar0 + 8 * (5 * kStages + 8 + kStagesE + s); };
   auto bar_staged = [&](int b) { return bar0 + 8 * (5 * kStages + 3 + b); };  // P / dS staging buffer b written
   auto bar_stfree = [&](int b) { return bar0 + 8 * (5 * kStages + 5 + b); };  // ... and read by the MMAs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmem);
@@ -201,8 +204,10 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
       mbar_init(bar_stfree(b), 1);
       mbar_init(bar_sfree(b), 8);
     }
-    mbar_init(bar_acc, 1);
-    mbar_init(bar_accfree, 8);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_acc(a), 1);
+      mbar_init(bar_accfree(a), 8);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -335,42 +340,51 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
       }
     } else if (warp == 2) {
       // ---------------------------------------------------------------- issuer of dV, dK^, dQ^, dBias
-      const uint32_t id_t = idesc_bf16(128, 64, 1, 1);   // A = P^T / dS^T (MN-major), B = dO / q^ (MN-major)
-      const uint32_t id_q = idesc_bf16(128, 64, 0, 1);   // A = dS (K-major), B = k^ (MN-major)
-      const uint32_t id_b = idesc_bf16(128, 64, 0, 0);   // A = dS (K-major), B = identity
-      // A, MN-major view of the [query][key] tiles: 64 keys = one 128-byte atom, unit b 8 KB further (LBO), 8 queries = 1 KB (SBO)
-      const uint64_t a_pt = smem_desc(sb + kOffP, 2 * 4096, 1024, 2), a_dst = smem_desc(sb + kOffDS, 2 * 4096, 1024, 2);
-      // A, K-major view: 128 query rows of 128 B, 8-row groups 1 KB apart
+      // dV, dK^, dQ^: one M = 64 MMA chain per unit (accumulator rows interleave in the lanes like S / dP: unit b at lane
+      // offset 16), 32 columns each and two accumulator buffers, so the MMAs of pair k+1 never wait for the epilogue of
+      // pair k.  dBias stays one stacked M = 128 chain accumulating over all pairs.
+      const uint32_t id_t = idesc_bf16(64, 32, 1, 1);    // A = P^T / dS^T (MN-major), B = dO / q^ (MN-major)
+      const uint32_t id_q = idesc_bf16(64, 32, 0, 1);    // A = dS (K-major), B = k^ (MN-major)
+      const uint32_t id_b = idesc_bf16(128, 64, 0, 0);   // A = dS of both units (K-major), B = identity
+      // A, MN-major view of a [query][key] tile: 64 keys = one 128-byte atom, 8 queries = 1 KB (SBO)
+      const uint64_t a_pt = smem_desc(sb + kOffP, 16, 1024, 2), a_dst = smem_desc(sb + kOffDS, 16, 1024, 2);
+      // A, K-major view: query rows of 128 B, 8-row groups 1 KB apart (unit b's tile follows unit a's: 128 rows for dBias)
       const uint64_t a_ds = smem_desc(sb + kOffDS, 16, 1024, 2);
       const uint64_t b_eye = smem_desc(sb + kOffEye, 16, 1024, 2);
-      // B, MN-major view of two adjacent 64 x 64-byte tiles (units a | b): 32 channels = one 64-byte atom, unit b 4 KB further
-      const uint64_t b_q = smem_desc(sb + kOffStage, 4096, 512, 4), b_k = smem_desc(sb + kOffStage + 2 * kTile, 4096, 512, 4);
-      const uint64_t b_g = smem_desc(sb + kOffStage + 4 * kTile, 4096, 512, 4);
+      // B, MN-major view of a 64 x 64-byte tile: 32 channels = one 64-byte atom, 8 tokens = 512 B (SBO)
+      const uint64_t b_q = smem_desc(sb + kOffStage, 16, 512, 4), b_k = smem_desc(sb + kOffStage + 2 * kTile, 16, 512, 4);
+      const uint64_t b_g = smem_desc(sb + kOffStage + 4 * kTile, 16, 512, 4);
       for (int k = 0; k < npairs; ++k) {
         const int s = k % kStages;
         const int buf = k & 1;
         mbar_wait_fast(bar_staged(buf), (k >> 1) & 1);
         TRACE(k, 10);
         mbar_wait_fast(bar_hat(s), (k / kStages) & 1);
-        if (k > 0) mbar_wait_fast(bar_accfree, (k - 1) & 1);
+        if (k > 1) mbar_wait_fast(bar_accfree(buf), ((k >> 1) - 1) & 1);  // epilogue of pair k-2 has drained this buffer
         tc_fence_after();
         if (elect_one()) {
           const uint64_t so = (uint64_t)((s * kStage) >> 4), bo = (uint64_t)(buf * ((2 * kPdTile) >> 4));
+          const uint32_t acc = tmem + kAccCols * buf;
           if (!KO(8)) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)  // 16 queries per step: A += 2 KB, B += 1 KB
-            umma_ss(tmem + kColDV, a_pt + bo + (uint64_t)(128 * ks), b_g + so + (uint64_t)(64 * ks), id_t, ks > 0);
+            for (int u = 0; u < 2; ++u) {
+              const uint32_t dl = (uint32_t)(16 * u) << 16;
+              const uint64_t ao = bo + (uint64_t)(u * (kPdTile >> 4)), to = so + (uint64_t)(u * (kTile >> 4));
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_ss(tmem + kColDK, a_dst + bo + (uint64_t)(128 * ks), b_q + so + (uint64_t)(64 * ks), id_t, ks > 0);
+              for (int ks = 0; ks < 4; ++ks)  // 16 queries per step: A += 2 KB, B += 1 KB
+                umma_ss(acc + dl + kColDV, a_pt + ao + (uint64_t)(128 * ks), b_g + to + (uint64_t)(64 * ks), id_t, ks > 0);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)  // 16 keys per step: A += 32 B inside the swizzle atom, B += 1 KB
-            umma_ss(tmem + kColDQ, a_ds + bo + (uint64_t)(2 * ks), b_k + so + (uint64_t)(64 * ks), id_q, ks > 0);
+              for (int ks = 0; ks < 4; ++ks)
+                umma_ss(acc + dl + kColDK, a_dst + ao + (uint64_t)(128 * ks), b_q + to + (uint64_t)(64 * ks), id_t, ks > 0);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_ss(tmem + kColDB, a_ds + bo + (uint64_t)(2 * ks), b_eye + (uint64_t)(2 * ks), id_b, (k > 0 || ks > 0) ? 1u : 0u);
+              for (int ks = 0; ks < 4; ++ks)  // 16 keys per step: A += 32 B inside the swizzle atom, B += 1 KB
+                umma_ss(acc + dl + kColDQ, a_ds + ao + (uint64_t)(2 * ks), b_k + to + (uint64_t)(64 * ks), id_q, ks > 0);
+            }
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_ss(tmem + kColDB, a_ds + bo + (uint64_t)(2 * ks), b_eye + (uint64_t)(2 * ks), id_b, (k > 0 || ks > 0) ? 1u : 0u);
           }
-          umma_commit(bar_acc);
+          umma_commit(bar_acc(buf));
           umma_commit(bar_stfree(buf));
           TRACE(k, 12);
         }
@@ -578,8 +592,8 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
     constexpr int role = decltype(role_tag)::value;  // 1 dV + dK, 2 dQ
     if (role == 2) reg_alloc<88>();
     const int quad = warp & 3;
-    const int row = quad * 32 + lane;
-    const int u = row >> 6, t = row & 63;
+    const int u = lane >> 4, t = 16 * quad + (lane & 15);  // M = 64 accumulator layout: lanes 0-15 unit a, 16-31 unit b
+    const int row = 64 * u + t;
     const int head = u == 0 ? work.head_a : work.head_b;
     const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16);
     const int sl = slotmap[t], ih = sl >> 3, iw = sl & 7;
@@ -623,7 +637,8 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
 
     for (int k = 0; k < npairs; ++k) {
       const int s = k % kStages;
-      mbar_wait_fast(bar_acc, k & 1);
+      const int ab = k & 1;
+      mbar_wait_fast(bar_acc(ab), (k >> 1) & 1);
       if (warp == 24) TRACE(k, 13);
       tc_fence_after();
       uint32_t a[32];
@@ -634,7 +649,7 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
       bf16* drow = dqkv + tok * (3 * g.C) + head * 32 + (role == 1 ? g.C : 0);
       const bool valid = (ug.rflags & 1) && !KO(2);
       if (role == 1) {  // dV first: pack and store, then the same registers take dK
-        HV_TMEM_LD32(tl + kColDV + 32 * u, a);
+        HV_TMEM_LD32(tl + kAccCols * ab + kColDV, a);
         tmem_wait_ld();
         HV_REG_FENCE32(a);
         if (valid) {
@@ -650,7 +665,7 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
           }
         }
       }
-      HV_TMEM_LD32(tl + (role == 1 ? kColDK : kColDQ) + 32 * u, a);
+      HV_TMEM_LD32(tl + kAccCols * ab + (role == 1 ? kColDK : kColDQ), a);
       float qdot = 0.f;
       if (role == 2) {
         const float* dp = reinterpret_cast<const float*>(smem + kOffDot) + (k & 3) * 256 + row;
@@ -660,7 +675,7 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
       HV_REG_FENCE32(a);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_accfree);
+      if (lane == 0) mbar_arrive(bar_accfree(ab));
       if (k + 1 < npairs) hat(k + 1);
       // projection of the gradient of the normalised row back to the raw row: d x = sc (M - (x^ . M) x^)
       const float* vec = vecs + s * 4 * 128;
@@ -718,8 +733,8 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
       float* col = reinterpret_cast<float*>(smem + kOffCol) + u * 32;
 #pragma unroll
       for (int e = 0; e < 32; ++e) {
-        const float v = warp_sum(csum[e]);
-        if (lane == 0) atomicAdd(&col[e], v);
+        const float v = group_sum<16>(csum[e]);  // lanes 0-15 / 16-31 are rows of unit a / b
+        if ((lane & 15) == 0) atomicAdd(&col[e], v);
       }
     }
     };
