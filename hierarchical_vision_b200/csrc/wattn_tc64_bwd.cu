@@ -506,6 +506,31 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
     const uint32_t tS = tl + kColS + 64 * grp + 32 * half, tP = tl + kColDP + 64 * grp + 32 * half;
     float acc_tau = 0.f;
     float* dots = reinterpret_cast<float*>(smem + kOffDot);
+    // In-place normalisation of the q / k tiles of the group's own pair once S has been computed from the raw tiles
+    // (q^ = q / |q|, k^ = k / |k|): half a tile (one row per lane) per warp, after the group's own arithmetic and under the
+    // same fence.proxy.async as its staging stores -- independent of the accumulator / epilogue chain
+    const int hw = 4 * half + quad, htile = hw >> 1, hpart = htile >> 1, hu = htile & 1, hrow = 32 * (hw & 1) + lane;
+    const float inv_mult = hpart == 0 ? 1.0f : 1.0f / (__ldg(&tau[hu == 0 ? work.head_a : work.head_b]) * kLog2e);
+    auto hat = [&](int k) {
+      const int s = k % kStages;
+      const uint32_t tile = sb + kOffStage + s * kStage + (2 * hpart + hu) * kTile;
+      const float* vec = vecs + s * 4 * 128 + hpart * 128 + 64 * hu;
+      if (!KO(16)) {
+        uint4 v[4];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) v[ch] = lds128(tile + hrow * 64 + ((ch ^ ((hrow >> 1) & 3)) << 4));
+        const float sc = vec[hrow] * inv_mult;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          uint4 w = v[ch];
+          w.x = pack_bf16x2(bf16lo_to_f32(w.x) * sc, bf16hi_to_f32(w.x) * sc);
+          w.y = pack_bf16x2(bf16lo_to_f32(w.y) * sc, bf16hi_to_f32(w.y) * sc);
+          w.z = pack_bf16x2(bf16lo_to_f32(w.z) * sc, bf16hi_to_f32(w.z) * sc);
+          w.w = pack_bf16x2(bf16lo_to_f32(w.w) * sc, bf16hi_to_f32(w.w) * sc);
+          sts128(tile + hrow * 64 + ((ch ^ ((hrow >> 1) & 3)) << 4), w);
+        }
+      }
+    };
 
     for (int k = grp; k < npairs; k += 2) {
       const int s = k % kStages;
@@ -575,10 +600,14 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
       if (warp == 8) TRACE(k, 8);
       acc_tau += racc;
       dots[((k & 3) * 2 + half) * 128 + row] = racc;
+      hat(k);
       fence_async_smem();
       __syncwarp();
       if (warp == 8) TRACE(k, 9);
-      if (lane == 0) mbar_arrive(bar_staged(grp));
+      if (lane == 0) {
+        mbar_arrive(bar_staged(grp));
+        mbar_arrive(bar_hat(s));
+      }
     }
     // d(tau) = sum dS cos = sum dS t / (tau log2e); lanes 0-15 / 16-31 of a warp belong to unit a / b
     const float tot = group_sum<16>(acc_tau);
@@ -602,38 +631,6 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
     float csum[32];
 #pragma unroll
     for (int e = 0; e < 32; ++e) csum[e] = 0.f;
-    // In-place normalisation of the q / k tiles once S has been computed from the raw tiles (q^ = q / |q|, k^ = k / |k|):
-    // half a tile (one row per lane) per epilogue warp, one pair ahead and right after the accumulators of the current
-    // pair have been handed back, so that neither the pre-pass nor the epilogue arithmetic sits in front of it
-    const int hw = warp - 24, htile = hw >> 1, hpart = htile >> 1, hu = htile & 1, hrow = 32 * (hw & 1) + lane;
-    const float inv_mult = hpart == 0 ? 1.0f : 1.0f / (__ldg(&tau[hu == 0 ? work.head_a : work.head_b]) * kLog2e);
-    auto hat = [&](int k) {
-      const int s = k % kStages;
-      mbar_wait(bar_pre(s), (k / kStages) & 1);
-      mbar_wait(bar_sdp(s), (k / kStages) & 1);
-      const uint32_t tile = sb + kOffStage + s * kStage + (2 * hpart + hu) * kTile;
-      const float* vec = vecs + s * 4 * 128 + hpart * 128 + 64 * hu;
-      if (!KO(16)) {
-        uint4 v[4];
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) v[ch] = lds128(tile + hrow * 64 + ((ch ^ ((hrow >> 1) & 3)) << 4));
-        const float sc = vec[hrow] * inv_mult;
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          uint4 w = v[ch];
-          w.x = pack_bf16x2(bf16lo_to_f32(w.x) * sc, bf16hi_to_f32(w.x) * sc);
-          w.y = pack_bf16x2(bf16lo_to_f32(w.y) * sc, bf16hi_to_f32(w.y) * sc);
-          w.z = pack_bf16x2(bf16lo_to_f32(w.z) * sc, bf16hi_to_f32(w.z) * sc);
-          w.w = pack_bf16x2(bf16lo_to_f32(w.w) * sc, bf16hi_to_f32(w.w) * sc);
-          sts128(tile + hrow * 64 + ((ch ^ ((hrow >> 1) & 3)) << 4), w);
-        }
-      }
-      fence_async_smem();
-      __syncwarp();
-      if (warp == 24) TRACE(k, 4);
-      if (lane == 0) mbar_arrive(bar_hat(s));
-    };
-    if (npairs > 0) hat(0);
 
     for (int k = 0; k < npairs; ++k) {
       const int s = k % kStages;
@@ -676,7 +673,6 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_accfree(ab));
-      if (k + 1 < npairs) hat(k + 1);
       // projection of the gradient of the normalised row back to the raw row: d x = sc (M - (x^ . M) x^)
       const float* vec = vecs + s * 4 * 128;
       const uint32_t tile = sb + kOffStage + s * kStage + ((role == 2 ? 0 : 2) + u) * kTile + t * 64;
