@@ -257,8 +257,8 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
       // ---------------------------------------------------------------- TMA producer: lane t < 8 loads tile t of the stage
       for (int k = 0; k < npairs; ++k) {
         const int s = k % kStages, se = k % kStagesE;
-        mbar_wait(bar_empty(s), ((k / kStages) & 1) ^ 1);
-        mbar_wait(bar_emptyE(se), ((k / kStagesE) & 1) ^ 1);
+        mbar_wait_fast(bar_empty(s), ((k / kStages) & 1) ^ 1);
+        mbar_wait_fast(bar_emptyE(se), ((k / kStagesE) & 1) ^ 1);
         TRACE(k, 0);
         const int which = lane & 1, kind = lane >> 1;  // kind: 0 q, 1 k, 2 v, 3 dO, 4 o
         bool valid;
@@ -408,8 +408,8 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
 
     auto pre = [&](int k) {
       const int s = k % kStages, se = k % kStagesE;
-      mbar_wait(bar_full(s), (k / kStages) & 1);  // sleeping wait: polling would take issue slots from the softmax warps
-      mbar_wait(bar_fullE(se), (k / kStagesE) & 1);
+      mbar_wait_fast(bar_full(s), (k / kStages) & 1);
+      mbar_wait_fast(bar_fullE(se), (k / kStagesE) & 1);
       const uint32_t st = sb + kOffStage + s * kStage;
       float* vec = vecs + s * 4 * 128;
       // lse of the pair's rows (1e30 for the padding unit of an odd tail: P = dS = 0 there); the load is issued first and
