@@ -24,6 +24,7 @@ SIGNATURES = {
     "hv_window_attn_kernel_kind": (_I, [_I, _I, _I, _I]),
     "hv_window_attn_fwd_variant": (_I, [_I]),
     "hv_window_attn_bwd_variant": (_I, [_I]),
+    "hv_window_attn_stats_floats": (_S, [_I, _I, _I, _I, _I, _I, _I]),
     "hv_relative_position_index": (_I, [_I, _P]),
     "hv_shift_window_mask": (_I, [_I, _I, _I, _I, _P]),
     "hv_window_token_index": (_I, [_I, _I, _I, _I, _I, _P]),
@@ -63,8 +64,8 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.hv_abi_version() != 2:
-        raise RuntimeError(f"libhv_swin.so ABI version {lib.hv_abi_version()} != 2")
+    if lib.hv_abi_version() != 3:
+        raise RuntimeError(f"libhv_swin.so ABI version {lib.hv_abi_version()} != 3")
     _lib = lib
     return lib
 

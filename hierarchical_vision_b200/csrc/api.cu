@@ -21,9 +21,9 @@ size_t wattn_mma64_bwd_workspace_bytes(const Geom& g);
 bool wattn_tc64_bwd_supported(const Geom& g, int dtype);
 int wattn_bwd_variant_set(int v);
 size_t wattn_tc64_bwd_workspace_bytes(const Geom& g);
-int wattn_tc64_bwd(const Geom& g, const void* qkv, const void* out, const void* dout, const float* lse,
-                   const float* bias_table, const float* tau, void* dqkv, float* dbias_table, float* dtau,
-                   float* dq_colsum, void* workspace, size_t workspace_bytes, cudaStream_t st);
+int wattn_tc64_bwd(const Geom& g, const void* qkv, const void* dout, const float* stats, const float* bias_table,
+                   const float* tau, void* dqkv, float* dbias_table, float* dtau, float* dq_colsum, void* workspace,
+                   size_t workspace_bytes, cudaStream_t st);
 int wattn_mma64_fwd(const Geom& g, const void* qkv, const float* bias_table, const float* tau, const float* mask,
                     int mask_windows, void* out, float* lse, cudaStream_t st);
 int wattn_mma64_bwd(const Geom& g, const void* qkv, const void* out, const void* dout, const float* lse,
@@ -136,6 +136,13 @@ int hv_window_attn_kernel_kind(int C, int heads, int ws, int dtype) {
   return wattn_mma64_supported(g, dtype) ? 1 : 0;
 }
 
+size_t hv_window_attn_stats_floats(int B, int H, int W, int C, int heads, int ws, int dtype) {
+  if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || heads <= 0 || ws <= 0 || C % heads || H % ws || W % ws) return 0;
+  const Geom g = make_geom(B, H, W, C, heads, ws, 0);
+  const size_t plane = (size_t)g.B * g.nW * g.heads * g.N;
+  return wattn_mma64_supported(g, dtype) ? 3 * plane : plane;
+}
+
 int hv_relative_position_index(int ws, int64_t* out) {
   if (!out) HV_FAIL(HV_ERR_NULL, "hv_relative_position_index: out is NULL");
   if (ws <= 0) HV_FAIL(HV_ERR_SHAPE, "ws=%d", ws);
@@ -235,7 +242,7 @@ int hv_window_attn_bwd(const void* qkv, const void* out, const void* dout, const
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (mask == nullptr && wattn_mma64_supported(g, dtype)) {
     if (wattn_tc64_bwd_supported(g, dtype))
-      return wattn_tc64_bwd(g, qkv, out, dout, lse, bias_table, tau, dqkv, dbias_table, dtau, dq_colsum, workspace,
+      return wattn_tc64_bwd(g, qkv, dout, lse, bias_table, tau, dqkv, dbias_table, dtau, dq_colsum, workspace,
                             workspace_bytes, st);
     return wattn_mma64_bwd(g, qkv, out, dout, lse, bias_table, tau, mask, mask_windows, dqkv, dbias_table, dtau, dq_colsum,
                            workspace, workspace_bytes, st);

@@ -432,13 +432,22 @@ wattn_mma64_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ b
     {
       float s0, s1;
       rowdot_mma(ka, ka, lane, s0, s1);
+      const float c0 = tau2 * inv_norm(s0), c1 = tau2 * inv_norm(s1);
       if (t_ == 0) {
-        cvec[i0] = tau2 * inv_norm(s0);
-        cvec[i1] = tau2 * inv_norm(s1);
+        cvec[i0] = c0;
+        cvec[i1] = c1;
       }
       rowdot_mma(qa, qa, lane, s0, s1);
       r0 = inv_norm(s0);
       r1 = inv_norm(s1);
+      if (t_ == 0) {  // row scales beside the log-sum-exp (planes 1: r, 2: c) for the tcgen05 backward kernel
+        const int64_t plane = (int64_t)nrows * g.heads * kN;
+        float* sp = lse + plane + ((int64_t)row * g.heads + head) * kN;
+        sp[i0] = r0;
+        sp[i1] = r1;
+        sp[plane + i0] = c0;
+        sp[plane + i1] = c1;
+      }
     }
     named_bar_sync(1 + hh, 128);
 

@@ -69,6 +69,7 @@ struct TcParams {
   int ctas_same;     // CTAs per same-window group
   int ctas_cross;    // CTAs of the cross-window group
   int ko;            // HV_TC_TRACE builds only: knock-out bits for bottleneck experiments (results are wrong)
+  int64_t plane;     // floats per statistics plane (lse | r | c): B * nW * heads * 64
 };
 // box shapes (w, h): 0 full (8,8) | 1 (8,8-s) 2 (8,s) row wrap | 3 (8-s,8) 4 (s,8) column wrap | 5..8 corner
 struct TcMaps { CUtensorMap m[9]; };
@@ -396,6 +397,15 @@ wattn_tc64_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restri
         if (warp == 4) TRACE(k, 2);  // norm done
         mbar_arrive(bar_empty(s));
       }
+      // the row scales go out beside the log-sum-exp (planes 1: r_i = 1 / |q_i|, 2: c_j = tau log2e / |k_j|, slot order):
+      // the backward kernel reads them back instead of recomputing the norms from the tiles
+      const int rf = geo[(k & 7) * 2 + u].rflags;
+      if (rf & 1) {
+        float* sp = lse + (1 + part) * p.plane + ((int64_t)(rf >> 3) * g.heads + head) * kN;
+        const unsigned char* sm = slotmap + ((rf & 4) ? 64 : 0);
+        sp[sm[lane]] = vec[lane];
+        sp[sm[lane + 32]] = vec[lane + 32];
+      }
     }
   } else if (warp < 24) {
     // ------------------------------------------------------------------ softmax: 2 groups (alternate pairs) x 2 column
@@ -601,6 +611,7 @@ int wattn_tc64_fwd(const Geom& g, const void* qkv, const float* bias_table, cons
   p.n_same = g.heads / 2;
   p.has_cross = g.heads & 1;
   p.ko = 0;
+  p.plane = (int64_t)g.B * g.nW * g.heads * kN;
 #ifdef HV_TC_TRACE
   if (getenv("HV_TC_KO")) p.ko = atoi(getenv("HV_TC_KO"));
 #endif

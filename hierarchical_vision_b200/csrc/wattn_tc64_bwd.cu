@@ -1,27 +1,35 @@
 // tcgen05 / TMEM / TMA backward kernel of the fused shifted-window scaled-cosine attention, window 8x8 (N = 64), head
-// dim 32, bf16 (every stage of SwinV2-T).  Same contract as wattn_mma64_bwd (reference swinv2.py:210-263 differentiated;
-// qkv / dqkv (B, H*W, 3C), out / dout (B, H*W, C) in IMAGE token order, lse in log2 units, per-CTA partials of
-// d(bias table), d(tau) and the dq column sums folded by a second small kernel), different machine mapping:
+// dim 32, bf16 (every stage of SwinV2-T).  Reference swinv2.py:210-263 differentiated; qkv / dqkv (B, H*W, 3C) and dout
+// (B, H*W, C) in IMAGE token order; per-CTA partials of d(bias table), d(tau) and the dq column sums are folded by a
+// second small kernel.  Machine mapping:
 //
-//   * one thread per query row of a (window, head) unit, two units stacked into the 128 TMEM lanes.  The five GEMMs of
-//     the backward are tcgen05.mma with fp32 accumulators in tensor memory:
-//         S  = [Q_a; Q_b] [K_a; K_b]^T      dP = [dO_a; dO_b] [V_a; V_b]^T        (128 x 128 x 32, diagonal blocks used)
-//         dV = P^T dO      dK^ = dS^T Q^      dQ^ = dS K^      dBias += dS I        (128 x 64 x 64)
-//     P and dS = P o (dP - D) are written once to shared memory as a [query][key] bf16 tile (128-byte rows, SWIZZLE_128B):
-//     read MN-major it is the A operand P^T / dS^T, read K-major it is dS.  Nothing is transposed by threads, no
-//     fragment shuffles, and d(bias) accumulates over all windows of the CTA inside the tensor core (64 TMEM columns);
-//   * cosine attention: S uses the raw q, k tiles and is scaled by 1/|q_i| * tau/|k_j| in fp32 exactly like the
-//     forward kernels (so P matches the forward's lse); afterwards the q / k tiles are normalised IN PLACE (bf16) and
-//     serve as the B operands of dK^ / dQ^ and for the projection dq = tau/|q| (M - (q^.M) q^) in the epilogue;
-//   * cyclic shift + window partition = coordinates of 4-D TMA tile loads (as in wattn_tc64_fwd).  A shifted layer loads
-//     EVERY window as two column parts ([0, 8-s) and [8-s, 8)): one token order for all windows of the launch, so bias
-//     lookup, mask and the d(bias) accumulator are uniform and column-wrapped windows need no special case;
-//   * the continuous position bias is looked up from a Toeplitz table in shared memory (4 alignment copies of the
-//     15 x 15 table per head, 10 KB) instead of an expanded 64 x 64 matrix: 16-byte conflict-free loads, and the
-//     shared memory goes to a 4-deep ring of 40 KB stages;
-//   * warp roles (24 warps): 0 TMA producer | 1 issuer of S, dP | 2 issuer of dV, dK, dQ, dBias | 4-7 pre-pass (row
-//     norms, D = dO.o by tensor-pipe self products, lse; later the in-place normalisation) | 8-15 softmax / dS threads
-//     (half a logit row each) | 16-19 dV, dK epilogue | 20-23 dQ epilogue.  All hand-overs are mbarriers.
+//   * the cyclic shift + window partition is the coordinate of 4-D TMA tile LOADS (q, k, v, dO tiles of a (window, head)
+//     unit: 64 rows x 64 B, SWIZZLE_64B) and of 4-D TMA tile STORES: the epilogue writes dq / dk / dv over the q / k /
+//     dO tiles of the stage (same swizzled layout) and one warp hands them to `cp.async.bulk.tensor` with the same box
+//     geometry -- window_reverse + un-roll never exist as copies or as per-thread 64-byte global stores;
+//   * nothing is recomputed that the forward already had: the forward kernels save, beside the row log-sum-exp, the
+//     row scales r_i = 1 / |q_i| and c_j = tau log2e / |k_j| (three fp32 planes, 768 B per unit, fetched by 1-D bulk
+//     copies onto the stage's mbarrier), and D_i = sum_j P_ij dP_ij is formed by the softmax threads themselves (the
+//     reference's own softmax backward) -- no pre-pass over the tiles and the attention output `o` is never read;
+//   * all products are tcgen05.mma with fp32 accumulators in tensor memory.  S = Q K^T, dP = dO V^T, dV = P^T dO,
+//     dK^ = dS^T Q^, dQ^ = dS K^ are M = 64 MMAs, one chain per unit: the accumulator rows of an M = 64 MMA land in
+//     lanes 32 (r / 16) + r % 16 and a lane offset of 16 moves them to the other half of every 32-lane quadrant, so the
+//     two units of a pair interleave in the 128 lanes and share columns.  dBias += dS I accumulates over all windows
+//     of the CTA in 64 columns;
+//   * two softmax groups (8 warps each) work on alternate pairs.  A thread owns half a query row: pass 1 streams S and
+//     dP from TMEM 16 keys at a time, forms P (staged to shared memory as bf16, and kept packed), the partial sums of
+//     P dP, P dP t and P t (t = tau log2e cos); the two half-row owners swap their partial D through shared memory
+//     (64-thread named barrier); pass 2 forms dS = P (dP - D) from the packed registers and stages it.  P / dS tiles
+//     are [query][key] with 128-byte rows (SWIZZLE_128B): read MN-major they are the A operands P^T / dS^T, read
+//     K-major dS -- no thread transposes anything.  sum_j dS_ij t_ij = A1 - D A2 is the d(tau) contribution and the
+//     q^.M of the dQ epilogue;
+//   * after its own arithmetic the group normalises the q / k tiles of its pair in place (q^ = r q, k^ = k / |k|):
+//     the B operands of dK^ / dQ^ and the x^ of dx = scale (M - (x^.M) x^) in the epilogue;
+//   * one token order per launch: a shifted layer loads / stores EVERY window as two column parts [0, 8-s) | [8-s, 8)
+//     (2 boxes per tile, 4 on the bottom row); the position bias is a Toeplitz lookup (4 alignment copies of the
+//     15 x 15 table per head, 10 KB);
+//   * 28 warps: 0 TMA loads | 1 issuer of S, dP | 2 issuer of dV, dK^, dQ^, dBias | 3 TMA stores + dq column sums |
+//     4-19 softmax / dS (2 groups) | 20-23 dV, dK epilogue | 24-27 dQ epilogue.  All hand-overs are mbarriers.
 #include "hv_tc.cuh"
 
 namespace hv {
@@ -31,17 +39,17 @@ using namespace tc;
 constexpr int kN = 64;
 constexpr int kWs = 8;
 constexpr int kTab = 225;
-constexpr int kTile = kN * 64;         // one (window, head) q / k / v / dO / o tile: 64 rows x 64 B (SWIZZLE_64B)
-// Two rings: v and o are dead as soon as dP and D exist (early in the life of a pair), q, k and dO live until the epilogue
-// has read the normalised rows.  Splitting them lets the long-lived ring be four deep in the same shared memory.
+constexpr int kTile = kN * 64;         // one (window, head) q / k / v / dO tile: 64 rows x 64 B (SWIZZLE_64B)
+// Two rings: v is dead as soon as dP exists, q, k and dO live until the stores of dq, dk, dv have left the stage.
 constexpr int kStage = 6 * kTile;      // late ring:  q_a q_b k_a k_b g_a g_b   (g = dO)
 constexpr int kStages = 4;
-constexpr int kStageE = 4 * kTile;     // early ring: v_a v_b o_a o_b
-constexpr int kStagesE = 2;
-constexpr int kThreads = 1024;  // 32 warps
+constexpr int kStageE = 2 * kTile;     // early ring: v_a v_b
+constexpr int kStagesE = 3;
+constexpr int kThreads = 896;          // 28 warps
 constexpr int kPdTile = kN * 128;      // P or dS of one unit: 64 rows x 128 B (SWIZZLE_128B)
 constexpr int kBiasRow = 20;           // floats per table row (15 + alignment slack)
 constexpr int kBiasCopy = 328;         // floats per alignment copy: >= 15 * 20 and = 8 (mod 32) so 8 lanes hit 8 bank groups
+constexpr int kStatBytes = kN * 4;     // one plane (lse | r | c) of one unit
 
 // ---- shared memory map (dynamic, 1024-byte aligned base)
 constexpr int kOffStage = 0;
@@ -50,17 +58,18 @@ constexpr int kOffP = kOffStageE + kStagesE * kStageE;    // [2 buffers][2 units
 constexpr int kOffDS = kOffP + 4 * kPdTile;
 constexpr int kOffEye = kOffDS + 4 * kPdTile;             // 64 x 64 bf16 identity (SWIZZLE_128B)
 constexpr int kOffBias = kOffEye + kPdTile;               // [2 units][4 copies][kBiasCopy] float
-constexpr int kOffVec = kOffBias + 2 * 4 * kBiasCopy * 4; // [kStages][4: r, c, D, lse][128] float
-constexpr int kOffDot = kOffVec + kStages * 4 * 128 * 4;  // [4 pairs in flight][2 halves][128] float: sum_j dS_ij t_ij per half row
-constexpr int kOffCol = kOffDot + 4 * 2 * 128 * 4;        // [2][32] float dq column sums, [2] d(tau)
+constexpr int kOffVec = kOffBias + 2 * 4 * kBiasCopy * 4; // [kStages][3: lse, r, c][2 units][64] float, SLOT order
+constexpr int kOffDot = kOffVec + kStages * 3 * 128 * 4;  // [4 pairs in flight][2 halves][128] float: sum_j dS_ij t_ij per half row
+constexpr int kOffDpart = kOffDot + 4 * 2 * 128 * 4;      // [2 parities][2 groups][2 halves][128] float: partial D
+constexpr int kOffCol = kOffDpart + 2 * 2 * 2 * 128 * 4;  // [2][32] float dq column sums, [2] d(tau)
 constexpr int kOffBins = kOffP;                           // [2][256] float: d(bias) bins, after the main loop (aliases P)
 constexpr int kOffGeo = kOffCol + (2 * 32 + 4) * 4;       // [8][2] UnitGeo
 constexpr int kOffSlotMap = kOffGeo + 8 * 2 * 16;         // [64] bytes
 constexpr int kOffBar = kOffSlotMap + 64;
-constexpr int kNumBars = 5 * kStages + 10 + 2 * kStagesE;
+constexpr int kNumBars = 5 * kStages + 2 * kStagesE + 10;
 constexpr int kOffTmem = kOffBar + kNumBars * 8;
 constexpr int kSmem = kOffTmem + 16;
-static_assert(kOffP % 1024 == 0 && kOffBias % 16 == 0 && kOffBar % 8 == 0, "shared-memory alignment");
+static_assert(kOffP % 1024 == 0 && kOffBias % 16 == 0 && kOffVec % 16 == 0 && kOffBar % 8 == 0, "shared-memory alignment");
 static_assert(kSmem <= 227 * 1024, "shared memory budget");
 
 // TMEM columns
@@ -74,10 +83,10 @@ constexpr int kColDB = 448;
 struct BwdParams {
   Geom g;
   int n_same, has_cross, ctas_same, ctas_cross;
-  int ko;  // HV_TC_TRACE builds only: knock-out bits for bottleneck experiments (results are wrong)
+  int64_t plane;  // floats per plane of the forward's statistics: B * nW * heads * 64
 };
 // per tensor: [0] full (8, 8) | split order: [1] (wa, 8) [2] (s, 8) [3] (wa, wa) [4] (wa, s) [5] (s, wa) [6] (s, s)
-struct BwdMaps { CUtensorMap m[3][7]; };  // qkv, dout, out
+struct BwdMaps { CUtensorMap m[3][7]; };  // qkv, dout, dqkv
 
 struct CtaWork {
   int head_a, head_b, cross, first, stride, npairs;
@@ -118,6 +127,29 @@ __device__ __forceinline__ int tile_row_slot(int t, int shift) {
   return ih << 3 | iw;
 }
 
+// The TMA boxes of one tile: f(byte offset inside the tile, map index, image column, image row).  The same list drives
+// the loads of q / k / v / dO and the stores of dq / dk / dv.
+template <bool kSplit, typename F>
+__device__ __forceinline__ void for_each_box(const Geom& g, int col0, int row0, bool bottom, F&& f) {
+  if (!kSplit) {
+    f(0, 0, col0, row0);
+    return;
+  }
+  const int sh = g.shift, wa = kWs - g.shift;
+  int colb = col0 + wa;
+  if (colb >= g.W) colb -= g.W;
+  const int offb = kWs * wa * 64;
+  if (!bottom) {
+    f(0, 1, col0, row0);
+    f(offb, 2, colb, row0);
+  } else {
+    f(0, 3, col0, row0);
+    f(wa * wa * 64, 4, col0, 0);
+    f(offb, 5, colb, row0);
+    f(offb + sh * wa * 64, 6, colb, 0);
+  }
+}
+
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 |
 // version 1 << 46 | layout type << 61 (2: SWIZZLE_128B, 4: SWIZZLE_64B)
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t type) {
@@ -135,23 +167,11 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// diagonal of X Y^T for 16 rows x 32 bf16 held as two A fragments each (rows g, g + 8 of the block)
-__device__ __forceinline__ void rowdot_mma(const uint32_t (&x)[2][4], const uint32_t (&y)[2][4], float (&n0)[4], float (&n1)[4]) {
-#pragma unroll
-  for (int e = 0; e < 4; ++e) n0[e] = n1[e] = 0.f;
-  mma_bf16(n0, x[0], y[0][0], y[0][2]);
-  mma_bf16(n1, x[0], y[0][1], y[0][3]);
-  mma_bf16(n0, x[1], y[1][0], y[1][2]);
-  mma_bf16(n1, x[1], y[1][1], y[1][3]);
-}
-
 #ifdef HV_TC_TRACE
 __device__ long long* g_btrace = nullptr;  // [pairs][16 events] clock64 stamps of CTA 0
 #define TRACE(k, ev) do { if (blockIdx.x == 0 && lane == 0 && g_btrace && (k) < 64) g_btrace[(k) * 16 + (ev)] = clock64(); } while (0)
-#define KO(bit) (p.ko & (bit))
 #else
 #define TRACE(k, ev) do { } while (0)
-#define KO(bit) false
 #endif
 
 template <bool V> struct BoolTag { static constexpr bool value = V; };
@@ -159,27 +179,27 @@ template <int V> struct IntTag { static constexpr int value = V; };
 
 template <bool kSplit>
 __global__ void __launch_bounds__(kThreads, 1)
-wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restrict__ lse, const float* __restrict__ bias_table,
-                      const float* __restrict__ tau, bf16* __restrict__ dqkv, float* __restrict__ ws_dbias,
-                      float* __restrict__ ws_dtau, float* __restrict__ ws_colsum, int want_colsum, BwdParams p) {
+wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restrict__ stats, const float* __restrict__ bias_table,
+                      const float* __restrict__ tau, float* __restrict__ ws_dbias, float* __restrict__ ws_dtau,
+                      float* __restrict__ ws_colsum, int want_colsum, BwdParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const Geom& g = p.g;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t sb = smem_u32(smem);
   const uint32_t bar0 = sb + kOffBar;
-  auto bar_full = [&](int s) { return bar0 + 8 * s; };
-  auto bar_empty = [&](int s) { return bar0 + 8 * (kStages + s); };
-  auto bar_pre = [&](int s) { return bar0 + 8 * (2 * kStages + s); };
-  auto bar_hat = [&](int s) { return bar0 + 8 * (3 * kStages + s); };
-  auto bar_sdp = [&](int s) { return bar0 + 8 * (4 * kStages + s); };
-  // accumulator buffer a (= pair parity): output MMAs complete / epilogue has pulled the accumulators out of TMEM
-  auto bar_acc = [&](int a) { return bar0 + 8 * (a ? 5 * kStages + 8 + 2 * kStagesE : 5 * kStages + 1); };
-  auto bar_accfree = [&](int a) { return bar0 + 8 * (a ? 5 * kStages + 9 + 2 * kStagesE : 5 * kStages + 2); };
-  auto bar_sfree = [&](int b) { return bar0 + 8 * (5 * kStages + (b ? 0 : 7)); };  // S / dP buffer b read by its softmax group
-  auto bar_fullE = [&](int s) { return bar0 + 8 * (5 * kStages + 8 + s); };
-  auto bar_emptyE = [&](int s) { return bar0 + 8 * (5 * kStages + 8 + kStagesE + s); };
-  auto bar_staged = [&](int b) { return bar0 + 8 * (5 * kStages + 3 + b); };  // P / dS staging buffer b written
-  auto bar_stfree = [&](int b) { return bar0 + 8 * (5 * kStages + 5 + b); };  // ... and read by the MMAs
+  auto bar_full = [&](int s) { return bar0 + 8 * s; };                      // q, k, dO tiles + statistics landed
+  auto bar_empty = [&](int s) { return bar0 + 8 * (kStages + s); };         // the stores of dq, dk, dv have read the stage
+  auto bar_written = [&](int s) { return bar0 + 8 * (2 * kStages + s); };   // epilogue wrote dq, dk, dv over the tiles
+  auto bar_hat = [&](int s) { return bar0 + 8 * (3 * kStages + s); };       // q, k tiles normalised in place
+  auto bar_sdp = [&](int s) { return bar0 + 8 * (4 * kStages + s); };       // S, dP accumulators complete
+  auto bar_fullE = [&](int s) { return bar0 + 8 * (5 * kStages + s); };
+  auto bar_emptyE = [&](int s) { return bar0 + 8 * (5 * kStages + kStagesE + s); };
+  const uint32_t barx = bar0 + 8 * (5 * kStages + 2 * kStagesE);
+  auto bar_staged = [&](int b) { return barx + 8 * b; };        // P / dS staging buffer b written
+  auto bar_stfree = [&](int b) { return barx + 8 * (2 + b); };  // ... and read by the MMAs
+  auto bar_sfree = [&](int b) { return barx + 8 * (4 + b); };   // S / dP buffer b read by its softmax group
+  auto bar_acc = [&](int a) { return barx + 8 * (6 + a); };     // output MMAs of accumulator buffer a complete
+  auto bar_accfree = [&](int a) { return barx + 8 * (8 + a); }; // epilogue has pulled the accumulators out of TMEM
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmem);
   const int nrows = g.B * g.nW;
 
@@ -190,23 +210,21 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
     s_work = w0;
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_full(s), 1);
-      mbar_init(bar_empty(s), 8);  // the eight epilogue warps
-      mbar_init(bar_pre(s), 4);
+      mbar_init(bar_empty(s), 1);    // the store warp
+      mbar_init(bar_written(s), 8);  // the eight epilogue warps
       mbar_init(bar_hat(s), 8);
       mbar_init(bar_sdp(s), 1);
     }
     for (int s = 0; s < kStagesE; ++s) {
       mbar_init(bar_fullE(s), 1);
-      mbar_init(bar_emptyE(s), 5);  // the four pre-pass warps (o, for D) and the commit behind the dP MMAs (v)
+      mbar_init(bar_emptyE(s), 1);  // the commit behind the dP MMAs
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_staged(b), 8);
       mbar_init(bar_stfree(b), 1);
       mbar_init(bar_sfree(b), 8);
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(bar_acc(a), 1);
-      mbar_init(bar_accfree(a), 8);
+      mbar_init(bar_acc(b), 1);
+      mbar_init(bar_accfree(b), 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -254,13 +272,14 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
   if (warp < 4) {
     reg_dealloc<40>();
     if (warp == 0) {
-      // ---------------------------------------------------------------- TMA producer: lane t < 8 loads tile t of the stage
+      // ---------------------------------------------------------------- TMA producer: lanes 0-7 load one tile each (q, k, v,
+      // dO of the two units), lanes 8-13 one plane (lse, r, c) of the forward's statistics of one unit
       for (int k = 0; k < npairs; ++k) {
         const int s = k % kStages, se = k % kStagesE;
         mbar_wait_fast(bar_empty(s), ((k / kStages) & 1) ^ 1);
         mbar_wait_fast(bar_emptyE(se), ((k / kStagesE) & 1) ^ 1);
         TRACE(k, 0);
-        const int which = lane & 1, kind = lane >> 1;  // kind: 0 q, 1 k, 2 v, 3 dO, 4 o
+        const int which = lane & 1;
         bool valid;
         const int r = work.row(k, which, nrows, valid);
         const int b = r / g.nW, win = r - b * g.nW;
@@ -275,36 +294,26 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
         }
         __syncwarp();
         if (lane == 0) {
-          mbar_expect_tx(bar_full(s), KO(1) ? 0 : kStage);
-          mbar_expect_tx(bar_fullE(se), KO(1) ? 0 : kStageE);
+          mbar_expect_tx(bar_full(s), kStage + 6 * kStatBytes);
+          mbar_expect_tx(bar_fullE(se), kStageE);
         }
         __syncwarp();
-        if (lane < 10 && !KO(1)) {
-          const int head = which == 0 ? work.head_a : work.head_b;
-          const int tsr = kind < 3 ? 0 : (kind == 3 ? 1 : 2);
+        const int head = which == 0 ? work.head_a : work.head_b;
+        if (lane < 8) {
+          const int kind = lane >> 1;  // 0 q, 1 k, 2 v, 3 dO
           const int c0 = (kind < 3 ? kind * g.C : 0) + head * 32;
-          const bool early = kind == 2 || kind == 4;  // v, o
-          const int tidx = (kind == 0 ? 0 : (kind == 1 ? 2 : (kind == 3 ? 4 : (kind == 2 ? 0 : 2)))) + which;
+          const bool early = kind == 2;
+          const int tidx = (kind == 0 ? 0 : (kind == 1 ? 2 : (kind == 3 ? 4 : 0))) + which;
           const uint32_t dst = early ? sb + kOffStageE + se * kStageE + tidx * kTile : sb + kOffStage + s * kStage + tidx * kTile;
           const uint32_t bar = early ? bar_fullE(se) : bar_full(s);
-          const CUtensorMap* mm = maps.m[tsr];
-          if (!kSplit) {
-            tma_load_4d(dst, &mm[0], bar, c0, col0, row0, b);
-          } else {
-            const int sh = g.shift, wa = kWs - g.shift;
-            int colb = col0 + wa;
-            if (colb >= g.W) colb -= g.W;
-            const uint32_t dstb = dst + kWs * wa * 64;
-            if (!bottom) {
-              tma_load_4d(dst, &mm[1], bar, c0, col0, row0, b);
-              tma_load_4d(dstb, &mm[2], bar, c0, colb, row0, b);
-            } else {
-              tma_load_4d(dst, &mm[3], bar, c0, col0, row0, b);
-              tma_load_4d(dst + wa * wa * 64, &mm[4], bar, c0, col0, 0, b);
-              tma_load_4d(dstb, &mm[5], bar, c0, colb, row0, b);
-              tma_load_4d(dstb + sh * wa * 64, &mm[6], bar, c0, colb, 0, b);
-            }
-          }
+          const CUtensorMap* mm = maps.m[kind == 3 ? 1 : 0];
+          for_each_box<kSplit>(g, col0, row0, bottom, [&](int off, int mi, int col, int row) {
+            tma_load_4d(dst + off, &mm[mi], bar, c0, col, row, b);
+          });
+        } else if (lane < 14) {
+          const int plane = (lane - 8) >> 1;
+          const float* src = stats + plane * p.plane + ((int64_t)r * g.heads + head) * kN;
+          bulk_load(sb + kOffVec + ((s * 3 + plane) * 128 + which * 64) * 4, src, kStatBytes, bar_full(s));
         }
       }
     } else if (warp == 1) {
@@ -365,125 +374,105 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
         if (elect_one()) {
           const uint64_t so = (uint64_t)((s * kStage) >> 4), bo = (uint64_t)(buf * ((2 * kPdTile) >> 4));
           const uint32_t acc = tmem + kAccCols * buf;
-          if (!KO(8)) {
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const uint32_t dl = (uint32_t)(16 * u) << 16;
-              const uint64_t ao = bo + (uint64_t)(u * (kPdTile >> 4)), to = so + (uint64_t)(u * (kTile >> 4));
+          for (int u = 0; u < 2; ++u) {
+            const uint32_t dl = (uint32_t)(16 * u) << 16;
+            const uint64_t ao = bo + (uint64_t)(u * (kPdTile >> 4)), to = so + (uint64_t)(u * (kTile >> 4));
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks)  // 16 queries per step: A += 2 KB, B += 1 KB
-                umma_ss(acc + dl + kColDV, a_pt + ao + (uint64_t)(128 * ks), b_g + to + (uint64_t)(64 * ks), id_t, ks > 0);
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks)
-                umma_ss(acc + dl + kColDK, a_dst + ao + (uint64_t)(128 * ks), b_q + to + (uint64_t)(64 * ks), id_t, ks > 0);
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks)  // 16 keys per step: A += 32 B inside the swizzle atom, B += 1 KB
-                umma_ss(acc + dl + kColDQ, a_ds + ao + (uint64_t)(2 * ks), b_k + to + (uint64_t)(64 * ks), id_q, ks > 0);
-            }
+            for (int ks = 0; ks < 4; ++ks)  // 16 queries per step: A += 2 KB, B += 1 KB
+              umma_ss(acc + dl + kColDV, a_pt + ao + (uint64_t)(128 * ks), b_g + to + (uint64_t)(64 * ks), id_t, ks > 0);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
-              umma_ss(tmem + kColDB, a_ds + bo + (uint64_t)(2 * ks), b_eye + (uint64_t)(2 * ks), id_b, (k > 0 || ks > 0) ? 1u : 0u);
+              umma_ss(acc + dl + kColDK, a_dst + ao + (uint64_t)(128 * ks), b_q + to + (uint64_t)(64 * ks), id_t, ks > 0);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)  // 16 keys per step: A += 32 B inside the swizzle atom, B += 1 KB
+              umma_ss(acc + dl + kColDQ, a_ds + ao + (uint64_t)(2 * ks), b_k + to + (uint64_t)(64 * ks), id_q, ks > 0);
           }
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_ss(tmem + kColDB, a_ds + bo + (uint64_t)(2 * ks), b_eye + (uint64_t)(2 * ks), id_b, (k > 0 || ks > 0) ? 1u : 0u);
           umma_commit(bar_acc(buf));
           umma_commit(bar_stfree(buf));
           TRACE(k, 12);
         }
         __syncwarp();
       }
+    } else {
+      // ---------------------------------------------------------------- warp 3: TMA stores of dq, dk, dv + dq column sums
+      // The epilogue warps have written dq over the q tile, dk over the k tile and dv over the dO tile of the stage (same
+      // swizzled layout the loads produced), so the boxes of the loads are the boxes of the stores.  Lanes 0-5 own one
+      // tile each.  While the TMA engine reads the stage the warp sums the dq tiles over their rows (gradient of q_bias).
+      float cs[2][8];
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) cs[u][e] = 0.f;
+      const int which = lane & 1, kind = lane >> 1;  // kind: 0 dq (q tile), 1 dk (k tile), 2 dv (dO tile)
+      const int head = which == 0 ? work.head_a : work.head_b;
+      const int c0 = kind * g.C + head * 32;
+      const CUtensorMap* mm = maps.m[2];
+      for (int k = 0; k < npairs; ++k) {
+        const int s = k % kStages;
+        mbar_wait_fast(bar_written(s), (k / kStages) & 1);
+        TRACE(k, 14);
+        const uint32_t st = sb + kOffStage + s * kStage;
+        if (lane < 6) {
+          const UnitGeo ug = geo[(k & 7) * 2 + which];
+          if (ug.rflags & 1) {
+            const uint32_t src = st + (2 * kind + which) * kTile;
+            for_each_box<kSplit>(g, ug.col0, ug.row0, (ug.rflags & 2) != 0, [&](int off, int mi, int col, int row) {
+              tma_store_4d(&mm[mi], src + off, c0, col, row, ug.b);
+            });
+          }
+        }
+        bulk_commit();
+        if (want_colsum) {
+          const int ch = lane & 3, r0 = lane >> 2;
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            if (!(geo[(k & 7) * 2 + u].rflags & 1)) continue;
+            const uint32_t tile = st + u * kTile;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int row = r0 + 8 * i;
+              const uint4 v = lds128(tile + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
+              cs[u][0] += bf16lo_to_f32(v.x); cs[u][1] += bf16hi_to_f32(v.x);
+              cs[u][2] += bf16lo_to_f32(v.y); cs[u][3] += bf16hi_to_f32(v.y);
+              cs[u][4] += bf16lo_to_f32(v.z); cs[u][5] += bf16hi_to_f32(v.z);
+              cs[u][6] += bf16lo_to_f32(v.w); cs[u][7] += bf16hi_to_f32(v.w);
+            }
+          }
+        }
+        bulk_wait_read0();
+        __syncwarp();
+        TRACE(k, 15);
+        if (lane == 0) mbar_arrive(bar_empty(s));
+      }
+      bulk_wait0();
+      if (want_colsum) {
+        float* col = reinterpret_cast<float*>(smem + kOffCol);
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float v = cs[u][e];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (lane < 4) col[u * 32 + 8 * lane + e] = v;
+          }
+      }
     }
-  } else if (warp < 8) {
-    // ------------------------------------------------------------------ pre-pass warps
-    const int w4 = warp - 4;
-    const int u = w4 & 1, part = w4 >> 1;  // norms: tile (part: q | k, unit u); D: unit u, rows 32 * part ..
-    const int head_u = u == 0 ? work.head_a : work.head_b;
-    const float tau_u = __ldg(&tau[head_u]);
-    const float mult = part == 0 ? 1.0f : tau_u * kLog2e;
-    const int g_ = lane >> 2, t_ = lane & 3;
-    const int arow = (lane & 7) + 8 * ((lane >> 3) & 1), achunk = lane >> 4;
-    const bool odd = (lane >> 2) & 1;
-    const int src = (lane & ~3) | (lane >> 3);
-    // lse gather: this warp fetches pair rows 32 * w4 + lane
-    const int lrow = 32 * w4 + lane, lu = lrow >> 6, lslot = slotmap[lrow & 63];
-    const int lhead = lu == 0 ? work.head_a : work.head_b;
-
-    auto pre = [&](int k) {
-      const int s = k % kStages, se = k % kStagesE;
-      mbar_wait_fast(bar_full(s), (k / kStages) & 1);
-      mbar_wait_fast(bar_fullE(se), (k / kStagesE) & 1);
-      const uint32_t st = sb + kOffStage + s * kStage;
-      float* vec = vecs + s * 4 * 128;
-      // lse of the pair's rows (1e30 for the padding unit of an odd tail: P = dS = 0 there); the load is issued first and
-      // consumed at the end of the pre-pass so that its latency hides behind the tensor-pipe work
-      const int rf = geo[(k & 7) * 2 + lu].rflags;
-      const float lse_v = (rf & 1) ? __ldg(&lse[((int64_t)(rf >> 3) * g.heads + lhead) * kN + lslot]) : 1e30f;
-      const uint32_t tile = st + (2 * part + u) * kTile;
-      const uint32_t gt = st + (4 + u) * kTile, ot = sb + kOffStageE + se * kStageE + (2 + u) * kTile;
-#pragma unroll
-      for (int bp = 0; bp < 2; ++bp) {
-        uint32_t x[2][2][4];
-#pragma unroll
-        for (int b2 = 0; b2 < 2; ++b2) {
-          const int row = 16 * (2 * bp + b2) + arow;
-          ldsm_x4(tile + row * 64 + (((achunk) ^ ((row >> 1) & 3)) << 4), x[b2][0]);
-          ldsm_x4(tile + row * 64 + (((2 + achunk) ^ ((row >> 1) & 3)) << 4), x[b2][1]);
-        }
-        float n0[2][4], n1[2][4];
-#pragma unroll
-        for (int b2 = 0; b2 < 2; ++b2) rowdot_mma(x[b2], x[b2], n0[b2], n1[b2]);
-#pragma unroll
-        for (int b2 = 0; b2 < 2; ++b2) {
-          const float s0 = __shfl_sync(0xffffffffu, odd ? n0[b2][1] : n0[b2][0], src);
-          const float s1 = __shfl_sync(0xffffffffu, odd ? n1[b2][3] : n1[b2][2], src);
-          if (t_ == 0) {
-            vec[part * 128 + 64 * u + 16 * (2 * bp + b2) + g_] = mult * inv_norm(s0);
-            vec[part * 128 + 64 * u + 16 * (2 * bp + b2) + g_ + 8] = mult * inv_norm(s1);
-          }
-        }
-      }
-      {  // D = rowsum(dO o o) for rows 32 * part .. + 32 of unit u
-        uint32_t x[2][2][4], y[2][2][4];
-#pragma unroll
-        for (int b2 = 0; b2 < 2; ++b2) {
-          const int row = 32 * part + 16 * b2 + arow;
-          const uint32_t o0 = row * 64 + (((achunk) ^ ((row >> 1) & 3)) << 4), o1 = row * 64 + (((2 + achunk) ^ ((row >> 1) & 3)) << 4);
-          ldsm_x4(gt + o0, x[b2][0]);
-          ldsm_x4(gt + o1, x[b2][1]);
-          ldsm_x4(ot + o0, y[b2][0]);
-          ldsm_x4(ot + o1, y[b2][1]);
-        }
-        float n0[2][4], n1[2][4];
-#pragma unroll
-        for (int b2 = 0; b2 < 2; ++b2) rowdot_mma(x[b2], y[b2], n0[b2], n1[b2]);
-#pragma unroll
-        for (int b2 = 0; b2 < 2; ++b2) {
-          const float s0 = __shfl_sync(0xffffffffu, odd ? n0[b2][1] : n0[b2][0], src);
-          const float s1 = __shfl_sync(0xffffffffu, odd ? n1[b2][3] : n1[b2][2], src);
-          if (t_ == 0) {
-            vec[2 * 128 + 64 * u + 32 * part + 16 * b2 + g_] = s0;
-            vec[2 * 128 + 64 * u + 32 * part + 16 * b2 + g_ + 8] = s1;
-          }
-        }
-      }
-      vec[3 * 128 + lrow] = lse_v;
-      __syncwarp();
-      if (warp == 4) TRACE(k, 3);
-      if (lane == 0) {
-        mbar_arrive(bar_pre(s));
-        mbar_arrive(bar_emptyE(se));  // o is dead once D exists
-      }
-    };
-    for (int k = 0; k < npairs; ++k) pre(k);
-
-  } else if (warp < 24) {
-    // ------------------------------------------------------------------ softmax / dS threads: two groups (warps 8-15 even
-    // pairs, 16-23 odd pairs) so that the hand-over latencies of one group hide behind the arithmetic of the other; a thread
-    // owns half a logit row and streams it from TMEM 16 keys at a time (64 registers per thread: S / dP stay in TMEM, which
-    // has room for one buffer per group).  Lanes 0-15 of a warp are rows of unit a, lanes 16-31 of unit b (M = 64 layout).
-    const int grp = (warp - 8) >> 3;
-    const int half = ((warp - 8) >> 2) & 1;
+  } else if (warp < 20) {
+    // ------------------------------------------------------------------ softmax / dS threads: two groups (warps 4-11 even
+    // pairs, 12-19 odd pairs) so that the hand-over latencies of one group hide behind the arithmetic of the other; a thread
+    // owns half a logit row.  Lanes 0-15 of a warp are rows of unit a, lanes 16-31 of unit b (M = 64 layout).
+    reg_alloc<80>();
+    const int grp = (warp - 4) >> 3;
+    const int half = ((warp - 4) >> 2) & 1;
     const int quad = warp & 3;
     const int u = lane >> 4, i = 16 * quad + (lane & 15);  // unit of the pair, tile row (query) inside the unit
-    const int row = 64 * u + i;                            // row of the pair in the per-stage vectors
+    const int row = 64 * u + i;                            // row of the pair in the per-pair vectors
     const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16);
     const float kNeg = kMaskValue * kLog2e;
     const int si = slotmap[i], ih = si >> 3, iw = si & 7;
@@ -506,49 +495,55 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
     const uint32_t tS = tl + kColS + 64 * grp + 32 * half, tP = tl + kColDP + 64 * grp + 32 * half;
     float acc_tau = 0.f;
     float* dots = reinterpret_cast<float*>(smem + kOffDot);
+    float* dpart = reinterpret_cast<float*>(smem + kOffDpart) + grp * 256;
     // In-place normalisation of the q / k tiles of the group's own pair once S has been computed from the raw tiles
     // (q^ = q / |q|, k^ = k / |k|): half a tile (one row per lane) per warp, after the group's own arithmetic and under the
     // same fence.proxy.async as its staging stores -- independent of the accumulator / epilogue chain
     const int hw = 4 * half + quad, htile = hw >> 1, hpart = htile >> 1, hu = htile & 1, hrow = 32 * (hw & 1) + lane;
+    const int hslot = slotmap[hrow];
     const float inv_mult = hpart == 0 ? 1.0f : 1.0f / (__ldg(&tau[hu == 0 ? work.head_a : work.head_b]) * kLog2e);
     auto hat = [&](int k) {
       const int s = k % kStages;
       const uint32_t tile = sb + kOffStage + s * kStage + (2 * hpart + hu) * kTile;
-      const float* vec = vecs + s * 4 * 128 + hpart * 128 + 64 * hu;
-      if (!KO(16)) {
-        uint4 v[4];
+      const float* vec = vecs + (s * 3 + 1 + hpart) * 128 + 64 * hu;
+      uint4 v[4];
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) v[ch] = lds128(tile + hrow * 64 + ((ch ^ ((hrow >> 1) & 3)) << 4));
-        const float sc = vec[hrow] * inv_mult;
+      for (int ch = 0; ch < 4; ++ch) v[ch] = lds128(tile + hrow * 64 + ((ch ^ ((hrow >> 1) & 3)) << 4));
+      const float sc = vec[hslot] * inv_mult;
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          uint4 w = v[ch];
-          w.x = pack_bf16x2(bf16lo_to_f32(w.x) * sc, bf16hi_to_f32(w.x) * sc);
-          w.y = pack_bf16x2(bf16lo_to_f32(w.y) * sc, bf16hi_to_f32(w.y) * sc);
-          w.z = pack_bf16x2(bf16lo_to_f32(w.z) * sc, bf16hi_to_f32(w.z) * sc);
-          w.w = pack_bf16x2(bf16lo_to_f32(w.w) * sc, bf16hi_to_f32(w.w) * sc);
-          sts128(tile + hrow * 64 + ((ch ^ ((hrow >> 1) & 3)) << 4), w);
-        }
+      for (int ch = 0; ch < 4; ++ch) {
+        uint4 w = v[ch];
+        w.x = pack_bf16x2(bf16lo_to_f32(w.x) * sc, bf16hi_to_f32(w.x) * sc);
+        w.y = pack_bf16x2(bf16lo_to_f32(w.y) * sc, bf16hi_to_f32(w.y) * sc);
+        w.z = pack_bf16x2(bf16lo_to_f32(w.z) * sc, bf16hi_to_f32(w.z) * sc);
+        w.w = pack_bf16x2(bf16lo_to_f32(w.w) * sc, bf16hi_to_f32(w.w) * sc);
+        sts128(tile + hrow * 64 + ((ch ^ ((hrow >> 1) & 3)) << 4), w);
       }
     };
 
     for (int k = grp; k < npairs; k += 2) {
       const int s = k % kStages;
       const uint32_t ph = (k / kStages) & 1;
-      mbar_wait_fast(bar_pre(s), ph);
-      if (warp == 8) TRACE(k, 5);
+      mbar_wait_fast(bar_full(s), ph);  // statistics (and tiles) of the pair have landed
+      if (warp == 4) TRACE(k, 5);
       const int rflags = geo[(k & 7) * 2 + u].rflags;
-      const float* vec = vecs + s * 4 * 128;
-      const float ri = vec[row], Di = vec[2 * 128 + row], li = vec[3 * 128 + row];
-      const float* cv = vec + 128 + 64 * u + 32 * half;
+      const float* vec = vecs + s * 3 * 128;
+      // lse = 1e30 for the padding unit of an odd tail: P = dS = 0 there
+      const float li = (rflags & 1) ? vec[64 * u + si] : 1e30f;
+      const float ri = vec[128 + 64 * u + si];
+      // c_j of keys 4q .. 4q + 3 of this half (slot order): slot order = tile order | split order: window row q, columns 4 half ..
+      const float* cv = vec + 256 + 64 * u + (kSplit ? 4 * half : 32 * half);
       uint32_t m = 0u;
       if (kSplit) m = ((rflags & 2) ? mH : 0u) | ((rflags & 4) ? mW : 0u);
       const bool any_mask = kSplit && __any_sync(0xffffffffu, m != 0u);
       if (k > 1) mbar_wait_fast(bar_stfree(grp), ((k >> 1) - 1) & 1);  // the MMAs of pair k-2 have read this group's staging tiles
       mbar_wait_fast(bar_sdp(s), ph);
-      if (warp == 8) TRACE(k, 6);
+      if (warp == 4) TRACE(k, 6);
       tc_fence_after();
-      float racc = 0.f;  // sum_j dS_ij t_ij over this half row: d(tau) contribution and the dQ epilogue's q^.M
+      // pass 1: P (staged, and kept packed), dP kept packed (the reference's dP is a bf16 matmul output as well), partial
+      // sums over this half row: Dp = sum P dP, A1 = sum P dP t, A2 = sum P t
+      float Dp = 0.f, A1 = 0.f, A2 = 0.f;
+      uint32_t pk[16], dk[16];
       auto chunk = [&](auto masked, auto ck_tag) {
         constexpr int ck = decltype(ck_tag)::value;  // keys 16 ck .. 16 ck + 15 of this half
         uint32_t sa[16], pa[16];
@@ -558,19 +553,18 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
         if (ck == 1) {  // the whole half row has left TMEM: hand the buffer back to the S / dP issuer
           tc_fence_before();
           __syncwarp();
-          if (warp == 8) TRACE(k, 7);
+          if (warp == 4) TRACE(k, 7);
           if (lane == 0) mbar_arrive(bar_sfree(grp));
         }
 #pragma unroll
-        for (int h8 = 0; h8 < 2; ++h8) {  // eight keys = one 16-byte staging chunk of P and of dS
-          uint32_t pp[4], dd[4];
+        for (int h8 = 0; h8 < 2; ++h8) {  // eight keys = one 16-byte staging chunk of P
 #pragma unroll
           for (int q2 = 0; q2 < 2; ++q2) {
             const int q = 4 * ck + 2 * h8 + q2;
             // keys 4q .. 4q + 3 of this half: slot order = window row 4 half + q / 2, columns 4 (q & 1) ..;
             // split order = window row q, columns 4 half ..
             const float4 b = *reinterpret_cast<const float4*>(bias_base + (kSplit ? -q * kBiasRow : -(q >> 1) * kBiasRow + 4 * (q & 1)));
-            const float4 c = *reinterpret_cast<const float4*>(cv + 4 * q);
+            const float4 c = *reinterpret_cast<const float4*>(cv + (kSplit ? 8 * q : 4 * q));
             const float bb[4] = {b.x, b.y, b.z, b.w}, cc[4] = {c.x, c.y, c.z, c.w};
             float pv[4], dv[4];
 #pragma unroll
@@ -580,30 +574,52 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
               float x = (t + bb[e]) - li;
               if (decltype(masked)::value && ((m >> j) & 1u)) x += kNeg;
               const float pe = ex2(x);
-              const float de = pe * (__uint_as_float(pa[jj]) - Di);
-              racc = fmaf(de, t, racc);
+              const float dp = __uint_as_float(pa[jj]);
+              const float ge = pe * dp;
+              Dp += ge;
+              A1 = fmaf(ge, t, A1);
+              A2 = fmaf(pe, t, A2);
               pv[e] = pe;
-              dv[e] = de;
+              dv[e] = dp;
             }
-            pp[2 * q2] = pack_bf16x2(pv[0], pv[1]);
-            pp[2 * q2 + 1] = pack_bf16x2(pv[2], pv[3]);
-            dd[2 * q2] = pack_bf16x2(dv[0], dv[1]);
-            dd[2 * q2 + 1] = pack_bf16x2(dv[2], dv[3]);
+            const int w = 8 * ck + 4 * h8 + 2 * q2;
+            pk[w] = pack_bf16x2(pv[0], pv[1]);
+            pk[w + 1] = pack_bf16x2(pv[2], pv[3]);
+            dk[w] = pack_bf16x2(dv[0], dv[1]);
+            dk[w + 1] = pack_bf16x2(dv[2], dv[3]);
           }
+          const int w0 = 8 * ck + 4 * h8;
           const uint32_t off = (uint32_t)(((4 * half + 2 * ck + h8) ^ (i & 7)) << 4);
-          sts128(p_row + off, make_uint4(pp[0], pp[1], pp[2], pp[3]));
-          sts128(ds_row + off, make_uint4(dd[0], dd[1], dd[2], dd[3]));
+          sts128(p_row + off, make_uint4(pk[w0], pk[w0 + 1], pk[w0 + 2], pk[w0 + 3]));
         }
       };
       if (any_mask) { chunk(BoolTag<true>{}, IntTag<0>{}); chunk(BoolTag<true>{}, IntTag<1>{}); }
       else { chunk(BoolTag<false>{}, IntTag<0>{}); chunk(BoolTag<false>{}, IntTag<1>{}); }
-      if (warp == 8) TRACE(k, 8);
+      // D = both halves' partial sums: swap through shared memory with the warp that owns the other half of these rows
+      float* dpp = dpart + ((k >> 1) & 1) * 512;
+      dpp[half * 128 + row] = Dp;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + grp * 4 + quad) : "memory");
+      const float Di = Dp + dpp[(half ^ 1) * 128 + row];
+      if (warp == 4) TRACE(k, 8);
+      // pass 2: dS = P (dP - D)
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) {
+        uint32_t dd[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const uint32_t pw = pk[4 * c8 + w], dw = dk[4 * c8 + w];
+          dd[w] = pack_bf16x2(bf16lo_to_f32(pw) * (bf16lo_to_f32(dw) - Di), bf16hi_to_f32(pw) * (bf16hi_to_f32(dw) - Di));
+        }
+        const uint32_t off = (uint32_t)(((4 * half + c8) ^ (i & 7)) << 4);
+        sts128(ds_row + off, make_uint4(dd[0], dd[1], dd[2], dd[3]));
+      }
+      const float racc = fmaf(-Di, A2, A1);  // sum_j dS_ij t_ij over this half row: d(tau) contribution, the dQ epilogue's q^.M
       acc_tau += racc;
       dots[((k & 3) * 2 + half) * 128 + row] = racc;
       hat(k);
       fence_async_smem();
       __syncwarp();
-      if (warp == 8) TRACE(k, 9);
+      if (warp == 4) TRACE(k, 9);
       if (lane == 0) {
         mbar_arrive(bar_staged(grp));
         mbar_arrive(bar_hat(s));
@@ -616,50 +632,42 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
       atomicAdd(reinterpret_cast<float*>(smem + kOffCol) + 64 + u, tot / tu);
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps: 24-27 dV and dK, 28-31 dQ
+    // ------------------------------------------------------------------ epilogue warps: 20-23 dV and dK, 24-27 dQ.  A thread
+    // owns one token row: accumulators from TMEM, projection of the normalised-row gradient back to the raw row, result
+    // written as bf16 over the row of the dO (dv), k (dk) or q (dq) tile -- the store warp sends the tiles out by TMA
     auto epilogue = [&](auto role_tag) {
     constexpr int role = decltype(role_tag)::value;  // 1 dV + dK, 2 dQ
-    if (role == 2) reg_alloc<88>();
     const int quad = warp & 3;
     const int u = lane >> 4, t = 16 * quad + (lane & 15);  // M = 64 accumulator layout: lanes 0-15 unit a, 16-31 unit b
     const int row = 64 * u + t;
     const int head = u == 0 ? work.head_a : work.head_b;
     const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16);
-    const int sl = slotmap[t], ih = sl >> 3, iw = sl & 7;
+    const int sl = slotmap[t];
     const float tau_h = __ldg(&tau[head]);
     const float inv_tl = 1.0f / (tau_h * kLog2e);
-    float csum[32];
-#pragma unroll
-    for (int e = 0; e < 32; ++e) csum[e] = 0.f;
+    const uint32_t swz = (uint32_t)((t >> 1) & 3);
 
     for (int k = 0; k < npairs; ++k) {
       const int s = k % kStages;
       const int ab = k & 1;
       mbar_wait_fast(bar_acc(ab), (k >> 1) & 1);
-      if (warp == 24) TRACE(k, 13);
+      if (warp == 20) TRACE(k, 13);
       tc_fence_after();
       uint32_t a[32];
-      const UnitGeo ug = geo[(k & 7) * 2 + u];
-      int prow = ug.row0 + ih; if (prow >= g.H) prow -= g.H;
-      int pcol = ug.col0 + iw; if (pcol >= g.W) pcol -= g.W;
-      const int64_t tok = ((int64_t)ug.b * g.H + prow) * g.W + pcol;
-      bf16* drow = dqkv + tok * (3 * g.C) + head * 32 + (role == 1 ? g.C : 0);
-      const bool valid = (ug.rflags & 1) && !KO(2);
-      if (role == 1) {  // dV first: pack and store, then the same registers take dK
+      const uint32_t st = sb + kOffStage + s * kStage;
+      if (role == 1) {  // dV first: pack and write over the dO row, then the same registers take dK
         HV_TMEM_LD32(tl + kAccCols * ab + kColDV, a);
         tmem_wait_ld();
         HV_REG_FENCE32(a);
-        if (valid) {
-          uint4* dst = reinterpret_cast<uint4*>(drow + g.C);
+        const uint32_t grow = st + (4 + u) * kTile + t * 64;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 v;
-            v.x = pack_bf16x2(__uint_as_float(a[8 * q + 0]), __uint_as_float(a[8 * q + 1]));
-            v.y = pack_bf16x2(__uint_as_float(a[8 * q + 2]), __uint_as_float(a[8 * q + 3]));
-            v.z = pack_bf16x2(__uint_as_float(a[8 * q + 4]), __uint_as_float(a[8 * q + 5]));
-            v.w = pack_bf16x2(__uint_as_float(a[8 * q + 6]), __uint_as_float(a[8 * q + 7]));
-            dst[q] = v;
-          }
+        for (int q = 0; q < 4; ++q) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(a[8 * q + 0]), __uint_as_float(a[8 * q + 1]));
+          v.y = pack_bf16x2(__uint_as_float(a[8 * q + 2]), __uint_as_float(a[8 * q + 3]));
+          v.z = pack_bf16x2(__uint_as_float(a[8 * q + 4]), __uint_as_float(a[8 * q + 5]));
+          v.w = pack_bf16x2(__uint_as_float(a[8 * q + 6]), __uint_as_float(a[8 * q + 7]));
+          sts128(grow + ((q ^ swz) << 4), v);
         }
       }
       HV_TMEM_LD32(tl + kAccCols * ab + (role == 1 ? kColDK : kColDQ), a);
@@ -674,20 +682,16 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_accfree(ab));
       // projection of the gradient of the normalised row back to the raw row: d x = sc (M - (x^ . M) x^)
-      const float* vec = vecs + s * 4 * 128;
-      const uint32_t tile = sb + kOffStage + s * kStage + ((role == 2 ? 0 : 2) + u) * kTile + t * 64;
-      const float sc = role == 2 ? vec[row] * tau_h : vec[128 + row] * kLn2;  // tau / |q_i|  |  tau / |k_j| = c_j ln 2
-      uint4* dst = reinterpret_cast<uint4*>(drow);
+      const float* vec = vecs + s * 3 * 128;
+      const uint32_t xrow = st + ((role == 2 ? 0 : 2) + u) * kTile + t * 64;
+      const float sc = role == 2 ? vec[128 + 64 * u + sl] * tau_h : vec[256 + 64 * u + sl] * kLn2;  // tau / |q_i|  |  tau / |k_j| = c_j ln 2
       if (role == 1) {
         uint32_t xh[16];
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-          const uint4 v = lds128(tile + ((ch ^ ((t >> 1) & 3)) << 4));
+          const uint4 v = lds128(xrow + ((ch ^ swz) << 4));
           xh[4 * ch] = v.x; xh[4 * ch + 1] = v.y; xh[4 * ch + 2] = v.z; xh[4 * ch + 3] = v.w;
         }
-        __syncwarp();
-        if (warp == 24) TRACE(k, 15);
-        if (lane == 0) mbar_arrive(bar_empty(s));  // last read of the stage by this warp
         float dot = 0.f;
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
@@ -703,38 +707,30 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
             const float v1 = sc * fmaf(-dot, bf16hi_to_f32(xh[4 * ch + e]), __uint_as_float(a[8 * ch + 2 * e + 1]));
             o[e] = pack_bf16x2(v0, v1);
           }
-          if (valid) dst[ch] = make_uint4(o[0], o[1], o[2], o[3]);
+          sts128(xrow + ((ch ^ swz) << 4), make_uint4(o[0], o[1], o[2], o[3]));
         }
       } else {
         // q^_i . M_i = sum_j dS_ij cos_ij: the softmax threads already have it (two half-row sums of dS t, t = tau log2e cos)
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-          const uint4 v = lds128(tile + ((ch ^ ((t >> 1) & 3)) << 4));
+          const uint4 v = lds128(xrow + ((ch ^ swz) << 4));
           const uint32_t w[4] = {v.x, v.y, v.z, v.w};
           uint32_t o[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float v0 = sc * fmaf(-qdot, bf16lo_to_f32(w[e]), __uint_as_float(a[8 * ch + 2 * e]));
             const float v1 = sc * fmaf(-qdot, bf16hi_to_f32(w[e]), __uint_as_float(a[8 * ch + 2 * e + 1]));
-            if (valid) { csum[8 * ch + 2 * e] += v0; csum[8 * ch + 2 * e + 1] += v1; }
             o[e] = pack_bf16x2(v0, v1);
           }
-          if (valid) dst[ch] = make_uint4(o[0], o[1], o[2], o[3]);
+          sts128(xrow + ((ch ^ swz) << 4), make_uint4(o[0], o[1], o[2], o[3]));
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_empty(s));  // last read of the stage by this warp
       }
-    }
-    if (role == 2 && want_colsum) {
-      float* col = reinterpret_cast<float*>(smem + kOffCol) + u * 32;
-#pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        const float v = group_sum<16>(csum[e]);  // lanes 0-15 / 16-31 are rows of unit a / b
-        if ((lane & 15) == 0) atomicAdd(&col[e], v);
-      }
+      fence_async_smem();  // the tiles are read by the TMA engine (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_written(s));
     }
     };
-    if (warp < 28) epilogue(IntTag<1>{}); else epilogue(IntTag<2>{});
+    if (warp < 24) epilogue(IntTag<1>{}); else epilogue(IntTag<2>{});
   }
   tc_fence_before();
   __syncthreads();
@@ -824,15 +820,14 @@ int wattn_bwd_variant_set(int v) {
 }
 
 bool wattn_tc64_bwd_supported(const Geom& g, int dtype) {
+  // HV_ATTN_TCGEN05_BWD: unset = automatic (this kernel wherever it is valid), 0 = never (mma.sync backward), 1 = same as unset
   static const int env = []() { const char* e = getenv("HV_ATTN_TCGEN05_BWD"); return e == nullptr ? -1 : (atoi(e) != 0 ? 1 : 0); }();
   const int mode = g_bwd_variant < 0 ? env : g_bwd_variant;
   if (mode == 0) return false;
   // shifted layers: the bias lookup reads runs of four keys, i.e. the column split must sit at 4 (shift = ws / 2, the
   // only shift SwinV2 uses, swinv2.py:560)
-  const bool valid = dtype == HV_BF16 && g.ws == kWs && g.d == 32 && g.C % 32 == 0 && (g.shift == 0 || g.shift == 4) &&
-                     (int64_t)g.B * g.H * g.W < (int64_t(1) << 31) && g.W * g.C * 2 % 16 == 0;
-  if (!valid || mode == 1) return valid;
-  return false;  // automatic: the mma.sync backward until this kernel is measured to be the faster one
+  return dtype == HV_BF16 && g.ws == kWs && g.d == 32 && g.C % 32 == 0 && (g.shift == 0 || g.shift == 4) &&
+         (int64_t)g.B * g.H * g.W < (int64_t(1) << 31) && g.W * g.C * 2 % 16 == 0;
 }
 
 size_t wattn_tc64_bwd_workspace_bytes(const Geom& g) {
@@ -840,22 +835,23 @@ size_t wattn_tc64_bwd_workspace_bytes(const Geom& g) {
   return (size_t)num_sms() * (2 * kTab + 2 + 64) * sizeof(float) + 256;
 }
 
-int wattn_tc64_bwd(const Geom& g, const void* qkv, const void* out, const void* dout, const float* lse,
-                   const float* bias_table, const float* tau, void* dqkv, float* dbias_table, float* dtau,
-                   float* dq_colsum, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  if (!aligned16(qkv) || !aligned16(out) || !aligned16(dout) || !aligned16(dqkv) || !aligned16(lse))
+// `stats`: the three planes (lse | r | c) written by the forward kernels of this geometry (hv_window_attn_stats_floats)
+int wattn_tc64_bwd(const Geom& g, const void* qkv, const void* dout, const float* stats, const float* bias_table,
+                   const float* tau, void* dqkv, float* dbias_table, float* dtau, float* dq_colsum, void* workspace,
+                   size_t workspace_bytes, cudaStream_t st) {
+  if (!aligned16(qkv) || !aligned16(dout) || !aligned16(dqkv) || !aligned16(stats))
     HV_FAIL(HV_ERR_ALIGN, "window_attn_bwd: tensors must be 16-byte aligned");
   if (workspace == nullptr || workspace_bytes < wattn_tc64_bwd_workspace_bytes(g))
     HV_FAIL(HV_ERR_WORKSPACE, "window_attn_bwd: workspace of %zu bytes required", wattn_tc64_bwd_workspace_bytes(g));
-  struct MapKey { const void *qkv, *out, *dout; int B, H, W, C, shift; };
+  struct MapKey { const void *qkv, *dout, *dqkv; int B, H, W, C, shift; };
   struct MapEntry { MapKey key; BwdMaps maps; };
   static thread_local MapEntry cache[32];
   static thread_local int cache_n = 0, cache_next = 0;
-  const MapKey key = {qkv, out, dout, g.B, g.H, g.W, g.C, g.shift};
+  const MapKey key = {qkv, dout, dqkv, g.B, g.H, g.W, g.C, g.shift};
   const BwdMaps* mp = nullptr;
   for (int i = 0; i < cache_n; ++i) {
     const MapKey& c = cache[i].key;
-    if (c.qkv == key.qkv && c.out == key.out && c.dout == key.dout && c.B == key.B && c.H == key.H && c.W == key.W &&
+    if (c.qkv == key.qkv && c.dout == key.dout && c.dqkv == key.dqkv && c.B == key.B && c.H == key.H && c.W == key.W &&
         c.C == key.C && c.shift == key.shift) { mp = &cache[i].maps; break; }
   }
   if (!mp) {
@@ -863,8 +859,8 @@ int wattn_tc64_bwd(const Geom& g, const void* qkv, const void* out, const void* 
     const int s = g.shift, wa = kWs - g.shift;
     const int bw[7] = {kWs, s ? wa : kWs, s ? s : kWs, s ? wa : kWs, s ? wa : kWs, s ? s : kWs, s ? s : kWs};
     const int bh[7] = {kWs, kWs, kWs, s ? wa : kWs, s ? s : kWs, s ? wa : kWs, s ? s : kWs};
-    const void* base[3] = {qkv, dout, out};
-    const int row_elems[3] = {3 * g.C, g.C, g.C};
+    const void* base[3] = {qkv, dout, dqkv};
+    const int row_elems[3] = {3 * g.C, g.C, 3 * g.C};
     for (int t = 0; t < 3; ++t)
       for (int i = 0; i < 7; ++i) {
         const int rc = make_map(&e.maps.m[t][i], base[t], g, row_elems[t], bw[i], bh[i]);
@@ -879,10 +875,7 @@ int wattn_tc64_bwd(const Geom& g, const void* qkv, const void* out, const void* 
   p.g = g;
   p.n_same = g.heads / 2;
   p.has_cross = g.heads & 1;
-  p.ko = 0;
-#ifdef HV_TC_TRACE
-  if (getenv("HV_TC_KO")) p.ko = atoi(getenv("HV_TC_KO"));
-#endif
+  p.plane = (int64_t)g.B * g.nW * g.heads * kN;
   const int nsm = num_sms();
   const int nrows = g.B * g.nW;
   if (p.n_same == 0) {
@@ -920,10 +913,10 @@ int wattn_tc64_bwd(const Geom& g, const void* qkv, const void* out, const void* 
   cudaMemsetAsync(dtrace, 0, 64 * 16 * sizeof(long long), st);
 #endif
   if (g.shift > 0)
-    wattn_tc64_bwd_kernel<true><<<grid, kThreads, kSmem, st>>>(*mp, lse, bias_table, tau, (bf16*)dqkv, ws_dbias, ws_dtau, ws_colsum,
+    wattn_tc64_bwd_kernel<true><<<grid, kThreads, kSmem, st>>>(*mp, stats, bias_table, tau, ws_dbias, ws_dtau, ws_colsum,
                                                                dq_colsum != nullptr, p);
   else
-    wattn_tc64_bwd_kernel<false><<<grid, kThreads, kSmem, st>>>(*mp, lse, bias_table, tau, (bf16*)dqkv, ws_dbias, ws_dtau, ws_colsum,
+    wattn_tc64_bwd_kernel<false><<<grid, kThreads, kSmem, st>>>(*mp, stats, bias_table, tau, ws_dbias, ws_dtau, ws_colsum,
                                                                 dq_colsum != nullptr, p);
   HV_LAUNCH_OK("wattn_tc64_bwd_kernel");
 #ifdef HV_TC_TRACE

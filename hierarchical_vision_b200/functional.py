@@ -100,6 +100,15 @@ def window_attention_fwd_raw(qkv, bias_table, tau, mask, out, lse, B, H, W, C, h
     check(rc, "hv_window_attn_fwd")
 
 
+def window_attention_stats(qkv, B, H, W, C, heads, ws):
+    """Uninitialised statistics buffer (`lse` of hv_window_attn_fwd / _bwd) for a geometry; its size depends on the
+    kernel kind (hv_window_attn_stats_floats)."""
+    n = int(_lib.load().hv_window_attn_stats_floats(B, H, W, C, heads, ws, _code(qkv)))
+    if n <= 0:
+        raise RuntimeError(f"window_attention: invalid geometry B={B} H={H} W={W} C={C} heads={heads} ws={ws}")
+    return torch.empty((n,), dtype=torch.float32, device=qkv.device)
+
+
 def window_attention_bwd_workspace(qkv, B, H, W, C, heads, ws):
     lib = _lib.load()
     with torch.cuda.device(qkv.device):
@@ -133,7 +142,7 @@ class _WindowAttention(torch.autograd.Function):
         N = ws * ws
         nW = (H // ws) * (W // ws)
         out = torch.empty((B, H * W, C), dtype=qkv.dtype, device=qkv.device)
-        lse = torch.empty((B * nW, heads, N), dtype=torch.float32, device=qkv.device)
+        lse = window_attention_stats(qkv, B, H, W, C, heads, ws)
         _timed(f"attn_fwd/C{C}", B * nW, qkv.device, lambda: window_attention_fwd_raw(
             qkv, bias_table, tau, mask, out, lse, B, H, W, C, heads, ws, shift))
         ctx.save_for_backward(qkv, out, lse, bias_table, tau, mask)
@@ -191,7 +200,7 @@ class _QkvWindowAttention(torch.autograd.Function):
         tau = _f32c(tau)
         nW = (H // ws) * (W // ws)
         out = torch.empty((B, H * W, C), dtype=qkv.dtype, device=qkv.device)
-        lse = torch.empty((B * nW, heads, ws * ws), dtype=torch.float32, device=qkv.device)
+        lse = window_attention_stats(qkv, B, H, W, C, heads, ws)
         _timed(f"attn_fwd/C{C}", B * nW, qkv.device, lambda: window_attention_fwd_raw(
             qkv, bias_table, tau, None, out, lse, B, H, W, C, heads, ws, shift))
         ctx.save_for_backward(x, weight, qkv, out, lse, bias_table, tau)

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define HV_ABI_VERSION 2
+#define HV_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define HV_API __attribute__((visibility("default")))
@@ -60,13 +60,17 @@ HV_API int hv_window_attn_kernel_kind(int C, int heads, int ws, int dtype);
 
 /* Forward kernel of the tensor-core path (kind 1): 0 = mma.sync + cp.async kernel, 1 = tcgen05 / TMEM / TMA kernel
  * (even shift sizes; falls back to 0 otherwise), -1 = decided by the HV_ATTN_TCGEN05 environment variable
- * (0 / 1 as above; unset = automatic: the tcgen05 kernel where it is the faster one, i.e. <= 4 heads and >= 4096
- * windows per launch).  Both write the same outputs; process-wide setting, not thread-safe against concurrent launches. */
+ * (0 / 1 as above; unset = automatic: the tcgen05 kernel wherever it is valid).  Both write the same outputs.  A test /
+ * benchmarking switch: process-wide, read at launch time, not meant to be flipped while other threads launch. */
 HV_API int hv_window_attn_fwd_variant(int variant);
 /* Backward kernel of the tensor-core path: 0 = mma.sync + cp.async kernel, 1 = tcgen05 / TMEM / TMA kernel (shift 0 or
- * ws / 2; falls back to 0 otherwise), -1 = decided by the HV_ATTN_TCGEN05_BWD environment variable (unset = automatic).
- * Same outputs and workspace; process-wide setting. */
+ * ws / 2; falls back to 0 otherwise), -1 = decided by the HV_ATTN_TCGEN05_BWD environment variable (unset = automatic:
+ * the tcgen05 kernel wherever it is valid).  Same outputs and workspace; process-wide test / benchmarking switch. */
 HV_API int hv_window_attn_bwd_variant(int variant);
+/* Number of float32 elements of the `lse` statistics buffer of hv_window_attn_fwd / _bwd for a geometry: B*nW*heads*N
+ * for the generic kernel; three such planes for the tensor-core kernels (row log-sum-exp | r_i = 1 / |q_i| |
+ * c_j = tau log2(e) / |k_j|, each (B*nW, heads, N) in window-slot order).  0 on invalid sizes.  Host-only query. */
+HV_API size_t hv_window_attn_stats_floats(int B, int H, int W, int C, int heads, int ws, int dtype);
 
 /* ---- host-side integer maps (CPU; same arithmetic the kernels use on the device) ------ */
 /* relative_position_index (N,N) int64 -- reference swinv2.py:175-190 */
@@ -97,8 +101,10 @@ HV_API int hv_merge_token_index(int B, int H, int W, int64_t* out);
  *         else device float32 (mask_windows, N, N) added to window (row % mask_windows) and the
  *         in-kernel shift mask is NOT applied (WindowAttention.forward(x, mask) semantics)
  *   out   device, (B, H*W, C) `dtype`, image token order
- *   lse   device float32 (B*nW, heads, N): softmax row statistics saved for hv_window_attn_bwd.  Opaque to the
- *         caller: row log-sum-exp in natural-log units (generic kernel) or log2 units (tensor-core kernel); the
+ *   lse   device float32, hv_window_attn_stats_floats() elements: row statistics saved for hv_window_attn_bwd.  Opaque
+ *         to the caller: (B*nW, heads, N) row log-sum-exp in natural-log units (generic kernel); for the tensor-core
+ *         kernels the log2-unit log-sum-exp followed by two more planes with the row scales of the cosine logits
+ *         (1 / |q_i| and tau log2(e) / |k_j|), which the backward kernel reads back instead of recomputing them.  The
  *         pair fwd/bwd of one geometry always dispatches to the same kernel kind.
  */
 HV_API int hv_window_attn_fwd(const void* qkv, const float* bias_table, const float* tau, const float* mask,
@@ -108,7 +114,9 @@ HV_API int hv_window_attn_fwd(const void* qkv, const float* bias_table, const fl
 /* Workspace (bytes) hv_window_attn_bwd needs for its partial reductions. */
 HV_API size_t hv_window_attn_bwd_workspace_bytes(int B, int H, int W, int C, int heads, int ws, int dtype);
 
-/*   dout  device (B, H*W, C) `dtype`: gradient of `out`
+/*   out   device (B, H*W, C) `dtype`: the forward's output (read by the generic and mma.sync kernels; the tcgen05
+ *         kernel forms D = rowsum(P o dP) itself and never touches it)
+ *   dout  device (B, H*W, C) `dtype`: gradient of `out`
  *   dqkv  device (B, H*W, 3C) `dtype`: fully overwritten
  *   dbias_table device float32 ((2ws-1)^2, heads): overwritten with d loss / d bias_table
  *   dtau  device float32 (heads): overwritten with d loss / d tau

@@ -52,6 +52,11 @@ CORE_CASES = [
     (1, 32, 32, 64, 2, 16, 8),    # SwinV2-B window
     (1, 16, 16, 128, 2, 8, 4),    # head dim 64
     (3, 16, 16, 192, 6, 8, 4),    # stage-1 shape of SwinV2-T
+    (4, 16, 16, 384, 12, 8, 0),   # stage-2 shape of SwinV2-T (12 heads, 4 windows per image)
+    (4, 16, 16, 384, 12, 8, 4),
+    (8, 8, 8, 768, 24, 8, 0),     # stage-3 shape: one window per image, shift forced to 0 (swinv2.py:328-331)
+    (1, 24, 8, 96, 3, 8, 0),      # odd number of windows and heads: the padding unit of the last pair
+    (3, 8, 24, 96, 3, 8, 4),      # ... on a shifted layer
 ]
 
 
@@ -133,7 +138,7 @@ def test_window_attention_dq_colsum(case, bwd_variant):
     do = torch.randn(B, H * W, C, generator=gen).to(DEV, torch.bfloat16)
     nW = (H // ws) * (W // ws)
     out = torch.empty(B, H * W, C, device=DEV, dtype=torch.bfloat16)
-    lse = torch.empty(B * nW, h, ws * ws, device=DEV)
+    lse = hvf.window_attention_stats(qkv, B, H, W, C, h, ws)
     hvf.window_attention_fwd_raw(qkv, tab, tau, None, out, lse, B, H, W, C, h, ws, s)
     dqkv = torch.empty_like(qkv)
     dbias, dtau, colsum = torch.empty_like(tab), torch.empty_like(tau), torch.full((C,), float("nan"), device=DEV)

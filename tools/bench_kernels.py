@@ -51,7 +51,7 @@ def bench_attn(B, res, C, heads, ws, shift, dtype, iters, tau_mode="init"):
     for _ in range(nsets):
         qkv = torch.randn(B, L, 3 * C, device=dev).to(dtype)
         out = torch.empty(B, L, C, device=dev, dtype=dtype)
-        lse = torch.empty(B * nW, heads, ws * ws, device=dev, dtype=torch.float32)
+        lse = hvf.window_attention_stats(qkv, B, res, res, C, heads, ws)
         dout = torch.randn(B, L, C, device=dev).to(dtype)
         dqkv = torch.empty_like(qkv)
         sets.append((qkv, out, lse, dout, dqkv))
