@@ -11,7 +11,8 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libhv_swin.so")
+# HV_SWIN_LIB: another build of the same library (e.g. an instrumented -DHV_TC_TRACE build); never a different backend
+LIB_PATH = os.environ.get("HV_SWIN_LIB") or os.path.join(PKG_DIR, "libhv_swin.so")
 
 HV_F32, HV_BF16, HV_U8 = 0, 1, 2
 

@@ -42,9 +42,9 @@ constexpr int kTab = 225;
 constexpr int kTile = kN * 64;         // one (window, head) q / k / v / dO tile: 64 rows x 64 B (SWIZZLE_64B)
 // Two rings: v is dead as soon as dP exists, q, k and dO live until the stores of dq, dk, dv have left the stage.
 constexpr int kStage = 6 * kTile;      // late ring:  q_a q_b k_a k_b g_a g_b   (g = dO)
-constexpr int kStages = 4;
+constexpr int kStages = 5;
 constexpr int kStageE = 2 * kTile;     // early ring: v_a v_b
-constexpr int kStagesE = 3;
+constexpr int kStagesE = 2;
 constexpr int kThreads = 896;          // 28 warps
 constexpr int kPdTile = kN * 128;      // P or dS of one unit: 64 rows x 128 B (SWIZZLE_128B)
 constexpr int kBiasRow = 20;           // floats per table row (15 + alignment slack)
@@ -56,12 +56,14 @@ constexpr int kOffStage = 0;
 constexpr int kOffStageE = kOffStage + kStages * kStage;
 constexpr int kOffP = kOffStageE + kStagesE * kStageE;    // [2 buffers][2 units][64][128 B]
 constexpr int kOffDS = kOffP + 4 * kPdTile;
-constexpr int kOffEye = kOffDS + 4 * kPdTile;             // 64 x 64 bf16 identity (SWIZZLE_128B)
-constexpr int kOffBias = kOffEye + kPdTile;               // [2 units][4 copies][kBiasCopy] float
+constexpr int kOffEye = kOffDS + 4 * kPdTile;             // 16 rows x 128 B: 16 x 16 bf16 identity in K columns 0-15 (SWIZZLE_128B)
+constexpr int kEyeBytes = 16 * 128;
+constexpr int kOffBias = kOffEye + kEyeBytes;             // [2 units][4 copies][kBiasCopy] float
 constexpr int kOffVec = kOffBias + 2 * 4 * kBiasCopy * 4; // [kStages][3: lse, r, c][2 units][64] float, SLOT order
-constexpr int kOffDot = kOffVec + kStages * 3 * 128 * 4;  // [4 pairs in flight][2 halves][128] float: sum_j dS_ij t_ij per half row
-constexpr int kOffDpart = kOffDot + 4 * 2 * 128 * 4;      // [2 parities][2 groups][2 halves][128] float: partial D
-constexpr int kOffCol = kOffDpart + 2 * 2 * 2 * 128 * 4;  // [2][32] float dq column sums, [2] d(tau)
+// [kStages pairs in flight][2 halves][128] float: first the partial D of the half row (swapped between the two owners of
+// a row), then sum_j dS_ij t_ij of the half row (read by the dQ epilogue)
+constexpr int kOffDot = kOffVec + kStages * 3 * 128 * 4;
+constexpr int kOffCol = kOffDot + kStages * 2 * 128 * 4;  // [2][32] float dq column sums, [2] d(tau)
 constexpr int kOffBins = kOffP;                           // [2][256] float: d(bias) bins, after the main loop (aliases P)
 constexpr int kOffGeo = kOffCol + (2 * 32 + 4) * 4;       // [8][2] UnitGeo
 constexpr int kOffSlotMap = kOffGeo + 8 * 2 * 16;         // [64] bytes
@@ -69,7 +71,7 @@ constexpr int kOffBar = kOffSlotMap + 64;
 constexpr int kNumBars = 5 * kStages + 2 * kStagesE + 10;
 constexpr int kOffTmem = kOffBar + kNumBars * 8;
 constexpr int kSmem = kOffTmem + 16;
-static_assert(kOffP % 1024 == 0 && kOffBias % 16 == 0 && kOffVec % 16 == 0 && kOffBar % 8 == 0, "shared-memory alignment");
+static_assert(kOffP % 1024 == 0 && kOffEye % 1024 == 0 && kOffBias % 16 == 0 && kOffVec % 16 == 0 && kOffBar % 8 == 0, "shared-memory alignment");
 static_assert(kSmem <= 227 * 1024, "shared memory budget");
 
 // TMEM columns
@@ -84,6 +86,7 @@ struct BwdParams {
   Geom g;
   int n_same, has_cross, ctas_same, ctas_cross;
   int64_t plane;  // floats per plane of the forward's statistics: B * nW * heads * 64
+  int ko;         // HV_TC_TRACE builds only: knock-out bits for bottleneck experiments (results are wrong)
 };
 // per tensor: [0] full (8, 8) | split order: [1] (wa, 8) [2] (s, 8) [3] (wa, wa) [4] (wa, s) [5] (s, wa) [6] (s, s)
 struct BwdMaps { CUtensorMap m[3][7]; };  // qkv, dout, dqkv
@@ -170,8 +173,14 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 #ifdef HV_TC_TRACE
 __device__ long long* g_btrace = nullptr;  // [pairs][16 events] clock64 stamps of CTA 0
 #define TRACE(k, ev) do { if (blockIdx.x == 0 && lane == 0 && g_btrace && (k) < 64) g_btrace[(k) * 16 + (ev)] = clock64(); } while (0)
+#define KO(bit) (p.ko & (bit))  // 1: no tile loads | 2: no tile stores | 4: no dq column sums
 #else
 #define TRACE(k, ev) do { } while (0)
+#define KO(bit) false
+#endif
+// L2 prefetch distance of the TMA producer (pairs ahead of the loads; 0 = off)
+#ifndef HV_BWD_PREFETCH
+#define HV_BWD_PREFETCH 0
 #endif
 
 template <bool V> struct BoolTag { static constexpr bool value = V; };
@@ -234,7 +243,7 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
   }
   // ---- one-time tables: identity tile, slot of every tile row, Toeplitz bias copies (log2 units), zeroed reduction bins
   unsigned char* slotmap = smem + kOffSlotMap;
-  for (int idx = threadIdx.x; idx < kPdTile / 4; idx += kThreads) {
+  for (int idx = threadIdx.x; idx < kEyeBytes / 4; idx += kThreads) {
     // 32-bit word idx of the swizzled identity: row = byte / 128, physical chunk = (byte / 16) & 7, logical chunk = phys ^ (row & 7)
     const int byte = idx * 4, row = byte >> 7, chunk = ((byte >> 4) & 7) ^ (row & 7);
     const int col = chunk * 8 + ((byte & 15) >> 1);  // first of the two bf16 columns of this word
@@ -294,8 +303,8 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
         }
         __syncwarp();
         if (lane == 0) {
-          mbar_expect_tx(bar_full(s), kStage + 6 * kStatBytes);
-          mbar_expect_tx(bar_fullE(se), kStageE);
+          mbar_expect_tx(bar_full(s), (KO(1) ? 0 : kStage) + 6 * kStatBytes);
+          mbar_expect_tx(bar_fullE(se), KO(1) ? 0 : kStageE);
         }
         __syncwarp();
         const int head = which == 0 ? work.head_a : work.head_b;
@@ -307,13 +316,34 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
           const uint32_t dst = early ? sb + kOffStageE + se * kStageE + tidx * kTile : sb + kOffStage + s * kStage + tidx * kTile;
           const uint32_t bar = early ? bar_fullE(se) : bar_full(s);
           const CUtensorMap* mm = maps.m[kind == 3 ? 1 : 0];
-          for_each_box<kSplit>(g, col0, row0, bottom, [&](int off, int mi, int col, int row) {
-            tma_load_4d(dst + off, &mm[mi], bar, c0, col, row, b);
-          });
+          if (!KO(1))
+            for_each_box<kSplit>(g, col0, row0, bottom, [&](int off, int mi, int col, int row) {
+              tma_load_4d(dst + off, &mm[mi], bar, c0, col, row, b);
+            });
         } else if (lane < 14) {
           const int plane = (lane - 8) >> 1;
           const float* src = stats + plane * p.plane + ((int64_t)r * g.heads + head) * kN;
           bulk_load(sb + kOffVec + ((s * 3 + plane) * 128 + which * 64) * 4, src, kStatBytes, bar_full(s));
+        }
+        if (HV_BWD_PREFETCH > 0 && k + HV_BWD_PREFETCH < npairs) {
+          // pull the tiles of a later pair into L2 now: its loads (issued when a stage frees up) then see L2 latency
+          bool v2;
+          const int r2 = work.row(k + HV_BWD_PREFETCH, which, nrows, v2);
+          const int b2 = r2 / g.nW, win2 = r2 - b2 * g.nW;
+          const int wh2 = win2 / g.nWw, ww2 = win2 - wh2 * g.nWw;
+          const int row2 = wh2 * kWs + g.shift, col2 = ww2 * kWs + g.shift;
+          const bool bottom2 = g.shift > 0 && wh2 == g.H / kWs - 1;
+          if (lane < 8) {
+            const int kind = lane >> 1;
+            const int c0 = (kind < 3 ? kind * g.C : 0) + head * 32;
+            const CUtensorMap* mm = maps.m[kind == 3 ? 1 : 0];
+            for_each_box<kSplit>(g, col2, row2, bottom2, [&](int, int mi, int col, int row) {
+              tma_prefetch_4d(&mm[mi], c0, col, row, b2);
+            });
+          } else if (lane < 14) {
+            const int plane = (lane - 8) >> 1;
+            bulk_prefetch(stats + plane * p.plane + ((int64_t)r2 * g.heads + head) * kN, kStatBytes);
+          }
         }
       }
     } else if (warp == 1) {
@@ -354,7 +384,9 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
       // pair k.  dBias stays one stacked M = 128 chain accumulating over all pairs.
       const uint32_t id_t = idesc_bf16(64, 32, 1, 1);    // A = P^T / dS^T (MN-major), B = dO / q^ (MN-major)
       const uint32_t id_q = idesc_bf16(64, 32, 0, 1);    // A = dS (K-major), B = k^ (MN-major)
-      const uint32_t id_b = idesc_bf16(128, 64, 0, 0);   // A = dS of both units (K-major), B = identity
+      // dBias += dS I, 16 keys at a time: A = dS of both units (K-major, 16 key columns), B = a 16 x 16 identity, D = the
+      // same 16 columns of the accumulator
+      const uint32_t id_b = idesc_bf16(128, 16, 0, 0);
       // A, MN-major view of a [query][key] tile: 64 keys = one 128-byte atom, 8 queries = 1 KB (SBO)
       const uint64_t a_pt = smem_desc(sb + kOffP, 16, 1024, 2), a_dst = smem_desc(sb + kOffDS, 16, 1024, 2);
       // A, K-major view: query rows of 128 B, 8-row groups 1 KB apart (unit b's tile follows unit a's: 128 rows for dBias)
@@ -390,7 +422,7 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
           }
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
-            umma_ss(tmem + kColDB, a_ds + bo + (uint64_t)(2 * ks), b_eye + (uint64_t)(2 * ks), id_b, (k > 0 || ks > 0) ? 1u : 0u);
+            umma_ss(tmem + kColDB + 16 * ks, a_ds + bo + (uint64_t)(2 * ks), b_eye, id_b, k > 0 ? 1u : 0u);
           umma_commit(bar_acc(buf));
           umma_commit(bar_stfree(buf));
           TRACE(k, 12);
@@ -418,7 +450,7 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
         const uint32_t st = sb + kOffStage + s * kStage;
         if (lane < 6) {
           const UnitGeo ug = geo[(k & 7) * 2 + which];
-          if (ug.rflags & 1) {
+          if ((ug.rflags & 1) && !KO(2)) {
             const uint32_t src = st + (2 * kind + which) * kTile;
             for_each_box<kSplit>(g, ug.col0, ug.row0, (ug.rflags & 2) != 0, [&](int off, int mi, int col, int row) {
               tma_store_4d(&mm[mi], src + off, c0, col, row, ug.b);
@@ -426,7 +458,7 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
           }
         }
         bulk_commit();
-        if (want_colsum) {
+        if (want_colsum && !KO(4)) {
           const int ch = lane & 3, r0 = lane >> 2;
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
@@ -495,7 +527,6 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
     const uint32_t tS = tl + kColS + 64 * grp + 32 * half, tP = tl + kColDP + 64 * grp + 32 * half;
     float acc_tau = 0.f;
     float* dots = reinterpret_cast<float*>(smem + kOffDot);
-    float* dpart = reinterpret_cast<float*>(smem + kOffDpart) + grp * 256;
     // In-place normalisation of the q / k tiles of the group's own pair once S has been computed from the raw tiles
     // (q^ = q / |q|, k^ = k / |k|): half a tile (one row per lane) per warp, after the group's own arithmetic and under the
     // same fence.proxy.async as its staging stores -- independent of the accumulator / epilogue chain
@@ -596,7 +627,7 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
       if (any_mask) { chunk(BoolTag<true>{}, IntTag<0>{}); chunk(BoolTag<true>{}, IntTag<1>{}); }
       else { chunk(BoolTag<false>{}, IntTag<0>{}); chunk(BoolTag<false>{}, IntTag<1>{}); }
       // D = both halves' partial sums: swap through shared memory with the warp that owns the other half of these rows
-      float* dpp = dpart + ((k >> 1) & 1) * 512;
+      float* dpp = dots + s * 256;
       dpp[half * 128 + row] = Dp;
       asm volatile("bar.sync %0, 64;" ::"r"(1 + grp * 4 + quad) : "memory");
       const float Di = Dp + dpp[(half ^ 1) * 128 + row];
@@ -615,7 +646,8 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
       }
       const float racc = fmaf(-Di, A2, A1);  // sum_j dS_ij t_ij over this half row: d(tau) contribution, the dQ epilogue's q^.M
       acc_tau += racc;
-      dots[((k & 3) * 2 + half) * 128 + row] = racc;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + grp * 4 + quad) : "memory");  // the other owner has read this row's partial D
+      dpp[half * 128 + row] = racc;
       hat(k);
       fence_async_smem();
       __syncwarp();
@@ -673,7 +705,7 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
       HV_TMEM_LD32(tl + kAccCols * ab + (role == 1 ? kColDK : kColDQ), a);
       float qdot = 0.f;
       if (role == 2) {
-        const float* dp = reinterpret_cast<const float*>(smem + kOffDot) + (k & 3) * 256 + row;
+        const float* dp = reinterpret_cast<const float*>(smem + kOffDot) + s * 256 + row;
         qdot = (dp[0] + dp[128]) * inv_tl;
       }
       tmem_wait_ld();
@@ -876,6 +908,10 @@ int wattn_tc64_bwd(const Geom& g, const void* qkv, const void* dout, const float
   p.n_same = g.heads / 2;
   p.has_cross = g.heads & 1;
   p.plane = (int64_t)g.B * g.nW * g.heads * kN;
+  p.ko = 0;
+#ifdef HV_TC_TRACE
+  if (getenv("HV_TC_KO")) p.ko = atoi(getenv("HV_TC_KO"));
+#endif
   const int nsm = num_sms();
   const int nrows = g.B * g.nW;
   if (p.n_same == 0) {

@@ -25,7 +25,7 @@ B, L, C, h, ws = a.batch, a.res * a.res, a.C, a.heads, a.ws
 nW = (a.res // ws) ** 2
 qkv = torch.randn(B, L, 3 * C, device=dev).to(dt)
 out = torch.empty(B, L, C, device=dev, dtype=dt)
-lse = torch.empty(B * nW, h, ws * ws, device=dev)
+lse = hvf.window_attention_stats(qkv, B, a.res, a.res, C, h, ws)
 dout = torch.randn(B, L, C, device=dev).to(dt)
 dqkv = torch.empty_like(qkv)
 tab = 16 * torch.rand((2 * ws - 1) ** 2, h, device=dev)
