@@ -218,6 +218,40 @@ __device__ __forceinline__ void rownorm2_mma(const uint32_t (&x)[2][4], int lane
   s1 = __shfl_sync(0xffffffffu, v1, src);
 }
 
+// Walks the windows idx0, idx0 + step, ... of a (B * nWh) x wcls grid of windows without divisions in the loop
+// (wcls = windows per image row that belong to the walking CTA's class; see the kernels' CtaWork)
+struct WinCursor {
+  int b, wh, ww, idx;
+  int sb, swh, sww, step, wcls, nWh;
+  __device__ __forceinline__ void init(int idx0, int step_, int wcls_, int nWh_) {
+    wcls = wcls_; nWh = nWh_; step = step_; idx = idx0;
+    int bh = idx0 / wcls;
+    ww = idx0 - bh * wcls;
+    b = bh / nWh;
+    wh = bh - b * nWh;
+    bh = step_ / wcls;
+    sww = step_ - bh * wcls;
+    sb = bh / nWh;
+    swh = bh - sb * nWh;
+  }
+  __device__ __forceinline__ void advance() {
+    idx += step;
+    ww += sww;
+    int c = ww >= wcls ? 1 : 0;
+    ww -= c ? wcls : 0;
+    wh += swh + c;
+    c = wh >= nWh ? 1 : 0;
+    wh -= c ? nWh : 0;
+    b += sb + c;
+  }
+  // the window after the current one (second unit of a cross-group pair)
+  __device__ __forceinline__ void next(int& b1, int& wh1, int& ww1) const {
+    ww1 = ww + 1; wh1 = wh; b1 = b;
+    if (ww1 >= wcls) { ww1 = 0; ++wh1; }
+    if (wh1 >= nWh) { wh1 = 0; ++b1; }
+  }
+};
+
 // one converged-warp leader: the compiler emits single-thread tcgen05 / TMA instructions without an election loop
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;

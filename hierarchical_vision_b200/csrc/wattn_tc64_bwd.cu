@@ -84,37 +84,41 @@ constexpr int kColDB = 448;
 
 struct BwdParams {
   Geom g;
-  int n_same, has_cross, ctas_same, ctas_cross;
+  // head-pair groups (both units = heads 2g, 2g+1 of one window) and the cross group (odd last head of two windows); of the
+  // ctas_same / ctas_cross CTAs of a group the last ctas_same1 / ctas_cross1 take the right-edge windows of a shifted layer
+  int n_same, has_cross, ctas_same, ctas_cross, ctas_same1, ctas_cross1;
   int64_t plane;  // floats per plane of the forward's statistics: B * nW * heads * 64
-  int ko;         // HV_TC_TRACE builds only: knock-out bits for bottleneck experiments (results are wrong)
+  int ko;         // HV_TC_TRACE builds only: knock-out bits (results are wrong) | traced CTA << 8
 };
-// per tensor: [0] full (8, 8) | split order: [1] (wa, 8) [2] (s, 8) [3] (wa, wa) [4] (wa, s) [5] (s, wa) [6] (s, s)
-struct BwdMaps { CUtensorMap m[3][7]; };  // qkv, dout, dqkv
+// per tensor, box (w, h): [0] full (8, 8) | column-split order: [1] (wa, 8) [2] (s, 8) [3] (wa, wa) [4] (wa, s) [5] (s, wa)
+// [6] (s, s) | row wrap in slot order: [7] (8, wa) [8] (8, s)
+constexpr int kNumMaps = 9;
+struct BwdMaps { CUtensorMap m[3][kNumMaps]; };  // qkv, dout, dqkv
 
+// Window classes of a shifted layer: 0 = windows left of the last window column (no column wrap: slot order, the bottom row
+// wraps as two row boxes), 1 = right-edge windows (column wrap: two column parts, permuted token order).  A CTA serves
+// one class, so that its tile order -- and with it bias lookup, mask and the d(bias) accumulator -- is uniform.
 struct CtaWork {
-  int head_a, head_b, cross, first, stride, npairs;
+  int head_a, head_b, cross, cls, first, stride, npairs, ncls, nWw, shifted;
   __device__ __forceinline__ void init(const BwdParams& p, int cta) {
     const int nrows = p.g.B * p.g.nW;
     const int same_total = p.n_same * p.ctas_same;
+    int pos, c1, ctas;
     if (cta < same_total) {
       const int grp = cta / p.ctas_same;
       cross = 0; head_a = 2 * grp; head_b = 2 * grp + 1;
-      first = cta - grp * p.ctas_same; stride = p.ctas_same;
-      npairs = first < nrows ? (nrows - first + stride - 1) / stride : 0;
+      pos = cta - grp * p.ctas_same; c1 = p.ctas_same1; ctas = p.ctas_same;
     } else {
       cross = 1; head_a = head_b = p.g.heads - 1;
-      first = cta - same_total; stride = p.ctas_cross;
-      const int nrp = (nrows + 1) / 2;
-      npairs = first < nrp ? (nrp - first + stride - 1) / stride : 0;
+      pos = cta - same_total; c1 = p.ctas_cross1; ctas = p.ctas_cross;
     }
-  }
-  __device__ __forceinline__ int row(int k, int which, int nrows, bool& valid) const {
-    const int idx = first + k * stride;
-    valid = true;
-    if (!cross) return idx;
-    const int r = 2 * idx + which;
-    if (r >= nrows) { valid = false; return nrows - 1; }
-    return r;
+    nWw = p.g.nWw;
+    shifted = p.g.shift > 0;
+    const int n1 = shifted ? nrows / nWw : 0;
+    if (pos < ctas - c1) { cls = 0; first = pos; stride = ctas - c1; ncls = nrows - n1; }
+    else { cls = 1; first = pos - (ctas - c1); stride = c1; ncls = n1; }
+    const int units = cross ? (ncls + 1) / 2 : ncls;
+    npairs = first < units ? (units - first + stride - 1) / stride : 0;
   }
 };
 
@@ -132,24 +136,31 @@ __device__ __forceinline__ int tile_row_slot(int t, int shift) {
 
 // The TMA boxes of one tile: f(byte offset inside the tile, map index, image column, image row).  The same list drives
 // the loads of q / k / v / dO and the stores of dq / dk / dv.
-template <bool kSplit, typename F>
+template <int kMode, typename F>
 __device__ __forceinline__ void for_each_box(const Geom& g, int col0, int row0, bool bottom, F&& f) {
-  if (!kSplit) {
-    f(0, 0, col0, row0);
-    return;
-  }
   const int sh = g.shift, wa = kWs - g.shift;
-  int colb = col0 + wa;
-  if (colb >= g.W) colb -= g.W;
-  const int offb = kWs * wa * 64;
-  if (!bottom) {
-    f(0, 1, col0, row0);
-    f(offb, 2, colb, row0);
-  } else {
-    f(0, 3, col0, row0);
-    f(wa * wa * 64, 4, col0, 0);
-    f(offb, 5, colb, row0);
-    f(offb + sh * wa * 64, 6, colb, 0);
+  if (kMode == 0) {
+    f(0, 0, col0, row0);
+  } else if (kMode == 1) {  // slot order; the rows of a bottom window wrap
+    if (!bottom) {
+      f(0, 0, col0, row0);
+    } else {
+      f(0, 7, col0, row0);
+      f(wa * kWs * 64, 8, col0, 0);
+    }
+  } else {                  // two column parts [0, wa) | [wa, 8); both wrap along the rows in a bottom window
+    int colb = col0 + wa;
+    if (colb >= g.W) colb -= g.W;
+    const int offb = kWs * wa * 64;
+    if (!bottom) {
+      f(0, 1, col0, row0);
+      f(offb, 2, colb, row0);
+    } else {
+      f(0, 3, col0, row0);
+      f(wa * wa * 64, 4, col0, 0);
+      f(offb, 5, colb, row0);
+      f(offb + sh * wa * 64, 6, colb, 0);
+    }
   }
 }
 
@@ -172,25 +183,25 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 #ifdef HV_TC_TRACE
 __device__ long long* g_btrace = nullptr;  // [pairs][16 events] clock64 stamps of CTA 0
-#define TRACE(k, ev) do { if (blockIdx.x == 0 && lane == 0 && g_btrace && (k) < 64) g_btrace[(k) * 16 + (ev)] = clock64(); } while (0)
+#define TRACE(k, ev) do { if (blockIdx.x == (p.ko >> 8) && lane == 0 && g_btrace && (k) < 64) g_btrace[(k) * 16 + (ev)] = clock64(); } while (0)
 #define KO(bit) (p.ko & (bit))  // 1: no tile loads | 2: no tile stores | 4: no dq column sums
 #else
 #define TRACE(k, ev) do { } while (0)
 #define KO(bit) false
 #endif
-// L2 prefetch distance of the TMA producer (pairs ahead of the loads; 0 = off)
-#ifndef HV_BWD_PREFETCH
-#define HV_BWD_PREFETCH 0
-#endif
 
 template <bool V> struct BoolTag { static constexpr bool value = V; };
 template <int V> struct IntTag { static constexpr int value = V; };
 
-template <bool kSplit>
-__global__ void __launch_bounds__(kThreads, 1)
-wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restrict__ stats, const float* __restrict__ bias_table,
-                      const float* __restrict__ tau, float* __restrict__ ws_dbias, float* __restrict__ ws_dtau,
-                      float* __restrict__ ws_colsum, int want_colsum, BwdParams p) {
+// kMode 0: unshifted layer | 1: shifted layer, windows without column wrap (slot order) | 2: shifted layer, right-edge
+// windows (column-split order)
+template <int kMode>
+__device__ __forceinline__ void wattn_tc64_bwd_body(const BwdMaps& maps, const float* __restrict__ stats,
+                                                    const float* __restrict__ bias_table, const float* __restrict__ tau,
+                                                    float* __restrict__ ws_dbias, float* __restrict__ ws_dtau,
+                                                    float* __restrict__ ws_colsum, int want_colsum, const BwdParams& p) {
+  constexpr bool kSplit = kMode == 2;
+  constexpr bool kMasked = kMode > 0;
   extern __shared__ __align__(1024) unsigned char smem[];
   const Geom& g = p.g;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -252,7 +263,7 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
     else if (col + 1 == row) w = 0x3F800000u;
     reinterpret_cast<uint32_t*>(smem + kOffEye)[idx] = w;
   }
-  if (threadIdx.x < 64) slotmap[threadIdx.x] = (unsigned char)tile_row_slot(threadIdx.x, g.shift);
+  if (threadIdx.x < 64) slotmap[threadIdx.x] = (unsigned char)tile_row_slot(threadIdx.x, kSplit ? g.shift : 0);
   for (int idx = threadIdx.x; idx < 2 * 32 + 4; idx += kThreads) reinterpret_cast<float*>(smem + kOffCol)[idx] = 0.f;
   {
     CtaWork w0;
@@ -283,68 +294,82 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
     if (warp == 0) {
       // ---------------------------------------------------------------- TMA producer: lanes 0-7 load one tile each (q, k, v,
       // dO of the two units), lanes 8-13 one plane (lse, r, c) of the forward's statistics of one unit
-      for (int k = 0; k < npairs; ++k) {
+      // the windows of this CTA: a cursor over its class's grid (cross group: two consecutive windows per pair)
+      const int nWh = g.H / kWs;
+      const int wcls = !kMasked ? g.nWw : (kSplit ? 1 : g.nWw - 1);
+      WinCursor cur;
+      cur.init(work.cross ? 2 * work.first : work.first, work.cross ? 2 * work.stride : work.stride, wcls, nWh);
+      for (int k = 0; k < npairs; ++k, cur.advance()) {
         const int s = k % kStages, se = k % kStagesE;
         mbar_wait_fast(bar_empty(s), ((k / kStages) & 1) ^ 1);
         mbar_wait_fast(bar_emptyE(se), ((k / kStagesE) & 1) ^ 1);
         TRACE(k, 0);
-        const int which = lane & 1;
-        bool valid;
-        const int r = work.row(k, which, nrows, valid);
-        const int b = r / g.nW, win = r - b * g.nW;
-        const int wh = win / g.nWw, ww = win - wh * g.nWw;
-        const int row0 = wh * kWs + g.shift, col0 = ww * kWs + g.shift;
-        const bool bottom = g.shift > 0 && wh == g.H / kWs - 1, right = g.shift > 0 && ww == g.nWw - 1;
-        if (lane < 2) {
-          UnitGeo ug;
-          ug.b = b; ug.row0 = row0; ug.col0 = col0;
-          ug.rflags = (r << 3) | (right ? 4 : 0) | (bottom ? 2 : 0) | (valid ? 1 : 0);
-          geo[(k & 7) * 2 + which] = ug;
-        }
-        __syncwarp();
-        if (lane == 0) {
-          mbar_expect_tx(bar_full(s), (KO(1) ? 0 : kStage) + 6 * kStatBytes);
-          mbar_expect_tx(bar_fullE(se), KO(1) ? 0 : kStageE);
-        }
-        __syncwarp();
-        const int head = which == 0 ? work.head_a : work.head_b;
-        if (lane < 8) {
-          const int kind = lane >> 1;  // 0 q, 1 k, 2 v, 3 dO
-          const int c0 = (kind < 3 ? kind * g.C : 0) + head * 32;
-          const bool early = kind == 2;
-          const int tidx = (kind == 0 ? 0 : (kind == 1 ? 2 : (kind == 3 ? 4 : 0))) + which;
-          const uint32_t dst = early ? sb + kOffStageE + se * kStageE + tidx * kTile : sb + kOffStage + s * kStage + tidx * kTile;
-          const uint32_t bar = early ? bar_fullE(se) : bar_full(s);
-          const CUtensorMap* mm = maps.m[kind == 3 ? 1 : 0];
-          if (!KO(1))
-            for_each_box<kSplit>(g, col0, row0, bottom, [&](int off, int mi, int col, int row) {
-              tma_load_4d(dst + off, &mm[mi], bar, c0, col, row, b);
-            });
-        } else if (lane < 14) {
-          const int plane = (lane - 8) >> 1;
-          const float* src = stats + plane * p.plane + ((int64_t)r * g.heads + head) * kN;
-          bulk_load(sb + kOffVec + ((s * 3 + plane) * 128 + which * 64) * 4, src, kStatBytes, bar_full(s));
-        }
-        if (HV_BWD_PREFETCH > 0 && k + HV_BWD_PREFETCH < npairs) {
-          // pull the tiles of a later pair into L2 now: its loads (issued when a stage frees up) then see L2 latency
-          bool v2;
-          const int r2 = work.row(k + HV_BWD_PREFETCH, which, nrows, v2);
-          const int b2 = r2 / g.nW, win2 = r2 - b2 * g.nW;
-          const int wh2 = win2 / g.nWw, ww2 = win2 - wh2 * g.nWw;
-          const int row2 = wh2 * kWs + g.shift, col2 = ww2 * kWs + g.shift;
-          const bool bottom2 = g.shift > 0 && wh2 == g.H / kWs - 1;
-          if (lane < 8) {
-            const int kind = lane >> 1;
-            const int c0 = (kind < 3 ? kind * g.C : 0) + head * 32;
-            const CUtensorMap* mm = maps.m[kind == 3 ? 1 : 0];
-            for_each_box<kSplit>(g, col2, row2, bottom2, [&](int, int mi, int col, int row) {
-              tma_prefetch_4d(&mm[mi], c0, col, row, b2);
-            });
-          } else if (lane < 14) {
-            const int plane = (lane - 8) >> 1;
-            bulk_prefetch(stats + plane * p.plane + ((int64_t)r2 * g.heads + head) * kN, kStatBytes);
+        // Every operand of the TMA instructions below is warp-uniform and ONE elected lane issues them all: a
+        // `cp.async.bulk.tensor` whose operands differ per lane compiles into a loop over the active lanes
+        int ur[2], ub[2], urow0[2], ucol0[2];
+        bool ubottom[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          int b = cur.b, wh = cur.wh, ww = cur.ww;
+          bool valid = true;
+          if (u == 1 && work.cross) {
+            if (cur.idx + 1 < work.ncls) cur.next(b, wh, ww);
+            else valid = false;  // padding unit of an odd tail: a copy of unit 0 whose results are dropped
+          }
+          if (kSplit) ww = g.nWw - 1;
+          const int r = (b * nWh + wh) * g.nWw + ww;
+          ur[u] = r; ub[u] = b;
+          urow0[u] = wh * kWs + g.shift; ucol0[u] = ww * kWs + g.shift;
+          ubottom[u] = kMasked && wh == nWh - 1;
+          if (lane == u) {
+            UnitGeo ug;
+            ug.b = b; ug.row0 = urow0[u]; ug.col0 = ucol0[u];
+            ug.rflags = (r << 3) | (kSplit ? 4 : 0) | (ubottom[u] ? 2 : 0) | (valid ? 1 : 0);
+            geo[(k & 7) * 2 + u] = ug;
           }
         }
+        __syncwarp();
+        // ONE elected lane issues every TMA instruction of the pair with warp-uniform operands (a `cp.async.bulk.tensor`
+        // whose operands differ per lane compiles into a loop over the active lanes).  Unrolled where a tile is one box;
+        // rolled on shifted layers, whose 8 tiles x up to 6 box variants would add ~10 KB to the ~35 KB of loop bodies the
+        // 28 warps of the CTA run through (measured: the unrolled form made every role of such a CTA ~2x slower --
+        // instruction-cache misses)
+        if (elect_one()) {
+          mbar_expect_tx(bar_full(s), (KO(1) ? 0 : kStage) + 6 * kStatBytes);
+          mbar_expect_tx(bar_fullE(se), KO(1) ? 0 : kStageE);
+          auto issue_tile = [&](int t) {
+            const int u = t & 1, kind = t >> 1;  // kind: 0 q, 1 k, 2 v, 3 dO
+            const int head = u == 0 ? work.head_a : work.head_b;
+            const int c0 = (kind < 3 ? kind * g.C : 0) + head * 32;
+            const bool early = kind == 2;
+            const int tidx = (kind == 0 ? 0 : (kind == 1 ? 2 : (kind == 3 ? 4 : 0))) + u;
+            const uint32_t dst = early ? sb + kOffStageE + se * kStageE + tidx * kTile : sb + kOffStage + s * kStage + tidx * kTile;
+            const uint32_t bar = early ? bar_fullE(se) : bar_full(s);
+            const CUtensorMap* mm = maps.m[kind == 3 ? 1 : 0];
+            const int bb = u ? ub[1] : ub[0];
+            if (!KO(1))
+              for_each_box<kMode>(g, u ? ucol0[1] : ucol0[0], u ? urow0[1] : urow0[0], u ? ubottom[1] : ubottom[0],
+                                  [&](int off, int mi, int col, int row) { tma_load_4d(dst + off, &mm[mi], bar, c0, col, row, bb); });
+          };
+          auto issue_stats = [&](int t) {
+            const int u = t & 1, plane = t >> 1;
+            const int head = u == 0 ? work.head_a : work.head_b;
+            bulk_load(sb + kOffVec + ((s * 3 + plane) * 128 + u * 64) * 4,
+                      stats + plane * p.plane + ((int64_t)(u ? ur[1] : ur[0]) * g.heads + head) * kN, kStatBytes, bar_full(s));
+          };
+          if (kMasked) {
+#pragma unroll 1
+            for (int t = 0; t < 8; ++t) issue_tile(t);
+#pragma unroll 1
+            for (int t = 0; t < 6; ++t) issue_stats(t);
+          } else {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) issue_tile(t);
+#pragma unroll
+            for (int t = 0; t < 6; ++t) issue_stats(t);
+          }
+        }
+        __syncwarp();
       }
     } else if (warp == 1) {
       // ---------------------------------------------------------------- issuer of S = Q K^T and dP = dO V^T
@@ -432,31 +457,41 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
     } else {
       // ---------------------------------------------------------------- warp 3: TMA stores of dq, dk, dv + dq column sums
       // The epilogue warps have written dq over the q tile, dk over the k tile and dv over the dO tile of the stage (same
-      // swizzled layout the loads produced), so the boxes of the loads are the boxes of the stores.  Lanes 0-5 own one
-      // tile each.  While the TMA engine reads the stage the warp sums the dq tiles over their rows (gradient of q_bias).
+      // swizzled layout the loads produced), so the boxes of the loads are the boxes of the stores.  While the TMA engine
+      // reads the stage the warp sums the dq tiles over their rows (gradient of q_bias).
       float cs[2][8];
 #pragma unroll
       for (int u = 0; u < 2; ++u)
 #pragma unroll
         for (int e = 0; e < 8; ++e) cs[u][e] = 0.f;
-      const int which = lane & 1, kind = lane >> 1;  // kind: 0 dq (q tile), 1 dk (k tile), 2 dv (dO tile)
-      const int head = which == 0 ? work.head_a : work.head_b;
-      const int c0 = kind * g.C + head * 32;
       const CUtensorMap* mm = maps.m[2];
       for (int k = 0; k < npairs; ++k) {
         const int s = k % kStages;
         mbar_wait_fast(bar_written(s), (k / kStages) & 1);
         TRACE(k, 14);
         const uint32_t st = sb + kOffStage + s * kStage;
-        if (lane < 6) {
-          const UnitGeo ug = geo[(k & 7) * 2 + which];
-          if ((ug.rflags & 1) && !KO(2)) {
-            const uint32_t src = st + (2 * kind + which) * kTile;
-            for_each_box<kSplit>(g, ug.col0, ug.row0, (ug.rflags & 2) != 0, [&](int off, int mi, int col, int row) {
-              tma_store_4d(&mm[mi], src + off, c0, col, row, ug.b);
-            });
+        if (elect_one()) {  // warp-uniform operands, one issuing lane (see the producer)
+          auto store_tile = [&](int t) {
+            const int u = t & 1, kind = t >> 1;  // kind: 0 dq (q tile), 1 dk (k tile), 2 dv (dO tile)
+            const UnitGeo ug = geo[(k & 7) * 2 + u];
+            const int head = u == 0 ? work.head_a : work.head_b;
+            if ((ug.rflags & 1) && !KO(2)) {
+              const uint32_t src = st + (2 * kind + u) * kTile;
+              const int c0 = kind * g.C + head * 32;
+              for_each_box<kMode>(g, ug.col0, ug.row0, (ug.rflags & 2) != 0, [&](int off, int mi, int col, int row) {
+                tma_store_4d(&mm[mi], src + off, c0, col, row, ug.b);
+              });
+            }
+          };
+          if (kMasked) {
+#pragma unroll 1
+            for (int t = 0; t < 6; ++t) store_tile(t);
+          } else {
+#pragma unroll
+            for (int t = 0; t < 6; ++t) store_tile(t);
           }
         }
+        __syncwarp();
         bulk_commit();
         if (want_colsum && !KO(4)) {
           const int ch = lane & 3, r0 = lane >> 2;
@@ -514,7 +549,7 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
                              (ih + 7) * kBiasRow + (7 - iw - cpy) + 4 + (kSplit ? 4 * half : -(4 * half) * kBiasRow);
     // masks of a shifted layer: bit j set = key j of this thread's half sits on the other side of the wrap than the query
     uint32_t mH = 0u, mW = 0u;
-    if (kSplit) {
+    if (kMasked) {
       const int thr = kWs - g.shift;
       for (int j = 0; j < 32; ++j) {
         const int sj = slotmap[32 * half + j];
@@ -565,8 +600,7 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
       // c_j of keys 4q .. 4q + 3 of this half (slot order): slot order = tile order | split order: window row q, columns 4 half ..
       const float* cv = vec + 256 + 64 * u + (kSplit ? 4 * half : 32 * half);
       uint32_t m = 0u;
-      if (kSplit) m = ((rflags & 2) ? mH : 0u) | ((rflags & 4) ? mW : 0u);
-      const bool any_mask = kSplit && __any_sync(0xffffffffu, m != 0u);
+      if (kMasked) m = ((rflags & 2) ? mH : 0u) | ((rflags & 4) ? mW : 0u);
       if (k > 1) mbar_wait_fast(bar_stfree(grp), ((k >> 1) - 1) & 1);  // the MMAs of pair k-2 have read this group's staging tiles
       mbar_wait_fast(bar_sdp(s), ph);
       if (warp == 4) TRACE(k, 6);
@@ -624,8 +658,10 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
           sts128(p_row + off, make_uint4(pk[w0], pk[w0 + 1], pk[w0 + 2], pk[w0 + 3]));
         }
       };
-      if (any_mask) { chunk(BoolTag<true>{}, IntTag<0>{}); chunk(BoolTag<true>{}, IntTag<1>{}); }
-      else { chunk(BoolTag<false>{}, IntTag<0>{}); chunk(BoolTag<false>{}, IntTag<1>{}); }
+      // one instantiation per kernel mode: a second (unmasked) copy of this loop body for the interior windows of a shifted
+      // layer costs more in instruction-cache misses than the two predicated instructions per logit it would save
+      chunk(BoolTag<kMasked>{}, IntTag<0>{});
+      chunk(BoolTag<kMasked>{}, IntTag<1>{});
       // D = both halves' partial sums: swap through shared memory with the warp that owns the other half of these rows
       float* dpp = dots + s * 256;
       dpp[half * 128 + row] = Dp;
@@ -803,6 +839,24 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
 }
 
+template <bool kShift>
+__global__ void __launch_bounds__(kThreads, 1)
+wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restrict__ stats, const float* __restrict__ bias_table,
+                      const float* __restrict__ tau, float* __restrict__ ws_dbias, float* __restrict__ ws_dtau,
+                      float* __restrict__ ws_colsum, int want_colsum, const __grid_constant__ BwdParams p) {
+  if (!kShift) {
+    wattn_tc64_bwd_body<0>(maps, stats, bias_table, tau, ws_dbias, ws_dtau, ws_colsum, want_colsum, p);
+  } else {
+    // class of this CTA (see CtaWork): the last ctas_*1 CTAs of every group take the right-edge windows
+    const int same_total = p.n_same * p.ctas_same;
+    const int cta = blockIdx.x;
+    const bool edge = cta < same_total ? (cta % p.ctas_same) >= p.ctas_same - p.ctas_same1
+                                       : (cta - same_total) >= p.ctas_cross - p.ctas_cross1;
+    if (edge) wattn_tc64_bwd_body<2>(maps, stats, bias_table, tau, ws_dbias, ws_dtau, ws_colsum, want_colsum, p);
+    else wattn_tc64_bwd_body<1>(maps, stats, bias_table, tau, ws_dbias, ws_dtau, ws_colsum, want_colsum, p);
+  }
+}
+
 // Sum the per-CTA partials.  CTA c of a same-window group holds heads (2 grp, 2 grp + 1) in units 0 / 1; the CTAs of the
 // cross group hold the last (odd) head in both units.  One warp per output value: the lanes stride over the CTAs (a serial
 // loop over ~100 partial rows would cost more than the attention kernel's own tail).
@@ -864,7 +918,7 @@ bool wattn_tc64_bwd_supported(const Geom& g, int dtype) {
 
 size_t wattn_tc64_bwd_workspace_bytes(const Geom& g) {
   (void)g;
-  return (size_t)num_sms() * (2 * kTab + 2 + 64) * sizeof(float) + 256;
+  return (size_t)(2 * num_sms()) * (2 * kTab + 2 + 64) * sizeof(float) + 256;  // one row of partials per CTA; grid <= 2 * SMs
 }
 
 // `stats`: the three planes (lse | r | c) written by the forward kernels of this geometry (hv_window_attn_stats_floats)
@@ -889,12 +943,12 @@ int wattn_tc64_bwd(const Geom& g, const void* qkv, const void* dout, const float
   if (!mp) {
     MapEntry& e = cache[cache_next];
     const int s = g.shift, wa = kWs - g.shift;
-    const int bw[7] = {kWs, s ? wa : kWs, s ? s : kWs, s ? wa : kWs, s ? wa : kWs, s ? s : kWs, s ? s : kWs};
-    const int bh[7] = {kWs, kWs, kWs, s ? wa : kWs, s ? s : kWs, s ? wa : kWs, s ? s : kWs};
+    const int bw[kNumMaps] = {kWs, s ? wa : kWs, s ? s : kWs, s ? wa : kWs, s ? wa : kWs, s ? s : kWs, s ? s : kWs, kWs, kWs};
+    const int bh[kNumMaps] = {kWs, kWs, kWs, s ? wa : kWs, s ? s : kWs, s ? wa : kWs, s ? s : kWs, s ? wa : kWs, s ? s : kWs};
     const void* base[3] = {qkv, dout, dqkv};
     const int row_elems[3] = {3 * g.C, g.C, 3 * g.C};
     for (int t = 0; t < 3; ++t)
-      for (int i = 0; i < 7; ++i) {
+      for (int i = 0; i < kNumMaps; ++i) {
         const int rc = make_map(&e.maps.m[t][i], base[t], g, row_elems[t], bw[i], bh[i]);
         if (rc) return rc;
       }
@@ -911,6 +965,7 @@ int wattn_tc64_bwd(const Geom& g, const void* qkv, const void* dout, const float
   p.ko = 0;
 #ifdef HV_TC_TRACE
   if (getenv("HV_TC_KO")) p.ko = atoi(getenv("HV_TC_KO"));
+  if (getenv("HV_TC_TRACE_CTA")) p.ko |= atoi(getenv("HV_TC_TRACE_CTA")) << 8;
 #endif
   const int nsm = num_sms();
   const int nrows = g.B * g.nW;
@@ -928,6 +983,24 @@ int wattn_tc64_bwd(const Geom& g, const void* qkv, const void* dout, const float
   if (p.ctas_same < 1 && p.n_same) p.ctas_same = 1;
   if (p.ctas_same > nrows) p.ctas_same = nrows;
   if (p.ctas_cross > (nrows + 1) / 2) p.ctas_cross = (nrows + 1) / 2;
+  // shifted layer: split every group's CTAs between the two window classes in proportion to their work (a right-edge
+  // window costs kEdgeCost x an interior one: twice the TMA boxes, every row masked; HV_EDGE_COST overrides for tuning)
+  p.ctas_same1 = p.ctas_cross1 = 0;
+  if (g.shift > 0) {
+    const int n1 = nrows / g.nWw, n0 = nrows - n1;
+    static const double kEdgeCost = []() { const char* e = getenv("HV_EDGE_COST"); return e ? atof(e) : 1.2; }();
+    auto split = [&](int& ctas) {
+      if (ctas == 0) return 0;
+      if (n0 == 0) return ctas;
+      if (ctas < 2) ctas = 2;
+      int c1 = (int)((double)ctas * kEdgeCost * n1 / (n0 + kEdgeCost * n1) + 0.5);
+      if (c1 < 1) c1 = 1;
+      if (c1 > ctas - 1) c1 = ctas - 1;
+      return c1;
+    };
+    p.ctas_same1 = split(p.ctas_same);
+    p.ctas_cross1 = split(p.ctas_cross);
+  }
   const int grid = p.n_same * p.ctas_same + p.ctas_cross;
   float* ws_dbias = static_cast<float*>(workspace);
   float* ws_dtau = ws_dbias + (size_t)grid * 2 * kTab;
