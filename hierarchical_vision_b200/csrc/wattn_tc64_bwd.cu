@@ -499,8 +499,8 @@ __device__ __forceinline__ void wattn_tc64_bwd_body(const BwdMaps& maps, const f
           for (int u = 0; u < 2; ++u) {
             if (!(geo[(k & 7) * 2 + u].rflags & 1)) continue;
             const uint32_t tile = st + u * kTile;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
+#pragma unroll 1
+            for (int i = 0; i < 8; ++i) {  // rolled: code size (see the producer)
               const int row = r0 + 8 * i;
               const uint4 v = lds128(tile + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
               cs[u][0] += bf16lo_to_f32(v.x); cs[u][1] += bf16hi_to_f32(v.x);
