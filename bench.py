@@ -12,11 +12,12 @@ One JSON line on rank 0:
   value     whole-job images/s with the uint8 batch already resident in HBM
   e2e       same step driven from pinned HOST buffers: H2D copy of the images/labels and a D2H read of
             the loss inside the timed region
-  roofline  the dominant hand-written kernel (stage-0 fused window-attention backward): algorithmic bytes
-            per launch / its mean duration measured with CUDA events inside the timed region
+  roofline  the dominant hand-written kernel (the fused window-attention launch group with the largest total time;
+            its name comes from the library's dispatch): algorithmic bytes per launch / mean duration (CUDA events)
   window_attn  aggregate over every fused window-attention launch (fwd+bwd) of the timed region: windows/s
             and fraction of the HBM roofline (12*N*C*e bytes per window)
-  cpu_baseline  the oracle (CPU restatement of the reference's algorithm) timed on this box's host cores
+  cpu_baseline  the reference's CPU path (unmodified swinv2.py from oracle/_ref, else the oracle port) on this box's
+            host cores: SwinV2-T img/s and, under window_attn.cpu_block_cfg0, BASELINE configs[0] windows/s
 """
 from __future__ import annotations
 
@@ -118,48 +119,98 @@ def build_model(device, drop_path_rate=0.1):
     return T.Model(backbone).to(device)
 
 
-def cpu_baseline(seconds_budget=14.0, batch=8, steps=None, warmup=1):
-    """The oracle port (oracle/swin_oracle.py, torch CPU ops = what the reference's swinv2.py executes)
-    on this box's host cores: SwinV2-T fwd+bwd+SGD on a bounded sample of the same workload."""
-    from oracle import swin_oracle as O
-
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    spec = O.SWINV2_T
-    p = {k: v.requires_grad_(True) for k, v in O.init_state(spec, seed=0).items()}
-    params = list(p.values())
-    opt = torch.optim.SGD(params, lr=0.01, momentum=0.875, weight_decay=5e-4)
-    g = torch.Generator().manual_seed(1)
-    img = torch.randn(batch, 3, 256, 256, generator=g)
-    lab = torch.randint(0, 10000, (batch,), generator=g)
-
-    def one():
-        opt.zero_grad(set_to_none=True)
-        loss = torch.nn.functional.cross_entropy(O.swin_model(img, p, spec), lab)
-        loss.backward()
-        opt.step()
-        return float(loss)
-
+def _timed_loop(one, seconds_budget, steps, warmup, max_steps=20):
     for _ in range(warmup):
         one()
     times = []
     t_start = time.perf_counter()
-    n = 0
     while True:
         t0 = time.perf_counter()
         one()
         times.append(time.perf_counter() - t0)
-        n += 1
         if steps is not None:
-            if n >= steps:
+            if len(times) >= steps:
                 break
-        elif time.perf_counter() - t_start > seconds_budget or n >= 20:
+        elif time.perf_counter() - t_start > seconds_budget or len(times) >= max_steps:
             break
-    total = sum(times)
-    return {"value": batch * n / total, "unit": "img/s", "cores": cores, "kind": "port",
-            "sample": f"{n} steps of batch {batch} (fp32, SwinV2-T 256x256 fwd+bwd+SGD, torch CPU ops, "
-                      f"{torch.get_num_threads()} threads); best step {min(times) * 1e3:.0f} ms",
-            "ms_per_step": total / n * 1e3, "steps": n, "batch": batch}
+    return times
+
+
+def cpu_baseline(seconds_budget=12.0, batch=8, steps=None, warmup=1):
+    """The reference's CPU path on this box's host cores, on a bounded sample of the same workload: SwinV2-T
+    fwd+bwd+SGD (img/s) and the BASELINE configs[0] block (windows/s).  kind "reference": the UNMODIFIED reference
+    swinv2.py (oracle/_ref, placed by oracle/build_ref.py; /root/reference in the build container);
+    kind "port": the oracle restatement (oracle/swin_oracle.py) when that file is not available."""
+    from oracle import ref_loader
+    from oracle import swin_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(1)
+    img = torch.randn(batch, 3, 256, 256, generator=g)
+    lab = torch.randint(0, 10000, (batch,), generator=g)
+    kind = "reference" if ref_loader.available() else "port"
+    if kind == "reference":
+        ref = ref_loader.load()
+        torch.manual_seed(0)
+        net = ref.SwinTransformerV2(img_size=256, window_size=8, embed_dim=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24],
+                                    num_classes=10000, drop_path_rate=0.1)
+        with torch.no_grad():  # the reference zero-inits the blocks' LayerNorm affine (swinv2.py:603-608): make them work
+            for layer in net.layers:
+                for blk in layer.blocks:
+                    for n in (blk.norm1, blk.norm2):
+                        n.weight.normal_(1.0, 0.1)
+                        n.bias.normal_(0.0, 0.1)
+        net.train()
+        opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.875, weight_decay=5e-4, nesterov=True)  # optim.py:16-23
+
+        def one():
+            opt.zero_grad(set_to_none=True)
+            loss = torch.nn.functional.cross_entropy(net(img), lab)
+            loss.backward()
+            opt.step()
+            return float(loss.detach())
+
+        # BASELINE configs[0]: WindowAttention block fwd+bwd, batch 8, 64x64 tokens, window 8, 3 heads, dim 96, shifted
+        blk = ref.SwinTransformerBlock(dim=96, input_resolution=(64, 64), num_heads=3, window_size=8, shift_size=4)
+        with torch.no_grad():
+            for n in (blk.norm1, blk.norm2):
+                n.weight.normal_(1.0, 0.1)
+                n.bias.normal_(0.0, 0.1)
+        xb = torch.randn(8, 4096, 96, generator=g, requires_grad=True)
+        gb = torch.randn(8, 4096, 96, generator=g)
+
+        def one_block():
+            blk.zero_grad(set_to_none=True)
+            xb.grad = None
+            blk(xb).backward(gb)
+    else:
+        spec = O.SWINV2_T
+        p = {k: v.requires_grad_(True) for k, v in O.init_state(spec, seed=0).items()}
+        opt = torch.optim.SGD(list(p.values()), lr=0.01, momentum=0.875, weight_decay=5e-4, nesterov=True)
+
+        def one():
+            opt.zero_grad(set_to_none=True)
+            loss = torch.nn.functional.cross_entropy(O.swin_model(img, p, spec), lab)
+            loss.backward()
+            opt.step()
+            return float(loss.detach())
+
+        one_block = None
+
+    times = _timed_loop(one, seconds_budget, steps, warmup)
+    n, total = len(times), sum(times)
+    out = {"value": batch * n / total, "unit": "img/s", "cores": cores, "kind": kind,
+           "sample": f"{n} steps of batch {batch} (fp32, SwinV2-T 256x256 fwd+bwd+SGD, "
+                     f"{'unmodified reference swinv2.py' if kind == 'reference' else 'oracle port'}, torch CPU ops, "
+                     f"{torch.get_num_threads()} threads); best step {min(times) * 1e3:.0f} ms",
+           "ms_per_step": total / n * 1e3, "steps": n, "batch": batch}
+    if one_block is not None:
+        bt = _timed_loop(one_block, 4.0, None, 1, max_steps=10)
+        out["block_cfg0"] = {"windows_per_s_fwd_bwd": 512 * len(bt) / sum(bt), "best_windows_per_s": 512 / min(bt),
+                             "sample": f"{len(bt)} x SwinTransformerBlock fwd+bwd (BASELINE configs[0]: batch 8, 64x64 "
+                                       f"tokens, window 8, 3 heads, dim 96, shift 4 = 512 windows), fp32, {cores} threads"}
+    return out
 
 
 def run_reference(args):
@@ -171,10 +222,13 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "per_step_sample": "batch 8 on the host CPU",
-                       "note": "the reference is pure Python/PyTorch with no tests or GPU kernels of its own; its "
-                               "CPU path is timed through the oracle port (oracle/swin_oracle.py), all host threads"},
+                       "note": "the reference is pure Python/PyTorch with no GPU kernels of its own; its CPU path is "
+                               "timed on all host threads -- the unmodified swinv2.py from oracle/_ref when present "
+                               "(kind reference), else the oracle port"},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if "block_cfg0" in cb:
+        line["window_attn_block_cpu"] = cb["block_cfg0"]
     print(json.dumps(line), flush=True)
 
 
@@ -303,37 +357,46 @@ def run_ours(args):
         d["ms"] += a.elapsed_time(b)
         d["launches"] += 1
         d["windows"] += windows
-    stage_dims = {"C96": 96, "C192": 192, "C384": 384, "C768": 768}
-    tot_bytes = tot_ms = tot_windows0 = 0.0
+    stage = {"C96": (96, 3, 64), "C192": (192, 6, 32), "C384": (384, 12, 16), "C768": (768, 24, 8)}  # C: heads, resolution
+    tot_bytes = tot_ms = 0.0
     kernels = {}
     for tag, d in sorted(per_tag.items()):
-        kind, cname = tag.split("/")
-        C = stage_dims.get(cname)
-        if C is None:
+        kind, cname, sname = tag.split("/")
+        if cname not in stage:
             continue
+        C, heads, res = stage[cname]
+        shift = int(sname[1:])
         mult = 4 if kind == "attn_fwd" else 8
         nbytes = d["windows"] * mult * 64 * C * 2
-        kernels[tag] = {"launches": d["launches"], "ms_per_launch": d["ms"] / d["launches"],
+        kernels[tag] = {"kernel": hvf.window_attention_kernel_name(B, res, res, C, heads, 8, shift, torch.bfloat16, kind == "attn_bwd"),
+                        "launches": d["launches"], "ms_per_launch": d["ms"] / d["launches"], "ms_total": d["ms"],
                         "gbs": nbytes / d["ms"] / 1e6, "frac": nbytes / d["ms"] / 1e6 / peak}
         tot_bytes += nbytes
         tot_ms += d["ms"]
-        if cname == "C96" and kind == "attn_fwd":
-            tot_windows0 += d["windows"]
-    dom = "attn_bwd/C96"
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "attn_dram_traffic.json")
-    if os.path.exists(tpath) and dom in per_tag:
-        rec = json.load(open(tpath)).get(dom)
-        if rec:
-            traffic = rec["dram_bytes_per_window"] * per_tag[dom]["windows"] / per_tag[dom]["launches"]
+    # the dominant hand-written kernel of the step: the fused-attention launch group with the largest total time
+    dom = max(kernels, key=lambda t: kernels[t]["ms_total"]) if kernels else None
     roofline = None
-    if dom in kernels:
+    if dom is not None:
         k = kernels[dom]
-        roofline = {"bound": "hbm", "kernel": "wattn_mma64_bwd_kernel<3> (stage 0: C 96, 3 heads, window 8)",
+        kind, cname, sname = dom.split("/")
+        C, heads, res = stage[cname]
+        win_per_launch = per_tag[dom]["windows"] / per_tag[dom]["launches"]
+        # DRAM traffic: not measurable inside this run (no profiler in a bench run); a committed `ncu --set full` capture of
+        # the same kernel at the same shape, scaled per window, labelled as such
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "attn_dram_traffic.json")
+        if os.path.exists(tpath):
+            rec = json.load(open(tpath)).get(k["kernel"] + "/" + cname)
+            if rec:
+                traffic = rec["dram_bytes_per_window"] * win_per_launch
+                traffic_src = "static: " + rec.get("source", "ncu capture under profiles/")
+        roofline = {"bound": "hbm", "kernel": f"{k['kernel']} (stage {list(stage).index(cname)}: C {C}, {heads} heads, window 8, "
+                                              f"shift {sname[1:]}; {'backward' if kind == 'attn_bwd' else 'forward'})",
                     "achieved": k["gbs"], "peak": peak, "unit": "GB/s", "frac": k["frac"], "traffic": traffic,
-                    "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": per_tag[dom]["windows"] / per_tag[dom]["launches"] * 8 * 64 * 96 * 2,
-                    "ms_per_launch": k["ms_per_launch"]}
+                    "traffic_source": traffic_src, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": win_per_launch * (8 if kind == "attn_bwd" else 4) * 64 * C * 2,
+                    "ms_per_launch": k["ms_per_launch"],
+                    "selection": "fused-attention launch group with the largest total time in the step (CUDA events)"}
     attn_windows = sum(d["windows"] for t, d in per_tag.items() if t.startswith("attn_fwd"))
     window_attn = {"windows_per_s_fwd_bwd": attn_windows / (tot_ms / 1e3) if tot_ms else None,
                    "hbm_gbs": tot_bytes / tot_ms / 1e6 if tot_ms else None,
@@ -345,6 +408,8 @@ def run_ours(args):
                    else "CUDA events around each launch inside the timed region"}
 
     cb = cpu_baseline() if (env.world_size == 1 and not args.no_cpu_baseline) else None
+    if cb and "block_cfg0" in cb:
+        window_attn["cpu_block_cfg0"] = cb["block_cfg0"]
     n = env.world_size
     imgs = B * n * args.steps
     line = {"metric": METRIC, "value": imgs / (ms_total / 1e3), "unit": "img/s", "n_gpus": n, "steps": args.steps,
@@ -352,11 +417,12 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * n,
                        "precision": "torch.autocast(bfloat16), fp32 master weights, bf16 activations",
-                       "optimizer": "SGD momentum 0.875 wd 5e-4, grad-clip 2.0, drop_path 0.1", "parallelism": f"dp{n}",
+                       "optimizer": "DecoupledSGDW (reference default) momentum 0.875 wd 5e-4, grad-clip 2.0, drop_path 0.1", "parallelism": f"dp{n}",
                        "e2e_input": ("every step copies its uint8 batch + labels from pinned host memory (side stream, overlapped "
                                      "with the previous step) and reads the loss back") if use_graph else "copy, step, read back",
-                       "launch": ("one CUDA graph per step (flat fp32 gradient buffer, one NCCL all-reduce(avg) captured "
-                                  "in the graph when N > 1)") if use_graph else "eager, DistributedDataParallel",
+                       "launch": ("one CUDA graph per step (flat fp32 gradient buffer; when N > 1 its NCCL all-reduce(avg) is "
+                                  "issued per stage bucket from inside the backward pass and captured in the graph)")
+                       if use_graph else "eager, DistributedDataParallel",
                        "l2": "no flush needed: each step streams > 10 GB of activations, far beyond the 126 MB L2"},
             "clocks": clocks,
             "e2e": {"value": imgs / (ms_e2e / 1e3), "unit": "img/s", "ms_per_step": ms_e2e / args.steps,

@@ -26,6 +26,7 @@ SIGNATURES = {
     "hv_window_attn_fwd_variant": (_I, [_I]),
     "hv_window_attn_bwd_variant": (_I, [_I]),
     "hv_window_attn_stats_floats": (_S, [_I, _I, _I, _I, _I, _I, _I]),
+    "hv_window_attn_kernel_name": (_I, [_I, _I, _I, _I, _I, _I, _I, _I, _I, c_char_p, _I]),
     "hv_relative_position_index": (_I, [_I, _P]),
     "hv_shift_window_mask": (_I, [_I, _I, _I, _I, _P]),
     "hv_window_token_index": (_I, [_I, _I, _I, _I, _I, _P]),
@@ -34,6 +35,8 @@ SIGNATURES = {
     "hv_window_attn_bwd_workspace_bytes": (_S, [_I, _I, _I, _I, _I, _I, _I]),
     "hv_window_attn_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _S,
                                 _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "hv_dq_colsum_workspace_bytes": (_S, [_I]),
+    "hv_dq_colsum": (_I, [_P, _P, _P, _S, _L, _I, _I, _P]),
     "hv_ln_residual_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _L, _F, _I, _I, _P]),
     "hv_ln_residual_bwd_workspace_bytes": (_S, [_L, _I]),
     "hv_ln_residual_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _S, _L, _I, _L, _I, _I, _P]),

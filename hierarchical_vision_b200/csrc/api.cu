@@ -18,6 +18,9 @@ int wattn_fwd_variant_set(int v);
 int wattn_tc64_fwd(const Geom& g, const void* qkv, const float* bias_table, const float* tau, void* out, float* lse,
                    cudaStream_t st);
 size_t wattn_mma64_bwd_workspace_bytes(const Geom& g);
+size_t dq_colsum_workspace_bytes(int C);
+int dq_colsum(const void* dqkv, int64_t tokens, int C, float* out, void* workspace, size_t workspace_bytes, cudaStream_t st);
+int wattn_mma64_heads_per_cta(int heads);
 bool wattn_tc64_bwd_supported(const Geom& g, int dtype);
 int wattn_bwd_variant_set(int v);
 size_t wattn_tc64_bwd_workspace_bytes(const Geom& g);
@@ -143,6 +146,24 @@ size_t hv_window_attn_stats_floats(int B, int H, int W, int C, int heads, int ws
   return wattn_mma64_supported(g, dtype) ? 3 * plane : plane;
 }
 
+int hv_window_attn_kernel_name(int B, int H, int W, int C, int heads, int ws, int shift, int dtype, int backward, char* out,
+                               int out_len) {
+  if (!out || out_len <= 0) HV_FAIL(HV_ERR_NULL, "hv_window_attn_kernel_name: out is NULL");
+  Geom g;
+  int rc = make_checked_geom(B, H, W, C, heads, ws, shift, g);
+  if (rc) return rc;
+  // the same decisions as hv_window_attn_fwd / _bwd (mask == NULL)
+  if (!wattn_mma64_supported(g, dtype))
+    snprintf(out, out_len, "wattn_generic_%s_kernel<%s>", backward ? "bwd" : "fwd", dtype == HV_BF16 ? "bf16" : "float");
+  else if (!backward && wattn_tc64_supported(g, dtype))
+    snprintf(out, out_len, "wattn_tc64_fwd_kernel");
+  else if (backward && wattn_tc64_bwd_supported(g, dtype))
+    snprintf(out, out_len, "wattn_tc64_bwd_kernel<%s>", shift > 0 ? "true" : "false");
+  else
+    snprintf(out, out_len, "wattn_mma64_%s_kernel<%d>", backward ? "bwd" : "fwd", wattn_mma64_heads_per_cta(heads));
+  return HV_OK;
+}
+
 int hv_relative_position_index(int ws, int64_t* out) {
   if (!out) HV_FAIL(HV_ERR_NULL, "hv_relative_position_index: out is NULL");
   if (ws <= 0) HV_FAIL(HV_ERR_SHAPE, "ws=%d", ws);
@@ -251,6 +272,18 @@ int hv_window_attn_bwd(const void* qkv, const void* out, const void* dout, const
     HV_FAIL(HV_ERR_SHAPE, "hv_window_attn_bwd: dq_colsum is only produced by the tensor-core kernel "
                           "(hv_window_attn_kernel_kind() == 1 and mask == NULL)");
   return wattn_generic_bwd(g, dtype, qkv, out, dout, lse, bias_table, tau, mask, mask_windows, dqkv, dbias_table, dtau, st);
+}
+
+size_t hv_dq_colsum_workspace_bytes(int C) { return C > 0 ? dq_colsum_workspace_bytes(C) : 0; }
+
+int hv_dq_colsum(const void* dqkv, float* dq_colsum_out, void* workspace, size_t workspace_bytes, int64_t tokens, int C,
+                 int dtype, void* stream) {
+  if (!dqkv || !dq_colsum_out) HV_FAIL(HV_ERR_NULL, "hv_dq_colsum: NULL argument");
+  if (dtype != HV_BF16) HV_FAIL(HV_ERR_DTYPE, "hv_dq_colsum: bf16 only (the tensor-core attention path)");
+  if (tokens <= 0 || C <= 0) HV_FAIL(HV_ERR_SHAPE, "hv_dq_colsum: tokens=%lld C=%d", (long long)tokens, C);
+  int rc = check_device_arch();
+  if (rc) return rc;
+  return dq_colsum(dqkv, tokens, C, dq_colsum_out, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int hv_ln_residual_fwd(const void* y, const void* shortcut, const float* gamma, const float* beta, const float* bias,

@@ -44,7 +44,9 @@ __device__ __forceinline__ float tanh_fast(float x) {
 }
 __device__ __forceinline__ GeluParts gelu_parts_bf16(float x) {
   constexpr float c1 = 0.7974857091903687f, c3 = 0.03703207150101662f, c5 = -0.000356393022229895f;
-  const float x2 = x * x;
+  // c5 < 0: unclamped, the polynomial turns around at |x| ~ 8.3 and changes sign at ~11 (GELU(12) would come out as 0).
+  // With x^2 capped at 64 the tanh argument is monotone (1.7 x beyond |x| = 8) and tanh saturates to +-1, sech^2 to 0.
+  const float x2 = fminf(x * x, 64.0f);
   const float t = tanh_fast(x * fmaf(x2, fmaf(x2, c5, c3), c1));
   GeluParts p;
   p.cdf = fmaf(0.5f, t, 0.5f);
@@ -59,7 +61,8 @@ __device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
 template <bool DERIV>
 __device__ __forceinline__ GeluParts2 gelu_parts_bf16x2(float2 x) {
   constexpr float c1 = 0.7974857091903687f, c3 = 0.03703207150101662f, c5 = -0.000356393022229895f;
-  const float2 x2 = __fmul2_rn(x, x);
+  float2 x2 = __fmul2_rn(x, x);
+  x2 = make_float2(fminf(x2.x, 64.0f), fminf(x2.y, 64.0f));  // see gelu_parts_bf16
   const float2 u = __fmul2_rn(x, __ffma2_rn(x2, __ffma2_rn(x2, splat2(c5), splat2(c3)), splat2(c1)));
   const float2 t = make_float2(tanh_fast(u.x), tanh_fast(u.y));
   GeluParts2 p;

@@ -1122,6 +1122,8 @@ int launch_bwd(const Geom& g, const void* qkv, const void* out, const void* dout
 
 }  // namespace
 
+int wattn_mma64_heads_per_cta(int heads) { return pick_hg(heads); }
+
 bool wattn_mma64_supported(const Geom& g, int dtype) {
   // token index must fit 31 bits and the per-image window count 16 bits (Cursor / window_rc arithmetic)
   return dtype == HV_BF16 && g.ws == kWs && g.d == 32 && g.C % 32 == 0 && g.nW < 65536 &&

@@ -562,17 +562,18 @@ int wattn_fwd_variant_set(int v) {
 }
 
 bool wattn_tc64_supported(const Geom& g, int dtype) {
-  // HV_ATTN_TCGEN05: unset = automatic (where it is measured to be the faster forward), 0 = never, 1 = wherever valid
+  // HV_ATTN_TCGEN05: unset or 1 = wherever valid (automatic), 0 = never (mma.sync forward)
   static const int env = []() { const char* e = getenv("HV_ATTN_TCGEN05"); return e == nullptr ? -1 : (atoi(e) != 0 ? 1 : 0); }();
   const int mode = g_fwd_variant < 0 ? env : g_fwd_variant;
   if (mode == 0) return false;
   // an odd shift would put the second half of a column-wrapped row at a 64-byte (not 128-byte) shared-memory offset
   const bool valid = dtype == HV_BF16 && g.ws == kWs && g.d == 32 && g.C % 32 == 0 && (g.shift & 1) == 0 &&
                      (int64_t)g.B * g.H * g.W < (int64_t(1) << 31) && g.W * 3 * g.C * 2 % 16 == 0;
-  if (!valid || mode == 1) return valid;
-  // automatic: B200 measurements (tools/bench_kernels.py, batch 256): 0.74 vs 0.65 of the HBM roofline at the stage-0
-  // shape (3 heads, 16 k windows); with more head groups per launch the mma.sync kernel's 192-byte reads still win
-  return g.heads <= 4 && (int64_t)g.B * g.nW >= 4096;
+  // automatic = wherever valid.  B200 measurements (tools/bench_kernels.py, batch 256, profiles/r02_summary.md): 0.69 vs
+  // 0.61 of the HBM roofline at the stage-0 shape; at the later stages the mma.sync + cp.async forward is 2-4 % faster
+  // (192-byte rows per token against this kernel's 64-byte TMA rows), which is not worth a second forward path
+  (void)mode;
+  return valid;
 }
 
 int wattn_tc64_fwd(const Geom& g, const void* qkv, const float* bias_table, const float* tau, void* out, float* lse,

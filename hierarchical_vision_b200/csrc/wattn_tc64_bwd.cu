@@ -28,7 +28,7 @@
 //   * one token order per launch: a shifted layer loads / stores EVERY window as two column parts [0, 8-s) | [8-s, 8)
 //     (2 boxes per tile, 4 on the bottom row); the position bias is a Toeplitz lookup (4 alignment copies of the
 //     15 x 15 table per head, 10 KB);
-//   * 28 warps: 0 TMA loads | 1 issuer of S, dP | 2 issuer of dV, dK^, dQ^, dBias | 3 TMA stores + dq column sums |
+//   * 28 warps: 0 TMA loads | 1 issuer of S, dP | 2 issuer of dV, dK^, dQ^, dBias | 3 TMA stores |
 //     4-19 softmax / dS (2 groups) | 20-23 dV, dK epilogue | 24-27 dQ epilogue.  All hand-overs are mbarriers.
 #include "hv_tc.cuh"
 
@@ -184,7 +184,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 #ifdef HV_TC_TRACE
 __device__ long long* g_btrace = nullptr;  // [pairs][16 events] clock64 stamps of CTA 0
 #define TRACE(k, ev) do { if (blockIdx.x == (p.ko >> 8) && lane == 0 && g_btrace && (k) < 64) g_btrace[(k) * 16 + (ev)] = clock64(); } while (0)
-#define KO(bit) (p.ko & (bit))  // 1: no tile loads | 2: no tile stores | 4: no dq column sums
+#define KO(bit) (p.ko & (bit))  // 1: no tile loads | 2: no tile stores
 #else
 #define TRACE(k, ev) do { } while (0)
 #define KO(bit) false
@@ -198,8 +198,7 @@ template <int V> struct IntTag { static constexpr int value = V; };
 template <int kMode>
 __device__ __forceinline__ void wattn_tc64_bwd_body(const BwdMaps& maps, const float* __restrict__ stats,
                                                     const float* __restrict__ bias_table, const float* __restrict__ tau,
-                                                    float* __restrict__ ws_dbias, float* __restrict__ ws_dtau,
-                                                    float* __restrict__ ws_colsum, int want_colsum, const BwdParams& p) {
+                                                    float* __restrict__ ws_dbias, float* __restrict__ ws_dtau, const BwdParams& p) {
   constexpr bool kSplit = kMode == 2;
   constexpr bool kMasked = kMode > 0;
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -457,13 +456,9 @@ __device__ __forceinline__ void wattn_tc64_bwd_body(const BwdMaps& maps, const f
     } else {
       // ---------------------------------------------------------------- warp 3: TMA stores of dq, dk, dv + dq column sums
       // The epilogue warps have written dq over the q tile, dk over the k tile and dv over the dO tile of the stage (same
-      // swizzled layout the loads produced), so the boxes of the loads are the boxes of the stores.  While the TMA engine
-      // reads the stage the warp sums the dq tiles over their rows (gradient of q_bias).
-      float cs[2][8];
-#pragma unroll
-      for (int u = 0; u < 2; ++u)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) cs[u][e] = 0.f;
+      // swizzled layout the loads produced), so the boxes of the loads are the boxes of the stores.
+      // (The gradient of q_bias -- the column sums of dq -- is a separate streaming kernel below: summed here, by this one
+      // warp, it cost 30 % of the whole kernel.)
       const CUtensorMap* mm = maps.m[2];
       for (int k = 0; k < npairs; ++k) {
         const int s = k % kStages;
@@ -493,42 +488,12 @@ __device__ __forceinline__ void wattn_tc64_bwd_body(const BwdMaps& maps, const f
         }
         __syncwarp();
         bulk_commit();
-        if (want_colsum && !KO(4)) {
-          const int ch = lane & 3, r0 = lane >> 2;
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            if (!(geo[(k & 7) * 2 + u].rflags & 1)) continue;
-            const uint32_t tile = st + u * kTile;
-#pragma unroll 1
-            for (int i = 0; i < 8; ++i) {  // rolled: code size (see the producer)
-              const int row = r0 + 8 * i;
-              const uint4 v = lds128(tile + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
-              cs[u][0] += bf16lo_to_f32(v.x); cs[u][1] += bf16hi_to_f32(v.x);
-              cs[u][2] += bf16lo_to_f32(v.y); cs[u][3] += bf16hi_to_f32(v.y);
-              cs[u][4] += bf16lo_to_f32(v.z); cs[u][5] += bf16hi_to_f32(v.z);
-              cs[u][6] += bf16lo_to_f32(v.w); cs[u][7] += bf16hi_to_f32(v.w);
-            }
-          }
-        }
         bulk_wait_read0();
         __syncwarp();
         TRACE(k, 15);
         if (lane == 0) mbar_arrive(bar_empty(s));
       }
       bulk_wait0();
-      if (want_colsum) {
-        float* col = reinterpret_cast<float*>(smem + kOffCol);
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float v = cs[u][e];
-            v += __shfl_xor_sync(0xffffffffu, v, 4);
-            v += __shfl_xor_sync(0xffffffffu, v, 8);
-            v += __shfl_xor_sync(0xffffffffu, v, 16);
-            if (lane < 4) col[u * 32 + 8 * lane + e] = v;
-          }
-      }
     }
   } else if (warp < 20) {
     // ------------------------------------------------------------------ softmax / dS threads: two groups (warps 4-11 even
@@ -834,7 +799,6 @@ __device__ __forceinline__ void wattn_tc64_bwd_body(const BwdMaps& maps, const f
       ws_dbias[((int64_t)blockIdx.x * 2 + u) * kTab + r] = bins[u * 256 + r];
     }
     if (threadIdx.x < 2) ws_dtau[blockIdx.x * 2 + threadIdx.x] = col[64 + threadIdx.x];
-    if (threadIdx.x < 64) ws_colsum[blockIdx.x * 64 + threadIdx.x] = col[threadIdx.x];
   }
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
 }
@@ -843,41 +807,93 @@ template <bool kShift>
 __global__ void __launch_bounds__(kThreads, 1)
 wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restrict__ stats, const float* __restrict__ bias_table,
                       const float* __restrict__ tau, float* __restrict__ ws_dbias, float* __restrict__ ws_dtau,
-                      float* __restrict__ ws_colsum, int want_colsum, const __grid_constant__ BwdParams p) {
+                      const __grid_constant__ BwdParams p) {
   if (!kShift) {
-    wattn_tc64_bwd_body<0>(maps, stats, bias_table, tau, ws_dbias, ws_dtau, ws_colsum, want_colsum, p);
+    wattn_tc64_bwd_body<0>(maps, stats, bias_table, tau, ws_dbias, ws_dtau, p);
   } else {
     // class of this CTA (see CtaWork): the last ctas_*1 CTAs of every group take the right-edge windows
     const int same_total = p.n_same * p.ctas_same;
     const int cta = blockIdx.x;
     const bool edge = cta < same_total ? (cta % p.ctas_same) >= p.ctas_same - p.ctas_same1
                                        : (cta - same_total) >= p.ctas_cross - p.ctas_cross1;
-    if (edge) wattn_tc64_bwd_body<2>(maps, stats, bias_table, tau, ws_dbias, ws_dtau, ws_colsum, want_colsum, p);
-    else wattn_tc64_bwd_body<1>(maps, stats, bias_table, tau, ws_dbias, ws_dtau, ws_colsum, want_colsum, p);
+    if (edge) wattn_tc64_bwd_body<2>(maps, stats, bias_table, tau, ws_dbias, ws_dtau, p);
+    else wattn_tc64_bwd_body<1>(maps, stats, bias_table, tau, ws_dbias, ws_dtau, p);
   }
 }
 
-// Sum the per-CTA partials.  CTA c of a same-window group holds heads (2 grp, 2 grp + 1) in units 0 / 1; the CTAs of the
-// cross group hold the last (odd) head in both units.  One warp per output value: the lanes stride over the CTAs (a serial
-// loop over ~100 partial rows would cost more than the attention kernel's own tail).
+// d(q_bias) = column sums of the q third of dqkv (swinv2.py:193-195, 211-220): a streaming pass over C of every 3C
+// channels, 16-byte loads, eight rows per thread in flight, one row of partial sums per CTA (folded, in a fixed order, by
+// the reduce kernel below).  HBM-bound: tokens * C * 2 bytes.
+constexpr int kCsThreads = 256;
+__global__ void __launch_bounds__(kCsThreads) dq_colsum_kernel(const bf16* __restrict__ dqkv, int64_t tokens, int C,
+                                                              float* __restrict__ partials) {
+  __shared__ float red[kCsThreads * 8];
+  const int vecs = C / 8, rpi = kCsThreads / vecs;  // 16-byte vectors per row, rows per block iteration
+  const int rl = threadIdx.x / vecs, v = threadIdx.x - rl * vecs;
+  const int64_t per = (tokens + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = (int64_t)blockIdx.x * per, r1 = min(r0 + per, tokens);
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  if (rl < rpi) {
+    const bf16* base = dqkv + v * 8;
+    for (int64_t r = r0 + rl; r < r1; r += 8 * rpi) {
+      uint4 q[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t rr = r + (int64_t)i * rpi;
+        q[i] = rr < r1 ? __ldcs(reinterpret_cast<const uint4*>(base + rr * (3 * C))) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[0] += bf16lo_to_f32(q[i].x); acc[1] += bf16hi_to_f32(q[i].x);
+        acc[2] += bf16lo_to_f32(q[i].y); acc[3] += bf16hi_to_f32(q[i].y);
+        acc[4] += bf16lo_to_f32(q[i].z); acc[5] += bf16hi_to_f32(q[i].z);
+        acc[6] += bf16lo_to_f32(q[i].w); acc[7] += bf16hi_to_f32(q[i].w);
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[threadIdx.x * 8 + e] = acc[e];
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += kCsThreads) {
+    const int cv = c >> 3, ce = c & 7;
+    float sum = 0.f;
+    for (int j = 0; j < rpi; ++j) sum += red[(j * vecs + cv) * 8 + ce];
+    partials[(int64_t)blockIdx.x * C + c] = sum;
+  }
+}
+
+__global__ void __launch_bounds__(256) dq_colsum_fold_kernel(const float* __restrict__ partials, int rows, int C, float* __restrict__ out) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int b = lane; b < rows; b += 32) s += partials[(int64_t)b * C + c];
+  s = warp_sum(s);
+  if (lane == 0) out[c] = s;
+}
+
+// Sum the per-CTA partials.  Attention CTA c of a same-window group holds heads (2 grp, 2 grp + 1) in units 0 / 1; the
+// CTAs of the cross group hold the last (odd) head in both units; the column-sum kernel left cs_rows rows of C partial
+// sums.  One warp per output value: the lanes stride over the partial rows (a serial loop over hundreds of rows would
+// cost more than the attention kernel's own tail).
 __global__ void __launch_bounds__(256) wattn_tc64_bwd_reduce_kernel(const float* __restrict__ ws_dbias, const float* __restrict__ ws_dtau,
-                                                                    const float* __restrict__ ws_colsum, BwdParams p,
+                                                                    const float* __restrict__ cs_partials, int cs_rows, BwdParams p,
                                                                     float* __restrict__ dbias_table, float* __restrict__ dtau,
                                                                     float* __restrict__ dq_colsum) {
   const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int heads = p.g.heads, per_head = kTab + 1, n_tab = heads * per_head;
-  int head, what, e = 0;  // what: 0 bias bin, 1 tau, 2 column sum
-  if (idx < n_tab) {
-    head = idx / per_head;
-    e = idx - head * per_head;
-    what = e < kTab ? 0 : 1;
-  } else if (idx < n_tab + p.g.C && dq_colsum != nullptr) {
-    head = (idx - n_tab) / 32;
-    e = (idx - n_tab) & 31;
-    what = 2;
-  } else {
+  if (idx >= n_tab) {
+    const int c = idx - n_tab;
+    if (c >= p.g.C || dq_colsum == nullptr) return;
+    float s = 0.f;
+    for (int b = lane; b < cs_rows; b += 32) s += cs_partials[(int64_t)b * p.g.C + c];
+    s = warp_sum(s);
+    if (lane == 0) dq_colsum[c] = s;
     return;
   }
+  const int head = idx / per_head, e = idx - head * per_head;
+  const bool is_tau = e == kTab;
   int c0, c1, u0, u1;
   if (head < 2 * p.n_same) {
     c0 = (head >> 1) * p.ctas_same; c1 = c0 + p.ctas_same; u0 = u1 = head & 1;
@@ -886,13 +902,11 @@ __global__ void __launch_bounds__(256) wattn_tc64_bwd_reduce_kernel(const float*
   }
   float s = 0.f;
   for (int c = c0 + lane; c < c1; c += 32)
-    for (int u = u0; u <= u1; ++u)
-      s += what == 0 ? ws_dbias[((int64_t)c * 2 + u) * kTab + e] : (what == 1 ? ws_dtau[c * 2 + u] : ws_colsum[c * 64 + u * 32 + e]);
+    for (int u = u0; u <= u1; ++u) s += is_tau ? ws_dtau[c * 2 + u] : ws_dbias[((int64_t)c * 2 + u) * kTab + e];
   s = warp_sum(s);
   if (lane != 0) return;
-  if (what == 0) dbias_table[e * heads + head] = s;
-  else if (what == 1) dtau[head] = s;
-  else dq_colsum[idx - n_tab] = s;
+  if (is_tau) dtau[head] = s;
+  else dbias_table[e * heads + head] = s;
 }
 
 }  // namespace
@@ -916,9 +930,27 @@ bool wattn_tc64_bwd_supported(const Geom& g, int dtype) {
          (int64_t)g.B * g.H * g.W < (int64_t(1) << 31) && g.W * g.C * 2 % 16 == 0;
 }
 
+size_t dq_colsum_workspace_bytes(int C) { return (size_t)(4 * num_sms()) * C * sizeof(float) + 256; }
+
+// out[c] = sum over tokens of dqkv[token, c], c < C (dqkv: (tokens, 3C) bf16): the gradient of WindowAttention.q_bias
+int dq_colsum(const void* dqkv, int64_t tokens, int C, float* out, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if (!aligned16(dqkv) || C % 8 != 0) HV_FAIL(HV_ERR_ALIGN, "dq_colsum: dqkv must be 16-byte aligned and C a multiple of 8");
+  if (C / 8 > kCsThreads) HV_FAIL(HV_ERR_SHAPE, "dq_colsum: C = %d > %d", C, 8 * kCsThreads);
+  if (workspace == nullptr || workspace_bytes < dq_colsum_workspace_bytes(C))
+    HV_FAIL(HV_ERR_WORKSPACE, "dq_colsum: workspace of %zu bytes required", dq_colsum_workspace_bytes(C));
+  int cgrid = 4 * num_sms();
+  if ((int64_t)cgrid > (tokens + 127) / 128) cgrid = (int)((tokens + 127) / 128);
+  float* partials = static_cast<float*>(workspace);
+  dq_colsum_kernel<<<cgrid, kCsThreads, 0, st>>>((const bf16*)dqkv, tokens, C, partials);
+  HV_LAUNCH_OK("dq_colsum_kernel");
+  dq_colsum_fold_kernel<<<(C + 7) / 8, 256, 0, st>>>(partials, cgrid, C, out);
+  HV_LAUNCH_OK("dq_colsum_fold_kernel");
+  return HV_OK;
+}
+
 size_t wattn_tc64_bwd_workspace_bytes(const Geom& g) {
-  (void)g;
-  return (size_t)(2 * num_sms()) * (2 * kTab + 2 + 64) * sizeof(float) + 256;  // one row of partials per CTA; grid <= 2 * SMs
+  // one row of partials per attention CTA (grid <= 2 * SMs) | the column-sum kernel's partial rows (4 CTAs per SM)
+  return (size_t)(2 * num_sms()) * (2 * kTab + 2) * sizeof(float) + (size_t)(4 * num_sms()) * g.C * sizeof(float) + 256;
 }
 
 // `stats`: the three planes (lse | r | c) written by the forward kernels of this geometry (hv_window_attn_stats_floats)
@@ -1004,7 +1036,8 @@ int wattn_tc64_bwd(const Geom& g, const void* qkv, const void* dout, const float
   const int grid = p.n_same * p.ctas_same + p.ctas_cross;
   float* ws_dbias = static_cast<float*>(workspace);
   float* ws_dtau = ws_dbias + (size_t)grid * 2 * kTab;
-  float* ws_colsum = ws_dtau + (size_t)grid * 2;
+  // behind the attention kernel's partials (sized for 2 * SMs CTAs): the column-sum kernel's partial rows
+  float* cs_partials = static_cast<float*>(workspace) + (size_t)(2 * nsm) * (2 * kTab + 2);
   static thread_local int attr_dev = -1;
   int dev = 0;
   HV_CUDA_OK(cudaGetDevice(&dev));
@@ -1022,11 +1055,9 @@ int wattn_tc64_bwd(const Geom& g, const void* qkv, const void* dout, const float
   cudaMemsetAsync(dtrace, 0, 64 * 16 * sizeof(long long), st);
 #endif
   if (g.shift > 0)
-    wattn_tc64_bwd_kernel<true><<<grid, kThreads, kSmem, st>>>(*mp, stats, bias_table, tau, ws_dbias, ws_dtau, ws_colsum,
-                                                               dq_colsum != nullptr, p);
+    wattn_tc64_bwd_kernel<true><<<grid, kThreads, kSmem, st>>>(*mp, stats, bias_table, tau, ws_dbias, ws_dtau, p);
   else
-    wattn_tc64_bwd_kernel<false><<<grid, kThreads, kSmem, st>>>(*mp, stats, bias_table, tau, ws_dbias, ws_dtau, ws_colsum,
-                                                                dq_colsum != nullptr, p);
+    wattn_tc64_bwd_kernel<false><<<grid, kThreads, kSmem, st>>>(*mp, stats, bias_table, tau, ws_dbias, ws_dtau, p);
   HV_LAUNCH_OK("wattn_tc64_bwd_kernel");
 #ifdef HV_TC_TRACE
   if (getenv("HV_TC_BTRACE_DUMP")) {
@@ -1040,8 +1071,16 @@ int wattn_tc64_bwd(const Geom& g, const void* qkv, const void* dout, const float
     }
   }
 #endif
-  const int n = g.heads * (kTab + 1) + g.C;
-  wattn_tc64_bwd_reduce_kernel<<<(n + 7) / 8, 256, 0, st>>>(ws_dbias, ws_dtau, ws_colsum, p, dbias_table, dtau, dq_colsum);
+  int cgrid = 0;
+  if (dq_colsum != nullptr) {
+    const int64_t tokens = (int64_t)g.B * g.H * g.W;
+    cgrid = 4 * nsm;
+    if ((int64_t)cgrid > (tokens + 127) / 128) cgrid = (int)((tokens + 127) / 128);
+    dq_colsum_kernel<<<cgrid, kCsThreads, 0, st>>>((const bf16*)dqkv, tokens, g.C, cs_partials);
+    HV_LAUNCH_OK("dq_colsum_kernel");
+  }
+  const int n = g.heads * (kTab + 1) + (dq_colsum != nullptr ? g.C : 0);
+  wattn_tc64_bwd_reduce_kernel<<<(n + 7) / 8, 256, 0, st>>>(ws_dbias, ws_dtau, cs_partials, cgrid, p, dbias_table, dtau, dq_colsum);
   HV_LAUNCH_OK("wattn_tc64_bwd_reduce_kernel");
   return HV_OK;
 }

@@ -44,19 +44,26 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 
 # The residual shortcut's gradient arrives in the node that also produces the branch's dx (see _QkvWindowAttention /
 # _LinearShortcut): the dx GEMM then accumulates straight into that incoming buffer (beta = 1, in place) instead of
-# copying it first.  The buffer is the LayerNorm backward's pass-through of its own incoming gradient, which nothing
-# reads again.  Set to False to accumulate out of place.
+# copying it first -- but ONLY when the buffer is one this package allocated itself and nothing else can see: the
+# pass-through gradient of _LnResidual.backward is tagged with `_hv_owned` and the tag is checked here.  A gradient
+# handed in by the caller (y.backward(g), torch.autograd.grad) or by any other autograd node is never modified.
 INPLACE_SHORTCUT_GRAD = True
+
+
+def _own(t: torch.Tensor) -> torch.Tensor:
+    """Mark a gradient buffer allocated by this package as safe to accumulate into."""
+    t._hv_owned = True
+    return t
 
 
 def _dx_with_shortcut(dx_shortcut, d2, weight, shape):
     C = shape[-1]
     if dx_shortcut is None:
         return torch.matmul(d2, weight).view(shape)
-    if (INPLACE_SHORTCUT_GRAD and dx_shortcut.dtype == d2.dtype and dx_shortcut.is_contiguous()
-            and not torch.is_grad_enabled() and not dx_shortcut.requires_grad):
-        return dx_shortcut.view(-1, C).addmm_(d2, weight).view(shape)
-    return torch.addmm(dx_shortcut.reshape(-1, C).to(d2.dtype), d2, weight).view(shape)
+    if (INPLACE_SHORTCUT_GRAD and getattr(dx_shortcut, "_hv_owned", False) and dx_shortcut.dtype == d2.dtype
+            and dx_shortcut.is_contiguous() and not torch.is_grad_enabled() and not dx_shortcut.requires_grad):
+        return _own(dx_shortcut.view(-1, C).addmm_(d2, weight).view(shape))
+    return _own(torch.addmm(dx_shortcut.reshape(-1, C).to(d2.dtype), d2, weight).view(shape))
 
 
 # Optional per-launch instrumentation used by bench.py: when set to a list, every attention
@@ -143,7 +150,7 @@ class _WindowAttention(torch.autograd.Function):
         nW = (H // ws) * (W // ws)
         out = torch.empty((B, H * W, C), dtype=qkv.dtype, device=qkv.device)
         lse = window_attention_stats(qkv, B, H, W, C, heads, ws)
-        _timed(f"attn_fwd/C{C}", B * nW, qkv.device, lambda: window_attention_fwd_raw(
+        _timed(f"attn_fwd/C{C}/s{shift}", B * nW, qkv.device, lambda: window_attention_fwd_raw(
             qkv, bias_table, tau, mask, out, lse, B, H, W, C, heads, ws, shift))
         ctx.save_for_backward(qkv, out, lse, bias_table, tau, mask)
         ctx.geom = (B, H, W, C, heads, ws, shift)
@@ -160,7 +167,7 @@ class _WindowAttention(torch.autograd.Function):
         dbias = torch.empty_like(bias_table)
         dtau = torch.empty_like(tau)
         workspace = window_attention_bwd_workspace(qkv, B, H, W, C, heads, ws)
-        _timed(f"attn_bwd/C{C}", B * (H // ws) * (W // ws), qkv.device, lambda: window_attention_bwd_raw(
+        _timed(f"attn_bwd/C{C}/s{shift}", B * (H // ws) * (W // ws), qkv.device, lambda: window_attention_bwd_raw(
             qkv, out, dout, lse, bias_table, tau, mask, dqkv, dbias, dtau, workspace, B, H, W, C, heads, ws, shift),
             kernels=2)  # backward kernel + partial-sum reduction kernel
         return dqkv, dbias, dtau, None, None, None, None, None, None, None, None
@@ -172,6 +179,16 @@ def window_attention(qkv: torch.Tensor, bias_table: torch.Tensor, tau: torch.Ten
     16*sigmoid(cpb_mlp(coords)) of shape ((2ws-1)^2, heads); ``tau`` = exp(clamped logit_scale), (heads,).
     ``mask`` None: shifted-window mask generated in-kernel from the geometry; else (nW, N, N) added as given."""
     return _WindowAttention.apply(qkv, bias_table, tau.reshape(-1), mask, B, H, W, C, heads, ws, shift)
+
+
+def window_attention_kernel_name(B: int, H: int, W: int, C: int, heads: int, ws: int, shift: int, dtype: torch.dtype,
+                                 backward: bool) -> str:
+    """Name of the kernel the fused attention launches for this geometry (hv_window_attn_kernel_name)."""
+    import ctypes
+    buf = ctypes.create_string_buffer(96)
+    check(_lib.load().hv_window_attn_kernel_name(B, H, W, C, heads, ws, shift, HV_BF16 if dtype == torch.bfloat16 else HV_F32,
+                                                 1 if backward else 0, buf, len(buf)), "hv_window_attn_kernel_name")
+    return buf.value.decode()
 
 
 def window_attention_kind(C: int, heads: int, ws: int, dtype: torch.dtype) -> int:
@@ -201,7 +218,7 @@ class _QkvWindowAttention(torch.autograd.Function):
         nW = (H // ws) * (W // ws)
         out = torch.empty((B, H * W, C), dtype=qkv.dtype, device=qkv.device)
         lse = window_attention_stats(qkv, B, H, W, C, heads, ws)
-        _timed(f"attn_fwd/C{C}", B * nW, qkv.device, lambda: window_attention_fwd_raw(
+        _timed(f"attn_fwd/C{C}/s{shift}", B * nW, qkv.device, lambda: window_attention_fwd_raw(
             qkv, bias_table, tau, None, out, lse, B, H, W, C, heads, ws, shift))
         ctx.save_for_backward(x, weight, qkv, out, lse, bias_table, tau)
         ctx.geom = (B, H, W, C, heads, ws, shift)
@@ -220,11 +237,22 @@ class _QkvWindowAttention(torch.autograd.Function):
         dqkv = torch.empty_like(qkv)
         dbias = torch.empty_like(bias_table)
         dtau = torch.empty_like(tau)
-        dq_colsum = torch.empty((C,), dtype=torch.float32, device=qkv.device) if ctx.q_bias_dtype is not None else None
         workspace = window_attention_bwd_workspace(qkv, B, H, W, C, heads, ws)
-        _timed(f"attn_bwd/C{C}", B * (H // ws) * (W // ws), qkv.device, lambda: window_attention_bwd_raw(
-            qkv, out, dout, lse, bias_table, tau, None, dqkv, dbias, dtau, workspace, B, H, W, C, heads, ws, shift,
-            dq_colsum=dq_colsum), kernels=2)
+        _timed(f"attn_bwd/C{C}/s{shift}", B * (H // ws) * (W // ws), qkv.device, lambda: window_attention_bwd_raw(
+            qkv, out, dout, lse, bias_table, tau, None, dqkv, dbias, dtau, workspace, B, H, W, C, heads, ws, shift),
+            kernels=2)  # backward + partial-sum fold
+        dq_colsum = None
+        if ctx.q_bias_dtype is not None and ctx.needs_input_grad[2]:
+            # gradient of q_bias: column sums of dq, a streaming pass of its own (hv_dq_colsum)
+            dq_colsum = torch.empty((C,), dtype=torch.float32, device=qkv.device)
+            lib = _lib.load()
+            with torch.cuda.device(qkv.device):
+                nb = int(lib.hv_dq_colsum_workspace_bytes(C))
+                cws = torch.empty((nb,), dtype=torch.uint8, device=qkv.device)
+                check(lib.hv_dq_colsum(_ptr(dqkv), _ptr(dq_colsum), _ptr(cws), nb, B * H * W, C, _code(dqkv), _stream(qkv.device)),
+                      "hv_dq_colsum")
+            global LAUNCH_COUNT
+            LAUNCH_COUNT += 2
         d2 = dqkv.view(-1, 3 * C)
         dx = None
         if ctx.needs_input_grad[0]:
@@ -277,7 +305,7 @@ class _LnResidual(torch.autograd.Function):
     """out = shortcut + keep_scale[sample] * LayerNorm(y + bias) (shortcut / bias / keep_scale optional)."""
 
     @staticmethod
-    def forward(ctx, y, shortcut, gamma, beta, bias, keep_scale, rows_per_sample, eps):
+    def forward(ctx, y, shortcut, gamma, beta, bias, keep_scale, rows_per_sample, eps, out_dtype=None):
         _need_cuda(y, "ln_residual")
         lib = _lib.load()
         y = y.contiguous()
@@ -289,7 +317,7 @@ class _LnResidual(torch.autograd.Function):
             shortcut = shortcut.contiguous()
             res_dtype = shortcut.dtype
         else:
-            res_dtype = y.dtype
+            res_dtype = out_dtype or y.dtype
         if keep_scale is not None:
             keep_scale = _f32c(keep_scale)
         out = torch.empty(y.shape, dtype=res_dtype, device=y.device)
@@ -327,16 +355,17 @@ class _LnResidual(torch.autograd.Function):
         global LAUNCH_COUNT
         LAUNCH_COUNT += 2
         return (dy, (dout if has_shortcut else None), dgamma.to(gdt), dbeta.to(bdt),
-                (dbias.to(biasdt) if dbias is not None else None), None, None, None)
+                (dbias.to(biasdt) if dbias is not None else None), None, None, None, None)
 
 
 def ln_residual(y: torch.Tensor, shortcut: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor,
                 keep_scale: Optional[torch.Tensor] = None, eps: float = 1e-5,
-                bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+                bias: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
     """shortcut + keep_scale[b] * LayerNorm(y + bias) over the last dim; y is (B, L, C) (or (rows, C)).
-    ``bias``: the bias of the Linear that produced ``y`` when that Linear was run without it."""
+    ``bias``: the bias of the Linear that produced ``y`` when that Linear was run without it.
+    The result has the shortcut's dtype; without a shortcut ``out_dtype`` (float32 / bfloat16, default: y's)."""
     rows_per_sample = (y.numel() // y.shape[-1]) // y.shape[0] if y.dim() >= 2 else 1
-    return _LnResidual.apply(y, shortcut, gamma, beta, bias, keep_scale, rows_per_sample, eps)
+    return _LnResidual.apply(y, shortcut, gamma, beta, bias, keep_scale, rows_per_sample, eps, out_dtype)
 
 
 class _BiasGelu(torch.autograd.Function):

@@ -25,11 +25,35 @@ import torch.utils.checkpoint as checkpoint
 
 from . import functional as hvf
 
-__all__ = ["DropPath", "to_2tuple", "trunc_normal_", "MultitaskHead", "Mlp", "window_partition", "window_reverse",
+__all__ = ["set_amp_residual_dtype", "DropPath", "to_2tuple", "trunc_normal_", "MultitaskHead", "Mlp", "window_partition", "window_reverse",
            "WindowAttention", "SwinTransformerBlock", "PatchMerging", "BasicLayer", "PatchEmbed",
            "SwinTransformerV2", "Checkpoint", "swinv2_tiny", "swinv2_base"]
 
 trunc_normal_ = nn.init.trunc_normal_  # the reference takes it from timm (swinv2.py:9)
+
+# dtype of the residual stream under torch.autocast.  The reference's AMP run keeps it in float32: autocast executes
+# layer_norm in fp32, so `x = shortcut + drop_path(norm(...))` (swinv2.py:431, 434, 494, 656) never leaves fp32 and only
+# the Linear inputs are cast down.  None (default) = the stream follows the autocast dtype (bf16): the LayerNorm +
+# residual kernels then move 6 instead of 10 bytes per element and the casts in front of every Linear disappear, at the
+# price of one bf16 rounding per residual add -- a documented deviation from reference AMP, inside the bf16 tolerance of
+# the parity tests (tests/test_gpu_parity.py::test_swinv2_tiny_bf16_autocast_vs_oracle runs both settings).
+# torch.float32 = reference AMP semantics.  Outside autocast the stream always has the input's dtype.
+AMP_RESIDUAL_DTYPE: Optional[torch.dtype] = None
+
+
+def set_amp_residual_dtype(dtype: Optional[torch.dtype]) -> None:
+    """None: bf16 residual stream under autocast (fast); torch.float32: fp32 stream as in the reference's AMP run."""
+    global AMP_RESIDUAL_DTYPE
+    if dtype not in (None, torch.float32, torch.bfloat16):
+        raise ValueError(f"residual stream dtype must be None, float32 or bfloat16, not {dtype}")
+    AMP_RESIDUAL_DTYPE = dtype
+
+
+def _stream_dtype(y: torch.Tensor) -> Optional[torch.dtype]:
+    """Output dtype of a LayerNorm that starts (a stage of) the residual stream."""
+    if y.is_cuda and torch.is_autocast_enabled("cuda") and AMP_RESIDUAL_DTYPE is not None:
+        return AMP_RESIDUAL_DTYPE
+    return None
 
 
 def to_2tuple(v):
@@ -370,8 +394,8 @@ class PatchMerging(nn.Module):
         assert L == H * W, "input feature has wrong size"
         assert H % 2 == 0 and W % 2 == 0, f"x size ({H}*{W}) are not even."
         x = self.reduction(hvf.patch_merge_gather(x, H, W))
-        if type(self.norm) is nn.LayerNorm and self.norm.elementwise_affine and self.norm.bias is not None:
-            return hvf.ln_residual(x, None, self.norm.weight, self.norm.bias, None, self.norm.eps)
+        if SwinTransformerBlock._fusable(self.norm):
+            return hvf.ln_residual(x, None, self.norm.weight, self.norm.bias, None, self.norm.eps, out_dtype=_stream_dtype(x))
         return self.norm(x)
 
     def extra_repr(self) -> str:
@@ -467,14 +491,15 @@ class PatchEmbed(nn.Module):
             if dt not in (torch.float32, torch.bfloat16):
                 dt = torch.float32
             rows = hvf.patch_rows(x, scale, shift, dt)
-            fold = type(self.norm) is nn.LayerNorm and self.norm.elementwise_affine and self.norm.bias is not None
+            fold = self.norm is not None and SwinTransformerBlock._fusable(self.norm)
             w = self.proj.weight.view(self.embed_dim, -1)
             x = F.linear(rows, w.to(dt), None if (fold or self.proj.bias is None) else self.proj.bias.to(dt))
             x = x.view(B, -1, self.embed_dim)
             bias = self.proj.bias if fold else None
         if self.norm is not None:
-            if type(self.norm) is nn.LayerNorm and x.is_cuda and x.dtype in (torch.float32, torch.bfloat16):
-                x = hvf.ln_residual(x, None, self.norm.weight, self.norm.bias, None, self.norm.eps, bias=bias)
+            if SwinTransformerBlock._fusable(self.norm) and x.is_cuda and x.dtype in (torch.float32, torch.bfloat16):
+                x = hvf.ln_residual(x, None, self.norm.weight, self.norm.bias, None, self.norm.eps, bias=bias,
+                                    out_dtype=_stream_dtype(x))
             else:
                 x = self.norm(x)
         return x

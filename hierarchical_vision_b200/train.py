@@ -6,8 +6,10 @@ module restates only what the measurement needs, following the reference's own p
   * ``Model.forward(batch)`` / ``Model.loss(outputs, batch)``            reference models.py:121-152
   * multitask cross entropy ``dot(coeffs, CE_t)``                         reference hierarchy.py:65-94
   * optimizer parameter groups: no weight decay for 1-D params / biases   reference optim.py:48-58
-  * SGD with momentum 0.875, weight decay 5e-4, gradient clipping 2.0     reference configs.py:46-48,
-                                                                          configs/pretrain/inat21.yaml:44-47
+  * DecoupledSGDW (the reference default) / SGD with nesterov momentum    reference optim.py:16-44, configs.py:44-48
+    0.875, weight decay 5e-4, gradient clipping 2.0                       configs/pretrain/inat21.yaml:44-47
+  * cosine annealing with linear warm-up                                  reference configs.py:52-54, main.py:62-64
+  * label smoothing, also per tier of a multitask head                    reference algorithmic.py:88-119, 160-164
   * per-rank batch = global batch / world size                            reference main.py:44-48
   * uint8 images normalised on the device                                 reference data.py:130-136, 154-164
 
@@ -18,6 +20,7 @@ product, the oracle in tests).
 """
 from __future__ import annotations
 
+import math
 import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
@@ -82,18 +85,36 @@ class NormalizeOnDevice(nn.Module):
         return (x.float() - self.mean) / self.std
 
 
-def multitask_cross_entropy(logits: List[torch.Tensor], targets: torch.Tensor,
-                            coeffs: Sequence[float] = MULTITASK_COEFFS) -> torch.Tensor:
-    """targets (B, tiers); loss = sum_t coeff_t * CE(logits_t, targets[:, t])  (hierarchy.py:86-94)."""
+def smooth_labels(logits: torch.Tensor, target: torch.Tensor, smoothing: float = 0.1) -> torch.Tensor:
+    """(B,) class indices -> (B, classes) soft targets ``onehot * (1 - smoothing) + smoothing / classes``
+    (algorithmic.py:160-164, itself Composer's ``smooth_labels``)."""
+    n_classes = logits.shape[1]
+    onehot = F.one_hot(target, n_classes).to(torch.float32)
+    return onehot * (1.0 - smoothing) + smoothing / n_classes
+
+
+def multitask_cross_entropy(logits: List[torch.Tensor], targets, coeffs: Sequence[float] = MULTITASK_COEFFS,
+                            label_smoothing: float = 0.0) -> torch.Tensor:
+    """targets (B, tiers) class indices, or a list of per-tier (soft) targets as the reference's patched
+    LabelSmoothing produces (algorithmic.py:100-112); loss = sum_t coeff_t * CE(logits_t, targets_t)
+    (hierarchy.py:65-94).  ``label_smoothing`` > 0 smooths every tier like that algorithm does."""
+    if not isinstance(targets, (list, tuple)):
+        targets = list(targets.unbind(dim=1))
+    if not (len(logits) == len(targets) == len(coeffs)):
+        raise ValueError(f"{len(logits)} != {len(targets)} != {len(coeffs)}")
     total = logits[0].new_zeros((), dtype=torch.float32)
     for t, lg in enumerate(logits):
-        total = total + coeffs[t] * F.cross_entropy(lg.float(), targets[:, t])
+        tg = targets[t]
+        if label_smoothing > 0.0 and not tg.is_floating_point():
+            tg = smooth_labels(lg, tg, label_smoothing)
+        total = total + coeffs[t] * F.cross_entropy(lg.float(), tg)
     return total
 
 
 class Model(nn.Module):
     """Composer-protocol wrapper (models.py:121-152): ``forward(batch) = module(batch[0])``,
-    ``loss(outputs, batch)`` = cross entropy, or the multitask sum when the module returns a list."""
+    ``loss(outputs, batch)`` = cross entropy, or the multitask sum when the module returns a list.
+    ``label_smoothing``: what the reference's LabelSmoothing algorithm does to the targets before the loss."""
 
     def __init__(self, module: nn.Module, coeffs: Sequence[float] = MULTITASK_COEFFS, label_smoothing: float = 0.0):
         super().__init__()
@@ -108,27 +129,109 @@ class Model(nn.Module):
     def loss(self, outputs, batch):
         _, targets = batch
         if isinstance(outputs, (list, tuple)):
-            return multitask_cross_entropy(list(outputs), targets, self.coeffs)
+            return multitask_cross_entropy(list(outputs), targets, self.coeffs, self.label_smoothing)
         return F.cross_entropy(outputs.float(), targets, label_smoothing=self.label_smoothing)
 
 
-def build_optimizer(model: nn.Module, lr: float = 0.1, momentum: float = 0.875, weight_decay: float = 5e-4):
-    """SGD with the reference's grouping: 1-D parameters, ``.bias`` and ``no_weight_decay()`` names get no
-    decay (optim.py:5-58)."""
-    skip = set()
-    inner = model.module if hasattr(model, "module") else model
-    if hasattr(inner, "no_weight_decay"):
-        skip = set(inner.no_weight_decay())
+def cosine_warmup_factor(step: int, warmup_steps: int, total_steps: int, alpha_f: float = 0.0) -> float:
+    """LR multiplier of Composer's CosineAnnealingWithWarmupScheduler(t_warmup, alpha_f) (configs.py:52-54): linear
+    from 0 to 1 over the warm-up, then ``alpha_f + (1 - alpha_f) * (1 + cos(pi * frac)) / 2`` over the remaining steps.
+    Composer is not vendored here; this restates its documented schedule."""
+    if warmup_steps > 0 and step < warmup_steps:
+        return step / warmup_steps
+    span = max(total_steps - warmup_steps, 1)
+    frac = min(max(step - warmup_steps, 0) / span, 1.0)
+    return alpha_f + (1.0 - alpha_f) * 0.5 * (1.0 + math.cos(math.pi * frac))
+
+
+class FlatSGD(torch.optim.Optimizer):
+    """The reference's two SGD flavours over a CUDA-graph-friendly layout (optim.py:16-44):
+
+      * ``decoupled=True``  Composer's DecoupledSGDW, the reference default (configs.py:45): momentum buffer
+        ``buf = momentum * buf + grad``, update ``p = p * (1 - (lr / initial_lr) * weight_decay) - lr * buf`` (restated
+        from Composer 0.13's documented rule; the package itself is not installable here);
+      * ``decoupled=False`` ``torch.optim.SGD(..., nesterov=True)`` of the reference's "sgd" branch:
+        ``g = grad + wd * p; buf = momentum * buf + g; p -= lr * (g + momentum * buf)``.
+
+    The learning rate lives in a device tensor (``set_lr``), so a captured CUDA graph follows a schedule instead of
+    baking the value of capture time into its kernels; all tensors of a group are updated by a handful of
+    multi-tensor kernels.  Parameter groups follow the reference (``build_optimizer``): a group's ``weight_decay``
+    0 disables decay for it."""
+
+    def __init__(self, params, lr: float, momentum: float = 0.875, weight_decay: float = 5e-4, decoupled: bool = True,
+                 nesterov: bool = True):
+        defaults = dict(lr=lr, momentum=momentum, weight_decay=weight_decay, decoupled=decoupled, nesterov=nesterov,
+                        initial_lr=lr)
+        super().__init__(params, defaults)
+        dev = self.param_groups[0]["params"][0].device
+        self.lr_t = torch.tensor(float(lr), dtype=torch.float32, device=dev)
+        self._lr_host = float(lr)
+
+    def set_lr(self, lr: float) -> None:
+        """New learning rate for every group, effective at the next step (also inside a replayed CUDA graph)."""
+        if lr != self._lr_host:
+            self.lr_t.fill_(float(lr))
+            self._lr_host = float(lr)
+        for g in self.param_groups:
+            g["lr"] = float(lr)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        for g in self.param_groups:
+            params = [p for p in g["params"] if p.grad is not None]
+            if not params:
+                continue
+            if g["lr"] != self._lr_host:  # a scheduler wrote param_group["lr"] directly
+                self.set_lr(g["lr"])
+            grads = [p.grad for p in params]
+            mom, wd = g["momentum"], g["weight_decay"]
+            bufs = []
+            for p in params:
+                st = self.state[p]
+                if "momentum_buffer" not in st:
+                    st["momentum_buffer"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                bufs.append(st["momentum_buffer"])
+            if g["decoupled"]:
+                torch._foreach_mul_(bufs, mom)
+                torch._foreach_add_(bufs, grads)
+                if wd != 0.0:
+                    torch._foreach_mul_(params, 1.0 - self.lr_t * (wd / g["initial_lr"]))
+                upd = torch._foreach_mul(bufs, -self.lr_t)
+            else:
+                if wd != 0.0:
+                    grads = torch._foreach_add(grads, params, alpha=wd)
+                torch._foreach_mul_(bufs, mom)
+                torch._foreach_add_(bufs, grads)
+                if g["nesterov"]:
+                    grads = torch._foreach_add(grads, bufs, alpha=mom)
+                else:
+                    grads = bufs
+                upd = torch._foreach_mul(grads, -self.lr_t)
+            torch._foreach_add_(params, upd)
+        return loss
+
+
+def build_optimizer(model: nn.Module, lr: float = 0.1, momentum: float = 0.875, weight_decay: float = 5e-4,
+                    name: str = "decoupledsgdw"):
+    """The reference's optimizer factory (optim.py:5-58) for its two SGD branches: ``"decoupledsgdw"`` (default,
+    configs.py:45) and ``"sgd"`` (nesterov).  Grouping as in ``set_weight_decay``: 1-D parameters, ``.bias`` and
+    ``no_weight_decay()`` names get no decay.  Like the reference, the skip list comes from the object handed in
+    (its Composer ``Model`` has no ``no_weight_decay``, so ``logit_scale`` and ``cpb_mlp`` weights ARE decayed there;
+    pass the bare backbone to honour ``SwinTransformerV2.no_weight_decay``)."""
+    skip = set(model.no_weight_decay()) if hasattr(model, "no_weight_decay") else set()
     decay, no_decay = [], []
-    for name, p in model.named_parameters():
+    for pname, p in model.named_parameters():
         if not p.requires_grad:
             continue
-        short = name.split("module.")[-1]
-        (no_decay if (p.dim() == 1 or name.endswith(".bias") or short in skip) else decay).append(p)
+        short = pname.removeprefix("module.")  # DistributedDataParallel's wrapper prefix
+        (no_decay if (p.dim() == 1 or pname.endswith(".bias") or short in skip) else decay).append(p)
     groups = [{"params": decay}, {"params": no_decay, "weight_decay": 0.0}]
-    # one fused multi-tensor kernel per group on CUDA instead of a foreach chain of ~25 launches
-    fused = all(p.is_cuda for p in decay + no_decay) and len(decay) + len(no_decay) > 0
-    return torch.optim.SGD(groups, lr=lr, momentum=momentum, weight_decay=weight_decay, fused=fused)
+    groups = [g for g in groups if g["params"]]
+    key = name.lower()
+    if key not in ("decoupledsgdw", "sgd"):
+        raise ValueError(f"optimizer '{name}': this training stand-in covers the reference's SGD branches (decoupledsgdw, sgd)")
+    return FlatSGD(groups, lr=lr, momentum=momentum, weight_decay=weight_decay, decoupled=key == "decoupledsgdw")
 
 
 def wrap_ddp(model: nn.Module, env: DistEnv, device: torch.device) -> nn.Module:
@@ -158,6 +261,86 @@ def train_step(model: nn.Module, optimizer: torch.optim.Optimizer, batch, *, aut
     return loss.detach()
 
 
+class BucketedGradSync:
+    """Gradient all-reduce(avg) of a flat gradient buffer in a few contiguous buckets, each started as soon as its last
+    gradient has been accumulated -- late layers first, overlapping with the rest of the backward pass (the NCCL
+    stream runs beside the compute stream; inside a CUDA graph this becomes a fork / join of the captured graph).
+    This is what DistributedDataParallel's bucket hooks do (reference main.py trains through Composer's DDP), without
+    the per-step host work: the hooks only run while the graph is being captured.
+
+    ``params``: parameters in flat-buffer order, every ``p.grad`` a view into ``flat``.  ``bounds``: bucket
+    boundaries as parameter indices (ascending, first 0, last len(params))."""
+
+    def __init__(self, params: Sequence[torch.nn.Parameter], flat: torch.Tensor, bounds: Sequence[int]):
+        self.flat = flat
+        self.bounds = list(bounds)
+        self.nb = len(self.bounds) - 1
+        offs = [0]
+        for p in params:
+            offs.append(offs[-1] + p.numel())
+        self.views = [flat[offs[self.bounds[b]]:offs[self.bounds[b + 1]]] for b in range(self.nb)]
+        self.sizes = [self.bounds[b + 1] - self.bounds[b] for b in range(self.nb)]
+        self._count = [0] * self.nb
+        self._works = []
+        self._started = [False] * self.nb
+        self.enabled = True
+        # NCCL averages inside the collective; gloo (CPU tests of this logic) only sums
+        self._avg = dist.is_initialized() and dist.get_backend() == "nccl"
+        for b in range(self.nb):
+            for p in params[self.bounds[b]:self.bounds[b + 1]]:
+                p.register_post_accumulate_grad_hook(self._make_hook(b))
+
+    @staticmethod
+    def stage_bounds(named_params: Sequence[Tuple[str, torch.nn.Parameter]], min_bucket_numel: int = 1 << 20) -> List[int]:
+        """One bucket per top-level stage of the model (``module.layers.<i>`` and whatever sits before / after),
+        merged upwards until a bucket holds at least ``min_bucket_numel`` elements."""
+        def key(name):
+            parts = name.removeprefix("module.").split(".")
+            return ".".join(parts[:2]) if parts[0] == "layers" and len(parts) > 1 else parts[0]
+        bounds, sizes, last = [0], [], None
+        for i, (name, p) in enumerate(named_params):
+            k = key(name)
+            if last is not None and k != last and sum(sizes) >= min_bucket_numel:
+                bounds.append(i)
+                sizes = []
+            sizes.append(p.numel())
+            last = k
+        bounds.append(len(named_params))
+        return bounds
+
+    def _make_hook(self, b: int):
+        def hook(_param):
+            if not self.enabled:
+                return
+            self._count[b] += 1
+            if self._count[b] == self.sizes[b]:
+                self._start(b)
+        return hook
+
+    def _start(self, b: int) -> None:
+        self._started[b] = True
+        op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
+        self._works.append(dist.all_reduce(self.views[b], op=op, async_op=True))
+
+    def begin(self) -> None:
+        """Call before backward."""
+        self._count = [0] * self.nb
+        self._started = [False] * self.nb
+        self._works = []
+
+    def finish(self) -> None:
+        """Call after backward: reduce buckets whose hooks did not all fire (unused parameters), then make the
+        current stream wait for every bucket."""
+        for b in range(self.nb):
+            if not self._started[b]:
+                self._start(b)
+        for w in self._works:
+            w.wait()
+        self._works = []
+        if not self._avg:
+            self.flat.div_(dist.get_world_size())
+
+
 class GraphedTrainStep:
     """The whole training step as ONE CUDA graph: uint8 normalisation, forward, loss, backward, gradient
     all-reduce, clipping and the SGD update are captured once and replayed, so a step costs one launch on the
@@ -165,14 +348,17 @@ class GraphedTrainStep:
     per-bucket hooks add host work on top).
 
     Gradients live in one flat fp32 buffer (every ``p.grad`` is a view into it, like DDP's
-    ``gradient_as_bucket_view``); with world_size > 1 the only collective is one NCCL all-reduce(avg) of that
-    buffer, captured inside the graph (parameter-gradient sync only, nothing to overlap it with is
-    lost: 141 MB over NVLink is < 2 % of the step).  Inputs are copied into static buffers before each replay.
+    ``gradient_as_bucket_view``); with world_size > 1 the only collective is the NCCL all-reduce(avg) of that buffer,
+    issued per stage bucket from inside the backward pass (:class:`BucketedGradSync`) and captured in the graph.
+    Inputs are copied into static buffers before each replay.  The learning rate is a device tensor of the optimizer
+    (:class:`FlatSGD`): ``set_lr`` before a replay changes the step the graph takes.  Capturing does not train: the
+    warm-up iterations it needs run on a snapshot of the parameters and optimizer state, which is restored.
     """
 
     def __init__(self, model: "Model", optimizer: torch.optim.Optimizer, env: DistEnv, example_batch, *,
                  transform: Optional[nn.Module] = None, autocast_dtype=torch.bfloat16,
-                 clip_norm: Optional[float] = 2.0, warmup: int = 3):
+                 clip_norm: Optional[float] = 2.0, warmup: int = 3, overlap_allreduce: bool = True,
+                 min_bucket_numel: int = 1 << 20):
         img, lab = example_batch
         if not img.is_cuda:
             raise RuntimeError("GraphedTrainStep needs CUDA tensors")
@@ -180,7 +366,8 @@ class GraphedTrainStep:
         self.transform, self.autocast_dtype, self.clip_norm = transform, autocast_dtype, clip_norm
         self.static_img = torch.empty_like(img)
         self.static_lab = torch.empty_like(lab)
-        params = [p for p in model.parameters() if p.requires_grad]
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        params = [p for _, p in named]
         self.flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=img.device)
         off = 0
         for p in params:
@@ -189,6 +376,9 @@ class GraphedTrainStep:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
         self.params = params
+        self.sync = None
+        if env.world_size > 1 and overlap_allreduce:
+            self.sync = BucketedGradSync(params, self.flat, BucketedGradSync.stage_bounds(named, min_bucket_numel))
         self.launches_per_step = 0
         self.graph = None
         self.static_loss = None
@@ -202,6 +392,14 @@ class GraphedTrainStep:
         self._consumed = [torch.cuda.Event() for _ in range(2)]  # staging slot copied into the static buffers
         self._staged = 0
 
+    def set_lr(self, lr: float) -> None:
+        """Learning rate of the next step (replayed graphs included).  Needs an optimizer with a device-side learning
+        rate (:class:`FlatSGD`); a plain torch optimizer bakes its lr into the captured kernels."""
+        if not hasattr(self.optimizer, "set_lr"):
+            raise RuntimeError("the optimizer has no device-side learning rate: its lr at capture time is baked into "
+                               "the CUDA graph; use train.build_optimizer / FlatSGD")
+        self.optimizer.set_lr(lr)
+
     def eager(self, img: torch.Tensor, lab: torch.Tensor) -> torch.Tensor:
         """The same step without the graph (warm-up, per-kernel instrumentation, debugging)."""
         self.static_img.copy_(img, non_blocking=True)
@@ -210,6 +408,11 @@ class GraphedTrainStep:
 
     def capture(self) -> "GraphedTrainStep":
         dev = self.static_img.device
+        # the warm-up steps (allocator / NCCL / cuBLAS initialisation before capture) must not train the model
+        snap_p = [p.detach().clone() for p in self.params]
+        snap_o = {k: (v.clone() if torch.is_tensor(v) else v) for p in self.params
+                  for k, v in ((id(p), dict(self.optimizer.state.get(p, {}))),)}
+        snap_o = {pid: {k: (v.clone() if torch.is_tensor(v) else v) for k, v in st.items()} for pid, st in snap_o.items()}
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -217,6 +420,19 @@ class GraphedTrainStep:
                 self._body()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        with torch.no_grad():
+            for p, q in zip(self.params, snap_p):
+                p.copy_(q)
+                st = self.optimizer.state.get(p, None)
+                if st is None:
+                    continue
+                old = snap_o[id(p)]
+                for k, v in st.items():
+                    if torch.is_tensor(v):
+                        if k in old:
+                            v.copy_(old[k])
+                        else:
+                            v.zero_()  # state created by the warm-up (momentum buffer): back to its initial value
         from . import functional as hvf
 
         n0 = hvf.LAUNCH_COUNT
@@ -233,8 +449,12 @@ class GraphedTrainStep:
         with torch.autocast("cuda", dtype=self.autocast_dtype, enabled=self.autocast_dtype is not None):
             outputs = self.model(batch)
             loss = self.model.loss(outputs, batch)
+        if self.sync is not None:
+            self.sync.begin()
         loss.backward()
-        if self.env.world_size > 1:
+        if self.sync is not None:
+            self.sync.finish()
+        elif self.env.world_size > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)
         if self.clip_norm is not None:
             # torch.nn.utils.clip_grad_norm_ on the flat view: one norm, one scale

@@ -72,6 +72,13 @@ HV_API int hv_window_attn_bwd_variant(int variant);
  * c_j = tau log2(e) / |k_j|, each (B*nW, heads, N) in window-slot order).  0 on invalid sizes.  Host-only query. */
 HV_API size_t hv_window_attn_stats_floats(int B, int H, int W, int C, int heads, int ws, int dtype);
 
+/* Name of the kernel hv_window_attn_fwd (backward = 0) / hv_window_attn_bwd (backward = 1) launches for a geometry with
+ * mask == NULL under the current variant settings, e.g. "wattn_tc64_bwd_kernel<true>" (tcgen05 / TMEM / TMA, shifted
+ * layer), "wattn_mma64_fwd_kernel<3>", "wattn_generic_bwd_kernel<float>".  For measurement records (bench.py names the
+ * kernel its roofline line is about from the dispatch, not from a literal).  Host-only query. */
+HV_API int hv_window_attn_kernel_name(int B, int H, int W, int C, int heads, int ws, int shift, int dtype, int backward,
+                                      char* out, int out_len);
+
 /* ---- host-side integer maps (CPU; same arithmetic the kernels use on the device) ------ */
 /* relative_position_index (N,N) int64 -- reference swinv2.py:175-190 */
 HV_API int hv_relative_position_index(int ws, int64_t* out);
@@ -131,6 +138,14 @@ HV_API int hv_window_attn_bwd(const void* qkv, const void* out, const void* dout
                        void* dqkv, float* dbias_table, float* dtau, float* dq_colsum, void* workspace,
                        size_t workspace_bytes, int B, int H, int W, int C, int heads, int ws, int shift, int dtype,
                        void* stream);
+
+/* Gradient of WindowAttention.q_bias (swinv2.py:193-195, 211-220) as its own streaming pass: dq_colsum[c] = sum over all
+ * tokens of dqkv[token, c], c < C, for dqkv (tokens, 3C) bf16.  The same numbers hv_window_attn_bwd writes when its
+ * dq_colsum argument is not NULL (it calls this); separate so that a caller can time / schedule it apart from the
+ * attention kernel.  HBM-bound: tokens * C * 2 bytes. */
+HV_API size_t hv_dq_colsum_workspace_bytes(int C);
+HV_API int hv_dq_colsum(const void* dqkv, float* dq_colsum, void* workspace, size_t workspace_bytes, int64_t tokens, int C,
+                        int dtype, void* stream);
 
 /* ---- res-post-norm: out = shortcut + keep_scale[sample] * LayerNorm(y + bias) ------------
  * Replaces `shortcut + drop_path(norm1(x))` / `x + drop_path(norm2(mlp(x)))`, swinv2.py:431, 434,

@@ -192,3 +192,25 @@ def test_kernel_variant_setters_validate_their_argument(lib, setter):
     assert fn(2) != 0 and b"variant" in lib.hv_last_error()
     assert fn(-2) != 0
     assert fn(-1) == 0
+
+
+def test_kernel_name_query_follows_the_dispatch(lib):
+    """hv_window_attn_kernel_name (host-only): which kernel a geometry launches -- what bench.py prints next to its
+    roofline numbers.  SwinV2-T stages run on the tcgen05 kernels in both directions."""
+    import ctypes
+
+    def name(B, H, W, C, heads, ws, shift, dtype, bwd):
+        buf = ctypes.create_string_buffer(96)
+        assert lib.hv_window_attn_kernel_name(B, H, W, C, heads, ws, shift, dtype, bwd, buf, len(buf)) == 0
+        return buf.value.decode()
+
+    for C, heads, res in ((96, 3, 64), (192, 6, 32), (384, 12, 16), (768, 24, 8)):
+        assert name(4, res, res, C, heads, 8, 0, _lib.HV_BF16, 0) == "wattn_tc64_fwd_kernel"
+        assert name(4, res, res, C, heads, 8, 0, _lib.HV_BF16, 1) == "wattn_tc64_bwd_kernel<false>"
+        if res > 8:
+            assert name(4, res, res, C, heads, 8, 4, _lib.HV_BF16, 1) == "wattn_tc64_bwd_kernel<true>"
+    assert name(1, 24, 24, 96, 3, 8, 3, _lib.HV_BF16, 0) == "wattn_mma64_fwd_kernel<3>"     # odd shift: no TMA split
+    assert name(1, 32, 32, 128, 4, 16, 8, _lib.HV_BF16, 1) == "wattn_generic_bwd_kernel<bf16>"  # SwinV2-B window 16
+    assert name(1, 16, 16, 96, 3, 8, 4, _lib.HV_F32, 0) == "wattn_generic_fwd_kernel<float>"
+    buf = ctypes.create_string_buffer(8)
+    assert lib.hv_window_attn_kernel_name(1, 16, 16, 96, 5, 8, 0, _lib.HV_BF16, 0, buf, 8) != 0  # C % heads

@@ -85,9 +85,15 @@ def test_optimizer_groups_and_sharding_rules():
     opt = T.build_optimizer(model, lr=0.1, momentum=0.875, weight_decay=5e-4)
     decay, no_decay = opt.param_groups
     names = {id(p): n for n, p in model.named_parameters()}
-    assert sorted(names[id(p)] for p in decay["params"]) == ["module.head.weight"]
+    # like the reference's Composer Model (models.py:121-152) the wrapper has no no_weight_decay(): only 1-D parameters and
+    # biases escape the decay (optim.py:48-58) ...
+    assert sorted(names[id(p)] for p in decay["params"]) == ["module.fc1.weight", "module.head.weight"]
     assert no_decay["weight_decay"] == 0.0 and decay["weight_decay"] == 5e-4
-    assert "module.fc1.weight" in {names[id(p)] for p in no_decay["params"]}  # no_weight_decay() honoured
+    # ... while the bare backbone's skip list is honoured
+    bare = TinyBackbone()
+    d2, nd2 = T.build_optimizer(bare, lr=0.1).param_groups
+    n2 = {id(p): n for n, p in bare.named_parameters()}
+    assert sorted(n2[id(p)] for p in d2["params"]) == ["head.weight"] and "fc1.weight" in {n2[id(p)] for p in nd2["params"]}
     assert T.per_rank_batch(2048, 8) == 256
     with pytest.raises(ValueError):
         T.per_rank_batch(10, 4)
@@ -97,4 +103,136 @@ def test_optimizer_groups_and_sharding_rules():
     logits = [torch.zeros(2, 3), torch.zeros(2, 4)]
     tgt = torch.zeros(2, 2, dtype=torch.long)
     want = 8.0 * torch.log(torch.tensor(3.0)) + 5.65 * torch.log(torch.tensor(4.0))
-    assert torch.allclose(T.multitask_cross_entropy(logits, tgt), want, atol=1e-5)
+    assert torch.allclose(T.multitask_cross_entropy(logits, tgt, (8.0, 5.65)), want, atol=1e-5)
+    with pytest.raises(ValueError):  # hierarchy.py:80-82: one coefficient per tier
+        T.multitask_cross_entropy(logits, tgt)
+
+
+def _two_models():
+    torch.manual_seed(0)
+    a = TinyBackbone()
+    torch.manual_seed(0)
+    b = TinyBackbone()
+    return a, b
+
+
+def test_flat_sgd_matches_torch_nesterov_and_decoupled_rule():
+    """reference optim.py:16-23 ("sgd": torch SGD with nesterov) and optim.py:37-44 (DecoupledSGDW), with the learning
+    rate changed mid-run through the device-side lr (what a scheduler does, also under a CUDA graph)."""
+    a, b = _two_models()
+    oa = T.build_optimizer(a, lr=0.1, name="sgd")
+    decay = [p for n, p in b.named_parameters() if p.dim() > 1 and n != "fc1.weight"]
+    nd = [p for n, p in b.named_parameters() if p.dim() == 1 or n == "fc1.weight"]
+    ob = torch.optim.SGD([{"params": decay}, {"params": nd, "weight_decay": 0.0}], lr=0.1, momentum=0.875, nesterov=True,
+                         weight_decay=5e-4)
+    for i in range(4):
+        x = torch.randn(5, 3, 2, 2)
+        for m, o in ((a, oa), (b, ob)):
+            o.zero_grad()
+            m(x).square().mean().backward()
+            o.step()
+        if i == 1:
+            oa.set_lr(0.05)
+            for g in ob.param_groups:
+                g["lr"] = 0.05
+    for p, q in zip(a.parameters(), b.parameters()):
+        assert torch.allclose(p, q, rtol=1e-5, atol=1e-6)
+    # decoupled: p <- p (1 - lr / lr0 * wd) - lr * buf, buf <- momentum * buf + grad
+    a, b = _two_models()
+    oa = T.build_optimizer(a, lr=0.2, momentum=0.5, weight_decay=0.1, name="decoupledsgdw")
+    bufs = {n: torch.zeros_like(p) for n, p in b.named_parameters()}
+    lr = 0.2
+    for i in range(3):
+        x = torch.randn(5, 3, 2, 2)
+        oa.zero_grad()
+        a(x).square().mean().backward()
+        oa.step()
+        b.zero_grad()
+        b(x).square().mean().backward()
+        with torch.no_grad():
+            for n, p in b.named_parameters():
+                bufs[n] = 0.5 * bufs[n] + p.grad
+                if p.dim() > 1 and n != "fc1.weight":
+                    p.mul_(1 - lr / 0.2 * 0.1)
+                p.add_(bufs[n], alpha=-lr)
+        if i == 0:
+            lr = 0.1
+            oa.set_lr(lr)
+    for p, q in zip(a.parameters(), b.parameters()):
+        assert torch.allclose(p, q, rtol=1e-5, atol=1e-6)
+    with pytest.raises(ValueError):
+        T.build_optimizer(a, name="adamw")
+
+
+def test_cosine_warmup_and_label_smoothing():
+    f = [T.cosine_warmup_factor(s, 4, 20) for s in (0, 2, 4, 12, 20, 25)]
+    assert f[0] == 0.0 and f[1] == 0.5 and f[2] == 1.0 and abs(f[3] - 0.5) < 1e-12 and abs(f[4]) < 1e-12 and abs(f[5]) < 1e-12
+    assert abs(T.cosine_warmup_factor(20, 0, 20, alpha_f=0.1) - 0.1) < 1e-12
+    g = torch.Generator().manual_seed(1)
+    logits = torch.randn(6, 9, generator=g)
+    tgt = torch.randint(0, 9, (6,), generator=g)
+    soft = T.smooth_labels(logits, tgt, 0.1)
+    assert torch.allclose(soft.sum(1), torch.ones(6)) and abs(float(soft[0, tgt[0]]) - (0.9 + 0.1 / 9)) < 1e-6
+    # algorithmic.py:88-119: smoothing applied per tier, loss on the soft targets == torch's label_smoothing
+    lg = [torch.randn(6, 3, generator=g), torch.randn(6, 4, generator=g)]
+    tg = torch.stack([torch.randint(0, 3, (6,), generator=g), torch.randint(0, 4, (6,), generator=g)], dim=1)
+    want = 2.0 * torch.nn.functional.cross_entropy(lg[0], tg[:, 0], label_smoothing=0.1) + \
+        0.5 * torch.nn.functional.cross_entropy(lg[1], tg[:, 1], label_smoothing=0.1)
+    got = T.multitask_cross_entropy(lg, tg, (2.0, 0.5), label_smoothing=0.1)
+    assert torch.allclose(got, want, atol=1e-6)
+    m = T.Model(torch.nn.Identity(), coeffs=(2.0, 0.5), label_smoothing=0.1)
+    assert torch.allclose(m.loss(lg, (None, tg)), want, atol=1e-6)
+
+
+def _bucket_worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    env = T.init_distributed("gloo")
+    torch.manual_seed(0)
+    model = TinyBackbone()
+    named = list(model.named_parameters())
+    params = [p for _, p in named]
+    flat = torch.zeros(sum(p.numel() for p in params))
+    off = 0
+    for p in params:
+        p.grad = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+    bounds = T.BucketedGradSync.stage_bounds(named, min_bucket_numel=1)  # one bucket per top-level module
+    sync = T.BucketedGradSync(params, flat, bounds)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(8, 3, 2, 2, generator=g)
+    y = torch.randint(0, 5, (8,), generator=g)
+    lo, hi = T.shard_range(8, env.rank, env.world_size)
+    for _ in range(2):  # twice: the per-step bookkeeping resets
+        flat.zero_()
+        sync.begin()
+        torch.nn.functional.cross_entropy(model(x[lo:hi]), y[lo:hi]).backward()
+        sync.finish()
+    q.put((rank, flat.numpy().copy(), bounds))
+    T.barrier(env)
+    torch.distributed.destroy_process_group()
+
+
+def test_bucketed_grad_sync_two_ranks_matches_single_process():
+    """The overlapped per-stage all-reduce of GraphedTrainStep (train.BucketedGradSync) leaves every rank with the
+    gradient of the concatenated batch (reference main.py:44-48: per-rank batch = global / world)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = sorted((q.get(timeout=120) for _ in range(2)), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    torch.manual_seed(0)
+    model = TinyBackbone()
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(8, 3, 2, 2, generator=g)
+    y = torch.randint(0, 5, (8,), generator=g)
+    torch.nn.functional.cross_entropy(model(x), y).backward()
+    want = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+    assert results[0][2] == [0, 2, 4, 6]  # fc1 | norm | head
+    for r in results:
+        assert torch.allclose(torch.from_numpy(r[1]), want, atol=1e-6)

@@ -33,7 +33,7 @@ def timeit(fns, iters, warmup=5):
     return e0.elapsed_time(e1) / iters
 
 
-def bench_attn(B, res, C, heads, ws, shift, dtype, iters, tau_mode="init"):
+def bench_attn(B, res, C, heads, ws, shift, dtype, iters, tau_mode="init", colsum=False):
     dev = "cuda"
     L = res * res
     nW = (res // ws) ** 2
@@ -62,7 +62,8 @@ def bench_attn(B, res, C, heads, ws, shift, dtype, iters, tau_mode="init"):
     fw = [lambda s=s: hvf.window_attention_fwd_raw(s[0], tab, tau, None, s[1], s[2], *geom) for s in sets]
     for f in fw:
         f()
-    bw = [lambda s=s: hvf.window_attention_bwd_raw(s[0], s[1], s[3], s[2], tab, tau, None, s[4], dbias, dtau, wsp, *geom)
+    cs = torch.empty(C, device=dev) if colsum else None  # the training step asks for d(q_bias) = column sums of dq
+    bw = [lambda s=s: hvf.window_attention_bwd_raw(s[0], s[1], s[3], s[2], tab, tau, None, s[4], dbias, dtau, wsp, *geom, dq_colsum=cs)
           for s in sets]
     t_f = timeit(fw, iters)
     t_b = timeit(bw, iters)
@@ -179,6 +180,7 @@ def main():
     ap.add_argument("--json", default="")
     ap.add_argument("--only", default="")
     ap.add_argument("--tau", default="init", choices=["init", "clamp", "mixed"])
+    ap.add_argument("--colsum", action="store_true", help="attention backward also produces d(q_bias) (as in the training step)")
     a = ap.parse_args()
     rows = []
     B = a.batch
@@ -186,7 +188,7 @@ def main():
     if a.only in ("", "attn", "attn0"):
         for res, C, h in stages:
             for shift in ((0, 4) if res > 8 and a.only != "attn0" else (0,)):
-                rows.append(bench_attn(B, res, C, h, 8, shift, torch.bfloat16, a.iters, a.tau))
+                rows.append(bench_attn(B, res, C, h, 8, shift, torch.bfloat16, a.iters, a.tau, a.colsum))
                 print(json.dumps(rows[-1]), flush=True)
         if a.only != "attn0":
             rows.append(bench_attn(max(B // 8, 8), 64, 96, 3, 8, 4, torch.float32, max(a.iters // 6, 3)))
