@@ -195,7 +195,7 @@ class FlatSGD(torch.optim.Optimizer):
             if g["decoupled"]:
                 torch._foreach_mul_(bufs, mom)
                 torch._foreach_add_(bufs, grads)
-                if wd != 0.0:
+                if wd != 0.0 and g["initial_lr"] != 0.0:
                     torch._foreach_mul_(params, 1.0 - self.lr_t * (wd / g["initial_lr"]))
                 upd = torch._foreach_mul(bufs, -self.lr_t)
             else:
