@@ -47,6 +47,7 @@ SIGNATURES = {
     "hv_patch_merge_gather_bwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "hv_cpb_bias_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "hv_cpb_bias_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "hv_cross_entropy_fwd_grad": (_I, [_P, _P, _P, _P, _L, _I, _F, _F, _I, _P]),
     "hv_patch_rows": (_I, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
 }
 

@@ -51,6 +51,8 @@ int cpb_bias_fwd(const float* coords, const float* w1, const float* b1, const fl
                  int heads, cudaStream_t st);
 int cpb_bias_bwd(const float* coords, const float* w1, const float* b1, const float* w2, const float* dtable, float* dw1,
                  float* db1, float* dw2, float* workspace, int M, int hid, int heads, cudaStream_t st);
+int ce_fwd_grad(const void* logits, const int64_t* target, float* loss_rows, void* dlogits, int64_t rows, int classes,
+                float smoothing, float scale, int dtype, cudaStream_t st);
 int patch_rows(const void* img, int img_dtype, const float* scale, const float* shift, void* out, int out_dtype, int B,
                int Cin, int H, int W, int P, cudaStream_t st);
 
@@ -348,6 +350,14 @@ int hv_patch_rows(const void* img, int img_dtype, const float* scale, const floa
   int rc = check_device_arch();
   if (rc) return rc;
   return patch_rows(img, img_dtype, scale, shift, out, out_dtype, B, Cin, H, W, P, static_cast<cudaStream_t>(stream));
+}
+
+int hv_cross_entropy_fwd_grad(const void* logits, const int64_t* target, float* loss_rows, void* dlogits, int64_t rows,
+                              int classes, float smoothing, float scale, int dtype, void* stream) {
+  if (!logits || !target || !loss_rows || !dlogits) HV_FAIL(HV_ERR_NULL, "hv_cross_entropy_fwd_grad: NULL argument");
+  int rc = check_device_arch();
+  if (rc) return rc;
+  return ce_fwd_grad(logits, target, loss_rows, dlogits, rows, classes, smoothing, scale, dtype, static_cast<cudaStream_t>(stream));
 }
 
 int hv_cpb_bias_fwd(const float* coords, const float* w1, const float* b1, const float* w2, float* table, int M, int hidden,

@@ -30,10 +30,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (++spins > (1u << 17)) __trap();  // a lost arrival must abort the kernel (~seconds), never hang the GPU
   }
 }
+// A lost arrival must abort the kernel after a few seconds instead of hanging the GPU.  Profilers that patch the SASS
+// (ncu --set full, SourceCounters) slow the kernel down enough to hit the default limit: build with a larger one
+// (tools/build_variant.sh ncu "-DHV_SPIN_LIMIT_LOG2=31" ...) for those captures.
+#ifndef HV_SPIN_LIMIT_LOG2
+#define HV_SPIN_LIMIT_LOG2 24
+#endif
 // latency-critical variant: plain try_wait loop (the hardware's default suspend window), no extra sleep
 __device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity) {
   uint32_t done = 0, spins = 0;
   while (true) {
+#ifdef HV_WAIT_HINT_NS
+    // with a suspend-time hint the hardware parks the warp until the phase completes (or the hint expires) instead of
+    // returning after its short default window: far fewer polling instructions compete with the working warps
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity), "n"(HV_WAIT_HINT_NS)
+        : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -41,11 +58,12 @@ __device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity) {
         : "=r"(done)
         : "r"(bar), "r"(parity)
         : "memory");
+#endif
     if (done) break;
 #ifdef HV_SPIN_SLEEP_NS
     asm volatile("nanosleep.u32 %0;" ::"n"(HV_SPIN_SLEEP_NS));  // back off: a tight poll loop takes issue slots from the working warps
 #endif
-    if (++spins > (1u << 24)) __trap();
+    if (++spins > (1u << HV_SPIN_LIMIT_LOG2)) __trap();
   }
 }
 // non-blocking phase test

@@ -15,6 +15,9 @@
 //   * warp roles: 0 TMA producer, 1 MMA issuer (one thread), 2-3 L2 norms of the q / k rows (tensor-pipe self
 //     products via mma.sync on the swizzled tiles), 4-11 two softmax groups working on alternate unit pairs so that
 //     the MMAs, the loads and the exponentials of neighbouring pairs overlap; everything hands over through mbarriers.
+// waits with a suspend-time hint: measured 2-3 % faster for this kernel (fewer polling instructions), neutral to slightly
+// negative for the backward, which keeps the plain try_wait loop
+#define HV_WAIT_HINT_NS 1000
 #include "hv_tc.cuh"
 
 namespace hv {

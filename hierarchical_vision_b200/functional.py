@@ -521,3 +521,39 @@ def cpb_bias_supported(w1: torch.Tensor, w2: torch.Tensor) -> bool:
 def cpb_bias(coords: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor) -> torch.Tensor:
     """((2ws-1)^2, heads) continuous position bias table, 16 * sigmoid(cpb_mlp(coords)) (swinv2.py:233-246)."""
     return _CpbBias.apply(coords, w1, b1, w2)
+
+
+class _CrossEntropy(torch.autograd.Function):
+    """mean over rows of CE(logits, target) with label smoothing; loss rows and d logits come out of one kernel
+    (hv_cross_entropy_fwd_grad), the backward only multiplies by the upstream scalar."""
+
+    @staticmethod
+    def forward(ctx, logits, target, smoothing, weight):
+        _need_cuda(logits, "cross_entropy")
+        lib = _lib.load()
+        logits = logits.contiguous()
+        rows, classes = logits.shape
+        target = target.contiguous()
+        if target.dtype != torch.int64 or target.shape != (rows,):
+            raise RuntimeError("cross_entropy: target must be int64 class indices of shape (rows,)")
+        loss_rows = torch.empty((rows,), dtype=torch.float32, device=logits.device)
+        dlogits = torch.empty_like(logits)
+        with torch.cuda.device(logits.device):
+            rc = lib.hv_cross_entropy_fwd_grad(_ptr(logits), _ptr(target), _ptr(loss_rows), _ptr(dlogits), rows, classes,
+                                               float(smoothing), float(weight) / rows, _code(logits), _stream(logits.device))
+        check(rc, "hv_cross_entropy_fwd_grad")
+        global LAUNCH_COUNT
+        LAUNCH_COUNT += 1
+        ctx.save_for_backward(dlogits)
+        return loss_rows.mean() * weight
+
+    @staticmethod
+    def backward(ctx, g):
+        (dlogits,) = ctx.saved_tensors
+        return dlogits * g.to(dlogits.dtype), None, None, None
+
+
+def cross_entropy(logits: torch.Tensor, target: torch.Tensor, label_smoothing: float = 0.0, weight: float = 1.0) -> torch.Tensor:
+    """``weight * F.cross_entropy(logits, target, label_smoothing=...)`` (mean reduction) for (rows, classes) float32 /
+    bfloat16 logits on the device; one kernel forward, one elementwise multiply backward."""
+    return _CrossEntropy.apply(logits, target, label_smoothing, weight)

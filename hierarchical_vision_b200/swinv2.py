@@ -250,13 +250,17 @@ class WindowAttention(nn.Module):
         return torch.clamp(self.logit_scale.float(), max=self.logit_clamp_max.float()).exp().reshape(-1)
 
     def _fused(self, x_tokens, B, H, W, shift, mask, with_proj_bias=True):
+        """Returns (y, bias, shortcut): the attention branch output; with ``with_proj_bias=False`` the proj bias the caller
+        folds into its LayerNorm kernel (else None, already added); and the tensor the caller must use for the residual
+        shortcut -- ``x_tokens`` routed through the attention node when that node can absorb the shortcut's gradient into
+        its dx GEMM, else ``x_tokens`` itself."""
         if self.window_size[0] != self.window_size[1]:
             raise NotImplementedError("fused window attention needs square windows (the reference's "
                                       "SwinTransformerBlock only ever builds square ones, swinv2.py:339)")
         if self.attn_drop.p > 0.0 and self.training:
             raise NotImplementedError("attention dropout is not fused; every reference config uses attn_drop=0")
         ws = self.window_size[0]
-        self._shortcut = None
+        shortcut = x_tokens
         table, tau = self._bias_table(), self._tau()
         dt = torch.get_autocast_dtype("cuda") if (x_tokens.is_cuda and torch.is_autocast_enabled("cuda")) else x_tokens.dtype
         v_bias = None
@@ -266,7 +270,7 @@ class WindowAttention(nn.Module):
             o, sc = hvf.qkv_window_attention(x_tokens.to(dt), self.qkv.weight.to(dt), self.q_bias, table, tau, B=B, H=H,
                                              W=W, C=self.dim, heads=self.num_heads, ws=ws, shift=shift)
             if sc.dtype == x_tokens.dtype:
-                self._shortcut = sc  # same tensor as x_tokens; picked up by SwinTransformerBlock for the residual
+                shortcut = sc  # same values as x_tokens; its gradient is accumulated inside the node's dx GEMM
             v_bias = self.v_bias
         else:
             o = hvf.window_attention(self._qkv(x_tokens), table, tau, B=B, H=H, W=W, C=self.dim,
@@ -274,13 +278,13 @@ class WindowAttention(nn.Module):
         if with_proj_bias:
             if v_bias is not None:
                 o = o + v_bias.to(o.dtype)
-            return self.proj_drop(self.proj(o))
+            return self.proj_drop(self.proj(o)), None, shortcut
         # the caller folds the bias into its LayerNorm kernel: proj(o + v_bias) = o W^T + (W v_bias + proj.bias)
         bias = self.proj.bias
         if v_bias is not None:
             with torch.autocast(device_type="cuda", enabled=False):
                 bias = bias + F.linear(v_bias.float(), self.proj.weight.float())
-        return F.linear(o, self.proj.weight), bias
+        return F.linear(o, self.proj.weight), bias, shortcut
 
     def forward(self, x, mask=None):
         """x: (num_windows*B, N, C); mask: (num_windows, N, N) of 0/-100 or None (swinv2.py:204-264)."""
@@ -288,9 +292,7 @@ class WindowAttention(nn.Module):
         ws = self.window_size[0]
         assert N == self.window_size[0] * self.window_size[1], "input feature has wrong size"
         # a pre-partitioned window is a ws x ws image with no shift
-        out = self._fused(x, B_, ws, ws, 0, mask)
-        self._shortcut = None
-        return out
+        return self._fused(x, B_, ws, ws, 0, mask)[0]
 
     def extra_repr(self) -> str:
         return (f"dim={self.dim}, window_size={self.window_size}, "
@@ -354,12 +356,7 @@ class SwinTransformerBlock(nn.Module):
         fold1 = self._fusable(self.norm1) and self.attn.proj_drop.p == 0.0
         fold2 = self._fusable(self.norm2) and self.mlp.drop.p == 0.0 and isinstance(self.mlp, Mlp)
         # roll + partition + attention + reverse + roll back: one kernel, no rolled / partitioned copy
-        if fold1:
-            y, proj_bias = self.attn._fused(x, B, H, W, self.shift_size, None, with_proj_bias=False)
-        else:
-            y, proj_bias = self.attn._fused(x, B, H, W, self.shift_size, None), None
-        if self.attn._shortcut is not None:  # x itself, routed through the attention node (gradient add fused into its GEMM)
-            x, self.attn._shortcut = self.attn._shortcut, None
+        y, proj_bias, x = self.attn._fused(x, B, H, W, self.shift_size, None, with_proj_bias=not fold1)
         x = self._post_norm(self.norm1, y, x, proj_bias)                                       # swinv2.py:431
         if fold2:
             a, x = self.mlp._hidden(x, with_shortcut=True)
@@ -600,7 +597,10 @@ class SwinTransformerV2(nn.Module):
             x = layer(x)
             if output_activations:
                 activations.append(x)
-        x = self.norm(x)
+        if SwinTransformerBlock._fusable(self.norm) and x.is_cuda and x.dtype in (torch.float32, torch.bfloat16):
+            x = hvf.ln_residual(x, None, self.norm.weight, self.norm.bias, None, self.norm.eps)  # swinv2.py:833
+        else:
+            x = self.norm(x)
         x = torch.flatten(self.avgpool(x.transpose(1, 2)), 1)
         return (x, activations) if output_activations else x
 

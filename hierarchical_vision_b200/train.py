@@ -85,6 +85,16 @@ class NormalizeOnDevice(nn.Module):
         return (x.float() - self.mean) / self.std
 
 
+def _fused_ce_ok(logits: torch.Tensor, target: torch.Tensor) -> bool:
+    return (logits.is_cuda and logits.dim() == 2 and logits.dtype in (torch.float32, torch.bfloat16)
+            and target.dtype == torch.int64 and target.dim() == 1)
+
+
+def hvf_cross_entropy(logits, target, label_smoothing, weight=1.0):
+    from . import functional as hvf  # the kernels only exist on the device; the CPU host-logic tests never get here
+    return hvf.cross_entropy(logits, target, label_smoothing, weight)
+
+
 def smooth_labels(logits: torch.Tensor, target: torch.Tensor, smoothing: float = 0.1) -> torch.Tensor:
     """(B,) class indices -> (B, classes) soft targets ``onehot * (1 - smoothing) + smoothing / classes``
     (algorithmic.py:160-164, itself Composer's ``smooth_labels``)."""
@@ -105,6 +115,9 @@ def multitask_cross_entropy(logits: List[torch.Tensor], targets, coeffs: Sequenc
     total = logits[0].new_zeros((), dtype=torch.float32)
     for t, lg in enumerate(logits):
         tg = targets[t]
+        if _fused_ce_ok(lg, tg):  # class-index targets on the device: loss and gradient from one kernel per tier
+            total = total + hvf_cross_entropy(lg, tg, label_smoothing, coeffs[t])
+            continue
         if label_smoothing > 0.0 and not tg.is_floating_point():
             tg = smooth_labels(lg, tg, label_smoothing)
         total = total + coeffs[t] * F.cross_entropy(lg.float(), tg)
@@ -130,6 +143,8 @@ class Model(nn.Module):
         _, targets = batch
         if isinstance(outputs, (list, tuple)):
             return multitask_cross_entropy(list(outputs), targets, self.coeffs, self.label_smoothing)
+        if _fused_ce_ok(outputs, targets):
+            return hvf_cross_entropy(outputs, targets, self.label_smoothing)
         return F.cross_entropy(outputs.float(), targets, label_smoothing=self.label_smoothing)
 
 

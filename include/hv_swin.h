@@ -200,6 +200,16 @@ HV_API int hv_cpb_bias_fwd(const float* coords, const float* w1, const float* b1
 HV_API int hv_cpb_bias_bwd(const float* coords, const float* w1, const float* b1, const float* w2, const float* dtable,
                     float* dw1, float* db1, float* dw2, float* workspace, int M, int hidden, int heads, void* stream);
 
+/* ---- cross entropy with label smoothing, loss rows and gradient in one launch ---------------
+ * The tail of the step: reference models.py:121-152 (`loss`), hierarchy.py:65-94 (MultitaskCrossEntropy =
+ * dot(coeffs, CE per tier); call once per tier with scale = coeff / rows), algorithmic.py:88-119, 160-164 (label
+ * smoothing: target = onehot (1 - a) + a / classes).
+ *   logits    device (rows, classes) `dtype` (float32 / bfloat16)     target  device int64 (rows), class indices
+ *   loss_rows device float32 (rows): lse - (1 - a) x[t] - a mean(x)   (the caller averages / weights them)
+ *   dlogits   device (rows, classes) `dtype`: scale * (softmax - (1 - a) onehot - a / classes) */
+HV_API int hv_cross_entropy_fwd_grad(const void* logits, const int64_t* target, float* loss_rows, void* dlogits, int64_t rows,
+                                     int classes, float smoothing, float scale, int dtype, void* stream);
+
 /* ---- PatchEmbed input gather -------------------------------------------------------------
  * Left operand of PatchEmbed's Conv2d(in_chans, embed_dim, kernel = stride = patch) seen as a per-patch GEMM
  * (swinv2.py:648-657): out[(b, ph, pw), (c, dy, dx)] = img[b, c, ph*P + dy, pw*P + dx] * scale[c] + shift[c].

@@ -669,6 +669,44 @@ def test_bias_gelu_outliers(dtype):
     assert (h.grad.float().cpu() - h64.grad.float()).abs().max() <= (2e-2 if dtype == torch.bfloat16 else 1e-4)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("classes", [3, 273, 10000])
+@pytest.mark.parametrize("smoothing", [0.0, 0.1])
+def test_fused_cross_entropy(dtype, classes, smoothing):
+    """hv_cross_entropy_fwd_grad == F.cross_entropy(label_smoothing) in value and gradient (models.py:121-152,
+    algorithmic.py:160-164); bf16 logits are compared with torch on the same rounded logits."""
+    gen = torch.Generator().manual_seed(classes)
+    rows = 37
+    x = (3 * torch.randn(rows, classes, generator=gen)).to(DEV, dtype).requires_grad_(True)
+    t = torch.randint(0, classes, (rows,), generator=gen).to(DEV)
+    loss = hvf.cross_entropy(x, t, smoothing, 2.5)
+    (loss * 0.5).backward()
+    x64 = x.detach().double().cpu().requires_grad_(True)
+    want = 2.5 * torch.nn.functional.cross_entropy(x64, t.cpu(), label_smoothing=smoothing)
+    (want * 0.5).backward()
+    assert abs(loss.item() - want.item()) <= 1e-5 * abs(want.item()) + 1e-6
+    assert_close("dlogits", x.grad, x64.grad, 1e-5 if dtype == torch.float32 else 8e-3)
+
+
+def test_multitask_loss_on_device_matches_host():
+    """train.multitask_cross_entropy through the fused kernel (one launch per tier) == the torch composition of
+    hierarchy.py:65-94 with the per-tier label smoothing of algorithmic.py:100-112."""
+    from hierarchical_vision_b200 import train as T
+    gen = torch.Generator().manual_seed(2)
+    tiers = (3, 13, 51)
+    lg = [torch.randn(6, n, generator=gen) for n in tiers]
+    tg = torch.stack([torch.randint(0, n, (6,), generator=gen) for n in tiers], dim=1)
+    want = T.multitask_cross_entropy(lg, tg, (8.0, 5.65, 4.0), label_smoothing=0.1)  # CPU: torch ops
+    dev = [l.to(DEV).requires_grad_(True) for l in lg]
+    got = T.multitask_cross_entropy(dev, tg.to(DEV), (8.0, 5.65, 4.0), label_smoothing=0.1)
+    assert abs(got.item() - want.item()) <= 1e-5 * abs(want.item())
+    got.backward()
+    ref = [l.clone().requires_grad_(True) for l in lg]
+    T.multitask_cross_entropy(ref, tg, (8.0, 5.65, 4.0), label_smoothing=0.1).backward()
+    for a, b in zip(dev, ref):
+        assert_close("dlogits", a.grad, b.grad, 1e-5)
+
+
 def test_graphed_train_step_matches_eager():
     """GraphedTrainStep (one CUDA graph per step, flat gradient buffer) takes the same optimisation steps as the
     eager train_step on identical weights and batches (drop_path 0, so no RNG is involved)."""

@@ -180,11 +180,25 @@ def main():
     ap.add_argument("--json", default="")
     ap.add_argument("--only", default="")
     ap.add_argument("--tau", default="init", choices=["init", "clamp", "mixed"])
+    ap.add_argument("--sweep", action="store_true", help="BASELINE.json configs[4]: shifted window attention at the stage-0 and "
+                    "stage-1 shapes + PatchMerging's gather over batch 32 ... 512")
     ap.add_argument("--colsum", action="store_true", help="attention backward also produces d(q_bias) (as in the training step)")
     a = ap.parse_args()
     rows = []
     B = a.batch
     stages = [(64, 96, 3), (32, 192, 6), (16, 384, 12), (8, 768, 24)]
+    if a.sweep:
+        for b in (32, 64, 128, 256, 512):
+            for res, C, h in stages[:2]:
+                for shift in (0, 4):
+                    rows.append(bench_attn(b, res, C, h, 8, shift, torch.bfloat16, a.iters, a.tau))
+                    print(json.dumps(rows[-1]), flush=True)
+                rows.append(dict(bench_merge(b, res, C, torch.bfloat16, a.iters), B=b))
+                print(json.dumps(rows[-1]), flush=True)
+        if a.json:
+            with open(a.json, "w") as f:
+                json.dump(rows, f, indent=1)
+        return
     if a.only in ("", "attn", "attn0"):
         for res, C, h in stages:
             for shift in ((0, 4) if res > 8 and a.only != "attn0" else (0,)):
