@@ -84,9 +84,10 @@ constexpr int kColDB = 448;
 
 struct BwdParams {
   Geom g;
-  // head-pair groups (both units = heads 2g, 2g+1 of one window) and the cross group (odd last head of two windows); of the
-  // ctas_same / ctas_cross CTAs of a group the last ctas_same1 / ctas_cross1 take the right-edge windows of a shifted layer
-  int n_same, has_cross, ctas_same, ctas_cross, ctas_same1, ctas_cross1;
+  // head-pair groups (both units = heads 2g, 2g+1 of one window) and the cross group (odd last head of two windows); the
+  // ctas_same / ctas_cross CTAs of a group are split between the window classes of a shifted layer (cls_same / cls_cross
+  // CTAs per class, in class order; an unshifted layer has class 0 only)
+  int n_same, has_cross, ctas_same, ctas_cross, cls_same[3], cls_cross[3];
   int64_t plane;  // floats per plane of the forward's statistics: B * nW * heads * 64
   int ko;         // HV_TC_TRACE builds only: knock-out bits (results are wrong) | traced CTA << 8
 };
@@ -95,28 +96,32 @@ struct BwdParams {
 constexpr int kNumMaps = 9;
 struct BwdMaps { CUtensorMap m[3][kNumMaps]; };  // qkv, dout, dqkv
 
-// Window classes of a shifted layer: 0 = windows left of the last window column (no column wrap: slot order, the bottom row
-// wraps as two row boxes), 1 = right-edge windows (column wrap: two column parts, permuted token order).  A CTA serves
-// one class, so that its tile order -- and with it bias lookup, mask and the d(bias) accumulator -- is uniform.
+// Window classes of a shifted layer: 0 = interior windows (no wrap, no mask: exactly the unshifted code path), 1 = bottom
+// row of windows left of the last column (rows wrap: slot order, two row boxes, mask along h), 2 = right-edge windows
+// (columns wrap: two column parts, permuted token order, mask along w and, in the corner, h).  A CTA serves one class,
+// so that its tile order -- and with it bias lookup, mask and the d(bias) accumulator -- is uniform, and 49 of 64
+// windows of a stage-0 layer run the cheap class-0 code.
 struct CtaWork {
-  int head_a, head_b, cross, cls, first, stride, npairs, ncls, nWw, shifted;
+  int head_a, head_b, cross, cls, first, stride, npairs, ncls, wcls, hcls;
   __device__ __forceinline__ void init(const BwdParams& p, int cta) {
-    const int nrows = p.g.B * p.g.nW;
     const int same_total = p.n_same * p.ctas_same;
-    int pos, c1, ctas;
+    int pos;
+    const int* cc;
     if (cta < same_total) {
       const int grp = cta / p.ctas_same;
       cross = 0; head_a = 2 * grp; head_b = 2 * grp + 1;
-      pos = cta - grp * p.ctas_same; c1 = p.ctas_same1; ctas = p.ctas_same;
+      pos = cta - grp * p.ctas_same; cc = p.cls_same;
     } else {
       cross = 1; head_a = head_b = p.g.heads - 1;
-      pos = cta - same_total; c1 = p.ctas_cross1; ctas = p.ctas_cross;
+      pos = cta - same_total; cc = p.cls_cross;
     }
-    nWw = p.g.nWw;
-    shifted = p.g.shift > 0;
-    const int n1 = shifted ? nrows / nWw : 0;
-    if (pos < ctas - c1) { cls = 0; first = pos; stride = ctas - c1; ncls = nrows - n1; }
-    else { cls = 1; first = pos - (ctas - c1); stride = c1; ncls = n1; }
+    cls = pos < cc[0] ? 0 : (pos < cc[0] + cc[1] ? 1 : 2);
+    first = pos - (cls > 0 ? cc[0] : 0) - (cls > 1 ? cc[1] : 0);
+    stride = cc[cls];
+    const int nWh = p.g.H / kWs, nWw = p.g.nWw;
+    if (p.g.shift == 0) { wcls = nWw; hcls = nWh; }
+    else { wcls = cls == 2 ? 1 : nWw - 1; hcls = cls == 0 ? nWh - 1 : (cls == 1 ? 1 : nWh); }
+    ncls = p.g.B * hcls * wcls;
     const int units = cross ? (ncls + 1) / 2 : ncls;
     npairs = first < units ? (units - first + stride - 1) / stride : 0;
   }
@@ -295,9 +300,8 @@ __device__ __forceinline__ void wattn_tc64_bwd_body(const BwdMaps& maps, const f
       // dO of the two units), lanes 8-13 one plane (lse, r, c) of the forward's statistics of one unit
       // the windows of this CTA: a cursor over its class's grid (cross group: two consecutive windows per pair)
       const int nWh = g.H / kWs;
-      const int wcls = !kMasked ? g.nWw : (kSplit ? 1 : g.nWw - 1);
       WinCursor cur;
-      cur.init(work.cross ? 2 * work.first : work.first, work.cross ? 2 * work.stride : work.stride, wcls, nWh);
+      cur.init(work.cross ? 2 * work.first : work.first, work.cross ? 2 * work.stride : work.stride, work.wcls, work.hcls);
       for (int k = 0; k < npairs; ++k, cur.advance()) {
         const int s = k % kStages, se = k % kStagesE;
         mbar_wait_fast(bar_empty(s), ((k / kStages) & 1) ^ 1);
@@ -315,7 +319,8 @@ __device__ __forceinline__ void wattn_tc64_bwd_body(const BwdMaps& maps, const f
             if (cur.idx + 1 < work.ncls) cur.next(b, wh, ww);
             else valid = false;  // padding unit of an odd tail: a copy of unit 0 whose results are dropped
           }
-          if (kSplit) ww = g.nWw - 1;
+          if (kMode == 1) wh = nWh - 1;   // class 1: the bottom row of windows
+          if (kSplit) ww = g.nWw - 1;     // class 2: the last column
           const int r = (b * nWh + wh) * g.nWw + ww;
           ur[u] = r; ub[u] = b;
           urow0[u] = wh * kWs + g.shift; ucol0[u] = ww * kWs + g.shift;
@@ -811,13 +816,14 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
   if (!kShift) {
     wattn_tc64_bwd_body<0>(maps, stats, bias_table, tau, ws_dbias, ws_dtau, p);
   } else {
-    // class of this CTA (see CtaWork): the last ctas_*1 CTAs of every group take the right-edge windows
+    // window class of this CTA (see CtaWork)
     const int same_total = p.n_same * p.ctas_same;
     const int cta = blockIdx.x;
-    const bool edge = cta < same_total ? (cta % p.ctas_same) >= p.ctas_same - p.ctas_same1
-                                       : (cta - same_total) >= p.ctas_cross - p.ctas_cross1;
-    if (edge) wattn_tc64_bwd_body<2>(maps, stats, bias_table, tau, ws_dbias, ws_dtau, p);
-    else wattn_tc64_bwd_body<1>(maps, stats, bias_table, tau, ws_dbias, ws_dtau, p);
+    const int pos = cta < same_total ? cta % p.ctas_same : cta - same_total;
+    const int* cc = cta < same_total ? p.cls_same : p.cls_cross;
+    if (pos < cc[0]) wattn_tc64_bwd_body<0>(maps, stats, bias_table, tau, ws_dbias, ws_dtau, p);
+    else if (pos < cc[0] + cc[1]) wattn_tc64_bwd_body<1>(maps, stats, bias_table, tau, ws_dbias, ws_dtau, p);
+    else wattn_tc64_bwd_body<2>(maps, stats, bias_table, tau, ws_dbias, ws_dtau, p);
   }
 }
 
@@ -1015,23 +1021,43 @@ int wattn_tc64_bwd(const Geom& g, const void* qkv, const void* dout, const float
   if (p.ctas_same < 1 && p.n_same) p.ctas_same = 1;
   if (p.ctas_same > nrows) p.ctas_same = nrows;
   if (p.ctas_cross > (nrows + 1) / 2) p.ctas_cross = (nrows + 1) / 2;
-  // shifted layer: split every group's CTAs between the two window classes in proportion to their work (a right-edge
-  // window costs kEdgeCost x an interior one: twice the TMA boxes, every row masked; HV_EDGE_COST overrides for tuning)
-  p.ctas_same1 = p.ctas_cross1 = 0;
-  if (g.shift > 0) {
-    const int n1 = nrows / g.nWw, n0 = nrows - n1;
-    static const double kEdgeCost = []() { const char* e = getenv("HV_EDGE_COST"); return e ? atof(e) : 1.2; }();
-    auto split = [&](int& ctas) {
-      if (ctas == 0) return 0;
-      if (n0 == 0) return ctas;
-      if (ctas < 2) ctas = 2;
-      int c1 = (int)((double)ctas * kEdgeCost * n1 / (n0 + kEdgeCost * n1) + 0.5);
-      if (c1 < 1) c1 = 1;
-      if (c1 > ctas - 1) c1 = ctas - 1;
-      return c1;
+  // shifted layer: split every group's CTAs between the window classes in proportion to their work (windows x relative
+  // cost per window: a wrapped window needs twice the TMA boxes and the mask; HV_CLASS_COST="b,e" overrides for tuning)
+  {
+    const int nWh = g.H / kWs;
+    int n[3] = {nrows, 0, 0};
+    if (g.shift > 0) {
+      n[0] = g.B * (nWh - 1) * (g.nWw - 1);
+      n[1] = g.B * (g.nWw - 1);
+      n[2] = g.B * nWh;
+    }
+    static double cost[3] = {1.0, 1.3, 1.4};
+    static const bool cost_env = []() {
+      const char* e = getenv("HV_CLASS_COST");
+      if (e) sscanf(e, "%lf,%lf", &cost[1], &cost[2]);
+      return e != nullptr;
+    }();
+    (void)cost_env;
+    auto split = [&](int& ctas, int* out) {
+      out[0] = out[1] = out[2] = 0;
+      if (ctas == 0) return;
+      int nonempty = 0;
+      double wsum = 0;
+      for (int c = 0; c < 3; ++c) { nonempty += n[c] > 0; wsum += n[c] * cost[c]; }
+      if (ctas < nonempty) ctas = nonempty;
+      int used = 0, big = -1;
+      for (int c = 0; c < 3; ++c) {
+        if (n[c] == 0) continue;
+        out[c] = (int)(ctas * n[c] * cost[c] / wsum + 0.5);
+        if (out[c] < 1) out[c] = 1;
+        used += out[c];
+        if (big < 0 || n[c] * cost[c] > n[big] * cost[big]) big = c;
+      }
+      out[big] += ctas - used;  // rounding goes to the largest class
+      if (out[big] < 1) { ctas += 1 - out[big]; out[big] = 1; }
     };
-    p.ctas_same1 = split(p.ctas_same);
-    p.ctas_cross1 = split(p.ctas_cross);
+    split(p.ctas_same, p.cls_same);
+    split(p.ctas_cross, p.cls_cross);
   }
   const int grid = p.n_same * p.ctas_same + p.ctas_cross;
   float* ws_dbias = static_cast<float*>(workspace);
