@@ -66,6 +66,90 @@ def _dx_with_shortcut(dx_shortcut, d2, weight, shape):
     return _own(torch.addmm(dx_shortcut.reshape(-1, C).to(d2.dtype), d2, weight).view(shape))
 
 
+# ---- low-precision shadows of fp32 master weights -------------------------------------------------------------------
+# Under autocast every Linear casts its fp32 weight to bf16 in the forward and its bf16 weight gradient back to fp32 in
+# the backward: ~126 tiny launches per SwinV2-T step.  Here a weight keeps one persistent bf16 shadow, rewritten only
+# when the parameter's version counter has moved (optimizer step, load_state_dict) -- by ONE multi-tensor copy for all
+# weights (`refresh_weight_shadows`, called at the start of a training step) -- and the weight-gradient GEMMs write
+# fp32 directly (`torch.mm(..., out_dtype=torch.float32)`).
+import weakref
+
+_SHADOWS = {}  # id(parameter) -> [weakref to the parameter, shadow tensor, parameter version it holds]
+# (keyed by id: tensors compare element-wise, which rules out WeakKeyDictionary; the weakref callback drops dead entries)
+
+
+def weight_shadow(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """``w`` in ``dtype``: ``w`` itself, or its persistent shadow (refreshed here if the parameter changed since)."""
+    if w.dtype == dtype:
+        return w
+    key = id(w)
+    ent = _SHADOWS.get(key)
+    if ent is None or ent[0]() is not w or ent[1].dtype != dtype or ent[1].device != w.device or ent[1].shape != w.shape:
+        ent = [weakref.ref(w, lambda _r, k=key: _SHADOWS.pop(k, None)), torch.empty_like(w, dtype=dtype), -1]
+        _SHADOWS[key] = ent
+    if ent[2] != w._version:
+        with torch.no_grad():
+            ent[1].copy_(w)
+        ent[2] = w._version
+    return ent[1]
+
+
+def refresh_weight_shadows(force: bool = False) -> int:
+    """Bring every registered shadow up to date with one multi-tensor copy; ``force`` rewrites all of them (what a
+    captured CUDA graph needs: the copy must be part of the graph whether or not anything is stale at capture time).
+    Returns the number of shadows rewritten."""
+    src, dst, ents = [], [], []
+    for ent in list(_SHADOWS.values()):
+        w = ent[0]()
+        if w is not None and w.is_cuda and (force or ent[2] != w._version):
+            src.append(w.detach())
+            dst.append(ent[1])
+            ents.append((ent, w))
+    if src:
+        with torch.no_grad():
+            torch._foreach_copy_(dst, src)
+        for ent, w in ents:
+            ent[2] = w._version
+    return len(src)
+
+
+def _weight_grad(d2t: torch.Tensor, x2: torch.Tensor, wdtype: torch.dtype) -> torch.Tensor:
+    """d2t (N, tokens) @ x2 (tokens, K) in the master weight's dtype, without a separate cast kernel."""
+    if wdtype == torch.float32 and d2t.dtype == torch.bfloat16 and x2.dtype == torch.bfloat16 and d2t.is_cuda:
+        return torch.mm(d2t, x2, out_dtype=torch.float32)
+    g = torch.matmul(d2t, x2)
+    return g if g.dtype == wdtype else g.to(wdtype)
+
+
+class _ShadowLinear(torch.autograd.Function):
+    """F.linear(x, weight, bias) for an fp32 master weight and low-precision activations: the GEMMs read the weight's
+    persistent shadow, the weight gradient comes out of its GEMM in fp32."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        w = weight_shadow(weight, x.dtype)
+        ctx.save_for_backward(x, w)
+        ctx.wdtype = weight.dtype
+        ctx.bdtype = bias.dtype if bias is not None else None
+        return torch.nn.functional.linear(x, w, None if bias is None else bias.to(x.dtype))
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        d2 = dy.reshape(-1, dy.shape[-1])
+        if d2.dtype != x.dtype:
+            d2 = d2.to(x.dtype)
+        dx = torch.matmul(d2, w).view(x.shape) if ctx.needs_input_grad[0] else None
+        dw = _weight_grad(d2.t(), x.reshape(-1, x.shape[-1]), ctx.wdtype) if ctx.needs_input_grad[1] else None
+        db = d2.sum(dim=0, dtype=torch.float32).to(ctx.bdtype) if (ctx.bdtype is not None and ctx.needs_input_grad[2]) else None
+        return dx, dw, db
+
+
+def shadow_linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``F.linear`` for activations in a lower precision than the (fp32) master ``weight``; see ``weight_shadow``."""
+    return _ShadowLinear.apply(x, weight, bias)
+
+
 # Optional per-launch instrumentation used by bench.py: when set to a list, every attention
 # kernel launch appends (tag, start_event, end_event, windows).
 PROFILE_EVENTS = None
@@ -212,6 +296,8 @@ class _QkvWindowAttention(torch.autograd.Function):
         if q_bias is not None:
             bias = torch.zeros((3 * C,), dtype=x.dtype, device=x.device)
             bias[:C] = q_bias
+        wdtype = weight.dtype
+        weight = weight_shadow(weight, x.dtype)  # fp32 master weight under autocast: its persistent bf16 shadow
         qkv = torch.nn.functional.linear(x, weight, bias)
         bias_table = _f32c(bias_table)
         tau = _f32c(tau)
@@ -223,6 +309,7 @@ class _QkvWindowAttention(torch.autograd.Function):
         ctx.save_for_backward(x, weight, qkv, out, lse, bias_table, tau)
         ctx.geom = (B, H, W, C, heads, ws, shift)
         ctx.q_bias_dtype = q_bias.dtype if q_bias is not None else None
+        ctx.wdtype = wdtype
         # second output: x itself, for the residual shortcut.  Its gradient comes back into this node, where it is
         # the accumulator (beta = 1) of the dx GEMM instead of a separate elementwise add kernel.
         return out, x.view_as(x)
@@ -259,7 +346,7 @@ class _QkvWindowAttention(torch.autograd.Function):
             dx = _dx_with_shortcut(dx_shortcut, d2, weight, x.shape)
         elif dx_shortcut is not None:
             dx = dx_shortcut
-        dw = torch.matmul(d2.t(), x.view(-1, C)) if ctx.needs_input_grad[1] else None
+        dw = _weight_grad(d2.t(), x.view(-1, C), ctx.wdtype) if ctx.needs_input_grad[1] else None
         dqb = dq_colsum.to(ctx.q_bias_dtype) if dq_colsum is not None and ctx.needs_input_grad[2] else None
         return dx, dw, dqb, dbias, dtau, None, None, None, None, None, None, None
 
@@ -280,6 +367,8 @@ class _LinearShortcut(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight):
+        ctx.wdtype = weight.dtype
+        weight = weight_shadow(weight, x.dtype)
         ctx.save_for_backward(x, weight)
         return torch.nn.functional.linear(x, weight), x.view_as(x)
 
@@ -292,7 +381,7 @@ class _LinearShortcut(torch.autograd.Function):
             dx = _dx_with_shortcut(dx_shortcut, d2, weight, x.shape)
         elif dx_shortcut is not None:
             dx = dx_shortcut
-        dw = torch.matmul(d2.t(), x.reshape(-1, x.shape[-1])) if ctx.needs_input_grad[1] else None
+        dw = _weight_grad(d2.t(), x.reshape(-1, x.shape[-1]), ctx.wdtype) if ctx.needs_input_grad[1] else None
         return dx, dw
 
 

@@ -49,6 +49,15 @@ def set_amp_residual_dtype(dtype: Optional[torch.dtype]) -> None:
     AMP_RESIDUAL_DTYPE = dtype
 
 
+def _linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """F.linear; under CUDA autocast with an fp32 master weight the GEMMs read the weight's persistent low-precision
+    shadow and write the weight gradient in fp32 (functional.shadow_linear) instead of casting per call."""
+    if x.is_cuda and torch.is_autocast_enabled("cuda") and weight.dtype == torch.float32 and weight.is_cuda:
+        dt = torch.get_autocast_dtype("cuda")
+        return hvf.shadow_linear(x if x.dtype == dt else x.to(dt), weight, bias)
+    return F.linear(x, weight, bias)
+
+
 def _stream_dtype(y: torch.Tensor) -> Optional[torch.dtype]:
     """Output dtype of a LayerNorm that starts (a stage of) the residual stream."""
     if y.is_cuda and torch.is_autocast_enabled("cuda") and AMP_RESIDUAL_DTYPE is not None:
@@ -100,7 +109,7 @@ class MultitaskHead(nn.Module):
         self.heads = nn.ModuleList(nn.Linear(num_features, n) for n in self.num_classes)
 
     def forward(self, x):
-        return [head(x) for head in self.heads]
+        return [_linear(x, head.weight, head.bias) for head in self.heads]
 
 
 class Mlp(nn.Module):
@@ -120,11 +129,11 @@ class Mlp(nn.Module):
         sc = x
         if type(self.act) is nn.GELU and getattr(self.act, "approximate", "none") == "none" and self.fc1.bias is not None:
             if with_shortcut and x.is_cuda and torch.is_autocast_enabled("cuda") and x.dtype == torch.get_autocast_dtype("cuda"):
-                h, sc = hvf.linear_shortcut(x, self.fc1.weight.to(x.dtype))
+                h, sc = hvf.linear_shortcut(x, self.fc1.weight)  # the node reads the weight's bf16 shadow
             elif with_shortcut and x.is_cuda and not torch.is_autocast_enabled("cuda") and x.dtype == self.fc1.weight.dtype:
                 h, sc = hvf.linear_shortcut(x, self.fc1.weight)
             else:
-                h = F.linear(x, self.fc1.weight)
+                h = _linear(x, self.fc1.weight)
             if hvf.bias_gelu_supported(h):
                 a = hvf.bias_gelu(h, self.fc1.bias)
             else:
@@ -267,7 +276,7 @@ class WindowAttention(nn.Module):
         if mask is None and x_tokens.is_cuda and hvf.window_attention_kind(self.dim, self.num_heads, ws, dt) == 1:
             # tensor-core kernel: qkv Linear + attention are one autograd node (q_bias gradient from the kernel);
             # v_bias leaves the attention as a plain additive term because softmax rows sum to one
-            o, sc = hvf.qkv_window_attention(x_tokens.to(dt), self.qkv.weight.to(dt), self.q_bias, table, tau, B=B, H=H,
+            o, sc = hvf.qkv_window_attention(x_tokens.to(dt), self.qkv.weight, self.q_bias, table, tau, B=B, H=H,
                                              W=W, C=self.dim, heads=self.num_heads, ws=ws, shift=shift)
             if sc.dtype == x_tokens.dtype:
                 shortcut = sc  # same values as x_tokens; its gradient is accumulated inside the node's dx GEMM
@@ -278,13 +287,13 @@ class WindowAttention(nn.Module):
         if with_proj_bias:
             if v_bias is not None:
                 o = o + v_bias.to(o.dtype)
-            return self.proj_drop(self.proj(o)), None, shortcut
+            return self.proj_drop(_linear(o, self.proj.weight, self.proj.bias)), None, shortcut
         # the caller folds the bias into its LayerNorm kernel: proj(o + v_bias) = o W^T + (W v_bias + proj.bias)
         bias = self.proj.bias
         if v_bias is not None:
             with torch.autocast(device_type="cuda", enabled=False):
                 bias = bias + F.linear(v_bias.float(), self.proj.weight.float())
-        return F.linear(o, self.proj.weight), bias, shortcut
+        return _linear(o, self.proj.weight), bias, shortcut
 
     def forward(self, x, mask=None):
         """x: (num_windows*B, N, C); mask: (num_windows, N, N) of 0/-100 or None (swinv2.py:204-264)."""
@@ -360,7 +369,7 @@ class SwinTransformerBlock(nn.Module):
         x = self._post_norm(self.norm1, y, x, proj_bias)                                       # swinv2.py:431
         if fold2:
             a, x = self.mlp._hidden(x, with_shortcut=True)
-            m = F.linear(a, self.mlp.fc2.weight)
+            m = _linear(a, self.mlp.fc2.weight)
             return self._post_norm(self.norm2, m, x, self.mlp.fc2.bias)                         # swinv2.py:434
         return self._post_norm(self.norm2, self.mlp(x), x)
 
@@ -390,7 +399,7 @@ class PatchMerging(nn.Module):
         B, L, C = x.shape
         assert L == H * W, "input feature has wrong size"
         assert H % 2 == 0 and W % 2 == 0, f"x size ({H}*{W}) are not even."
-        x = self.reduction(hvf.patch_merge_gather(x, H, W))
+        x = _linear(hvf.patch_merge_gather(x, H, W), self.reduction.weight)
         if SwinTransformerBlock._fusable(self.norm):
             return hvf.ln_residual(x, None, self.norm.weight, self.norm.bias, None, self.norm.eps, out_dtype=_stream_dtype(x))
         return self.norm(x)
@@ -445,6 +454,25 @@ class BasicLayer(nn.Module):
                 nn.init.constant_(n.weight, 0)
 
 
+class _PatchProj(torch.autograd.Function):
+    """rows @ W^T (+ bias) of the patch embedding for an fp32 conv weight whose bf16 shadow ``w2d`` (E, 48) does the
+    GEMM; the weight gradient is written in fp32 in the conv weight's (E, 3, 4, 4) shape."""
+
+    @staticmethod
+    def forward(ctx, rows, weight, w2d, bias):
+        ctx.save_for_backward(rows)
+        ctx.wshape, ctx.bdtype = weight.shape, (bias.dtype if bias is not None else None)
+        return F.linear(rows, w2d, None if bias is None else bias.to(rows.dtype))
+
+    @staticmethod
+    def backward(ctx, dy):
+        (rows,) = ctx.saved_tensors
+        d2 = dy.reshape(-1, dy.shape[-1]).to(rows.dtype)
+        dw = hvf._weight_grad(d2.t(), rows, torch.float32).view(ctx.wshape) if ctx.needs_input_grad[1] else None
+        db = d2.sum(dim=0, dtype=torch.float32).to(ctx.bdtype) if (ctx.bdtype is not None and ctx.needs_input_grad[3]) else None
+        return None, dw, None, db
+
+
 class PatchEmbed(nn.Module):
     """Conv2d(k=s=patch) patch embedding + optional norm (swinv2.py:611-670)."""
 
@@ -489,8 +517,12 @@ class PatchEmbed(nn.Module):
                 dt = torch.float32
             rows = hvf.patch_rows(x, scale, shift, dt)
             fold = self.norm is not None and SwinTransformerBlock._fusable(self.norm)
-            w = self.proj.weight.view(self.embed_dim, -1)
-            x = F.linear(rows, w.to(dt), None if (fold or self.proj.bias is None) else self.proj.bias.to(dt))
+            pbias = None if (fold or self.proj.bias is None) else self.proj.bias
+            if self.proj.weight.dtype == torch.float32 and dt != torch.float32:
+                w = hvf.weight_shadow(self.proj.weight, dt).view(self.embed_dim, -1)  # images carry no gradient: no dx
+                x = _PatchProj.apply(rows, self.proj.weight, w, pbias)
+            else:
+                x = F.linear(rows, self.proj.weight.view(self.embed_dim, -1).to(dt), None if pbias is None else pbias.to(dt))
             x = x.view(B, -1, self.embed_dim)
             bias = self.proj.bias if fold else None
         if self.norm is not None:
@@ -605,7 +637,10 @@ class SwinTransformerV2(nn.Module):
         return (x, activations) if output_activations else x
 
     def forward(self, x):
-        return self.head(self.forward_features(x))
+        x = self.forward_features(x)
+        if type(self.head) is nn.Linear:
+            return _linear(x, self.head.weight, self.head.bias)
+        return self.head(x)
 
     def flops(self):
         total = self.patch_embed.flops() + sum(layer.flops() for layer in self.layers)

@@ -266,6 +266,9 @@ def train_step(model: nn.Module, optimizer: torch.optim.Optimizer, batch, *, aut
     inner = model.module if hasattr(model, "module") and isinstance(model.module, Model) else model
     optimizer.zero_grad(set_to_none=True)
     device_type = batch[0].device.type
+    if device_type == "cuda":
+        from . import functional as hvf
+        hvf.refresh_weight_shadows()  # the optimizer moved the master weights: one multi-tensor copy for all shadows
     with torch.autocast(device_type, dtype=autocast_dtype, enabled=autocast_dtype is not None):
         outputs = model(batch)
         loss = inner.loss(outputs, batch)
@@ -277,22 +280,30 @@ def train_step(model: nn.Module, optimizer: torch.optim.Optimizer, batch, *, aut
 
 
 class BucketedGradSync:
-    """Gradient all-reduce(avg) of a flat gradient buffer in a few contiguous buckets, each started as soon as its last
-    gradient has been accumulated -- late layers first, overlapping with the rest of the backward pass (the NCCL
-    stream runs beside the compute stream; inside a CUDA graph this becomes a fork / join of the captured graph).
-    This is what DistributedDataParallel's bucket hooks do (reference main.py trains through Composer's DDP), without
-    the per-step host work: the hooks only run while the graph is being captured.
+    """Collects the gradients of a backward pass into a flat buffer, bucket by bucket, and (world size > 1) all-reduces
+    each bucket as soon as its last gradient exists -- late layers first, overlapping with the rest of the backward
+    pass (the NCCL stream runs beside the compute stream; inside a CUDA graph this becomes a fork / join of the
+    captured graph).  This is what DistributedDataParallel's bucket hooks do (reference main.py trains through
+    Composer's DDP), without the per-step host work: the hooks only run while the graph is being captured.
 
-    ``params``: parameters in flat-buffer order, every ``p.grad`` a view into ``flat``.  ``bounds``: bucket
-    boundaries as parameter indices (ascending, first 0, last len(params))."""
+    Gradients are not accumulated into the flat buffer parameter by parameter (autograd would launch one `grad += g`
+    kernel per parameter and the buffer would have to be zeroed first): every ``p.grad`` starts the backward pass as
+    ``None``, autograd hands the freshly computed gradient over without a kernel, and a finished bucket is moved into
+    its slice of the flat buffer by one multi-tensor copy, after which ``p.grad`` is the view into the buffer.
 
-    def __init__(self, params: Sequence[torch.nn.Parameter], flat: torch.Tensor, bounds: Sequence[int]):
+    ``params``: parameters in flat-buffer order.  ``bounds``: bucket boundaries as parameter indices (ascending, first 0,
+    last len(params)).  ``reduce``: all-reduce(avg) the buckets over the default process group."""
+
+    def __init__(self, params: Sequence[torch.nn.Parameter], flat: torch.Tensor, bounds: Sequence[int], reduce: bool = True):
         self.flat = flat
+        self.params = list(params)
         self.bounds = list(bounds)
         self.nb = len(self.bounds) - 1
+        self.reduce = reduce
         offs = [0]
-        for p in params:
+        for p in self.params:
             offs.append(offs[-1] + p.numel())
+        self.pviews = [flat[offs[i]:offs[i + 1]].view_as(p) for i, p in enumerate(self.params)]
         self.views = [flat[offs[self.bounds[b]]:offs[self.bounds[b + 1]]] for b in range(self.nb)]
         self.sizes = [self.bounds[b + 1] - self.bounds[b] for b in range(self.nb)]
         self._count = [0] * self.nb
@@ -300,9 +311,9 @@ class BucketedGradSync:
         self._started = [False] * self.nb
         self.enabled = True
         # NCCL averages inside the collective; gloo (CPU tests of this logic) only sums
-        self._avg = dist.is_initialized() and dist.get_backend() == "nccl"
+        self._avg = reduce and dist.is_initialized() and dist.get_backend() == "nccl"
         for b in range(self.nb):
-            for p in params[self.bounds[b]:self.bounds[b + 1]]:
+            for p in self.params[self.bounds[b]:self.bounds[b + 1]]:
                 p.register_post_accumulate_grad_hook(self._make_hook(b))
 
     @staticmethod
@@ -332,27 +343,43 @@ class BucketedGradSync:
                 self._start(b)
         return hook
 
+    @torch.no_grad()
     def _start(self, b: int) -> None:
         self._started[b] = True
-        op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
-        self._works.append(dist.all_reduce(self.views[b], op=op, async_op=True))
+        src, dst = [], []
+        for i in range(self.bounds[b], self.bounds[b + 1]):
+            p, v = self.params[i], self.pviews[i]
+            g = p.grad
+            if g is None:
+                v.zero_()  # unused parameter: its slice must not keep the previous step's gradient
+            elif g.data_ptr() != v.data_ptr():
+                src.append(g)
+                dst.append(v)
+            p.grad = v
+        if src:
+            torch._foreach_copy_(dst, src)
+        if self.reduce:
+            op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
+            self._works.append(dist.all_reduce(self.views[b], op=op, async_op=True))
 
     def begin(self) -> None:
         """Call before backward."""
         self._count = [0] * self.nb
         self._started = [False] * self.nb
         self._works = []
+        for p in self.params:
+            p.grad = None
 
     def finish(self) -> None:
-        """Call after backward: reduce buckets whose hooks did not all fire (unused parameters), then make the
-        current stream wait for every bucket."""
+        """Call after backward: collect (and reduce) buckets whose hooks did not all fire (unused parameters), then make
+        the current stream wait for every bucket."""
         for b in range(self.nb):
             if not self._started[b]:
                 self._start(b)
         for w in self._works:
             w.wait()
         self._works = []
-        if not self._avg:
+        if self.reduce and not self._avg:
             self.flat.div_(dist.get_world_size())
 
 
@@ -391,9 +418,10 @@ class GraphedTrainStep:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
         self.params = params
-        self.sync = None
-        if env.world_size > 1 and overlap_allreduce:
-            self.sync = BucketedGradSync(params, self.flat, BucketedGradSync.stage_bounds(named, min_bucket_numel))
+        # gradient collection (and, with world size > 1, the overlapped all-reduce) per stage bucket
+        self.sync = BucketedGradSync(params, self.flat, BucketedGradSync.stage_bounds(named, min_bucket_numel),
+                                     reduce=env.world_size > 1 and overlap_allreduce)
+        self._trailing_allreduce = env.world_size > 1 and not overlap_allreduce
         self.launches_per_step = 0
         self.graph = None
         self.static_loss = None
@@ -458,18 +486,17 @@ class GraphedTrainStep:
         return self
 
     def _body(self) -> torch.Tensor:
-        self.flat.zero_()
+        from . import functional as hvf
+        hvf.refresh_weight_shadows(force=True)  # bf16 shadows of the fp32 master weights: one multi-tensor copy per step
         x = self.transform(self.static_img) if self.transform is not None else self.static_img
         batch = (x, self.static_lab)
         with torch.autocast("cuda", dtype=self.autocast_dtype, enabled=self.autocast_dtype is not None):
             outputs = self.model(batch)
             loss = self.model.loss(outputs, batch)
-        if self.sync is not None:
-            self.sync.begin()
+        self.sync.begin()
         loss.backward()
-        if self.sync is not None:
-            self.sync.finish()
-        elif self.env.world_size > 1:
+        self.sync.finish()
+        if self._trailing_allreduce:
             dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)
         if self.clip_norm is not None:
             # torch.nn.utils.clip_grad_norm_ on the flat view: one norm, one scale

@@ -795,7 +795,7 @@ def _ddp_graph_worker(rank, world, port, q):
     gs(img[lo:hi].to(dev), lab[lo:hi].to(dev))  # captured graph, bucketed all-reduce inside
     torch.cuda.synchronize(dev)
     out["graph"] = gs.flat.detach().cpu().numpy().copy()
-    out["buckets"] = gs.sync.nb if gs.sync is not None else 0
+    out["buckets"] = gs.sync.nb
     q.put((rank, out))
     q.close()
     q.join_thread()  # the result has left this process
