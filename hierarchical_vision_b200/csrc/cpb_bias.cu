@@ -44,7 +44,15 @@ __global__ void __launch_bounds__(32 * kChunks) cpb_bwd_hidden_kernel(const floa
                                                                        const float* __restrict__ dz, float* __restrict__ dw1,
                                                                        float* __restrict__ db1, float* __restrict__ dw2, int M,
                                                                        int hid, int heads) {
-  __shared__ float part[kChunks][kHeadsMax + 3][32];
+  // one buffer, two lives: first the staged dz rows (every thread reads all of them: from global that was a serial chain
+  // of ~700 dependent L2 loads per thread, 21 us for this tiny kernel), then the partial sums of the row chunks
+  __shared__ float buf[kChunks * (kHeadsMax + 3) * 32];
+  float (*part)[kHeadsMax + 3][32] = reinterpret_cast<float (*)[kHeadsMax + 3][32]>(buf);
+  const bool staged = M * heads <= kChunks * (kHeadsMax + 3) * 32;
+  if (staged)
+    for (int i = threadIdx.x; i < M * heads; i += 32 * kChunks) buf[i] = __ldg(&dz[i]);
+  __syncthreads();
+  const float* dzs = staged ? buf : dz;
   const int jl = threadIdx.x & 31, rc = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + jl;
   const bool live = j < hid;
@@ -64,7 +72,7 @@ __global__ void __launch_bounds__(32 * kChunks) cpb_bwd_hidden_kernel(const floa
 #pragma unroll
     for (int h = 0; h < kHeadsMax; ++h) {
       if (h < heads) {
-        const float d = __ldg(&dz[r * heads + h]);  // same address for every lane of the warp: broadcast
+        const float d = dzs[r * heads + h];  // same address for every lane of the warp: broadcast
         g2[h] = fmaf(d, a, g2[h]);
         da = fmaf(d, w2j[h], da);
       }
@@ -75,6 +83,7 @@ __global__ void __launch_bounds__(32 * kChunks) cpb_bwd_hidden_kernel(const floa
       gbias += da;
     }
   }
+  __syncthreads();  // everybody is done with the staged dz
 #pragma unroll
   for (int h = 0; h < kHeadsMax; ++h) part[rc][h][jl] = g2[h];
   part[rc][kHeadsMax][jl] = ga;
