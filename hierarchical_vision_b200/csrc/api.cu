@@ -15,6 +15,10 @@ int wattn_generic_bwd(const Geom& g, int dtype, const void* qkv, const void* out
 bool wattn_mma64_supported(const Geom& g, int dtype);
 bool wattn_tc64_supported(const Geom& g, int dtype);
 int wattn_fwd_variant_set(int v);
+int wattn_fwd_variant_get();
+bool wattn_tc64_fwd2_supported(const Geom& g, int dtype);
+int wattn_tc64_fwd2(const Geom& g, const void* qkv, const float* bias_table, const float* tau, void* out, float* stats,
+                    cudaStream_t st);
 int wattn_tc64_fwd(const Geom& g, const void* qkv, const float* bias_table, const float* tau, void* out, float* lse,
                    cudaStream_t st);
 size_t wattn_mma64_bwd_workspace_bytes(const Geom& g);
@@ -124,7 +128,7 @@ const char* hv_last_error(void) { return g_err; }
 int hv_compiled_arch(void) { return 100; }
 
 int hv_window_attn_fwd_variant(int variant) {
-  if (variant < -1 || variant > 1) HV_FAIL(HV_ERR_SHAPE, "hv_window_attn_fwd_variant: variant %d", variant);
+  if (variant < -1 || variant > 2) HV_FAIL(HV_ERR_SHAPE, "hv_window_attn_fwd_variant: variant %d", variant);
   wattn_fwd_variant_set(variant);
   return HV_OK;
 }
@@ -157,6 +161,8 @@ int hv_window_attn_kernel_name(int B, int H, int W, int C, int heads, int ws, in
   // the same decisions as hv_window_attn_fwd / _bwd (mask == NULL)
   if (!wattn_mma64_supported(g, dtype))
     snprintf(out, out_len, "wattn_generic_%s_kernel<%s>", backward ? "bwd" : "fwd", dtype == HV_BF16 ? "bf16" : "float");
+  else if (!backward && wattn_tc64_supported(g, dtype) && wattn_fwd_variant_get() != 2 && wattn_tc64_fwd2_supported(g, dtype))
+    snprintf(out, out_len, "wattn_tc64_fwd2_kernel<%s>", shift > 0 ? "true" : "false");
   else if (!backward && wattn_tc64_supported(g, dtype))
     snprintf(out, out_len, "wattn_tc64_fwd_kernel");
   else if (backward && wattn_tc64_bwd_supported(g, dtype))
@@ -235,7 +241,11 @@ int hv_window_attn_fwd(const void* qkv, const float* bias_table, const float* ta
   // tensor-core kernels (bf16, 8x8 window, head dim 32, in-kernel shift mask): tcgen05/TMEM/TMA forward when the
   // shift is even, otherwise the mma.sync one; both write lse in log2 units for wattn_mma64_bwd
   if (mask == nullptr && wattn_mma64_supported(g, dtype)) {
-    if (wattn_tc64_supported(g, dtype)) return wattn_tc64_fwd(g, qkv, bias_table, tau, out, lse, st);
+    if (wattn_tc64_supported(g, dtype)) {
+      if (wattn_fwd_variant_get() != 2 && wattn_tc64_fwd2_supported(g, dtype))
+        return wattn_tc64_fwd2(g, qkv, bias_table, tau, out, lse, st);
+      return wattn_tc64_fwd(g, qkv, bias_table, tau, out, lse, st);  // first-generation kernel: any even shift
+    }
     return wattn_mma64_fwd(g, qkv, bias_table, tau, mask, mask_windows, out, lse, st);
   }
   return wattn_generic_fwd(g, dtype, qkv, bias_table, tau, mask, mask_windows, out, lse, st);

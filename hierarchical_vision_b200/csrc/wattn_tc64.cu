@@ -563,12 +563,13 @@ int wattn_fwd_variant_set(int v) {
   g_fwd_variant = v;
   return old;
 }
+int wattn_fwd_variant_get() { return g_fwd_variant; }
 
 bool wattn_tc64_supported(const Geom& g, int dtype) {
   // HV_ATTN_TCGEN05: unset or 1 = wherever valid (automatic), 0 = never (mma.sync forward)
   static const int env = []() { const char* e = getenv("HV_ATTN_TCGEN05"); return e == nullptr ? -1 : (atoi(e) != 0 ? 1 : 0); }();
   const int mode = g_fwd_variant < 0 ? env : g_fwd_variant;
-  if (mode == 0) return false;
+  if (mode == 0) return false;  // 1: second-generation kernel where valid, else this one; 2: always this one
   // an odd shift would put the second half of a column-wrapped row at a 64-byte (not 128-byte) shared-memory offset
   const bool valid = dtype == HV_BF16 && g.ws == kWs && g.d == 32 && g.C % 32 == 0 && (g.shift & 1) == 0 &&
                      (int64_t)g.B * g.H * g.W < (int64_t(1) << 31) && g.W * 3 * g.C * 2 % 16 == 0;

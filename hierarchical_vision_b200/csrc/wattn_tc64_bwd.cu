@@ -30,7 +30,7 @@
 //     15 x 15 table per head, 10 KB);
 //   * 28 warps: 0 TMA loads | 1 issuer of S, dP | 2 issuer of dV, dK^, dQ^, dBias | 3 TMA stores |
 //     4-19 softmax / dS (2 groups) | 20-23 dV, dK epilogue | 24-27 dQ epilogue.  All hand-overs are mbarriers.
-#include "hv_tc.cuh"
+#include "hv_tc_win.cuh"
 
 namespace hv {
 namespace {
@@ -84,107 +84,11 @@ constexpr int kColDB = 448;
 
 struct BwdParams {
   Geom g;
-  // head-pair groups (both units = heads 2g, 2g+1 of one window) and the cross group (odd last head of two windows); the
-  // ctas_same / ctas_cross CTAs of a group are split between the window classes of a shifted layer (cls_same / cls_cross
-  // CTAs per class, in class order; an unshifted layer has class 0 only)
-  int n_same, has_cross, ctas_same, ctas_cross, cls_same[3], cls_cross[3];
-  int64_t plane;  // floats per plane of the forward's statistics: B * nW * heads * 64
-  int ko;         // HV_TC_TRACE builds only: knock-out bits (results are wrong) | traced CTA << 8
+  WinSchedule sched;  // CTAs per head group and window class (hv_tc_win.cuh)
+  int64_t plane;      // floats per plane of the forward's statistics: B * nW * heads * 64
+  int ko;             // HV_TC_TRACE builds only: knock-out bits (results are wrong) | traced CTA << 8
 };
-// per tensor, box (w, h): [0] full (8, 8) | column-split order: [1] (wa, 8) [2] (s, 8) [3] (wa, wa) [4] (wa, s) [5] (s, wa)
-// [6] (s, s) | row wrap in slot order: [7] (8, wa) [8] (8, s)
-constexpr int kNumMaps = 9;
-struct BwdMaps { CUtensorMap m[3][kNumMaps]; };  // qkv, dout, dqkv
-
-// Window classes of a shifted layer: 0 = interior windows (no wrap, no mask: exactly the unshifted code path), 1 = bottom
-// row of windows left of the last column (rows wrap: slot order, two row boxes, mask along h), 2 = right-edge windows
-// (columns wrap: two column parts, permuted token order, mask along w and, in the corner, h).  A CTA serves one class,
-// so that its tile order -- and with it bias lookup, mask and the d(bias) accumulator -- is uniform, and 49 of 64
-// windows of a stage-0 layer run the cheap class-0 code.
-struct CtaWork {
-  int head_a, head_b, cross, cls, first, stride, npairs, ncls, wcls, hcls;
-  __device__ __forceinline__ void init(const BwdParams& p, int cta) {
-    const int same_total = p.n_same * p.ctas_same;
-    int pos;
-    const int* cc;
-    if (cta < same_total) {
-      const int grp = cta / p.ctas_same;
-      cross = 0; head_a = 2 * grp; head_b = 2 * grp + 1;
-      pos = cta - grp * p.ctas_same; cc = p.cls_same;
-    } else {
-      cross = 1; head_a = head_b = p.g.heads - 1;
-      pos = cta - same_total; cc = p.cls_cross;
-    }
-    cls = pos < cc[0] ? 0 : (pos < cc[0] + cc[1] ? 1 : 2);
-    first = pos - (cls > 0 ? cc[0] : 0) - (cls > 1 ? cc[1] : 0);
-    stride = cc[cls];
-    const int nWh = p.g.H / kWs, nWw = p.g.nWw;
-    if (p.g.shift == 0) { wcls = nWw; hcls = nWh; }
-    else { wcls = cls == 2 ? 1 : nWw - 1; hcls = cls == 0 ? nWh - 1 : (cls == 1 ? 1 : nWh); }
-    ncls = p.g.B * hcls * wcls;
-    const int units = cross ? (ncls + 1) / 2 : ncls;
-    npairs = first < units ? (units - first + stride - 1) / stride : 0;
-  }
-};
-
-struct UnitGeo { int b, row0, col0, rflags; };  // rflags = window row << 3 | right << 2 | bottom << 1 | valid
-
-// window slot (ih, iw) of tile row t: slot order, or the two-column-part order of a shifted layer
-__device__ __forceinline__ int tile_row_slot(int t, int shift) {
-  if (shift == 0) return t;
-  const int wa = kWs - shift;
-  int ih, iw;
-  if (t < kWs * wa) { ih = t / wa; iw = t - ih * wa; }
-  else { const int t2 = t - kWs * wa; ih = t2 / shift; iw = wa + t2 - ih * shift; }
-  return ih << 3 | iw;
-}
-
-// The TMA boxes of one tile: f(byte offset inside the tile, map index, image column, image row).  The same list drives
-// the loads of q / k / v / dO and the stores of dq / dk / dv.
-template <int kMode, typename F>
-__device__ __forceinline__ void for_each_box(const Geom& g, int col0, int row0, bool bottom, F&& f) {
-  const int sh = g.shift, wa = kWs - g.shift;
-  if (kMode == 0) {
-    f(0, 0, col0, row0);
-  } else if (kMode == 1) {  // slot order; the rows of a bottom window wrap
-    if (!bottom) {
-      f(0, 0, col0, row0);
-    } else {
-      f(0, 7, col0, row0);
-      f(wa * kWs * 64, 8, col0, 0);
-    }
-  } else {                  // two column parts [0, wa) | [wa, 8); both wrap along the rows in a bottom window
-    int colb = col0 + wa;
-    if (colb >= g.W) colb -= g.W;
-    const int offb = kWs * wa * 64;
-    if (!bottom) {
-      f(0, 1, col0, row0);
-      f(offb, 2, colb, row0);
-    } else {
-      f(0, 3, col0, row0);
-      f(wa * wa * 64, 4, col0, 0);
-      f(offb, 5, colb, row0);
-      f(offb + sh * wa * 64, 6, colb, 0);
-    }
-  }
-}
-
-// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 |
-// version 1 << 46 | layout type << 61 (2: SWIZZLE_128B, 4: SWIZZLE_64B)
-__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t type) {
-  return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
-         ((uint64_t)1 << 46) | ((uint64_t)type << 61);
-}
-
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
-  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+struct BwdMaps { CUtensorMap m[3][kNumWinMaps]; };  // qkv, dout, dqkv
 
 #ifdef HV_TC_TRACE
 __device__ long long* g_btrace = nullptr;  // [pairs][16 events] clock64 stamps of CTA 0
@@ -194,9 +98,6 @@ __device__ long long* g_btrace = nullptr;  // [pairs][16 events] clock64 stamps 
 #define TRACE(k, ev) do { } while (0)
 #define KO(bit) false
 #endif
-
-template <bool V> struct BoolTag { static constexpr bool value = V; };
-template <int V> struct IntTag { static constexpr int value = V; };
 
 // kMode 0: unshifted layer | 1: shifted layer, windows without column wrap (slot order) | 2: shifted layer, right-edge
 // windows (column-split order)
@@ -230,7 +131,7 @@ __device__ __forceinline__ void wattn_tc64_bwd_body(const BwdMaps& maps, const f
   __shared__ CtaWork s_work;
   if (threadIdx.x == 0) {
     CtaWork w0;
-    w0.init(p, blockIdx.x);
+    w0.init(p.g, p.sched, blockIdx.x);
     s_work = w0;
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_full(s), 1);
@@ -271,7 +172,7 @@ __device__ __forceinline__ void wattn_tc64_bwd_body(const BwdMaps& maps, const f
   for (int idx = threadIdx.x; idx < 2 * 32 + 4; idx += kThreads) reinterpret_cast<float*>(smem + kOffCol)[idx] = 0.f;
   {
     CtaWork w0;
-    w0.init(p, blockIdx.x);
+    w0.init(p.g, p.sched, blockIdx.x);
     float* bt = reinterpret_cast<float*>(smem + kOffBias);
     for (int idx = threadIdx.x; idx < 2 * 4 * kBiasCopy; idx += kThreads) {
       const int u = idx / (4 * kBiasCopy), rem = idx - u * 4 * kBiasCopy;
@@ -816,13 +717,9 @@ wattn_tc64_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restr
   if (!kShift) {
     wattn_tc64_bwd_body<0>(maps, stats, bias_table, tau, ws_dbias, ws_dtau, p);
   } else {
-    // window class of this CTA (see CtaWork)
-    const int same_total = p.n_same * p.ctas_same;
-    const int cta = blockIdx.x;
-    const int pos = cta < same_total ? cta % p.ctas_same : cta - same_total;
-    const int* cc = cta < same_total ? p.cls_same : p.cls_cross;
-    if (pos < cc[0]) wattn_tc64_bwd_body<0>(maps, stats, bias_table, tau, ws_dbias, ws_dtau, p);
-    else if (pos < cc[0] + cc[1]) wattn_tc64_bwd_body<1>(maps, stats, bias_table, tau, ws_dbias, ws_dtau, p);
+    const int cls = cta_window_class(p.sched, blockIdx.x);  // a CTA serves one window class (hv_tc_win.cuh)
+    if (cls == 0) wattn_tc64_bwd_body<0>(maps, stats, bias_table, tau, ws_dbias, ws_dtau, p);
+    else if (cls == 1) wattn_tc64_bwd_body<1>(maps, stats, bias_table, tau, ws_dbias, ws_dtau, p);
     else wattn_tc64_bwd_body<2>(maps, stats, bias_table, tau, ws_dbias, ws_dtau, p);
   }
 }
@@ -901,10 +798,10 @@ __global__ void __launch_bounds__(256) wattn_tc64_bwd_reduce_kernel(const float*
   const int head = idx / per_head, e = idx - head * per_head;
   const bool is_tau = e == kTab;
   int c0, c1, u0, u1;
-  if (head < 2 * p.n_same) {
-    c0 = (head >> 1) * p.ctas_same; c1 = c0 + p.ctas_same; u0 = u1 = head & 1;
+  if (head < 2 * p.sched.n_same) {
+    c0 = (head >> 1) * p.sched.ctas_same; c1 = c0 + p.sched.ctas_same; u0 = u1 = head & 1;
   } else {
-    c0 = p.n_same * p.ctas_same; c1 = c0 + p.ctas_cross; u0 = 0; u1 = 1;
+    c0 = p.sched.n_same * p.sched.ctas_same; c1 = c0 + p.sched.ctas_cross; u0 = 0; u1 = 1;
   }
   float s = 0.f;
   for (int c = c0 + lane; c < c1; c += 32)
@@ -980,16 +877,12 @@ int wattn_tc64_bwd(const Geom& g, const void* qkv, const void* dout, const float
   }
   if (!mp) {
     MapEntry& e = cache[cache_next];
-    const int s = g.shift, wa = kWs - g.shift;
-    const int bw[kNumMaps] = {kWs, s ? wa : kWs, s ? s : kWs, s ? wa : kWs, s ? wa : kWs, s ? s : kWs, s ? s : kWs, kWs, kWs};
-    const int bh[kNumMaps] = {kWs, kWs, kWs, s ? wa : kWs, s ? s : kWs, s ? wa : kWs, s ? s : kWs, s ? wa : kWs, s ? s : kWs};
     const void* base[3] = {qkv, dout, dqkv};
     const int row_elems[3] = {3 * g.C, g.C, 3 * g.C};
-    for (int t = 0; t < 3; ++t)
-      for (int i = 0; i < kNumMaps; ++i) {
-        const int rc = make_map(&e.maps.m[t][i], base[t], g, row_elems[t], bw[i], bh[i]);
-        if (rc) return rc;
-      }
+    for (int t = 0; t < 3; ++t) {
+      const int rc = make_window_maps(e.maps.m[t], base[t], g, row_elems[t]);
+      if (rc) return rc;
+    }
     e.key = key;
     mp = &e.maps;
     cache_next = (cache_next + 1) % 32;
@@ -997,8 +890,6 @@ int wattn_tc64_bwd(const Geom& g, const void* qkv, const void* dout, const float
   }
   BwdParams p;
   p.g = g;
-  p.n_same = g.heads / 2;
-  p.has_cross = g.heads & 1;
   p.plane = (int64_t)g.B * g.nW * g.heads * kN;
   p.ko = 0;
 #ifdef HV_TC_TRACE
@@ -1006,60 +897,16 @@ int wattn_tc64_bwd(const Geom& g, const void* qkv, const void* dout, const float
   if (getenv("HV_TC_TRACE_CTA")) p.ko |= atoi(getenv("HV_TC_TRACE_CTA")) << 8;
 #endif
   const int nsm = num_sms();
-  const int nrows = g.B * g.nW;
-  if (p.n_same == 0) {
-    p.ctas_same = 0;
-    p.ctas_cross = nsm;
-  } else if (!p.has_cross) {
-    p.ctas_same = nsm / p.n_same;
-    p.ctas_cross = 0;
-  } else {
-    p.ctas_cross = nsm / (2 * p.n_same + 1);
-    if (p.ctas_cross < 1) p.ctas_cross = 1;
-    p.ctas_same = (nsm - p.ctas_cross) / p.n_same;
-  }
-  if (p.ctas_same < 1 && p.n_same) p.ctas_same = 1;
-  if (p.ctas_same > nrows) p.ctas_same = nrows;
-  if (p.ctas_cross > (nrows + 1) / 2) p.ctas_cross = (nrows + 1) / 2;
-  // shifted layer: split every group's CTAs between the window classes in proportion to their work (windows x relative
-  // cost per window: a wrapped window needs twice the TMA boxes and the mask; HV_CLASS_COST="b,e" overrides for tuning)
-  {
-    const int nWh = g.H / kWs;
-    int n[3] = {nrows, 0, 0};
-    if (g.shift > 0) {
-      n[0] = g.B * (nWh - 1) * (g.nWw - 1);
-      n[1] = g.B * (g.nWw - 1);
-      n[2] = g.B * nWh;
-    }
-    static double cost[3] = {1.0, 1.3, 1.4};
-    static const bool cost_env = []() {
-      const char* e = getenv("HV_CLASS_COST");
-      if (e) sscanf(e, "%lf,%lf", &cost[1], &cost[2]);
-      return e != nullptr;
-    }();
-    (void)cost_env;
-    auto split = [&](int& ctas, int* out) {
-      out[0] = out[1] = out[2] = 0;
-      if (ctas == 0) return;
-      int nonempty = 0;
-      double wsum = 0;
-      for (int c = 0; c < 3; ++c) { nonempty += n[c] > 0; wsum += n[c] * cost[c]; }
-      if (ctas < nonempty) ctas = nonempty;
-      int used = 0, big = -1;
-      for (int c = 0; c < 3; ++c) {
-        if (n[c] == 0) continue;
-        out[c] = (int)(ctas * n[c] * cost[c] / wsum + 0.5);
-        if (out[c] < 1) out[c] = 1;
-        used += out[c];
-        if (big < 0 || n[c] * cost[c] > n[big] * cost[big]) big = c;
-      }
-      out[big] += ctas - used;  // rounding goes to the largest class
-      if (out[big] < 1) { ctas += 1 - out[big]; out[big] = 1; }
-    };
-    split(p.ctas_same, p.cls_same);
-    split(p.ctas_cross, p.cls_cross);
-  }
-  const int grid = p.n_same * p.ctas_same + p.ctas_cross;
+  // CTAs per window class: windows x relative cost (a wrapped window needs twice the TMA boxes and the mask;
+  // HV_CLASS_COST="bottom,edge" overrides for tuning)
+  static double cost[3] = {1.0, 1.3, 1.4};
+  static const bool cost_env = []() {
+    const char* e = getenv("HV_CLASS_COST");
+    if (e) sscanf(e, "%lf,%lf", &cost[1], &cost[2]);
+    return e != nullptr;
+  }();
+  (void)cost_env;
+  const int grid = plan_window_schedule(g, nsm, cost, p.sched);
   float* ws_dbias = static_cast<float*>(workspace);
   float* ws_dtau = ws_dbias + (size_t)grid * 2 * kTab;
   // behind the attention kernel's partials (sized for 2 * SMs CTAs): the column-sum kernel's partial rows

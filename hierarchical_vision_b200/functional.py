@@ -172,7 +172,8 @@ def _timed(tag, windows, stream_device, fn, kernels=1):
 
 
 def set_attention_forward_variant(variant: int) -> None:
-    """0: mma.sync forward kernel, 1: tcgen05/TMEM/TMA forward kernel, -1: HV_ATTN_TCGEN05 environment (unset: automatic per geometry)."""
+    """0: mma.sync forward kernel, 1: tcgen05 / TMEM / TMA forward kernels (default), 2: the first-generation tcgen05
+    kernel wherever valid, -1: HV_ATTN_TCGEN05 environment (unset: 1)."""
     check(_lib.load().hv_window_attn_fwd_variant(int(variant)), "hv_window_attn_fwd_variant")
 
 

@@ -58,9 +58,10 @@ HV_API int hv_compiled_arch(void);
  * 1 = tensor-core kernel (N=64, head dim 32, bf16).  Host-only query. */
 HV_API int hv_window_attn_kernel_kind(int C, int heads, int ws, int dtype);
 
-/* Forward kernel of the tensor-core path (kind 1): 0 = mma.sync + cp.async kernel, 1 = tcgen05 / TMEM / TMA kernel
- * (even shift sizes; falls back to 0 otherwise), -1 = decided by the HV_ATTN_TCGEN05 environment variable
- * (0 / 1 as above; unset = automatic: the tcgen05 kernel wherever it is valid).  Both write the same outputs.  A test /
+/* Forward kernel of the tensor-core path (kind 1): 0 = mma.sync + cp.async kernel, 1 = tcgen05 / TMEM / TMA kernels (the
+ * second-generation kernel with TMA stores for shift 0 or ws / 2, the first-generation one for other even shifts; odd
+ * shifts fall back to 0), 2 = the first-generation tcgen05 kernel wherever valid, -1 = decided by the HV_ATTN_TCGEN05
+ * environment variable (0 / 1 as above; unset = 1).  All write the same outputs and statistics.  A test /
  * benchmarking switch: process-wide, read at launch time, not meant to be flipped while other threads launch. */
 HV_API int hv_window_attn_fwd_variant(int variant);
 /* Backward kernel of the tensor-core path: 0 = mma.sync + cp.async kernel, 1 = tcgen05 / TMEM / TMA kernel (shift 0 or

@@ -185,11 +185,14 @@ def test_product_does_not_import_oracle():
 @pytest.mark.parametrize("setter", ["hv_window_attn_fwd_variant", "hv_window_attn_bwd_variant"])
 def test_kernel_variant_setters_validate_their_argument(lib, setter):
     """The forward / backward variant switches are host-only state: -1 (automatic), 0 (mma.sync), 1 (tcgen05) are
-    accepted, anything else is an error code with a message, never a crash."""
+    accepted (the forward also takes 2: first-generation tcgen05 kernel), anything else is an error code with a message,
+    never a crash."""
     fn = getattr(lib, setter)
     for v in (0, 1, -1):
         assert fn(v) == 0
-    assert fn(2) != 0 and b"variant" in lib.hv_last_error()
+    top = 2 if setter == "hv_window_attn_fwd_variant" else 1
+    assert fn(top) == 0
+    assert fn(top + 1) != 0 and b"variant" in lib.hv_last_error()
     assert fn(-2) != 0
     assert fn(-1) == 0
 
@@ -205,10 +208,12 @@ def test_kernel_name_query_follows_the_dispatch(lib):
         return buf.value.decode()
 
     for C, heads, res in ((96, 3, 64), (192, 6, 32), (384, 12, 16), (768, 24, 8)):
-        assert name(4, res, res, C, heads, 8, 0, _lib.HV_BF16, 0) == "wattn_tc64_fwd_kernel"
+        assert name(4, res, res, C, heads, 8, 0, _lib.HV_BF16, 0) == "wattn_tc64_fwd2_kernel<false>"
         assert name(4, res, res, C, heads, 8, 0, _lib.HV_BF16, 1) == "wattn_tc64_bwd_kernel<false>"
         if res > 8:
             assert name(4, res, res, C, heads, 8, 4, _lib.HV_BF16, 1) == "wattn_tc64_bwd_kernel<true>"
+            assert name(4, res, res, C, heads, 8, 4, _lib.HV_BF16, 0) == "wattn_tc64_fwd2_kernel<true>"
+    assert name(1, 24, 24, 96, 3, 8, 2, _lib.HV_BF16, 0) == "wattn_tc64_fwd_kernel"         # even shift != ws / 2: first generation
     assert name(1, 24, 24, 96, 3, 8, 3, _lib.HV_BF16, 0) == "wattn_mma64_fwd_kernel<3>"     # odd shift: no TMA split
     assert name(1, 32, 32, 128, 4, 16, 8, _lib.HV_BF16, 1) == "wattn_generic_bwd_kernel<bf16>"  # SwinV2-B window 16
     assert name(1, 16, 16, 96, 3, 8, 4, _lib.HV_F32, 0) == "wattn_generic_fwd_kernel<float>"

@@ -60,9 +60,10 @@ CORE_CASES = [
 ]
 
 
-@pytest.fixture(params=[0, 1], ids=["fwd_mma_sync", "fwd_tcgen05"])
+@pytest.fixture(params=[0, 1, 2], ids=["fwd_mma_sync", "fwd_tcgen05", "fwd_tcgen05_gen1"])
 def fwd_variant(request):
-    """Both forward kernels of the tensor-core path: mma.sync + cp.async, and tcgen05 / TMEM / TMA."""
+    """The forward kernels of the tensor-core path: mma.sync + cp.async; tcgen05 / TMEM / TMA (second generation: TMA
+    stores, window classes; default), and the first-generation tcgen05 kernel (other even shifts)."""
     hvf.set_attention_forward_variant(request.param)
     yield request.param
     hvf.set_attention_forward_variant(-1)
