@@ -25,6 +25,7 @@ SIGNATURES = {
     "hv_window_attn_kernel_kind": (_I, [_I, _I, _I, _I]),
     "hv_window_attn_fwd_variant": (_I, [_I]),
     "hv_window_attn_bwd_variant": (_I, [_I]),
+    "hv_window_attn_tc256_variant": (_I, [_I]),
     "hv_window_attn_stats_floats": (_S, [_I, _I, _I, _I, _I, _I, _I]),
     "hv_window_attn_kernel_name": (_I, [_I, _I, _I, _I, _I, _I, _I, _I, _I, c_char_p, _I]),
     "hv_relative_position_index": (_I, [_I, _P]),

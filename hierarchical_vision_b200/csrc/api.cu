@@ -17,6 +17,14 @@ bool wattn_tc64_supported(const Geom& g, int dtype);
 int wattn_fwd_variant_set(int v);
 int wattn_fwd_variant_get();
 bool wattn_tc64_fwd2_supported(const Geom& g, int dtype);
+bool wattn_tc256_supported(const Geom& g, int dtype);
+int wattn_tc256_variant_set(int v);
+int wattn_tc256_fwd(const Geom& g, const void* qkv, const float* bias_table, const float* tau, void* out, float* stats,
+                    cudaStream_t st);
+size_t wattn_tc256_bwd_workspace_bytes(const Geom& g);
+int wattn_tc256_bwd(const Geom& g, const void* qkv, const void* out, const void* dout, const float* stats,
+                    const float* bias_table, const float* tau, void* dqkv, float* dbias_table, float* dtau, void* workspace,
+                    size_t workspace_bytes, cudaStream_t st);
 int wattn_tc64_fwd2(const Geom& g, const void* qkv, const float* bias_table, const float* tau, void* out, float* stats,
                     cudaStream_t st);
 int wattn_tc64_fwd(const Geom& g, const void* qkv, const float* bias_table, const float* tau, void* out, float* lse,
@@ -139,6 +147,12 @@ int hv_window_attn_bwd_variant(int variant) {
   return HV_OK;
 }
 
+int hv_window_attn_tc256_variant(int variant) {
+  if (variant < -1 || variant > 1) HV_FAIL(HV_ERR_SHAPE, "hv_window_attn_tc256_variant: variant %d", variant);
+  wattn_tc256_variant_set(variant);
+  return HV_OK;
+}
+
 int hv_window_attn_kernel_kind(int C, int heads, int ws, int dtype) {
   if (heads <= 0 || C % heads) return 0;
   Geom g = make_geom(1, ws, ws, C, heads, ws, 0);
@@ -149,7 +163,7 @@ size_t hv_window_attn_stats_floats(int B, int H, int W, int C, int heads, int ws
   if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || heads <= 0 || ws <= 0 || C % heads || H % ws || W % ws) return 0;
   const Geom g = make_geom(B, H, W, C, heads, ws, 0);
   const size_t plane = (size_t)g.B * g.nW * g.heads * g.N;
-  return wattn_mma64_supported(g, dtype) ? 3 * plane : plane;
+  return (wattn_mma64_supported(g, dtype) || wattn_tc256_supported(g, dtype)) ? 3 * plane : plane;
 }
 
 int hv_window_attn_kernel_name(int B, int H, int W, int C, int heads, int ws, int shift, int dtype, int backward, char* out,
@@ -159,7 +173,9 @@ int hv_window_attn_kernel_name(int B, int H, int W, int C, int heads, int ws, in
   int rc = make_checked_geom(B, H, W, C, heads, ws, shift, g);
   if (rc) return rc;
   // the same decisions as hv_window_attn_fwd / _bwd (mask == NULL)
-  if (!wattn_mma64_supported(g, dtype))
+  if (wattn_tc256_supported(g, dtype))
+    snprintf(out, out_len, "wattn_tc256_%s_kernel", backward ? "bwd" : "fwd");
+  else if (!wattn_mma64_supported(g, dtype))
     snprintf(out, out_len, "wattn_generic_%s_kernel<%s>", backward ? "bwd" : "fwd", dtype == HV_BF16 ? "bf16" : "float");
   else if (!backward && wattn_tc64_supported(g, dtype) && wattn_fwd_variant_get() != 2 && wattn_tc64_fwd2_supported(g, dtype))
     snprintf(out, out_len, "wattn_tc64_fwd2_kernel<%s>", shift > 0 ? "true" : "false");
@@ -248,6 +264,8 @@ int hv_window_attn_fwd(const void* qkv, const float* bias_table, const float* ta
     }
     return wattn_mma64_fwd(g, qkv, bias_table, tau, mask, mask_windows, out, lse, st);
   }
+  // 16 x 16 windows, head dim 32, bf16 (SwinV2-B): tcgen05 / TMEM / TMA kernels, statistics in tile order for wattn_tc256_bwd
+  if (mask == nullptr && wattn_tc256_supported(g, dtype)) return wattn_tc256_fwd(g, qkv, bias_table, tau, out, lse, st);
   return wattn_generic_fwd(g, dtype, qkv, bias_table, tau, mask, mask_windows, out, lse, st);
 }
 
@@ -258,6 +276,7 @@ size_t hv_window_attn_bwd_workspace_bytes(int B, int H, int W, int C, int heads,
     const size_t a = wattn_mma64_bwd_workspace_bytes(g), b = wattn_tc64_bwd_workspace_bytes(g);
     return a > b ? a : b;
   }
+  if (wattn_tc256_supported(g, dtype)) return wattn_tc256_bwd_workspace_bytes(g);
   return 16;  // the generic kernel reduces with atomics
 }
 
@@ -280,6 +299,8 @@ int hv_window_attn_bwd(const void* qkv, const void* out, const void* dout, const
     return wattn_mma64_bwd(g, qkv, out, dout, lse, bias_table, tau, mask, mask_windows, dqkv, dbias_table, dtau, dq_colsum,
                            workspace, workspace_bytes, st);
   }
+  if (mask == nullptr && dq_colsum == nullptr && wattn_tc256_supported(g, dtype))
+    return wattn_tc256_bwd(g, qkv, out, dout, lse, bias_table, tau, dqkv, dbias_table, dtau, workspace, workspace_bytes, st);
   if (dq_colsum != nullptr)
     HV_FAIL(HV_ERR_SHAPE, "hv_window_attn_bwd: dq_colsum is only produced by the tensor-core kernel "
                           "(hv_window_attn_kernel_kind() == 1 and mask == NULL)");

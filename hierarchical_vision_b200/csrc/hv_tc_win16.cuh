@@ -1,0 +1,84 @@
+// Window geometry shared by the tcgen05 / TMEM / TMA attention kernels for 16x16 windows (N = 256, head dim 32, bf16:
+// SwinV2-B at window 16, reference swinv2.py:105-283 with window_size = 16).
+//
+// One token order for every window (TILE order): the window is held as two COLUMN PARTS of 8 columns x 16 rows, tile
+// row t = 128 part + 8 ih + (iw & 7).  A part is one TMA box (8 w x 16 h tokens x 64 B of one head), so the cyclic shift
+// by ws / 2 = 8 (the only shift SwinV2 uses, swinv2.py:560) never splits a box along the columns: the second part of a
+// right-edge window simply starts at image column 0.  Only the bottom row of windows wraps along the rows and takes two
+// 8 x 8 boxes per part.  window_partition / window_reverse and torch.roll (swinv2.py:399-429) are these coordinates.
+//
+// In tile order a 64-row block of the tile is an 8 x 8 spatial sub-block of the window and a 128-row block a whole column
+// part, which is what makes the shift mask of a (128 query) x (64 key) block all-or-nothing per query row half, and the
+// relative-position lookup of such a block a Toeplitz window of the 31 x 31 table.
+#pragma once
+#include "hv_tc_win.cuh"
+
+namespace hv {
+namespace tc {
+
+constexpr int kWin16 = 16;
+constexpr int kN16 = 256;
+constexpr int kTab16 = 31;                // relative offsets per axis
+constexpr int kTile16 = kN16 * 64;        // one (window, head) q / k / v / dO tile: 256 rows x 64 B (SWIZZLE_64B)
+constexpr int kBiasStride16 = 40;         // floats per table row: 8 (mod 32), so the 4 x 8 queries of a warp hit 32 banks
+constexpr int kBiasFloats16 = kTab16 * kBiasStride16;
+
+struct UnitGeo16 { int b, row0, col0, flags; };  // flags = window row (b * nW + win) << 2 | right << 1 | bottom
+
+// Units (windows) of one head walked by a CTA: heads x cph CTAs, CTA c serves head c / cph, windows first, first + cph, ...
+struct Work16 {
+  int head, first, stride, nunits;
+  __device__ __forceinline__ void init(int cph, int total) {
+    head = blockIdx.x / cph;
+    first = blockIdx.x - head * cph;
+    stride = cph;
+    nunits = first < total ? (total - first + cph - 1) / cph : 0;
+  }
+};
+
+__device__ __forceinline__ UnitGeo16 unit_geo16(const Geom& g, int widx) {
+  const int b = widx / g.nW, win = widx - b * g.nW;
+  const int wh = win / g.nWw, ww = win - wh * g.nWw;
+  UnitGeo16 ug;
+  ug.b = b;
+  ug.row0 = wh * kWin16 + g.shift;
+  ug.col0 = ww * kWin16 + g.shift;
+  const int bottom = g.shift > 0 && wh == g.H / kWin16 - 1, right = g.shift > 0 && ww == g.nWw - 1;
+  ug.flags = (widx << 2) | (right << 1) | bottom;
+  return ug;
+}
+
+// The TMA boxes of one tile: f(byte offset inside the tile, map index (0: 8 x 16 box, 1: 8 x 8 box), image column, image
+// row).  The same list drives loads and stores.
+template <typename F>
+__device__ __forceinline__ void for_each_box16(const Geom& g, const UnitGeo16& ug, F&& f) {
+  int colb = ug.col0 + 8;
+  if (colb >= g.W) colb -= g.W;
+  if (!(ug.flags & 1)) {
+    f(0, 0, ug.col0, ug.row0);
+    f(8192, 0, colb, ug.row0);
+  } else {  // rows [row0, row0 + 8) then the wrapped rows [0, 8)
+    f(0, 1, ug.col0, ug.row0);
+    f(4096, 1, ug.col0, 0);
+    f(8192, 1, colb, ug.row0);
+    f(12288, 1, colb, 0);
+  }
+}
+
+// image (row, col) of tile row t of a window -- for the plain-load helper kernels
+__device__ __forceinline__ void tile_row_rc16(const Geom& g, const UnitGeo16& ug, int t, int& row, int& col) {
+  const int part = t >> 7, ih = (t & 127) >> 3, iw = 8 * part + (t & 7);
+  row = ug.row0 + ih;
+  col = ug.col0 + iw;
+  if (row >= g.H) row -= g.H;
+  if (col >= g.W) col -= g.W;
+}
+
+inline int make_window_maps16(CUtensorMap* m, const void* base, const Geom& g, int row_elems) {
+  int rc = make_map(&m[0], base, g, row_elems, 8, 16);
+  if (rc) return rc;
+  return make_map(&m[1], base, g, row_elems, 8, 8);
+}
+
+}  // namespace tc
+}  // namespace hv

@@ -182,6 +182,12 @@ def set_attention_backward_variant(variant: int) -> None:
     check(_lib.load().hv_window_attn_bwd_variant(int(variant)), "hv_window_attn_bwd_variant")
 
 
+def set_attention_tc256_variant(variant: int) -> None:
+    """16 x 16 windows, head dim 32, bf16: 1 tcgen05 / TMEM / TMA kernels (default), 0 generic CUDA-core kernels,
+    -1: HV_ATTN_TC256 environment (unset: 1).  Set it before a forward and keep it until that forward's backward ran."""
+    check(_lib.load().hv_window_attn_tc256_variant(int(variant)), "hv_window_attn_tc256_variant")
+
+
 def window_attention_fwd_raw(qkv, bias_table, tau, mask, out, lse, B, H, W, C, heads, ws, shift):
     """Enqueue hv_window_attn_fwd on the current stream; every tensor is caller-allocated."""
     lib = _lib.load()

@@ -68,9 +68,14 @@ HV_API int hv_window_attn_fwd_variant(int variant);
  * ws / 2; falls back to 0 otherwise), -1 = decided by the HV_ATTN_TCGEN05_BWD environment variable (unset = automatic:
  * the tcgen05 kernel wherever it is valid).  Same outputs and workspace; process-wide test / benchmarking switch. */
 HV_API int hv_window_attn_bwd_variant(int variant);
+/* 16 x 16 windows with head dim 32 in bf16 (SwinV2-B at window 16, reference swinv2.py:105-283 with window_size = 16,
+ * shift 0 or 8): 1 = tcgen05 / TMEM / TMA kernels wattn_tc256_{fwd,bwd}_kernel, 0 = the generic CUDA-core kernels,
+ * -1 = decided by the HV_ATTN_TC256 environment variable (unset = 1).  Forward and backward of one call pair must run
+ * under the same setting (the statistics layouts differ).  Process-wide test / benchmarking switch. */
+HV_API int hv_window_attn_tc256_variant(int variant);
 /* Number of float32 elements of the `lse` statistics buffer of hv_window_attn_fwd / _bwd for a geometry: B*nW*heads*N
  * for the generic kernel; three such planes for the tensor-core kernels (row log-sum-exp | r_i = 1 / |q_i| |
- * c_j = tau log2(e) / |k_j|, each (B*nW, heads, N) in window-slot order).  0 on invalid sizes.  Host-only query. */
+ * c_j = tau log2(e) / |k_j|, each (B*nW, heads, N); window-slot order for N = 64, the kernels' tile order for N = 256).  0 on invalid sizes.  Host-only query. */
 HV_API size_t hv_window_attn_stats_floats(int B, int H, int W, int C, int heads, int ws, int dtype);
 
 /* Name of the kernel hv_window_attn_fwd (backward = 0) / hv_window_attn_bwd (backward = 1) launches for a geometry with
