@@ -307,6 +307,11 @@ inline EncodeTiledFn encode_fn() {
 inline int make_map(CUtensorMap* m, const void* base, const Geom& g, int row_elems, int bw, int bh) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) HV_FAIL(HV_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  // the driver call needs the device's primary context current on THIS thread; a fresh autograd worker thread that has
+  // not made a runtime call yet has none (CUDA_ERROR_INVALID_CONTEXT).  Only on the map-cache miss path.
+  int dev = 0;
+  HV_CUDA_OK(cudaGetDevice(&dev));
+  HV_CUDA_OK(cudaSetDevice(dev));
   cuuint64_t dims[4] = {(cuuint64_t)row_elems, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.B};
   cuuint64_t strides[3] = {(cuuint64_t)row_elems * 2, (cuuint64_t)g.W * row_elems * 2, (cuuint64_t)g.H * g.W * row_elems * 2};
   cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, 1};

@@ -1,9 +1,630 @@
+// tcgen05 / TMEM / TMA backward kernel of the fused shifted-window scaled-cosine attention for 16 x 16 windows (N = 256),
+// head dim 32, bf16 -- SwinV2-B at window 16 (BASELINE configs[3]); reference swinv2.py:210-263 differentiated.  qkv / dqkv
+// (B, H*W, 3C), out / dout (B, H*W, C) in IMAGE token order; statistics (lse | r | c) from wattn_tc256_fwd_kernel in TILE
+// order (hv_tc_win16.cuh).  Three launches: D_i = dO_i . O_i (streaming pre-pass into the workspace), the main kernel,
+// and the fold of the per-CTA partials of d(bias table) and d(tau).
+//
+//   * a unit = one (window, head): q, k, v, dO tiles of 256 rows x 64 B (SWIZZLE_64B) by 4-D TMA box loads (cyclic shift +
+//     window partition are the coordinates), the four statistics vectors by 1-D bulk copies on the same mbarrier; dq, dk,
+//     dv are written over the q, k, v tiles and leave by TMA box stores (window_reverse + un-roll);
+//   * an item = (query block a of 128 rows = one column part) x (key block b of 64 rows = one 8 x 8 sub-block), eight per
+//     unit, a-major.  S_ab = Q_a K_b^T and dP_ab = dO_a V_b^T are M = 128, N = 64 chains (64 TMEM columns each, two
+//     buffers).  Sixteen softmax warps, a thread owns 16 keys of a row: P = exp2(s - lse), g = P (dP - D) (the gradient
+//     of the logit), W = g r_i c_j / log2e (the gradient routed to the RAW q.k product), all in fp32, staged as bf16
+//     [query][key] tiles (SWIZZLE_128B);
+//   * dV_b += P^T dO_a and dK_b += W^T Q_a (M = 64, A read MN-major from the staged tile), dQ_a += W K_b (M = 128): raw
+//     tiles as B operands, nothing is normalised in place; the epilogues project onto the tangent space of the
+//     normalisation, dq_i = M_i - q_i r_i^2 A_i with A_i = sum_j g_ij l_ij summed in fp32 by the softmax threads, and
+//     dk_j = M_j - k_j (k_j . M_j) / |k_j|^2;
+//   * d(bias table): g is staged a second time as G'[(ih, jh)][(iw, jw)] (rows: query row x key row of the sub-blocks,
+//     columns: query column x key column), and G' T with the one-hot T[(iw, jw)][dx] folds the column pairs onto the 31
+//     column offsets on the tensor core: two 128 x 32 accumulators (key row half 0 / 1) collect every window of the CTA
+//     and are folded onto the 31 row offsets once, at the end.  d(tau) = sum g l / tau from the same fp32 sums;
+//   * TMEM (512 columns): S 2 x 64 | dP 2 x 64 | dV 64 | dK 64 | dQ 2 x 32 | dBias 2 x 32.
+//   * 28 warps: 0 TMA loads | 1 issuer of S, dP | 2 issuer of dV, dK, dQ, dBias | 3 TMA stores | 4-19 softmax |
+//     20-23 dV, dK epilogue | 24-27 dQ epilogue.  All hand-overs are mbarriers.
+#define HV_WAIT_HINT_NS 1000
 #include "hv_tc_win16.cuh"
+
 namespace hv {
-size_t wattn_tc256_bwd_workspace_bytes(const Geom& g) { return 16; }
+namespace {
+using namespace tc;
+
+constexpr int kStage = 4 * kTile16;    // q k v dO
+constexpr int kStages = 2;
+constexpr int kThreads = 896;          // 28 warps
+constexpr int kPdTile = 128 * 128;     // P, W or G' of one item: 128 rows x 128 B (SWIZZLE_128B)
+constexpr int kBins = kTab16 * kTab16;
+constexpr int kBinsPad = 964;
+
+// ---- shared memory map (dynamic, 1024-byte aligned base; no static shared memory in this kernel)
+constexpr int kOffStage = 0;
+constexpr int kOffP = kOffStage + kStages * kStage;
+constexpr int kOffW = kOffP + kPdTile;
+constexpr int kOffG = kOffW + kPdTile;
+constexpr int kOffTT = kOffG + kPdTile;                    // 48 rows x 128 B: one-hot T^T (SWIZZLE_128B), row r = 23 + iw - jw
+constexpr int kOffBias = kOffTT + 48 * 128;                // [31][40] float: log2e * table (reversed columns)
+constexpr int kOffVec = kOffBias + kBiasFloats16 * 4;      // [kStages][4: lse, r, c, D][256] float, tile order
+// [2 a][4 sums][4 quarters][128] float, sums over a quarter of the row: sum g t | sum P dP t | sum P t | sum P dP
+constexpr int kOffArow = kOffVec + kStages * 4 * 256 * 4;
+constexpr int kOffGeo = kOffArow + 2 * 4 * 4 * 128 * 4;    // [4] UnitGeo16
+constexpr int kOffMisc = kOffGeo + 4 * 16;                 // d(tau) partial
+constexpr int kOffBar = kOffMisc + 16;
+constexpr int kNumBars = 3 * kStages + 12;
+constexpr int kOffTmem = kOffBar + kNumBars * 8;
+constexpr int kSmem = kOffTmem + 16;
+constexpr int kOffBinsS = kOffP;                           // [961] float d(bias) bins, after the main loop (aliases P)
+static_assert(kOffP % 1024 == 0 && kOffTT % 1024 == 0 && kOffBias % 16 == 0 && kOffVec % 16 == 0 && kOffBar % 8 == 0, "shared-memory alignment");
+static_assert(kSmem <= 227 * 1024, "shared memory budget");
+
+constexpr int kColS = 0, kColDP = 128;                  // + 64 * buffer
+constexpr int kColDV = 256, kColDK = 320;               // + 32 * (key block / 2); key block parity = lane offset 16 (M = 64)
+constexpr int kColDQ = 384, kColDB = 448;               // + 32 * a, + 32 * key row half
+constexpr int kTmemCols = 512;
+
+struct BwdParams {
+  Geom g;
+  int cph, total;
+  int64_t plane;
+};
+struct BwdMaps { CUtensorMap m[3][2]; };  // qkv, dout, dqkv
+
+// D_i = dO_i . O_i per (window, head, tile row): the row term of the softmax backward (sum_j P_ij dP_ij)
+__global__ void __launch_bounds__(256)
+wattn_tc256_rowdot_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout, float* __restrict__ D, Geom g) {
+  const int64_t unit = blockIdx.x;  // (b * nW + win) * heads + head
+  const int head = (int)(unit % g.heads);
+  const int widx = (int)(unit / g.heads);
+  const UnitGeo16 ug = unit_geo16(g, widx);
+  int row, col;
+  tile_row_rc16(g, ug, threadIdx.x, row, col);
+  const int64_t tok = ((int64_t)ug.b * g.H + row) * g.W + col;
+  const uint4* po = reinterpret_cast<const uint4*>(out + tok * g.C + head * 32);
+  const uint4* pg = reinterpret_cast<const uint4*>(dout + tok * g.C + head * 32);
+  float acc = 0.f;
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    const uint4 a = __ldg(po + ch), b = __ldg(pg + ch);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      acc = fmaf(bf16lo_to_f32(aw[e]), bf16lo_to_f32(bw[e]), acc);
+      acc = fmaf(bf16hi_to_f32(aw[e]), bf16hi_to_f32(bw[e]), acc);
+    }
+  }
+  D[unit * kN16 + threadIdx.x] = acc;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __restrict__ stats, const float* __restrict__ Dvec,
+                       const float* __restrict__ bias_table, const float* __restrict__ tau, float* __restrict__ ws_dbias,
+                       float* __restrict__ ws_dtau, const __grid_constant__ BwdParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const Geom& g = p.g;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t sb = smem_u32(smem);
+  const uint32_t bar0 = sb + kOffBar;
+  auto bar_full = [&](int s) { return bar0 + 8 * s; };                     // q, k, v, dO tiles + statistics landed
+  auto bar_empty = [&](int s) { return bar0 + 8 * (kStages + s); };        // the stores of dq, dk, dv have read the stage
+  auto bar_written = [&](int s) { return bar0 + 8 * (2 * kStages + s); };  // epilogues wrote dq, dk, dv over the tiles
+  const uint32_t barx = bar0 + 8 * 3 * kStages;
+  auto bar_sdp = [&](int b) { return barx + 8 * b; };            // S, dP accumulator buffer b complete
+  auto bar_sfree = [&](int b) { return barx + 8 * (2 + b); };    // ... and read by the softmax threads
+  const uint32_t bar_staged = barx + 8 * 4;                      // P, W, G' staging tiles written
+  const uint32_t bar_stfree = barx + 8 * 5;                      // ... and read by the output MMAs
+  auto bar_accq = [&](int a) { return barx + 8 * (6 + a); };     // dQ_a complete
+  auto bar_accqfree = [&](int a) { return barx + 8 * (8 + a); }; // ... and pulled out of TMEM
+  const uint32_t bar_acckv = barx + 8 * 10;                      // dV, dK of the unit complete
+  const uint32_t bar_acckvfree = barx + 8 * 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmem);
+  float* misc = reinterpret_cast<float*>(smem + kOffMisc);
+
+  Work16 work;
+  work.init(p.cph, p.total);
+  const int head = work.head, nunits = work.nunits, nitems = 8 * work.nunits;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 1);
+      mbar_init(bar_written(s), 12);  // 4 dV / dK epilogue warps + 4 dQ epilogue warps x 2 query blocks
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_sdp(b), 1);
+      mbar_init(bar_sfree(b), 16);
+      mbar_init(bar_accq(b), 1);
+      mbar_init(bar_accqfree(b), 4);
+    }
+    mbar_init(bar_staged, 16);
+    mbar_init(bar_stfree, 1);
+    mbar_init(bar_acckv, 1);
+    mbar_init(bar_acckvfree, 4);
+    misc[0] = 0.f;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  {
+    float* bt = reinterpret_cast<float*>(smem + kOffBias);
+    for (int idx = threadIdx.x; idx < kBiasFloats16; idx += kThreads) {
+      const int dy = idx / kBiasStride16, x = idx - dy * kBiasStride16;
+      bt[idx] = x < kTab16 ? kLog2e * __ldg(&bias_table[(dy * kTab16 + 30 - x) * g.heads + head]) : 0.f;
+    }
+    // one-hot T^T: row r, K index (iw8, jw8) -> 1 iff r = 23 + iw8 - jw8; 128-byte rows, 16-byte chunk iw8 at (iw8 ^ (r & 7))
+    for (int idx = threadIdx.x; idx < 48 * 64; idx += kThreads) {
+      const int r = idx >> 6, col = idx & 63, iw8 = col >> 3, jw8 = col & 7;
+      const bf16 v = __float2bfloat16_rn(r == 23 + iw8 - jw8 ? 1.0f : 0.0f);
+      *reinterpret_cast<bf16*>(smem + kOffTT + r * 128 + ((iw8 ^ (r & 7)) << 4) + jw8 * 2) = v;
+    }
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  UnitGeo16* geo = reinterpret_cast<UnitGeo16*>(smem + kOffGeo);
+  float* vecs = reinterpret_cast<float*>(smem + kOffVec);
+  float* arow = reinterpret_cast<float*>(smem + kOffArow);
+
+  if (warp < 4) {
+    reg_dealloc<40>();
+    if (warp == 0) {
+      // ---------------------------------------------------------------- TMA producer
+      for (int u = 0; u < nunits; ++u) {
+        const int s = u % kStages;
+        mbar_wait_fast(bar_empty(s), ((u / kStages) & 1) ^ 1);
+        const int widx = work.first + u * work.stride;
+        const UnitGeo16 ug = unit_geo16(g, widx);
+        if (lane == 0) geo[u & 3] = ug;
+        __syncwarp();
+        if (elect_one()) {
+          mbar_expect_tx(bar_full(s), kStage + 4 * 1024);
+#pragma unroll 1
+          for (int part = 0; part < 4; ++part) {  // q, k, v from qkv; dO from dout
+            const int c0 = (part < 3 ? part * g.C : 0) + head * 32;
+            const CUtensorMap* mm = part < 3 ? maps.m[0] : maps.m[1];
+            const uint32_t dst = sb + kOffStage + s * kStage + part * kTile16;
+            for_each_box16(g, ug, [&](int boff, int mi, int col, int row) {
+              tma_load_4d(dst + boff, &mm[mi], bar_full(s), c0, col, row, ug.b);
+            });
+          }
+          const int64_t uo = ((int64_t)widx * g.heads + head) * kN16;
+          const uint32_t vdst = sb + kOffVec + s * 4096;
+#pragma unroll
+          for (int pl = 0; pl < 3; ++pl) bulk_load(vdst + pl * 1024, stats + pl * p.plane + uo, 1024, bar_full(s));
+          bulk_load(vdst + 3 * 1024, Dvec + uo, 1024, bar_full(s));
+        }
+        __syncwarp();
+      }
+    } else if (warp == 1) {
+      // ---------------------------------------------------------------- issuer of S_ab = Q_a K_b^T and dP_ab = dO_a V_b^T
+      const uint32_t id = idesc_bf16(128, 64, 0, 0);
+      const uint64_t d_q = smem_desc(sb + kOffStage, 16, 512, 4), d_k = smem_desc(sb + kOffStage + kTile16, 16, 512, 4);
+      const uint64_t d_v = smem_desc(sb + kOffStage + 2 * kTile16, 16, 512, 4), d_g = smem_desc(sb + kOffStage + 3 * kTile16, 16, 512, 4);
+      for (int n = 0; n < nitems; ++n) {
+        const int u = n >> 3, j = n & 7, a = j >> 2, b = j & 3, s = u % kStages, buf = n & 1;
+        if (j == 0) mbar_wait_fast(bar_full(s), (u / kStages) & 1);
+        if (n > 1) mbar_wait_fast(bar_sfree(buf), ((n >> 1) - 1) & 1);  // the softmax threads have read item n-2 out of this buffer
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t so = (uint64_t)((s * kStage) >> 4), ao = (uint64_t)(a * 512), bo = (uint64_t)(b * 256);
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk)
+            umma_ss(tmem + kColS + 64 * buf, d_q + so + ao + 2 * kk, d_k + so + bo + 2 * kk, id, kk > 0);
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk)
+            umma_ss(tmem + kColDP + 64 * buf, d_g + so + ao + 2 * kk, d_v + so + bo + 2 * kk, id, kk > 0);
+          umma_commit(bar_sdp(buf));
+        }
+        __syncwarp();
+      }
+    } else if (warp == 2) {
+      // ---------------------------------------------------------------- issuer of dV, dK, dQ, dBias
+      const uint32_t id_t = idesc_bf16(64, 32, 1, 1);    // A = P^T / W^T (MN-major), B = dO / q (MN-major)
+      const uint32_t id_q = idesc_bf16(128, 32, 0, 1);   // A = W (K-major), B = k (MN-major)
+      const uint32_t id_b = idesc_bf16(128, 32, 0, 0);   // A = G' (K-major), B = T^T (K-major)
+      // A, MN-major view of a [query][key] tile: 64 keys = one 128-byte atom, 8 queries = 1 KB (SBO)
+      const uint64_t a_pt = smem_desc(sb + kOffP, 16, 1024, 2), a_wt = smem_desc(sb + kOffW, 16, 1024, 2);
+      // A, K-major view: rows of 128 B, 8-row groups 1 KB apart
+      const uint64_t a_w = smem_desc(sb + kOffW, 16, 1024, 2), a_g = smem_desc(sb + kOffG, 16, 1024, 2);
+      const uint64_t b_tt = smem_desc(sb + kOffTT, 16, 1024, 2);
+      // B, MN-major view of a 256 x 64-byte tile: 32 channels = one 64-byte atom, 8 tokens = 512 B (SBO)
+      const uint64_t b_q = smem_desc(sb + kOffStage, 16, 512, 4), b_k = smem_desc(sb + kOffStage + kTile16, 16, 512, 4);
+      const uint64_t b_g = smem_desc(sb + kOffStage + 3 * kTile16, 16, 512, 4);
+      for (int n = 0; n < nitems; ++n) {
+        const int u = n >> 3, j = n & 7, a = j >> 2, b = j & 3, s = u % kStages;
+        mbar_wait_fast(bar_staged, n & 1);
+        if (u > 0 && j == 0) mbar_wait_fast(bar_acckvfree, (u - 1) & 1);    // dV, dK of the previous unit are out of TMEM
+        if (u > 0 && b == 0) mbar_wait_fast(bar_accqfree(a), (u - 1) & 1);  // ... and its dQ_a
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t so = (uint64_t)((s * kStage) >> 4), ao = (uint64_t)(a * 512), bo = (uint64_t)(b * 256);
+          const uint32_t dl = (uint32_t)(16 * (b & 1)) << 16;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)  // 16 queries per step: A += 2 KB, B += 1 KB
+            umma_ss(tmem + dl + kColDV + 32 * (b >> 1), a_pt + (uint64_t)(128 * ks), b_g + so + ao + (uint64_t)(64 * ks), id_t,
+                    (a > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            umma_ss(tmem + dl + kColDK + 32 * (b >> 1), a_wt + (uint64_t)(128 * ks), b_q + so + ao + (uint64_t)(64 * ks), id_t,
+                    (a > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)  // 16 keys per step: A += 32 B inside the swizzle atom, B += 1 KB
+            umma_ss(tmem + kColDQ + 32 * a, a_w + (uint64_t)(2 * ks), b_k + so + bo + (uint64_t)(64 * ks), id_q,
+                    (b > 0 || ks > 0) ? 1u : 0u);
+          // d(bias): column offset dx = 8 (a - pb) + iw8 - jw8 lands in accumulator column dx + 15 when the B rows start at
+          // row 8 - 8 (a - pb) of T^T (8 rows = one 1 KB swizzle atom)
+          const uint64_t to = (uint64_t)((8 - 8 * (a - (b >> 1))) * 128 >> 4);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_ss(tmem + kColDB + 32 * (b & 1), a_g + (uint64_t)(2 * ks), b_tt + to + (uint64_t)(2 * ks), id_b,
+                    (n > 1 || ks > 0) ? 1u : 0u);
+          umma_commit(bar_stfree);
+          if (b == 3) umma_commit(bar_accq(a));
+          if (j == 7) umma_commit(bar_acckv);
+        }
+        __syncwarp();
+      }
+    } else {
+      // ---------------------------------------------------------------- warp 3: TMA stores of dq, dk, dv (over the q, k, v tiles)
+      for (int u = 0; u < nunits; ++u) {
+        const int s = u % kStages;
+        mbar_wait_fast(bar_written(s), (u / kStages) & 1);
+        const uint32_t st = sb + kOffStage + s * kStage;
+        if (elect_one()) {
+          const UnitGeo16 ug = geo[u & 3];
+#pragma unroll 1
+          for (int part = 0; part < 3; ++part) {
+            const int c0 = part * g.C + head * 32;
+            for_each_box16(g, ug, [&](int boff, int mi, int col, int row) {
+              tma_store_4d(&maps.m[2][mi], st + part * kTile16 + boff, c0, col, row, ug.b);
+            });
+          }
+        }
+        __syncwarp();
+        bulk_commit();
+        bulk_wait_read0();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty(s));
+      }
+      bulk_wait0();
+    }
+  } else if (warp < 20) {
+    // ------------------------------------------------------------------ softmax / gradient threads: a thread owns 16 keys of a
+    // row.  Query = tile row t of block a (window row ih, column 8 a + iw8); keys = rows jl = 2 qt, 2 qt + 1 of key block b
+    // (column part b / 2, window rows 8 (b & 1) + jl), TMEM columns 16 qt ..
+    reg_alloc<80>();
+    const int quad = warp & 3, qt = (warp - 4) >> 2;
+    const int t = 32 * quad + lane, ih = t >> 3, iw8 = t & 7;
+    const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16) + 16 * qt;
+    const float kNeg = kMaskValue * kLog2e;
+    const float* bt = reinterpret_cast<const float*>(smem + kOffBias);
+    const uint32_t p_row = sb + kOffP + t * 128, w_row = sb + kOffW + t * 128;
+    const uint32_t swz = (uint32_t)(t & 7);
+    float arow_acc = 0.f, a1_acc = 0.f, a2_acc = 0.f, dp_acc = 0.f;
+    float li = 0.f, ri = 0.f, Di = 0.f, riL = 0.f;
+
+    for (int n = 0; n < nitems; ++n) {
+      const int u = n >> 3, j = n & 7, a = j >> 2, b = j & 3, s = u % kStages, buf = n & 1;
+      const float* vec = vecs + s * 1024;
+      if (j == 0) mbar_wait_fast(bar_full(s), (u / kStages) & 1);  // statistics (and tiles) of the unit have landed
+      if (b == 0) {
+        li = vec[128 * a + t];
+        ri = vec[256 + 128 * a + t];
+        Di = vec[768 + 128 * a + t];
+        riL = ri * kLn2;
+        arow_acc = a1_acc = a2_acc = dp_acc = 0.f;
+      }
+      const int flags = geo[u & 3].flags;
+      const float* cv = vec + 512 + 64 * b + 16 * qt;
+      const float* bp = bt + (ih - 8 * (b & 1) + 15) * kBiasStride16 + (15 - 8 * a - iw8 + 8 * (b >> 1));
+      const bool masked = ((flags & 1) && ((ih >= 8) != ((b & 1) != 0))) || ((flags & 2) && (a != (b >> 1)));
+      const float lim = masked ? li - kNeg : li;  // the whole 64-key block is on the other side of a wrap, or none of it
+      mbar_wait_fast(bar_sdp(buf), (n >> 1) & 1);
+      tc_fence_after();
+      uint32_t sa[16], pa[16];
+      HV_TMEM_LD16(tl + kColS + 64 * buf, sa);
+      HV_TMEM_LD16(tl + kColDP + 64 * buf, pa);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_sfree(buf));
+      uint32_t pk[8], wk[8], gk[8];
+      float As = 0.f, A1 = 0.f, A2 = 0.f, Dp = 0.f;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int jl = 2 * qt + r;
+        const float4 c0 = *reinterpret_cast<const float4*>(cv + 8 * r), c1 = *reinterpret_cast<const float4*>(cv + 8 * r + 4);
+        const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        float pe[8], ge[8], we[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float tt = (__uint_as_float(sa[8 * r + e]) * ri) * cc[e];  // tau log2e cos(q_i, k_j)
+          const float x = (tt + bp[-kBiasStride16 * jl + e]) - lim;
+          pe[e] = ex2(x);
+          const float dp = __uint_as_float(pa[8 * r + e]);
+          ge[e] = pe[e] * (dp - Di);
+          As = fmaf(ge[e], tt, As);
+          const float pd = pe[e] * dp;
+          Dp += pd;
+          A1 = fmaf(pd, tt, A1);
+          A2 = fmaf(pe[e], tt, A2);
+          we[e] = (ge[e] * riL) * cc[e];
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          pk[4 * r + e] = pack_bf16x2(pe[2 * e], pe[2 * e + 1]);
+          wk[4 * r + e] = pack_bf16x2(we[2 * e], we[2 * e + 1]);
+          gk[4 * r + e] = pack_bf16x2(ge[2 * e], ge[2 * e + 1]);
+        }
+      }
+      arow_acc += As;
+      a1_acc += A1;
+      a2_acc += A2;
+      dp_acc += Dp;
+      if (n > 0) mbar_wait_fast(bar_stfree, (n - 1) & 1);  // the output MMAs of the previous item have read the staging tiles
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const uint32_t jl = (uint32_t)(2 * qt + r);
+        sts128(p_row + ((jl ^ swz) << 4), make_uint4(pk[4 * r], pk[4 * r + 1], pk[4 * r + 2], pk[4 * r + 3]));
+        sts128(w_row + ((jl ^ swz) << 4), make_uint4(wk[4 * r], wk[4 * r + 1], wk[4 * r + 2], wk[4 * r + 3]));
+        // G': row (ih, jl), 16-byte chunk iw8 = the eight key columns of this key row
+        const uint32_t R = (uint32_t)(ih * 8) + jl;
+        sts128(sb + kOffG + R * 128 + ((((uint32_t)iw8) ^ (R & 7)) << 4), make_uint4(gk[4 * r], gk[4 * r + 1], gk[4 * r + 2], gk[4 * r + 3]));
+      }
+      if (b == 3) {
+        float* ar = arow + a * 2048 + qt * 128 + t;
+        ar[0] = arow_acc;
+        ar[512] = a1_acc;
+        ar[1024] = a2_acc;
+        ar[1536] = dp_acc;
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_staged);
+    }
+  } else if (warp < 24) {
+    // ------------------------------------------------------------------ dV / dK epilogue: M = 64 accumulators, lanes 0-15 of a
+    // quadrant = key block 2 cg, lanes 16-31 = key block 2 cg + 1
+    const int quad = warp & 3;
+    const int ub = lane >> 4, tt = 16 * quad + (lane & 15);
+    const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16);
+    const uint32_t swz = (uint32_t)((tt >> 1) & 3);
+    const float inv_tl = 1.0f / (__ldg(&tau[head]) * kLog2e);
+    for (int u = 0; u < nunits; ++u) {
+      const int s = u % kStages;
+      mbar_wait_fast(bar_acckv, u & 1);
+      tc_fence_after();
+      const uint32_t st = sb + kOffStage + s * kStage;
+      const float* vec = vecs + s * 1024;
+#pragma unroll 1
+      for (int cg = 0; cg < 2; ++cg) {
+        const int R = 64 * (2 * cg + ub) + tt;  // key tile row
+        uint32_t acc[32];
+        HV_TMEM_LD32(tl + kColDV + 32 * cg, acc);
+        tmem_wait_ld();
+        HV_REG_FENCE32(acc);
+        const uint32_t vrow = st + 2 * kTile16 + R * 64;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(acc[8 * q + 0]), __uint_as_float(acc[8 * q + 1]));
+          v.y = pack_bf16x2(__uint_as_float(acc[8 * q + 2]), __uint_as_float(acc[8 * q + 3]));
+          v.z = pack_bf16x2(__uint_as_float(acc[8 * q + 4]), __uint_as_float(acc[8 * q + 5]));
+          v.w = pack_bf16x2(__uint_as_float(acc[8 * q + 6]), __uint_as_float(acc[8 * q + 7]));
+          sts128(vrow + ((q ^ swz) << 4), v);
+        }
+        HV_TMEM_LD32(tl + kColDK + 32 * cg, acc);
+        tmem_wait_ld();
+        HV_REG_FENCE32(acc);
+        if (cg == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_acckvfree);
+        }
+        // dk_j = M_j - k_j (k_j . M_j) / |k_j|^2, 1 / |k_j| = c_j / (tau log2e)
+        const float rho = vec[512 + R] * inv_tl;
+        const uint32_t krow = st + kTile16 + R * 64;
+        uint32_t xh[16];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const uint4 v = lds128(krow + ((ch ^ swz) << 4));
+          xh[4 * ch] = v.x; xh[4 * ch + 1] = v.y; xh[4 * ch + 2] = v.z; xh[4 * ch + 3] = v.w;
+        }
+        float dot = 0.f;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          dot = fmaf(bf16lo_to_f32(xh[e]), __uint_as_float(acc[2 * e]), dot);
+          dot = fmaf(bf16hi_to_f32(xh[e]), __uint_as_float(acc[2 * e + 1]), dot);
+        }
+        dot *= rho * rho;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float v0 = fmaf(-dot, bf16lo_to_f32(xh[4 * ch + e]), __uint_as_float(acc[8 * ch + 2 * e]));
+            const float v1 = fmaf(-dot, bf16hi_to_f32(xh[4 * ch + e]), __uint_as_float(acc[8 * ch + 2 * e + 1]));
+            o[e] = pack_bf16x2(v0, v1);
+          }
+          sts128(krow + ((ch ^ swz) << 4), make_uint4(o[0], o[1], o[2], o[3]));
+        }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_written(s));
+    }
+  } else {
+    // ------------------------------------------------------------------ dQ epilogue: dq_i = M_i - q_i r_i^2 A_i
+    const int quad = warp & 3, t = 32 * quad + lane;
+    const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16);
+    const uint32_t swz = (uint32_t)((t >> 1) & 3);
+    float acc_tau = 0.f;
+    for (int u = 0; u < nunits; ++u) {
+      const int s = u % kStages;
+      const float* vec = vecs + s * 1024;
+#pragma unroll 1
+      for (int a = 0; a < 2; ++a) {
+        mbar_wait_fast(bar_accq(a), u & 1);
+        tc_fence_after();
+        uint32_t acc[32];
+        HV_TMEM_LD32(tl + kColDQ + 32 * a, acc);
+        const float* ap = arow + a * 2048 + t;
+        const float Ai = ((ap[0] + ap[128]) + (ap[256] + ap[384])) * kLn2;  // sum_j g_ij l_ij (natural units)
+        // d(tau): sum_j P (dP - D') t with D' = sum_j P dP from the SAME fp32 P, so that the row of dS sums to zero exactly
+        // (D from the bf16 output leaves a residue ~2^-9 |D| sum_j P t that does not cancel)
+        const float A1 = (ap[512] + ap[640]) + (ap[768] + ap[896]), A2 = (ap[1024] + ap[1152]) + (ap[1280] + ap[1408]);
+        const float Dq = (ap[1536] + ap[1664]) + (ap[1792] + ap[1920]);
+        acc_tau += fmaf(-Dq, A2, A1);
+        const float ri = vec[256 + 128 * a + t];
+        tmem_wait_ld();
+        HV_REG_FENCE32(acc);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_accqfree(a));
+        const float coef = ri * ri * Ai;
+        const uint32_t qrow = sb + kOffStage + s * kStage + (128 * a + t) * 64;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const uint4 v = lds128(qrow + ((ch ^ swz) << 4));
+          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+          uint32_t o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float v0 = fmaf(-coef, bf16lo_to_f32(w[e]), __uint_as_float(acc[8 * ch + 2 * e]));
+            const float v1 = fmaf(-coef, bf16hi_to_f32(w[e]), __uint_as_float(acc[8 * ch + 2 * e + 1]));
+            o[e] = pack_bf16x2(v0, v1);
+          }
+          sts128(qrow + ((ch ^ swz) << 4), make_uint4(o[0], o[1], o[2], o[3]));
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_written(s));
+      }
+    }
+    // d(tau) = sum g cos = sum g t / (tau log2e)
+    const float tot = warp_sum(acc_tau);
+    if (lane == 0) atomicAdd(&misc[0], tot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  // ---- d(bias): fold the two (query row, key row) x dx accumulators onto the 31 x 31 table bins of this head
+  float* bins = reinterpret_cast<float*>(smem + kOffBinsS);
+  for (int idx = threadIdx.x; idx < kBinsPad; idx += kThreads) bins[idx] = 0.f;
+  __syncthreads();
+  if (warp >= 24 && nunits > 0) {
+    const int quad = warp & 3, R = 32 * quad + lane;
+    const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+    for (int kh = 0; kh < 2; ++kh) {
+      uint32_t acc[32];
+      HV_TMEM_LD32(tl + kColDB + 32 * kh, acc);
+      tmem_wait_ld();
+      HV_REG_FENCE32(acc);
+      const int dy = (R >> 3) - (R & 7) - 8 * kh + 15;
+#pragma unroll
+      for (int n = 0; n < kTab16; ++n) atomicAdd(&bins[dy * kTab16 + n], __uint_as_float(acc[n]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < kBins; idx += kThreads) ws_dbias[(int64_t)blockIdx.x * kBinsPad + idx] = bins[idx];
+  if (threadIdx.x == 0) ws_dtau[blockIdx.x] = misc[0];
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols));
+}
+
+// d(bias table)[bin, head] and d(tau)[head] from the per-CTA partials (cph CTAs per head)
+__global__ void wattn_tc256_fold_kernel(const float* __restrict__ ws_dbias, const float* __restrict__ ws_dtau,
+                                        const float* __restrict__ tau, float* __restrict__ dbias_table, float* __restrict__ dtau,
+                                        int heads, int cph) {
+  const int head = blockIdx.x;
+  for (int bin = threadIdx.x; bin < kBins; bin += blockDim.x) {
+    float acc = 0.f;
+    for (int c = 0; c < cph; ++c) acc += ws_dbias[(int64_t)(head * cph + c) * kBinsPad + bin];
+    dbias_table[bin * heads + head] = acc;
+  }
+  if (threadIdx.x == 0) {
+    float acc = 0.f;
+    for (int c = 0; c < cph; ++c) acc += ws_dtau[head * cph + c];
+    dtau[head] = acc / (tau[head] * kLog2e);
+  }
+}
+
+int plan_cph(const Geom& g) {
+  const int total = g.B * g.nW;
+  int cph = num_sms() / g.heads;
+  if (cph > total) cph = total;
+  return cph < 1 ? 1 : cph;
+}
+
+}  // namespace
+
+size_t wattn_tc256_bwd_workspace_bytes(const Geom& g) {
+  const size_t plane = (size_t)g.B * g.nW * g.heads * kN16;
+  const size_t ctas = (size_t)num_sms() + (size_t)g.heads;  // >= heads * cph
+  return (plane + ctas * kBinsPad + ctas) * sizeof(float) + 64;
+}
+
 int wattn_tc256_bwd(const Geom& g, const void* qkv, const void* out, const void* dout, const float* stats,
                     const float* bias_table, const float* tau, void* dqkv, float* dbias_table, float* dtau, void* workspace,
                     size_t workspace_bytes, cudaStream_t st) {
-  HV_FAIL(HV_ERR_SHAPE, "wattn_tc256_bwd: not built yet");
+  if (!aligned16(qkv) || !aligned16(out) || !aligned16(dout) || !aligned16(dqkv) || !aligned16(stats) || !aligned16(workspace))
+    HV_FAIL(HV_ERR_ALIGN, "window_attn_bwd: qkv / out / dout / dqkv / statistics / workspace must be 16-byte aligned");
+  if (workspace == nullptr || workspace_bytes < wattn_tc256_bwd_workspace_bytes(g))
+    HV_FAIL(HV_ERR_SHAPE, "window_attn_bwd: workspace of %zu bytes, need %zu", workspace_bytes, wattn_tc256_bwd_workspace_bytes(g));
+  struct MapKey { const void *qkv, *dout, *dqkv; int B, H, W, C; };
+  struct MapEntry { MapKey key; BwdMaps maps; };
+  static thread_local MapEntry cache[32];
+  static thread_local int cache_n = 0, cache_next = 0;
+  const MapKey key = {qkv, dout, dqkv, g.B, g.H, g.W, g.C};
+  const BwdMaps* mp = nullptr;
+  for (int i = 0; i < cache_n; ++i) {
+    const MapKey& c = cache[i].key;
+    if (c.qkv == key.qkv && c.dout == key.dout && c.dqkv == key.dqkv && c.B == key.B && c.H == key.H && c.W == key.W && c.C == key.C) {
+      mp = &cache[i].maps;
+      break;
+    }
+  }
+  if (!mp) {
+    MapEntry& e = cache[cache_next];
+    int rc = make_window_maps16(e.maps.m[0], qkv, g, 3 * g.C);
+    if (rc) return rc;
+    rc = make_window_maps16(e.maps.m[1], dout, g, g.C);
+    if (rc) return rc;
+    rc = make_window_maps16(e.maps.m[2], dqkv, g, 3 * g.C);
+    if (rc) return rc;
+    e.key = key;
+    mp = &e.maps;
+    cache_next = (cache_next + 1) % 32;
+    if (cache_n < 32) ++cache_n;
+  }
+  BwdParams p;
+  p.g = g;
+  p.total = g.B * g.nW;
+  p.cph = plan_cph(g);
+  p.plane = (int64_t)g.B * g.nW * g.heads * kN16;
+  const int grid = g.heads * p.cph;
+  float* Dvec = static_cast<float*>(workspace);
+  float* ws_dbias = Dvec + p.plane;
+  float* ws_dtau = ws_dbias + (size_t)grid * kBinsPad;
+  static thread_local int attr_dev = -1;
+  int dev = 0;
+  HV_CUDA_OK(cudaGetDevice(&dev));
+  if (attr_dev != dev) {
+    HV_CUDA_OK(cudaFuncSetAttribute(wattn_tc256_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    attr_dev = dev;
+  }
+  wattn_tc256_rowdot_kernel<<<(unsigned)(g.B * g.nW * g.heads), 256, 0, st>>>(static_cast<const bf16*>(out),
+                                                                             static_cast<const bf16*>(dout), Dvec, g);
+  HV_LAUNCH_OK("wattn_tc256_rowdot_kernel");
+  wattn_tc256_bwd_kernel<<<grid, kThreads, kSmem, st>>>(*mp, stats, Dvec, bias_table, tau, ws_dbias, ws_dtau, p);
+  HV_LAUNCH_OK("wattn_tc256_bwd_kernel");
+  wattn_tc256_fold_kernel<<<g.heads, 256, 0, st>>>(ws_dbias, ws_dtau, tau, dbias_table, dtau, g.heads, p.cph);
+  HV_LAUNCH_OK("wattn_tc256_fold_kernel");
+  return HV_OK;
 }
+
 }  // namespace hv

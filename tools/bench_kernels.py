@@ -182,6 +182,7 @@ def main():
     ap.add_argument("--tau", default="init", choices=["init", "clamp", "mixed"])
     ap.add_argument("--sweep", action="store_true", help="BASELINE.json configs[4]: shifted window attention at the stage-0 and "
                     "stage-1 shapes + PatchMerging's gather over batch 32 ... 512")
+    ap.add_argument("--generic16", action="store_true", help="attn16: also time the generic CUDA-core kernels (batch / 8)")
     ap.add_argument("--colsum", action="store_true", help="attention backward also produces d(q_bias) (as in the training step)")
     a = ap.parse_args()
     rows = []
@@ -207,6 +208,19 @@ def main():
         if a.only != "attn0":
             rows.append(bench_attn(max(B // 8, 8), 64, 96, 3, 8, 4, torch.float32, max(a.iters // 6, 3)))
             print(json.dumps(rows[-1]), flush=True)
+    if a.only in ("", "attn16"):
+        # SwinV2-B at window 16 (BASELINE configs[3]): stages 0-2 run 16 x 16 windows (N = 256), stage 3 is 8 x 8 tokens
+        # (window clamped to 8: the N = 64 kernels).  tcgen05 kernels, then the generic CUDA-core kernels for comparison.
+        for res, C, h in ((64, 128, 4), (32, 256, 8), (16, 512, 16)):
+            for shift in ((0, 8) if res > 16 else (0,)):
+                for variant in ((1, 0) if a.generic16 else (1,)):
+                    hvf.set_attention_tc256_variant(variant)
+                    r = bench_attn(B if variant else max(B // 8, 4), res, C, h, 16, shift, torch.bfloat16,
+                                   a.iters if variant else max(a.iters // 6, 3), a.tau)
+                    r["kernel"] = "window_attn16_tcgen05" if variant else "window_attn16_generic"
+                    rows.append(r)
+                    print(json.dumps(rows[-1]), flush=True)
+        hvf.set_attention_tc256_variant(-1)
     if a.only in ("", "gelu"):
         for res, C, h in stages:
             rows.append(bench_gelu(B * res * res, 4 * C, torch.bfloat16, a.iters))
