@@ -215,7 +215,16 @@ def test_kernel_name_query_follows_the_dispatch(lib):
             assert name(4, res, res, C, heads, 8, 4, _lib.HV_BF16, 0) == "wattn_tc64_fwd2_kernel<true>"
     assert name(1, 24, 24, 96, 3, 8, 2, _lib.HV_BF16, 0) == "wattn_tc64_fwd_kernel"         # even shift != ws / 2: first generation
     assert name(1, 24, 24, 96, 3, 8, 3, _lib.HV_BF16, 0) == "wattn_mma64_fwd_kernel<3>"     # odd shift: no TMA split
-    assert name(1, 32, 32, 128, 4, 16, 8, _lib.HV_BF16, 1) == "wattn_generic_bwd_kernel<bf16>"  # SwinV2-B window 16
+    # SwinV2-B window 16, head dim 32, bf16: the N = 256 tcgen05 kernels for shift 0 / 8, generic otherwise
+    assert name(1, 32, 32, 128, 4, 16, 8, _lib.HV_BF16, 1) == "wattn_tc256_bwd_kernel"
+    assert name(2, 16, 16, 512, 16, 16, 0, _lib.HV_BF16, 0) == "wattn_tc256_fwd_kernel"
+    assert name(1, 32, 32, 128, 4, 16, 4, _lib.HV_BF16, 0) == "wattn_generic_fwd_kernel<bf16>"
+    assert name(1, 32, 32, 128, 2, 16, 8, _lib.HV_BF16, 1) == "wattn_generic_bwd_kernel<bf16>"  # head dim 64
+    assert name(1, 32, 32, 128, 4, 16, 8, _lib.HV_F32, 1) == "wattn_generic_bwd_kernel<float>"
+    assert lib.hv_window_attn_tc256_variant(0) == 0
+    assert name(1, 32, 32, 128, 4, 16, 8, _lib.HV_BF16, 1) == "wattn_generic_bwd_kernel<bf16>"
+    assert lib.hv_window_attn_tc256_variant(2) != 0 and b"variant" in lib.hv_last_error()
+    assert lib.hv_window_attn_tc256_variant(-1) == 0
     assert name(1, 16, 16, 96, 3, 8, 4, _lib.HV_F32, 0) == "wattn_generic_fwd_kernel<float>"
     buf = ctypes.create_string_buffer(8)
     assert lib.hv_window_attn_kernel_name(1, 16, 16, 96, 5, 8, 0, _lib.HV_BF16, 0, buf, 8) != 0  # C % heads

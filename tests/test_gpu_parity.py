@@ -49,7 +49,10 @@ CORE_CASES = [
     (1, 24, 16, 32, 1, 8, 7),
     (1, 14, 21, 48, 3, 7, 3),     # reference default window 7, head dim 16
     (2, 8, 8, 32, 1, 4, 2),
-    (1, 32, 32, 64, 2, 16, 8),    # SwinV2-B window
+    (1, 32, 32, 64, 2, 16, 8),    # SwinV2-B window: bf16 = the N = 256 tcgen05 kernels
+    (2, 32, 48, 128, 4, 16, 0),   # ... unshifted, rectangular grid of windows
+    (3, 16, 32, 96, 3, 16, 8),    # ... one row of windows: every window wraps along the rows, the last one in both directions
+    (2, 16, 16, 64, 2, 16, 0),    # ... one window per image (stage 2 of SwinV2-B at 256 px)
     (1, 16, 16, 128, 2, 8, 4),    # head dim 64
     (3, 16, 16, 192, 6, 8, 4),    # stage-1 shape of SwinV2-T
     (4, 16, 16, 384, 12, 8, 0),   # stage-2 shape of SwinV2-T (12 heads, 4 windows per image)
@@ -96,7 +99,10 @@ def test_window_attention_core(case, dtype, fwd_variant, bwd_variant):
     assert_close("out", out, o, tol)
     assert_close("dqkv", qkv.grad, dqkv, tol)
     assert_close("dbias_table", tab.grad, dtab, tol)
-    assert_close("dtau", tau.grad, dtau, DTAU_TOL[dtype])
+    # the tcgen05 backward kernels sum d(tau) from a self-consistent fp32 softmax backward (rows of dS sum to zero exactly):
+    # north_star's 2e-2 holds with a wide margin; the mma.sync / generic fallbacks keep the wider band (see DTAU_TOL)
+    name = hvf.window_attention_kernel_name(B, H, W, C, h, ws, s, dtype, True)
+    assert_close("dtau", tau.grad, dtau, 2e-2 if "_tc" in name else DTAU_TOL[dtype])
 
 
 @pytest.mark.parametrize("taus", [(0.05, 10.0, 100.0), (100.0, 100.0, 100.0), (1.0, 13.0, 15.0), (30.0, 2.0, 60.0)])
@@ -123,7 +129,61 @@ def test_window_attention_core_tau_range(taus, shift, fwd_variant, bwd_variant):
     # d(tau) = sum_ij dS_ij cos_ij with sum_j dS_ij = 0: every bf16 rounding on the way to dS (2^-9 per entry) leaves a
     # residue ~2^-9 * |cos| against a result of size ~|delta cos| ~ 1/tau, i.e. ~tau * 2e-3 relative.  Near the clamp
     # this gradient is multiplied by d clamp / d logit_scale = 0 (swinv2.py:230), so only its order of magnitude matters.
-    assert_close("dtau", tau.grad, dtau, DTAU_TOL[torch.bfloat16] if max(taus) < 50 else 0.35)
+    name = hvf.window_attention_kernel_name(B, H, W, C, h, ws, shift, torch.bfloat16, True)
+    if "_tc" in name:  # tcgen05 backward: self-consistent fp32 row sums, no residue (see test_window_attention_core)
+        assert_close("dtau", tau.grad, dtau, 2e-2)
+    else:
+        assert_close("dtau", tau.grad, dtau, DTAU_TOL[torch.bfloat16] if max(taus) < 50 else 0.35)
+
+
+@pytest.mark.parametrize("taus", [(0.05, 100.0), (100.0, 100.0), (1.0, 13.0), (30.0, 2.0)])
+@pytest.mark.parametrize("shift", [0, 8])
+def test_window_attention_core_tau_range_window16(taus, shift):
+    """The N = 256 tcgen05 kernels (SwinV2-B, window 16) across the logit-scale range: heads with a small scale take the
+    softmax path without a row maximum, heads near the clamp (swinv2.py:230) read S twice (maximum, then exponentials)."""
+    B, H, W, C, h, ws = 2, 32, 48, 64, 2, 16
+    g = O.Geometry(B, H, W, C, h, ws, shift)
+    assert hvf.window_attention_kernel_name(B, H, W, C, h, ws, shift, torch.bfloat16, False) == "wattn_tc256_fwd_kernel"
+    gen = torch.Generator().manual_seed(int(sum(taus) * 10) + shift)
+    qkv = torch.randn(B, H * W, 3 * C, generator=gen).to(DEV, torch.bfloat16).requires_grad_(True)
+    tab = (16 * torch.sigmoid(2 * torch.randn((2 * ws - 1) ** 2, h, generator=gen))).to(DEV).requires_grad_(True)
+    tau = torch.tensor(taus).to(DEV).requires_grad_(True)
+    do = torch.randn(B, H * W, C, generator=gen).to(DEV, torch.bfloat16)
+    out = hvf.window_attention(qkv, tab, tau, B=B, H=H, W=W, C=C, heads=h, ws=ws, shift=shift)
+    out.backward(do)
+    torch.cuda.synchronize()
+    o, lse, dqkv, dtab, dtau = _oracle_core(qkv, tab, tau, g, do)
+    assert torch.isfinite(out).all() and torch.isfinite(qkv.grad).all()
+    assert_close("out", out, o, 2e-2)
+    assert_close("dqkv", qkv.grad, dqkv, 2e-2)
+    assert_close("dbias_table", tab.grad, dtab, 2e-2)
+    assert_close("dtau", tau.grad, dtau, 2e-2)
+
+
+def test_window16_tcgen05_matches_generic_kernels():
+    """Both implementations of the 16 x 16-window attention (tcgen05 / TMEM / TMA and the generic CUDA-core kernels) on
+    the same inputs, through the variant switch of the C ABI."""
+    B, H, W, C, h, ws, shift = 2, 32, 32, 128, 4, 16, 8
+    gen = torch.Generator().manual_seed(5)
+    qkv0 = torch.randn(B, H * W, 3 * C, generator=gen).to(DEV, torch.bfloat16)
+    tab0 = (16 * torch.rand((2 * ws - 1) ** 2, h, generator=gen)).to(DEV)
+    tau0 = (5 + 20 * torch.rand(h, generator=gen)).to(DEV)
+    do = torch.randn(B, H * W, C, generator=gen).to(DEV, torch.bfloat16)
+    res = []
+    try:
+        for variant in (1, 0):
+            hvf.set_attention_tc256_variant(variant)
+            kind = hvf.window_attention_kernel_name(B, H, W, C, h, ws, shift, torch.bfloat16, True)
+            assert kind == ("wattn_tc256_bwd_kernel" if variant else "wattn_generic_bwd_kernel<bf16>")
+            qkv, tab, tau = (t.clone().requires_grad_(True) for t in (qkv0, tab0, tau0))
+            out = hvf.window_attention(qkv, tab, tau, B=B, H=H, W=W, C=C, heads=h, ws=ws, shift=shift)
+            out.backward(do)
+            torch.cuda.synchronize()
+            res.append((out.detach(), qkv.grad, tab.grad, tau.grad))
+    finally:
+        hvf.set_attention_tc256_variant(-1)
+    for name, a, b in zip(("out", "dqkv", "dbias_table", "dtau"), res[0], res[1]):
+        assert_close(name, a, b.double().cpu(), 2e-2 if name != "dtau" else DTAU_TOL[torch.bfloat16])
 
 
 @pytest.mark.parametrize("case", [(2, 16, 16, 96, 3, 4), (1, 32, 16, 192, 6, 0), (3, 8, 8, 64, 2, 0), (1, 16, 16, 32, 1, 5)])
