@@ -40,7 +40,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity) {
   uint32_t done = 0, spins = 0;
   while (true) {
-#ifdef HV_WAIT_HINT_NS
+#if defined(HV_WAIT_HINT_NS) && HV_WAIT_HINT_NS > 0
     // with a suspend-time hint the hardware parks the warp until the phase completes (or the hint expires) instead of
     // returning after its short default window: far fewer polling instructions compete with the working warps
     asm volatile(

@@ -20,8 +20,42 @@ constexpr int kWin16 = 16;
 constexpr int kN16 = 256;
 constexpr int kTab16 = 31;                // relative offsets per axis
 constexpr int kTile16 = kN16 * 64;        // one (window, head) q / k / v / dO tile: 256 rows x 64 B (SWIZZLE_64B)
-constexpr int kBiasStride16 = 40;         // floats per table row: 8 (mod 32), so the 4 x 8 queries of a warp hit 32 banks
-constexpr int kBiasFloats16 = kTab16 * kBiasStride16;
+constexpr int kBiasStride16 = 40;         // floats per table row (a multiple of 4: the alignment of a run does not depend on the row)
+// Four ALIGNMENT COPIES of the table, copy c shifted by c floats: a thread reads runs of 8 consecutive entries starting at
+// a column whose residue mod 4 is fixed by its query column, picks the copy that makes the run 16-byte aligned, and loads
+// it as two float4.  Copy stride = 8 (mod 32) floats so that the 8 lanes of a quarter warp hit 8 different bank groups.
+constexpr int kBiasCopy16 = 1256;
+constexpr int kBiasFloats16 = 4 * kBiasCopy16;
+
+// fill the alignment copies: entry (dy, x) = scale * table[(dy, 30 - x), head] - off, dy = ih - jh + 15, x = 15 - iw + jw
+// (REVERSED column, so the 8 keys of a window row are 8 consecutive floats)
+__device__ __forceinline__ void fill_bias16(float* bt, const float* __restrict__ bias_table, int heads, int head, float scale,
+                                            float off, int tid, int nthreads) {
+  for (int idx = tid; idx < kBiasFloats16; idx += nthreads) {
+    const int c = idx / kBiasCopy16, j = idx - c * kBiasCopy16 - c;  // copy_c[j + c] = table entry j
+    const int dy = j / kBiasStride16, x = j - dy * kBiasStride16;
+    bt[idx] = (j >= 0 && dy < kTab16 && x < kTab16) ? scale * __ldg(&bias_table[(dy * kTab16 + 30 - x) * heads + head]) - off : 0.f;
+  }
+}
+// pointer to the aligned run that holds table entries i0 .. i0 + 7 (i0 = dy * 40 + x0)
+__device__ __forceinline__ const float* bias_run16(const float* bt, int i0) {
+  const int c = (4 - (i0 & 3)) & 3;
+  return bt + c * kBiasCopy16 + i0 + c;
+}
+
+// Waits of warps that are NOT on the critical path (producer, store warp, epilogues): poll with a real sleep between
+// attempts -- a tight try_wait loop of a dozen waiting warps takes a third of the issue slots from the softmax warps
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t spins = 0;
+  while (!mbar_test(bar, parity)) {
+    asm volatile("nanosleep.u32 %0;" ::"r"(ns));
+    if (++spins > (1u << HV_SPIN_LIMIT_LOG2)) __trap();
+  }
+}  // (mbarrier.test_wait is an acquire at CTA scope by default, like try_wait)
+
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 
 struct UnitGeo16 { int b, row0, col0, flags; };  // flags = window row (b * nW + win) << 2 | right << 1 | bottom
 

@@ -23,7 +23,9 @@
 //   * TMEM (512 columns): S 2 x 64 | dP 2 x 64 | dV 64 | dK 64 | dQ 2 x 32 | dBias 2 x 32.
 //   * 28 warps: 0 TMA loads | 1 issuer of S, dP | 2 issuer of dV, dK, dQ, dBias | 3 TMA stores | 4-19 softmax |
 //     20-23 dV, dK epilogue | 24-27 dQ epilogue.  All hand-overs are mbarriers.
+#ifndef HV_WAIT_HINT_NS
 #define HV_WAIT_HINT_NS 1000
+#endif
 #include "hv_tc_win16.cuh"
 
 namespace hv {
@@ -43,17 +45,16 @@ constexpr int kOffP = kOffStage + kStages * kStage;
 constexpr int kOffW = kOffP + kPdTile;
 constexpr int kOffG = kOffW + kPdTile;
 constexpr int kOffTT = kOffG + kPdTile;                    // 48 rows x 128 B: one-hot T^T (SWIZZLE_128B), row r = 23 + iw - jw
-constexpr int kOffBias = kOffTT + 48 * 128;                // [31][40] float: log2e * table (reversed columns)
+constexpr int kOffBias = kOffTT + 48 * 128;                // four alignment copies of [31][40] float: log2e * table (reversed columns)
 constexpr int kOffVec = kOffBias + kBiasFloats16 * 4;      // [kStages][4: lse, r, c, D][256] float, tile order
-// [2 a][4 sums][4 quarters][128] float, sums over a quarter of the row: sum g t | sum P dP t | sum P t | sum P dP
+// [2 a][3 sums][4 quarters][128] float, sums over a quarter of the row: sum P dP t | sum P t | sum P dP
 constexpr int kOffArow = kOffVec + kStages * 4 * 256 * 4;
-constexpr int kOffGeo = kOffArow + 2 * 4 * 4 * 128 * 4;    // [4] UnitGeo16
+constexpr int kOffGeo = kOffArow + 2 * 3 * 4 * 128 * 4;    // [4] UnitGeo16
 constexpr int kOffMisc = kOffGeo + 4 * 16;                 // d(tau) partial
 constexpr int kOffBar = kOffMisc + 16;
 constexpr int kNumBars = 3 * kStages + 12;
 constexpr int kOffTmem = kOffBar + kNumBars * 8;
 constexpr int kSmem = kOffTmem + 16;
-constexpr int kOffBinsS = kOffP;                           // [961] float d(bias) bins, after the main loop (aliases P)
 static_assert(kOffP % 1024 == 0 && kOffTT % 1024 == 0 && kOffBias % 16 == 0 && kOffVec % 16 == 0 && kOffBar % 8 == 0, "shared-memory alignment");
 static_assert(kSmem <= 227 * 1024, "shared memory budget");
 
@@ -66,7 +67,20 @@ struct BwdParams {
   Geom g;
   int cph, total;
   int64_t plane;
+  int ko;  // HV_TC256_KO builds only: knock-out bits for timing experiments (results are wrong)
+  long long* trace;  // HV_TC256_TRACE builds only
 };
+#ifdef HV_TC256_TRACE
+// [items][16 events] clock64 stamps of CTA 0 (pointer in the kernel parameters: a predicated store, no dependent load)
+#define TRACE(n, ev) do { if (blockIdx.x == 0 && lane == 0 && (n) < 128) p.trace[(n) * 16 + (ev)] = clock64(); } while (0)
+#else
+#define TRACE(n, ev) do { } while (0)
+#endif
+#ifdef HV_TC256_KO
+#define KO(bit) (p.ko & (bit))  // 1: no output MMAs | 2: no d(bias) MMAs | 4: no staging stores | 8: no softmax math | 16: no G' store
+#else
+#define KO(bit) false
+#endif
 struct BwdMaps { CUtensorMap m[3][2]; };  // qkv, dout, dqkv
 
 // D_i = dO_i . O_i per (window, head, tile row): the row term of the softmax backward (sum_j P_ij dP_ij)
@@ -147,11 +161,7 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   {
-    float* bt = reinterpret_cast<float*>(smem + kOffBias);
-    for (int idx = threadIdx.x; idx < kBiasFloats16; idx += kThreads) {
-      const int dy = idx / kBiasStride16, x = idx - dy * kBiasStride16;
-      bt[idx] = x < kTab16 ? kLog2e * __ldg(&bias_table[(dy * kTab16 + 30 - x) * g.heads + head]) : 0.f;
-    }
+    fill_bias16(reinterpret_cast<float*>(smem + kOffBias), bias_table, g.heads, head, kLog2e, 0.f, threadIdx.x, kThreads);
     // one-hot T^T: row r, K index (iw8, jw8) -> 1 iff r = 23 + iw8 - jw8; 128-byte rows, 16-byte chunk iw8 at (iw8 ^ (r & 7))
     for (int idx = threadIdx.x; idx < 48 * 64; idx += kThreads) {
       const int r = idx >> 6, col = idx & 63, iw8 = col >> 3, jw8 = col & 7;
@@ -174,7 +184,7 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
       // ---------------------------------------------------------------- TMA producer
       for (int u = 0; u < nunits; ++u) {
         const int s = u % kStages;
-        mbar_wait_fast(bar_empty(s), ((u / kStages) & 1) ^ 1);
+        mbar_wait_sleep(bar_empty(s), ((u / kStages) & 1) ^ 1, 256);
         const int widx = work.first + u * work.stride;
         const UnitGeo16 ug = unit_geo16(g, widx);
         if (lane == 0) geo[u & 3] = ug;
@@ -207,6 +217,7 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
         const int u = n >> 3, j = n & 7, a = j >> 2, b = j & 3, s = u % kStages, buf = n & 1;
         if (j == 0) mbar_wait_fast(bar_full(s), (u / kStages) & 1);
         if (n > 1) mbar_wait_fast(bar_sfree(buf), ((n >> 1) - 1) & 1);  // the softmax threads have read item n-2 out of this buffer
+        TRACE(n, 0);
         tc_fence_after();
         if (elect_one()) {
           const uint64_t so = (uint64_t)((s * kStage) >> 4), ao = (uint64_t)(a * 512), bo = (uint64_t)(b * 256);
@@ -217,6 +228,7 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
           for (int kk = 0; kk < 2; ++kk)
             umma_ss(tmem + kColDP + 64 * buf, d_g + so + ao + 2 * kk, d_v + so + bo + 2 * kk, id, kk > 0);
           umma_commit(bar_sdp(buf));
+          TRACE(n, 1);
         }
         __syncwarp();
       }
@@ -236,12 +248,15 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
       for (int n = 0; n < nitems; ++n) {
         const int u = n >> 3, j = n & 7, a = j >> 2, b = j & 3, s = u % kStages;
         mbar_wait_fast(bar_staged, n & 1);
+        TRACE(n, 7);
         if (u > 0 && j == 0) mbar_wait_fast(bar_acckvfree, (u - 1) & 1);    // dV, dK of the previous unit are out of TMEM
         if (u > 0 && b == 0) mbar_wait_fast(bar_accqfree(a), (u - 1) & 1);  // ... and its dQ_a
+        TRACE(n, 8);
         tc_fence_after();
         if (elect_one()) {
           const uint64_t so = (uint64_t)((s * kStage) >> 4), ao = (uint64_t)(a * 512), bo = (uint64_t)(b * 256);
           const uint32_t dl = (uint32_t)(16 * (b & 1)) << 16;
+          if (!KO(1)) {
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)  // 16 queries per step: A += 2 KB, B += 1 KB
             umma_ss(tmem + dl + kColDV + 32 * (b >> 1), a_pt + (uint64_t)(128 * ks), b_g + so + ao + (uint64_t)(64 * ks), id_t,
@@ -257,13 +272,17 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
           // d(bias): column offset dx = 8 (a - pb) + iw8 - jw8 lands in accumulator column dx + 15 when the B rows start at
           // row 8 - 8 (a - pb) of T^T (8 rows = one 1 KB swizzle atom)
           const uint64_t to = (uint64_t)((8 - 8 * (a - (b >> 1))) * 128 >> 4);
+          if (!KO(2)) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
             umma_ss(tmem + kColDB + 32 * (b & 1), a_g + (uint64_t)(2 * ks), b_tt + to + (uint64_t)(2 * ks), id_b,
                     (n > 1 || ks > 0) ? 1u : 0u);
+          }
+          }
           umma_commit(bar_stfree);
           if (b == 3) umma_commit(bar_accq(a));
           if (j == 7) umma_commit(bar_acckv);
+          TRACE(n, 9);
         }
         __syncwarp();
       }
@@ -271,7 +290,8 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
       // ---------------------------------------------------------------- warp 3: TMA stores of dq, dk, dv (over the q, k, v tiles)
       for (int u = 0; u < nunits; ++u) {
         const int s = u % kStages;
-        mbar_wait_fast(bar_written(s), (u / kStages) & 1);
+        mbar_wait_sleep(bar_written(s), (u / kStages) & 1, 128);
+        TRACE(8 * u + 7, 14);
         const uint32_t st = sb + kOffStage + s * kStage;
         if (elect_one()) {
           const UnitGeo16 ug = geo[u & 3];
@@ -288,6 +308,7 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
         bulk_wait_read0();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_empty(s));
+        TRACE(8 * u + 7, 15);
       }
       bulk_wait0();
     }
@@ -303,8 +324,8 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
     const float* bt = reinterpret_cast<const float*>(smem + kOffBias);
     const uint32_t p_row = sb + kOffP + t * 128, w_row = sb + kOffW + t * 128;
     const uint32_t swz = (uint32_t)(t & 7);
-    float arow_acc = 0.f, a1_acc = 0.f, a2_acc = 0.f, dp_acc = 0.f;
-    float li = 0.f, ri = 0.f, Di = 0.f, riL = 0.f;
+    float2 a1_acc = make_float2(0.f, 0.f), a2_acc = a1_acc, dp_acc = a1_acc;
+    float li = 0.f, ri = 0.f, Di = 0.f;
 
     for (int n = 0; n < nitems; ++n) {
       const int u = n >> 3, j = n & 7, a = j >> 2, b = j & 3, s = u % kStages, buf = n & 1;
@@ -314,15 +335,16 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
         li = vec[128 * a + t];
         ri = vec[256 + 128 * a + t];
         Di = vec[768 + 128 * a + t];
-        riL = ri * kLn2;
-        arow_acc = a1_acc = a2_acc = dp_acc = 0.f;
+        a1_acc = a2_acc = dp_acc = make_float2(0.f, 0.f);
       }
       const int flags = geo[u & 3].flags;
       const float* cv = vec + 512 + 64 * b + 16 * qt;
-      const float* bp = bt + (ih - 8 * (b & 1) + 15) * kBiasStride16 + (15 - 8 * a - iw8 + 8 * (b >> 1));
+      const float* bp = bias_run16(bt, (ih - 8 * (b & 1) + 15) * kBiasStride16 + (15 - 8 * a - iw8 + 8 * (b >> 1)));
       const bool masked = ((flags & 1) && ((ih >= 8) != ((b & 1) != 0))) || ((flags & 2) && (a != (b >> 1)));
       const float lim = masked ? li - kNeg : li;  // the whole 64-key block is on the other side of a wrap, or none of it
+      const float2 ri2 = make_float2(ri, ri), nlim2 = make_float2(-lim, -lim), nDi2 = make_float2(-Di, -Di);
       mbar_wait_fast(bar_sdp(buf), (n >> 1) & 1);
+      if (warp == 4) TRACE(n, 2);
       tc_fence_after();
       uint32_t sa[16], pa[16];
       HV_TMEM_LD16(tl + kColS + 64 * buf, sa);
@@ -331,40 +353,44 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_sfree(buf));
+      if (warp == 4) TRACE(n, 3);
+      // per pair of keys (packed fp32): rc = r_i c_j, t = s rc (tau log2e cos), P = exp2(t + bias - lse), pd = P dP,
+      // g = pd - D P, W' = g rc (the epilogues apply ln 2); sums of pd, pd t, P t for d(tau) and the dq projection
       uint32_t pk[8], wk[8], gk[8];
-      float As = 0.f, A1 = 0.f, A2 = 0.f, Dp = 0.f;
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         const int jl = 2 * qt + r;
         const float4 c0 = *reinterpret_cast<const float4*>(cv + 8 * r), c1 = *reinterpret_cast<const float4*>(cv + 8 * r + 4);
-        const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-        float pe[8], ge[8], we[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float tt = (__uint_as_float(sa[8 * r + e]) * ri) * cc[e];  // tau log2e cos(q_i, k_j)
-          const float x = (tt + bp[-kBiasStride16 * jl + e]) - lim;
-          pe[e] = ex2(x);
-          const float dp = __uint_as_float(pa[8 * r + e]);
-          ge[e] = pe[e] * (dp - Di);
-          As = fmaf(ge[e], tt, As);
-          const float pd = pe[e] * dp;
-          Dp += pd;
-          A1 = fmaf(pd, tt, A1);
-          A2 = fmaf(pe[e], tt, A2);
-          we[e] = (ge[e] * riL) * cc[e];
-        }
+        const float4 b0 = *reinterpret_cast<const float4*>(bp - kBiasStride16 * jl), b1 = *reinterpret_cast<const float4*>(bp - kBiasStride16 * jl + 4);
+        const float2 cc[4] = {make_float2(c0.x, c0.y), make_float2(c0.z, c0.w), make_float2(c1.x, c1.y), make_float2(c1.z, c1.w)};
+        const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          pk[4 * r + e] = pack_bf16x2(pe[2 * e], pe[2 * e + 1]);
-          wk[4 * r + e] = pack_bf16x2(we[2 * e], we[2 * e + 1]);
-          gk[4 * r + e] = pack_bf16x2(ge[2 * e], ge[2 * e + 1]);
+          const float2 s2 = make_float2(__uint_as_float(sa[8 * r + 2 * e]), __uint_as_float(sa[8 * r + 2 * e + 1]));
+          const float2 dp2 = make_float2(__uint_as_float(pa[8 * r + 2 * e]), __uint_as_float(pa[8 * r + 2 * e + 1]));
+          const float2 rc2 = f2mul(ri2, cc[e]);
+          const float2 t2 = f2mul(s2, rc2);
+          const float2 x2 = f2add(f2add(t2, bb[e]), nlim2);
+          if (KO(8)) {
+            pk[4 * r + e] = __float_as_uint(x2.x); wk[4 * r + e] = __float_as_uint(dp2.x); gk[4 * r + e] = __float_as_uint(x2.y);
+            continue;
+          }
+          const float2 p2 = make_float2(ex2(x2.x), ex2(x2.y));
+          const float2 pd2 = f2mul(p2, dp2);
+          dp_acc = f2add(dp_acc, pd2);
+          a1_acc = f2fma(pd2, t2, a1_acc);
+          a2_acc = f2fma(p2, t2, a2_acc);
+          const float2 g2 = f2fma(nDi2, p2, pd2);
+          const float2 w2 = f2mul(g2, rc2);
+          pk[4 * r + e] = pack_bf16x2(p2.x, p2.y);
+          wk[4 * r + e] = pack_bf16x2(w2.x, w2.y);
+          gk[4 * r + e] = pack_bf16x2(g2.x, g2.y);
         }
       }
-      arow_acc += As;
-      a1_acc += A1;
-      a2_acc += A2;
-      dp_acc += Dp;
+      if (warp == 4) TRACE(n, 4);
       if (n > 0) mbar_wait_fast(bar_stfree, (n - 1) & 1);  // the output MMAs of the previous item have read the staging tiles
+      if (warp == 4) TRACE(n, 5);
+      if (!KO(4)) {
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         const uint32_t jl = (uint32_t)(2 * qt + r);
@@ -372,18 +398,19 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
         sts128(w_row + ((jl ^ swz) << 4), make_uint4(wk[4 * r], wk[4 * r + 1], wk[4 * r + 2], wk[4 * r + 3]));
         // G': row (ih, jl), 16-byte chunk iw8 = the eight key columns of this key row
         const uint32_t R = (uint32_t)(ih * 8) + jl;
-        sts128(sb + kOffG + R * 128 + ((((uint32_t)iw8) ^ (R & 7)) << 4), make_uint4(gk[4 * r], gk[4 * r + 1], gk[4 * r + 2], gk[4 * r + 3]));
+        if (!KO(16)) sts128(sb + kOffG + R * 128 + ((((uint32_t)iw8) ^ (R & 7)) << 4), make_uint4(gk[4 * r], gk[4 * r + 1], gk[4 * r + 2], gk[4 * r + 3]));
+      }
       }
       if (b == 3) {
-        float* ar = arow + a * 2048 + qt * 128 + t;
-        ar[0] = arow_acc;
-        ar[512] = a1_acc;
-        ar[1024] = a2_acc;
-        ar[1536] = dp_acc;
+        float* ar = arow + a * 1536 + qt * 128 + t;
+        ar[0] = a1_acc.x + a1_acc.y;
+        ar[512] = a2_acc.x + a2_acc.y;
+        ar[1024] = dp_acc.x + dp_acc.y;
       }
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_staged);
+      if (warp == 4) TRACE(n, 6);
     }
   } else if (warp < 24) {
     // ------------------------------------------------------------------ dV / dK epilogue: M = 64 accumulators, lanes 0-15 of a
@@ -395,7 +422,8 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
     const float inv_tl = 1.0f / (__ldg(&tau[head]) * kLog2e);
     for (int u = 0; u < nunits; ++u) {
       const int s = u % kStages;
-      mbar_wait_fast(bar_acckv, u & 1);
+      mbar_wait_sleep(bar_acckv, u & 1, 128);
+      if (warp == 20) TRACE(8 * u + 7, 10);
       tc_fence_after();
       const uint32_t st = sb + kOffStage + s * kStage;
       const float* vec = vecs + s * 1024;
@@ -423,6 +451,7 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_acckvfree);
+          if (warp == 20) TRACE(8 * u + 7, 11);
         }
         // dk_j = M_j - k_j (k_j . M_j) / |k_j|^2, 1 / |k_j| = c_j / (tau log2e)
         const float rho = vec[512 + R] * inv_tl;
@@ -439,14 +468,14 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
           dot = fmaf(bf16lo_to_f32(xh[e]), __uint_as_float(acc[2 * e]), dot);
           dot = fmaf(bf16hi_to_f32(xh[e]), __uint_as_float(acc[2 * e + 1]), dot);
         }
-        dot *= rho * rho;
+        dot *= rho * rho;  // the accumulator holds log2e * M (W' = g r c without the ln 2): dk = ln 2 (M' - k rho^2 (k . M'))
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           uint32_t o[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float v0 = fmaf(-dot, bf16lo_to_f32(xh[4 * ch + e]), __uint_as_float(acc[8 * ch + 2 * e]));
-            const float v1 = fmaf(-dot, bf16hi_to_f32(xh[4 * ch + e]), __uint_as_float(acc[8 * ch + 2 * e + 1]));
+            const float v0 = kLn2 * fmaf(-dot, bf16lo_to_f32(xh[4 * ch + e]), __uint_as_float(acc[8 * ch + 2 * e]));
+            const float v1 = kLn2 * fmaf(-dot, bf16hi_to_f32(xh[4 * ch + e]), __uint_as_float(acc[8 * ch + 2 * e + 1]));
             o[e] = pack_bf16x2(v0, v1);
           }
           sts128(krow + ((ch ^ swz) << 4), make_uint4(o[0], o[1], o[2], o[3]));
@@ -455,6 +484,7 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_written(s));
+      if (warp == 20) TRACE(8 * u + 7, 12);
     }
   } else {
     // ------------------------------------------------------------------ dQ epilogue: dq_i = M_i - q_i r_i^2 A_i
@@ -467,16 +497,20 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
       const float* vec = vecs + s * 1024;
 #pragma unroll 1
       for (int a = 0; a < 2; ++a) {
-        mbar_wait_fast(bar_accq(a), u & 1);
+        mbar_wait_sleep(bar_accq(a), u & 1, 128);
+        if (warp == 24) TRACE(8 * u + 4 * a + 3, 13);
         tc_fence_after();
         uint32_t acc[32];
         HV_TMEM_LD32(tl + kColDQ + 32 * a, acc);
-        const float* ap = arow + a * 2048 + t;
-        const float Ai = ((ap[0] + ap[128]) + (ap[256] + ap[384])) * kLn2;  // sum_j g_ij l_ij (natural units)
+        // sums over the row from the four quarter owners: A1 = sum P dP t, A2 = sum P t, D' = sum P dP (t = tau log2e cos)
+        const float* ap = arow + a * 1536 + t;
+        const float A1 = (ap[0] + ap[128]) + (ap[256] + ap[384]), A2 = (ap[512] + ap[640]) + (ap[768] + ap[896]);
+        const float Dq = (ap[1024] + ap[1152]) + (ap[1280] + ap[1408]);
+        const float Dv = vec[768 + 128 * a + t];
+        // dq projection: A_i = sum_j g_ij l_ij with the g that was staged (D from dO . O): (A1 - D A2) ln 2
+        const float Ai = fmaf(-Dv, A2, A1) * kLn2;
         // d(tau): sum_j P (dP - D') t with D' = sum_j P dP from the SAME fp32 P, so that the row of dS sums to zero exactly
         // (D from the bf16 output leaves a residue ~2^-9 |D| sum_j P t that does not cancel)
-        const float A1 = (ap[512] + ap[640]) + (ap[768] + ap[896]), A2 = (ap[1024] + ap[1152]) + (ap[1280] + ap[1408]);
-        const float Dq = (ap[1536] + ap[1664]) + (ap[1792] + ap[1920]);
         acc_tau += fmaf(-Dq, A2, A1);
         const float ri = vec[256 + 128 * a + t];
         tmem_wait_ld();
@@ -484,7 +518,7 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_accqfree(a));
-        const float coef = ri * ri * Ai;
+        const float coef = ri * ri * Ai;  // the accumulator holds log2e * M (W' = g r c without the ln 2)
         const uint32_t qrow = sb + kOffStage + s * kStage + (128 * a + t) * 64;
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
@@ -493,8 +527,8 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
           uint32_t o[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float v0 = fmaf(-coef, bf16lo_to_f32(w[e]), __uint_as_float(acc[8 * ch + 2 * e]));
-            const float v1 = fmaf(-coef, bf16hi_to_f32(w[e]), __uint_as_float(acc[8 * ch + 2 * e + 1]));
+            const float v0 = fmaf(-coef, bf16lo_to_f32(w[e]), kLn2 * __uint_as_float(acc[8 * ch + 2 * e]));
+            const float v1 = fmaf(-coef, bf16hi_to_f32(w[e]), kLn2 * __uint_as_float(acc[8 * ch + 2 * e + 1]));
             o[e] = pack_bf16x2(v0, v1);
           }
           sts128(qrow + ((ch ^ swz) << 4), make_uint4(o[0], o[1], o[2], o[3]));
@@ -511,10 +545,9 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  // ---- d(bias): fold the two (query row, key row) x dx accumulators onto the 31 x 31 table bins of this head
-  float* bins = reinterpret_cast<float*>(smem + kOffBinsS);
-  for (int idx = threadIdx.x; idx < kBinsPad; idx += kThreads) bins[idx] = 0.f;
-  __syncthreads();
+  // ---- d(bias): fold the two (query row, key row) x dx accumulators onto the 31 x 31 table bins of this head: the
+  // accumulators go to shared memory (aliasing the staging tiles), then one thread per bin gathers its <= 16 terms
+  float* accs = reinterpret_cast<float*>(smem + kOffP);  // [2 kh][128 rows][32]
   if (warp >= 24 && nunits > 0) {
     const int quad = warp & 3, R = 32 * quad + lane;
     const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16);
@@ -524,14 +557,27 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
       HV_TMEM_LD32(tl + kColDB + 32 * kh, acc);
       tmem_wait_ld();
       HV_REG_FENCE32(acc);
-      const int dy = (R >> 3) - (R & 7) - 8 * kh + 15;
 #pragma unroll
-      for (int n = 0; n < kTab16; ++n) atomicAdd(&bins[dy * kTab16 + n], __uint_as_float(acc[n]));
+      for (int n = 0; n < 32; ++n) accs[(kh * 128 + R) * 32 + ((n + R) & 31)] = __uint_as_float(acc[n]);  // rotated: conflict-free
     }
   }
   tc_fence_before();
   __syncthreads();
-  for (int idx = threadIdx.x; idx < kBins; idx += kThreads) ws_dbias[(int64_t)blockIdx.x * kBinsPad + idx] = bins[idx];
+  for (int bin = threadIdx.x; bin < kBins; bin += kThreads) {
+    const int dyi = bin / kTab16, n = bin - dyi * kTab16;
+    float v = 0.f;
+    if (nunits > 0) {
+      for (int kh = 0; kh < 2; ++kh)
+        for (int jl = 0; jl < 8; ++jl) {
+          const int ihq = jl + dyi - 15 + 8 * kh;  // row R = (ih, jl) holds dy = ih - jl - 8 kh
+          if (ihq >= 0 && ihq < 16) {
+            const int R = ihq * 8 + jl;
+            v += accs[(kh * 128 + R) * 32 + ((n + R) & 31)];
+          }
+        }
+    }
+    ws_dbias[(int64_t)blockIdx.x * kBinsPad + bin] = v;
+  }
   if (threadIdx.x == 0) ws_dtau[blockIdx.x] = misc[0];
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols));
 }
@@ -606,6 +652,11 @@ int wattn_tc256_bwd(const Geom& g, const void* qkv, const void* out, const void*
   p.total = g.B * g.nW;
   p.cph = plan_cph(g);
   p.plane = (int64_t)g.B * g.nW * g.heads * kN16;
+  p.ko = 0;
+  p.trace = nullptr;
+#ifdef HV_TC256_KO
+  if (const char* e = getenv("HV_TC256_KO")) p.ko = atoi(e);
+#endif
   const int grid = g.heads * p.cph;
   float* Dvec = static_cast<float*>(workspace);
   float* ws_dbias = Dvec + p.plane;
@@ -620,8 +671,27 @@ int wattn_tc256_bwd(const Geom& g, const void* qkv, const void* out, const void*
   wattn_tc256_rowdot_kernel<<<(unsigned)(g.B * g.nW * g.heads), 256, 0, st>>>(static_cast<const bf16*>(out),
                                                                              static_cast<const bf16*>(dout), Dvec, g);
   HV_LAUNCH_OK("wattn_tc256_rowdot_kernel");
+#ifdef HV_TC256_TRACE
+  static long long* dtrace = nullptr;
+  if (!dtrace) {
+    cudaMalloc(&dtrace, 128 * 16 * sizeof(long long));
+  }
+  cudaMemsetAsync(dtrace, 0, 128 * 16 * sizeof(long long), st);
+  p.trace = dtrace;
+#endif
   wattn_tc256_bwd_kernel<<<grid, kThreads, kSmem, st>>>(*mp, stats, Dvec, bias_table, tau, ws_dbias, ws_dtau, p);
   HV_LAUNCH_OK("wattn_tc256_bwd_kernel");
+#ifdef HV_TC256_TRACE
+  if (getenv("HV_TC256_TRACE_DUMP")) {
+    static long long h[128 * 16];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, dtrace, sizeof(h), cudaMemcpyDeviceToHost);
+    if (FILE* f = fopen(getenv("HV_TC256_TRACE_DUMP"), "w")) {
+      for (int k = 0; k < 128; ++k) { for (int e = 0; e < 16; ++e) fprintf(f, "%lld ", h[k * 16 + e] ? h[k * 16 + e] - h[1] : -1LL); fprintf(f, "\n"); }
+      fclose(f);
+    }
+  }
+#endif
   wattn_tc256_fold_kernel<<<g.heads, 256, 0, st>>>(ws_dbias, ws_dtau, tau, dbias_table, dtau, g.heads, p.cph);
   HV_LAUNCH_OK("wattn_tc256_fold_kernel");
   return HV_OK;

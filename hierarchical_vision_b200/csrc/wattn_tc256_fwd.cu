@@ -7,17 +7,19 @@
 //     coordinates are the cyclic shift + window partition; the epilogue writes the normalised output over the q tile and
 //     one warp hands it to `cp.async.bulk.tensor` stores with the same boxes (window_reverse + un-roll);
 //   * an item = one 128-query block (a column part of the window) of a unit: S = Q_blk K^T is ONE M = 128, N = 256
-//     tcgen05.mma chain (2 k-steps) into 256 TMEM columns; two S buffers fill the 512 columns.  O = P V (M = 128, N = 32,
-//     16 k-steps) lands in the first 32 columns of the item's own S buffer, which is dead once the softmax has read it;
+//     tcgen05.mma chain (2 k-steps) into 256 TMEM columns; two S buffers fill the 512 columns.  P never touches shared
+//     memory: the softmax threads write it back over their own logits as packed bf16 (tcgen05.st) and O = P V (M = 128,
+//     N = 32, 16 k-steps) takes its A operand from tensor memory; O lands in 32 dead logit columns of the same buffer;
 //   * sixteen softmax warps: a thread owns a quarter of a logit row (64 keys = one 8 x 8 sub-block of the window):
 //     tcgen05.ld 32 columns at a time, scale by 1/|q_i| * tau/|k_j|, Toeplitz position bias from the 31 x 31 table of the
-//     CTA's head, shift mask (all-or-nothing per quarter row, see hv_tc_win16.cuh), exp2, bf16 pack, 16-byte staging stores
-//     into the [query][key] P tile (four SWIZZLE_128B panels of 64 keys: the K-major A operand).  Heads whose logit range
+//     CTA's head, shift mask (all-or-nothing per quarter row, see hv_tc_win16.cuh), exp2, bf16 pack, tcgen05.st.  Heads whose logit range
 //     provably fits fp32 skip the row maximum; the others read S twice from TMEM (maximum, then exponentials) instead of
 //     holding 64 logits in registers;
 //   * a CTA serves one head (bias table and tau fixed) and walks windows first, first + cph, ...; three stages of 48 KB;
 //     28 warps: 0 TMA loads | 1 S issuer | 2 PV issuer | 3 TMA stores | 4-7 row norms | 8-23 softmax | 24-27 epilogue.
+#ifndef HV_WAIT_HINT_NS
 #define HV_WAIT_HINT_NS 1000
+#endif
 #include "hv_tc_win16.cuh"
 
 namespace hv {
@@ -27,13 +29,11 @@ using namespace tc;
 constexpr int kStage = 3 * kTile16;    // q k v; the q tile ends its life as the o tile
 constexpr int kStages = 3;
 constexpr int kThreads = 896;          // 28 warps
-constexpr int kPanel = 128 * 128;      // P of one item, 64 keys: 128 rows x 128 B (SWIZZLE_128B)
 constexpr float kNoMaxRange = 64.0f;
 
 // ---- shared memory map (dynamic, 1024-byte aligned base; no static shared memory in this kernel)
 constexpr int kOffStage = 0;
-constexpr int kOffP = kOffStage + kStages * kStage;         // [4 panels][128][128 B]
-constexpr int kOffBias = kOffP + 4 * kPanel;                // [31][40] float: log2e * table (reversed columns) - off
+constexpr int kOffBias = kOffStage + kStages * kStage;      // four alignment copies of [31][40] float: log2e * table (reversed columns) - off
 constexpr int kOffVec = kOffBias + kBiasFloats16 * 4;       // [kStages][2: r, c][256] float, tile order
 constexpr int kOffLsum = kOffVec + kStages * 2 * 256 * 4;   // [2 items in flight][4 quarters][128] float: partial row sums
 constexpr int kOffMx = kOffLsum + 2 * 4 * 128 * 4;          // [2][128] float: off + row maximum (for the lse)
@@ -44,10 +44,14 @@ constexpr int kOffBar = kOffMisc + 16;
 constexpr int kNumBars = 4 * kStages + 8;
 constexpr int kOffTmem = kOffBar + kNumBars * 8;
 constexpr int kSmem = kOffTmem + 16;
-static_assert(kOffP % 1024 == 0 && kOffBias % 16 == 0 && kOffVec % 16 == 0 && kOffBar % 8 == 0, "shared-memory alignment");
+static_assert(kOffBias % 16 == 0 && kOffVec % 16 == 0 && kOffBar % 8 == 0, "shared-memory alignment");
 static_assert(kSmem <= 227 * 1024, "shared memory budget");
 
-constexpr int kTmemCols = 512;  // two S buffers of 256 columns; O of an item in columns 0-31 of its S buffer
+// Two S buffers of 256 columns.  The softmax thread of key quarter qt writes its 64 probabilities back as 32 packed bf16
+// pairs over the first half of its OWN 64 logit columns (64 qt ..): the A operand of O = P V is read from tensor memory,
+// 8 columns per k-step.  O lands in columns 32-63 of the buffer (the dead second half of quarter 0's logits).
+constexpr int kTmemCols = 512;
+constexpr int kColO = 32;
 
 struct FwdParams {
   Geom g;
@@ -72,8 +76,7 @@ wattn_tc256_fwd_kernel(const __grid_constant__ FwdMaps maps, const float* __rest
   auto bar_s = [&](int b) { return barx + 8 * b; };            // S accumulator buffer b complete
   auto bar_o = [&](int b) { return barx + 8 * (2 + b); };      // O (columns 0-31 of buffer b) complete
   auto bar_ofree = [&](int b) { return barx + 8 * (4 + b); };  // ... and pulled out of TMEM by the epilogue
-  const uint32_t bar_staged = barx + 8 * 6;                    // P staging tile written
-  const uint32_t bar_stfree = barx + 8 * 7;                    // ... and read by the PV MMAs
+  auto bar_p = [&](int b) { return barx + 8 * (6 + b); };      // P of the item written back to tensor memory (buffer b)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmem);
   float* misc = reinterpret_cast<float*>(smem + kOffMisc);
 
@@ -93,8 +96,8 @@ wattn_tc256_fwd_kernel(const __grid_constant__ FwdMaps maps, const float* __rest
       mbar_init(bar_o(b), 1);
       mbar_init(bar_ofree(b), 4);
     }
-    mbar_init(bar_staged, 16);
-    mbar_init(bar_stfree, 1);
+    mbar_init(bar_p(0), 16);
+    mbar_init(bar_p(1), 16);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -123,16 +126,7 @@ wattn_tc256_fwd_kernel(const __grid_constant__ FwdMaps maps, const float* __rest
     }
   }
   __syncthreads();
-  {
-    // Toeplitz table: entry (dy, x) = log2e * bias[(ih - jh + 15), (iw - jw + 15)] with dy = ih - jh + 15 and the REVERSED
-    // column x = 15 - iw + jw, so the 8 keys of a window row are 8 consecutive floats
-    float* bt = reinterpret_cast<float*>(smem + kOffBias);
-    const float off0 = misc[0];
-    for (int idx = threadIdx.x; idx < kBiasFloats16; idx += kThreads) {
-      const int dy = idx / kBiasStride16, x = idx - dy * kBiasStride16;
-      bt[idx] = x < kTab16 ? kLog2e * __ldg(&bias_table[(dy * kTab16 + 30 - x) * g.heads + head]) - off0 : 0.f;
-    }
-  }
+  fill_bias16(reinterpret_cast<float*>(smem + kOffBias), bias_table, g.heads, head, kLog2e, misc[0], threadIdx.x, kThreads);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -150,7 +144,7 @@ wattn_tc256_fwd_kernel(const __grid_constant__ FwdMaps maps, const float* __rest
       // ---------------------------------------------------------------- TMA producer (one elected lane, warp-uniform operands)
       for (int u = 0; u < nunits; ++u) {
         const int s = u % kStages;
-        mbar_wait_fast(bar_empty(s), ((u / kStages) & 1) ^ 1);
+        mbar_wait_sleep(bar_empty(s), ((u / kStages) & 1) ^ 1, 256);
         const UnitGeo16 ug = unit_geo16(g, work.first + u * work.stride);
         if (lane == 0) geo[u & 3] = ug;
         __syncwarp();
@@ -187,24 +181,21 @@ wattn_tc256_fwd_kernel(const __grid_constant__ FwdMaps maps, const float* __rest
       }
     } else if (warp == 2) {
       // ---------------------------------------------------------------- issuer of O = P V (M = 128, N = 32, sixteen k-steps)
-      const uint32_t id_o = idesc_bf16(128, 32, 0, 1);  // A = P (K-major), B = v (MN-major)
-      // A, K-major view of a [query][64 keys] panel: query rows of 128 B, 8-row groups 1 KB apart; panels 16 KB apart
-      const uint64_t a_p = smem_desc(sb + kOffP, 16, 1024, 2);
+      const uint32_t id_o = idesc_bf16(128, 32, 0, 1);  // A = P (tensor memory, 128 lanes x 8 columns per k-step), B = v (MN-major)
       // B, MN-major view of the 256 x 64-byte v tile: 32 channels = one 64-byte atom, 8 tokens = 512 B (SBO)
       const uint64_t b_v = smem_desc(sb + kOffStage + 2 * kTile16, 16, 512, 4);
       for (int n = 0; n < nitems; ++n) {
         const int u = n >> 1, s = u % kStages, buf = n & 1;
         if ((n & 1) == 0) mbar_wait_fast(bar_full(s), (u / kStages) & 1);
-        mbar_wait_fast(bar_staged, n & 1);
+        mbar_wait_fast(bar_p(buf), (n >> 1) & 1);
         tc_fence_after();
         if (elect_one()) {
           const uint64_t so = (uint64_t)((s * kStage) >> 4);
+          const uint32_t tb = tmem + 256 * buf;
 #pragma unroll
-          for (int ks = 0; ks < 16; ++ks)  // 16 keys per step: A += 32 B inside the swizzle atom (next panel every 4), B += 1 KB
-            umma_ss(tmem + 256 * buf, a_p + (uint64_t)((ks >> 2) * (kPanel >> 4) + 2 * (ks & 3)), b_v + so + (uint64_t)(64 * ks),
-                    id_o, ks > 0);
+          for (int ks = 0; ks < 16; ++ks)  // 16 keys per step: A = 8 columns of key quarter ks / 4, B += 1 KB
+            umma_ts(tb + kColO, tb + 64 * (ks >> 2) + 8 * (ks & 3), b_v + so + (uint64_t)(64 * ks), id_o, ks > 0);
           umma_commit(bar_o(buf));
-          umma_commit(bar_stfree);
         }
         __syncwarp();
       }
@@ -212,7 +203,7 @@ wattn_tc256_fwd_kernel(const __grid_constant__ FwdMaps maps, const float* __rest
       // ---------------------------------------------------------------- warp 3: TMA stores of o (written over the q tile)
       for (int u = 0; u < nunits; ++u) {
         const int s = u % kStages;
-        mbar_wait_fast(bar_written(s), (u / kStages) & 1);
+        mbar_wait_sleep(bar_written(s), (u / kStages) & 1, 128);
         const uint32_t src = sb + kOffStage + s * kStage;
         if (elect_one()) {
           const UnitGeo16 ug = geo[u & 3];
@@ -234,7 +225,7 @@ wattn_tc256_fwd_kernel(const __grid_constant__ FwdMaps maps, const float* __rest
     const float tau2 = __ldg(&tau[head]) * kLog2e;
     for (int u = 0; u < nunits; ++u) {
       const int s = u % kStages;
-      mbar_wait_fast(bar_full(s), (u / kStages) & 1);
+      mbar_wait_sleep(bar_full(s), (u / kStages) & 1, 128);
       const int widx = geo[u & 3].flags >> 2;
       float* vec = vecs + s * 512;
       float* sp = stats + p.plane + ((int64_t)widx * g.heads + head) * kN16;
@@ -274,8 +265,6 @@ wattn_tc256_fwd_kernel(const __grid_constant__ FwdMaps maps, const float* __rest
     const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16) + 64 * qt;
     const float kNeg = kMaskValue * kLog2e;
     const float* bt = reinterpret_cast<const float*>(smem + kOffBias);
-    const uint32_t p_row = sb + kOffP + qt * kPanel + t * 128;
-    const uint32_t swz = (uint32_t)(t & 7);
     float* hmx = reinterpret_cast<float*>(smem + kOffHmx);
 
     for (int n = 0; n < nitems; ++n) {
@@ -285,17 +274,18 @@ wattn_tc256_fwd_kernel(const __grid_constant__ FwdMaps maps, const float* __rest
       const float* vec = vecs + s * 512;
       const float ri = vec[128 * a + t];
       const float* cv = vec + 256 + 64 * qt;
-      // bias of key (jl, jw8) of the block: bp[-40 jl + jw8]
-      const float* bp = bt + (ih - 8 * (qt & 1) + 15) * kBiasStride16 + (15 - 8 * a - iw8 + 8 * (qt >> 1));
+      // bias of key (jl, jw8) of the block: run of 8 floats at bp - 40 jl (16-byte aligned through the alignment copies)
+      const float* bp = bias_run16(bt, (ih - 8 * (qt & 1) + 15) * kBiasStride16 + (15 - 8 * a - iw8 + 8 * (qt >> 1)));
       // shift mask: the whole quarter row sits on the other side of a wrap than the query, or none of it (warp-uniform)
       const bool masked = ((flags & 1) && ((ih >= 8) != ((qt & 1) != 0))) || ((flags & 2) && (a != (qt >> 1)));
       const float madd = masked ? kNeg : 0.f;
+      const float2 ri2 = make_float2(ri, ri);
       mbar_wait_fast(bar_s(buf), (n >> 1) & 1);
       tc_fence_after();
       const uint32_t tS = tl + 256 * buf;
       float mx = 0.f;
       if (use_max) {
-        mx = -3.0e38f;
+        float2 mx2 = make_float2(-3.0e38f, -3.0e38f);
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           uint32_t acc[32];
@@ -305,49 +295,61 @@ wattn_tc256_fwd_kernel(const __grid_constant__ FwdMaps maps, const float* __rest
           for (int r4 = 0; r4 < 4; ++r4) {
             const int jl = 4 * c + r4;
             const float4 c0 = *reinterpret_cast<const float4*>(cv + 8 * jl), c1 = *reinterpret_cast<const float4*>(cv + 8 * jl + 4);
-            const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+            const float4 b0 = *reinterpret_cast<const float4*>(bp - kBiasStride16 * jl), b1 = *reinterpret_cast<const float4*>(bp - kBiasStride16 * jl + 4);
+            const float2 cc[4] = {make_float2(c0.x, c0.y), make_float2(c0.z, c0.w), make_float2(c1.x, c1.y), make_float2(c1.z, c1.w)};
+            const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
 #pragma unroll
-            for (int e = 0; e < 8; ++e)
-              mx = fmaxf(mx, fmaf(__uint_as_float(acc[8 * r4 + e]) * ri, cc[e], bp[-kBiasStride16 * jl + e]));
+            for (int e = 0; e < 4; ++e) {
+              const float2 a2 = make_float2(__uint_as_float(acc[8 * r4 + 2 * e]), __uint_as_float(acc[8 * r4 + 2 * e + 1]));
+              const float2 x2 = f2fma(f2mul(a2, ri2), cc[e], bb[e]);
+              mx2.x = fmaxf(mx2.x, x2.x);
+              mx2.y = fmaxf(mx2.y, x2.y);
+            }
           }
         }
-        mx += madd;
+        mx = fmaxf(mx2.x, mx2.y) + madd;
         hmx[qt * 128 + t] = mx;
         asm volatile("bar.sync %0, 128;" ::"r"(1 + quad) : "memory");
         mx = fmaxf(fmaxf(hmx[t], hmx[128 + t]), fmaxf(hmx[256 + t], hmx[384 + t]));
         asm volatile("bar.sync %0, 128;" ::"r"(1 + quad) : "memory");  // all four owners have read before the next item writes
       }
       const float sub = madd - mx;
-      float ls = 0.f;
+      const float2 sub2 = make_float2(sub, sub);
+      float2 ls2 = make_float2(0.f, 0.f);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t acc[32];
         HV_TMEM_LD32(tS + 32 * c, acc);
         tmem_wait_ld();
-        if (c == 0 && n > 0) mbar_wait_fast(bar_stfree, (n - 1) & 1);  // the PV MMAs of the previous item have read the P tile
+        uint32_t pk[16];
 #pragma unroll
         for (int r4 = 0; r4 < 4; ++r4) {
           const int jl = 4 * c + r4;
           const float4 c0 = *reinterpret_cast<const float4*>(cv + 8 * jl), c1 = *reinterpret_cast<const float4*>(cv + 8 * jl + 4);
-          const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-          float pe[8];
+          const float4 b0 = *reinterpret_cast<const float4*>(bp - kBiasStride16 * jl), b1 = *reinterpret_cast<const float4*>(bp - kBiasStride16 * jl + 4);
+          const float2 cc[4] = {make_float2(c0.x, c0.y), make_float2(c0.z, c0.w), make_float2(c1.x, c1.y), make_float2(c1.z, c1.w)};
+          const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float x = fmaf(__uint_as_float(acc[8 * r4 + e]) * ri, cc[e], bp[-kBiasStride16 * jl + e]);
-            if (use_max || masked) x += sub;
-            pe[e] = ex2(x);
-            ls += pe[e];
+          for (int e = 0; e < 4; ++e) {
+            const float2 a2 = make_float2(__uint_as_float(acc[8 * r4 + 2 * e]), __uint_as_float(acc[8 * r4 + 2 * e + 1]));
+            float2 x2 = f2fma(f2mul(a2, ri2), cc[e], bb[e]);
+            if (use_max || masked) x2 = f2add(x2, sub2);
+            const float2 p2 = make_float2(ex2(x2.x), ex2(x2.y));
+            ls2 = f2add(ls2, p2);
+            pk[4 * r4 + e] = pack_bf16x2(p2.x, p2.y);
           }
-          sts128(p_row + (((uint32_t)jl ^ swz) << 4),
-                 make_uint4(pack_bf16x2(pe[0], pe[1]), pack_bf16x2(pe[2], pe[3]), pack_bf16x2(pe[4], pe[5]), pack_bf16x2(pe[6], pe[7])));
         }
+        // keys 32 c .. 32 c + 31 of the quarter as 16 packed pairs into columns 16 c .. of the quarter's own logit columns (both
+        // chunks land in logits the thread has already read)
+        HV_TMEM_ST16(tS + 16 * c, pk);
       }
+      const float ls = ls2.x + ls2.y;
       lsum[((n & 1) * 4 + qt) * 128 + t] = ls;
       if (qt == 0) mxv[(n & 1) * 128 + t] = off + mx;
+      tmem_wait_st();
       tc_fence_before();
-      fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_staged);
+      if (lane == 0) mbar_arrive(bar_p(buf));
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps: O from TMEM, normalise, write the row as
@@ -357,10 +359,10 @@ wattn_tc256_fwd_kernel(const __grid_constant__ FwdMaps maps, const float* __rest
     const uint32_t swz = (uint32_t)((t >> 1) & 3);
     for (int n = 0; n < nitems; ++n) {
       const int u = n >> 1, a = n & 1, s = u % kStages, buf = n & 1;
-      mbar_wait_fast(bar_o(buf), (n >> 1) & 1);
+      mbar_wait_sleep(bar_o(buf), (n >> 1) & 1, 64);
       tc_fence_after();
       uint32_t o[32];
-      HV_TMEM_LD32(tl + 256 * buf, o);
+      HV_TMEM_LD32(tl + 256 * buf + kColO, o);
       const float* lp = lsum + (n & 1) * 512 + t;
       const float l = (lp[0] + lp[128]) + (lp[256] + lp[384]);
       const float lse_off = mxv[(n & 1) * 128 + t];
