@@ -38,6 +38,25 @@ import torch  # noqa: E402
 
 METRIC = "swinv2_t_train_images_per_sec"
 WORKLOAD = "SwinV2-T full training step (fwd+bwd+SGD), 256x256 synthetic images, window 8, 10k-class head (BASELINE configs[1])"
+TIERS_B = (3, 13, 51, 273, 1103, 4884, 10000)  # iNat21 taxonomy tiers of the multitask head (reference hierarchy.py)
+# --config: the headline workload (default; what the driver runs) and BASELINE configs[3].  `stages`: attention launch tag ->
+# (C, heads, token grid side, window side) for the per-kernel accounting.
+CONFIGS = {
+    "swinv2_t": dict(metric=METRIC, workload=WORKLOAD, batch=256, classes=10000,
+                     ref=dict(img_size=256, window_size=8, embed_dim=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24], num_classes=10000),
+                     stages={"C96": (96, 3, 64, 8), "C192": (192, 6, 32, 8), "C384": (384, 12, 16, 8), "C768": (768, 24, 8, 8)}),
+    "swinv2_b": dict(metric="swinv2_b_w16_train_images_per_sec", batch=128, classes=TIERS_B,
+                     workload="SwinV2-B full training step (fwd+bwd+SGD), 256x256 synthetic images, window 16 (head dim 32), "
+                              "multitask taxonomy heads (7 tiers) (BASELINE configs[3])",
+                     ref=dict(img_size=256, window_size=16, embed_dim=128, depths=[2, 2, 18, 2], num_heads=[4, 8, 16, 32], num_classes=TIERS_B),
+                     stages={"C128": (128, 4, 64, 16), "C256": (256, 8, 32, 16), "C512": (512, 16, 16, 16), "C1024": (1024, 32, 8, 8)}),
+}
+
+
+def synth_labels(classes, batch, gen):
+    if isinstance(classes, int):
+        return torch.randint(0, classes, (batch,), generator=gen)
+    return torch.stack([torch.randint(0, n, (batch,), generator=gen) for n in classes], dim=1)
 
 
 def measured_peaks():
@@ -99,12 +118,15 @@ class ClockSampler:
         return out
 
 
-def build_model(device, drop_path_rate=0.1):
+def build_model(device, drop_path_rate=0.1, config="swinv2_t"):
     import hierarchical_vision_b200 as hv
     from hierarchical_vision_b200 import train as T
 
     torch.manual_seed(0)
-    backbone = hv.swinv2_tiny(num_classes=10000, img_size=256, window_size=8, drop_path_rate=drop_path_rate)
+    if config == "swinv2_b":
+        backbone = hv.swinv2_base(num_classes=TIERS_B, img_size=256, window_size=16, drop_path_rate=drop_path_rate)
+    else:
+        backbone = hv.swinv2_tiny(num_classes=10000, img_size=256, window_size=8, drop_path_rate=drop_path_rate)
     # the reference zero-inits every block's LayerNorm affine (swinv2.py:603-608), which turns each block into
     # the identity and zeroes all attention gradients: re-randomise so the step does real work
     with torch.no_grad():
@@ -136,7 +158,7 @@ def _timed_loop(one, seconds_budget, steps, warmup, max_steps=20):
     return times
 
 
-def cpu_baseline(seconds_budget=12.0, batch=8, steps=None, warmup=1):
+def cpu_baseline(seconds_budget=12.0, batch=8, steps=None, warmup=1, config="swinv2_t"):
     """The reference's CPU path on this box's host cores, on a bounded sample of the same workload: SwinV2-T
     fwd+bwd+SGD (img/s) and the BASELINE configs[0] block (windows/s).  kind "reference": the UNMODIFIED reference
     swinv2.py (oracle/_ref, placed by oracle/build_ref.py; /root/reference in the build container);
@@ -144,17 +166,21 @@ def cpu_baseline(seconds_budget=12.0, batch=8, steps=None, warmup=1):
     from oracle import ref_loader
     from oracle import swin_oracle as O
 
+    cfg = CONFIGS[config]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     g = torch.Generator().manual_seed(1)
     img = torch.randn(batch, 3, 256, 256, generator=g)
-    lab = torch.randint(0, 10000, (batch,), generator=g)
+    lab = synth_labels(cfg["classes"], batch, g)
+
+    def loss_of(out):  # plain cross entropy, or the weighted sum over taxonomy tiers (reference hierarchy.py:65-94)
+        return O.multitask_cross_entropy(list(out), lab) if isinstance(out, (list, tuple)) else torch.nn.functional.cross_entropy(out, lab)
+
     kind = "reference" if ref_loader.available() else "port"
     if kind == "reference":
         ref = ref_loader.load()
         torch.manual_seed(0)
-        net = ref.SwinTransformerV2(img_size=256, window_size=8, embed_dim=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24],
-                                    num_classes=10000, drop_path_rate=0.1)
+        net = ref.SwinTransformerV2(drop_path_rate=0.1, **cfg["ref"])
         with torch.no_grad():  # the reference zero-inits the blocks' LayerNorm affine (swinv2.py:603-608): make them work
             for layer in net.layers:
                 for blk in layer.blocks:
@@ -166,7 +192,7 @@ def cpu_baseline(seconds_budget=12.0, batch=8, steps=None, warmup=1):
 
         def one():
             opt.zero_grad(set_to_none=True)
-            loss = torch.nn.functional.cross_entropy(net(img), lab)
+            loss = loss_of(net(img))
             loss.backward()
             opt.step()
             return float(loss.detach())
@@ -185,13 +211,13 @@ def cpu_baseline(seconds_budget=12.0, batch=8, steps=None, warmup=1):
             xb.grad = None
             blk(xb).backward(gb)
     else:
-        spec = O.SWINV2_T
+        spec = O.SWINV2_B if config == "swinv2_b" else O.SWINV2_T
         p = {k: v.requires_grad_(True) for k, v in O.init_state(spec, seed=0).items()}
         opt = torch.optim.SGD(list(p.values()), lr=0.01, momentum=0.875, weight_decay=5e-4, nesterov=True)
 
         def one():
             opt.zero_grad(set_to_none=True)
-            loss = torch.nn.functional.cross_entropy(O.swin_model(img, p, spec), lab)
+            loss = loss_of(O.swin_model(img, p, spec))
             loss.backward()
             opt.step()
             return float(loss.detach())
@@ -201,11 +227,11 @@ def cpu_baseline(seconds_budget=12.0, batch=8, steps=None, warmup=1):
     times = _timed_loop(one, seconds_budget, steps, warmup)
     n, total = len(times), sum(times)
     out = {"value": batch * n / total, "unit": "img/s", "cores": cores, "kind": kind,
-           "sample": f"{n} steps of batch {batch} (fp32, SwinV2-T 256x256 fwd+bwd+SGD, "
+           "sample": f"{n} steps of batch {batch} (fp32, {'SwinV2-B window 16' if config == 'swinv2_b' else 'SwinV2-T'} 256x256 fwd+bwd+SGD, "
                      f"{'unmodified reference swinv2.py' if kind == 'reference' else 'oracle port'}, torch CPU ops, "
                      f"{torch.get_num_threads()} threads); best step {min(times) * 1e3:.0f} ms",
            "ms_per_step": total / n * 1e3, "steps": n, "batch": batch}
-    if one_block is not None:
+    if one_block is not None and config == "swinv2_t":
         bt = _timed_loop(one_block, 4.0, None, 1, max_steps=10)
         out["block_cfg0"] = {"windows_per_s_fwd_bwd": 512 * len(bt) / sum(bt), "best_windows_per_s": 512 / min(bt),
                              "sample": f"{len(bt)} x SwinTransformerBlock fwd+bwd (BASELINE configs[0]: batch 8, 64x64 "
@@ -217,11 +243,12 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    cb = cpu_baseline(batch=8, steps=max(args.steps, 1), warmup=max(args.warmup, 1))
-    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "img/s", "n_gpus": args.gpus,
+    cfg = CONFIGS[args.config]
+    cb = cpu_baseline(batch=8 if args.config == "swinv2_t" else 4, steps=max(args.steps, 1), warmup=max(args.warmup, 1), config=args.config)
+    line = {"impl": "reference", "metric": cfg["metric"], "value": cb["value"], "unit": "img/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "per_step_sample": "batch 8 on the host CPU",
+            "config": {"workload": cfg["workload"], "per_step_sample": f"batch {cb['batch']} on the host CPU",
                        "note": "the reference is pure Python/PyTorch with no GPU kernels of its own; its CPU path is "
                                "timed on all host threads -- the unmodified swinv2.py from oracle/_ref when present "
                                "(kind reference), else the oracle port"},
@@ -248,12 +275,13 @@ def run_ours(args):
     T.init_distributed("nccl", env)
     hv._lib.load()
 
-    B = args.batch
-    model = build_model(device)
+    cfg = CONFIGS[args.config]
+    B = args.batch if args.batch > 0 else cfg["batch"]
+    model = build_model(device, config=args.config)
     gen = torch.Generator().manual_seed(1234 + env.rank)
     n_host = 2
     host_img = [torch.randint(0, 256, (B, 3, 256, 256), dtype=torch.uint8, generator=gen).pin_memory() for _ in range(n_host)]
-    host_lab = [torch.randint(0, 10000, (B,), generator=gen).pin_memory() for _ in range(n_host)]
+    host_lab = [synth_labels(cfg["classes"], B, gen).pin_memory() for _ in range(n_host)]
     dev_img = [t.to(device) for t in host_img]
     dev_lab = [t.to(device) for t in host_lab]
 
@@ -357,18 +385,18 @@ def run_ours(args):
         d["ms"] += a.elapsed_time(b)
         d["launches"] += 1
         d["windows"] += windows
-    stage = {"C96": (96, 3, 64), "C192": (192, 6, 32), "C384": (384, 12, 16), "C768": (768, 24, 8)}  # C: heads, resolution
+    stage = cfg["stages"]  # tag -> C, heads, token grid side, window side
     tot_bytes = tot_ms = 0.0
     kernels = {}
     for tag, d in sorted(per_tag.items()):
         kind, cname, sname = tag.split("/")
         if cname not in stage:
             continue
-        C, heads, res = stage[cname]
+        C, heads, res, ws = stage[cname]
         shift = int(sname[1:])
         mult = 4 if kind == "attn_fwd" else 8
-        nbytes = d["windows"] * mult * 64 * C * 2
-        kernels[tag] = {"kernel": hvf.window_attention_kernel_name(B, res, res, C, heads, 8, shift, torch.bfloat16, kind == "attn_bwd"),
+        nbytes = d["windows"] * mult * ws * ws * C * 2
+        kernels[tag] = {"kernel": hvf.window_attention_kernel_name(B, res, res, C, heads, ws, shift, torch.bfloat16, kind == "attn_bwd"),
                         "launches": d["launches"], "ms_per_launch": d["ms"] / d["launches"], "ms_total": d["ms"],
                         "gbs": nbytes / d["ms"] / 1e6, "frac": nbytes / d["ms"] / 1e6 / peak}
         tot_bytes += nbytes
@@ -379,11 +407,11 @@ def run_ours(args):
     by_kernel = {}
     for tag, k in kernels.items():
         kind, cname, sname = tag.split("/")
-        C = stage[cname][0]
+        C, ws = stage[cname][0], stage[cname][3]
         agg = by_kernel.setdefault(k["kernel"], {"launches": 0, "ms_total": 0.0, "bytes": 0.0})
         agg["launches"] += k["launches"]
         agg["ms_total"] += k["ms_total"]
-        agg["bytes"] += per_tag[tag]["windows"] * (8 if kind == "attn_bwd" else 4) * 64 * C * 2
+        agg["bytes"] += per_tag[tag]["windows"] * (8 if kind == "attn_bwd" else 4) * ws * ws * C * 2
     for agg in by_kernel.values():
         agg["gbs"] = agg["bytes"] / agg["ms_total"] / 1e6
         agg["frac"] = agg["gbs"] / peak
@@ -392,7 +420,7 @@ def run_ours(args):
     if dom is not None:
         k = kernels[dom]
         kind, cname, sname = dom.split("/")
-        C, heads, res = stage[cname]
+        C, heads, res, ws = stage[cname]
         win_per_launch = per_tag[dom]["windows"] / per_tag[dom]["launches"]
         # DRAM traffic: not measurable inside this run (no profiler in a bench run); a committed `ncu --set full` capture of
         # the same kernel at the same shape, scaled per window, labelled as such
@@ -403,11 +431,11 @@ def run_ours(args):
             if rec:
                 traffic = rec["dram_bytes_per_window"] * win_per_launch
                 traffic_src = "static: " + rec.get("source", "ncu capture under profiles/")
-        roofline = {"bound": "hbm", "kernel": f"{k['kernel']} (stage {list(stage).index(cname)}: C {C}, {heads} heads, window 8, "
+        roofline = {"bound": "hbm", "kernel": f"{k['kernel']} (stage {list(stage).index(cname)}: C {C}, {heads} heads, window {ws}, "
                                               f"shift {sname[1:]}; {'backward' if kind == 'attn_bwd' else 'forward'})",
                     "achieved": k["gbs"], "peak": peak, "unit": "GB/s", "frac": k["frac"], "traffic": traffic,
                     "traffic_source": traffic_src, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": win_per_launch * (8 if kind == "attn_bwd" else 4) * 64 * C * 2,
+                    "algorithmic_bytes_per_launch": win_per_launch * (8 if kind == "attn_bwd" else 4) * ws * ws * C * 2,
                     "ms_per_launch": k["ms_per_launch"],
                     "selection": "the fused-attention launch with the largest duration in the step (CUDA events); "
                                  "per-kernel aggregates over all launch shapes under by_kernel",
@@ -422,15 +450,16 @@ def run_ours(args):
                               "(the timed region replays a CUDA graph of it)" % n_instr) if use_graph
                    else "CUDA events around each launch inside the timed region"}
 
-    cb = cpu_baseline() if (env.world_size == 1 and not args.no_cpu_baseline) else None
+    cb = (cpu_baseline(config=args.config, batch=8 if args.config == "swinv2_t" else 4)
+          if (env.world_size == 1 and not args.no_cpu_baseline) else None)
     if cb and "block_cfg0" in cb:
         window_attn["cpu_block_cfg0"] = cb["block_cfg0"]
     n = env.world_size
     imgs = B * n * args.steps
-    line = {"metric": METRIC, "value": imgs / (ms_total / 1e3), "unit": "img/s", "n_gpus": n, "steps": args.steps,
+    line = {"metric": cfg["metric"], "value": imgs / (ms_total / 1e3), "unit": "img/s", "n_gpus": n, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * n,
+            "config": {"workload": cfg["workload"], "per_gpu_batch": B, "global_batch": B * n,
                        "precision": "torch.autocast(bfloat16), fp32 master weights, bf16 activations",
                        "optimizer": "DecoupledSGDW (reference default) momentum 0.875 wd 5e-4, grad-clip 2.0, drop_path 0.1", "parallelism": f"dp{n}",
                        "e2e_input": ("every step copies its uint8 batch + labels from pinned host memory (side stream, overlapped "
@@ -455,7 +484,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (the eager step is host-launch-bound below ~200)")
+    ap.add_argument("--config", default="swinv2_t", choices=sorted(CONFIGS), help="swinv2_t: the headline workload (BASELINE configs[1]); "
+                    "swinv2_b: SwinV2-B at window 16 with the multitask heads (BASELINE configs[3])")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: 256 for swinv2_t, 128 for swinv2_b)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="one all-reduce after the backward instead of per-stage buckets inside it")
     ap.add_argument("--no-graph", action="store_true", help="eager step + DistributedDataParallel instead of the CUDA graph")
