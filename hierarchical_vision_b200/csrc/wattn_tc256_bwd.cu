@@ -123,7 +123,7 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
   auto bar_written = [&](int s) { return bar0 + 8 * (2 * kStages + s); };  // epilogues wrote dq, dk, dv over the tiles
   const uint32_t barx = bar0 + 8 * 3 * kStages;
   auto bar_sdp = [&](int b) { return barx + 8 * b; };            // S, dP accumulator buffer b complete
-  auto bar_sfree = [&](int b) { return barx + 8 * (2 + b); };    // ... and read by the softmax threads
+  auto bar_sdone = [&](int b) { return barx + 8 * (2 + b); };    // ... read by the softmax threads AND by the dQ MMAs (W' lives in its columns)
   const uint32_t bar_staged = barx + 8 * 4;                      // P, W, G' staging tiles written
   const uint32_t bar_stfree = barx + 8 * 5;                      // ... and read by the output MMAs
   auto bar_accq = [&](int a) { return barx + 8 * (6 + a); };     // dQ_a complete
@@ -145,7 +145,7 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_sdp(b), 1);
-      mbar_init(bar_sfree(b), 16);
+      mbar_init(bar_sdone(b), 1);
       mbar_init(bar_accq(b), 1);
       mbar_init(bar_accqfree(b), 4);
     }
@@ -216,7 +216,7 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
       for (int n = 0; n < nitems; ++n) {
         const int u = n >> 3, j = n & 7, a = j >> 2, b = j & 3, s = u % kStages, buf = n & 1;
         if (j == 0) mbar_wait_fast(bar_full(s), (u / kStages) & 1);
-        if (n > 1) mbar_wait_fast(bar_sfree(buf), ((n >> 1) - 1) & 1);  // the softmax threads have read item n-2 out of this buffer
+        if (n > 1) mbar_wait_fast(bar_sdone(buf), ((n >> 1) - 1) & 1);  // the dQ MMAs of item n-2 have read W' out of this buffer
         TRACE(n, 0);
         tc_fence_after();
         if (elect_one()) {
@@ -235,12 +235,12 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
     } else if (warp == 2) {
       // ---------------------------------------------------------------- issuer of dV, dK, dQ, dBias
       const uint32_t id_t = idesc_bf16(64, 32, 1, 1);    // A = P^T / W^T (MN-major), B = dO / q (MN-major)
-      const uint32_t id_q = idesc_bf16(128, 32, 0, 1);   // A = W (K-major), B = k (MN-major)
+      const uint32_t id_q = idesc_bf16(128, 32, 0, 1);   // A = W' (tensor memory), B = k (MN-major)
       const uint32_t id_b = idesc_bf16(128, 32, 0, 0);   // A = G' (K-major), B = T^T (K-major)
       // A, MN-major view of a [query][key] tile: 64 keys = one 128-byte atom, 8 queries = 1 KB (SBO)
       const uint64_t a_pt = smem_desc(sb + kOffP, 16, 1024, 2), a_wt = smem_desc(sb + kOffW, 16, 1024, 2);
       // A, K-major view: rows of 128 B, 8-row groups 1 KB apart
-      const uint64_t a_w = smem_desc(sb + kOffW, 16, 1024, 2), a_g = smem_desc(sb + kOffG, 16, 1024, 2);
+      const uint64_t a_g = smem_desc(sb + kOffG, 16, 1024, 2);
       const uint64_t b_tt = smem_desc(sb + kOffTT, 16, 1024, 2);
       // B, MN-major view of a 256 x 64-byte tile: 32 channels = one 64-byte atom, 8 tokens = 512 B (SBO)
       const uint64_t b_q = smem_desc(sb + kOffStage, 16, 512, 4), b_k = smem_desc(sb + kOffStage + kTile16, 16, 512, 4);
@@ -256,6 +256,15 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
         if (elect_one()) {
           const uint64_t so = (uint64_t)((s * kStage) >> 4), ao = (uint64_t)(a * 512), bo = (uint64_t)(b * 256);
           const uint32_t dl = (uint32_t)(16 * (b & 1)) << 16;
+          // dQ first: its A operand is the W' the softmax threads wrote over the item's S columns, and the S / dP issuer may
+          // reuse that buffer as soon as these four MMAs are done
+          if (!KO(1)) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)  // 16 keys per step: A = 8 TMEM columns of the key quarter ks, B += 1 KB
+            umma_ts(tmem + kColDQ + 32 * a, tmem + kColS + 64 * (n & 1) + 16 * ks, b_k + so + bo + (uint64_t)(64 * ks), id_q,
+                    (b > 0 || ks > 0) ? 1u : 0u);
+          }
+          umma_commit(bar_sdone(n & 1));
           if (!KO(1)) {
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)  // 16 queries per step: A += 2 KB, B += 1 KB
@@ -265,10 +274,6 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
           for (int ks = 0; ks < 8; ++ks)
             umma_ss(tmem + dl + kColDK + 32 * (b >> 1), a_wt + (uint64_t)(128 * ks), b_q + so + ao + (uint64_t)(64 * ks), id_t,
                     (a > 0 || ks > 0) ? 1u : 0u);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks)  // 16 keys per step: A += 32 B inside the swizzle atom, B += 1 KB
-            umma_ss(tmem + kColDQ + 32 * a, a_w + (uint64_t)(2 * ks), b_k + so + bo + (uint64_t)(64 * ks), id_q,
-                    (b > 0 || ks > 0) ? 1u : 0u);
           // d(bias): column offset dx = 8 (a - pb) + iw8 - jw8 lands in accumulator column dx + 15 when the B rows start at
           // row 8 - 8 (a - pb) of T^T (8 rows = one 1 KB swizzle atom)
           const uint64_t to = (uint64_t)((8 - 8 * (a - (b >> 1))) * 128 >> 4);
@@ -350,9 +355,6 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
       HV_TMEM_LD16(tl + kColS + 64 * buf, sa);
       HV_TMEM_LD16(tl + kColDP + 64 * buf, pa);
       tmem_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_sfree(buf));
       if (warp == 4) TRACE(n, 3);
       // per pair of keys (packed fp32): rc = r_i c_j, t = s rc (tau log2e cos), P = exp2(t + bias - lse), pd = P dP,
       // g = pd - D P, W' = g rc (the epilogues apply ln 2); sums of pd, pd t, P t for d(tau) and the dq projection
@@ -387,6 +389,9 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
           gk[4 * r + e] = pack_bf16x2(g2.x, g2.y);
         }
       }
+      // W' also goes back to tensor memory, over the first 8 of this thread's own 16 logit columns: the A operand of dQ += W' K
+      // is read from there (an A tile in shared memory costs 4 KB of operand fetch per k-step, one in TMEM none)
+      HV_TMEM_ST8(tl + kColS + 64 * buf, wk);
       if (warp == 4) TRACE(n, 4);
       if (n > 0) mbar_wait_fast(bar_stfree, (n - 1) & 1);  // the output MMAs of the previous item have read the staging tiles
       if (warp == 4) TRACE(n, 5);
@@ -408,6 +413,8 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
         ar[1024] = dp_acc.x + dp_acc.y;
       }
       fence_async_smem();
+      tmem_wait_st();
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_staged);
       if (warp == 4) TRACE(n, 6);

@@ -316,32 +316,36 @@ wattn_tc256_fwd_kernel(const __grid_constant__ FwdMaps maps, const float* __rest
       const float sub = madd - mx;
       const float2 sub2 = make_float2(sub, sub);
       float2 ls2 = make_float2(0.f, 0.f);
+      // four chunks of 16 keys (two window rows), software-pipelined: the tcgen05.ld of chunk c + 1 is in flight while chunk c
+      // is exponentiated; its 8 packed pairs go back into columns 8 c .. of the quarter (logits already in registers)
+      uint32_t accs[2][16];
+      HV_TMEM_LD16(tS, accs[0]);
+      tmem_wait_ld();
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t acc[32];
-        HV_TMEM_LD32(tS + 32 * c, acc);
-        tmem_wait_ld();
-        uint32_t pk[16];
+      for (int c = 0; c < 4; ++c) {
+        uint32_t (&acc)[16] = accs[c & 1];
+        HV_REG_FENCE16(acc);
+        if (c < 3) HV_TMEM_LD16(tS + 16 * (c + 1), accs[(c + 1) & 1]);
+        uint32_t pk[8];
 #pragma unroll
-        for (int r4 = 0; r4 < 4; ++r4) {
-          const int jl = 4 * c + r4;
+        for (int r2 = 0; r2 < 2; ++r2) {
+          const int jl = 2 * c + r2;
           const float4 c0 = *reinterpret_cast<const float4*>(cv + 8 * jl), c1 = *reinterpret_cast<const float4*>(cv + 8 * jl + 4);
           const float4 b0 = *reinterpret_cast<const float4*>(bp - kBiasStride16 * jl), b1 = *reinterpret_cast<const float4*>(bp - kBiasStride16 * jl + 4);
           const float2 cc[4] = {make_float2(c0.x, c0.y), make_float2(c0.z, c0.w), make_float2(c1.x, c1.y), make_float2(c1.z, c1.w)};
           const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float2 a2 = make_float2(__uint_as_float(acc[8 * r4 + 2 * e]), __uint_as_float(acc[8 * r4 + 2 * e + 1]));
+            const float2 a2 = make_float2(__uint_as_float(acc[8 * r2 + 2 * e]), __uint_as_float(acc[8 * r2 + 2 * e + 1]));
             float2 x2 = f2fma(f2mul(a2, ri2), cc[e], bb[e]);
             if (use_max || masked) x2 = f2add(x2, sub2);
             const float2 p2 = make_float2(ex2(x2.x), ex2(x2.y));
             ls2 = f2add(ls2, p2);
-            pk[4 * r4 + e] = pack_bf16x2(p2.x, p2.y);
+            pk[4 * r2 + e] = pack_bf16x2(p2.x, p2.y);
           }
         }
-        // keys 32 c .. 32 c + 31 of the quarter as 16 packed pairs into columns 16 c .. of the quarter's own logit columns (both
-        // chunks land in logits the thread has already read)
-        HV_TMEM_ST16(tS + 16 * c, pk);
+        HV_TMEM_ST8(tS + 8 * c, pk);
+        if (c < 3) tmem_wait_ld();
       }
       const float ls = ls2.x + ls2.y;
       lsum[((n & 1) * 4 + qt) * 128 + t] = ls;
