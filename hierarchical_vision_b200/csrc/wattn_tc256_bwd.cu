@@ -52,7 +52,7 @@ constexpr int kOffArow = kOffVec + kStages * 4 * 256 * 4;
 constexpr int kOffGeo = kOffArow + 2 * 3 * 4 * 128 * 4;    // [4] UnitGeo16
 constexpr int kOffMisc = kOffGeo + 4 * 16;                 // d(tau) partial
 constexpr int kOffBar = kOffMisc + 16;
-constexpr int kNumBars = 3 * kStages + 12;
+constexpr int kNumBars = 3 * kStages + 15;
 constexpr int kOffTmem = kOffBar + kNumBars * 8;
 constexpr int kSmem = kOffTmem + 16;
 static_assert(kOffP % 1024 == 0 && kOffTT % 1024 == 0 && kOffBias % 16 == 0 && kOffVec % 16 == 0 && kOffBar % 8 == 0, "shared-memory alignment");
@@ -125,7 +125,7 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
   auto bar_sdp = [&](int b) { return barx + 8 * b; };            // S, dP accumulator buffer b complete
   auto bar_sdone = [&](int b) { return barx + 8 * (2 + b); };    // ... read by the softmax threads AND by the dQ MMAs (W' lives in its columns)
   const uint32_t bar_staged = barx + 8 * 4;                      // P, W, G' staging tiles written
-  const uint32_t bar_stfree = barx + 8 * 5;                      // ... and read by the output MMAs
+  auto bar_stfree = [&](int k) { return barx + 8 * (12 + k); };  // ... and read by the output MMAs: 0 P (dV), 1 W (dK), 2 G' (dBias)
   auto bar_accq = [&](int a) { return barx + 8 * (6 + a); };     // dQ_a complete
   auto bar_accqfree = [&](int a) { return barx + 8 * (8 + a); }; // ... and pulled out of TMEM
   const uint32_t bar_acckv = barx + 8 * 10;                      // dV, dK of the unit complete
@@ -150,7 +150,7 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
       mbar_init(bar_accqfree(b), 4);
     }
     mbar_init(bar_staged, 16);
-    mbar_init(bar_stfree, 1);
+    for (int k = 0; k < 3; ++k) mbar_init(bar_stfree(k), 1);
     mbar_init(bar_acckv, 1);
     mbar_init(bar_acckvfree, 4);
     misc[0] = 0.f;
@@ -270,10 +270,16 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
           for (int ks = 0; ks < 8; ++ks)  // 16 queries per step: A += 2 KB, B += 1 KB
             umma_ss(tmem + dl + kColDV + 32 * (b >> 1), a_pt + (uint64_t)(128 * ks), b_g + so + ao + (uint64_t)(64 * ks), id_t,
                     (a > 0 || ks > 0) ? 1u : 0u);
+          }
+          umma_commit(bar_stfree(0));  // each staging tile is handed back as soon as its own MMAs are done
+          if (!KO(1)) {
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
             umma_ss(tmem + dl + kColDK + 32 * (b >> 1), a_wt + (uint64_t)(128 * ks), b_q + so + ao + (uint64_t)(64 * ks), id_t,
                     (a > 0 || ks > 0) ? 1u : 0u);
+          }
+          umma_commit(bar_stfree(1));
+          if (!KO(1)) {
           // d(bias): column offset dx = 8 (a - pb) + iw8 - jw8 lands in accumulator column dx + 15 when the B rows start at
           // row 8 - 8 (a - pb) of T^T (8 rows = one 1 KB swizzle atom)
           const uint64_t to = (uint64_t)((8 - 8 * (a - (b >> 1))) * 128 >> 4);
@@ -284,7 +290,7 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
                     (n > 1 || ks > 0) ? 1u : 0u);
           }
           }
-          umma_commit(bar_stfree);
+          umma_commit(bar_stfree(2));
           if (b == 3) umma_commit(bar_accq(a));
           if (j == 7) umma_commit(bar_acckv);
           TRACE(n, 9);
@@ -393,18 +399,25 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
       // is read from there (an A tile in shared memory costs 4 KB of operand fetch per k-step, one in TMEM none)
       HV_TMEM_ST8(tl + kColS + 64 * buf, wk);
       if (warp == 4) TRACE(n, 4);
-      if (n > 0) mbar_wait_fast(bar_stfree, (n - 1) & 1);  // the output MMAs of the previous item have read the staging tiles
+      if (n > 0) mbar_wait_fast(bar_stfree(0), (n - 1) & 1);  // the dV MMAs of the previous item have read the P tile
       if (warp == 4) TRACE(n, 5);
       if (!KO(4)) {
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const uint32_t jl = (uint32_t)(2 * qt + r);
-        sts128(p_row + ((jl ^ swz) << 4), make_uint4(pk[4 * r], pk[4 * r + 1], pk[4 * r + 2], pk[4 * r + 3]));
-        sts128(w_row + ((jl ^ swz) << 4), make_uint4(wk[4 * r], wk[4 * r + 1], wk[4 * r + 2], wk[4 * r + 3]));
-        // G': row (ih, jl), 16-byte chunk iw8 = the eight key columns of this key row
-        const uint32_t R = (uint32_t)(ih * 8) + jl;
-        if (!KO(16)) sts128(sb + kOffG + R * 128 + ((((uint32_t)iw8) ^ (R & 7)) << 4), make_uint4(gk[4 * r], gk[4 * r + 1], gk[4 * r + 2], gk[4 * r + 3]));
-      }
+        const uint32_t j0 = (uint32_t)(2 * qt), j1 = j0 + 1;
+        sts128(p_row + ((j0 ^ swz) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+        sts128(p_row + ((j1 ^ swz) << 4), make_uint4(pk[4], pk[5], pk[6], pk[7]));
+        if (n > 0) mbar_wait_fast(bar_stfree(1), (n - 1) & 1);  // ... the dK MMAs the W tile
+        sts128(w_row + ((j0 ^ swz) << 4), make_uint4(wk[0], wk[1], wk[2], wk[3]));
+        sts128(w_row + ((j1 ^ swz) << 4), make_uint4(wk[4], wk[5], wk[6], wk[7]));
+        if (n > 0) mbar_wait_fast(bar_stfree(2), (n - 1) & 1);  // ... the d(bias) MMAs the G' tile
+        if (!KO(16)) {
+          // G': row (ih, jl), 16-byte chunk iw8 = the eight key columns of this key row
+          const uint32_t R0 = (uint32_t)(ih * 8) + j0, R1 = R0 + 1;
+          sts128(sb + kOffG + R0 * 128 + ((((uint32_t)iw8) ^ (R0 & 7)) << 4), make_uint4(gk[0], gk[1], gk[2], gk[3]));
+          sts128(sb + kOffG + R1 * 128 + ((((uint32_t)iw8) ^ (R1 & 7)) << 4), make_uint4(gk[4], gk[5], gk[6], gk[7]));
+        }
+      } else if (n > 0) {
+        mbar_wait_fast(bar_stfree(1), (n - 1) & 1);
+        mbar_wait_fast(bar_stfree(2), (n - 1) & 1);
       }
       if (b == 3) {
         float* ar = arow + a * 1536 + qt * 128 + t;
