@@ -23,24 +23,30 @@ constexpr int kTile16 = kN16 * 64;        // one (window, head) q / k / v / dO t
 constexpr int kBiasStride16 = 40;         // floats per table row (a multiple of 4: the alignment of a run does not depend on the row)
 // Four ALIGNMENT COPIES of the table, copy c shifted by c floats: a thread reads runs of 8 consecutive entries starting at
 // a column whose residue mod 4 is fixed by its query column, picks the copy that makes the run 16-byte aligned, and loads
-// it as two float4.  Copy stride = 8 (mod 32) floats so that the 8 lanes of a quarter warp hit 8 different bank groups.
-constexpr int kBiasCopy16 = 1256;
-constexpr int kBiasFloats16 = 4 * kBiasCopy16;
+// it as two float4.  The 8 lanes of a quarter warp (one window row of queries, columns 0 .. 7) then read the runs
+// (copy, start) = (1, U) (2, U) (3, U) (0, U - 4) (1, U - 4) (2, U - 4) (3, U - 4) (0, U - 8): with the copies based at 0, 4,
+// 12, 20 (mod 32) floats the eight float4 fall into eight different 4-bank groups -- a uniform copy stride cannot do that
+// (measured: 2-way conflicts on every load with a stride of 8 mod 32).
+constexpr int kBiasCopyLen16 = kTab16 * kBiasStride16 + 4;  // entries of one copy, shift included
+__host__ __device__ constexpr int bias_copy_base16(int c) { return c * 1248 + (c == 0 ? 0 : 8 * c - 4); }
+constexpr int kBiasFloats16 = bias_copy_base16(3) + kBiasCopyLen16 + 12;
+static_assert(kBiasFloats16 % 4 == 0, "bias copies end on a 16-byte boundary");
 
 // fill the alignment copies: entry (dy, x) = scale * table[(dy, 30 - x), head] - off, dy = ih - jh + 15, x = 15 - iw + jw
 // (REVERSED column, so the 8 keys of a window row are 8 consecutive floats)
 __device__ __forceinline__ void fill_bias16(float* bt, const float* __restrict__ bias_table, int heads, int head, float scale,
                                             float off, int tid, int nthreads) {
-  for (int idx = tid; idx < kBiasFloats16; idx += nthreads) {
-    const int c = idx / kBiasCopy16, j = idx - c * kBiasCopy16 - c;  // copy_c[j + c] = table entry j
+  for (int idx = tid; idx < 4 * kBiasCopyLen16; idx += nthreads) {
+    const int c = idx / kBiasCopyLen16, pos = idx - c * kBiasCopyLen16, j = pos - c;  // copy_c[j + c] = table entry j
     const int dy = j / kBiasStride16, x = j - dy * kBiasStride16;
-    bt[idx] = (j >= 0 && dy < kTab16 && x < kTab16) ? scale * __ldg(&bias_table[(dy * kTab16 + 30 - x) * heads + head]) - off : 0.f;
+    bt[bias_copy_base16(c) + pos] =
+        (j >= 0 && dy < kTab16 && x < kTab16) ? scale * __ldg(&bias_table[(dy * kTab16 + 30 - x) * heads + head]) - off : 0.f;
   }
 }
 // pointer to the aligned run that holds table entries i0 .. i0 + 7 (i0 = dy * 40 + x0)
 __device__ __forceinline__ const float* bias_run16(const float* bt, int i0) {
   const int c = (4 - (i0 & 3)) & 3;
-  return bt + c * kBiasCopy16 + i0 + c;
+  return bt + bias_copy_base16(c) + i0 + c;
 }
 
 // Waits of warps that are NOT on the critical path (producer, store warp, epilogues): poll with a real sleep between
