@@ -156,7 +156,7 @@ int hv_window_attn_tc256_variant(int variant) {
 int hv_window_attn_kernel_kind(int C, int heads, int ws, int dtype) {
   if (heads <= 0 || C % heads) return 0;
   Geom g = make_geom(1, ws, ws, C, heads, ws, 0);
-  return wattn_mma64_supported(g, dtype) ? 1 : 0;
+  return (wattn_mma64_supported(g, dtype) || wattn_tc256_supported(g, dtype)) ? 1 : 0;
 }
 
 size_t hv_window_attn_stats_floats(int B, int H, int W, int C, int heads, int ws, int dtype) {

@@ -38,6 +38,8 @@ __global__ void __launch_bounds__(kHidMax) cpb_rows_kernel(const float* __restri
 
 // 32 hidden units per CTA, 8 row chunks per unit (thread = unit x chunk): every thread accumulates dW2[:, j],
 // dW1[j, :], db1[j] over its rows in registers, the 8 partials are summed through shared memory in a fixed order.
+// gridDim.y > 1 splits the table rows between CTAs (the 961-row table of a 16 x 16 window is a 120-step serial chain per
+// thread otherwise, 80 us on 16 SMs): the CTAs then accumulate into the zeroed outputs with fp32 atomics.
 constexpr int kChunks = 8;
 __global__ void __launch_bounds__(32 * kChunks) cpb_bwd_hidden_kernel(const float* __restrict__ coords, const float* __restrict__ w1,
                                                                        const float* __restrict__ b1, const float* __restrict__ w2,
@@ -48,11 +50,13 @@ __global__ void __launch_bounds__(32 * kChunks) cpb_bwd_hidden_kernel(const floa
   // of ~700 dependent L2 loads per thread, 21 us for this tiny kernel), then the partial sums of the row chunks
   __shared__ float buf[kChunks * (kHeadsMax + 3) * 32];
   float (*part)[kHeadsMax + 3][32] = reinterpret_cast<float (*)[kHeadsMax + 3][32]>(buf);
-  const bool staged = M * heads <= kChunks * (kHeadsMax + 3) * 32;
+  const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const int r_begin = blockIdx.y * rows_per, r_end = min(M, r_begin + rows_per);
+  const bool staged = rows_per * heads <= kChunks * (kHeadsMax + 3) * 32;
   if (staged)
-    for (int i = threadIdx.x; i < M * heads; i += 32 * kChunks) buf[i] = __ldg(&dz[i]);
+    for (int i = threadIdx.x; i < (r_end - r_begin) * heads; i += 32 * kChunks) buf[i] = __ldg(&dz[r_begin * heads + i]);
   __syncthreads();
-  const float* dzs = staged ? buf : dz;
+  const float* dzs = staged ? buf - r_begin * heads : dz;
   const int jl = threadIdx.x & 31, rc = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + jl;
   const bool live = j < hid;
@@ -64,7 +68,7 @@ __global__ void __launch_bounds__(32 * kChunks) cpb_bwd_hidden_kernel(const floa
     g2[h] = 0.f;
   }
   float ga = 0.f, gb = 0.f, gbias = 0.f;
-  for (int r = rc; r < M; r += kChunks) {
+  for (int r = r_begin + rc; r < r_end; r += kChunks) {
     const float c0 = __ldg(&coords[2 * r]), c1 = __ldg(&coords[2 * r + 1]);
     const float pre = fmaf(wa, c0, fmaf(wb, c1, bb));
     const float a = fmaxf(pre, 0.f);
@@ -96,10 +100,14 @@ __global__ void __launch_bounds__(32 * kChunks) cpb_bwd_hidden_kernel(const floa
 #pragma unroll
     for (int c = 0; c < kChunks; ++c) sum += part[c][slot][jl];
     if (!live) continue;
-    if (slot < kHeadsMax) { if (slot < heads) dw2[slot * hid + j] = sum; }
-    else if (slot == kHeadsMax) dw1[2 * j] = sum;
-    else if (slot == kHeadsMax + 1) dw1[2 * j + 1] = sum;
-    else db1[j] = sum;
+    float* dst = nullptr;
+    if (slot < kHeadsMax) { if (slot < heads) dst = &dw2[slot * hid + j]; }
+    else if (slot == kHeadsMax) dst = &dw1[2 * j];
+    else if (slot == kHeadsMax + 1) dst = &dw1[2 * j + 1];
+    else dst = &db1[j];
+    if (dst == nullptr) continue;
+    if (gridDim.y == 1) *dst = sum;
+    else atomicAdd(dst, sum);
   }
 }
 
@@ -126,7 +134,13 @@ int cpb_bias_bwd(const float* coords, const float* w1, const float* b1, const fl
   if (rc) return rc;
   cpb_rows_kernel<1><<<M, hid, 0, st>>>(coords, w1, b1, w2, dtable, workspace, hid, heads);
   HV_LAUNCH_OK("cpb_rows_kernel<1>");
-  cpb_bwd_hidden_kernel<<<(hid + 31) / 32, 32 * kChunks, 0, st>>>(coords, w1, b1, w2, workspace, dw1, db1, dw2, M, hid, heads);
+  const int splits = M >= 512 ? 8 : 1;  // the (2 * 16 - 1)^2 table of 16 x 16 windows
+  if (splits > 1) {
+    HV_CUDA_OK(cudaMemsetAsync(dw1, 0, sizeof(float) * 2 * hid, st));
+    HV_CUDA_OK(cudaMemsetAsync(db1, 0, sizeof(float) * hid, st));
+    HV_CUDA_OK(cudaMemsetAsync(dw2, 0, sizeof(float) * heads * hid, st));
+  }
+  cpb_bwd_hidden_kernel<<<dim3((hid + 31) / 32, splits), 32 * kChunks, 0, st>>>(coords, w1, b1, w2, workspace, dw1, db1, dw2, M, hid, heads);
   HV_LAUNCH_OK("cpb_bwd_hidden_kernel");
   return HV_OK;
 }

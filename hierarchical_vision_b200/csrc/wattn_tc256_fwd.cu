@@ -286,26 +286,30 @@ wattn_tc256_fwd_kernel(const __grid_constant__ FwdMaps maps, const float* __rest
       float mx = 0.f;
       if (use_max) {
         float2 mx2 = make_float2(-3.0e38f, -3.0e38f);
+        uint32_t accm[2][16];
+        HV_TMEM_LD16(tS, accm[0]);
+        tmem_wait_ld();
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t acc[32];
-          HV_TMEM_LD32(tS + 32 * c, acc);
-          tmem_wait_ld();
+        for (int c = 0; c < 4; ++c) {  // same software pipeline as the exponentiation pass below
+          uint32_t (&acc)[16] = accm[c & 1];
+          HV_REG_FENCE16(acc);
+          if (c < 3) HV_TMEM_LD16(tS + 16 * (c + 1), accm[(c + 1) & 1]);
 #pragma unroll
-          for (int r4 = 0; r4 < 4; ++r4) {
-            const int jl = 4 * c + r4;
+          for (int r2 = 0; r2 < 2; ++r2) {
+            const int jl = 2 * c + r2;
             const float4 c0 = *reinterpret_cast<const float4*>(cv + 8 * jl), c1 = *reinterpret_cast<const float4*>(cv + 8 * jl + 4);
             const float4 b0 = *reinterpret_cast<const float4*>(bp - kBiasStride16 * jl), b1 = *reinterpret_cast<const float4*>(bp - kBiasStride16 * jl + 4);
             const float2 cc[4] = {make_float2(c0.x, c0.y), make_float2(c0.z, c0.w), make_float2(c1.x, c1.y), make_float2(c1.z, c1.w)};
             const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float2 a2 = make_float2(__uint_as_float(acc[8 * r4 + 2 * e]), __uint_as_float(acc[8 * r4 + 2 * e + 1]));
+              const float2 a2 = make_float2(__uint_as_float(acc[8 * r2 + 2 * e]), __uint_as_float(acc[8 * r2 + 2 * e + 1]));
               const float2 x2 = f2fma(f2mul(a2, ri2), cc[e], bb[e]);
               mx2.x = fmaxf(mx2.x, x2.x);
               mx2.y = fmaxf(mx2.y, x2.y);
             }
           }
+          if (c < 3) tmem_wait_ld();
         }
         mx = fmaxf(mx2.x, mx2.y) + madd;
         hmx[qt * 128 + t] = mx;

@@ -54,8 +54,9 @@ HV_API int hv_abi_version(void);
 HV_API const char* hv_last_error(void);
 /* 100 when built for sm_100a */
 HV_API int hv_compiled_arch(void);
-/* Which attention kernel a geometry dispatches to: 0 = generic CUDA-core kernel,
- * 1 = tensor-core kernel (N=64, head dim 32, bf16).  Host-only query. */
+/* Which attention kernel family a geometry dispatches to: 0 = generic CUDA-core kernel, 1 = tensor-core kernels (bf16,
+ * head dim 32, window 8 (N = 64) or window 16 (N = 256)).  For kind 1 the module wraps the qkv Linear and the attention in
+ * one autograd node and takes d(q_bias) from hv_dq_colsum.  Host-only query. */
 HV_API int hv_window_attn_kernel_kind(int C, int heads, int ws, int dtype);
 
 /* Forward kernel of the tensor-core path (kind 1): 0 = mma.sync + cp.async kernel, 1 = tcgen05 / TMEM / TMA kernels (the

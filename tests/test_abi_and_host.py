@@ -94,12 +94,14 @@ def test_bad_arguments_return_codes_not_crashes(lib):
 
 
 def test_kernel_kind_dispatch(lib):
-    # bf16, N=64, head dim 32 -> tensor-core kernel; everything else -> generic kernel
+    # bf16, head dim 32, window 8 (N = 64) or 16 (N = 256) -> tensor-core kernels; everything else -> generic kernel
     assert lib.hv_window_attn_kernel_kind(96, 3, 8, _lib.HV_BF16) == 1
     assert lib.hv_window_attn_kernel_kind(768, 24, 8, _lib.HV_BF16) == 1
     assert lib.hv_window_attn_kernel_kind(96, 3, 7, _lib.HV_BF16) == 0
     assert lib.hv_window_attn_kernel_kind(96, 3, 8, _lib.HV_F32) == 0
-    assert lib.hv_window_attn_kernel_kind(128, 4, 16, _lib.HV_BF16) == 0
+    assert lib.hv_window_attn_kernel_kind(128, 4, 16, _lib.HV_BF16) == 1
+    assert lib.hv_window_attn_kernel_kind(128, 2, 16, _lib.HV_BF16) == 0  # head dim 64
+    assert lib.hv_window_attn_kernel_kind(128, 4, 16, _lib.HV_F32) == 0
     assert lib.hv_window_attn_kernel_kind(128, 2, 8, _lib.HV_BF16) == 0  # head dim 64
 
 
