@@ -1,5 +1,5 @@
 """Kernel-time breakdown of one training step via torch.profiler (CUPTI), far cheaper than an ncu launch list.
-    python tools/step_profile.py --batch 256 --steps 3"""
+    python tools/step_profile.py [--config swinv2_b] [--batch 256] --steps 3"""
 import argparse
 import os
 import re
@@ -14,15 +14,18 @@ import bench  # noqa: E402
 from hierarchical_vision_b200 import train as T  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--batch", type=int, default=256)
+ap.add_argument("--config", default="swinv2_t", choices=sorted(bench.CONFIGS))
+ap.add_argument("--batch", type=int, default=0)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--top", type=int, default=45)
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
-model = bench.build_model(dev)
+cfg = bench.CONFIGS[a.config]
+a.batch = a.batch or cfg["batch"]
+model = bench.build_model(dev, config=a.config)
 opt = T.build_optimizer(model, lr=0.05)
 img = torch.randint(0, 256, (a.batch, 3, 256, 256), dtype=torch.uint8, device=dev)
-lab = torch.randint(0, 10000, (a.batch,), device=dev)
+lab = bench.synth_labels(cfg["classes"], a.batch, torch.Generator().manual_seed(0)).to(dev)
 step = lambda: T.train_step(model, opt, (img, lab), autocast_dtype=torch.bfloat16, clip_norm=2.0)
 for _ in range(3):
     step()
