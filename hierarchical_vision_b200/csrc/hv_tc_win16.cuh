@@ -49,9 +49,11 @@ __device__ __forceinline__ const float* bias_run16(const float* bt, int i0) {
   return bt + bias_copy_base16(c) + i0 + c;
 }
 
-// Waits of warps that are NOT on the critical path (producer, store warp, epilogues): poll with a real sleep between
-// attempts -- a tight try_wait loop of a dozen waiting warps takes a third of the issue slots from the softmax warps
+// Wait with a real sleep between polls (ns = 0: the plain try_wait loop).  An experiment switch: a dozen waiting warps in
+// tight try_wait loops execute a third of the kernel's instructions, but letting the off-path warps (producer, store warp,
+// epilogues) sleep 64-1000 ns between polls made both N = 256 kernels 3-4 % SLOWER (late wake-ups), so the kernels pass 0
 __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, uint32_t ns) {
+  if (ns == 0) { mbar_wait_fast(bar, parity); return; }
   uint32_t spins = 0;
   while (!mbar_test(bar, parity)) {
     asm volatile("nanosleep.u32 %0;" ::"r"(ns));

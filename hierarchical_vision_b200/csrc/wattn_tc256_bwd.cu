@@ -70,6 +70,21 @@ struct BwdParams {
   int ko;  // HV_TC256_KO builds only: knock-out bits for timing experiments (results are wrong)
   long long* trace;  // HV_TC256_TRACE builds only
 };
+// sleep (ns) between polls of the warps that wait for long, off the critical path; 0 = tight try_wait loop.  Measured at the
+// SwinV2-B stage-0 shape: no sleeps 0.656 ms, 256 / 128 / 128 ns 0.682, 1000 / 500 / 300 ns 0.679, issuers at 40-100 ns 0.69:
+// the wake-up latency costs more than the issue slots the polls take
+#ifndef HV_SLEEP_PROD
+#define HV_SLEEP_PROD 0
+#endif
+#ifndef HV_SLEEP_STORE
+#define HV_SLEEP_STORE 0
+#endif
+#ifndef HV_SLEEP_EPI
+#define HV_SLEEP_EPI 0
+#endif
+#ifndef HV_SLEEP_ISSUER
+#define HV_SLEEP_ISSUER 0
+#endif
 #ifdef HV_TC256_TRACE
 // [items][16 events] clock64 stamps of CTA 0 (pointer in the kernel parameters: a predicated store, no dependent load)
 #define TRACE(n, ev) do { if (blockIdx.x == 0 && lane == 0 && (n) < 128) p.trace[(n) * 16 + (ev)] = clock64(); } while (0)
@@ -184,7 +199,7 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
       // ---------------------------------------------------------------- TMA producer
       for (int u = 0; u < nunits; ++u) {
         const int s = u % kStages;
-        mbar_wait_sleep(bar_empty(s), ((u / kStages) & 1) ^ 1, 256);
+        mbar_wait_sleep(bar_empty(s), ((u / kStages) & 1) ^ 1, HV_SLEEP_PROD);
         const int widx = work.first + u * work.stride;
         const UnitGeo16 ug = unit_geo16(g, widx);
         if (lane == 0) geo[u & 3] = ug;
@@ -216,7 +231,7 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
       for (int n = 0; n < nitems; ++n) {
         const int u = n >> 3, j = n & 7, a = j >> 2, b = j & 3, s = u % kStages, buf = n & 1;
         if (j == 0) mbar_wait_fast(bar_full(s), (u / kStages) & 1);
-        if (n > 1) mbar_wait_fast(bar_sdone(buf), ((n >> 1) - 1) & 1);  // the dQ MMAs of item n-2 have read W' out of this buffer
+        if (n > 1) mbar_wait_sleep(bar_sdone(buf), ((n >> 1) - 1) & 1, HV_SLEEP_ISSUER);  // the dQ MMAs of item n-2 have read W' out of this buffer
         TRACE(n, 0);
         tc_fence_after();
         if (elect_one()) {
@@ -247,7 +262,7 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
       const uint64_t b_g = smem_desc(sb + kOffStage + 3 * kTile16, 16, 512, 4);
       for (int n = 0; n < nitems; ++n) {
         const int u = n >> 3, j = n & 7, a = j >> 2, b = j & 3, s = u % kStages;
-        mbar_wait_fast(bar_staged, n & 1);
+        mbar_wait_sleep(bar_staged, n & 1, HV_SLEEP_ISSUER);
         TRACE(n, 7);
         if (u > 0 && j == 0) mbar_wait_fast(bar_acckvfree, (u - 1) & 1);    // dV, dK of the previous unit are out of TMEM
         if (u > 0 && b == 0) mbar_wait_fast(bar_accqfree(a), (u - 1) & 1);  // ... and its dQ_a
@@ -301,7 +316,7 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
       // ---------------------------------------------------------------- warp 3: TMA stores of dq, dk, dv (over the q, k, v tiles)
       for (int u = 0; u < nunits; ++u) {
         const int s = u % kStages;
-        mbar_wait_sleep(bar_written(s), (u / kStages) & 1, 128);
+        mbar_wait_sleep(bar_written(s), (u / kStages) & 1, HV_SLEEP_STORE);
         TRACE(8 * u + 7, 14);
         const uint32_t st = sb + kOffStage + s * kStage;
         if (elect_one()) {
@@ -442,7 +457,7 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
     const float inv_tl = 1.0f / (__ldg(&tau[head]) * kLog2e);
     for (int u = 0; u < nunits; ++u) {
       const int s = u % kStages;
-      mbar_wait_sleep(bar_acckv, u & 1, 128);
+      mbar_wait_sleep(bar_acckv, u & 1, HV_SLEEP_EPI);
       if (warp == 20) TRACE(8 * u + 7, 10);
       tc_fence_after();
       const uint32_t st = sb + kOffStage + s * kStage;
@@ -517,7 +532,7 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
       const float* vec = vecs + s * 1024;
 #pragma unroll 1
       for (int a = 0; a < 2; ++a) {
-        mbar_wait_sleep(bar_accq(a), u & 1, 128);
+        mbar_wait_sleep(bar_accq(a), u & 1, HV_SLEEP_EPI);
         if (warp == 24) TRACE(8 * u + 4 * a + 3, 13);
         tc_fence_after();
         uint32_t acc[32];
