@@ -21,6 +21,7 @@
 #define HV_WAIT_HINT_NS 1000
 #endif
 #include "hv_tc_win16.cuh"
+#include <atomic>
 
 // sleep (ns) between polls of the off-path warps: measured slower than tight try_wait loops (0.201 vs 0.195 ms at the
 // SwinV2-B stage-0 shape), so the default is none
@@ -408,19 +409,19 @@ wattn_tc256_fwd_kernel(const __grid_constant__ FwdMaps maps, const float* __rest
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols));
 }
 
-int g_tc256_mode = -1;  // -1: HV_ATTN_TC256 environment (unset: on), 0: off (generic kernels), 1: on
+std::atomic<int> g_tc256_mode{-1};  // -1: HV_ATTN_TC256 environment (unset: on), 0: off (generic kernels), 1: on
 
 }  // namespace
 
 int wattn_tc256_variant_set(int v) {
-  const int old = g_tc256_mode;
-  g_tc256_mode = v;
+  const int old = g_tc256_mode.exchange(v, std::memory_order_relaxed);
   return old;
 }
 
 bool wattn_tc256_supported(const Geom& g, int dtype) {
   static const int env = []() { const char* e = getenv("HV_ATTN_TC256"); return e == nullptr ? 1 : (atoi(e) != 0 ? 1 : 0); }();
-  const int mode = g_tc256_mode < 0 ? env : g_tc256_mode;
+  const int cur = g_tc256_mode.load(std::memory_order_relaxed);
+  const int mode = cur < 0 ? env : cur;
   if (mode == 0) return false;
   // shift 0 or ws / 2 (the only shift SwinV2 uses, swinv2.py:560): the column parts of the tile order are the halves of the wrap
   return dtype == HV_BF16 && g.ws == kWin16 && g.d == 32 && g.C % 32 == 0 && (g.shift == 0 || g.shift == 8) &&

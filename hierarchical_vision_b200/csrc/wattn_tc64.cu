@@ -19,6 +19,7 @@
 // negative for the backward, which keeps the plain try_wait loop
 #define HV_WAIT_HINT_NS 1000
 #include "hv_tc.cuh"
+#include <atomic>
 
 namespace hv {
 namespace {
@@ -556,19 +557,19 @@ wattn_tc64_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restri
 
 }  // namespace
 
-static int g_fwd_variant = -1;  // -1: HV_ATTN_TCGEN05 environment variable (default automatic), 0: mma.sync, 1: tcgen05
+static std::atomic<int> g_fwd_variant{-1};  // -1: HV_ATTN_TCGEN05 environment variable (default automatic), 0: mma.sync, 1: tcgen05
 
 int wattn_fwd_variant_set(int v) {
-  const int old = g_fwd_variant;
-  g_fwd_variant = v;
+  const int old = g_fwd_variant.exchange(v, std::memory_order_relaxed);
   return old;
 }
-int wattn_fwd_variant_get() { return g_fwd_variant; }
+int wattn_fwd_variant_get() { return g_fwd_variant.load(std::memory_order_relaxed); }
 
 bool wattn_tc64_supported(const Geom& g, int dtype) {
   // HV_ATTN_TCGEN05: unset or 1 = wherever valid (automatic), 0 = never (mma.sync forward)
   static const int env = []() { const char* e = getenv("HV_ATTN_TCGEN05"); return e == nullptr ? -1 : (atoi(e) != 0 ? 1 : 0); }();
-  const int mode = g_fwd_variant < 0 ? env : g_fwd_variant;
+  const int cur = g_fwd_variant.load(std::memory_order_relaxed);
+  const int mode = cur < 0 ? env : cur;
   if (mode == 0) return false;  // 1: second-generation kernel where valid, else this one; 2: always this one
   // an odd shift would put the second half of a column-wrapped row at a 64-byte (not 128-byte) shared-memory offset
   const bool valid = dtype == HV_BF16 && g.ws == kWs && g.d == 32 && g.C % 32 == 0 && (g.shift & 1) == 0 &&

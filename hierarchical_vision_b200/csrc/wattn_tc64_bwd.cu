@@ -31,6 +31,7 @@
 //   * 28 warps: 0 TMA loads | 1 issuer of S, dP | 2 issuer of dV, dK^, dQ^, dBias | 3 TMA stores |
 //     4-19 softmax / dS (2 groups) | 20-23 dV, dK epilogue | 24-27 dQ epilogue.  All hand-overs are mbarriers.
 #include "hv_tc_win.cuh"
+#include <atomic>
 
 namespace hv {
 namespace {
@@ -814,18 +815,18 @@ __global__ void __launch_bounds__(256) wattn_tc64_bwd_reduce_kernel(const float*
 
 }  // namespace
 
-static int g_bwd_variant = -1;  // -1: HV_ATTN_TCGEN05_BWD environment variable (default automatic), 0: mma.sync, 1: tcgen05
+static std::atomic<int> g_bwd_variant{-1};  // -1: HV_ATTN_TCGEN05_BWD environment variable (default automatic), 0: mma.sync, 1: tcgen05
 
 int wattn_bwd_variant_set(int v) {
-  const int old = g_bwd_variant;
-  g_bwd_variant = v;
+  const int old = g_bwd_variant.exchange(v, std::memory_order_relaxed);
   return old;
 }
 
 bool wattn_tc64_bwd_supported(const Geom& g, int dtype) {
   // HV_ATTN_TCGEN05_BWD: unset = automatic (this kernel wherever it is valid), 0 = never (mma.sync backward), 1 = same as unset
   static const int env = []() { const char* e = getenv("HV_ATTN_TCGEN05_BWD"); return e == nullptr ? -1 : (atoi(e) != 0 ? 1 : 0); }();
-  const int mode = g_bwd_variant < 0 ? env : g_bwd_variant;
+  const int cur = g_bwd_variant.load(std::memory_order_relaxed);
+  const int mode = cur < 0 ? env : cur;
   if (mode == 0) return false;
   // shifted layers: the bias lookup reads runs of four keys, i.e. the column split must sit at 4 (shift = ws / 2, the
   // only shift SwinV2 uses, swinv2.py:560)
