@@ -93,6 +93,20 @@ def test_bad_arguments_return_codes_not_crashes(lib):
     assert lib.hv_window_attn_bwd_workspace_bytes(1, 8, 8, 30, 4, 8, 1) == 0  # C % heads != 0
 
 
+def test_window16_statistics_and_workspace_sizes(lib):
+    """Host-only queries for the N = 256 kernels: three statistics planes (lse | r | c) like the N = 64 kernels, and a
+    backward workspace that holds the D = dO . O plane plus the per-CTA partials of d(bias table) / d(tau)."""
+    B, H, W, C, heads, ws = 2, 32, 48, 128, 4, 16
+    plane = B * (H // ws) * (W // ws) * heads * ws * ws
+    assert lib.hv_window_attn_stats_floats(B, H, W, C, heads, ws, _lib.HV_BF16) == 3 * plane
+    assert lib.hv_window_attn_stats_floats(B, H, W, C, heads, ws, _lib.HV_F32) == plane       # generic kernel
+    assert lib.hv_window_attn_stats_floats(B, H, W, C, 2, ws, _lib.HV_BF16) == plane // 2    # head dim 64: generic kernel
+    nbytes = lib.hv_window_attn_bwd_workspace_bytes(B, H, W, C, heads, ws, _lib.HV_BF16)
+    assert nbytes >= 4 * plane + 4 * 961 * heads                                              # D plane + at least one partial per head
+    assert lib.hv_window_attn_bwd_workspace_bytes(B, H, W, C, heads, ws, _lib.HV_F32) == 16  # generic: atomics, no workspace
+    assert lib.hv_window_attn_stats_floats(B, H + 1, W, C, heads, ws, _lib.HV_BF16) == 0      # H % ws != 0
+
+
 def test_kernel_kind_dispatch(lib):
     # bf16, head dim 32, window 8 (N = 64) or 16 (N = 256) -> tensor-core kernels; everything else -> generic kernel
     assert lib.hv_window_attn_kernel_kind(96, 3, 8, _lib.HV_BF16) == 1
