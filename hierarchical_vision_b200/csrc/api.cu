@@ -17,6 +17,10 @@ bool wattn_tc64_supported(const Geom& g, int dtype);
 int wattn_fwd_variant_set(int v);
 int wattn_fwd_variant_get();
 bool wattn_tc64_fwd2_supported(const Geom& g, int dtype);
+bool mlp_dgelu_gemm_supported(int64_t M, int N, int K);
+size_t mlp_dgelu_gemm_workspace_bytes(int N);
+int mlp_dgelu_gemm(const void* dy, const void* w2, const void* h, const float* b1, void* dh, float* db1, void* workspace,
+                   size_t workspace_bytes, int64_t M, int N, int K, cudaStream_t st);
 bool wattn_tc256_supported(const Geom& g, int dtype);
 int wattn_tc256_variant_set(int v);
 int wattn_tc256_fwd(const Geom& g, const void* qkv, const float* bias_table, const float* tau, void* out, float* stats,
@@ -340,6 +344,19 @@ int hv_ln_residual_bwd(const void* dout, const void* y, const float* gamma, cons
   if (rc) return rc;
   return ln_residual_bwd(dout, y, gamma, bias, mean, rstd, keep_scale, dy, dgamma, dbeta, dbias, workspace, workspace_bytes,
                          rows, C, rows_per_sample, y_dtype, res_dtype, static_cast<cudaStream_t>(stream));
+}
+
+size_t hv_mlp_dgelu_gemm_workspace_bytes(int64_t rows, int hidden, int C) {
+  return mlp_dgelu_gemm_supported(rows, hidden, C) ? mlp_dgelu_gemm_workspace_bytes(hidden) : 0;
+}
+
+int hv_mlp_dgelu_gemm(const void* dy, const void* w2, const void* h, const float* b1, void* dh, float* db1, void* workspace,
+                      size_t workspace_bytes, int64_t rows, int hidden, int C, int dtype, void* stream) {
+  if (!dy || !w2 || !h || !b1 || !dh || !db1) HV_FAIL(HV_ERR_NULL, "hv_mlp_dgelu_gemm: NULL argument");
+  if (dtype != HV_BF16) HV_FAIL(HV_ERR_DTYPE, "hv_mlp_dgelu_gemm: bf16 activations only");
+  int rc = check_device_arch();
+  if (rc) return rc;
+  return mlp_dgelu_gemm(dy, w2, h, b1, dh, db1, workspace, workspace_bytes, rows, hidden, C, static_cast<cudaStream_t>(stream));
 }
 
 int hv_bias_gelu_fwd(const void* h, const float* bias, void* out, int64_t rows, int cols, int dtype, void* stream) {

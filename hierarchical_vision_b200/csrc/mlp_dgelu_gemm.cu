@@ -1,0 +1,353 @@
+// Backward of the Mlp hidden activation fused into the GEMM that produces its upstream gradient (reference swinv2.py:43-66,
+// Mlp.forward: fc2(drop(act(fc1(x)))), differentiated):
+//
+//     dH = (dY W2) * GELU'(h + b1)        dY (M, C) bf16, W2 = fc2.weight (C, 4C) bf16, h = x W1^T (M, 4C) bf16 (no bias)
+//     db1 = column sums of dH
+//
+// Without this kernel the step runs a cuBLAS GEMM that writes dA = dY W2 (M x 4C, the largest tensor of the block) and the
+// bias+GELU backward kernel that reads dA and h and writes dH: three passes over M x 4C where this kernel makes two (read h,
+// write dH) -- dA never exists.  tcgen05 / TMEM / TMA, persistent CTAs:
+//
+//   * tile 128 (tokens) x 128 (hidden units), K = C in blocks of 64: A = dY tile (K-major, SWIZZLE_128B) and two B
+//     sub-tiles of W2 (64 k-rows x 64 hidden units = 128-byte rows, read MN-major: W2 is used as stored, no transposed
+//     copy) by 2-D TMA boxes into a four-stage ring; one elected thread issues M = 128, N = 64 tcgen05.mma chains into
+//     one of two 128-column accumulators in tensor memory;
+//   * the 128 x 128 tile of h arrives by TMA as well, dh is written over it in shared memory and leaves by TMA stores
+//     (per-thread 64-byte row segments straight from / to global memory ran at 0.39 of HBM: 32 lines per request);
+//   * sixteen epilogue warps (four per TMEM lane quadrant, 32 columns each): tcgen05.ld 32 columns, the matching 64 bytes
+//     of h from the staged tile, packed fp32x2 GELU' (the same fitted tanh form as bias_gelu.cu), bf16 row out,
+//     and a butterfly transpose-reduce over the warp's 32 rows (31 shuffles) so that lane c ends with the sum of column c;
+//   * a CTA keeps ONE column block (hidden units n0 .. n0 + 127) for all its tiles and walks token blocks, so the column
+//     sums live in one register per epilogue thread for the whole kernel; a second tiny kernel folds the per-warp rows
+//     into db1;
+//   * the epilogue of tile i overlaps the MMAs of tile i + 1 (two accumulators).
+#include <atomic>
+
+#include "hv_tc_win.cuh"
+
+namespace hv {
+namespace {
+using namespace tc;
+
+constexpr int kBM = 128, kBN = 128, kBK = 64;
+constexpr int kStages = 4;
+constexpr int kStageA = kBM * kBK * 2;       // 16 KB
+constexpr int kStageB = kBK * kBN * 2;       // 16 KB: two sub-tiles of 64 k-rows x 128 B
+constexpr int kStage = kStageA + kStageB;
+constexpr int kThreads = 640;                // 20 warps: 0 TMA | 1 MMA | 2 TMA stores | 3 idle | 4-19 epilogue
+constexpr int kMaxN = 4096;
+
+constexpr int kHTile = kBM * kBN * 2;        // 32 KB: two sub-tiles of 128 rows x 128 B (SWIZZLE_128B); h in, dh out (in place)
+constexpr int kOffStage = 0;
+constexpr int kOffH = kStages * kStage;      // [2] h / dh tiles
+constexpr int kOffBar = kOffH + 2 * kHTile;
+constexpr int kNumBars = 2 * kStages + 10;
+constexpr int kOffTmem = kOffBar + kNumBars * 8;
+constexpr int kSmem = kOffTmem + 16;
+constexpr int kTmemCols = 256;
+
+struct GemmMaps { CUtensorMap a, b, h, dh; };  // dY, W2, h (loads), dh (stores)
+
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// GELU'(x) = Phi(x) + x phi(x) with the fitted tanh form of bias_gelu.cu (gelu_parts_bf16x2<true>), two elements at a time
+__device__ __forceinline__ float2 dgelu2(float2 x) {
+  constexpr float c1 = 0.7974857091903687f, c3 = 0.03703207150101662f, c5 = -0.000356393022229895f;
+  const float2 one = make_float2(1.f, 1.f), half = make_float2(0.5f, 0.5f);
+  float2 x2 = __fmul2_rn(x, x);
+  x2 = make_float2(fminf(x2.x, 64.0f), fminf(x2.y, 64.0f));
+  const float2 u = __fmul2_rn(x, __ffma2_rn(x2, __ffma2_rn(x2, make_float2(c5, c5), make_float2(c3, c3)), make_float2(c1, c1)));
+  const float2 t = make_float2(tanh_fast(u.x), tanh_fast(u.y));
+  const float2 cdf = __ffma2_rn(half, t, half);
+  const float2 up = __ffma2_rn(x2, __ffma2_rn(x2, make_float2(5.0f * c5, 5.0f * c5), make_float2(3.0f * c3, 3.0f * c3)), make_float2(c1, c1));
+  const float2 sech2 = __ffma2_rn(make_float2(-t.x, -t.y), t, one);
+  return __ffma2_rn(__fmul2_rn(__fmul2_rn(half, x), up), sech2, cdf);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+mlp_dgelu_gemm_kernel(const __grid_constant__ GemmMaps maps, const bf16* __restrict__ h, const float* __restrict__ b1,
+                      bf16* __restrict__ dh, float* __restrict__ partials, int M, int N, int K) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t sb = smem_u32(smem);
+  const uint32_t bar0 = sb + kOffBar;
+  auto bar_full = [&](int s) { return bar0 + 8 * s; };
+  auto bar_empty = [&](int s) { return bar0 + 8 * (kStages + s); };
+  auto bar_acc = [&](int b) { return bar0 + 8 * (2 * kStages + b); };          // accumulator b complete
+  auto bar_accfree = [&](int b) { return bar0 + 8 * (2 * kStages + 2 + b); };  // ... and pulled out of TMEM
+  auto bar_hfull = [&](int b) { return bar0 + 8 * (2 * kStages + 4 + b); };    // h tile b landed
+  auto bar_hwritten = [&](int b) { return bar0 + 8 * (2 * kStages + 6 + b); }; // dh written over it by the 16 epilogue warps
+  auto bar_hfree = [&](int b) { return bar0 + 8 * (2 * kStages + 8 + b); };    // ... and read by the TMA store
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmem);
+
+  // CTA c: column block c % n_tiles, token blocks c / n_tiles, + gridDim.x / n_tiles, ... (gridDim.x is a multiple of n_tiles)
+  const int n_tiles = N / kBN, m_tiles = M / kBM;
+  const int kblocks = (K + kBK - 1) / kBK;
+  const int n0 = ((int)blockIdx.x % n_tiles) * kBN;
+  const int m_first = (int)blockIdx.x / n_tiles, m_stride = (int)gridDim.x / n_tiles;
+  const int my_tiles = m_first < m_tiles ? (m_tiles - m_first + m_stride - 1) / m_stride : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_acc(b), 1);
+      mbar_init(bar_accfree(b), 16);
+      mbar_init(bar_hfull(b), 1);
+      mbar_init(bar_hwritten(b), 16);
+      mbar_init(bar_hfree(b), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    int it = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int m0 = (m_first + i * m_stride) * kBM;
+      {  // the tile of pre-activations the epilogue needs (two boxes of 64 columns), into the buffer tile i - 2 has left
+        const int hb = i & 1;
+        if (i > 1) mbar_wait_fast(bar_hfree(hb), ((i >> 1) - 1) & 1);
+        if (elect_one()) {
+          mbar_expect_tx(bar_hfull(hb), kHTile);
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub)
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                         ::"r"(sb + kOffH + hb * kHTile + sub * (kHTile / 2)), "l"(reinterpret_cast<uint64_t>(&maps.h)),
+                           "r"(bar_hfull(hb)), "r"(n0 + 64 * sub), "r"(m0) : "memory");
+        }
+        __syncwarp();
+      }
+      for (int kb = 0; kb < kblocks; ++kb, ++it) {
+        const int s = it % kStages;
+        mbar_wait_fast(bar_empty(s), ((it / kStages) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(bar_full(s), kStage);
+          const uint32_t dst = sb + kOffStage + s * kStage;
+          asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(&maps.a)), "r"(bar_full(s)), "r"(kb * kBK), "r"(m0) : "memory");
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub)
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                         ::"r"(dst + kStageA + sub * (kStageB / 2)), "l"(reinterpret_cast<uint64_t>(&maps.b)), "r"(bar_full(s)),
+                           "r"(n0 + 64 * sub), "r"(kb * kBK) : "memory");
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer: D[128 x 64 sub] += A (K-major) x B sub-tile (MN-major)
+    const uint32_t id = idesc_bf16(128, 64, 0, 1);
+    const uint64_t d_a = smem_desc(sb + kOffStage, 16, 1024, 2);
+    const uint64_t d_b = smem_desc(sb + kOffStage + kStageA, 16, 1024, 2);
+    int it = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int buf = i & 1;
+      if (i > 1) mbar_wait_fast(bar_accfree(buf), ((i >> 1) - 1) & 1);
+      tc_fence_after();
+      for (int kb = 0; kb < kblocks; ++kb, ++it) {
+        const int s = it % kStages;
+        mbar_wait_fast(bar_full(s), (it / kStages) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t so = (uint64_t)((s * kStage) >> 4);
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)  // 16 k per step: A += 32 B inside the swizzle atom, B += 16 rows of 128 B
+              umma_ss(tmem + 128 * buf + 64 * sub, d_a + so + (uint64_t)(2 * ks),
+                      d_b + so + (uint64_t)(sub * (kStageB / 2 >> 4) + 128 * ks), id, (kb > 0 || ks > 0) ? 1u : 0u);
+          umma_commit(bar_empty(s));
+          if (kb == kblocks - 1) umma_commit(bar_acc(buf));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 2) {
+    // ---------------------------------------------------------------- TMA stores of the dh tiles
+    for (int i = 0; i < my_tiles; ++i) {
+      const int m0 = (m_first + i * m_stride) * kBM, hb = i & 1;
+      mbar_wait_fast(bar_hwritten(hb), (i >> 1) & 1);
+      if (elect_one()) {
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub)
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                       ::"l"(reinterpret_cast<uint64_t>(&maps.dh)), "r"(sb + kOffH + hb * kHTile + sub * (kHTile / 2)),
+                         "r"(n0 + 64 * sub), "r"(m0) : "memory");
+      }
+      __syncwarp();
+      bulk_commit();
+      bulk_wait_read0();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_hfree(hb));
+    }
+    bulk_wait0();
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- epilogue: rows 32 quad .. of the tile, columns 32 cq ..
+    const int quad = warp & 3, cq = (warp - 4) >> 2;
+    const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16) + 32 * cq;
+    const int nc = n0 + 32 * cq;
+    float2 bias[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) bias[q] = make_float2(__ldg(b1 + nc + 2 * q), __ldg(b1 + nc + 2 * q + 1));
+    float csum = 0.f;  // column nc + lane, over this warp's rows of every tile
+    for (int i = 0; i < my_tiles; ++i) {
+      const int buf = i & 1;
+      // this thread's row of the h tile: 128-byte rows (64 columns) per sub-tile, 16-byte chunk c at position c ^ (row & 7)
+      const int r = 32 * quad + lane;
+      const uint32_t hrow = sb + kOffH + buf * kHTile + (cq >> 1) * (kHTile / 2) + r * 128;
+      const uint32_t cbase = (uint32_t)(4 * (cq & 1)), swz = (uint32_t)(r & 7);
+      mbar_wait_fast(bar_hfull(buf), (i >> 1) & 1);
+      uint4 hv[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) hv[q] = lds128(hrow + (((cbase + q) ^ swz) << 4));
+      mbar_wait_fast(bar_acc(buf), (i >> 1) & 1);
+      tc_fence_after();
+      uint32_t acc[32];
+      HV_TMEM_LD32(tl + 128 * buf, acc);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_accfree(buf));
+      float v[32];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t hw[4] = {hv[q].x, hv[q].y, hv[q].z, hv[q].w};
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 x = __fadd2_rn(make_float2(bf16lo_to_f32(hw[e]), bf16hi_to_f32(hw[e])), bias[4 * q + e]);
+          const float2 g = dgelu2(x);
+          const float2 d = __fmul2_rn(make_float2(__uint_as_float(acc[8 * q + 2 * e]), __uint_as_float(acc[8 * q + 2 * e + 1])), g);
+          v[8 * q + 2 * e] = d.x;
+          v[8 * q + 2 * e + 1] = d.y;
+          o[e] = pack_bf16x2(d.x, d.y);
+        }
+        sts128(hrow + (((cbase + q) ^ swz) << 4), make_uint4(o[0], o[1], o[2], o[3]));  // dh over h, in place
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_hwritten(buf));
+      // column sums over the warp's 32 rows: butterfly transpose-reduce, lane L ends with column L of the chunk
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int j = 0; j < o; ++j) {
+          const float send = up ? v[j] : v[j + o];
+          const float keep = up ? v[j + o] : v[j];
+          v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+      }
+      csum += v[0];
+    }
+    // one row of 128 partial column sums per (CTA, quadrant)
+    partials[((int64_t)blockIdx.x * 4 + quad) * kBN + 32 * cq + lane] = csum;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols));
+}
+
+// db1[n] = sum over the CTAs of n's column block and their four quadrant rows
+__global__ void mlp_dgelu_fold_kernel(const float* __restrict__ partials, float* __restrict__ db1, int N, int n_tiles, int ctas) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int nt = n / kBN, j = n - nt * kBN;
+  float acc = 0.f;
+  for (int c = nt; c < ctas; c += n_tiles)
+    for (int q = 0; q < 4; ++q) acc += partials[((int64_t)c * 4 + q) * kBN + j];
+  db1[n] = acc;
+}
+
+int make_map_2d(CUtensorMap* m, const void* base, int64_t inner, int64_t outer, int box_inner, int box_outer) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) HV_FAIL(HV_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  int dev = 0;
+  HV_CUDA_OK(cudaGetDevice(&dev));
+  HV_CUDA_OK(cudaSetDevice(dev));
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)inner * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) HV_FAIL(HV_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a 2-D box (%d, %d)", (int)r, box_inner, box_outer);
+  return HV_OK;
+}
+
+}  // namespace
+
+bool mlp_dgelu_gemm_supported(int64_t M, int N, int K) {
+  return M > 0 && M % kBM == 0 && M < (int64_t(1) << 31) && N % kBN == 0 && N <= kMaxN && N / kBN <= num_sms() && K % 8 == 0 && K >= 16;
+}
+
+size_t mlp_dgelu_gemm_workspace_bytes(int N) { return (size_t)num_sms() * 4 * kBN * sizeof(float) + 64; }
+
+int mlp_dgelu_gemm(const void* dy, const void* w2, const void* h, const float* b1, void* dh, float* db1, void* workspace,
+                   size_t workspace_bytes, int64_t M, int N, int K, cudaStream_t st) {
+  if (!mlp_dgelu_gemm_supported(M, N, K)) HV_FAIL(HV_ERR_SHAPE, "mlp_dgelu_gemm: M=%lld N=%d K=%d", (long long)M, N, K);
+  if (!aligned16(dy) || !aligned16(w2) || !aligned16(h) || !aligned16(dh) || !aligned16(b1))
+    HV_FAIL(HV_ERR_ALIGN, "mlp_dgelu_gemm: pointers must be 16-byte aligned");
+  if (workspace == nullptr || workspace_bytes < mlp_dgelu_gemm_workspace_bytes(N))
+    HV_FAIL(HV_ERR_WORKSPACE, "mlp_dgelu_gemm: workspace of %zu bytes required", mlp_dgelu_gemm_workspace_bytes(N));
+  struct MapKey { const void *dy, *w2, *h, *dh; int64_t M; int N, K; };
+  struct MapEntry { MapKey key; GemmMaps maps; };
+  static thread_local MapEntry cache[32];
+  static thread_local int cache_n = 0, cache_next = 0;
+  const GemmMaps* mp = nullptr;
+  for (int i = 0; i < cache_n; ++i) {
+    const MapKey& c = cache[i].key;
+    if (c.dy == dy && c.w2 == w2 && c.h == h && c.dh == dh && c.M == M && c.N == N && c.K == K) { mp = &cache[i].maps; break; }
+  }
+  if (!mp) {
+    MapEntry& e = cache[cache_next];
+    int rc = make_map_2d(&e.maps.a, dy, K, M, kBK, kBM);  // dY (M, K): box 64 k x 128 rows
+    if (rc) return rc;
+    rc = make_map_2d(&e.maps.b, w2, N, K, 64, kBK);       // W2 (K, N): box 64 hidden units x 64 k-rows
+    if (rc) return rc;
+    rc = make_map_2d(&e.maps.h, h, N, M, 64, kBM);        // h (M, N): box 64 hidden units x 128 rows
+    if (rc) return rc;
+    rc = make_map_2d(&e.maps.dh, dh, N, M, 64, kBM);
+    if (rc) return rc;
+    e.key = MapKey{dy, w2, h, dh, M, N, K};
+    mp = &e.maps;
+    cache_next = (cache_next + 1) % 32;
+    if (cache_n < 32) ++cache_n;
+  }
+  static thread_local int attr_dev = -1;
+  int dev = 0;
+  HV_CUDA_OK(cudaGetDevice(&dev));
+  if (attr_dev != dev) {
+    HV_CUDA_OK(cudaFuncSetAttribute(mlp_dgelu_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    attr_dev = dev;
+  }
+  const int n_tiles = N / kBN, m_tiles = (int)(M / kBM);
+  int per_col = num_sms() / n_tiles;  // CTAs per column block
+  if (per_col < 1) per_col = 1;
+  if (per_col > m_tiles) per_col = m_tiles;
+  const int grid = per_col * n_tiles;
+  float* partials = static_cast<float*>(workspace);
+  mlp_dgelu_gemm_kernel<<<grid, kThreads, kSmem, st>>>(*mp, static_cast<const bf16*>(h), b1, static_cast<bf16*>(dh), partials,
+                                                       (int)M, N, K);
+  HV_LAUNCH_OK("mlp_dgelu_gemm_kernel");
+  mlp_dgelu_fold_kernel<<<(N + 255) / 256, 256, 0, st>>>(partials, db1, N, n_tiles, grid);
+  HV_LAUNCH_OK("mlp_dgelu_fold_kernel");
+  return HV_OK;
+}
+
+}  // namespace hv

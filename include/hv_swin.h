@@ -179,6 +179,16 @@ HV_API int hv_ln_residual_bwd(const void* dout, const void* y, const float* gamm
                        float* dbeta, float* dbias, void* workspace, size_t workspace_bytes, int64_t rows, int C,
                        int64_t rows_per_sample, int y_dtype, int res_dtype, void* stream);
 
+/* Backward of the Mlp hidden activation fused into the GEMM that produces its upstream gradient (reference swinv2.py:43-66
+ * differentiated): dh = (dy W2) * GELU'(h + b1) and db1 = column sums of dh, with dy (rows, C), w2 = fc2.weight (C, hidden)
+ * as stored, h = x W1^T (rows, hidden) without the fc1 bias, all bf16; b1, db1 fp32 (hidden).  Replaces the dgrad GEMM of
+ * fc2 plus hv_bias_gelu_bwd: the (rows, hidden) gradient of the activation output is never written.  tcgen05 / TMEM / TMA.
+ * Requires rows % 128 == 0, hidden % 128 == 0, hidden <= 4096, C % 8 == 0 (hv_mlp_dgelu_gemm_workspace_bytes returns 0
+ * otherwise; callers then use the two-kernel path). */
+HV_API size_t hv_mlp_dgelu_gemm_workspace_bytes(int64_t rows, int hidden, int C);
+HV_API int hv_mlp_dgelu_gemm(const void* dy, const void* w2, const void* h, const float* b1, void* dh, float* db1,
+                             void* workspace, size_t workspace_bytes, int64_t rows, int hidden, int C, int dtype, void* stream);
+
 /* ---- Mlp activation with the fc1 bias folded in: out = GELU_erf(h + bias) ------------------
  * Replaces the bias add of `fc1` plus `self.act(x)` (nn.GELU, exact erf form), swinv2.py:61-62, and their
  * autograd; the caller runs fc1 as a bias-free GEMM.  Backward also yields d fc1.bias (column sums of dh).
