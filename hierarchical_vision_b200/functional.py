@@ -72,6 +72,7 @@ def _dx_with_shortcut(dx_shortcut, d2, weight, shape):
 # when the parameter's version counter has moved (optimizer step, load_state_dict) -- by ONE multi-tensor copy for all
 # weights (`refresh_weight_shadows`, called at the start of a training step) -- and the weight-gradient GEMMs write
 # fp32 directly (`torch.mm(..., out_dtype=torch.float32)`).
+import os
 import weakref
 
 _SHADOWS = {}  # id(parameter) -> [weakref to the parameter, shadow tensor, parameter version it holds]
@@ -514,6 +515,72 @@ def bias_gelu_supported(h: torch.Tensor) -> bool:
 def bias_gelu(h: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
     """GELU (exact erf form) of ``h + bias`` where ``h`` is the bias-free fc1 output (..., cols)."""
     return _BiasGelu.apply(h, bias)
+
+
+# the fused backward GEMM (hv_mlp_dgelu_gemm) replaces the fc2 dgrad GEMM + hv_bias_gelu_bwd where it is faster than that
+# pair; measured on B200 (tools/mlp_gemm_check.py): faster up to C = 384, level at C = 768.  A test / benchmarking switch.
+MLP_DGELU_GEMM_MAX_C = int(os.environ.get("HV_MLP_DGELU_GEMM_MAX_C", "384"))
+
+
+class _GeluFc2(torch.autograd.Function):
+    """m = GELU_erf(h + b1) @ W2^T (the fc2 bias is added by the caller or folded into its LayerNorm kernel): reference
+    swinv2.py:61-64.  One autograd node for the activation and the fc2 GEMM so that the backward can form
+    dh = (dm W2) * GELU'(h + b1) and db1 in ONE tcgen05 GEMM (hv_mlp_dgelu_gemm): the gradient of the activation output,
+    the largest tensor of the block, is never written."""
+
+    @staticmethod
+    def forward(ctx, h, b1, w2):
+        _need_cuda(h, "gelu_fc2")
+        lib = _lib.load()
+        h = h.contiguous()
+        cols = h.shape[-1]
+        rows = h.numel() // cols
+        b32 = _f32c(b1)
+        a = torch.empty_like(h)
+        with torch.cuda.device(h.device):
+            check(lib.hv_bias_gelu_fwd(_ptr(h), _ptr(b32), _ptr(a), rows, cols, _code(h), _stream(h.device)), "hv_bias_gelu_fwd")
+        global LAUNCH_COUNT
+        LAUNCH_COUNT += 1
+        w = weight_shadow(w2, h.dtype)
+        ctx.save_for_backward(h, b32, a, w)
+        ctx.meta = (rows, cols, b1.dtype, w2.dtype)
+        return torch.nn.functional.linear(a, w)
+
+    @staticmethod
+    def backward(ctx, dm):
+        h, b32, a, w = ctx.saved_tensors
+        rows, cols, bdt, wdt = ctx.meta
+        lib = _lib.load()
+        C = w.shape[0]
+        dm2 = dm.reshape(rows, C)
+        if dm2.dtype != h.dtype:
+            dm2 = dm2.to(h.dtype)
+        dm2 = dm2.contiguous()
+        global LAUNCH_COUNT
+        dh = db1 = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            dh = torch.empty_like(h)
+            db1 = torch.empty_like(b32)
+            with torch.cuda.device(h.device):
+                nb = int(lib.hv_mlp_dgelu_gemm_workspace_bytes(rows, cols, C)) if (h.dtype == torch.bfloat16 and C <= MLP_DGELU_GEMM_MAX_C) else 0
+                if nb > 0:
+                    ws = torch.empty((nb,), dtype=torch.uint8, device=h.device)
+                    check(lib.hv_mlp_dgelu_gemm(_ptr(dm2), _ptr(w), _ptr(h), _ptr(b32), _ptr(dh), _ptr(db1), _ptr(ws), nb, rows,
+                                                cols, C, _code(h), _stream(h.device)), "hv_mlp_dgelu_gemm")
+                else:  # the two-kernel path: dgrad GEMM, then the bias + GELU backward
+                    da = torch.mm(dm2, w)
+                    nb = int(lib.hv_bias_gelu_bwd_workspace_bytes(rows, cols))
+                    ws = torch.empty((nb,), dtype=torch.uint8, device=h.device)
+                    check(lib.hv_bias_gelu_bwd(_ptr(da), _ptr(h), _ptr(b32), _ptr(dh), _ptr(db1), _ptr(ws), ws.numel(), rows, cols,
+                                               _code(h), _stream(h.device)), "hv_bias_gelu_bwd")
+            LAUNCH_COUNT += 2
+        dw2 = _weight_grad(dm2.t(), a.reshape(rows, cols), wdt) if ctx.needs_input_grad[2] else None
+        return dh, (db1.to(bdt) if db1 is not None else None), dw2
+
+
+def gelu_fc2(h: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor) -> torch.Tensor:
+    """GELU(h + b1) @ w2^T for the bias-free fc1 output ``h`` (..., hidden) and ``w2`` = fc2.weight (C, hidden)."""
+    return _GeluFc2.apply(h, b1, w2)
 
 
 class _PatchMergeGather(torch.autograd.Function):

@@ -142,7 +142,31 @@ class Mlp(nn.Module):
             a = self.act(self.fc1(x))
         return (a, sc) if with_shortcut else a
 
+    def _hidden_fc2(self, x, with_shortcut=False):
+        """fc2(act(fc1(x))) WITHOUT the fc2 bias (the caller adds it or folds it into its LayerNorm kernel), and x for the
+        residual connection.  bf16 activations with the exact GELU take one autograd node for the activation and the fc2
+        GEMM, whose backward is the fused dGELU GEMM (functional._GeluFc2); everything else the two separate nodes."""
+        sc = x
+        fused = (type(self.act) is nn.GELU and getattr(self.act, "approximate", "none") == "none" and self.fc1.bias is not None
+                 and self.drop.p == 0.0 and x.is_cuda)
+        if fused:
+            if with_shortcut and torch.is_autocast_enabled("cuda") and x.dtype == torch.get_autocast_dtype("cuda"):
+                h, sc = hvf.linear_shortcut(x, self.fc1.weight)
+            elif with_shortcut and not torch.is_autocast_enabled("cuda") and x.dtype == self.fc1.weight.dtype:
+                h, sc = hvf.linear_shortcut(x, self.fc1.weight)
+            else:
+                h = _linear(x, self.fc1.weight)
+            if h.dtype == torch.bfloat16 and hvf.bias_gelu_supported(h):
+                return hvf.gelu_fc2(h, self.fc1.bias, self.fc2.weight), sc
+            a = hvf.bias_gelu(h, self.fc1.bias) if hvf.bias_gelu_supported(h) else self.act(h + self.fc1.bias)
+            return _linear(a, self.fc2.weight), sc
+        a = self._hidden(x)
+        return _linear(self.drop(a), self.fc2.weight), sc
+
     def forward(self, x):
+        if self.drop.p == 0.0 and x.is_cuda and self.fc2.bias is not None:
+            m, _ = self._hidden_fc2(x)
+            return m + self.fc2.bias.to(m.dtype)
         return self.drop(self.fc2(self.drop(self._hidden(x))))
 
 
@@ -368,8 +392,7 @@ class SwinTransformerBlock(nn.Module):
         y, proj_bias, x = self.attn._fused(x, B, H, W, self.shift_size, None, with_proj_bias=not fold1)
         x = self._post_norm(self.norm1, y, x, proj_bias)                                       # swinv2.py:431
         if fold2:
-            a, x = self.mlp._hidden(x, with_shortcut=True)
-            m = _linear(a, self.mlp.fc2.weight)
+            m, x = self.mlp._hidden_fc2(x, with_shortcut=True)
             return self._post_norm(self.norm2, m, x, self.mlp.fc2.bias)                         # swinv2.py:434
         return self._post_norm(self.norm2, self.mlp(x), x)
 

@@ -730,6 +730,37 @@ def test_bias_gelu_outliers(dtype):
     assert (h.grad.float().cpu() - h64.grad.float()).abs().max() <= (2e-2 if dtype == torch.bfloat16 else 1e-4)
 
 
+@pytest.mark.parametrize("shape", [(512, 96), (384, 192), (256, 384), (128, 768), (200, 96), (1024, 32)])
+@pytest.mark.parametrize("force_fused", [False, True])
+def test_gelu_fc2_fused_backward_gemm(shape, force_fused):
+    """m = GELU(h + b1) W2^T with the backward dh = (dm W2) * GELU'(h + b1), db1 = column sums, dW2 = dm^T a
+    (swinv2.py:61-64 differentiated): the tcgen05 GEMM with the GELU backward in its epilogue (hv_mlp_dgelu_gemm: rows a
+    multiple of 128, C up to the dispatch limit, or forced) and the two-kernel path it falls back to, against torch in
+    fp64 on the same bf16 inputs.  C = 96 exercises the zero-filled half k-block, rows = 200 the fallback."""
+    rows, C = shape
+    hidden = 4 * C
+    gen = torch.Generator().manual_seed(rows + C)
+    h = (1.5 * torch.randn(rows, hidden, generator=gen)).to(DEV, torch.bfloat16).requires_grad_(True)
+    b1 = (0.5 * torch.randn(hidden, generator=gen)).to(DEV).requires_grad_(True)
+    w2 = (torch.randn(C, hidden, generator=gen) / hidden ** 0.5).to(DEV, torch.bfloat16).requires_grad_(True)
+    dm = torch.randn(rows, C, generator=gen).to(DEV, torch.bfloat16)
+    old = hvf.MLP_DGELU_GEMM_MAX_C
+    hvf.MLP_DGELU_GEMM_MAX_C = 4096 if force_fused else old
+    try:
+        m = hvf.gelu_fc2(h, b1, w2)
+        m.backward(dm)
+        torch.cuda.synchronize()
+    finally:
+        hvf.MLP_DGELU_GEMM_MAX_C = old
+    h64, b64, w64 = (t.detach().double().cpu().requires_grad_(True) for t in (h, b1, w2))
+    want = torch.nn.functional.gelu(h64 + b64) @ w64.t()
+    want.backward(dm.double().cpu())
+    assert_close("m", m, want, 2e-2)
+    assert_close("dh", h.grad, h64.grad, 2e-2)
+    assert_close("db1", b1.grad, b64.grad, 2e-2)
+    assert_close("dw2", w2.grad, w64.grad, 2e-2)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("classes", [3, 273, 10000])
 @pytest.mark.parametrize("smoothing", [0.0, 0.1])
