@@ -21,6 +21,7 @@ bool mlp_dgelu_gemm_supported(int64_t M, int N, int K);
 size_t mlp_dgelu_gemm_workspace_bytes(int N);
 int mlp_dgelu_gemm(const void* dy, const void* w2, const void* h, const float* b1, void* dh, float* db1, void* workspace,
                    size_t workspace_bytes, int64_t M, int N, int K, cudaStream_t st);
+int mlp_fc1_gelu_gemm(const void* x, const void* w1, const float* b1, void* h, void* act, int64_t M, int N, int K, cudaStream_t st);
 bool wattn_tc256_supported(const Geom& g, int dtype);
 int wattn_tc256_variant_set(int v);
 int wattn_tc256_fwd(const Geom& g, const void* qkv, const float* bias_table, const float* tau, void* out, float* stats,
@@ -357,6 +358,15 @@ int hv_mlp_dgelu_gemm(const void* dy, const void* w2, const void* h, const float
   int rc = check_device_arch();
   if (rc) return rc;
   return mlp_dgelu_gemm(dy, w2, h, b1, dh, db1, workspace, workspace_bytes, rows, hidden, C, static_cast<cudaStream_t>(stream));
+}
+
+int hv_mlp_fc1_gelu_gemm(const void* x, const void* w1, const float* b1, void* h, void* act, int64_t rows, int hidden, int C,
+                         int dtype, void* stream) {
+  if (!x || !w1 || !b1 || !h || !act) HV_FAIL(HV_ERR_NULL, "hv_mlp_fc1_gelu_gemm: NULL argument");
+  if (dtype != HV_BF16) HV_FAIL(HV_ERR_DTYPE, "hv_mlp_fc1_gelu_gemm: bf16 activations only");
+  int rc = check_device_arch();
+  if (rc) return rc;
+  return mlp_fc1_gelu_gemm(x, w1, b1, h, act, rows, hidden, C, static_cast<cudaStream_t>(stream));
 }
 
 int hv_bias_gelu_fwd(const void* h, const float* bias, void* out, int64_t rows, int cols, int dtype, void* stream) {

@@ -10,7 +10,7 @@
 //
 //   * tile 128 (tokens) x 128 (hidden units), K = C in blocks of 64: A = dY tile (K-major, SWIZZLE_128B) and two B
 //     sub-tiles of W2 (64 k-rows x 64 hidden units = 128-byte rows, read MN-major: W2 is used as stored, no transposed
-//     copy) by 2-D TMA boxes into a four-stage ring; one elected thread issues M = 128, N = 64 tcgen05.mma chains into
+//     copy) by 2-D TMA boxes into a three-stage ring; one elected thread issues M = 128, N = 64 tcgen05.mma chains into
 //     one of two 128-column accumulators in tensor memory;
 //   * the 128 x 128 tile of h arrives by TMA as well, dh is written over it in shared memory and leaves by TMA stores
 //     (per-thread 64-byte row segments straight from / to global memory ran at 0.39 of HBM: 32 lines per request);
@@ -30,7 +30,8 @@ namespace {
 using namespace tc;
 
 constexpr int kBM = 128, kBN = 128, kBK = 64;
-constexpr int kStages = 4;
+// ring depths are template parameters: (operand stages, h / dh tiles in flight) = (3, 3) for C <= 192 (two or three k-blocks
+// per tile: the kernel is a stream of h / dh tiles), (4, 2) beyond (the mainloop needs the deeper operand ring)
 constexpr int kStageA = kBM * kBK * 2;       // 16 KB
 constexpr int kStageB = kBK * kBN * 2;       // 16 KB: two sub-tiles of 64 k-rows x 128 B
 constexpr int kStage = kStageA + kStageB;
@@ -39,11 +40,14 @@ constexpr int kMaxN = 4096;
 
 constexpr int kHTile = kBM * kBN * 2;        // 32 KB: two sub-tiles of 128 rows x 128 B (SWIZZLE_128B); h in, dh out (in place)
 constexpr int kOffStage = 0;
-constexpr int kOffH = kStages * kStage;      // [2] h / dh tiles
-constexpr int kOffBar = kOffH + 2 * kHTile;
-constexpr int kNumBars = 2 * kStages + 10;
-constexpr int kOffTmem = kOffBar + kNumBars * 8;
-constexpr int kSmem = kOffTmem + 16;
+template <int kStages, int kHBufs> struct Layout {
+  static constexpr int kOffH = kStages * kStage;  // [kHBufs] h / dh tiles
+  static constexpr int kOffBar = kOffH + kHBufs * kHTile;
+  static constexpr int kNumBars = 2 * kStages + 4 + 3 * kHBufs;
+  static constexpr int kOffTmem = kOffBar + kNumBars * 8;
+  static constexpr int kSmem = kOffTmem + 16;
+  static_assert(kSmem <= 227 * 1024, "shared memory budget");
+};
 constexpr int kTmemCols = 256;
 
 struct GemmMaps { CUtensorMap a, b, h, dh; };  // dY, W2, h (loads), dh (stores)
@@ -67,10 +71,13 @@ __device__ __forceinline__ float2 dgelu2(float2 x) {
   return __ffma2_rn(__fmul2_rn(__fmul2_rn(half, x), up), sech2, cdf);
 }
 
+template <int kStages, int kHBufs>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_dgelu_gemm_kernel(const __grid_constant__ GemmMaps maps, const bf16* __restrict__ h, const float* __restrict__ b1,
                       bf16* __restrict__ dh, float* __restrict__ partials, int M, int N, int K) {
   extern __shared__ __align__(1024) unsigned char smem[];
+  using L = Layout<kStages, kHBufs>;
+  constexpr int kOffH = L::kOffH, kOffBar = L::kOffBar, kOffTmem = L::kOffTmem;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t sb = smem_u32(smem);
   const uint32_t bar0 = sb + kOffBar;
@@ -78,9 +85,9 @@ mlp_dgelu_gemm_kernel(const __grid_constant__ GemmMaps maps, const bf16* __restr
   auto bar_empty = [&](int s) { return bar0 + 8 * (kStages + s); };
   auto bar_acc = [&](int b) { return bar0 + 8 * (2 * kStages + b); };          // accumulator b complete
   auto bar_accfree = [&](int b) { return bar0 + 8 * (2 * kStages + 2 + b); };  // ... and pulled out of TMEM
-  auto bar_hfull = [&](int b) { return bar0 + 8 * (2 * kStages + 4 + b); };    // h tile b landed
-  auto bar_hwritten = [&](int b) { return bar0 + 8 * (2 * kStages + 6 + b); }; // dh written over it by the 16 epilogue warps
-  auto bar_hfree = [&](int b) { return bar0 + 8 * (2 * kStages + 8 + b); };    // ... and read by the TMA store
+  auto bar_hfull = [&](int b) { return bar0 + 8 * (2 * kStages + 4 + b); };                  // h tile b landed
+  auto bar_hwritten = [&](int b) { return bar0 + 8 * (2 * kStages + 4 + kHBufs + b); };      // dh written over it by the 16 epilogue warps
+  auto bar_hfree = [&](int b) { return bar0 + 8 * (2 * kStages + 4 + 2 * kHBufs + b); };     // ... and read by the TMA store
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmem);
 
   // CTA c: column block c % n_tiles, token blocks c / n_tiles, + gridDim.x / n_tiles, ... (gridDim.x is a multiple of n_tiles)
@@ -98,6 +105,8 @@ mlp_dgelu_gemm_kernel(const __grid_constant__ GemmMaps maps, const bf16* __restr
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_acc(b), 1);
       mbar_init(bar_accfree(b), 16);
+    }
+    for (int b = 0; b < kHBufs; ++b) {
       mbar_init(bar_hfull(b), 1);
       mbar_init(bar_hwritten(b), 16);
       mbar_init(bar_hfree(b), 1);
@@ -119,8 +128,8 @@ mlp_dgelu_gemm_kernel(const __grid_constant__ GemmMaps maps, const bf16* __restr
     for (int i = 0; i < my_tiles; ++i) {
       const int m0 = (m_first + i * m_stride) * kBM;
       {  // the tile of pre-activations the epilogue needs (two boxes of 64 columns), into the buffer tile i - 2 has left
-        const int hb = i & 1;
-        if (i > 1) mbar_wait_fast(bar_hfree(hb), ((i >> 1) - 1) & 1);
+        const int hb = i % kHBufs;
+        if (i >= kHBufs) mbar_wait_fast(bar_hfree(hb), ((i / kHBufs) - 1) & 1);
         if (elect_one()) {
           mbar_expect_tx(bar_hfull(hb), kHTile);
 #pragma unroll
@@ -179,8 +188,8 @@ mlp_dgelu_gemm_kernel(const __grid_constant__ GemmMaps maps, const bf16* __restr
   } else if (warp == 2) {
     // ---------------------------------------------------------------- TMA stores of the dh tiles
     for (int i = 0; i < my_tiles; ++i) {
-      const int m0 = (m_first + i * m_stride) * kBM, hb = i & 1;
-      mbar_wait_fast(bar_hwritten(hb), (i >> 1) & 1);
+      const int m0 = (m_first + i * m_stride) * kBM, hb = i % kHBufs;
+      mbar_wait_fast(bar_hwritten(hb), (i / kHBufs) & 1);
       if (elect_one()) {
 #pragma unroll
         for (int sub = 0; sub < 2; ++sub)
@@ -208,9 +217,10 @@ mlp_dgelu_gemm_kernel(const __grid_constant__ GemmMaps maps, const bf16* __restr
       const int buf = i & 1;
       // this thread's row of the h tile: 128-byte rows (64 columns) per sub-tile, 16-byte chunk c at position c ^ (row & 7)
       const int r = 32 * quad + lane;
-      const uint32_t hrow = sb + kOffH + buf * kHTile + (cq >> 1) * (kHTile / 2) + r * 128;
+      const int hb = i % kHBufs;
+      const uint32_t hrow = sb + kOffH + hb * kHTile + (cq >> 1) * (kHTile / 2) + r * 128;
       const uint32_t cbase = (uint32_t)(4 * (cq & 1)), swz = (uint32_t)(r & 7);
-      mbar_wait_fast(bar_hfull(buf), (i >> 1) & 1);
+      mbar_wait_fast(bar_hfull(hb), (i / kHBufs) & 1);
       uint4 hv[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) hv[q] = lds128(hrow + (((cbase + q) ^ swz) << 4));
@@ -240,7 +250,7 @@ mlp_dgelu_gemm_kernel(const __grid_constant__ GemmMaps maps, const bf16* __restr
       }
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_hwritten(buf));
+      if (lane == 0) mbar_arrive(bar_hwritten(hb));
       // column sums over the warp's 32 rows: butterfly transpose-reduce, lane L ends with column L of the chunk
 #pragma unroll
       for (int o = 16; o >= 1; o >>= 1) {
@@ -290,6 +300,193 @@ int make_map_2d(CUtensorMap* m, const void* base, int64_t inner, int64_t outer, 
   return HV_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Forward: h = x W1^T (bf16, WITHOUT the fc1 bias: what the backward kernels read) and a = GELU(h + b1) from ONE GEMM
+// (reference swinv2.py:60-62).  Same machine mapping; B = W1 (4C, C) is K-major as stored (one M = 128, N = 128 MMA per
+// k-step), the epilogue writes both tiles to shared memory and the store warp sends them out by TMA.  Without it the step
+// runs the cuBLAS GEMM (writes h) and the bias+GELU kernel (reads h, writes a): this kernel saves the read.
+// GELU(x) = x Phi(x) with the fitted tanh form of bias_gelu.cu (gelu_parts_bf16x2<false>), two elements at a time
+__device__ __forceinline__ float2 gelu2(float2 x) {
+  constexpr float c1 = 0.7974857091903687f, c3 = 0.03703207150101662f, c5 = -0.000356393022229895f;
+  const float2 half = make_float2(0.5f, 0.5f);
+  float2 x2 = __fmul2_rn(x, x);
+  x2 = make_float2(fminf(x2.x, 64.0f), fminf(x2.y, 64.0f));
+  const float2 u = __fmul2_rn(x, __ffma2_rn(x2, __ffma2_rn(x2, make_float2(c5, c5), make_float2(c3, c3)), make_float2(c1, c1)));
+  const float2 t = make_float2(tanh_fast(u.x), tanh_fast(u.y));
+  return __fmul2_rn(x, __ffma2_rn(half, t, half));
+}
+
+struct FwdGemmMaps { CUtensorMap a, b, h, act; };  // x, W1 (loads), h, a (stores)
+constexpr int kOTile = 2 * kHTile;  // h tile + a tile of one 128 x 128 output tile
+template <int kStages, int kOBufs> struct FwdLayout {
+  static constexpr int kOffO = kStages * kStage;
+  static constexpr int kOffBar = kOffO + kOBufs * kOTile;
+  static constexpr int kNumBars = 2 * kStages + 4 + 2 * kOBufs;
+  static constexpr int kOffTmem = kOffBar + kNumBars * 8;
+  static constexpr int kSmem = kOffTmem + 16;
+  static_assert(kSmem <= 227 * 1024, "shared memory budget");
+};
+
+template <int kStages, int kOBufs>
+__global__ void __launch_bounds__(kThreads, 1)
+mlp_fc1_gelu_gemm_kernel(const __grid_constant__ FwdGemmMaps maps, const float* __restrict__ b1, int M, int N, int K) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  using L = FwdLayout<kStages, kOBufs>;
+  constexpr int kOffO = L::kOffO, kOffBar = L::kOffBar, kOffTmem = L::kOffTmem;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t sb = smem_u32(smem);
+  const uint32_t bar0 = sb + kOffBar;
+  auto bar_full = [&](int s) { return bar0 + 8 * s; };
+  auto bar_empty = [&](int s) { return bar0 + 8 * (kStages + s); };
+  auto bar_acc = [&](int b) { return bar0 + 8 * (2 * kStages + b); };
+  auto bar_accfree = [&](int b) { return bar0 + 8 * (2 * kStages + 2 + b); };
+  auto bar_owritten = [&](int b) { return bar0 + 8 * (2 * kStages + 4 + b); };        // both output tiles written
+  auto bar_ofree = [&](int b) { return bar0 + 8 * (2 * kStages + 4 + kOBufs + b); };  // ... and read by the TMA stores
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmem);
+
+  const int n_tiles = N / kBN, m_tiles = M / kBM;
+  const int kblocks = (K + kBK - 1) / kBK;
+  const int n0 = ((int)blockIdx.x % n_tiles) * kBN;
+  const int m_first = (int)blockIdx.x / n_tiles, m_stride = (int)gridDim.x / n_tiles;
+  const int my_tiles = m_first < m_tiles ? (m_tiles - m_first + m_stride - 1) / m_stride : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_acc(b), 1);
+      mbar_init(bar_accfree(b), 16);
+    }
+    for (int b = 0; b < kOBufs; ++b) {
+      mbar_init(bar_owritten(b), 16);
+      mbar_init(bar_ofree(b), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer: x tile (128 rows x 64 k), W1 tile (128 units x 64 k)
+    int it = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int m0 = (m_first + i * m_stride) * kBM;
+      for (int kb = 0; kb < kblocks; ++kb, ++it) {
+        const int s = it % kStages;
+        mbar_wait_fast(bar_empty(s), ((it / kStages) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(bar_full(s), kStage);
+          const uint32_t dst = sb + kOffStage + s * kStage;
+          asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(&maps.a)), "r"(bar_full(s)), "r"(kb * kBK), "r"(m0) : "memory");
+          asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                       ::"r"(dst + kStageA), "l"(reinterpret_cast<uint64_t>(&maps.b)), "r"(bar_full(s)), "r"(kb * kBK), "r"(n0) : "memory");
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer: D[128 x 128] += A (K-major) x B (K-major)
+    const uint32_t id = idesc_bf16(128, 128, 0, 0);
+    const uint64_t d_a = smem_desc(sb + kOffStage, 16, 1024, 2);
+    const uint64_t d_b = smem_desc(sb + kOffStage + kStageA, 16, 1024, 2);
+    int it = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int buf = i & 1;
+      if (i > 1) mbar_wait_fast(bar_accfree(buf), ((i >> 1) - 1) & 1);
+      tc_fence_after();
+      for (int kb = 0; kb < kblocks; ++kb, ++it) {
+        const int s = it % kStages;
+        mbar_wait_fast(bar_full(s), (it / kStages) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t so = (uint64_t)((s * kStage) >> 4);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)  // 16 k per step: both operands += 32 B inside the swizzle atom
+            umma_ss(tmem + 128 * buf, d_a + so + (uint64_t)(2 * ks), d_b + so + (uint64_t)(2 * ks), id, (kb > 0 || ks > 0) ? 1u : 0u);
+          umma_commit(bar_empty(s));
+          if (kb == kblocks - 1) umma_commit(bar_acc(buf));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 2) {
+    // ---------------------------------------------------------------- TMA stores of the h and a tiles
+    for (int i = 0; i < my_tiles; ++i) {
+      const int m0 = (m_first + i * m_stride) * kBM, ob = i % kOBufs;
+      mbar_wait_fast(bar_owritten(ob), (i / kOBufs) & 1);
+      if (elect_one()) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {  // h sub-tiles 0, 1; a sub-tiles 0, 1
+          const CUtensorMap* mm = t < 2 ? &maps.h : &maps.act;
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                       ::"l"(reinterpret_cast<uint64_t>(mm)), "r"(sb + kOffO + ob * kOTile + t * (kHTile / 2)), "r"(n0 + 64 * (t & 1)),
+                         "r"(m0) : "memory");
+        }
+      }
+      __syncwarp();
+      bulk_commit();
+      bulk_wait_read0();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_ofree(ob));
+    }
+    bulk_wait0();
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- epilogue: rows 32 quad .. of the tile, columns 32 cq ..
+    const int quad = warp & 3, cq = (warp - 4) >> 2;
+    const uint32_t tl = tmem + ((uint32_t)(quad * 32) << 16) + 32 * cq;
+    const int nc = n0 + 32 * cq;
+    float2 bias[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) bias[q] = make_float2(__ldg(b1 + nc + 2 * q), __ldg(b1 + nc + 2 * q + 1));
+    const int r = 32 * quad + lane;
+    const uint32_t cbase = (uint32_t)(4 * (cq & 1)), swz = (uint32_t)(r & 7);
+    for (int i = 0; i < my_tiles; ++i) {
+      const int buf = i & 1, ob = i % kOBufs;
+      const uint32_t hrow = sb + kOffO + ob * kOTile + (cq >> 1) * (kHTile / 2) + r * 128;  // the a tile follows at + kHTile
+      mbar_wait_fast(bar_acc(buf), (i >> 1) & 1);
+      tc_fence_after();
+      uint32_t acc[32];
+      HV_TMEM_LD32(tl + 128 * buf, acc);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_accfree(buf));
+      if (i >= kOBufs) mbar_wait_fast(bar_ofree(ob), ((i / kOBufs) - 1) & 1);  // the stores of tile i - kOBufs have read the buffer
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t ho[4], ao[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          ho[e] = pack_bf16x2(__uint_as_float(acc[8 * q + 2 * e]), __uint_as_float(acc[8 * q + 2 * e + 1]));
+          // the activation is computed from the ROUNDED h, the value the backward kernels will read
+          const float2 x = __fadd2_rn(make_float2(bf16lo_to_f32(ho[e]), bf16hi_to_f32(ho[e])), bias[4 * q + e]);
+          const float2 g = gelu2(x);
+          ao[e] = pack_bf16x2(g.x, g.y);
+        }
+        const uint32_t off = ((cbase + q) ^ swz) << 4;
+        sts128(hrow + off, make_uint4(ho[0], ho[1], ho[2], ho[3]));
+        sts128(hrow + kHTile + off, make_uint4(ao[0], ao[1], ao[2], ao[3]));
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_owritten(ob));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols));
+}
+
 }  // namespace
 
 bool mlp_dgelu_gemm_supported(int64_t M, int N, int K) {
@@ -333,7 +530,8 @@ int mlp_dgelu_gemm(const void* dy, const void* w2, const void* h, const float* b
   int dev = 0;
   HV_CUDA_OK(cudaGetDevice(&dev));
   if (attr_dev != dev) {
-    HV_CUDA_OK(cudaFuncSetAttribute(mlp_dgelu_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    HV_CUDA_OK(cudaFuncSetAttribute(mlp_dgelu_gemm_kernel<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Layout<3, 3>::kSmem));
+    HV_CUDA_OK(cudaFuncSetAttribute(mlp_dgelu_gemm_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Layout<4, 2>::kSmem));
     attr_dev = dev;
   }
   const int n_tiles = N / kBN, m_tiles = (int)(M / kBM);
@@ -342,11 +540,65 @@ int mlp_dgelu_gemm(const void* dy, const void* w2, const void* h, const float* b
   if (per_col > m_tiles) per_col = m_tiles;
   const int grid = per_col * n_tiles;
   float* partials = static_cast<float*>(workspace);
-  mlp_dgelu_gemm_kernel<<<grid, kThreads, kSmem, st>>>(*mp, static_cast<const bf16*>(h), b1, static_cast<bf16*>(dh), partials,
-                                                       (int)M, N, K);
+  if (K <= 192)
+    mlp_dgelu_gemm_kernel<3, 3><<<grid, kThreads, Layout<3, 3>::kSmem, st>>>(*mp, static_cast<const bf16*>(h), b1,
+                                                                            static_cast<bf16*>(dh), partials, (int)M, N, K);
+  else
+    mlp_dgelu_gemm_kernel<4, 2><<<grid, kThreads, Layout<4, 2>::kSmem, st>>>(*mp, static_cast<const bf16*>(h), b1,
+                                                                            static_cast<bf16*>(dh), partials, (int)M, N, K);
   HV_LAUNCH_OK("mlp_dgelu_gemm_kernel");
   mlp_dgelu_fold_kernel<<<(N + 255) / 256, 256, 0, st>>>(partials, db1, N, n_tiles, grid);
   HV_LAUNCH_OK("mlp_dgelu_fold_kernel");
+  return HV_OK;
+}
+
+
+int mlp_fc1_gelu_gemm(const void* x, const void* w1, const float* b1, void* h, void* act, int64_t M, int N, int K, cudaStream_t st) {
+  if (!mlp_dgelu_gemm_supported(M, N, K)) HV_FAIL(HV_ERR_SHAPE, "mlp_fc1_gelu_gemm: M=%lld N=%d K=%d", (long long)M, N, K);
+  if (!aligned16(x) || !aligned16(w1) || !aligned16(h) || !aligned16(act) || !aligned16(b1))
+    HV_FAIL(HV_ERR_ALIGN, "mlp_fc1_gelu_gemm: pointers must be 16-byte aligned");
+  struct MapKey { const void *x, *w1, *h, *act; int64_t M; int N, K; };
+  struct MapEntry { MapKey key; FwdGemmMaps maps; };
+  static thread_local MapEntry cache[32];
+  static thread_local int cache_n = 0, cache_next = 0;
+  const FwdGemmMaps* mp = nullptr;
+  for (int i = 0; i < cache_n; ++i) {
+    const MapKey& c = cache[i].key;
+    if (c.x == x && c.w1 == w1 && c.h == h && c.act == act && c.M == M && c.N == N && c.K == K) { mp = &cache[i].maps; break; }
+  }
+  if (!mp) {
+    MapEntry& e = cache[cache_next];
+    int rc = make_map_2d(&e.maps.a, x, K, M, kBK, kBM);   // x (M, K): box 64 k x 128 rows
+    if (rc) return rc;
+    rc = make_map_2d(&e.maps.b, w1, K, N, kBK, kBN);      // W1 (N, K): box 64 k x 128 hidden units
+    if (rc) return rc;
+    rc = make_map_2d(&e.maps.h, h, N, M, 64, kBM);
+    if (rc) return rc;
+    rc = make_map_2d(&e.maps.act, act, N, M, 64, kBM);
+    if (rc) return rc;
+    e.key = MapKey{x, w1, h, act, M, N, K};
+    mp = &e.maps;
+    cache_next = (cache_next + 1) % 32;
+    if (cache_n < 32) ++cache_n;
+  }
+  static thread_local int attr_dev = -1;
+  int dev = 0;
+  HV_CUDA_OK(cudaGetDevice(&dev));
+  if (attr_dev != dev) {
+    HV_CUDA_OK(cudaFuncSetAttribute(mlp_fc1_gelu_gemm_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdLayout<3, 2>::kSmem));
+    HV_CUDA_OK(cudaFuncSetAttribute(mlp_fc1_gelu_gemm_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdLayout<4, 1>::kSmem));
+    attr_dev = dev;
+  }
+  const int n_tiles = N / kBN, m_tiles = (int)(M / kBM);
+  int per_col = num_sms() / n_tiles;
+  if (per_col < 1) per_col = 1;
+  if (per_col > m_tiles) per_col = m_tiles;
+  const int grid = per_col * n_tiles;
+  if (K <= 192)
+    mlp_fc1_gelu_gemm_kernel<3, 2><<<grid, kThreads, FwdLayout<3, 2>::kSmem, st>>>(*mp, b1, (int)M, N, K);
+  else
+    mlp_fc1_gelu_gemm_kernel<4, 1><<<grid, kThreads, FwdLayout<4, 1>::kSmem, st>>>(*mp, b1, (int)M, N, K);
+  HV_LAUNCH_OK("mlp_fc1_gelu_gemm_kernel");
   return HV_OK;
 }
 

@@ -578,6 +578,90 @@ class _GeluFc2(torch.autograd.Function):
         return dh, (db1.to(bdt) if db1 is not None else None), dw2
 
 
+# the fused forward GEMM (hv_mlp_fc1_gelu_gemm: h and GELU(h + b1) from one kernel) where it beats cuBLAS + hv_bias_gelu_fwd:
+# measured faster up to C = 192, level at 384, slower at 768 (a 128 x 128 single-CTA tile is not a cuBLAS-class mainloop)
+MLP_FC1_GELU_GEMM_MAX_C = int(os.environ.get("HV_MLP_FC1_GELU_GEMM_MAX_C", "192"))
+
+
+class _MlpFused(torch.autograd.Function):
+    """(m, x) with m = GELU_erf(x W1^T + b1) W2^T (the fc2 bias is left to the caller) for bf16 activations: the whole Mlp of
+    reference swinv2.py:43-66 as ONE autograd node.  Forward: h = x W1^T and a = GELU(h + b1) from one tcgen05 GEMM where
+    that is faster than cuBLAS + the activation kernel, then the fc2 GEMM.  Backward: dh = (dm W2) * GELU'(h + b1) and
+    db1 from one tcgen05 GEMM (hv_mlp_dgelu_gemm), the weight gradients in fp32, and dx = dh W1 accumulated onto the
+    gradient of the residual shortcut (second output) inside the GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2):
+        _need_cuda(x, "mlp_fused")
+        lib = _lib.load()
+        x = x.contiguous()
+        C = x.shape[-1]
+        rows = x.numel() // C
+        hidden = w1.shape[0]
+        w1s, w2s = weight_shadow(w1, x.dtype), weight_shadow(w2, x.dtype)
+        b32 = _f32c(b1)
+        x2 = x.view(rows, C)
+        global LAUNCH_COUNT
+        with torch.cuda.device(x.device):
+            fused = C <= MLP_FC1_GELU_GEMM_MAX_C and int(lib.hv_mlp_dgelu_gemm_workspace_bytes(rows, hidden, C)) > 0
+            if fused:
+                h = torch.empty((rows, hidden), dtype=x.dtype, device=x.device)
+                a = torch.empty_like(h)
+                check(lib.hv_mlp_fc1_gelu_gemm(_ptr(x2), _ptr(w1s), _ptr(b32), _ptr(h), _ptr(a), rows, hidden, C, _code(x),
+                                               _stream(x.device)), "hv_mlp_fc1_gelu_gemm")
+            else:
+                h = torch.mm(x2, w1s.t())
+                a = torch.empty_like(h)
+                check(lib.hv_bias_gelu_fwd(_ptr(h), _ptr(b32), _ptr(a), rows, hidden, _code(h), _stream(h.device)), "hv_bias_gelu_fwd")
+        LAUNCH_COUNT += 1
+        ctx.save_for_backward(x2, w1s, h, b32, a, w2s)
+        ctx.meta = (x.shape, b1.dtype, w1.dtype, w2.dtype)
+        m = torch.mm(a, w2s.t()).view(*x.shape[:-1], w2.shape[0])
+        return m, x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dm, dx_shortcut):
+        x2, w1s, h, b32, a, w2s = ctx.saved_tensors
+        xshape, bdt, w1dt, w2dt = ctx.meta
+        lib = _lib.load()
+        rows, C = x2.shape
+        hidden = h.shape[1]
+        Co = w2s.shape[0]
+        dm2 = dm.reshape(rows, Co)
+        if dm2.dtype != h.dtype:
+            dm2 = dm2.to(h.dtype)
+        dm2 = dm2.contiguous()
+        dh = torch.empty_like(h)
+        db1 = torch.empty_like(b32)
+        global LAUNCH_COUNT
+        with torch.cuda.device(h.device):
+            nb = int(lib.hv_mlp_dgelu_gemm_workspace_bytes(rows, hidden, Co)) if Co <= MLP_DGELU_GEMM_MAX_C else 0
+            if nb > 0:
+                ws = torch.empty((nb,), dtype=torch.uint8, device=h.device)
+                check(lib.hv_mlp_dgelu_gemm(_ptr(dm2), _ptr(w2s), _ptr(h), _ptr(b32), _ptr(dh), _ptr(db1), _ptr(ws), nb, rows, hidden,
+                                            Co, _code(h), _stream(h.device)), "hv_mlp_dgelu_gemm")
+            else:  # the two-kernel path: dgrad GEMM, then the bias + GELU backward
+                da = torch.mm(dm2, w2s)
+                nb = int(lib.hv_bias_gelu_bwd_workspace_bytes(rows, hidden))
+                ws = torch.empty((nb,), dtype=torch.uint8, device=h.device)
+                check(lib.hv_bias_gelu_bwd(_ptr(da), _ptr(h), _ptr(b32), _ptr(dh), _ptr(db1), _ptr(ws), ws.numel(), rows, hidden,
+                                           _code(h), _stream(h.device)), "hv_bias_gelu_bwd")
+        LAUNCH_COUNT += 2
+        dw2 = _weight_grad(dm2.t(), a, w2dt) if ctx.needs_input_grad[3] else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = _dx_with_shortcut(dx_shortcut, dh, w1s, xshape)
+        elif dx_shortcut is not None:
+            dx = dx_shortcut
+        dw1 = _weight_grad(dh.t(), x2, w1dt) if ctx.needs_input_grad[1] else None
+        return dx, dw1, (db1.to(bdt) if ctx.needs_input_grad[2] else None), dw2
+
+
+def mlp_fused(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor):
+    """Returns (GELU(x w1^T + b1) w2^T, x): bf16 ``x`` (..., C); use the returned x for the residual shortcut."""
+    return _MlpFused.apply(x, w1, b1, w2)
+
+
 def gelu_fc2(h: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor) -> torch.Tensor:
     """GELU(h + b1) @ w2^T for the bias-free fc1 output ``h`` (..., hidden) and ``w2`` = fc2.weight (C, hidden)."""
     return _GeluFc2.apply(h, b1, w2)

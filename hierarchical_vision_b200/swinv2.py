@@ -149,6 +149,12 @@ class Mlp(nn.Module):
         sc = x
         fused = (type(self.act) is nn.GELU and getattr(self.act, "approximate", "none") == "none" and self.fc1.bias is not None
                  and self.drop.p == 0.0 and x.is_cuda)
+        if fused and x.dtype == torch.bfloat16 and self.fc1.out_features % 128 == 0 \
+                and self.fc2.in_features == self.fc1.out_features and (
+                    (torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16)
+                    or self.fc1.weight.dtype == torch.bfloat16):
+            # bf16 activations: the whole Mlp as one autograd node (fused fc1 + GELU GEMM, fused dGELU GEMM in the backward)
+            return hvf.mlp_fused(x, self.fc1.weight, self.fc1.bias, self.fc2.weight)
         if fused:
             if with_shortcut and torch.is_autocast_enabled("cuda") and x.dtype == torch.get_autocast_dtype("cuda"):
                 h, sc = hvf.linear_shortcut(x, self.fc1.weight)

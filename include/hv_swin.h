@@ -186,6 +186,12 @@ HV_API int hv_ln_residual_bwd(const void* dout, const void* y, const float* gamm
  * Requires rows % 128 == 0, hidden % 128 == 0, hidden <= 4096, C % 8 == 0 (hv_mlp_dgelu_gemm_workspace_bytes returns 0
  * otherwise; callers then use the two-kernel path). */
 HV_API size_t hv_mlp_dgelu_gemm_workspace_bytes(int64_t rows, int hidden, int C);
+/* Forward counterpart (reference swinv2.py:60-62): h = x W1^T (rows, hidden) bf16 WITHOUT the fc1 bias (what the backward
+ * kernels read) and act = GELU(h + b1) from one tcgen05 GEMM; x (rows, C), w1 = fc1.weight (hidden, C) as stored.  Replaces
+ * the fc1 GEMM + hv_bias_gelu_fwd (h is written once and never re-read in the forward).  Same shape conditions as
+ * hv_mlp_dgelu_gemm (query them with hv_mlp_dgelu_gemm_workspace_bytes != 0). */
+HV_API int hv_mlp_fc1_gelu_gemm(const void* x, const void* w1, const float* b1, void* h, void* act, int64_t rows, int hidden,
+                                int C, int dtype, void* stream);
 HV_API int hv_mlp_dgelu_gemm(const void* dy, const void* w2, const void* h, const float* b1, void* dh, float* db1,
                              void* workspace, size_t workspace_bytes, int64_t rows, int hidden, int C, int dtype, void* stream);
 

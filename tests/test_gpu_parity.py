@@ -761,6 +761,42 @@ def test_gelu_fc2_fused_backward_gemm(shape, force_fused):
     assert_close("dw2", w2.grad, w64.grad, 2e-2)
 
 
+@pytest.mark.parametrize("shape", [(512, 96), (256, 192), (128, 384), (128, 768), (200, 96)])
+@pytest.mark.parametrize("force_fused", [False, True])
+def test_mlp_fused_node(shape, force_fused):
+    """The whole Mlp (swinv2.py:43-66) as one autograd node: forward through the fused fc1 + GELU tcgen05 GEMM (C up to the
+    dispatch limit, or forced) or cuBLAS + the activation kernel, backward through the fused dGELU GEMM or the two-kernel
+    path; outputs, dx (with the residual shortcut's gradient accumulated in the dx GEMM), dW1, db1, dW2 against torch in
+    fp64 on the same bf16 inputs."""
+    rows, C = shape
+    hidden = 4 * C
+    gen = torch.Generator().manual_seed(rows * 7 + C)
+    x = torch.randn(2, rows // 2, C, generator=gen).to(DEV, torch.bfloat16).requires_grad_(True)
+    w1 = (torch.randn(hidden, C, generator=gen) / C ** 0.5).to(DEV, torch.bfloat16).requires_grad_(True)
+    b1 = (0.5 * torch.randn(hidden, generator=gen)).to(DEV).requires_grad_(True)
+    w2 = (torch.randn(C, hidden, generator=gen) / hidden ** 0.5).to(DEV, torch.bfloat16).requires_grad_(True)
+    dm = torch.randn(2, rows // 2, C, generator=gen).to(DEV, torch.bfloat16)
+    dsc = torch.randn(2, rows // 2, C, generator=gen).to(DEV, torch.bfloat16)
+    old = (hvf.MLP_DGELU_GEMM_MAX_C, hvf.MLP_FC1_GELU_GEMM_MAX_C)
+    if force_fused:
+        hvf.MLP_DGELU_GEMM_MAX_C = hvf.MLP_FC1_GELU_GEMM_MAX_C = 4096
+    try:
+        m, sc = hvf.mlp_fused(x, w1, b1, w2)
+        torch.autograd.backward([m, sc], [dm, dsc])
+        torch.cuda.synchronize()
+    finally:
+        hvf.MLP_DGELU_GEMM_MAX_C, hvf.MLP_FC1_GELU_GEMM_MAX_C = old
+    x64, w164, b64, w264 = (t.detach().double().cpu().requires_grad_(True) for t in (x, w1, b1, w2))
+    want = torch.nn.functional.gelu(x64 @ w164.t() + b64) @ w264.t()
+    torch.autograd.backward([want, x64 * 1.0], [dm.double().cpu(), dsc.double().cpu()])
+    assert torch.equal(sc, x)
+    assert_close("m", m, want, 2e-2)
+    assert_close("dx", x.grad, x64.grad, 2e-2)
+    assert_close("dw1", w1.grad, w164.grad, 2e-2)
+    assert_close("db1", b1.grad, b64.grad, 2e-2)
+    assert_close("dw2", w2.grad, w264.grad, 2e-2)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("classes", [3, 273, 10000])
 @pytest.mark.parametrize("smoothing", [0.0, 0.1])

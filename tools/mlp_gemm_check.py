@@ -35,6 +35,16 @@ def fused(dy, w2, h, b1):
     return dh, db1
 
 
+def fused_fwd(x, w1, b1):
+    M, C = x.shape
+    N = w1.shape[0]
+    hh = torch.empty((M, N), dtype=torch.bfloat16, device=dev)
+    act = torch.empty((M, N), dtype=torch.bfloat16, device=dev)
+    check(lib.hv_mlp_fc1_gelu_gemm(_ptr(x), _ptr(w1), _ptr(b1), _ptr(hh), _ptr(act), M, N, C, 1, _stream(x.device)),
+          "hv_mlp_fc1_gelu_gemm")
+    return hh, act
+
+
 def timeit(fn, iters):
     for _ in range(3):
         fn()
@@ -81,6 +91,24 @@ for res, C in ((64, 96), (32, 192), (16, 384), (8, 768)):
     o2, d2 = two_kernel()
     err2 = ((dh.float() - o2.float()).norm() / o2.float().norm()).item()
     t_2 = timeit(two_kernel, a.iters)
+    # ---- forward: h = x W1^T, a = GELU(h + b1)
+    x = torch.randn(M, C, device=dev, generator=g).to(torch.bfloat16)
+    w1 = (torch.randn(N, C, device=dev, generator=g) / C ** 0.5).to(torch.bfloat16)
+    hh, act = fused_fwd(x, w1, b1)
+    torch.cuda.synchronize()
+    h_ref = x[rows].float() @ w1.float().t()
+    a_ref = torch.nn.functional.gelu(h_ref + b1)
+    eh = ((hh[rows].float() - h_ref).norm() / h_ref.norm()).item()
+    ea = ((act[rows].float() - a_ref).norm() / a_ref.norm()).item()
+    t_ff = timeit(lambda: fused_fwd(x, w1, b1), a.iters)
+
+    def two_kernel_fwd():
+        h2 = x @ w1.t()
+        return h2, hvf.bias_gelu(h2, b1)
+
+    t_f2 = timeit(two_kernel_fwd, a.iters)
+    print(f"C {C:4d} forward: h {eh:.2e} a {ea:.2e} | fused {t_ff:.3f} ms ({(M * N * 4 + M * C * 2) / t_ff / 1e6:.0f} GB/s) vs GEMM + bias_gelu "
+          f"{t_f2:.3f} ms", flush=True)
     nbytes = M * N * 2 * 2 + M * C * 2
     print(f"C {C:4d} M {M:8d}: dh rel-L2 vs torch {err:.2e}, vs two-kernel path {err2:.2e}, db1 {err_b:.2e} | fused {t_f:.3f} ms "
           f"({nbytes / t_f / 1e6:.0f} GB/s) vs GEMM + bias_gelu_bwd {t_2:.3f} ms", flush=True)
