@@ -30,8 +30,24 @@ namespace {
 using namespace tc;
 
 constexpr int kBM = 128, kBN = 128, kBK = 64;
-// ring depths are template parameters: (operand stages, h / dh tiles in flight) = (3, 3) for C <= 192 (two or three k-blocks
-// per tile: the kernel is a stream of h / dh tiles), (4, 2) beyond (the mainloop needs the deeper operand ring)
+#ifndef HV_GEMM_LK_STAGES
+#define HV_GEMM_LK_STAGES 4
+#endif
+#ifndef HV_GEMM_LK_HBUFS
+#define HV_GEMM_LK_HBUFS 2
+#endif
+#ifndef HV_GEMM_LK_FSTAGES
+#define HV_GEMM_LK_FSTAGES 5
+#endif
+#ifndef HV_GEMM_SK_STAGES
+#define HV_GEMM_SK_STAGES 3
+#endif
+#ifndef HV_GEMM_SK_HBUFS
+#define HV_GEMM_SK_HBUFS 3
+#endif
+// ring depths are template parameters: backward (operand stages, h / dh tiles in flight) = (3, 3) for C <= 192 (two or three
+// k-blocks per tile: the kernel is a stream of h / dh tiles), (4, 2) beyond; forward (stages, output buffers) = (3, 2) / (5, 1):
+// at C = 384 five stages took the forward from 0.145 to 0.133 ms (load latency), the backward did not move (0.161-0.163)
 constexpr int kStageA = kBM * kBK * 2;       // 16 KB
 constexpr int kStageB = kBK * kBN * 2;       // 16 KB: two sub-tiles of 64 k-rows x 128 B
 constexpr int kStage = kStageA + kStageB;
@@ -470,7 +486,11 @@ mlp_fc1_gelu_gemm_kernel(const __grid_constant__ FwdGemmMaps maps, const float* 
           ho[e] = pack_bf16x2(__uint_as_float(acc[8 * q + 2 * e]), __uint_as_float(acc[8 * q + 2 * e + 1]));
           // the activation is computed from the ROUNDED h, the value the backward kernels will read
           const float2 x = __fadd2_rn(make_float2(bf16lo_to_f32(ho[e]), bf16hi_to_f32(ho[e])), bias[4 * q + e]);
+#ifdef HV_GEMM_KO_MATH
+          const float2 g = x;
+#else
           const float2 g = gelu2(x);
+#endif
           ao[e] = pack_bf16x2(g.x, g.y);
         }
         const uint32_t off = ((cbase + q) ^ swz) << 4;
@@ -530,8 +550,8 @@ int mlp_dgelu_gemm(const void* dy, const void* w2, const void* h, const float* b
   int dev = 0;
   HV_CUDA_OK(cudaGetDevice(&dev));
   if (attr_dev != dev) {
-    HV_CUDA_OK(cudaFuncSetAttribute(mlp_dgelu_gemm_kernel<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Layout<3, 3>::kSmem));
-    HV_CUDA_OK(cudaFuncSetAttribute(mlp_dgelu_gemm_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Layout<4, 2>::kSmem));
+    HV_CUDA_OK(cudaFuncSetAttribute(mlp_dgelu_gemm_kernel<HV_GEMM_SK_STAGES, HV_GEMM_SK_HBUFS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Layout<HV_GEMM_SK_STAGES, HV_GEMM_SK_HBUFS>::kSmem));
+    HV_CUDA_OK(cudaFuncSetAttribute(mlp_dgelu_gemm_kernel<HV_GEMM_LK_STAGES, HV_GEMM_LK_HBUFS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Layout<HV_GEMM_LK_STAGES, HV_GEMM_LK_HBUFS>::kSmem));
     attr_dev = dev;
   }
   const int n_tiles = N / kBN, m_tiles = (int)(M / kBM);
@@ -541,10 +561,10 @@ int mlp_dgelu_gemm(const void* dy, const void* w2, const void* h, const float* b
   const int grid = per_col * n_tiles;
   float* partials = static_cast<float*>(workspace);
   if (K <= 192)
-    mlp_dgelu_gemm_kernel<3, 3><<<grid, kThreads, Layout<3, 3>::kSmem, st>>>(*mp, static_cast<const bf16*>(h), b1,
+    mlp_dgelu_gemm_kernel<HV_GEMM_SK_STAGES, HV_GEMM_SK_HBUFS><<<grid, kThreads, Layout<HV_GEMM_SK_STAGES, HV_GEMM_SK_HBUFS>::kSmem, st>>>(*mp, static_cast<const bf16*>(h), b1,
                                                                             static_cast<bf16*>(dh), partials, (int)M, N, K);
   else
-    mlp_dgelu_gemm_kernel<4, 2><<<grid, kThreads, Layout<4, 2>::kSmem, st>>>(*mp, static_cast<const bf16*>(h), b1,
+    mlp_dgelu_gemm_kernel<HV_GEMM_LK_STAGES, HV_GEMM_LK_HBUFS><<<grid, kThreads, Layout<HV_GEMM_LK_STAGES, HV_GEMM_LK_HBUFS>::kSmem, st>>>(*mp, static_cast<const bf16*>(h), b1,
                                                                             static_cast<bf16*>(dh), partials, (int)M, N, K);
   HV_LAUNCH_OK("mlp_dgelu_gemm_kernel");
   mlp_dgelu_fold_kernel<<<(N + 255) / 256, 256, 0, st>>>(partials, db1, N, n_tiles, grid);
@@ -586,7 +606,7 @@ int mlp_fc1_gelu_gemm(const void* x, const void* w1, const float* b1, void* h, v
   HV_CUDA_OK(cudaGetDevice(&dev));
   if (attr_dev != dev) {
     HV_CUDA_OK(cudaFuncSetAttribute(mlp_fc1_gelu_gemm_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdLayout<3, 2>::kSmem));
-    HV_CUDA_OK(cudaFuncSetAttribute(mlp_fc1_gelu_gemm_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdLayout<4, 1>::kSmem));
+    HV_CUDA_OK(cudaFuncSetAttribute(mlp_fc1_gelu_gemm_kernel<HV_GEMM_LK_FSTAGES, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdLayout<HV_GEMM_LK_FSTAGES, 1>::kSmem));
     attr_dev = dev;
   }
   const int n_tiles = N / kBN, m_tiles = (int)(M / kBM);
@@ -594,10 +614,13 @@ int mlp_fc1_gelu_gemm(const void* x, const void* w1, const float* b1, void* h, v
   if (per_col < 1) per_col = 1;
   if (per_col > m_tiles) per_col = m_tiles;
   const int grid = per_col * n_tiles;
-  if (K <= 192)
+#ifndef HV_GEMM_FWD_SMALLK
+#define HV_GEMM_FWD_SMALLK 192
+#endif
+  if (K <= HV_GEMM_FWD_SMALLK)
     mlp_fc1_gelu_gemm_kernel<3, 2><<<grid, kThreads, FwdLayout<3, 2>::kSmem, st>>>(*mp, b1, (int)M, N, K);
   else
-    mlp_fc1_gelu_gemm_kernel<4, 1><<<grid, kThreads, FwdLayout<4, 1>::kSmem, st>>>(*mp, b1, (int)M, N, K);
+    mlp_fc1_gelu_gemm_kernel<HV_GEMM_LK_FSTAGES, 1><<<grid, kThreads, FwdLayout<HV_GEMM_LK_FSTAGES, 1>::kSmem, st>>>(*mp, b1, (int)M, N, K);
   HV_LAUNCH_OK("mlp_fc1_gelu_gemm_kernel");
   return HV_OK;
 }

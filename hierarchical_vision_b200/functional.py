@@ -579,8 +579,9 @@ class _GeluFc2(torch.autograd.Function):
 
 
 # the fused forward GEMM (hv_mlp_fc1_gelu_gemm: h and GELU(h + b1) from one kernel) where it beats cuBLAS + hv_bias_gelu_fwd:
-# measured faster up to C = 192, level at 384, slower at 768 (a 128 x 128 single-CTA tile is not a cuBLAS-class mainloop)
-MLP_FC1_GELU_GEMM_MAX_C = int(os.environ.get("HV_MLP_FC1_GELU_GEMM_MAX_C", "192"))
+# measured faster up to C = 384 (0.306 / 0.214 / 0.133 ms against 0.474 / 0.239 / 0.143), slower at 768 (a 128 x 128 single-CTA
+# tile is not a cuBLAS-class mainloop)
+MLP_FC1_GELU_GEMM_MAX_C = int(os.environ.get("HV_MLP_FC1_GELU_GEMM_MAX_C", "384"))
 
 
 class _MlpFused(torch.autograd.Function):
