@@ -518,8 +518,9 @@ def bias_gelu(h: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
 
 
 # the fused backward GEMM (hv_mlp_dgelu_gemm) replaces the fc2 dgrad GEMM + hv_bias_gelu_bwd where it is faster than that
-# pair; measured on B200 (tools/mlp_gemm_check.py): faster up to C = 384, level at C = 768.  A test / benchmarking switch.
-MLP_DGELU_GEMM_MAX_C = int(os.environ.get("HV_MLP_DGELU_GEMM_MAX_C", "384"))
+# pair; measured on B200 (tools/mlp_gemm_check.py): faster up to C = 512 (0.123 vs 0.132 ms at the SwinV2-B stage-2 shape),
+# slower at C = 768 (0.123 vs 0.117).  A test / benchmarking switch.
+MLP_DGELU_GEMM_MAX_C = int(os.environ.get("HV_MLP_DGELU_GEMM_MAX_C", "512"))
 
 
 class _GeluFc2(torch.autograd.Function):

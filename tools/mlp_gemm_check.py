@@ -17,6 +17,7 @@ from hierarchical_vision_b200.functional import _ptr, _stream, check  # noqa: E4
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--shapes", default="64:96,32:192,16:384,8:768", help="token-grid side : C per stage (SwinV2-B: 64:128,32:256,16:512)")
 a = ap.parse_args()
 dev = "cuda"
 lib = _lib.load()
@@ -58,7 +59,7 @@ def timeit(fn, iters):
     return e0.elapsed_time(e1) / iters
 
 
-for res, C in ((64, 96), (32, 192), (16, 384), (8, 768)):
+for res, C in [tuple(int(v) for v in item.split(":")) for item in a.shapes.split(",")]:
     M, N = a.batch * res * res, 4 * C
     g = torch.Generator(device=dev).manual_seed(res)
     dy = torch.randn(M, C, device=dev, generator=g).to(torch.bfloat16)
