@@ -53,6 +53,8 @@ CORE_CASES = [
     (2, 32, 48, 128, 4, 16, 0),   # ... unshifted, rectangular grid of windows
     (3, 16, 32, 96, 3, 16, 8),    # ... one row of windows: every window wraps along the rows, the last one in both directions
     (2, 16, 16, 64, 2, 16, 0),    # ... one window per image (stage 2 of SwinV2-B at 256 px)
+    (5, 48, 32, 160, 5, 16, 8),   # ... odd head count and batch: uneven split of the windows over the CTAs of a head
+    (1, 64, 16, 32, 1, 16, 8),    # ... one column of windows: every window wraps along the columns
     (1, 16, 16, 128, 2, 8, 4),    # head dim 64
     (3, 16, 16, 192, 6, 8, 4),    # stage-1 shape of SwinV2-T
     (4, 16, 16, 384, 12, 8, 0),   # stage-2 shape of SwinV2-T (12 heads, 4 windows per image)
@@ -761,7 +763,7 @@ def test_gelu_fc2_fused_backward_gemm(shape, force_fused):
     assert_close("dw2", w2.grad, w64.grad, 2e-2)
 
 
-@pytest.mark.parametrize("shape", [(512, 96), (256, 192), (128, 384), (128, 768), (200, 96)])
+@pytest.mark.parametrize("shape", [(512, 96), (256, 192), (128, 384), (128, 768), (200, 96), (640, 160), (1280, 32)])
 @pytest.mark.parametrize("force_fused", [False, True])
 def test_mlp_fused_node(shape, force_fused):
     """The whole Mlp (swinv2.py:43-66) as one autograd node: forward through the fused fc1 + GELU tcgen05 GEMM (C up to the
