@@ -290,7 +290,8 @@ def run_ours(args):
         # one CUDA graph per step; gradients in one flat buffer, one captured NCCL all-reduce when N > 1
         opt = T.build_optimizer(model, lr=0.05)
         gs = T.GraphedTrainStep(model, opt, env, (dev_img[0], dev_lab[0]), transform=None,
-                                autocast_dtype=torch.bfloat16, clip_norm=2.0, overlap_allreduce=not args.no_overlap)
+                                autocast_dtype=torch.bfloat16, clip_norm=2.0, overlap_allreduce=not args.no_overlap,
+                                fused_optimizer=not args.no_fused_optimizer)
         eager = gs.eager
     else:
         ddp = T.wrap_ddp(model, env, device)
@@ -489,6 +490,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: 256 for swinv2_t, 128 for swinv2_b)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="one all-reduce after the backward instead of per-stage buckets inside it")
+    ap.add_argument("--no-fused-optimizer", action="store_true", help="multi-tensor (foreach) DecoupledSGDW + in-place clip instead of hv_sgdw_step")
     ap.add_argument("--no-graph", action="store_true", help="eager step + DistributedDataParallel instead of the CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

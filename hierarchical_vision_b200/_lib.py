@@ -42,6 +42,7 @@ SIGNATURES = {
     "hv_ln_residual_bwd_workspace_bytes": (_S, [_L, _I]),
     "hv_ln_residual_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _S, _L, _I, _L, _I, _I, _P]),
     "hv_mlp_dgelu_gemm_workspace_bytes": (_S, [_L, _I, _I]),
+    "hv_sgdw_step": (_I, [_P, _P, _I, _P, _P, _P, _F, _P]),
     "hv_mlp_fc1_gelu_gemm": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _I, _P]),
     "hv_mlp_dgelu_gemm": (_I, [_P, _P, _P, _P, _P, _P, _P, _S, _L, _I, _I, _I, _P]),
     "hv_bias_gelu_fwd": (_I, [_P, _P, _P, _L, _I, _I, _P]),

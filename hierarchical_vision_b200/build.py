@@ -17,7 +17,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 BUILD = os.path.join(PKG, "_build")
 LIB = os.path.join(PKG, "libhv_swin.so")
-SOURCES = ["api.cu", "wattn_generic.cu", "wattn_mma64.cu", "wattn_tc64.cu", "wattn_tc64_fwd2.cu", "wattn_tc64_bwd.cu", "wattn_tc256_fwd.cu", "wattn_tc256_bwd.cu", "ln_residual.cu", "bias_gelu.cu", "mlp_dgelu_gemm.cu", "patch_merge.cu", "patch_embed.cu", "cpb_bias.cu", "ce_loss.cu"]
+SOURCES = ["api.cu", "wattn_generic.cu", "wattn_mma64.cu", "wattn_tc64.cu", "wattn_tc64_fwd2.cu", "wattn_tc64_bwd.cu", "wattn_tc256_fwd.cu", "wattn_tc256_bwd.cu", "ln_residual.cu", "bias_gelu.cu", "mlp_dgelu_gemm.cu", "patch_merge.cu", "patch_embed.cu", "cpb_bias.cu", "ce_loss.cu", "sgdw_step.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
           "--expt-relaxed-constexpr", "-Xptxas", "-v"]

@@ -17,6 +17,8 @@ bool wattn_tc64_supported(const Geom& g, int dtype);
 int wattn_fwd_variant_set(int v);
 int wattn_fwd_variant_get();
 bool wattn_tc64_fwd2_supported(const Geom& g, int dtype);
+int sgdw_step(const void* table, const void* chunks, int nchunks, const float* flat, const float* lr, const float* coef,
+              float momentum, cudaStream_t st);
 bool mlp_dgelu_gemm_supported(int64_t M, int N, int K);
 size_t mlp_dgelu_gemm_workspace_bytes(int N);
 int mlp_dgelu_gemm(const void* dy, const void* w2, const void* h, const float* b1, void* dh, float* db1, void* workspace,
@@ -345,6 +347,15 @@ int hv_ln_residual_bwd(const void* dout, const void* y, const float* gamma, cons
   if (rc) return rc;
   return ln_residual_bwd(dout, y, gamma, bias, mean, rstd, keep_scale, dy, dgamma, dbeta, dbias, workspace, workspace_bytes,
                          rows, C, rows_per_sample, y_dtype, res_dtype, static_cast<cudaStream_t>(stream));
+}
+
+int hv_sgdw_step(const void* table, const void* chunks, int nchunks, const float* flat_grad, const float* lr, const float* clip_coef,
+                 float momentum, void* stream) {
+  if (!table || !chunks || !flat_grad || !lr) HV_FAIL(HV_ERR_NULL, "hv_sgdw_step: NULL argument");
+  if (nchunks < 0) HV_FAIL(HV_ERR_SHAPE, "hv_sgdw_step: nchunks=%d", nchunks);
+  int rc = check_device_arch();
+  if (rc) return rc;
+  return sgdw_step(table, chunks, nchunks, flat_grad, lr, clip_coef, momentum, static_cast<cudaStream_t>(stream));
 }
 
 size_t hv_mlp_dgelu_gemm_workspace_bytes(int64_t rows, int hidden, int C) {

@@ -190,6 +190,61 @@ class FlatSGD(torch.optim.Optimizer):
         for g in self.param_groups:
             g["lr"] = float(lr)
 
+    def prepare_fused(self, flat: torch.Tensor) -> bool:
+        """Build the tables of the one-pass kernel (hv_sgdw_step) for gradients that are views into ``flat`` (the layout of
+        GraphedTrainStep).  Returns False (and leaves the multi-tensor path in place) for the nesterov-SGD flavour, CPU
+        tensors or gradients that are not views of ``flat``."""
+        import struct
+
+        self._fused = None
+        if not flat.is_cuda or flat.dtype != torch.float32 or not all(g["decoupled"] for g in self.param_groups):
+            return False
+        recs, chunks = [], []
+        base, esz, moms = flat.data_ptr(), flat.element_size(), {g["momentum"] for g in self.param_groups}
+        if len(moms) != 1:
+            return False
+        for g in self.param_groups:
+            wd_scale = (g["weight_decay"] / g["initial_lr"]) if (g["weight_decay"] != 0.0 and g["initial_lr"] != 0.0) else 0.0
+            for p in g["params"]:
+                if p.grad is None or p.dtype != torch.float32 or not p.is_contiguous() or not p.grad.is_contiguous():
+                    return False
+                goff = (p.grad.data_ptr() - base) // esz
+                if goff < 0 or goff + p.numel() > flat.numel() or (p.grad.data_ptr() - base) % esz:
+                    return False
+                st = self.state[p]
+                if "momentum_buffer" not in st:
+                    st["momentum_buffer"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                buf = st["momentum_buffer"]
+                if not buf.is_contiguous():
+                    return False
+                idx = len(recs)
+                recs.append(struct.pack("<QQqif", p.data_ptr(), buf.data_ptr(), goff, p.numel(), wd_scale))
+                chunks.extend((idx, off) for off in range(0, p.numel(), 4096))
+        dev = flat.device
+        table = torch.frombuffer(bytearray(b"".join(recs)), dtype=torch.uint8).to(dev)
+        chunk_t = torch.tensor(chunks, dtype=torch.int32).reshape(-1, 2).to(dev)
+        self._fused = (table, chunk_t, len(chunks), float(next(iter(moms))), flat)
+        return True
+
+    @torch.no_grad()
+    def step_fused(self, clip_coef: Optional[torch.Tensor] = None) -> None:
+        """The step of every group in ONE kernel (after :meth:`prepare_fused`); ``clip_coef``: device scalar the gradients
+        are multiplied by on the fly (gradient clipping), or None.  The parameters are written through raw pointers: their
+        autograd version counters do not move, so callers refresh weight shadows with ``force=True`` (GraphedTrainStep does)."""
+        from . import _lib
+        from . import functional as hvf
+
+        table, chunk_t, n, mom, flat = self._fused
+        if self.param_groups[0]["lr"] != self._lr_host:
+            self.set_lr(self.param_groups[0]["lr"])
+        lib = _lib.load()
+        with torch.cuda.device(flat.device):
+            rc = lib.hv_sgdw_step(table.data_ptr(), chunk_t.data_ptr(), n, flat.data_ptr(), self.lr_t.data_ptr(),
+                                  clip_coef.data_ptr() if clip_coef is not None else None, mom,
+                                  torch.cuda.current_stream(flat.device).cuda_stream)
+        _lib.check(rc, "hv_sgdw_step")
+        hvf.LAUNCH_COUNT += 1
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
@@ -400,7 +455,7 @@ class GraphedTrainStep:
     def __init__(self, model: "Model", optimizer: torch.optim.Optimizer, env: DistEnv, example_batch, *,
                  transform: Optional[nn.Module] = None, autocast_dtype=torch.bfloat16,
                  clip_norm: Optional[float] = 2.0, warmup: int = 3, overlap_allreduce: bool = True,
-                 min_bucket_numel: int = 1 << 20):
+                 min_bucket_numel: int = 1 << 20, fused_optimizer: bool = True):
         img, lab = example_batch
         if not img.is_cuda:
             raise RuntimeError("GraphedTrainStep needs CUDA tensors")
@@ -422,6 +477,8 @@ class GraphedTrainStep:
         self.sync = BucketedGradSync(params, self.flat, BucketedGradSync.stage_bounds(named, min_bucket_numel),
                                      reduce=env.world_size > 1 and overlap_allreduce)
         self._trailing_allreduce = env.world_size > 1 and not overlap_allreduce
+        # DecoupledSGDW as one pass over (p, buf, g) with the clip coefficient applied on the fly (hv_sgdw_step)
+        self._fused_opt = bool(fused_optimizer and hasattr(optimizer, "prepare_fused") and optimizer.prepare_fused(self.flat))
         self.launches_per_step = 0
         self.graph = None
         self.static_loss = None
@@ -498,6 +555,13 @@ class GraphedTrainStep:
         self.sync.finish()
         if self._trailing_allreduce:
             dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)
+        if self._fused_opt:
+            # clip coefficient on the device, applied to the gradients inside the one-pass optimizer kernel
+            coef = None
+            if self.clip_norm is not None:
+                coef = torch.clamp(self.clip_norm / (torch.linalg.vector_norm(self.flat) + 1e-6), max=1.0)
+            self.optimizer.step_fused(coef)
+            return loss.detach()
         if self.clip_norm is not None:
             # torch.nn.utils.clip_grad_norm_ on the flat view: one norm, one scale
             total = torch.linalg.vector_norm(self.flat)

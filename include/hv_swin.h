@@ -179,6 +179,14 @@ HV_API int hv_ln_residual_bwd(const void* dout, const void* y, const float* gamm
                        float* dbeta, float* dbias, void* workspace, size_t workspace_bytes, int64_t rows, int C,
                        int64_t rows_per_sample, int y_dtype, int res_dtype, void* stream);
 
+/* One-pass DecoupledSGDW step over all parameters (reference optim.py:16-44, configs.py:45; Composer's rule):
+ * g' = g * clip_coef; buf = momentum * buf + g'; p = p * (1 - lr * wd / lr0) - lr * buf, bit-identical to the multi-tensor
+ * path of train.FlatSGD.  `table`: device array of 32-byte records {float* p; float* buf; int64 grad_offset; int32 numel;
+ * float wd_over_lr0}; `chunks`: device array of int32 pairs (record index, element offset), one per 4096 elements of a
+ * tensor; flat_grad: the flat fp32 gradient buffer; lr, clip_coef (may be NULL = 1): device scalars. */
+HV_API int hv_sgdw_step(const void* table, const void* chunks, int nchunks, const float* flat_grad, const float* lr,
+                        const float* clip_coef, float momentum, void* stream);
+
 /* Backward of the Mlp hidden activation fused into the GEMM that produces its upstream gradient (reference swinv2.py:43-66
  * differentiated): dh = (dy W2) * GELU'(h + b1) and db1 = column sums of dh, with dy (rows, C), w2 = fc2.weight (C, hidden)
  * as stored, h = x W1^T (rows, hidden) without the fc1 bias, all bf16; b1, db1 fp32 (hidden).  Replaces the dgrad GEMM of

@@ -732,6 +732,48 @@ def test_bias_gelu_outliers(dtype):
     assert (h.grad.float().cpu() - h64.grad.float()).abs().max() <= (2e-2 if dtype == torch.bfloat16 else 1e-4)
 
 
+@pytest.mark.parametrize("clip", [None, 0.37])
+def test_fused_sgdw_step_is_bit_identical_to_the_multi_tensor_path(clip):
+    """hv_sgdw_step (one pass over p, buf, g with the clip coefficient applied on the fly) against FlatSGD.step after an
+    in-place scaling of the gradients: DecoupledSGDW (optim.py:16-44, configs.py:45), two parameter groups (decay / no
+    decay), tensors whose sizes and offsets break 16-byte alignment, a learning rate that changes between steps."""
+    from hierarchical_vision_b200 import train as T
+
+    gen = torch.Generator().manual_seed(3)
+    shapes = [(96, 288), (288,), (7, 13), (4097,), (1,), (384, 96), (5, 5, 3)]
+
+    def make():
+        ps = [torch.nn.Parameter(torch.randn(*s, generator=torch.Generator().manual_seed(i)).to(DEV)) for i, s in enumerate(shapes)]
+        flat = torch.zeros(sum(p.numel() for p in ps), device=DEV)
+        off = 0
+        for p in ps:
+            p.grad = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        opt = T.FlatSGD([{"params": ps[::2], "weight_decay": 5e-4}, {"params": ps[1::2], "weight_decay": 0.0}], lr=0.05)
+        return ps, flat, opt
+
+    pa, fa, oa = make()
+    pb, fb, ob = make()
+    assert ob.prepare_fused(fb)
+    for step in range(3):
+        g = torch.randn(fa.numel(), generator=gen).to(DEV)
+        fa.copy_(g)
+        fb.copy_(g)
+        lr = 0.05 * (1.0 - 0.3 * step)
+        oa.set_lr(lr)
+        ob.set_lr(lr)
+        coef = None
+        if clip is not None:
+            coef = torch.clamp(clip / (torch.linalg.vector_norm(fb) + 1e-6), max=1.0)
+            fa.mul_(torch.clamp(clip / (torch.linalg.vector_norm(fa) + 1e-6), max=1.0))
+        oa.step()
+        ob.step_fused(coef)
+    torch.cuda.synchronize()
+    for x, y in zip(pa, pb):
+        assert torch.equal(x, y)
+        assert torch.equal(oa.state[x]["momentum_buffer"], ob.state[y]["momentum_buffer"])
+
+
 @pytest.mark.parametrize("shape", [(512, 96), (384, 192), (256, 384), (128, 768), (200, 96), (1024, 32)])
 @pytest.mark.parametrize("force_fused", [False, True])
 def test_gelu_fc2_fused_backward_gemm(shape, force_fused):
