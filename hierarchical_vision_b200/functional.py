@@ -114,6 +114,13 @@ def refresh_weight_shadows(force: bool = False) -> int:
     return len(src)
 
 
+def mark_weight_shadows_stale() -> None:
+    """Host-only: every shadow is refreshed at its next use.  For parameter updates that do not move the autograd version
+    counters: a replayed CUDA graph (no Python runs during a replay) and the one-pass optimizer kernel (raw pointers)."""
+    for ent in _SHADOWS.values():
+        ent[2] = -1
+
+
 def _weight_grad(d2t: torch.Tensor, x2: torch.Tensor, wdtype: torch.dtype) -> torch.Tensor:
     """d2t (N, tokens) @ x2 (tokens, K) in the master weight's dtype, without a separate cast kernel."""
     if wdtype == torch.float32 and d2t.dtype == torch.bfloat16 and x2.dtype == torch.bfloat16 and d2t.is_cuda:

@@ -500,11 +500,21 @@ class GraphedTrainStep:
                                "the CUDA graph; use train.build_optimizer / FlatSGD")
         self.optimizer.set_lr(lr)
 
+    @staticmethod
+    def _after_step() -> None:
+        """The step has changed the master weights without moving their version counters (graph replay / one-pass optimizer
+        kernel): the bf16 shadows are stale for any forward outside this class (evaluation, checkpoint export) until
+        refreshed; the next step refreshes them itself."""
+        from . import functional as hvf
+        hvf.mark_weight_shadows_stale()
+
     def eager(self, img: torch.Tensor, lab: torch.Tensor) -> torch.Tensor:
         """The same step without the graph (warm-up, per-kernel instrumentation, debugging)."""
         self.static_img.copy_(img, non_blocking=True)
         self.static_lab.copy_(lab, non_blocking=True)
-        return self._body()
+        loss = self._body()
+        self._after_step()
+        return loss
 
     def capture(self) -> "GraphedTrainStep":
         dev = self.static_img.device
@@ -592,6 +602,7 @@ class GraphedTrainStep:
         self.static_lab.copy_(dlab, non_blocking=True)
         self._consumed[self._staged].record(cur)
         self.graph.replay()
+        self._after_step()
         return self.static_loss
 
     def __call__(self, img: torch.Tensor, lab: torch.Tensor) -> torch.Tensor:
@@ -601,6 +612,7 @@ class GraphedTrainStep:
         self.static_img.copy_(img, non_blocking=True)
         self.static_lab.copy_(lab, non_blocking=True)
         self.graph.replay()
+        self._after_step()
         return self.static_loss
 
 

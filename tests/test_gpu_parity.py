@@ -732,6 +732,43 @@ def test_bias_gelu_outliers(dtype):
     assert (h.grad.float().cpu() - h64.grad.float()).abs().max() <= (2e-2 if dtype == torch.bfloat16 else 1e-4)
 
 
+def test_evaluation_after_graphed_steps_sees_the_updated_weights():
+    """A forward outside GraphedTrainStep (evaluation) after replayed steps must use the UPDATED master weights: a replay
+    runs no Python and the one-pass optimizer writes through raw pointers, so the bf16 weight shadows are marked stale
+    after every step and refreshed at their next use."""
+    from hierarchical_vision_b200 import train as T
+
+    torch.manual_seed(0)
+    backbone = hv.SwinTransformerV2(img_size=64, patch_size=4, num_classes=10, embed_dim=32, depths=[2, 2], num_heads=[1, 2],
+                                    window_size=8, drop_path_rate=0.0)
+    with torch.no_grad():
+        for layer in backbone.layers:
+            for blk in layer.blocks:
+                for n in (blk.norm1, blk.norm2):
+                    n.weight.normal_(1.0, 0.1)
+    model = T.Model(backbone).to(DEV)
+    env = T.DistEnv(0, 0, 1)
+    img = torch.randn(4, 3, 64, 64, device=DEV)
+    lab = torch.randint(0, 10, (4,), device=DEV)
+    opt = T.build_optimizer(model, lr=0.5)
+    gs = T.GraphedTrainStep(model, opt, env, (img, lab), autocast_dtype=torch.bfloat16, clip_norm=None)
+    gs.capture()
+    for _ in range(3):
+        gs(img, lab)
+    torch.cuda.synchronize()
+    model.eval()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        got = model.module(img).float()
+    # the same weights in a fresh module (fresh shadows)
+    fresh = hv.SwinTransformerV2(img_size=64, patch_size=4, num_classes=10, embed_dim=32, depths=[2, 2], num_heads=[1, 2],
+                                 window_size=8, drop_path_rate=0.0).to(DEV)
+    fresh.load_state_dict(model.module.state_dict())
+    fresh.eval()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        want = fresh(img).float()
+    assert torch.equal(got, want)
+
+
 @pytest.mark.parametrize("clip", [None, 0.37])
 def test_fused_sgdw_step_is_bit_identical_to_the_multi_tensor_path(clip):
     """hv_sgdw_step (one pass over p, buf, g with the clip coefficient applied on the fly) against FlatSGD.step after an
