@@ -74,8 +74,8 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.hv_abi_version() != 3:
-        raise RuntimeError(f"libhv_swin.so ABI version {lib.hv_abi_version()} != 3")
+    if lib.hv_abi_version() != 4:
+        raise RuntimeError(f"libhv_swin.so ABI version {lib.hv_abi_version()} != 4")
     _lib = lib
     return lib
 

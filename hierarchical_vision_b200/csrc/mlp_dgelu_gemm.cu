@@ -21,8 +21,6 @@
 //     sums live in one register per epilogue thread for the whole kernel; a second tiny kernel folds the per-warp rows
 //     into db1;
 //   * the epilogue of tile i overlaps the MMAs of tile i + 1 (two accumulators).
-#include <atomic>
-
 #include "hv_tc_win.cuh"
 
 namespace hv {
@@ -89,8 +87,8 @@ __device__ __forceinline__ float2 dgelu2(float2 x) {
 
 template <int kStages, int kHBufs>
 __global__ void __launch_bounds__(kThreads, 1)
-mlp_dgelu_gemm_kernel(const __grid_constant__ GemmMaps maps, const bf16* __restrict__ h, const float* __restrict__ b1,
-                      bf16* __restrict__ dh, float* __restrict__ partials, int M, int N, int K) {
+mlp_dgelu_gemm_kernel(const __grid_constant__ GemmMaps maps, const float* __restrict__ b1, float* __restrict__ partials, int M,
+                      int N, int K) {
   extern __shared__ __align__(1024) unsigned char smem[];
   using L = Layout<kStages, kHBufs>;
   constexpr int kOffH = L::kOffH, kOffBar = L::kOffBar, kOffTmem = L::kOffTmem;
@@ -561,11 +559,11 @@ int mlp_dgelu_gemm(const void* dy, const void* w2, const void* h, const float* b
   const int grid = per_col * n_tiles;
   float* partials = static_cast<float*>(workspace);
   if (K <= 192)
-    mlp_dgelu_gemm_kernel<HV_GEMM_SK_STAGES, HV_GEMM_SK_HBUFS><<<grid, kThreads, Layout<HV_GEMM_SK_STAGES, HV_GEMM_SK_HBUFS>::kSmem, st>>>(*mp, static_cast<const bf16*>(h), b1,
-                                                                            static_cast<bf16*>(dh), partials, (int)M, N, K);
+    mlp_dgelu_gemm_kernel<HV_GEMM_SK_STAGES, HV_GEMM_SK_HBUFS>
+        <<<grid, kThreads, Layout<HV_GEMM_SK_STAGES, HV_GEMM_SK_HBUFS>::kSmem, st>>>(*mp, b1, partials, (int)M, N, K);
   else
-    mlp_dgelu_gemm_kernel<HV_GEMM_LK_STAGES, HV_GEMM_LK_HBUFS><<<grid, kThreads, Layout<HV_GEMM_LK_STAGES, HV_GEMM_LK_HBUFS>::kSmem, st>>>(*mp, static_cast<const bf16*>(h), b1,
-                                                                            static_cast<bf16*>(dh), partials, (int)M, N, K);
+    mlp_dgelu_gemm_kernel<HV_GEMM_LK_STAGES, HV_GEMM_LK_HBUFS>
+        <<<grid, kThreads, Layout<HV_GEMM_LK_STAGES, HV_GEMM_LK_HBUFS>::kSmem, st>>>(*mp, b1, partials, (int)M, N, K);
   HV_LAUNCH_OK("mlp_dgelu_gemm_kernel");
   mlp_dgelu_fold_kernel<<<(N + 255) / 256, 256, 0, st>>>(partials, db1, N, n_tiles, grid);
   HV_LAUNCH_OK("mlp_dgelu_fold_kernel");

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define HV_ABI_VERSION 3
+#define HV_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define HV_API __attribute__((visibility("default")))

@@ -39,7 +39,7 @@ def test_every_declared_symbol_is_exported(lib):
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.hv_abi_version() == 3
+    assert lib.hv_abi_version() == 4
     assert lib.hv_compiled_arch() == 100
 
 
