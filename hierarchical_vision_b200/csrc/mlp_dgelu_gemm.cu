@@ -53,16 +53,21 @@ constexpr int kThreads = 640;                // 20 warps: 0 TMA | 1 MMA | 2 TMA 
 constexpr int kMaxN = 4096;
 
 constexpr int kHTile = kBM * kBN * 2;        // 32 KB: two sub-tiles of 128 rows x 128 B (SWIZZLE_128B); h in, dh out (in place)
+#ifndef HV_GEMM_ACC_BUFS
+#define HV_GEMM_ACC_BUFS 2
+#endif
+constexpr int kAcc = HV_GEMM_ACC_BUFS;     // 128-column accumulators in tensor memory
+constexpr int kTmemCols = 128 * kAcc;
 constexpr int kOffStage = 0;
 template <int kStages, int kHBufs> struct Layout {
   static constexpr int kOffH = kStages * kStage;  // [kHBufs] h / dh tiles
   static constexpr int kOffBar = kOffH + kHBufs * kHTile;
-  static constexpr int kNumBars = 2 * kStages + 4 + 3 * kHBufs;
+  static constexpr int kNumBars = 2 * kStages + 2 * kAcc + 3 * kHBufs;
   static constexpr int kOffTmem = kOffBar + kNumBars * 8;
   static constexpr int kSmem = kOffTmem + 16;
   static_assert(kSmem <= 227 * 1024, "shared memory budget");
 };
-constexpr int kTmemCols = 256;
+
 
 struct GemmMaps { CUtensorMap a, b, h, dh; };  // dY, W2, h (loads), dh (stores)
 
@@ -98,10 +103,10 @@ mlp_dgelu_gemm_kernel(const __grid_constant__ GemmMaps maps, const float* __rest
   auto bar_full = [&](int s) { return bar0 + 8 * s; };
   auto bar_empty = [&](int s) { return bar0 + 8 * (kStages + s); };
   auto bar_acc = [&](int b) { return bar0 + 8 * (2 * kStages + b); };          // accumulator b complete
-  auto bar_accfree = [&](int b) { return bar0 + 8 * (2 * kStages + 2 + b); };  // ... and pulled out of TMEM
-  auto bar_hfull = [&](int b) { return bar0 + 8 * (2 * kStages + 4 + b); };                  // h tile b landed
-  auto bar_hwritten = [&](int b) { return bar0 + 8 * (2 * kStages + 4 + kHBufs + b); };      // dh written over it by the 16 epilogue warps
-  auto bar_hfree = [&](int b) { return bar0 + 8 * (2 * kStages + 4 + 2 * kHBufs + b); };     // ... and read by the TMA store
+  auto bar_accfree = [&](int b) { return bar0 + 8 * (2 * kStages + kAcc + b); };  // ... and pulled out of TMEM
+  auto bar_hfull = [&](int b) { return bar0 + 8 * (2 * kStages + 2 * kAcc + b); };           // h tile b landed
+  auto bar_hwritten = [&](int b) { return bar0 + 8 * (2 * kStages + 2 * kAcc + kHBufs + b); };  // dh written over it by the 16 epilogue warps
+  auto bar_hfree = [&](int b) { return bar0 + 8 * (2 * kStages + 2 * kAcc + 2 * kHBufs + b); };  // ... and read by the TMA store
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmem);
 
   // CTA c: column block c % n_tiles, token blocks c / n_tiles, + gridDim.x / n_tiles, ... (gridDim.x is a multiple of n_tiles)
@@ -116,7 +121,7 @@ mlp_dgelu_gemm_kernel(const __grid_constant__ GemmMaps maps, const float* __rest
       mbar_init(bar_full(s), 1);
       mbar_init(bar_empty(s), 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < kAcc; ++b) {
       mbar_init(bar_acc(b), 1);
       mbar_init(bar_accfree(b), 16);
     }
@@ -178,8 +183,8 @@ mlp_dgelu_gemm_kernel(const __grid_constant__ GemmMaps maps, const float* __rest
     const uint64_t d_b = smem_desc(sb + kOffStage + kStageA, 16, 1024, 2);
     int it = 0;
     for (int i = 0; i < my_tiles; ++i) {
-      const int buf = i & 1;
-      if (i > 1) mbar_wait_fast(bar_accfree(buf), ((i >> 1) - 1) & 1);
+      const int buf = i % kAcc;
+      if (i >= kAcc) mbar_wait_fast(bar_accfree(buf), ((i / kAcc) - 1) & 1);
       tc_fence_after();
       for (int kb = 0; kb < kblocks; ++kb, ++it) {
         const int s = it % kStages;
@@ -228,7 +233,7 @@ mlp_dgelu_gemm_kernel(const __grid_constant__ GemmMaps maps, const float* __rest
     for (int q = 0; q < 16; ++q) bias[q] = make_float2(__ldg(b1 + nc + 2 * q), __ldg(b1 + nc + 2 * q + 1));
     float csum = 0.f;  // column nc + lane, over this warp's rows of every tile
     for (int i = 0; i < my_tiles; ++i) {
-      const int buf = i & 1;
+      const int buf = i % kAcc;
       // this thread's row of the h tile: 128-byte rows (64 columns) per sub-tile, 16-byte chunk c at position c ^ (row & 7)
       const int r = 32 * quad + lane;
       const int hb = i % kHBufs;
@@ -238,7 +243,7 @@ mlp_dgelu_gemm_kernel(const __grid_constant__ GemmMaps maps, const float* __rest
       uint4 hv[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) hv[q] = lds128(hrow + (((cbase + q) ^ swz) << 4));
-      mbar_wait_fast(bar_acc(buf), (i >> 1) & 1);
+      mbar_wait_fast(bar_acc(buf), (i / kAcc) & 1);
       tc_fence_after();
       uint32_t acc[32];
       HV_TMEM_LD32(tl + 128 * buf, acc);
@@ -336,7 +341,7 @@ constexpr int kOTile = 2 * kHTile;  // h tile + a tile of one 128 x 128 output t
 template <int kStages, int kOBufs> struct FwdLayout {
   static constexpr int kOffO = kStages * kStage;
   static constexpr int kOffBar = kOffO + kOBufs * kOTile;
-  static constexpr int kNumBars = 2 * kStages + 4 + 2 * kOBufs;
+  static constexpr int kNumBars = 2 * kStages + 2 * kAcc + 2 * kOBufs;
   static constexpr int kOffTmem = kOffBar + kNumBars * 8;
   static constexpr int kSmem = kOffTmem + 16;
   static_assert(kSmem <= 227 * 1024, "shared memory budget");
@@ -354,9 +359,9 @@ mlp_fc1_gelu_gemm_kernel(const __grid_constant__ FwdGemmMaps maps, const float* 
   auto bar_full = [&](int s) { return bar0 + 8 * s; };
   auto bar_empty = [&](int s) { return bar0 + 8 * (kStages + s); };
   auto bar_acc = [&](int b) { return bar0 + 8 * (2 * kStages + b); };
-  auto bar_accfree = [&](int b) { return bar0 + 8 * (2 * kStages + 2 + b); };
-  auto bar_owritten = [&](int b) { return bar0 + 8 * (2 * kStages + 4 + b); };        // both output tiles written
-  auto bar_ofree = [&](int b) { return bar0 + 8 * (2 * kStages + 4 + kOBufs + b); };  // ... and read by the TMA stores
+  auto bar_accfree = [&](int b) { return bar0 + 8 * (2 * kStages + kAcc + b); };
+  auto bar_owritten = [&](int b) { return bar0 + 8 * (2 * kStages + 2 * kAcc + b); };        // both output tiles written
+  auto bar_ofree = [&](int b) { return bar0 + 8 * (2 * kStages + 2 * kAcc + kOBufs + b); };  // ... and read by the TMA stores
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffTmem);
 
   const int n_tiles = N / kBN, m_tiles = M / kBM;
@@ -370,7 +375,7 @@ mlp_fc1_gelu_gemm_kernel(const __grid_constant__ FwdGemmMaps maps, const float* 
       mbar_init(bar_full(s), 1);
       mbar_init(bar_empty(s), 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < kAcc; ++b) {
       mbar_init(bar_acc(b), 1);
       mbar_init(bar_accfree(b), 16);
     }
@@ -415,8 +420,8 @@ mlp_fc1_gelu_gemm_kernel(const __grid_constant__ FwdGemmMaps maps, const float* 
     const uint64_t d_b = smem_desc(sb + kOffStage + kStageA, 16, 1024, 2);
     int it = 0;
     for (int i = 0; i < my_tiles; ++i) {
-      const int buf = i & 1;
-      if (i > 1) mbar_wait_fast(bar_accfree(buf), ((i >> 1) - 1) & 1);
+      const int buf = i % kAcc;
+      if (i >= kAcc) mbar_wait_fast(bar_accfree(buf), ((i / kAcc) - 1) & 1);
       tc_fence_after();
       for (int kb = 0; kb < kblocks; ++kb, ++it) {
         const int s = it % kStages;
@@ -465,9 +470,9 @@ mlp_fc1_gelu_gemm_kernel(const __grid_constant__ FwdGemmMaps maps, const float* 
     const int r = 32 * quad + lane;
     const uint32_t cbase = (uint32_t)(4 * (cq & 1)), swz = (uint32_t)(r & 7);
     for (int i = 0; i < my_tiles; ++i) {
-      const int buf = i & 1, ob = i % kOBufs;
+      const int buf = i % kAcc, ob = i % kOBufs;
       const uint32_t hrow = sb + kOffO + ob * kOTile + (cq >> 1) * (kHTile / 2) + r * 128;  // the a tile follows at + kHTile
-      mbar_wait_fast(bar_acc(buf), (i >> 1) & 1);
+      mbar_wait_fast(bar_acc(buf), (i / kAcc) & 1);
       tc_fence_after();
       uint32_t acc[32];
       HV_TMEM_LD32(tl + 128 * buf, acc);
