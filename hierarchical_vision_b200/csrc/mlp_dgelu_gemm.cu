@@ -49,7 +49,7 @@ constexpr int kBM = 128, kBN = 128, kBK = 64;
 constexpr int kStageA = kBM * kBK * 2;       // 16 KB
 constexpr int kStageB = kBK * kBN * 2;       // 16 KB: two sub-tiles of 64 k-rows x 128 B
 constexpr int kStage = kStageA + kStageB;
-constexpr int kThreads = 640;                // 20 warps: 0 TMA | 1 MMA | 2 TMA stores | 3 idle | 4-19 epilogue
+constexpr int kThreads = 640;                // 20 warps: 0 TMA operands | 1 MMA | 2 TMA stores | 3 TMA h tiles (backward) | 4-19 epilogue
 constexpr int kMaxN = 4096;
 
 constexpr int kHTile = kBM * kBN * 2;        // 32 KB: two sub-tiles of 128 rows x 128 B (SWIZZLE_128B); h in, dh out (in place)
@@ -146,19 +146,6 @@ mlp_dgelu_gemm_kernel(const __grid_constant__ GemmMaps maps, const float* __rest
     int it = 0;
     for (int i = 0; i < my_tiles; ++i) {
       const int m0 = (m_first + i * m_stride) * kBM;
-      {  // the tile of pre-activations the epilogue needs (two boxes of 64 columns), into the buffer tile i - 2 has left
-        const int hb = i % kHBufs;
-        if (i >= kHBufs) mbar_wait_fast(bar_hfree(hb), ((i / kHBufs) - 1) & 1);
-        if (elect_one()) {
-          mbar_expect_tx(bar_hfull(hb), kHTile);
-#pragma unroll
-          for (int sub = 0; sub < 2; ++sub)
-            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                         ::"r"(sb + kOffH + hb * kHTile + sub * (kHTile / 2)), "l"(reinterpret_cast<uint64_t>(&maps.h)),
-                           "r"(bar_hfull(hb)), "r"(n0 + 64 * sub), "r"(m0) : "memory");
-        }
-        __syncwarp();
-      }
       for (int kb = 0; kb < kblocks; ++kb, ++it) {
         const int s = it % kStages;
         mbar_wait_fast(bar_empty(s), ((it / kStages) & 1) ^ 1);
@@ -203,6 +190,23 @@ mlp_dgelu_gemm_kernel(const __grid_constant__ GemmMaps maps, const float* __rest
         }
         __syncwarp();
       }
+    }
+  } else if (warp == 3) {
+    // ---------------------------------------------------------------- TMA producer of the h tiles (its own warp: the operand
+    // producer blocks on the stage ring, this one on the h / dh buffers; in one warp each delayed the other)
+    for (int i = 0; i < my_tiles; ++i) {
+      const int m0 = (m_first + i * m_stride) * kBM;
+      const int hb = i % kHBufs;
+      if (i >= kHBufs) mbar_wait_fast(bar_hfree(hb), ((i / kHBufs) - 1) & 1);
+      if (elect_one()) {
+        mbar_expect_tx(bar_hfull(hb), kHTile);
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub)
+          asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                       ::"r"(sb + kOffH + hb * kHTile + sub * (kHTile / 2)), "l"(reinterpret_cast<uint64_t>(&maps.h)),
+                         "r"(bar_hfull(hb)), "r"(n0 + 64 * sub), "r"(m0) : "memory");
+      }
+      __syncwarp();
     }
   } else if (warp == 2) {
     // ---------------------------------------------------------------- TMA stores of the dh tiles
