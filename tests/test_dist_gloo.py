@@ -116,6 +116,29 @@ def _two_models():
     return a, b
 
 
+def test_fused_optimizer_tables_need_cuda_gradient_views_and_shadows_can_be_marked_stale():
+    """Host logic around the one-pass optimizer kernel: FlatSGD.prepare_fused declines (multi-tensor path stays) for CPU tensors
+    and for the nesterov-SGD flavour; mark_weight_shadows_stale makes every registered shadow refresh at its next use."""
+    from hierarchical_vision_b200 import functional as hvf
+
+    a, _ = _two_models()
+    ps = [p for p in a.parameters()]
+    flat = torch.zeros(sum(p.numel() for p in ps))
+    off = 0
+    for p in ps:
+        p.grad = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+    assert T.FlatSGD(ps, lr=0.1).prepare_fused(flat) is False                    # CPU tensors
+    assert T.FlatSGD(ps, lr=0.1, decoupled=False).prepare_fused(flat) is False   # torch-SGD flavour
+    w = torch.nn.Parameter(torch.randn(4, 3))
+    sh = hvf.weight_shadow(w, torch.bfloat16)
+    assert torch.equal(sh, w.detach().to(torch.bfloat16))
+    w.data.mul_(2.0)  # a write that does not move the version counter (what a raw-pointer kernel or a graph replay does)
+    assert torch.equal(hvf.weight_shadow(w, torch.bfloat16), sh)                  # stale: the version did not move
+    hvf.mark_weight_shadows_stale()
+    assert torch.equal(hvf.weight_shadow(w, torch.bfloat16), w.detach().to(torch.bfloat16))
+
+
 def test_flat_sgd_matches_torch_nesterov_and_decoupled_rule():
     """reference optim.py:16-23 ("sgd": torch SGD with nesterov) and optim.py:37-44 (DecoupledSGDW), with the learning
     rate changed mid-run through the device-side lr (what a scheduler does, also under a CUDA graph)."""
