@@ -31,6 +31,7 @@ SIGNATURES = {
     "hv_relative_position_index": (_I, [_I, _P]),
     "hv_shift_window_mask": (_I, [_I, _I, _I, _I, _P]),
     "hv_window_token_index": (_I, [_I, _I, _I, _I, _I, _P]),
+    "hv_window16_tile_token_index": (_I, [_I, _I, _I, _I, _P]),
     "hv_merge_token_index": (_I, [_I, _I, _I, _P]),
     "hv_window_attn_fwd": (_I, [_P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "hv_window_attn_bwd_workspace_bytes": (_S, [_I, _I, _I, _I, _I, _I, _I]),

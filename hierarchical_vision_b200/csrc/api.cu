@@ -25,6 +25,7 @@ int mlp_dgelu_gemm(const void* dy, const void* w2, const void* h, const float* b
                    size_t workspace_bytes, int64_t M, int N, int K, cudaStream_t st);
 int mlp_fc1_gelu_gemm(const void* x, const void* w1, const float* b1, void* h, void* act, int64_t M, int N, int K, cudaStream_t st);
 bool wattn_tc256_supported(const Geom& g, int dtype);
+void window16_tile_token_index(const Geom& g, int64_t* out);
 int wattn_tc256_variant_set(int v);
 int wattn_tc256_fwd(const Geom& g, const void* qkv, const float* bias_table, const float* tau, void* out, float* stats,
                     cudaStream_t st);
@@ -228,6 +229,16 @@ int hv_window_token_index(int B, int H, int W, int ws, int shift, int64_t* out) 
   for (int b = 0; b < B; ++b)
     for (int win = 0; win < g.nW; ++win)
       for (int s = 0; s < g.N; ++s) out[((size_t)b * g.nW + win) * g.N + s] = window_slot_to_token(g, b, win, s);
+  return HV_OK;
+}
+
+int hv_window16_tile_token_index(int B, int H, int W, int shift, int64_t* out) {
+  if (!out) HV_FAIL(HV_ERR_NULL, "hv_window16_tile_token_index: out is NULL");
+  Geom g;
+  int rc = make_checked_geom(B, H, W, 32, 1, 16, shift, g);
+  if (rc) return rc;
+  if (shift != 0 && shift != 8) HV_FAIL(HV_ERR_SHAPE, "hv_window16_tile_token_index: shift %d (the N = 256 kernels take 0 or 8)", shift);
+  window16_tile_token_index(g, out);
   return HV_OK;
 }
 

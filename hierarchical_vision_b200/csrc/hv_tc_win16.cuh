@@ -78,7 +78,7 @@ struct Work16 {
   }
 };
 
-__device__ __forceinline__ UnitGeo16 unit_geo16(const Geom& g, int widx) {
+HV_HD UnitGeo16 unit_geo16(const Geom& g, int widx) {
   const int b = widx / g.nW, win = widx - b * g.nW;
   const int wh = win / g.nWw, ww = win - wh * g.nWw;
   UnitGeo16 ug;
@@ -108,7 +108,7 @@ __device__ __forceinline__ void for_each_box16(const Geom& g, const UnitGeo16& u
 }
 
 // image (row, col) of tile row t of a window -- for the plain-load helper kernels
-__device__ __forceinline__ void tile_row_rc16(const Geom& g, const UnitGeo16& ug, int t, int& row, int& col) {
+HV_HD void tile_row_rc16(const Geom& g, const UnitGeo16& ug, int t, int& row, int& col) {
   const int part = t >> 7, ih = (t & 127) >> 3, iw = 8 * part + (t & 7);
   row = ug.row0 + ih;
   col = ug.col0 + iw;

@@ -472,4 +472,18 @@ int wattn_tc256_fwd(const Geom& g, const void* qkv, const float* bias_table, con
   return HV_OK;
 }
 
+// Host: image token feeding tile row t of window `win` of image b in the TILE order of the N = 256 kernels -- the same
+// unit_geo16 / tile_row_rc16 arithmetic the kernels' TMA coordinates come from (for bit-exact checks against the reference's
+// torch.roll + window_partition, swinv2.py:399-412)
+void window16_tile_token_index(const Geom& g, int64_t* out) {
+  for (int widx = 0; widx < g.B * g.nW; ++widx) {
+    const tc::UnitGeo16 ug = tc::unit_geo16(g, widx);
+    for (int t = 0; t < tc::kN16; ++t) {
+      int row, col;
+      tc::tile_row_rc16(g, ug, t, row, col);
+      out[(size_t)widx * tc::kN16 + t] = ((int64_t)ug.b * g.H + row) * g.W + col;
+    }
+  }
+}
+
 }  // namespace hv

@@ -95,6 +95,12 @@ HV_API int hv_shift_window_mask(int H, int W, int ws, int shift, float* out);
  * -- reference swinv2.py:69-83, 399-412; also the scatter map of window_reverse + roll(+shift)
  * (swinv2.py:86-102, 420-429) */
 HV_API int hv_window_token_index(int B, int H, int W, int ws, int shift, int64_t* out);
+/* Host-only: image token index (b * H * W + row * W + col) feeding tile row t of window `win` of image b in the TILE order
+ * of the 16 x 16-window kernels (two column parts of 8 x 16 tokens: t = 128 part + 8 ih + iw % 8), out[(b * nW + win) * 256 + t]:
+ * the same arithmetic the kernels' TMA box coordinates come from, for bit-exact checks against torch.roll +
+ * window_partition (reference swinv2.py:69-83, 399-412).  shift 0 or 8. */
+HV_API int hv_window16_tile_token_index(int B, int H, int W, int shift, int64_t* out);
+
 /* PatchMerging concat sources (B*H/2*W/2, 4) int64 -- reference swinv2.py:486-490 */
 HV_API int hv_merge_token_index(int B, int H, int W, int64_t* out);
 

@@ -79,6 +79,22 @@ def test_host_window_token_index_bit_exact(lib):
         assert _sha(out) == rec["sha256"], key
 
 
+@pytest.mark.parametrize("geom", [(2, 32, 48, 0), (2, 32, 48, 8), (1, 16, 16, 8), (3, 16, 64, 8), (1, 64, 16, 0)])
+def test_window16_tile_order_is_the_reference_roll_and_partition(lib, geom):
+    """The tile order of the N = 256 kernels (two column parts of 8 x 16 tokens per window) is a fixed permutation of the
+    window slots; composed with it, the kernels' token map equals torch.roll(-shift) + window_partition of the reference
+    (swinv2.py:69-83, 399-412) bit for bit -- including the windows that wrap along the rows, the columns, or both."""
+    B, H, W, shift = geom
+    nW = (H // 16) * (W // 16)
+    out = np.empty((B, nW, 256), dtype=np.int64)
+    assert lib.hv_window16_tile_token_index(B, H, W, shift, out.ctypes.data_as(ctypes.c_void_p)) == 0
+    ref = O.window_token_index(B, H, W, 16, shift).reshape(B, nW, 256)   # slot order: ih * 16 + iw
+    t = np.arange(256)
+    slot = ((t & 127) >> 3) * 16 + 8 * (t >> 7) + (t & 7)
+    assert np.array_equal(out, ref[:, :, slot])
+    assert lib.hv_window16_tile_token_index(B, H, W, 4, out.ctypes.data_as(ctypes.c_void_p)) != 0
+
+
 def test_host_merge_token_index(lib):
     out = np.empty((2 * 3 * 4, 4), dtype=np.int64)
     assert lib.hv_merge_token_index(2, 6, 8, out.ctypes.data_as(ctypes.c_void_p)) == 0
