@@ -350,6 +350,8 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
     const float* bt = reinterpret_cast<const float*>(smem + kOffBias);
     const uint32_t p_row = sb + kOffP + t * 128, w_row = sb + kOffW + t * 128;
     const uint32_t swz = (uint32_t)(t & 7);
+    // bias run of key (jl, jw8) for query block 0 / key block 0; the other blocks are offsets of whole rows and of 8 columns
+    const float* bp0 = bias_run16(bt, (ih + 15) * kBiasStride16 + (15 - iw8));
     float2 a1_acc = make_float2(0.f, 0.f), a2_acc = a1_acc, dp_acc = a1_acc;
     float li = 0.f, ri = 0.f, Di = 0.f;
 
@@ -365,7 +367,7 @@ wattn_tc256_bwd_kernel(const __grid_constant__ BwdMaps maps, const float* __rest
       }
       const int flags = geo[u & 3].flags;
       const float* cv = vec + 512 + 64 * b + 16 * qt;
-      const float* bp = bias_run16(bt, (ih - 8 * (b & 1) + 15) * kBiasStride16 + (15 - 8 * a - iw8 + 8 * (b >> 1)));
+      const float* bp = bp0 + ((b >> 1) - a) * 8 - (b & 1) * (8 * kBiasStride16);  // a multiple of 8: same alignment copy
       const bool masked = ((flags & 1) && ((ih >= 8) != ((b & 1) != 0))) || ((flags & 2) && (a != (b >> 1)));
       const float lim = masked ? li - kNeg : li;  // the whole 64-key block is on the other side of a wrap, or none of it
       const float2 ri2 = make_float2(ri, ri), nlim2 = make_float2(-lim, -lim), nDi2 = make_float2(-Di, -Di);

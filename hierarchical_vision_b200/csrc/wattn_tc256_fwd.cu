@@ -273,6 +273,8 @@ wattn_tc256_fwd_kernel(const __grid_constant__ FwdMaps maps, const float* __rest
     const float kNeg = kMaskValue * kLog2e;
     const float* bt = reinterpret_cast<const float*>(smem + kOffBias);
     float* hmx = reinterpret_cast<float*>(smem + kOffHmx);
+    // bias run of key (jl, jw8) of this thread's key block for query block 0
+    const float* bp0 = bias_run16(bt, (ih - 8 * (qt & 1) + 15) * kBiasStride16 + (15 - iw8 + 8 * (qt >> 1)));
 
     for (int n = 0; n < nitems; ++n) {
       const int u = n >> 1, a = n & 1, s = u % kStages, buf = n & 1;
@@ -282,7 +284,7 @@ wattn_tc256_fwd_kernel(const __grid_constant__ FwdMaps maps, const float* __rest
       const float ri = vec[128 * a + t];
       const float* cv = vec + 256 + 64 * qt;
       // bias of key (jl, jw8) of the block: run of 8 floats at bp - 40 jl (16-byte aligned through the alignment copies)
-      const float* bp = bias_run16(bt, (ih - 8 * (qt & 1) + 15) * kBiasStride16 + (15 - 8 * a - iw8 + 8 * (qt >> 1)));
+      const float* bp = bp0 - 8 * a;  // a multiple of 8: same alignment copy
       // shift mask: the whole quarter row sits on the other side of a wrap than the query, or none of it (warp-uniform)
       const bool masked = ((flags & 1) && ((ih >= 8) != ((qt & 1) != 0))) || ((flags & 2) && (a != (qt >> 1)));
       const float madd = masked ? kNeg : 0.f;
