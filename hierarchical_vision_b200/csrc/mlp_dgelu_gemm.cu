@@ -484,25 +484,27 @@ mlp_fc1_gelu_gemm_kernel(const __grid_constant__ FwdGemmMaps maps, const float* 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_accfree(buf));
+      // all of the arithmetic first (in place: acc[0..15] become the packed h pairs, acc[16..31] the packed activations), THEN the
+      // wait for the staging buffer: with one buffer (large K) the math of tile i overlaps the TMA stores of tile i - 1
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const uint32_t hp = pack_bf16x2(__uint_as_float(acc[2 * e]), __uint_as_float(acc[2 * e + 1]));
+        // the activation is computed from the ROUNDED h, the value the backward kernels will read
+        const float2 x = __fadd2_rn(make_float2(bf16lo_to_f32(hp), bf16hi_to_f32(hp)), bias[e]);
+#ifdef HV_GEMM_KO_MATH
+        const float2 g = x;
+#else
+        const float2 g = gelu2(x);
+#endif
+        acc[2 * e] = hp;
+        acc[2 * e + 1] = pack_bf16x2(g.x, g.y);
+      }
       if (i >= kOBufs) mbar_wait_fast(bar_ofree(ob), ((i / kOBufs) - 1) & 1);  // the stores of tile i - kOBufs have read the buffer
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        uint32_t ho[4], ao[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          ho[e] = pack_bf16x2(__uint_as_float(acc[8 * q + 2 * e]), __uint_as_float(acc[8 * q + 2 * e + 1]));
-          // the activation is computed from the ROUNDED h, the value the backward kernels will read
-          const float2 x = __fadd2_rn(make_float2(bf16lo_to_f32(ho[e]), bf16hi_to_f32(ho[e])), bias[4 * q + e]);
-#ifdef HV_GEMM_KO_MATH
-          const float2 g = x;
-#else
-          const float2 g = gelu2(x);
-#endif
-          ao[e] = pack_bf16x2(g.x, g.y);
-        }
         const uint32_t off = ((cbase + q) ^ swz) << 4;
-        sts128(hrow + off, make_uint4(ho[0], ho[1], ho[2], ho[3]));
-        sts128(hrow + kHTile + off, make_uint4(ao[0], ao[1], ao[2], ao[3]));
+        sts128(hrow + off, make_uint4(acc[8 * q], acc[8 * q + 2], acc[8 * q + 4], acc[8 * q + 6]));
+        sts128(hrow + kHTile + off, make_uint4(acc[8 * q + 1], acc[8 * q + 3], acc[8 * q + 5], acc[8 * q + 7]));
       }
       fence_async_smem();
       __syncwarp();
